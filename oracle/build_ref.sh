@@ -1,0 +1,40 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE: compiles the UNMODIFIED reference sources for the visibility path where they lie under
+# $REF (default /root/reference) into oracle/_ref/libu3dref.so, together with oracle/ref_harness.cpp.
+# Nothing is written into the reference tree; no reference source is copied into this repo.
+# Recipe = SURVEY.md 8(c).  Canonical float mode: -ffp-contract=off (no FMA contraction), -O3 -msse3.
+set -e
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${REF:-/root/reference}"
+OUT="$HERE/_ref"
+SRC="$REF/Source/Urho3D"
+TP="$REF/Source/ThirdParty"
+JOBS="${JOBS:-$(nproc)}"
+if [ ! -d "$SRC" ]; then echo "reference not present at $REF: keeping prebuilt $OUT (if any)"; exit 0; fi
+mkdir -p "$OUT/obj" "$OUT/inc" "$OUT/inc2/Urho3D"
+# include roots: <Urho3D/...> -> reference sources; <SDL/...>, <PugiXml/...>, <LZ4/...> etc. -> ThirdParty
+ln -sfn "$SRC" "$OUT/inc/Urho3D"
+ln -sfn "$TP/SDL/include" "$OUT/inc/SDL"
+ln -sfn "$TP/PugiXml/src" "$OUT/inc/PugiXml"
+CXXFLAGS="-std=c++11 -O3 -DNDEBUG -msse3 -ffp-contract=off -fPIC -w -DGLEW_NO_GLU -DGLEW_STATIC -DURHO3D_STATIC_DEFINE -DURHO3D_THREADING -DURHO3D_LOGGING -DURHO3D_OPENGL -DURHO3D_SSE \
+ -I$HERE/ref_stub -I$HERE/ref_stub/Urho3D -I$HERE/ref_stub/sdlcfg -I$OUT/inc -I$SRC -I$REF/Source -I$TP -I$TP/SDL/include -I$TP/rapidjson/include -I$TP/WebP/src"
+FILES=""
+for d in Container Math Core IO Resource Scene; do FILES="$FILES $(ls $SRC/$d/*.cpp)"; done
+for f in OcclusionBuffer Octree OctreeQuery Camera Drawable GraphicsDefs; do FILES="$FILES $SRC/Graphics/$f.cpp"; done
+FILES="$FILES $TP/PugiXml/src/pugixml.cpp $HERE/ref_harness.cpp $HERE/ref_stubs.cpp"
+MK="$OUT/obj/build.mk"
+: > "$MK"
+OBJS=""
+for f in $FILES; do
+  o="$OUT/obj/$(echo "$f" | sed -e "s#$REF/##" -e "s#$HERE/##" -e 's#[/.]#_#g').o"
+  OBJS="$OBJS $o"
+  printf '%s: %s\n\tg++ %s -c %s -o %s\n' "$o" "$f" "$CXXFLAGS" "$f" "$o" >> "$MK"
+done
+for f in lz4 lz4hc; do
+  o="$OUT/obj/tp_$f.o"; OBJS="$OBJS $o"
+  printf '%s: %s\n\tgcc -O2 -fPIC -w -c %s -o %s\n' "$o" "$TP/LZ4/$f.c" "$TP/LZ4/$f.c" "$o" >> "$MK"
+done
+printf 'all:%s\n' "$OBJS" >> "$MK"
+make -s -j"$JOBS" -f "$MK" all
+g++ -shared -o "$OUT/libu3dref.so" $OBJS -lpthread -ldl -Wl,-z,defs 2> "$OUT/link.log" || { sort -u "$OUT/link.log" | grep -o "undefined reference to .*" | sort -u | head -80; exit 1; }
+echo "built $OUT/libu3dref.so"

@@ -1,0 +1,488 @@
+// TEST INFRASTRUCTURE ONLY (oracle/): a C-ABI harness that drives the UNMODIFIED reference
+// classes compiled straight out of /root/reference (see oracle/build_ref.sh).  Nothing in the
+// product path may load the library this file builds into (oracle/_ref/libu3dref.so).
+//
+// It exposes, for ctypes:
+//   * the reference Octree (Octree.cpp:134-190 insertion, :229-255 DFS query) over drawables whose
+//     world AABBs are supplied directly (a test Drawable subclass),
+//   * the reference Camera (Camera.cpp:284-308 frustum, :585-595 view, :648-691 projection),
+//   * the reference OcclusionBuffer (OcclusionBuffer.h:101-158),
+//   * a verbatim-behaviour restatement of the ~45-line OccludedFrustumOctreeQuery /
+//     ShadowCasterOctreeQuery classes, which are private to View.cpp:59-158 and so cannot be linked,
+//   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
+//     View.cpp:897-920 does when worker threads exist.
+//
+// The private-member peeking (#define protected public) is needed only to dump the octant tree.
+
+#include <cstdint>
+#include <cstring>
+#include <chrono>
+#include <vector>
+
+#define protected public
+#define private public
+#include <Urho3D/Graphics/Octree.h>
+#include <Urho3D/Graphics/OcclusionBuffer.h>
+#undef protected
+#undef private
+
+#include <Urho3D/Core/Context.h>
+#include <Urho3D/Core/WorkQueue.h>
+#include <Urho3D/Graphics/Camera.h>
+#include <Urho3D/Graphics/Drawable.h>
+#include <Urho3D/Graphics/OctreeQuery.h>
+#include <Urho3D/Scene/Node.h>
+#include <Urho3D/Scene/Scene.h>
+
+using namespace Urho3D;
+
+namespace
+{
+
+/// Drawable whose world AABB is handed in by the test, and whose DrawOcclusion does what
+/// StaticModel::DrawOcclusion does (StaticModel.cpp:189-228): SetCullMode + indexed AddTriangles.
+class TestDrawable : public Drawable
+{
+    URHO3D_OBJECT(TestDrawable, Drawable);
+
+public:
+    explicit TestDrawable(Context* context) : Drawable(context, DRAWABLE_GEOMETRY) {}
+
+    void Setup(const BoundingBox& worldBox, unsigned char flags, unsigned viewMask, bool occludee, bool castShadows, int id)
+    {
+        fixedWorldBox_ = worldBox;
+        drawableFlags_ = flags;
+        viewMask_ = viewMask;
+        occludee_ = occludee;
+        castShadows_ = castShadows;
+        id_ = id;
+        worldBoundingBoxDirty_ = true;
+    }
+
+    void OnWorldBoundingBoxUpdate() override { worldBoundingBox_ = fixedWorldBox_; }
+
+    BoundingBox fixedWorldBox_;
+    int id_{};
+};
+
+/// Behavioural restatement of View.cpp:116-158 (class is file-local there).
+class OccludedQuery : public FrustumOctreeQuery
+{
+public:
+    OccludedQuery(PODVector<Drawable*>& result, const Frustum& frustum, OcclusionBuffer* buffer, unsigned char flags, unsigned mask) :
+        FrustumOctreeQuery(result, frustum, flags, mask), buffer_(buffer) {}
+
+    Intersection TestOctant(const BoundingBox& box, bool inside) override
+    {
+        if (inside)
+            return buffer_->IsVisible(box) ? INSIDE : OUTSIDE;
+        Intersection result = frustum_.IsInside(box);
+        if (result != OUTSIDE && !buffer_->IsVisible(box))
+            result = OUTSIDE;
+        return result;
+    }
+
+    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
+    {
+        while (start != end)
+        {
+            Drawable* drawable = *start++;
+            if ((drawable->GetDrawableFlags() & drawableFlags_) && (drawable->GetViewMask() & viewMask_))
+            {
+                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
+                    result_.Push(drawable);
+            }
+        }
+    }
+
+    OcclusionBuffer* buffer_;
+};
+
+/// Behavioural restatement of View.cpp:59-84.
+class ShadowCasterQuery : public FrustumOctreeQuery
+{
+public:
+    ShadowCasterQuery(PODVector<Drawable*>& result, const Frustum& frustum, unsigned char flags, unsigned mask) :
+        FrustumOctreeQuery(result, frustum, flags, mask) {}
+
+    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
+    {
+        while (start != end)
+        {
+            Drawable* drawable = *start++;
+            if (drawable->GetCastShadows() && (drawable->GetDrawableFlags() & drawableFlags_) && (drawable->GetViewMask() & viewMask_))
+            {
+                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
+                    result_.Push(drawable);
+            }
+        }
+    }
+};
+
+struct Ref
+{
+    SharedPtr<Context> context_;
+    SharedPtr<Scene> scene_;
+    Octree* octree_{};
+    SharedPtr<Node> cameraNode_;
+    Camera* camera_{};
+    SharedPtr<OcclusionBuffer> buffer_;
+    std::vector<TestDrawable*> drawables_;
+    PODVector<Drawable*> result_;
+    std::vector<unsigned char> visFlags_;
+};
+
+struct VisWork
+{
+    OcclusionBuffer* buffer_;
+    unsigned char* flagsBase_;
+    Drawable** base_;
+};
+
+/// The occlusion predicate of CheckVisibilityWork (View.cpp:177) over a slice.
+void CheckVisWork(const WorkItem* item, unsigned)
+{
+    auto* w = reinterpret_cast<VisWork*>(item->aux_);
+    auto** start = reinterpret_cast<Drawable**>(item->start_);
+    auto** end = reinterpret_cast<Drawable**>(item->end_);
+    while (start != end)
+    {
+        Drawable* drawable = *start;
+        bool vis = !w->buffer_ || !drawable->IsOccludee() || w->buffer_->IsVisible(drawable->GetWorldBoundingBox());
+        w->flagsBase_[start - w->base_] = vis ? 1 : 0;
+        ++start;
+    }
+}
+
+double Now()
+{
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void FlattenRec(const Octant* o, int parent, std::vector<int>& parents, std::vector<int>& levels, std::vector<float>& boxes,
+    std::vector<int>& firsts, std::vector<int>& counts, std::vector<int>& order)
+{
+    int me = (int)parents.size();
+    parents.push_back(parent);
+    levels.push_back((int)o->level_);
+    const BoundingBox& b = o->cullingBox_;
+    boxes.push_back(b.min_.x_); boxes.push_back(b.min_.y_); boxes.push_back(b.min_.z_);
+    boxes.push_back(b.max_.x_); boxes.push_back(b.max_.y_); boxes.push_back(b.max_.z_);
+    firsts.push_back((int)order.size());
+    counts.push_back((int)o->drawables_.Size());
+    for (unsigned i = 0; i < o->drawables_.Size(); ++i)
+        order.push_back(static_cast<TestDrawable*>(o->drawables_[i])->id_);
+    for (unsigned i = 0; i < NUM_OCTANTS; ++i)
+        if (o->children_[i])
+            FlattenRec(o->children_[i], me, parents, levels, boxes, firsts, counts, order);
+}
+
+}
+
+extern "C"
+{
+
+void* ref_create(int numWorkerThreads)
+{
+    auto* r = new Ref();
+    r->context_ = new Context();
+    Context* c = r->context_;
+    auto* queue = new WorkQueue(c);
+    c->RegisterSubsystem(queue);
+    if (numWorkerThreads > 0)
+        queue->CreateThreads((unsigned)numWorkerThreads);
+    RegisterSceneLibrary(c);
+    Octree::RegisterObject(c);
+    Camera::RegisterObject(c);
+    c->RegisterFactory<TestDrawable>();
+    r->scene_ = new Scene(c);
+    r->octree_ = r->scene_->CreateComponent<Octree>();
+    r->cameraNode_ = new Node(c);
+    r->camera_ = r->cameraNode_->CreateComponent<Camera>();
+    r->buffer_ = new OcclusionBuffer(c);
+    return r;
+}
+
+void ref_destroy(void* h)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    r->buffer_.Reset();
+    r->cameraNode_.Reset();
+    r->scene_.Reset();
+    r->context_.Reset();
+    delete r;
+}
+
+int ref_num_threads(void* h)
+{
+    return (int)reinterpret_cast<Ref*>(h)->context_->GetSubsystem<WorkQueue>()->GetNumThreads();
+}
+
+void ref_octree_set_size(void* h, const float* mn, const float* mx, unsigned levels)
+{
+    reinterpret_cast<Ref*>(h)->octree_->SetSize(BoundingBox(Vector3(mn), Vector3(mx)), levels);
+}
+
+/// Create n drawables (in order) and insert each once, from the root, with its final world box.
+void ref_add_drawables(void* h, int n, const float* aabb6, const unsigned char* flags, const unsigned* viewMask,
+    const unsigned char* occludee, const unsigned char* castShadows)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Context* c = r->context_;
+    for (int i = 0; i < n; ++i)
+    {
+        Node* node = r->scene_->CreateChild(String::EMPTY, LOCAL);
+        auto* d = new TestDrawable(c);
+        const float* b = aabb6 + 6 * (size_t)i;
+        d->Setup(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5])), flags ? flags[i] : (unsigned char)DRAWABLE_GEOMETRY,
+            viewMask ? viewMask[i] : DEFAULT_VIEWMASK, occludee ? occludee[i] != 0 : true, castShadows ? castShadows[i] != 0 : false,
+            (int)r->drawables_.size());
+        r->drawables_.push_back(d);
+        node->AddComponent(d, 0, LOCAL); // -> OnSceneSet -> AddToOctree -> Octree::InsertDrawable (Drawable.cpp:366-405)
+    }
+}
+
+int ref_num_drawables(void* h) { return (int)reinterpret_cast<Ref*>(h)->drawables_.size(); }
+
+int ref_octree_num_octants(void* h)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    std::vector<int> p, l, f, cnt, o; std::vector<float> b;
+    FlattenRec(r->octree_, -1, p, l, b, f, cnt, o);
+    return (int)p.size();
+}
+
+/// DFS pre-order dump (the order Octant::GetDrawablesInternal visits, Octree.cpp:229-255).
+void ref_octree_flatten(void* h, int* parent, int* level, float* cullingBox6, int* first, int* count, int* order)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    std::vector<int> p, l, f, cnt, o; std::vector<float> b;
+    FlattenRec(r->octree_, -1, p, l, b, f, cnt, o);
+    memcpy(parent, p.data(), p.size() * sizeof(int));
+    memcpy(level, l.data(), l.size() * sizeof(int));
+    memcpy(cullingBox6, b.data(), b.size() * sizeof(float));
+    memcpy(first, f.data(), f.size() * sizeof(int));
+    memcpy(count, cnt.data(), cnt.size() * sizeof(int));
+    memcpy(order, o.data(), o.size() * sizeof(int));
+}
+
+/// Camera set-up.  rot = quaternion (w,x,y,z).
+void ref_camera_set(void* h, const float* pos, const float* rot, float fov, float aspect, float nearClip, float farClip,
+    int ortho, float orthoSize, float zoom, int flipVertical)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    r->cameraNode_->SetTransform(Vector3(pos), Quaternion(rot[0], rot[1], rot[2], rot[3]));
+    Camera* cam = r->camera_;
+    cam->SetOrthographic(ortho != 0);
+    cam->SetFov(fov);
+    cam->SetNearClip(nearClip);
+    cam->SetFarClip(farClip);
+    if (ortho)
+        cam->SetOrthoSize(orthoSize);
+    cam->SetAspectRatio(aspect);
+    cam->SetZoom(zoom);
+    cam->SetFlipVertical(flipVertical != 0);
+}
+
+/// view (3x4 row-major), projection (4x4 row-major, as Camera::GetProjection incl. flip), 6 planes (nx,ny,nz,d),
+/// absNormals (6x3), near/far (Camera::GetNearClip/GetFarClip), reverseCulling.
+void ref_camera_get(void* h, float* view12, float* proj16, float* planes24, float* absNormals18, float* nearFar2, int* reverseCulling)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Camera* cam = r->camera_;
+    memcpy(view12, cam->GetView().Data(), 12 * sizeof(float));
+    Matrix4 p = cam->GetProjection();
+    memcpy(proj16, p.Data(), 16 * sizeof(float));
+    const Frustum& f = cam->GetFrustum();
+    for (unsigned i = 0; i < NUM_FRUSTUM_PLANES; ++i)
+    {
+        planes24[i * 4 + 0] = f.planes_[i].normal_.x_;
+        planes24[i * 4 + 1] = f.planes_[i].normal_.y_;
+        planes24[i * 4 + 2] = f.planes_[i].normal_.z_;
+        planes24[i * 4 + 3] = f.planes_[i].d_;
+        absNormals18[i * 3 + 0] = f.planes_[i].absNormal_.x_;
+        absNormals18[i * 3 + 1] = f.planes_[i].absNormal_.y_;
+        absNormals18[i * 3 + 2] = f.planes_[i].absNormal_.z_;
+    }
+    nearFar2[0] = cam->GetNearClip();
+    nearFar2[1] = cam->GetFarClip();
+    *reverseCulling = cam->GetReverseCulling() ? 1 : 0;
+}
+
+int ref_ob_set_size(void* h, int w, int ht, int threaded)
+{
+    return reinterpret_cast<Ref*>(h)->buffer_->SetSize(w, ht, threaded != 0) ? 1 : 0;
+}
+int ref_ob_width(void* h) { return reinterpret_cast<Ref*>(h)->buffer_->GetWidth(); }
+int ref_ob_height(void* h) { return reinterpret_cast<Ref*>(h)->buffer_->GetHeight(); }
+void ref_ob_set_view(void* h) { auto* r = reinterpret_cast<Ref*>(h); r->buffer_->SetView(r->camera_); }
+void ref_ob_set_max_triangles(void* h, unsigned n) { reinterpret_cast<Ref*>(h)->buffer_->SetMaxTriangles(n); }
+void ref_ob_set_cull_mode(void* h, int mode) { reinterpret_cast<Ref*>(h)->buffer_->SetCullMode((CullMode)mode); }
+int ref_ob_get_cull_mode(void* h) { return (int)reinterpret_cast<Ref*>(h)->buffer_->GetCullMode(); }
+void ref_ob_clear(void* h) { reinterpret_cast<Ref*>(h)->buffer_->Clear(); }
+void ref_ob_reset(void* h) { reinterpret_cast<Ref*>(h)->buffer_->Reset(); }
+
+int ref_ob_add_triangles(void* h, const float* model12, const void* vtx, unsigned vtxSize, const void* idx, unsigned idxSize,
+    unsigned start, unsigned count)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Matrix3x4 model(model12);
+    bool ok = idx ? r->buffer_->AddTriangles(model, vtx, vtxSize, idx, idxSize, start, count)
+                  : r->buffer_->AddTriangles(model, vtx, vtxSize, start, count);
+    return ok ? 1 : 0;
+}
+
+void ref_ob_draw(void* h) { reinterpret_cast<Ref*>(h)->buffer_->DrawTriangles(); }
+void ref_ob_build_hierarchy(void* h) { reinterpret_cast<Ref*>(h)->buffer_->BuildDepthHierarchy(); }
+unsigned ref_ob_num_triangles(void* h) { return reinterpret_cast<Ref*>(h)->buffer_->GetNumTriangles(); }
+
+int ref_ob_is_visible(void* h, const float* b)
+{
+    return reinterpret_cast<Ref*>(h)->buffer_->IsVisible(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]))) ? 1 : 0;
+}
+
+void ref_ob_is_visible_many(void* h, int n, const float* aabb6, unsigned char* out)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    for (int i = 0; i < n; ++i)
+    {
+        const float* b = aabb6 + 6 * (size_t)i;
+        out[i] = r->buffer_->IsVisible(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]))) ? 1 : 0;
+    }
+}
+
+void ref_ob_read_depth(void* h, int* out)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    memcpy(out, r->buffer_->GetBuffer(), sizeof(int) * (size_t)r->buffer_->GetWidth() * r->buffer_->GetHeight());
+}
+
+int ref_ob_num_mips(void* h) { return (int)reinterpret_cast<Ref*>(h)->buffer_->mipBuffers_.Size(); }
+
+/// Level `level` as interleaved (min,max) ints; dims follow OcclusionBuffer.cpp:97-106.
+void ref_ob_read_mip(void* h, int level, int* out)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    int w = r->buffer_->GetWidth(), ht = r->buffer_->GetHeight();
+    for (int i = 0; i <= level; ++i) { w = (w + 1) / 2; ht = (ht + 1) / 2; }
+    memcpy(out, r->buffer_->mipBuffers_[level].Get(), sizeof(DepthValue) * (size_t)w * ht);
+}
+
+/// Octree::GetDrawables with a frustum query built from the current camera.
+/// mode 0 = FrustumOctreeQuery, 1 = OccludedFrustumOctreeQuery (current buffer), 2 = ShadowCasterOctreeQuery.
+int ref_query(void* h, int mode, unsigned flags, unsigned viewMask, int* outIdx, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    const Frustum& fr = r->camera_->GetFrustum();
+    if (mode == 1)
+    {
+        OccludedQuery q(r->result_, fr, r->buffer_, (unsigned char)flags, viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    else if (mode == 2)
+    {
+        ShadowCasterQuery q(r->result_, fr, (unsigned char)flags, viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    else
+    {
+        FrustumOctreeQuery q(r->result_, fr, (unsigned char)flags, viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    int n = (int)r->result_.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+        outIdx[i] = static_cast<TestDrawable*>(r->result_[i])->id_;
+    return n;
+}
+
+/// CheckVisibilityWork's occlusion predicate over the last ref_query() result, work split as View.cpp:897-920.
+/// Output keeps query order (set-equal to what the reference's per-thread lists hold).
+int ref_check_visibility(void* h, int useBuffer, int* outIdx, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    auto* queue = r->context_->GetSubsystem<WorkQueue>();
+    unsigned n = r->result_.Size();
+    r->visFlags_.assign(n, 0);
+    if (!n)
+        return 0;
+    VisWork w{useBuffer ? r->buffer_.Get() : nullptr, r->visFlags_.data(), &r->result_[0]};
+
+    int numWorkItems = (int)queue->GetNumThreads() + 1;
+    int drawablesPerItem = (int)n / numWorkItems;
+    Drawable** start = &r->result_[0];
+    Drawable** endAll = start + n;
+    for (int i = 0; i < numWorkItems; ++i)
+    {
+        SharedPtr<WorkItem> item = queue->GetFreeItem();
+        item->priority_ = M_MAX_UNSIGNED;
+        item->workFunction_ = CheckVisWork;
+        item->aux_ = &w;
+        Drawable** end = endAll;
+        if (i < numWorkItems - 1 && end - start > drawablesPerItem)
+            end = start + drawablesPerItem;
+        item->start_ = start;
+        item->end_ = end;
+        queue->AddWorkItem(item);
+        start = end;
+    }
+    queue->Complete(M_MAX_UNSIGNED);
+
+    int m = 0;
+    for (unsigned i = 0; i < n; ++i)
+        if (r->visFlags_[i])
+        {
+            if (m < cap)
+                outIdx[m] = static_cast<TestDrawable*>(r->result_[i])->id_;
+            ++m;
+        }
+    return m;
+}
+
+/// One whole view, the way View::GetDrawables runs it with threaded occlusion (View.cpp:2258-2273, :873-878, :885-921):
+/// select occluders by frustum.IsInsideFast(worldBox) in scene order, Clear, AddTriangles each,
+/// DrawTriangles, BuildDepthHierarchy, occluded query, visibility predicate.  Camera must be set already.
+/// times4 (seconds): raster(incl. select+submit), hierarchy, query, visibility.  Returns visible count.
+int ref_run_view(void* h, int numOccluders, const float* occAabb6, const float* occModel12, const void* vtx, unsigned vtxSize,
+    const void* idx, unsigned idxSize, unsigned idxCount, int cullMode, unsigned flags, unsigned viewMask, int* outVisible, int cap,
+    int* outCounts3 /* submittedTris, candidates, visible */, double* times4)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    OcclusionBuffer* ob = r->buffer_;
+    double t0 = Now();
+    ob->SetView(r->camera_);
+    ob->SetMaxTriangles(1u << 30);
+    ob->Clear();
+    const Frustum& fr = r->camera_->GetFrustum();
+    unsigned submitted = 0;
+    for (int i = 0; i < numOccluders; ++i)
+    {
+        const float* b = occAabb6 + 6 * (size_t)i;
+        if (fr.IsInsideFast(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]))) == OUTSIDE)
+            continue;
+        ob->SetCullMode((CullMode)cullMode);
+        ob->AddTriangles(Matrix3x4(occModel12 + 12 * (size_t)i), vtx, vtxSize, idx, idxSize, 0, idxCount);
+        submitted += idxCount / 3;
+    }
+    ob->DrawTriangles();
+    double t1 = Now();
+    ob->BuildDepthHierarchy();
+    double t2 = Now();
+    OccludedQuery q(r->result_, fr, ob, (unsigned char)flags, viewMask);
+    r->octree_->GetDrawables(q);
+    double t3 = Now();
+    int nvis = ref_check_visibility(h, 1, outVisible, cap);
+    double t4 = Now();
+    if (outCounts3)
+    {
+        outCounts3[0] = (int)submitted;
+        outCounts3[1] = (int)r->result_.Size();
+        outCounts3[2] = nvis;
+    }
+    if (times4)
+    {
+        times4[0] = t1 - t0; times4[1] = t2 - t1; times4[2] = t3 - t2; times4[3] = t4 - t3;
+    }
+    return nvis;
+}
+
+}
