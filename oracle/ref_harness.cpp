@@ -130,6 +130,10 @@ struct Ref
     std::vector<TestDrawable*> drawables_;
     PODVector<Drawable*> result_;
     std::vector<unsigned char> visFlags_;
+    /// When set (ref_set_frustum_raw), queries use this frustum instead of the camera's.
+    bool rawFrustum_{};
+    Frustum frustum_;
+    const Frustum& QueryFrustum() const { return rawFrustum_ ? frustum_ : camera_->GetFrustum(); }
 };
 
 struct VisWork
@@ -309,6 +313,44 @@ void ref_camera_get(void* h, float* view12, float* proj16, float* planes24, floa
     *reverseCulling = cam->GetReverseCulling() ? 1 : 0;
 }
 
+/// Inject the frustum planes directly (normal xyz + d per plane, order NEAR,LEFT,RIGHT,UP,DOWN,FAR; Frustum.h:37-45).
+/// Plane::Define(Vector4) (Plane.h:83-88) derives absNormal_ exactly as the reference does.  planes24 == NULL -> camera frustum again.
+void ref_set_frustum_raw(void* h, const float* planes24)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    r->rawFrustum_ = planes24 != nullptr;
+    if (planes24)
+        for (unsigned i = 0; i < NUM_FRUSTUM_PLANES; ++i)
+            r->frustum_.planes_[i].Define(Vector4(planes24[i * 4], planes24[i * 4 + 1], planes24[i * 4 + 2], planes24[i * 4 + 3]));
+}
+
+/// Inject view/projection directly: exactly the assignments of OcclusionBuffer::SetView (OcclusionBuffer.cpp:115-127)
+/// with the Camera getters replaced by caller-supplied values, so the same bytes can be fed to every implementation.
+void ref_ob_set_view_raw(void* h, const float* view12, const float* proj16, float nearClip, float farClip, int reverseCulling)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    OcclusionBuffer* ob = r->buffer_;
+    ob->view_ = Matrix3x4(view12);
+    ob->projection_ = Matrix4(proj16);
+    ob->viewProj_ = ob->projection_ * ob->view_;
+    ob->nearClip_ = nearClip;
+    ob->farClip_ = farClip;
+    ob->reverseCulling_ = reverseCulling != 0;
+    ob->CalculateViewport();
+}
+
+void ref_ob_get_viewproj(void* h, float* out16)
+{
+    memcpy(out16, reinterpret_cast<Ref*>(h)->buffer_->viewProj_.Data(), 16 * sizeof(float));
+}
+
+int ref_frustum_is_inside(void* h, const float* b, int fast)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    BoundingBox box(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]));
+    return (int)(fast ? r->QueryFrustum().IsInsideFast(box) : r->QueryFrustum().IsInside(box));
+}
+
 int ref_ob_set_size(void* h, int w, int ht, int threaded)
 {
     return reinterpret_cast<Ref*>(h)->buffer_->SetSize(w, ht, threaded != 0) ? 1 : 0;
@@ -373,7 +415,7 @@ void ref_ob_read_mip(void* h, int level, int* out)
 int ref_query(void* h, int mode, unsigned flags, unsigned viewMask, int* outIdx, int cap)
 {
     auto* r = reinterpret_cast<Ref*>(h);
-    const Frustum& fr = r->camera_->GetFrustum();
+    const Frustum& fr = r->QueryFrustum();
     if (mode == 1)
     {
         OccludedQuery q(r->result_, fr, r->buffer_, (unsigned char)flags, viewMask);
@@ -449,10 +491,11 @@ int ref_run_view(void* h, int numOccluders, const float* occAabb6, const float* 
     auto* r = reinterpret_cast<Ref*>(h);
     OcclusionBuffer* ob = r->buffer_;
     double t0 = Now();
-    ob->SetView(r->camera_);
+    if (!r->rawFrustum_)
+        ob->SetView(r->camera_); // raw mode: caller already injected the view with ref_ob_set_view_raw
     ob->SetMaxTriangles(1u << 30);
     ob->Clear();
-    const Frustum& fr = r->camera_->GetFrustum();
+    const Frustum& fr = r->QueryFrustum();
     unsigned submitted = 0;
     for (int i = 0; i < numOccluders; ++i)
     {

@@ -1,0 +1,689 @@
+/* TEST INFRASTRUCTURE ONLY -- CPU restatement (plain C, scalar, one thread) of the reference's per-frame visibility
+ * path.  It is the checker for the CUDA path; nothing in urho3d_b200/ may link, load or call it.
+ *
+ * PARITY PINNING: the reference ships no golden vectors for this path.  This restatement is
+ * pinned differentially against the UNMODIFIED reference sources compiled into oracle/_ref/libu3dref.so
+ * (oracle/build_ref.sh) by tests/test_oracle_vs_reference.py, and against tests/golden/ fixtures generated from that
+ * library by tests/golden/make_golden.py.
+ *
+ * Float mode: compile with -ffp-contract=off (no FMA contraction), no -ffast-math: SURVEY.md hard part 1.
+ * "OB.cpp" = Source/Urho3D/Graphics/OcclusionBuffer.cpp of the reference.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define Z_SCALE 16777216.0f    /* OCCLUSION_Z_SCALE, OcclusionBuffer.h:86 */
+#define X_SCALE 65536.0f       /* OCCLUSION_X_SCALE, OcclusionBuffer.h:85 */
+#define MIN_MIP 8              /* OCCLUSION_MIN_SIZE, OcclusionBuffer.h:83 */
+#define FIXED_BIAS 16          /* OCCLUSION_FIXED_BIAS, OcclusionBuffer.h:87 */
+#define REL_BIAS 0.00001f      /* OCCLUSION_RELATIVE_BIAS, OcclusionBuffer.h:88 */
+#define MAX_LEVELS 32
+
+enum { CULL_NONE = 0, CULL_CCW = 1, CULL_CW = 2 };
+enum { OUTSIDE = 0, INTERSECTS = 1, INSIDE = 2 }; /* MathDefs.h Intersection */
+
+typedef struct { float x, y, z, w; } V4;
+typedef struct { float x, y, z; } V3;
+
+typedef struct OrcOB
+{
+    int w, h;
+    int nlev;
+    int* base;                 /* w*(h+2)+2 ints, OB.cpp:89 */
+    int* depth;                /* base + w + 1, OB.cpp:90 */
+    int* mip[MAX_LEVELS];      /* interleaved (min,max) */
+    int mw[MAX_LEVELS], mh[MAX_LEVELS];
+    float vp[16];              /* viewProj_ row-major */
+    float sx, sy, ox, oy;
+    int cull, reverse;
+    unsigned num_tris, max_tris;
+    int dirty;
+} OrcOB;
+
+/* x86 cvttss2si/cvttsd2si semantics made explicit: out-of-range and NaN give INT_MIN (SURVEY hard part 2). */
+static int cvtt(double v)
+{
+    if (!(v >= -2147483648.0 && v < 2147483648.0))
+        return INT32_MIN;
+    return (int)v;
+}
+static int trunc_f(float v) { return cvtt((double)v); }
+static int round_to_int(float v) { return cvtt(round((double)v)); } /* MathDefs.h:238 */
+static int wrap_add(int a, int b) { return (int)((uint32_t)a + (uint32_t)b); }
+
+OrcOB* orc_ob_create(void)
+{
+    OrcOB* ob = (OrcOB*)calloc(1, sizeof(OrcOB));
+    ob->cull = CULL_CCW;
+    ob->max_tris = 5000; /* OCCLUSION_DEFAULT_MAX_TRIANGLES, OcclusionBuffer.h:84 */
+    ob->dirty = 1;
+    return ob;
+}
+
+static void free_buffers(OrcOB* ob)
+{
+    free(ob->base);
+    ob->base = NULL;
+    for (int i = 0; i < ob->nlev; ++i)
+        free(ob->mip[i]);
+    ob->nlev = 0;
+}
+
+void orc_ob_destroy(OrcOB* ob)
+{
+    free_buffers(ob);
+    free(ob);
+}
+
+static void calc_viewport(OrcOB* ob) /* OB.cpp:578-587 */
+{
+    ob->sx = 0.5f * ob->w;
+    ob->sy = -0.5f * ob->h;
+    ob->ox = 0.5f * ob->w + 0.5f;
+    ob->oy = 0.5f * ob->h + 0.5f;
+}
+
+/* OB.cpp:61-113.  Returns 1 on success like the reference's bool. */
+int orc_ob_set_size(OrcOB* ob, int w, int h)
+{
+    if (h & 1)
+        ++h;
+    if (w == ob->w && h == ob->h)
+        return 1;
+    if (w <= 0 || h <= 0)
+        return 0;
+    if (w & (w - 1))
+        return 0;
+    free_buffers(ob);
+    ob->w = w;
+    ob->h = h;
+    ob->base = (int*)malloc(sizeof(int) * ((size_t)w * (h + 2) + 2));
+    ob->depth = ob->base + w + 1;
+    for (;;)
+    {
+        w = (w + 1) / 2;
+        h = (h + 1) / 2;
+        ob->mw[ob->nlev] = w;
+        ob->mh[ob->nlev] = h;
+        ob->mip[ob->nlev] = (int*)malloc(sizeof(int) * 2 * (size_t)w * h);
+        ++ob->nlev;
+        if (w <= MIN_MIP && h <= MIN_MIP)
+            break;
+    }
+    calc_viewport(ob);
+    return 1;
+}
+
+int orc_ob_width(const OrcOB* ob) { return ob->w; }
+int orc_ob_height(const OrcOB* ob) { return ob->h; }
+int orc_ob_num_levels(const OrcOB* ob) { return ob->nlev; }
+unsigned orc_ob_num_triangles(const OrcOB* ob) { return ob->num_tris; }
+int orc_ob_cull_mode(const OrcOB* ob) { return ob->cull; }
+
+/* Matrix4 * Matrix3x4, Matrix4.cpp:43-63 (a = 4x4 row-major, b = 3x4 row-major). */
+static void mul44_34(const float* a, const float* b, float* o)
+{
+    for (int r = 0; r < 4; ++r)
+    {
+        const float* ar = a + 4 * r;
+        for (int c = 0; c < 3; ++c)
+            o[4 * r + c] = ar[0] * b[c] + ar[1] * b[4 + c] + ar[2] * b[8 + c];
+        o[4 * r + 3] = ar[0] * b[3] + ar[1] * b[7] + ar[2] * b[11] + ar[3];
+    }
+}
+
+/* OB.cpp:115-127 with the Camera getters replaced by their values. */
+void orc_ob_set_view(OrcOB* ob, const float* view12, const float* proj16, int reverse_culling)
+{
+    mul44_34(proj16, view12, ob->vp);
+    ob->reverse = reverse_culling != 0;
+    calc_viewport(ob);
+}
+
+void orc_ob_get_viewproj(const OrcOB* ob, float* out16) { memcpy(out16, ob->vp, sizeof(ob->vp)); }
+void orc_ob_set_max_triangles(OrcOB* ob, unsigned n) { ob->max_tris = n; }
+
+void orc_ob_set_cull_mode(OrcOB* ob, int mode) /* OB.cpp:134-144 */
+{
+    if (ob->reverse)
+    {
+        if (mode == CULL_CW)
+            mode = CULL_CCW;
+        else if (mode == CULL_CCW)
+            mode = CULL_CW;
+    }
+    ob->cull = mode;
+}
+
+void orc_ob_reset(OrcOB* ob) { ob->num_tris = 0; }
+
+void orc_ob_clear(OrcOB* ob) /* OB.cpp:152-162, 1028-1039 */
+{
+    ob->num_tris = 0;
+    if (ob->base)
+    {
+        int fill = (int)Z_SCALE;
+        size_t n = (size_t)ob->w * ob->h;
+        for (size_t i = 0; i < n; ++i)
+            ob->depth[i] = fill;
+    }
+    ob->dirty = 1;
+}
+
+static V4 xform(const float* m, const float* p) /* ModelTransform, OB.cpp:543-551 */
+{
+    V4 r;
+    r.x = m[0] * p[0] + m[1] * p[1] + m[2] * p[2] + m[3];
+    r.y = m[4] * p[0] + m[5] * p[1] + m[6] * p[2] + m[7];
+    r.z = m[8] * p[0] + m[9] * p[1] + m[10] * p[2] + m[11];
+    r.w = m[12] * p[0] + m[13] * p[1] + m[14] * p[2] + m[15];
+    return r;
+}
+
+static V3 to_screen(const OrcOB* ob, V4 v) /* ViewportTransform, OB.cpp:553-561 */
+{
+    float inv_w = 1.0f / v.w;
+    V3 r;
+    r.x = inv_w * v.x * ob->sx + ob->ox;
+    r.y = inv_w * v.y * ob->sy + ob->oy;
+    r.z = inv_w * v.z * Z_SCALE;
+    return r;
+}
+
+static V4 clip_lerp(V4 a, V4 b, float da, float db) /* ClipEdge, OB.cpp:563-567 */
+{
+    float t = da / (da - db);
+    V4 r;
+    r.x = a.x + t * (b.x - a.x);
+    r.y = a.y + t * (b.y - a.y);
+    r.z = a.z + t * (b.z - a.z);
+    r.w = a.w + t * (b.w - a.w);
+    return r;
+}
+
+/* Store an int into the depth plane by linear offset from data_.  The reference writes through a raw pointer into
+ * an allocation padded by one row + 1 int each side (OB.cpp:87-90); anything beyond that is undefined behaviour there.
+ * Writes outside [0, w*h) never reach the visible plane, so they are dropped here. */
+static void depth_min(OrcOB* ob, int64_t off, int z)
+{
+    if (off < 0 || off >= (int64_t)ob->w * ob->h)
+        return;
+    if (z < ob->depth[off])
+        ob->depth[off] = z;
+}
+
+typedef struct { int x, xstep, z, zstep; } EdgeI;
+
+/* Edge constructor, OB.cpp:792-803 */
+static EdgeI make_edge(float dzdx, float dzdy, V3 top, V3 bot, int top_y)
+{
+    EdgeI e;
+    float height = bot.y - top.y;
+    float slope = (height != 0.0f) ? (bot.x - top.x) / height : 0.0f;
+    float ypre = (float)(top_y + 1) - top.y;
+    float xpre = slope * ypre;
+    e.x = round_to_int((xpre + top.x) * X_SCALE);
+    e.xstep = round_to_int(slope * X_SCALE);
+    e.z = round_to_int(top.z + xpre * dzdx + ypre * dzdy);
+    e.zstep = round_to_int(slope * dzdx + dzdy);
+    return e;
+}
+
+/* One half of the triangle: rows [y0, y1), span from `left` to `right`, depth walks along `left`. OB.cpp:897-1001 */
+static void fill_half(OrcOB* ob, int y0, int y1, EdgeI* left, EdgeI* right, int dzdx_i)
+{
+    /* Rows whose linear span could touch [0,w*h): |x>>16| <= 32768, so rows far outside can be skipped without
+     * changing the visible plane; the edges are still stepped for them. */
+    int64_t guard = 32768 / ob->w + 2;
+    for (int64_t y = y0; y < y1; ++y)
+    {
+        if (y >= -guard && y <= (int64_t)ob->h + guard)
+        {
+            int z = left->z;
+            int64_t xs = left->x >> 16;
+            int64_t xe = right->x >> 16;
+            int64_t row = y * ob->w;
+            for (int64_t x = xs; x < xe; ++x)
+            {
+                depth_min(ob, row + x, z);
+                z = wrap_add(z, dzdx_i);
+            }
+        }
+        left->x = wrap_add(left->x, left->xstep);
+        left->z = wrap_add(left->z, left->zstep);
+        right->x = wrap_add(right->x, right->xstep);
+    }
+}
+
+/* DrawTriangle2D, OB.cpp:815-1002 */
+static void raster_tri(OrcOB* ob, const V3* v, int clockwise)
+{
+    int top, mid, bot, mid_right;
+    if (v[0].y < v[1].y)
+    {
+        if (v[2].y < v[0].y) { top = 2; mid = 0; bot = 1; mid_right = 1; }
+        else
+        {
+            top = 0;
+            if (v[1].y < v[2].y) { mid = 1; bot = 2; mid_right = 1; }
+            else { mid = 2; bot = 1; mid_right = 0; }
+        }
+    }
+    else
+    {
+        if (v[2].y < v[1].y) { top = 2; mid = 1; bot = 0; mid_right = 0; }
+        else
+        {
+            top = 1;
+            if (v[0].y < v[2].y) { mid = 0; bot = 2; mid_right = 0; }
+            else { mid = 2; bot = 0; mid_right = 1; }
+        }
+    }
+    int ty = trunc_f(v[top].y), my = trunc_f(v[mid].y), by = trunc_f(v[bot].y);
+    if (ty == by)
+        return;
+    if (!clockwise)
+        mid_right = !mid_right;
+
+    /* Gradients, OB.cpp:762-778 */
+    float inv_dx = 1.0f / (((v[1].x - v[2].x) * (v[0].y - v[2].y)) - ((v[0].x - v[2].x) * (v[1].y - v[2].y)));
+    float inv_dy = -inv_dx;
+    float dzdx = inv_dx * (((v[1].z - v[2].z) * (v[0].y - v[2].y)) - ((v[0].z - v[2].z) * (v[1].y - v[2].y)));
+    float dzdy = inv_dy * (((v[1].z - v[2].z) * (v[0].x - v[2].x)) - ((v[0].z - v[2].z) * (v[1].x - v[2].x)));
+    int dzdx_i = trunc_f(dzdx);
+
+    EdgeI lng = make_edge(dzdx, dzdy, v[top], v[bot], ty);
+    if (ty != my)
+    {
+        EdgeI e = make_edge(dzdx, dzdy, v[top], v[mid], ty);
+        if (mid_right)
+            fill_half(ob, ty, my, &lng, &e, dzdx_i);
+        else
+            fill_half(ob, ty, my, &e, &lng, dzdx_i);
+    }
+    if (my != by)
+    {
+        EdgeI e = make_edge(dzdx, dzdy, v[mid], v[bot], my);
+        if (mid_right)
+            fill_half(ob, my, by, &lng, &e, dzdx_i);
+        else
+            fill_half(ob, my, by, &e, &lng, dzdx_i);
+    }
+}
+
+static int project_and_fill(OrcOB* ob, const V4* c)
+{
+    V3 p[3];
+    p[0] = to_screen(ob, c[0]);
+    p[1] = to_screen(ob, c[1]);
+    p[2] = to_screen(ob, c[2]);
+    /* SignedArea, OB.cpp:569-576 */
+    float ax = p[0].x - p[1].x, ay = p[0].y - p[1].y, bx = p[2].x - p[1].x, by = p[2].y - p[1].y;
+    int clockwise = (ax * by - ay * bx) < 0.0f;
+    if (ob->cull == CULL_NONE || (ob->cull == CULL_CCW && clockwise) || (ob->cull == CULL_CW && !clockwise))
+    {
+        raster_tri(ob, p, clockwise);
+        return 1;
+    }
+    return 0;
+}
+
+static float plane_dot(const float* pl, V4 v) { return pl[0] * v.x + pl[1] * v.y + pl[2] * v.z + pl[3] * v.w; }
+
+/* ClipVertices, OB.cpp:685-753: every live triangle is cut by one plane; a triangle with one vertex behind spawns a second. */
+static void clip_plane(const float* pl, V4* vv, unsigned char* live, unsigned* count)
+{
+    unsigned n = *count;
+    for (unsigned i = 0; i < n; ++i)
+    {
+        if (!live[i])
+            continue;
+        V4* t = vv + 3 * i;
+        float d0 = plane_dot(pl, t[0]), d1 = plane_dot(pl, t[1]), d2 = plane_dot(pl, t[2]);
+        int b0 = d0 < 0.0f, b1 = d1 < 0.0f, b2 = d2 < 0.0f;
+        if (b0 && b1 && b2)
+            live[i] = 0;
+        else if (b0 && b1)
+        {
+            t[0] = clip_lerp(t[0], t[2], d0, d2);
+            t[1] = clip_lerp(t[1], t[2], d1, d2);
+        }
+        else if (b0 && b2)
+        {
+            t[0] = clip_lerp(t[0], t[1], d0, d1);
+            t[2] = clip_lerp(t[2], t[1], d2, d1);
+        }
+        else if (b1 && b2)
+        {
+            t[1] = clip_lerp(t[1], t[0], d1, d0);
+            t[2] = clip_lerp(t[2], t[0], d2, d0);
+        }
+        else if (b0)
+        {
+            V4* nt = vv + 3 * (*count);
+            live[(*count)++] = 1;
+            nt[0] = clip_lerp(t[0], t[2], d0, d2);
+            nt[1] = t[0] = clip_lerp(t[0], t[1], d0, d1);
+            nt[2] = t[2];
+        }
+        else if (b1)
+        {
+            V4* nt = vv + 3 * (*count);
+            live[(*count)++] = 1;
+            nt[1] = clip_lerp(t[1], t[0], d1, d0);
+            nt[2] = t[1] = clip_lerp(t[1], t[2], d1, d2);
+            nt[0] = t[0];
+        }
+        else if (b2)
+        {
+            V4* nt = vv + 3 * (*count);
+            live[(*count)++] = 1;
+            nt[2] = clip_lerp(t[2], t[1], d2, d1);
+            nt[0] = t[2] = clip_lerp(t[2], t[0], d2, d0);
+            nt[1] = t[1];
+        }
+    }
+}
+
+/* DrawTriangle, OB.cpp:589-683.  vv has room for 64 triangles; vv[0..2] hold the clip-space input. */
+static void draw_tri(OrcOB* ob, V4* vv)
+{
+    unsigned any = 0, all = 0;
+    for (int i = 0; i < 3; ++i)
+    {
+        unsigned m = 0;
+        if (vv[i].x > vv[i].w) m |= 1;
+        if (vv[i].x < -vv[i].w) m |= 2;
+        if (vv[i].y > vv[i].w) m |= 4;
+        if (vv[i].y < -vv[i].w) m |= 8;
+        if (vv[i].z > vv[i].w) m |= 16;
+        if (vv[i].z < 0.0f) m |= 32;
+        any |= m;
+        all = i ? (all & m) : m;
+    }
+    if (all)
+        return;
+    int drawn = 0;
+    if (!any)
+        drawn = project_and_fill(ob, vv);
+    else
+    {
+        static const float planes[6][4] = {
+            {-1, 0, 0, 1}, {1, 0, 0, 1}, {0, -1, 0, 1}, {0, 1, 0, 1}, {0, 0, -1, 1}, {0, 0, 1, 0}};
+        unsigned char live[64];
+        unsigned count = 1;
+        live[0] = 1;
+        for (int p = 0; p < 6; ++p)
+            if (any & (1u << p))
+                clip_plane(planes[p], vv, live, &count);
+        for (unsigned i = 0; i < count; ++i)
+            if (live[i])
+                drawn |= project_and_fill(ob, vv + 3 * i);
+    }
+    if (drawn)
+        ++ob->num_tris;
+}
+
+/* AddTriangles (OB.cpp:164-198) immediately followed by DrawBatch (OB.cpp:464-541) for that one batch.
+ * idx == NULL -> non-indexed (start/count in vertices).  Returns AddTriangles' bool (budget not exceeded). */
+int orc_ob_draw_batch(OrcOB* ob, const float* model12, const void* vtx, unsigned stride, const void* idx, unsigned idx_size,
+    unsigned start, unsigned count)
+{
+    ob->num_tris += count / 3;
+    int ok = ob->num_tris <= ob->max_tris;
+    if (!ob->base)
+        return ok;
+    float mvp[16];
+    mul44_34(ob->vp, model12, mvp);
+    const unsigned char* vb = (const unsigned char*)vtx;
+    V4 vv[64 * 3];
+    if (!idx)
+    {
+        const unsigned char* src = vb + (size_t)start * stride;
+        for (unsigned i = 0; i + 2 < count; i += 3)
+        {
+            for (int k = 0; k < 3; ++k)
+                vv[k] = xform(mvp, (const float*)(src + (size_t)(i + k) * stride));
+            draw_tri(ob, vv);
+        }
+    }
+    else
+    {
+        for (unsigned i = 0; i < count; i += 3)
+        {
+            for (int k = 0; k < 3; ++k)
+            {
+                unsigned id = idx_size == 2 ? ((const uint16_t*)idx)[start + i + k] : ((const uint32_t*)idx)[start + i + k];
+                vv[k] = xform(mvp, (const float*)(vb + (size_t)id * stride));
+            }
+            draw_tri(ob, vv);
+        }
+    }
+    ob->dirty = 1;
+    return ok;
+}
+
+/* OB.cpp:234-329 */
+void orc_ob_build_hierarchy(OrcOB* ob)
+{
+    if (!ob->base || !ob->dirty)
+        return;
+    int pw = ob->w, ph = ob->h;
+    for (int lv = 0; lv < ob->nlev; ++lv)
+    {
+        int w = ob->mw[lv], h = ob->mh[lv];
+        int* dst = ob->mip[lv];
+        for (int y = 0; y < h; ++y)
+            for (int x = 0; x < w; ++x)
+            {
+                int mn = INT32_MAX, mx = INT32_MIN;
+                int rows = (2 * y + 1 < ph) ? 2 : 1;
+                for (int r = 0; r < rows; ++r)
+                    for (int c = 0; c < 2; ++c)
+                    {
+                        /* the reference always reads two texels per row (src[0], src[1]); with a power-of-two width >= 2
+                         * the second one always exists.  For a 1-texel-wide level it reads the next row's first texel. */
+                        size_t o = (size_t)(2 * y + r) * pw + 2 * x + c;
+                        int lo, hi;
+                        if (lv == 0) { lo = hi = ob->depth[o]; }
+                        else { lo = ob->mip[lv - 1][2 * o]; hi = ob->mip[lv - 1][2 * o + 1]; }
+                        if (lo < mn) mn = lo;
+                        if (hi > mx) mx = hi;
+                    }
+                dst[2 * ((size_t)y * w + x)] = mn;
+                dst[2 * ((size_t)y * w + x) + 1] = mx;
+            }
+        pw = w;
+        ph = h;
+    }
+    ob->dirty = 0;
+}
+
+/* OB.cpp:336-456 */
+int orc_ob_is_visible(const OrcOB* ob, const float* b /* minx,miny,minz,maxx,maxy,maxz */)
+{
+    if (!ob->base)
+        return 1;
+    float min_x = 0, max_x = 0, min_y = 0, max_y = 0, min_z = 0;
+    for (int i = 0; i < 8; ++i)
+    {
+        float p[3] = {b[(i & 1) ? 3 : 0], b[(i & 2) ? 4 : 1], b[(i & 4) ? 5 : 2]};
+        V4 v = xform(ob->vp, p);
+        v.z -= REL_BIAS;
+        /* The reference biases all 8 first and then walks them in order, returning at the first z <= 0; since the answer is
+         * "visible" whichever corner trips, checking while transforming gives the same result. */
+        if (v.z <= 0.0f)
+            return 1;
+        V3 s = to_screen(ob, v);
+        if (i == 0)
+        {
+            min_x = max_x = s.x;
+            min_y = max_y = s.y;
+            min_z = s.z;
+        }
+        else
+        {
+            if (s.x < min_x) min_x = s.x;
+            if (s.x > max_x) max_x = s.x;
+            if (s.y < min_y) min_y = s.y;
+            if (s.y > max_y) max_y = s.y;
+            if (s.z < min_z) min_z = s.z;
+        }
+    }
+    int left = trunc_f(min_x - 1.5f), top = trunc_f(min_y - 1.5f), right = round_to_int(max_x), bottom = round_to_int(max_y);
+    if (right < 0 || bottom < 0)
+        return 1;
+    if (left >= ob->w || top >= ob->h)
+        return 1;
+    if (left < 0) left = 0;
+    if (top < 0) top = 0;
+    if (right >= ob->w) right = ob->w - 1;
+    if (bottom >= ob->h) bottom = ob->h - 1;
+    int z = (int)((uint32_t)round_to_int(min_z) - FIXED_BIAS);
+
+    if (!ob->dirty)
+    {
+        for (int lv = ob->nlev - 1; lv >= 0; --lv)
+        {
+            int sh = lv + 1;
+            int roww = ob->w >> sh; /* the reference indexes rows with width_ >> shift, OB.cpp:410 */
+            int all_occluded = 1;
+            for (int y = top >> sh; y <= (bottom >> sh); ++y)
+                for (int x = left >> sh; x <= (right >> sh); ++x)
+                {
+                    const int* t = ob->mip[lv] + 2 * ((size_t)y * roww + x);
+                    if (z <= t[0])
+                        return 1;
+                    if (z <= t[1])
+                        all_occluded = 0;
+                }
+            if (all_occluded)
+                return 0;
+        }
+    }
+    for (int y = top; y <= bottom; ++y)
+        for (int x = left; x <= right; ++x)
+            if (z <= ob->depth[(size_t)y * ob->w + x])
+                return 1;
+    return 0;
+}
+
+void orc_ob_is_visible_many(const OrcOB* ob, int n, const float* aabb6, unsigned char* out)
+{
+    for (int i = 0; i < n; ++i)
+        out[i] = (unsigned char)orc_ob_is_visible(ob, aabb6 + 6 * (size_t)i);
+}
+
+void orc_ob_read_depth(const OrcOB* ob, int* out) { memcpy(out, ob->depth, sizeof(int) * (size_t)ob->w * ob->h); }
+void orc_ob_read_mip(const OrcOB* ob, int lv, int* out) { memcpy(out, ob->mip[lv], sizeof(int) * 2 * (size_t)ob->mw[lv] * ob->mh[lv]); }
+void orc_ob_mip_size(const OrcOB* ob, int lv, int* w, int* h) { *w = ob->mw[lv]; *h = ob->mh[lv]; }
+
+/* Frustum::IsInside / IsInsideFast, Math/Frustum.h:123-159.  planes = 6 x (nx,ny,nz,d); absNormal = |n| (Plane.h:83-88). */
+int orc_frustum_test(const float* planes24, const float* b, int fast)
+{
+    float cx = (b[3] + b[0]) * 0.5f, cy = (b[4] + b[1]) * 0.5f, cz = (b[5] + b[2]) * 0.5f; /* BoundingBox::Center, BoundingBox.h:265 */
+    float ex = cx - b[0], ey = cy - b[1], ez = cz - b[2];
+    int all_inside = 1;
+    for (int i = 0; i < 6; ++i)
+    {
+        const float* p = planes24 + 4 * i;
+        float dist = p[0] * cx + p[1] * cy + p[2] * cz + p[3];
+        float ad = fabsf(p[0]) * ex + fabsf(p[1]) * ey + fabsf(p[2]) * ez;
+        if (dist < -ad)
+            return OUTSIDE;
+        if (!fast && dist < ad)
+            all_inside = 0;
+    }
+    return (fast || all_inside) ? INSIDE : INTERSECTS;
+}
+
+/* Flattened octree in DFS pre-order (the visiting order of Octant::GetDrawablesInternal, Octree.cpp:229-255):
+ * octant i has parent[i] (< i, -1 for the root), culling box box6[i], and owns drawables [first[i], first[i]+count[i])
+ * of the DFS-ordered drawable arrays.  num_desc[i] = number of octants in i's subtree excluding i. */
+typedef struct
+{
+    int m;
+    const int* parent;
+    const float* box6;
+    const int* first;
+    const int* count;
+    int n;
+    const float* aabb6;          /* DFS order */
+    const unsigned char* flags;  /* drawableFlags */
+    const unsigned* view_mask;
+    const unsigned char* occludee;
+    const unsigned char* cast_shadows;
+} OrcTree;
+
+enum { Q_FRUSTUM = 0, Q_OCCLUDED = 1, Q_SHADOWCASTER = 2 };
+
+/* Octree::GetDrawables(query) for FrustumOctreeQuery (OctreeQuery.cpp:98-118), OccludedFrustumOctreeQuery (View.cpp:116-158)
+ * and ShadowCasterOctreeQuery (View.cpp:59-84).  Writes DFS positions of the result; returns their number. */
+int orc_query(const OrcTree* t, int mode, const float* planes24, const OrcOB* ob, unsigned flags, unsigned view_mask, int* out)
+{
+    /* iterative pre-order walk: state[i] 0 = culled, 1 = visited with inside=false, 2 = visited with inside=true */
+    unsigned char* state = (unsigned char*)malloc((size_t)t->m);
+    int nout = 0;
+    for (int i = 0; i < t->m; ++i)
+    {
+        int inside = 0;
+        if (i > 0)
+        {
+            unsigned char ps = state[t->parent[i]];
+            if (!ps)
+            {
+                state[i] = 0;
+                continue;
+            }
+            inside = ps == 2;
+            const float* box = t->box6 + 6 * (size_t)i;
+            int res;
+            if (mode == Q_OCCLUDED)
+            {
+                if (inside)
+                    res = orc_ob_is_visible(ob, box) ? INSIDE : OUTSIDE;
+                else
+                {
+                    res = orc_frustum_test(planes24, box, 0);
+                    if (res != OUTSIDE && !orc_ob_is_visible(ob, box))
+                        res = OUTSIDE;
+                }
+            }
+            else
+                res = inside ? INSIDE : orc_frustum_test(planes24, box, 0);
+            if (res == OUTSIDE)
+            {
+                state[i] = 0;
+                continue;
+            }
+            if (res == INSIDE)
+                inside = 1;
+        }
+        state[i] = inside ? 2 : 1;
+        for (int d = t->first[i]; d < t->first[i] + t->count[i]; ++d)
+        {
+            if (mode == Q_SHADOWCASTER && !t->cast_shadows[d])
+                continue;
+            if ((t->flags[d] & flags) && (t->view_mask[d] & view_mask))
+                if (inside || orc_frustum_test(planes24, t->aabb6 + 6 * (size_t)d, 1) != OUTSIDE)
+                    out[nout++] = d;
+        }
+    }
+    free(state);
+    return nout;
+}
+
+/* CheckVisibilityWork's occlusion predicate, View.cpp:177, over a query result (DFS positions); keeps order. */
+int orc_check_visibility(const OrcTree* t, const OrcOB* ob, const int* cand, int ncand, int* out)
+{
+    int n = 0;
+    for (int i = 0; i < ncand; ++i)
+    {
+        int d = cand[i];
+        if (!ob || !t->occludee[d] || orc_ob_is_visible(ob, t->aabb6 + 6 * (size_t)d))
+            out[n++] = d;
+    }
+    return n;
+}
