@@ -1,0 +1,204 @@
+/* u3d_gpu.h -- C-ABI of the B200-native visibility path (libu3dgpu.so).
+ *
+ * The reference has no FFI layer for this path: it is a C++ class API.  Each entry point below therefore names the
+ * reference member function it replaces ("OB" = Source/Urho3D/Graphics/OcclusionBuffer, "Octree" = Source/Urho3D/Graphics/Octree).
+ * The C++ host module urho3d_b200/GPUCompute/ wraps these in classes with the reference's method names; INTEGRATION.md shows the
+ * edits that re-point View.cpp / Renderer.cpp at them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; host pointers unless a parameter says "device".
+ *   - functions that mirror a reference `bool` return 1 (true) / 0 (false); every function returns a NEGATIVE value
+ *     (-U3D_ERR_*) on failure and u3d_last_error() then holds a message for the calling thread.  Nothing throws.
+ *   - there is NO CPU fallback: without a usable sm_100 device u3d_ctx_create fails with -U3D_ERR_NO_DEVICE.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = the context's own stream).  Calls that return results to host
+ *     memory synchronise that stream before returning; `_async` / run calls do not.
+ *   - matrices are row-major as in the reference's Matrix3x4 / Matrix4 (Matrix3x4::Data(), Matrix4::Data()).
+ */
+#ifndef U3D_GPU_H
+#define U3D_GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define U3D_API __attribute__((visibility("default")))
+
+enum
+{
+    U3D_OK = 0,
+    U3D_ERR_INVALID = 1,    /* bad argument */
+    U3D_ERR_CUDA = 2,       /* a CUDA call failed; message has cudaGetErrorString */
+    U3D_ERR_NOMEM = 3,
+    U3D_ERR_CAPACITY = 4,   /* an output or pool capacity was exceeded; message says which */
+    U3D_ERR_NO_DEVICE = 5,  /* no CUDA device / not sm_100: the product has no CPU path */
+    U3D_ERR_UNSUPPORTED = 6
+};
+
+/* CullMode, GraphicsDefs.h */
+enum { U3D_CULL_NONE = 0, U3D_CULL_CCW = 1, U3D_CULL_CW = 2 };
+/* which OctreeQuery the cull evaluates */
+enum
+{
+    U3D_QUERY_FRUSTUM = 0,       /* FrustumOctreeQuery, OctreeQuery.h:140-158 / OctreeQuery.cpp:98-118 */
+    U3D_QUERY_OCCLUDED = 1,      /* OccludedFrustumOctreeQuery, View.cpp:116-158 */
+    U3D_QUERY_SHADOWCASTER = 2   /* ShadowCasterOctreeQuery, View.cpp:59-84 */
+};
+/* what is emitted */
+enum
+{
+    U3D_STAGE_QUERY = 0,    /* Octree::GetDrawables result_ (Octree.cpp:495-499), DFS order */
+    U3D_STAGE_VISIBLE = 1   /* ... filtered by CheckVisibilityWork's predicate !occludee || IsVisible(box) (View.cpp:177), same order */
+};
+
+typedef struct u3d_ctx u3d_ctx;             /* one per GPU */
+typedef struct u3d_octree u3d_octree;       /* host octree mirror (structure of the reference's Octree) */
+typedef struct u3d_scene u3d_scene;         /* flattened octree + drawable AABBs resident in HBM */
+typedef struct u3d_mesh u3d_mesh;           /* vertex/index data resident in HBM */
+typedef struct u3d_occluders u3d_occluders; /* occluder table resident in HBM */
+typedef struct u3d_ob u3d_ob;               /* one occlusion buffer: drop-in for class OcclusionBuffer */
+typedef struct u3d_batch u3d_batch;         /* many-view pipeline: raster + hierarchy + cull for V views per call */
+
+/* One view of the batched entry point = the inputs OcclusionBuffer::SetView (OB.cpp:115-127) takes from the Camera plus the
+ * query's frustum and filters (OctreeQuery.h:40-70, 140-158). */
+typedef struct u3d_view
+{
+    float view[12];          /* Camera::GetView(), 3x4 */
+    float projection[16];    /* Camera::GetProjection(), 4x4 */
+    float planes[24];        /* Camera::GetFrustum(): 6 x (normal.xyz, d), order NEAR,LEFT,RIGHT,UP,DOWN,FAR (Frustum.h:37-45) */
+    float near_clip, far_clip;
+    uint32_t drawable_flags; /* OctreeQuery::drawableFlags_ */
+    uint32_t view_mask;      /* OctreeQuery::viewMask_ */
+    int32_t reverse_culling; /* Camera::GetReverseCulling() */
+    int32_t query_mode;      /* U3D_QUERY_* */
+    int32_t use_occlusion;   /* 0: no occlusion buffer for this view (frustum-only query; predicate passes everything) */
+    int32_t reserved;
+} u3d_view;
+
+U3D_API const char* u3d_last_error(void);
+U3D_API int u3d_abi_version(void);
+
+/* ---- context -------------------------------------------------------------------------------------------------------------- */
+U3D_API int u3d_ctx_create(int device, u3d_ctx** out);
+U3D_API void u3d_ctx_destroy(u3d_ctx* ctx);
+U3D_API int u3d_ctx_device(const u3d_ctx* ctx);
+U3D_API int u3d_ctx_synchronize(u3d_ctx* ctx, void* stream);
+
+/* ---- host octree mirror (no GPU needed) ----------------------------------------------------------------------------------- */
+/* Octree::Octree / SetSize (Octree.cpp:296-353); defaults are +-1000 and 8 levels (Octree.cpp:46-47). */
+U3D_API int u3d_octree_create(const float min3[3], const float max3[3], uint32_t levels, u3d_octree** out);
+U3D_API void u3d_octree_destroy(u3d_octree* t);
+/* Octree::InsertDrawable for n new drawables in order (Octree.cpp:134-166).  aabb6 = n x (min.xyz, max.xyz) world boxes;
+ * NULL arrays mean DRAWABLE_GEOMETRY / DEFAULT_VIEWMASK / occludee / no shadows.  Ids are assigned consecutively; *first_id = first. */
+U3D_API int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask,
+    const uint8_t* occludee, const uint8_t* cast_shadows, uint32_t* first_id);
+/* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472). */
+U3D_API int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6]);
+/* Octree::RemoveDrawable path (Octree.h:66-74, DecDrawableCount :123-136). */
+U3D_API int u3d_octree_remove(u3d_octree* t, uint32_t id);
+/* Flatten in the visiting order of Octant::GetDrawablesInternal (Octree.cpp:229-255). */
+U3D_API int u3d_octree_counts(const u3d_octree* t, uint32_t* num_octants, uint32_t* num_drawables_in_tree);
+U3D_API int u3d_octree_flatten(const u3d_octree* t, int32_t* parent, int32_t* level, float* culling_box6, int32_t* first, int32_t* count,
+    int32_t* order);
+
+/* ---- scene ---------------------------------------------------------------------------------------------------------------- */
+/* Upload the flattened octree + per-drawable records (32-byte BoundingBox layout, BoundingBox.h:326-330, meta in the pad words). */
+U3D_API int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out);
+/* Same from caller-flattened arrays (what an engine integration produces from the real Octree).  Per-drawable arrays are indexed
+ * by drawable id; order[i] = id of the drawable in DFS slot i. */
+U3D_API int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t num_octants, const int32_t* parent, const int32_t* level, const float* culling_box6,
+    const int32_t* first, const int32_t* count, uint32_t num_slots, const int32_t* order, const float* aabb6, const uint8_t* drawable_flags,
+    const uint32_t* view_mask, const uint8_t* occludee, const uint8_t* cast_shadows, u3d_scene** out);
+U3D_API void u3d_scene_destroy(u3d_scene* s);
+U3D_API int u3d_scene_counts(const u3d_scene* s, uint32_t* num_octants, uint32_t* num_drawables);
+
+/* ---- occluder geometry ---------------------------------------------------------------------------------------------------- */
+/* Vertex data: first 12 bytes of every vertex_size-byte vertex are the position (callers verify SEM_POSITION at offset 0,
+ * StaticModel.cpp:216).  index_size 2 or 4, or 0 with indices == NULL for non-indexed geometry. */
+U3D_API int u3d_mesh_create(u3d_ctx* ctx, const void* vertices, uint32_t vertex_size, uint32_t vertex_count, const void* indices,
+    uint32_t index_size, uint32_t index_count, u3d_mesh** out);
+U3D_API void u3d_mesh_destroy(u3d_mesh* m);
+/* Occluder table for the batched path: per occluder its world box (selection test), model matrix (3x4), mesh and draw range
+ * (= the arguments its DrawOcclusion would pass to AddTriangles, StaticModel.cpp:189-228).  index_start/index_count may be NULL
+ * (whole mesh).  cull_mode is what DrawOcclusion passes to SetCullMode; the reference reads a single cullMode_ at draw time
+ * (OB.cpp:634), so one mode applies to every batch of a DrawTriangles call. */
+U3D_API int u3d_occluders_create(u3d_ctx* ctx, uint32_t n, const float* world_aabb6, const float* model12, u3d_mesh* const* meshes,
+    uint32_t num_meshes, const uint32_t* mesh_of_occluder, const uint32_t* index_start, const uint32_t* index_count, int cull_mode,
+    u3d_occluders** out);
+U3D_API void u3d_occluders_destroy(u3d_occluders* o);
+
+/* ---- OcclusionBuffer drop-in (OB.h:101-158) ------------------------------------------------------------------------------- */
+U3D_API int u3d_ob_create(u3d_ctx* ctx, u3d_ob** out);                        /* OcclusionBuffer::OcclusionBuffer */
+U3D_API void u3d_ob_destroy(u3d_ob* ob);
+U3D_API int u3d_ob_set_size(u3d_ob* ob, int width, int height, int threaded); /* SetSize, OB.cpp:61-113 (1/0) */
+U3D_API int u3d_ob_set_view(u3d_ob* ob, const float view12[12], const float projection16[16], float near_clip, float far_clip,
+    int reverse_culling);                                                      /* SetView, OB.cpp:115-127 */
+U3D_API int u3d_ob_set_max_triangles(u3d_ob* ob, uint32_t triangles);         /* SetMaxTriangles, OB.cpp:129-132 */
+U3D_API int u3d_ob_set_cull_mode(u3d_ob* ob, int mode);                       /* SetCullMode, OB.cpp:134-144 */
+U3D_API int u3d_ob_reset(u3d_ob* ob);                                         /* Reset, OB.cpp:146-150 */
+U3D_API int u3d_ob_clear(u3d_ob* ob);                                         /* Clear, OB.cpp:152-162 */
+/* AddTriangles (non-indexed / indexed), OB.cpp:164-198.  Like the reference, only the pointers are stored until DrawTriangles. */
+U3D_API int u3d_ob_add_triangles(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size, uint32_t vertex_start,
+    uint32_t vertex_count);
+U3D_API int u3d_ob_add_triangles_indexed(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size,
+    const void* index_data, uint32_t index_size, uint32_t index_start, uint32_t index_count);
+/* Same budget/queue semantics with geometry already resident in HBM (extension; avoids the per-frame upload). */
+U3D_API int u3d_ob_add_triangles_mesh(u3d_ob* ob, const float model12[12], const u3d_mesh* mesh, uint32_t start, uint32_t count);
+U3D_API int u3d_ob_draw_triangles(u3d_ob* ob);                                /* DrawTriangles, OB.cpp:200-232 */
+U3D_API int u3d_ob_build_depth_hierarchy(u3d_ob* ob);                         /* BuildDepthHierarchy, OB.cpp:234-329 */
+U3D_API int u3d_ob_is_visible(u3d_ob* ob, const float aabb6[6]);              /* IsVisible, OB.cpp:336-456 (1/0) */
+U3D_API int u3d_ob_is_visible_many(u3d_ob* ob, const float* aabb6, uint32_t n, uint8_t* out);
+U3D_API int u3d_ob_get_buffer(u3d_ob* ob, int32_t* out_depth);                /* GetBuffer, OB.h:126: width*height ints */
+U3D_API int u3d_ob_get_mip(u3d_ob* ob, int level, int32_t* out_minmax);       /* mipBuffers_[level]: (min,max) pairs */
+U3D_API int u3d_ob_num_levels(const u3d_ob* ob);
+U3D_API int u3d_ob_mip_size(const u3d_ob* ob, int level, int* width, int* height);
+U3D_API int u3d_ob_get_width(const u3d_ob* ob);                               /* GetWidth */
+U3D_API int u3d_ob_get_height(const u3d_ob* ob);                              /* GetHeight */
+U3D_API uint32_t u3d_ob_get_num_triangles(const u3d_ob* ob);                  /* GetNumTriangles */
+U3D_API uint32_t u3d_ob_get_max_triangles(const u3d_ob* ob);                  /* GetMaxTriangles */
+U3D_API int u3d_ob_get_cull_mode(const u3d_ob* ob);                           /* GetCullMode */
+U3D_API int u3d_ob_is_threaded(const u3d_ob* ob);                             /* IsThreaded */
+U3D_API int u3d_ob_get_view_proj(const u3d_ob* ob, float out16[16]);          /* viewProj_ (for the 1e-5 screen-bounds check) */
+
+/* Octree::GetDrawables(OctreeQuery&) (Octree.cpp:495-499) with a Frustum / OccludedFrustum / ShadowCaster query, optionally followed by
+ * the CheckVisibilityWork predicate.  ob may be NULL (no occlusion).  out_ids receives at most `capacity` drawable ids in result_ order;
+ * *out_query_count = size of the query result, *out_count = number emitted for `stage` (may exceed capacity: -U3D_ERR_CAPACITY). */
+U3D_API int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uint32_t drawable_flags, uint32_t view_mask, int query_mode,
+    int stage, uint32_t* out_ids, uint32_t capacity, uint32_t* out_query_count, uint32_t* out_count);
+
+/* ---- batched many-view entry point (new) ----------------------------------------------------------------------- */
+/* Buffers for up to max_views views of width x height.  occluders may be NULL (frustum-only views, BASELINE config 4).
+ * out_capacity = result slots per view.  tri_pool = capacity of the set-up triangle pool in triangles (0 = automatic). */
+U3D_API int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, int width, int height, uint32_t max_views,
+    uint32_t out_capacity, uint64_t tri_pool, u3d_batch** out);
+U3D_API void u3d_batch_destroy(u3d_batch* b);
+/* Host -> device copy of n views (asynchronous on `stream`; the host array is consumed before the call returns). */
+U3D_API int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* stream);
+/* The whole per-view pipeline for the views last set, all on `stream`, no host synchronisation:
+ *   View::DrawOccluders threaded branch (View.cpp:2258-2273): Clear, select + AddTriangles, DrawTriangles, BuildDepthHierarchy;
+ *   Octree::GetDrawables(query) (View.cpp:873-878); CheckVisibilityWork predicate (View.cpp:177) when stage == U3D_STAGE_VISIBLE. */
+U3D_API int u3d_batch_run(u3d_batch* b, int stage, void* stream);
+/* Parts of the pipeline, for measurement: 1 = raster+hierarchy only, 2 = cull only (buffers from a previous run). */
+U3D_API int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream);
+/* Results.  counts = n x 2 uint32: (query result size, emitted count).  Synchronises `stream`; reports pool/output overflow. */
+U3D_API int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream);
+/* Emitted ids of every view packed back to back; offsets has n+1 entries.  capacity in ids.  Synchronises. */
+U3D_API int u3d_batch_read_packed(u3d_batch* b, uint32_t* offsets, uint32_t* ids, uint64_t capacity, void* stream);
+U3D_API int u3d_batch_read_view(u3d_batch* b, uint32_t view, uint32_t* ids, uint32_t capacity, uint32_t* count, void* stream);
+U3D_API int u3d_batch_read_depth(u3d_batch* b, uint32_t view, int32_t* out_depth, void* stream);
+U3D_API int u3d_batch_read_mip(u3d_batch* b, uint32_t view, int level, int32_t* out_minmax, void* stream);
+/* Per view: (submitted triangles, numTriangles_ as the reference counts it = submitted + source triangles that drew, set-up triangles). */
+U3D_API int u3d_batch_read_tri_stats(u3d_batch* b, uint32_t* stats3, void* stream);
+/* One call, host buffers in and out (the e2e path): set_views + run + read_counts + read_packed. */
+U3D_API int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int stage, uint32_t* counts, uint32_t* offsets, uint32_t* ids,
+    uint64_t capacity, void* stream);
+/* Device pointers of the result arrays (for NCCL gathers): counts = max_views x 2 uint32, ids = max_views x out_capacity uint32. */
+U3D_API int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids_dev, uint32_t* out_capacity);
+/* Kernel launches issued by the last u3d_batch_run / run_part on this batch. */
+U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* U3D_GPU_H */

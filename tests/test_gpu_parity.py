@@ -1,0 +1,277 @@
+"""GPU parity tests: every call goes through the C-ABI of libu3dgpu.so and is compared bit-for-bit with the C oracle
+(oracle/u3d_oracle.c, itself pinned to the compiled reference) and with the golden fixtures."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oraclebind
+from urho3d_b200 import camera, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+
+
+def gpu_scene(ctx, sc):
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    flat = tree.flatten()
+    return tree, flat, capi.GpuScene(ctx, octree=tree)
+
+
+def oracle_view(sc, otree, ob, v):
+    sub = ob.draw_scene_view(sc, v)
+    cand = otree.query(1, v.planes, ob, as_ids=False)
+    vis = otree.order[otree.check_visibility(ob, cand)]
+    return sub, otree.order[cand], vis
+
+
+@pytest.mark.parametrize("w,h,stress", [(256, 160, False), (128, 128, True), (64, 30, True), (512, 288, False), (32, 32, True)])
+def test_occlusion_buffer_dropin(gpu_ctx, w, h, stress):
+    """OcclusionBuffer API call by call: SetSize/SetView/Clear/SetCullMode/AddTriangles/DrawTriangles/BuildDepthHierarchy/IsVisible."""
+    sc = helpers.small_scene(n=4000, k=128, extent=90.0, seed=3 + w)
+    views = helpers.stress_views(90.0, w, h, 6, seed=w + h) if stress else scenes.agent_cameras(6, 90.0, w, h, seed=w)
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    assert gob.IsVisible(sc.aabb[0])  # no buffer yet -> true (OB.cpp:338-339)
+    assert gob.SetSize(w, h)
+    ob = oraclebind.OracleOB()
+    ob.set_size(w, h)
+    assert (gob.GetWidth(), gob.GetHeight()) == ob.size()
+    for v in views:
+        gob.SetView(v)
+        ob.set_view(v)
+        assert np.array_equal(gob.GetViewProj(), ob.viewproj())
+        gob.SetMaxTriangles(1 << 30)
+        ob.set_max_triangles(1 << 30)
+        gob.Clear()
+        ob.clear()
+        for i in range(sc.k):
+            if oraclebind.frustum_test(v.planes, sc.occ_aabb[i], fast=True) == 0:
+                continue
+            gob.SetCullMode(sc.cull_mode)
+            ob.set_cull_mode(sc.cull_mode)
+            a = gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+            b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+            assert a == b
+        gob.DrawTriangles()
+        assert np.array_equal(gob.GetBuffer(), ob.depth())
+        assert gob.GetNumTriangles() == ob.num_triangles()
+        # hierarchy still dirty: pixel-scan path
+        assert np.array_equal(gob.IsVisibleMany(sc.aabb[:1500]), ob.is_visible_many(sc.aabb[:1500]))
+        gob.BuildDepthHierarchy()
+        ob.build_hierarchy()
+        for a, b in zip(gob.GetMips(), ob.mips()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(gob.IsVisibleMany(sc.aabb), ob.is_visible_many(sc.aabb))
+        assert gob.IsVisible(sc.aabb[7]) == ob.is_visible(sc.aabb[7])
+    gob.close()
+    ob.close()
+
+
+def test_set_size_rules(gpu_ctx):
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    assert not gob.SetSize(100, 64)      # not a power of two (OB.cpp:73-77)
+    assert not gob.SetSize(0, 64)
+    assert not gob.SetSize(64, -2)
+    assert gob.SetSize(64, 33)
+    assert gob.GetHeight() == 34         # odd heights are rounded up (OB.cpp:63-65)
+    assert gob.SetSize(64, 34)
+    gob.close()
+
+
+def test_budget_cullmodes_nonindexed_u32(gpu_ctx):
+    w, h = 64, 64
+    sc = helpers.small_scene(n=10, k=8, extent=10.0, seed=9)
+    v = helpers.stress_views(10.0, w, h, 1, seed=4)[0]
+    pos = sc.mesh_vtx[:, :12].copy().view(np.float32).reshape(24, 3)
+    flat_vtx = np.ascontiguousarray(pos[sc.mesh_idx.astype(np.int64)])
+    idx32 = sc.mesh_idx.astype(np.uint32)
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    gob.SetSize(w, h)
+    ob = oraclebind.OracleOB()
+    ob.set_size(w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, 52, sc.mesh_idx)
+    for cull in (0, 1, 2):
+        for reverse in (False, True):
+            v.reverse_culling = reverse
+            gob.SetView(v)
+            ob.set_view(v)
+            gob.SetMaxTriangles(20)
+            ob.set_max_triangles(20)
+            gob.Clear()
+            ob.clear()
+            for i in range(sc.k):
+                gob.SetCullMode(cull)
+                ob.set_cull_mode(cull)
+                if i % 4 == 0:
+                    a = gob.AddTriangles(sc.occ_model[i], flat_vtx, 12, None, 3, 33)
+                    b = ob.draw_batch(sc.occ_model[i], flat_vtx, 12, None, 3, 33)
+                elif i % 4 == 1:
+                    a = gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, 52, idx32, 6, 30)
+                    b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, idx32, 6, 30)
+                elif i % 4 == 2:
+                    a = gob.AddTrianglesMesh(sc.occ_model[i], mesh, 3, 33)
+                    b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 3, 33)
+                else:
+                    a = gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+                    b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+                assert a == b
+            assert gob.GetCullMode() == ob.cull_mode()
+            gob.DrawTriangles()
+            # a second DrawTriangles with nothing queued must not change anything (batches_ cleared, OB.cpp:231)
+            gob.DrawTriangles()
+            assert np.array_equal(gob.GetBuffer(), ob.depth())
+            assert gob.GetNumTriangles() == ob.num_triangles()
+    mesh.close()
+    gob.close()
+    ob.close()
+
+
+@pytest.mark.parametrize("mode", [capi.QUERY_FRUSTUM, capi.QUERY_OCCLUDED, capi.QUERY_SHADOWCASTER])
+def test_octree_queries(gpu_ctx, mode):
+    """Octree::GetDrawables(query) result_ sequence for the three frustum query classes, with flag/mask filtering."""
+    w, h = 256, 160
+    sc = helpers.small_scene(n=6000, k=128, extent=100.0, seed=31)
+    sc.flags[::7] = 0x2          # DRAWABLE_LIGHT: filtered by drawableFlags
+    sc.view_mask[::5] = 0x4
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    gob.SetSize(w, h)
+    for v in scenes.agent_cameras(5, 100.0, w, h, seed=8):
+        ob.draw_scene_view(sc, v)
+        gob.SetView(v)
+        gob.SetMaxTriangles(1 << 30)
+        gob.Clear()
+        gob.SetCullMode(sc.cull_mode)
+        for i in range(sc.k):
+            if oraclebind.frustum_test(v.planes, sc.occ_aabb[i], fast=True):
+                gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+        gob.DrawTriangles()
+        gob.BuildDepthHierarchy()
+        for flags, mask in ((0xFF, 0xFFFFFFFF), (0x1, 0xFFFFFFFF), (0xFF, 0x3), (0x2, 0x4)):
+            want = otree.query(mode, v.planes, ob if mode == 1 else None, flags, mask)
+            got, qc = gs.query(v.planes, gob if mode == 1 else None, flags, mask, mode, capi.STAGE_QUERY)
+            assert qc == len(want)
+            assert np.array_equal(got, want)
+            if mode == 1:
+                cand = otree.query(1, v.planes, ob, flags, mask, as_ids=False)
+                vis = otree.order[otree.check_visibility(ob, cand)]
+                got, qc = gs.query(v.planes, gob, flags, mask, mode, capi.STAGE_VISIBLE)
+                assert qc == len(cand) and np.array_equal(got, vis)
+    with pytest.raises(capi.U3DError) as e:
+        gs.query(v.planes, None, mode=capi.QUERY_FRUSTUM, capacity=1)
+    assert e.value.code == capi.ERR_CAPACITY
+    for o in (gob, gs, tree):
+        o.close()
+    ob.close()
+
+
+@pytest.mark.parametrize("w,h,nviews,stress", [(256, 160, 12, False), (256, 256, 8, True), (64, 64, 40, True), (1024, 576, 2, False)])
+def test_batched_views(gpu_ctx, w, h, nviews, stress):
+    """The batched many-view entry point: depth plane, every mip level, tri counts, query result and visible set per view."""
+    sc = helpers.small_scene(n=8000, k=160, extent=100.0, seed=w + 1)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = helpers.stress_views(100.0, w, h, nviews, seed=h) if stress else scenes.agent_cameras(nviews, 100.0, w, h, seed=h)
+    views[1].reverse_culling = True
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, nviews, sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    stats = batch.tri_stats()
+    for i, v in enumerate(views):
+        sub, cand, vis = oracle_view(sc, otree, ob, v)
+        assert np.array_equal(batch.depth(i), ob.depth()), "view %d depth" % i
+        for a, b in zip(batch.mips(i), ob.mips()):
+            assert np.array_equal(a, b)
+        assert stats[i, 0] == sub and stats[i, 1] == ob.num_triangles()
+        assert counts[i, 0] == len(cand) and counts[i, 1] == len(vis)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], vis)
+        assert np.array_equal(batch.view_ids(i), vis)
+    # query stage only
+    batch.set_views(capi.pack_views(views))
+    batch.run(capi.STAGE_QUERY)
+    off, qids = batch.packed()
+    for i, v in enumerate(views):
+        sub, cand, vis = oracle_view(sc, otree, ob, v)
+        assert np.array_equal(qids[off[i]:off[i + 1]], cand)
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+def test_frustum_only_shadow_views(gpu_ctx):
+    """BASELINE config 4 shape: ortho cascades + cube faces, no occlusion buffer, ShadowCasterOctreeQuery."""
+    sc = helpers.small_scene(n=20000, k=4, extent=120.0, seed=77)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, _ = helpers.make_oracle(sc, flat, 8, 8)
+    views = scenes.shadow_views(120.0, n_point_lights=6, seed=3)
+    batch = capi.Batch(gpu_ctx, gs, None, 0, 0, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views, query_mode=capi.QUERY_SHADOWCASTER, use_occlusion=False), capi.STAGE_VISIBLE)
+    total = 0
+    for i, v in enumerate(views):
+        want = otree.query(2, v.planes, None)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], want)
+        total += len(want)
+    assert total > 0
+    for o in (batch, gs, tree):
+        o.close()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p) for p in GOLDEN])
+def test_golden_fixtures_through_gpu(gpu_ctx, path):
+    """Committed outputs of the UNMODIFIED reference vs the CUDA path."""
+    g = np.load(path)
+    sc = scenes.Scene(int(g["n"]), int(g["k"]), float(g["extent"]), seed=int(g["seed"]))
+    w, h = int(g["width"]), int(g["height"])
+    views = []
+    for i in range(int(g["nviews"])):
+        nf = g["v%d_nearfar" % i]
+        views.append(camera.CameraView(g["v%d_view" % i], g["v%d_proj" % i], g["v%d_planes" % i], nf[0], nf[1]))
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    for key in ("parent", "level", "first", "count", "order", "box"):
+        assert np.array_equal(flat[key], g["flat_" + key])
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    stats = batch.tri_stats()
+    for i in range(len(views)):
+        assert np.array_equal(batch.depth(i), g["v%d_depth" % i])
+        for lv, m in enumerate(batch.mips(i)):
+            assert np.array_equal(m, g["v%d_mip%d" % (i, lv)])
+        assert stats[i, 1] == int(g["v%d_numtris" % i][0])
+        assert counts[i, 0] == len(g["v%d_query" % i])
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], g["v%d_visible" % i])
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+
+
+def test_million_drawables_slice(gpu_ctx):
+    """BASELINE configs 2/3 scene (1M drawables, 4000 occluders): one 1024x576 view and four 256x256 views against the oracle."""
+    cfg = scenes.CONFIGS["C3"]
+    sc = scenes.Scene(cfg["n"], cfg["k"], cfg["extent"])
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    assert gs.num_drawables == cfg["n"]
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    for (w, h, nv) in ((256, 256, 4), (1024, 576, 1)):
+        otree, ob = helpers.make_oracle(sc, flat, w, h)
+        views = scenes.agent_cameras(nv, cfg["extent"], w, h)
+        batch = capi.Batch(gpu_ctx, gs, occ, w, h, nv, 200000)
+        counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+        for i, v in enumerate(views):
+            sub, cand, vis = oracle_view(sc, otree, ob, v)
+            assert np.array_equal(batch.depth(i), ob.depth())
+            for a, b in zip(batch.mips(i), ob.mips()):
+                assert np.array_equal(a, b)
+            assert counts[i, 0] == len(cand)
+            assert np.array_equal(ids[offsets[i]:offsets[i + 1]], vis)
+        batch.close()
+        ob.close()
+    for o in (occ, mesh, gs, tree):
+        o.close()

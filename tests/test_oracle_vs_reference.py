@@ -1,0 +1,109 @@
+"""Differential pin of the C oracle against the compiled reference (oracle/_ref/libu3dref.so) on fresh random inputs.
+Skipped only where the reference could not be built (it ships prebuilt to the GPU box)."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oraclebind, refbind
+from urho3d_b200 import scenes
+
+pytestmark = pytest.mark.skipif(not refbind.available(), reason="oracle/_ref/libu3dref.so not built (run oracle/build_ref.sh)")
+
+
+@pytest.mark.parametrize("w,h,stress", [(256, 160, False), (128, 128, True), (64, 30, True), (512, 288, False)])
+def test_full_view_pipeline(w, h, stress):
+    sc = helpers.small_scene(n=4000, k=128, extent=90.0, seed=3 + w)
+    ref = helpers.make_ref(sc, w, h)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    views = helpers.stress_views(90.0, w, h, 10, seed=w + h) if stress else scenes.agent_cameras(10, 90.0, w, h, seed=w)
+    for v in views:
+        vis, counts = helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(ob.depth(), ref.ob_depth())
+        for a, b in zip(ob.mips(), ref.ob_mips()):
+            assert np.array_equal(a, b)
+        assert ob.num_triangles() == ref.ob_num_triangles()
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+        assert np.array_equal(tree.query(0, v.planes, None), ref.query(0))
+        assert np.array_equal(tree.query(2, v.planes, None), ref.query(2))
+    ref.close()
+    ob.close()
+
+
+def test_is_visible_dirty_and_clean_paths():
+    """IsVisible with the hierarchy dirty (pixel scan, OB.cpp:404, 440-455) and clean (mip walk) on random boxes."""
+    w, h = 128, 64
+    sc = helpers.small_scene(n=3000, k=64, extent=40.0, seed=5)
+    ref = helpers.make_ref(sc, w, h)
+    _, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    rs = np.random.RandomState(1)
+    # a camera in the middle of the region so that walls cover a good part of the buffer
+    from urho3d_b200 import camera
+    v = camera.make_view([0.0, 2.0, 0.0], 30.0, 0.0, 60.0, w / h, 0.1, 200.0)
+    ref.set_view_raw(v)
+    ref.ob_set_max_triangles(1 << 30)
+    ref.ob_clear()
+    ob.set_view(v)
+    ob.set_max_triangles(1 << 30)
+    ob.clear()
+    for i in range(sc.k):
+        ref.ob_set_cull_mode(sc.cull_mode)
+        ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+        ob.set_cull_mode(sc.cull_mode)
+        ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+    ref.ob_draw()
+    c = rs.uniform(-45, 45, size=(1000, 3)).astype(np.float32)
+    c[:, 1] = rs.uniform(0, 6, size=1000)
+    e = rs.uniform(0.2, 6, size=(1000, 3)).astype(np.float32)
+    boxes = np.concatenate([np.concatenate([c - e, c + e], axis=1).astype(np.float32), sc.aabb])
+    dirty_ref = ref.ob_is_visible_many(boxes)
+    assert np.array_equal(ob.is_visible_many(boxes), dirty_ref)
+    ref.ob_build_hierarchy()
+    ob.build_hierarchy()
+    clean_ref = ref.ob_is_visible_many(boxes)
+    assert np.array_equal(ob.is_visible_many(boxes), clean_ref)
+    assert np.array_equal(clean_ref, dirty_ref)  # SURVEY hard part 5: the mips never change the answer
+    assert 0.05 * len(boxes) < clean_ref.sum() < 0.95 * len(boxes)
+
+
+def test_non_indexed_and_u32_indices_and_cull_modes():
+    w, h = 64, 64
+    sc = helpers.small_scene(n=10, k=8, extent=10.0, seed=9)
+    ref = helpers.make_ref(sc, w, h)
+    _, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    v = helpers.stress_views(10.0, w, h, 1, seed=4)[0]
+    pos = sc.mesh_vtx[:, :12].copy().view(np.float32).reshape(24, 3)
+    flat_vtx = np.ascontiguousarray(pos[sc.mesh_idx.astype(np.int64)])  # 36 x 3 floats, stride 12, non-indexed
+    idx32 = sc.mesh_idx.astype(np.uint32)
+    for cull in (0, 1, 2):
+        for reverse in (False, True):
+            v.reverse_culling = reverse
+            ref.set_view_raw(v)
+            ob.set_view(v)
+            ref.ob_set_max_triangles(20)
+            ob.set_max_triangles(20)
+            ref.ob_clear()
+            ob.clear()
+            rets = []
+            for i in range(sc.k):
+                ref.ob_set_cull_mode(cull)
+                ob.set_cull_mode(cull)
+                if i % 3 == 0:
+                    a = ref.ob_add_triangles(sc.occ_model[i], flat_vtx, 12, None, 3, 33)
+                    b = ob.draw_batch(sc.occ_model[i], flat_vtx, 12, None, 3, 33)
+                elif i % 3 == 1:
+                    a = ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, 52, idx32, 6, 30)
+                    b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, idx32, 6, 30)
+                else:
+                    a = ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+                    b = ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+                rets.append((a, b))
+            assert all(a == b for a, b in rets) and not all(a for a, _ in rets)  # budget of 20 triangles is exceeded midway
+            ref.ob_draw()
+            assert ref.ob_get_cull_mode() == ob.cull_mode()
+            assert np.array_equal(ob.depth(), ref.ob_depth())
+            assert ob.num_triangles() == ref.ob_num_triangles()
+    v.reverse_culling = False

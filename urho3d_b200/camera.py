@@ -140,6 +140,8 @@ class CameraView:
 def make_view(pos, yaw_deg, pitch_deg, fov_deg, aspect, near, far, ortho=False, ortho_size=20.0, zoom=1.0):
     q = quat_from_euler(pitch_deg, yaw_deg, 0.0)
     xf = world_transform(pos, q)
+    if ortho:
+        near = 0.0  # Camera::GetNearClip() reports projNearClip_, which stays 0 for orthographic cameras (Camera.cpp:676-678)
     return CameraView(inverse_rigid(xf), projection(fov_deg, aspect, near, far, ortho, ortho_size, zoom),
                       frustum_planes(fov_deg, aspect, near, far, xf, ortho, ortho_size, zoom), near, far)
 

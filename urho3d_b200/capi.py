@@ -1,0 +1,466 @@
+"""ctypes binding of libu3dgpu.so (include/u3d_gpu.h) plus thin Python mirrors of the reference-facing objects.
+
+The library is the product; this file is plumbing for tests, smoke and bench.  It never falls back to a CPU
+implementation: if the shared library is missing it raises, and every compute call goes to the CUDA kernels.
+"""
+import ctypes as C
+import os
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "lib", "libu3dgpu.so")
+
+QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER = 0, 1, 2
+STAGE_QUERY, STAGE_VISIBLE = 0, 1
+CULL_NONE, CULL_CCW, CULL_CW = 0, 1, 2
+ERR_CAPACITY = 4
+
+_f = C.POINTER(C.c_float)
+_i32 = C.POINTER(C.c_int32)
+_u8 = C.POINTER(C.c_uint8)
+_u32 = C.POINTER(C.c_uint32)
+_vp = C.c_void_p
+
+
+class U3DView(C.Structure):
+    """struct u3d_view of include/u3d_gpu.h."""
+    _fields_ = [("view", C.c_float * 12), ("projection", C.c_float * 16), ("planes", C.c_float * 24), ("near_clip", C.c_float),
+                ("far_clip", C.c_float), ("drawable_flags", C.c_uint32), ("view_mask", C.c_uint32), ("reverse_culling", C.c_int32),
+                ("query_mode", C.c_int32), ("use_occlusion", C.c_int32), ("reserved", C.c_int32)]
+
+
+VIEW_DTYPE = np.dtype([("view", np.float32, 12), ("projection", np.float32, 16), ("planes", np.float32, 24), ("near_clip", np.float32),
+                       ("far_clip", np.float32), ("drawable_flags", np.uint32), ("view_mask", np.uint32), ("reverse_culling", np.int32),
+                       ("query_mode", np.int32), ("use_occlusion", np.int32), ("reserved", np.int32)])
+assert VIEW_DTYPE.itemsize == C.sizeof(U3DView) == 240
+
+# name -> (restype, argtypes); the list doubles as the symbol inventory checked by tests/test_capi_symbols.py
+SIGNATURES = {
+    "u3d_last_error": (C.c_char_p, []),
+    "u3d_abi_version": (C.c_int, []),
+    "u3d_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
+    "u3d_ctx_destroy": (None, [_vp]),
+    "u3d_ctx_device": (C.c_int, [_vp]),
+    "u3d_ctx_synchronize": (C.c_int, [_vp, _vp]),
+    "u3d_octree_create": (C.c_int, [_f, _f, C.c_uint32, C.POINTER(_vp)]),
+    "u3d_octree_destroy": (None, [_vp]),
+    "u3d_octree_add": (C.c_int, [_vp, C.c_uint32, _f, _u8, _u32, _u8, _u8, _u32]),
+    "u3d_octree_update": (C.c_int, [_vp, C.c_uint32, _f]),
+    "u3d_octree_remove": (C.c_int, [_vp, C.c_uint32]),
+    "u3d_octree_counts": (C.c_int, [_vp, _u32, _u32]),
+    "u3d_octree_flatten": (C.c_int, [_vp, _i32, _i32, _f, _i32, _i32, _i32]),
+    "u3d_scene_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    "u3d_scene_create_flat": (C.c_int, [_vp, C.c_uint32, _i32, _i32, _f, _i32, _i32, C.c_uint32, _i32, _f, _u8, _u32, _u8, _u8, C.POINTER(_vp)]),
+    "u3d_scene_destroy": (None, [_vp]),
+    "u3d_scene_counts": (C.c_int, [_vp, _u32, _u32]),
+    "u3d_mesh_create": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
+    "u3d_mesh_destroy": (None, [_vp]),
+    "u3d_occluders_create": (C.c_int, [_vp, C.c_uint32, _f, _f, C.POINTER(_vp), C.c_uint32, _u32, _u32, _u32, C.c_int, C.POINTER(_vp)]),
+    "u3d_occluders_destroy": (None, [_vp]),
+    "u3d_ob_create": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "u3d_ob_destroy": (None, [_vp]),
+    "u3d_ob_set_size": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int]),
+    "u3d_ob_set_view": (C.c_int, [_vp, _f, _f, C.c_float, C.c_float, C.c_int]),
+    "u3d_ob_set_max_triangles": (C.c_int, [_vp, C.c_uint32]),
+    "u3d_ob_set_cull_mode": (C.c_int, [_vp, C.c_int]),
+    "u3d_ob_reset": (C.c_int, [_vp]),
+    "u3d_ob_clear": (C.c_int, [_vp]),
+    "u3d_ob_add_triangles": (C.c_int, [_vp, _f, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "u3d_ob_add_triangles_indexed": (C.c_int, [_vp, _f, _vp, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.c_uint32]),
+    "u3d_ob_add_triangles_mesh": (C.c_int, [_vp, _f, _vp, C.c_uint32, C.c_uint32]),
+    "u3d_ob_draw_triangles": (C.c_int, [_vp]),
+    "u3d_ob_build_depth_hierarchy": (C.c_int, [_vp]),
+    "u3d_ob_is_visible": (C.c_int, [_vp, _f]),
+    "u3d_ob_is_visible_many": (C.c_int, [_vp, _f, C.c_uint32, _u8]),
+    "u3d_ob_get_buffer": (C.c_int, [_vp, _i32]),
+    "u3d_ob_get_mip": (C.c_int, [_vp, C.c_int, _i32]),
+    "u3d_ob_num_levels": (C.c_int, [_vp]),
+    "u3d_ob_mip_size": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "u3d_ob_get_width": (C.c_int, [_vp]),
+    "u3d_ob_get_height": (C.c_int, [_vp]),
+    "u3d_ob_get_num_triangles": (C.c_uint32, [_vp]),
+    "u3d_ob_get_max_triangles": (C.c_uint32, [_vp]),
+    "u3d_ob_get_cull_mode": (C.c_int, [_vp]),
+    "u3d_ob_is_threaded": (C.c_int, [_vp]),
+    "u3d_ob_get_view_proj": (C.c_int, [_vp, _f]),
+    "u3d_octree_query": (C.c_int, [_vp, _vp, _f, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u32, C.c_uint32, _u32, _u32]),
+    "u3d_batch_create": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
+    "u3d_batch_destroy": (None, [_vp]),
+    "u3d_batch_set_views": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
+    "u3d_batch_run": (C.c_int, [_vp, C.c_int, _vp]),
+    "u3d_batch_run_part": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "u3d_batch_read_counts": (C.c_int, [_vp, _u32, _vp]),
+    "u3d_batch_read_packed": (C.c_int, [_vp, _u32, _u32, C.c_uint64, _vp]),
+    "u3d_batch_read_view": (C.c_int, [_vp, C.c_uint32, _u32, C.c_uint32, _u32, _vp]),
+    "u3d_batch_read_depth": (C.c_int, [_vp, C.c_uint32, _i32, _vp]),
+    "u3d_batch_read_mip": (C.c_int, [_vp, C.c_uint32, C.c_int, _i32, _vp]),
+    "u3d_batch_read_tri_stats": (C.c_int, [_vp, _u32, _vp]),
+    "u3d_batch_cull_views": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _u32, _u32, _u32, C.c_uint64, _vp]),
+    "u3d_batch_device_results": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u32]),
+    "u3d_batch_last_launches": (C.c_uint32, [_vp]),
+}
+
+_lib = None
+
+
+class U3DError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("u3d error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    """Load libu3dgpu.so.  Fails loudly when the CUDA extension has not been built: there is no other implementation."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("libu3dgpu.so is missing (%s): run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "or `make -C urho3d_b200/csrc`; there is no CPU fallback" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _chk(rc):
+    if rc < 0:
+        raise U3DError(-rc, lib().u3d_last_error().decode())
+    return rc
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t) if a is not None else None
+
+
+def _arr(a, dtype):
+    return None if a is None else np.ascontiguousarray(a, dtype=dtype)
+
+
+class Context:
+    def __init__(self, device=0):
+        h = _vp()
+        _chk(lib().u3d_ctx_create(device, C.byref(h)))
+        self.h = h
+
+    def synchronize(self, stream=None):
+        _chk(lib().u3d_ctx_synchronize(self.h, stream))
+
+    def close(self):
+        if self.h:
+            lib().u3d_ctx_destroy(self.h)
+            self.h = None
+
+
+class Octree:
+    """Host octree mirror (no GPU needed).  Same structure as the reference's Octree for the same inserts."""
+
+    def __init__(self, mn=(-1000.0,) * 3, mx=(1000.0,) * 3, levels=8):
+        h = _vp()
+        mn = np.asarray(mn, np.float32)
+        mx = np.asarray(mx, np.float32)
+        _chk(lib().u3d_octree_create(_p(mn, _f), _p(mx, _f), levels, C.byref(h)))
+        self.h = h
+
+    def add(self, aabb6, flags=None, view_mask=None, occludee=None, cast_shadows=None):
+        a = _arr(aabb6, np.float32).reshape(-1, 6)
+        fl, vm, oc, cs = _arr(flags, np.uint8), _arr(view_mask, np.uint32), _arr(occludee, np.uint8), _arr(cast_shadows, np.uint8)
+        first = C.c_uint32()
+        _chk(lib().u3d_octree_add(self.h, a.shape[0], _p(a, _f), _p(fl, _u8), _p(vm, _u32), _p(oc, _u8), _p(cs, _u8), C.byref(first)))
+        return first.value
+
+    def update(self, idx, aabb6):
+        a = _arr(aabb6, np.float32)
+        _chk(lib().u3d_octree_update(self.h, idx, _p(a, _f)))
+
+    def remove(self, idx):
+        _chk(lib().u3d_octree_remove(self.h, idx))
+
+    def flatten(self):
+        m, n = C.c_uint32(), C.c_uint32()
+        _chk(lib().u3d_octree_counts(self.h, C.byref(m), C.byref(n)))
+        m, n = m.value, n.value
+        parent, level, first, count = (np.zeros(m, np.int32) for _ in range(4))
+        box = np.zeros((m, 6), np.float32)
+        order = np.zeros(max(n, 1), np.int32)
+        _chk(lib().u3d_octree_flatten(self.h, _p(parent, _i32), _p(level, _i32), _p(box, _f), _p(first, _i32), _p(count, _i32), _p(order, _i32)))
+        return dict(parent=parent, level=level, box=box, first=first, count=count, order=order[:n])
+
+    def close(self):
+        if self.h:
+            lib().u3d_octree_destroy(self.h)
+            self.h = None
+
+
+class GpuScene:
+    def __init__(self, ctx, octree=None, flat=None, aabb6=None, flags=None, view_mask=None, occludee=None, cast_shadows=None):
+        h = _vp()
+        if octree is not None:
+            _chk(lib().u3d_scene_create(ctx.h, octree.h, C.byref(h)))
+        else:
+            par, lev = _arr(flat["parent"], np.int32), _arr(flat["level"], np.int32)
+            box, fst, cnt = _arr(flat["box"], np.float32), _arr(flat["first"], np.int32), _arr(flat["count"], np.int32)
+            order = _arr(flat["order"], np.int32)
+            a = _arr(aabb6, np.float32)
+            fl, vm, oc, cs = _arr(flags, np.uint8), _arr(view_mask, np.uint32), _arr(occludee, np.uint8), _arr(cast_shadows, np.uint8)
+            _chk(lib().u3d_scene_create_flat(ctx.h, len(par), _p(par, _i32), _p(lev, _i32), _p(box, _f), _p(fst, _i32), _p(cnt, _i32), len(order),
+                                             _p(order, _i32), _p(a, _f), _p(fl, _u8), _p(vm, _u32), _p(oc, _u8), _p(cs, _u8), C.byref(h)))
+        self.h = h
+        self.ctx = ctx
+        m, n = C.c_uint32(), C.c_uint32()
+        _chk(lib().u3d_scene_counts(self.h, C.byref(m), C.byref(n)))
+        self.num_octants, self.num_drawables = m.value, n.value
+
+    def query(self, planes, ob=None, flags=0xFF, view_mask=0xFFFFFFFF, mode=QUERY_FRUSTUM, stage=STAGE_QUERY, capacity=None):
+        """Octree::GetDrawables with a frustum-type query (+ optional visibility predicate).  Returns (ids, query_count)."""
+        cap = self.num_drawables if capacity is None else capacity
+        out = np.zeros(max(cap, 1), np.uint32)
+        p = _arr(planes, np.float32)
+        qc, c = C.c_uint32(), C.c_uint32()
+        _chk(lib().u3d_octree_query(self.h, ob.h if ob is not None else None, _p(p, _f), flags, view_mask, mode, stage, _p(out, _u32), cap,
+                                    C.byref(qc), C.byref(c)))
+        return out[:c.value].astype(np.int64), qc.value
+
+    def close(self):
+        if self.h:
+            lib().u3d_scene_destroy(self.h)
+            self.h = None
+
+
+class Mesh:
+    def __init__(self, ctx, vtx, stride, idx=None):
+        h = _vp()
+        vtx = np.ascontiguousarray(vtx)
+        nv = vtx.nbytes // stride
+        self._keep = (vtx, idx)
+        _chk(lib().u3d_mesh_create(ctx.h, vtx.ctypes.data, stride, nv, None if idx is None else idx.ctypes.data,
+                                   0 if idx is None else idx.dtype.itemsize, 0 if idx is None else idx.shape[0], C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().u3d_mesh_destroy(self.h)
+            self.h = None
+
+
+class Occluders:
+    def __init__(self, ctx, world_aabb6, model12, meshes, mesh_of=None, start=None, count=None, cull_mode=CULL_CCW):
+        h = _vp()
+        a, m = _arr(world_aabb6, np.float32), _arr(model12, np.float32)
+        n = a.shape[0] if a is not None else 0
+        arr = (_vp * max(len(meshes), 1))(*[x.h for x in meshes])
+        mo, st, ct = _arr(mesh_of, np.uint32), _arr(start, np.uint32), _arr(count, np.uint32)
+        _chk(lib().u3d_occluders_create(ctx.h, n, _p(a, _f), _p(m, _f), arr, len(meshes), _p(mo, _u32), _p(st, _u32), _p(ct, _u32), cull_mode,
+                                        C.byref(h)))
+        self.h = h
+        self.n = n
+
+    def close(self):
+        if self.h:
+            lib().u3d_occluders_destroy(self.h)
+            self.h = None
+
+
+class OcclusionBuffer:
+    """Mirror of class OcclusionBuffer (OcclusionBuffer.h:91-226) over the C-ABI: same method names, argument meaning and returns."""
+
+    def __init__(self, ctx):
+        h = _vp()
+        _chk(lib().u3d_ob_create(ctx.h, C.byref(h)))
+        self.h = h
+        self._keep = []
+
+    def SetSize(self, width, height, threaded=False):
+        return bool(_chk(lib().u3d_ob_set_size(self.h, width, height, int(threaded))))
+
+    def SetView(self, v):
+        """v: urho3d_b200.camera.CameraView (what Camera::GetView/GetProjection/GetNearClip/GetFarClip/GetReverseCulling give)."""
+        _chk(lib().u3d_ob_set_view(self.h, _p(v.view, _f), _p(v.proj, _f), v.near, v.far, int(v.reverse_culling)))
+
+    def SetMaxTriangles(self, n):
+        _chk(lib().u3d_ob_set_max_triangles(self.h, n))
+
+    def SetCullMode(self, mode):
+        _chk(lib().u3d_ob_set_cull_mode(self.h, mode))
+
+    def Reset(self):
+        _chk(lib().u3d_ob_reset(self.h))
+        self._keep = []
+
+    def Clear(self):
+        _chk(lib().u3d_ob_clear(self.h))
+        self._keep = []
+
+    def AddTriangles(self, model12, vtx, vtx_size, idx=None, start=0, count=0):
+        model12 = _arr(model12, np.float32)
+        self._keep += [vtx, idx]
+        if idx is None:
+            return bool(_chk(lib().u3d_ob_add_triangles(self.h, _p(model12, _f), vtx.ctypes.data, vtx_size, start, count)))
+        return bool(_chk(lib().u3d_ob_add_triangles_indexed(self.h, _p(model12, _f), vtx.ctypes.data, vtx_size, idx.ctypes.data,
+                                                            idx.dtype.itemsize, start, count)))
+
+    def AddTrianglesMesh(self, model12, mesh, start, count):
+        model12 = _arr(model12, np.float32)
+        return bool(_chk(lib().u3d_ob_add_triangles_mesh(self.h, _p(model12, _f), mesh.h, start, count)))
+
+    def DrawTriangles(self):
+        _chk(lib().u3d_ob_draw_triangles(self.h))
+        self._keep = []
+
+    def BuildDepthHierarchy(self):
+        _chk(lib().u3d_ob_build_depth_hierarchy(self.h))
+
+    def IsVisible(self, aabb6):
+        b = _arr(aabb6, np.float32)
+        return bool(_chk(lib().u3d_ob_is_visible(self.h, _p(b, _f))))
+
+    def IsVisibleMany(self, aabb6):
+        b = _arr(aabb6, np.float32).reshape(-1, 6)
+        out = np.zeros(b.shape[0], np.uint8)
+        _chk(lib().u3d_ob_is_visible_many(self.h, _p(b, _f), b.shape[0], _p(out, _u8)))
+        return out
+
+    def GetBuffer(self):
+        out = np.zeros((self.GetHeight(), self.GetWidth()), np.int32)
+        _chk(lib().u3d_ob_get_buffer(self.h, _p(out, _i32)))
+        return out
+
+    def GetMips(self):
+        res = []
+        for lv in range(lib().u3d_ob_num_levels(self.h)):
+            w, h = C.c_int(), C.c_int()
+            _chk(lib().u3d_ob_mip_size(self.h, lv, C.byref(w), C.byref(h)))
+            out = np.zeros((h.value, w.value, 2), np.int32)
+            _chk(lib().u3d_ob_get_mip(self.h, lv, _p(out, _i32)))
+            res.append(out)
+        return res
+
+    def GetWidth(self):
+        return lib().u3d_ob_get_width(self.h)
+
+    def GetHeight(self):
+        return lib().u3d_ob_get_height(self.h)
+
+    def GetNumTriangles(self):
+        return lib().u3d_ob_get_num_triangles(self.h)
+
+    def GetMaxTriangles(self):
+        return lib().u3d_ob_get_max_triangles(self.h)
+
+    def GetCullMode(self):
+        return lib().u3d_ob_get_cull_mode(self.h)
+
+    def IsThreaded(self):
+        return bool(lib().u3d_ob_is_threaded(self.h))
+
+    def GetViewProj(self):
+        out = np.zeros((4, 4), np.float32)
+        _chk(lib().u3d_ob_get_view_proj(self.h, _p(out, _f)))
+        return out
+
+    def close(self):
+        if self.h:
+            lib().u3d_ob_destroy(self.h)
+            self.h = None
+
+
+def pack_views(views, flags=0xFF, view_mask=0xFFFFFFFF, query_mode=QUERY_OCCLUDED, use_occlusion=True):
+    """list of camera.CameraView -> numpy array of struct u3d_view."""
+    out = np.zeros(len(views), VIEW_DTYPE)
+    for i, v in enumerate(views):
+        out[i]["view"] = v.view.reshape(-1)
+        out[i]["projection"] = v.proj.reshape(-1)
+        out[i]["planes"] = v.planes.reshape(-1)
+        out[i]["near_clip"] = v.near
+        out[i]["far_clip"] = v.far
+        out[i]["reverse_culling"] = int(v.reverse_culling)
+    out["drawable_flags"] = flags
+    out["view_mask"] = view_mask
+    out["query_mode"] = query_mode
+    out["use_occlusion"] = int(use_occlusion)
+    return out
+
+
+class Batch:
+    """The batched many-view entry point."""
+
+    def __init__(self, ctx, scene, occluders, width, height, max_views, out_capacity, tri_pool=0):
+        h = _vp()
+        _chk(lib().u3d_batch_create(ctx.h, scene.h, occluders.h if occluders is not None else None, width, height, max_views, out_capacity,
+                                    tri_pool, C.byref(h)))
+        self.h = h
+        self.ctx = ctx
+        self.width, self.height = width, height + (height & 1)
+        self.max_views = max_views
+        self.out_capacity = out_capacity
+        self.n = 0
+
+    def set_views(self, packed, stream=None):
+        packed = np.ascontiguousarray(packed)
+        self._views = packed
+        self.n = packed.shape[0]
+        _chk(lib().u3d_batch_set_views(self.h, packed.ctypes.data, self.n, stream))
+
+    def run(self, stage=STAGE_VISIBLE, stream=None, part=0):
+        _chk(lib().u3d_batch_run_part(self.h, part, stage, stream))
+
+    def counts(self, stream=None):
+        out = np.zeros((self.n, 2), np.uint32)
+        _chk(lib().u3d_batch_read_counts(self.h, _p(out, _u32), stream))
+        return out
+
+    def packed(self, stream=None, capacity=None):
+        cap = self.n * self.out_capacity if capacity is None else capacity
+        off = np.zeros(self.n + 1, np.uint32)
+        ids = np.zeros(max(cap, 1), np.uint32)
+        _chk(lib().u3d_batch_read_packed(self.h, _p(off, _u32), _p(ids, _u32), cap, stream))
+        return off, ids[:off[-1]]
+
+    def cull_views(self, packed, stage=STAGE_VISIBLE, stream=None, counts=None, offsets=None, ids=None):
+        """One C-ABI call with host buffers in and out (the e2e path)."""
+        packed = np.ascontiguousarray(packed)
+        self.n = packed.shape[0]
+        counts = np.zeros((self.n, 2), np.uint32) if counts is None else counts
+        offsets = np.zeros(self.n + 1, np.uint32) if offsets is None else offsets
+        ids = np.zeros(max(self.n * self.out_capacity, 1), np.uint32) if ids is None else ids
+        _chk(lib().u3d_batch_cull_views(self.h, packed.ctypes.data, self.n, stage, _p(counts, _u32), _p(offsets, _u32), _p(ids, _u32), ids.shape[0],
+                                        stream))
+        return counts, offsets, ids
+
+    def view_ids(self, view, stream=None):
+        out = np.zeros(max(self.out_capacity, 1), np.uint32)
+        c = C.c_uint32()
+        _chk(lib().u3d_batch_read_view(self.h, view, _p(out, _u32), self.out_capacity, C.byref(c), stream))
+        return out[:min(c.value, self.out_capacity)].astype(np.int64)
+
+    def depth(self, view, stream=None):
+        out = np.zeros((self.height, self.width), np.int32)
+        _chk(lib().u3d_batch_read_depth(self.h, view, _p(out, _i32), stream))
+        return out
+
+    def mips(self, view, stream=None):
+        res = []
+        w, h = self.width, self.height
+        while True:
+            w, h = (w + 1) // 2, (h + 1) // 2
+            out = np.zeros((h, w, 2), np.int32)
+            _chk(lib().u3d_batch_read_mip(self.h, view, len(res), _p(out, _i32), stream))
+            res.append(out)
+            if w <= 8 and h <= 8:
+                break
+        return res
+
+    def tri_stats(self, stream=None):
+        out = np.zeros((self.n, 3), np.uint32)
+        _chk(lib().u3d_batch_read_tri_stats(self.h, _p(out, _u32), stream))
+        return out
+
+    def last_launches(self):
+        return lib().u3d_batch_last_launches(self.h)
+
+    def close(self):
+        if self.h:
+            lib().u3d_batch_destroy(self.h)
+            self.h = None

@@ -1,0 +1,1480 @@
+// C-ABI layer of libu3dgpu.so (include/u3d_gpu.h): object lifetimes, device memory, host<->device staging and kernel sequencing.
+// No CPU fallback anywhere: every compute entry point launches the sm_100a kernels of raster.cu / cull.cu or fails.
+#include "../../include/u3d_gpu.h"
+#include "u3d_host.h"
+#include "u3d_kernels.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace u3d;
+
+static thread_local std::string g_err;
+
+static int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return -code;
+}
+
+#define CU_CHECK(expr)                                                                                                   \
+    do                                                                                                                   \
+    {                                                                                                                    \
+        cudaError_t e_ = (expr);                                                                                         \
+        if (e_ != cudaSuccess)                                                                                           \
+            return fail(U3D_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));                               \
+    } while (0)
+
+namespace
+{
+
+/// Owning device buffer (grow-only helper).
+template <class T> struct DevBuf
+{
+    T* p{};
+    size_t n{};
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p)
+            cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n)
+            return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess)
+            n = count;
+        return e;
+    }
+};
+
+template <class T> struct PinnedBuf
+{
+    T* p{};
+    size_t n{};
+    ~PinnedBuf()
+    {
+        if (p)
+            cudaFreeHost(p);
+    }
+    cudaError_t ensure(size_t count)
+    {
+        if (count <= n)
+            return cudaSuccess;
+        if (p)
+            cudaFreeHost(p);
+        p = nullptr;
+        n = 0;
+        cudaError_t e = cudaMallocHost((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+        if (e == cudaSuccess)
+            n = count;
+        return e;
+    }
+};
+
+BufGeom make_geom(int w, int h)
+{
+    BufGeom g{};
+    g.w = w;
+    g.h = h;
+    int off = 0;
+    int lw = w, lh = h;
+    for (;;) // OB.cpp:97-106
+    {
+        lw = (lw + 1) / 2;
+        lh = (lh + 1) / 2;
+        g.mw[g.nlev] = lw;
+        g.mh[g.nlev] = lh;
+        g.moff[g.nlev] = off;
+        off += lw * lh;
+        ++g.nlev;
+        if ((lw <= kMinMip && lh <= kMinMip) || g.nlev == kMaxLevels)
+            break;
+    }
+    g.mipTexels = off;
+    g.sx = 0.5f * w; // CalculateViewport, OB.cpp:578-587
+    g.sy = -0.5f * h;
+    g.ox = 0.5f * w + 0.5f;
+    g.oy = 0.5f * h + 0.5f;
+    return g;
+}
+
+/// viewProj_ = projection_ * view_  (Matrix4 * Matrix3x4, Matrix4.cpp:43-63).  Host code is built with -ffp-contract=off.
+void mul_proj_view(const float* a, const float* b, float* o)
+{
+    for (int r = 0; r < 4; ++r)
+    {
+        const float* ar = a + 4 * r;
+        for (int c = 0; c < 3; ++c)
+            o[4 * r + c] = ar[0] * b[c] + ar[1] * b[4 + c] + ar[2] * b[8 + c];
+        o[4 * r + 3] = ar[0] * b[3] + ar[1] * b[7] + ar[2] * b[11] + ar[3];
+    }
+}
+
+int flip_cull(int mode, bool reverse) // SetCullMode, OB.cpp:134-144
+{
+    if (reverse)
+    {
+        if (mode == CULL_CW)
+            return CULL_CCW;
+        if (mode == CULL_CCW)
+            return CULL_CW;
+    }
+    return mode;
+}
+
+} // namespace
+
+struct u3d_ctx
+{
+    int device{};
+    cudaStream_t stream{};
+    cudaStream_t pick(void* s) const { return s ? (cudaStream_t)s : stream; }
+};
+
+struct u3d_octree
+{
+    HostOctree tree;
+    u3d_octree(const float* mn, const float* mx, unsigned lv) : tree(mn, mx, lv) {}
+};
+
+struct u3d_scene
+{
+    u3d_ctx* ctx{};
+    SceneDev dev{};
+    DevBuf<float4> octMin, octMax, drwMin, drwMax;
+    DevBuf<int> octCount, bfs, levelStart;
+    DevBuf<uint32_t> drwId;
+};
+
+struct u3d_mesh
+{
+    u3d_ctx* ctx{};
+    DevBuf<unsigned char> vtx;
+    DevBuf<unsigned char> idx;
+    uint32_t stride{}, vertexCount{}, idxSize{}, idxCount{};
+    MeshDev dev() const { return MeshDev{vtx.p, idxSize ? (const void*)idx.p : nullptr, stride, idxSize}; }
+};
+
+struct u3d_occluders
+{
+    u3d_ctx* ctx{};
+    uint32_t n{};
+    int cullMode{CULL_CCW};
+    uint32_t totalItems{};
+    uint64_t totalTris{};
+    DevBuf<float> aabb6, model12;
+    DevBuf<uint32_t> mesh, start, count;
+    DevBuf<MeshDev> meshTable;
+};
+
+/// Device state shared by the single-buffer object and the batched pipeline.
+struct ViewSet
+{
+    u3d_ctx* ctx{};
+    BufGeom g{};
+    uint32_t maxViews{};
+    DevBuf<ViewConst> views;
+    DevBuf<int> depth;
+    DevBuf<int2> mips;
+    DevBuf<uint32_t> itemCount, submitted, triCap, triCount, drawnSources, flags;
+    DevBuf<uint64_t> triBase;
+    DevBuf<TriSetup> pool;
+    DevBuf<DrawItem> items;
+    uint32_t itemCap{};
+    int alloc(u3d_ctx* c, int w, int h, uint32_t nviews, uint32_t itemCapPerView, uint64_t poolTris)
+    {
+        ctx = c;
+        g = make_geom(w, h);
+        maxViews = nviews;
+        itemCap = itemCapPerView;
+        CU_CHECK(views.ensure(nviews));
+        CU_CHECK(depth.ensure((size_t)nviews * w * h));
+        CU_CHECK(mips.ensure((size_t)nviews * g.mipTexels));
+        CU_CHECK(itemCount.ensure(nviews));
+        CU_CHECK(submitted.ensure(nviews));
+        CU_CHECK(triCap.ensure(nviews));
+        CU_CHECK(triCount.ensure(nviews));
+        CU_CHECK(drawnSources.ensure(nviews));
+        CU_CHECK(triBase.ensure(nviews));
+        CU_CHECK(flags.ensure(1));
+        CU_CHECK(items.ensure((size_t)nviews * std::max<uint32_t>(itemCap, 1)));
+        CU_CHECK(pool.ensure(std::max<uint64_t>(poolTris, 1)));
+        return 0;
+    }
+};
+
+struct HostBatchRec
+{
+    float model[12];
+    const void* vtx;
+    uint32_t vtxSize;
+    const void* idx;
+    uint32_t idxSize;
+    uint32_t start, count;
+    const u3d_mesh* mesh;
+};
+
+struct u3d_ob
+{
+    u3d_ctx* ctx{};
+    ViewSet vs;
+    bool allocated{};
+    int width{}, height{};
+    bool threaded{};
+    float view[12]{}, proj[16]{}, viewProj[16]{};
+    float nearClip{}, farClip{};
+    bool reverseCulling{};
+    int cullMode{CULL_CCW};
+    uint32_t numTriangles{}, maxTriangles{5000}; // OCCLUSION_DEFAULT_MAX_TRIANGLES, OB.h:84
+    bool hierarchyDirty{true};
+    std::vector<HostBatchRec> batches;
+    // per-draw staging
+    DevBuf<unsigned char> geom;
+    DevBuf<float> models;
+    DevBuf<MeshDev> meshTable;
+    DevBuf<float> boxes;
+    DevBuf<unsigned char> visOut;
+    // query scratch
+    DevBuf<unsigned char> octState;
+    DevBuf<uint32_t> outIdx, outCounts;
+};
+
+struct u3d_batch
+{
+    u3d_ctx* ctx{};
+    u3d_scene* scene{};
+    u3d_occluders* occ{};
+    ViewSet vs;
+    uint32_t numViews{};
+    uint32_t outCap{};
+    uint64_t poolTris{};
+    DevBuf<unsigned char> octState;
+    DevBuf<uint32_t> outIdx, outCounts, packOffsets, packed;
+    PinnedBuf<ViewConst> hostViews;
+    PinnedBuf<uint32_t> hostCounts;
+    uint32_t lastLaunches{};
+    bool hasBuffers{};
+};
+
+// -----------------------------------------------------------------------------------------------------------------------------
+extern "C"
+{
+
+const char* u3d_last_error(void) { return g_err.c_str(); }
+int u3d_abi_version(void) { return 1; }
+
+int u3d_ctx_create(int device, u3d_ctx** out)
+{
+    if (!out)
+        return fail(U3D_ERR_INVALID, "u3d_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0)
+        return fail(U3D_ERR_NO_DEVICE, std::string("no CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU path");
+    if (device < 0 || device >= count)
+        return fail(U3D_ERR_INVALID, "u3d_ctx_create: bad device index");
+    cudaDeviceProp prop{};
+    CU_CHECK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(U3D_ERR_NO_DEVICE, std::string("device is sm_") + std::to_string(prop.major * 10 + prop.minor) + "; kernels are built for sm_100a only");
+    CU_CHECK(cudaSetDevice(device));
+    u3d_ctx* c = new (std::nothrow) u3d_ctx();
+    if (!c)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    c->device = device;
+    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess)
+    {
+        delete c;
+        return fail(U3D_ERR_CUDA, std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    *out = c;
+    return U3D_OK;
+}
+
+void u3d_ctx_destroy(u3d_ctx* ctx)
+{
+    if (!ctx)
+        return;
+    cudaSetDevice(ctx->device);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int u3d_ctx_device(const u3d_ctx* ctx) { return ctx ? ctx->device : -U3D_ERR_INVALID; }
+
+int u3d_ctx_synchronize(u3d_ctx* ctx, void* stream)
+{
+    if (!ctx)
+        return fail(U3D_ERR_INVALID, "ctx is NULL");
+    CU_CHECK(cudaSetDevice(ctx->device));
+    CU_CHECK(cudaStreamSynchronize(ctx->pick(stream)));
+    return U3D_OK;
+}
+
+// ---- host octree ------------------------------------------------------------------------------------------------------------
+int u3d_octree_create(const float min3[3], const float max3[3], uint32_t levels, u3d_octree** out)
+{
+    if (!min3 || !max3 || !out)
+        return fail(U3D_ERR_INVALID, "u3d_octree_create: NULL argument");
+    *out = new (std::nothrow) u3d_octree(min3, max3, levels);
+    return *out ? U3D_OK : fail(U3D_ERR_NOMEM, "out of host memory");
+}
+
+void u3d_octree_destroy(u3d_octree* t) { delete t; }
+
+int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask, const uint8_t* occludee,
+    const uint8_t* cast_shadows, uint32_t* first_id)
+{
+    if (!t || (n && !aabb6))
+        return fail(U3D_ERR_INVALID, "u3d_octree_add: NULL argument");
+    uint32_t first = (uint32_t)t->tree.Drawables().size();
+    for (uint32_t i = 0; i < n; ++i)
+        t->tree.AddDrawable(aabb6 + 6 * (size_t)i, drawable_flags ? drawable_flags[i] : (uint8_t)1, view_mask ? view_mask[i] : 0xFFFFFFFFu,
+            occludee ? occludee[i] != 0 : true, cast_shadows ? cast_shadows[i] != 0 : false);
+    if (first_id)
+        *first_id = first;
+    return U3D_OK;
+}
+
+int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6])
+{
+    if (!t || !aabb6)
+        return fail(U3D_ERR_INVALID, "u3d_octree_update: NULL argument");
+    return t->tree.UpdateDrawable(id, aabb6) ? U3D_OK : fail(U3D_ERR_INVALID, "u3d_octree_update: unknown drawable id");
+}
+
+int u3d_octree_remove(u3d_octree* t, uint32_t id)
+{
+    if (!t)
+        return fail(U3D_ERR_INVALID, "u3d_octree_remove: NULL argument");
+    return t->tree.RemoveDrawable(id) ? U3D_OK : fail(U3D_ERR_INVALID, "u3d_octree_remove: unknown drawable id");
+}
+
+int u3d_octree_counts(const u3d_octree* t, uint32_t* num_octants, uint32_t* num_drawables_in_tree)
+{
+    if (!t)
+        return fail(U3D_ERR_INVALID, "u3d_octree_counts: NULL argument");
+    FlatOctree f;
+    t->tree.Flatten(f);
+    if (num_octants)
+        *num_octants = (uint32_t)f.parent.size();
+    if (num_drawables_in_tree)
+        *num_drawables_in_tree = (uint32_t)f.order.size();
+    return U3D_OK;
+}
+
+int u3d_octree_flatten(const u3d_octree* t, int32_t* parent, int32_t* level, float* culling_box6, int32_t* first, int32_t* count, int32_t* order)
+{
+    if (!t)
+        return fail(U3D_ERR_INVALID, "u3d_octree_flatten: NULL argument");
+    FlatOctree f;
+    t->tree.Flatten(f);
+    const size_t m = f.parent.size();
+    if (parent) std::memcpy(parent, f.parent.data(), m * sizeof(int));
+    if (level) std::memcpy(level, f.level.data(), m * sizeof(int));
+    if (culling_box6) std::memcpy(culling_box6, f.box6.data(), m * 6 * sizeof(float));
+    if (first) std::memcpy(first, f.first.data(), m * sizeof(int));
+    if (count) std::memcpy(count, f.count.data(), m * sizeof(int));
+    if (order) std::memcpy(order, f.order.data(), f.order.size() * sizeof(int));
+    return U3D_OK;
+}
+
+// ---- scene ------------------------------------------------------------------------------------------------------------------
+int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const int32_t* level, const float* box6, const int32_t* first,
+    const int32_t* count, uint32_t S, const int32_t* order, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask,
+    const uint8_t* occludee, const uint8_t* cast_shadows, u3d_scene** out)
+{
+    if (!ctx || !out || !M || !parent || !level || !box6 || !first || !count || (S && (!order || !aabb6)))
+        return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: NULL/empty argument");
+    *out = nullptr;
+    CU_CHECK(cudaSetDevice(ctx->device));
+    int maxLevel = 0;
+    for (uint32_t i = 0; i < M; ++i)
+    {
+        if (i && (parent[i] < 0 || parent[i] >= (int)i))
+            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: octants are not in DFS pre-order (parent must precede child)");
+        if (first[i] < 0 || count[i] < 0 || (uint64_t)first[i] + count[i] > S)
+            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: octant drawable range out of bounds");
+        maxLevel = std::max(maxLevel, level[i]);
+    }
+    std::vector<float4> omin(M), omax(M), dmin(std::max<uint32_t>(S, 1)), dmax(std::max<uint32_t>(S, 1));
+    std::vector<uint32_t> ids(std::max<uint32_t>(S, 1));
+    for (uint32_t i = 0; i < M; ++i)
+    {
+        const float* b = box6 + 6 * (size_t)i;
+        const int p = i ? parent[i] : -1;
+        omin[i] = make_float4(b[0], b[1], b[2], 0.f);
+        omax[i] = make_float4(b[3], b[4], b[5], 0.f);
+        std::memcpy(&omin[i].w, &p, 4);
+        std::memcpy(&omax[i].w, &first[i], 4);
+    }
+    for (uint32_t s = 0; s < S; ++s)
+    {
+        const uint32_t id = (uint32_t)order[s];
+        const float* b = aabb6 + 6 * (size_t)id;
+        uint32_t meta = drawable_flags ? drawable_flags[id] : 1u;
+        if (!occludee || occludee[id])
+            meta |= kMetaOccludee;
+        if (cast_shadows && cast_shadows[id])
+            meta |= kMetaCastShadows;
+        const uint32_t vm = view_mask ? view_mask[id] : 0xFFFFFFFFu;
+        dmin[s] = make_float4(b[0], b[1], b[2], 0.f);
+        dmax[s] = make_float4(b[3], b[4], b[5], 0.f);
+        std::memcpy(&dmin[s].w, &meta, 4);
+        std::memcpy(&dmax[s].w, &vm, 4);
+        ids[s] = id;
+    }
+    // octants sorted by level (stable): a child's parent is always resolved one sweep earlier
+    std::vector<int> levelStart(maxLevel + 2, 0), bfs(M);
+    for (uint32_t i = 0; i < M; ++i)
+        ++levelStart[level[i] + 1];
+    for (int l = 0; l <= maxLevel; ++l)
+        levelStart[l + 1] += levelStart[l];
+    {
+        std::vector<int> cur(levelStart.begin(), levelStart.end() - 1);
+        for (uint32_t i = 0; i < M; ++i)
+            bfs[cur[level[i]]++] = (int)i;
+    }
+    for (uint32_t i = 1; i < M; ++i)
+        if (level[parent[i]] >= level[i])
+            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: parent level must be smaller than child level");
+
+    u3d_scene* s = new (std::nothrow) u3d_scene();
+    if (!s)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    s->ctx = ctx;
+    auto up = [&](auto& buf, const auto& vec) -> cudaError_t {
+        cudaError_t e = buf.ensure(vec.size());
+        if (e != cudaSuccess)
+            return e;
+        return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
+    };
+    std::vector<int> cnt(count, count + M);
+    cudaError_t e = cudaSuccess;
+    if ((e = up(s->octMin, omin)) || (e = up(s->octMax, omax)) || (e = up(s->octCount, cnt)) || (e = up(s->bfs, bfs)) ||
+        (e = up(s->levelStart, levelStart)) || (e = up(s->drwMin, dmin)) || (e = up(s->drwMax, dmax)) || (e = up(s->drwId, ids)))
+    {
+        delete s;
+        return fail(U3D_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
+    }
+    s->dev.numOctants = (int)M;
+    s->dev.numDrawables = (int)S;
+    s->dev.numLevels = maxLevel + 1;
+    s->dev.octMin = s->octMin.p;
+    s->dev.octMax = s->octMax.p;
+    s->dev.octCount = s->octCount.p;
+    s->dev.bfs = s->bfs.p;
+    s->dev.levelStart = s->levelStart.p;
+    s->dev.drwMin = s->drwMin.p;
+    s->dev.drwMax = s->drwMax.p;
+    s->dev.drwId = s->drwId.p;
+    *out = s;
+    return U3D_OK;
+}
+
+int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
+{
+    if (!ctx || !t || !out)
+        return fail(U3D_ERR_INVALID, "u3d_scene_create: NULL argument");
+    FlatOctree f;
+    t->tree.Flatten(f);
+    const auto& dr = t->tree.Drawables();
+    const size_t n = dr.size();
+    std::vector<float> aabb(6 * std::max<size_t>(n, 1));
+    std::vector<uint8_t> fl(std::max<size_t>(n, 1)), oc(std::max<size_t>(n, 1)), cs(std::max<size_t>(n, 1));
+    std::vector<uint32_t> vm(std::max<size_t>(n, 1));
+    for (size_t i = 0; i < n; ++i)
+    {
+        std::memcpy(&aabb[6 * i], dr[i].box, sizeof(dr[i].box));
+        fl[i] = dr[i].flags;
+        vm[i] = dr[i].viewMask;
+        oc[i] = dr[i].occludee;
+        cs[i] = dr[i].castShadows;
+    }
+    return u3d_scene_create_flat(ctx, (uint32_t)f.parent.size(), f.parent.data(), f.level.data(), f.box6.data(), f.first.data(), f.count.data(),
+        (uint32_t)f.order.size(), f.order.data(), aabb.data(), fl.data(), vm.data(), oc.data(), cs.data(), out);
+}
+
+void u3d_scene_destroy(u3d_scene* s)
+{
+    if (!s)
+        return;
+    cudaSetDevice(s->ctx->device);
+    delete s;
+}
+
+int u3d_scene_counts(const u3d_scene* s, uint32_t* num_octants, uint32_t* num_drawables)
+{
+    if (!s)
+        return fail(U3D_ERR_INVALID, "u3d_scene_counts: NULL argument");
+    if (num_octants)
+        *num_octants = (uint32_t)s->dev.numOctants;
+    if (num_drawables)
+        *num_drawables = (uint32_t)s->dev.numDrawables;
+    return U3D_OK;
+}
+
+// ---- meshes / occluders -----------------------------------------------------------------------------------------------------
+int u3d_mesh_create(u3d_ctx* ctx, const void* vertices, uint32_t vertex_size, uint32_t vertex_count, const void* indices, uint32_t index_size,
+    uint32_t index_count, u3d_mesh** out)
+{
+    if (!ctx || !out || !vertices || vertex_size < 12 || !vertex_count)
+        return fail(U3D_ERR_INVALID, "u3d_mesh_create: bad vertex arguments (vertex_size must be >= 12)");
+    if (indices && index_size != 2 && index_size != 4)
+        return fail(U3D_ERR_INVALID, "u3d_mesh_create: index_size must be 2 or 4");
+    if ((vertex_size & 3) != 0)
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_mesh_create: vertex_size must be a multiple of 4 (float-aligned positions)");
+    *out = nullptr;
+    CU_CHECK(cudaSetDevice(ctx->device));
+    u3d_mesh* m = new (std::nothrow) u3d_mesh();
+    if (!m)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    m->ctx = ctx;
+    m->stride = vertex_size;
+    m->vertexCount = vertex_count;
+    // the reference reads 12 bytes per vertex; the last vertex need not be a full stride long
+    const size_t vbytes = (size_t)(vertex_count - 1) * vertex_size + 12;
+    cudaError_t e = m->vtx.ensure((size_t)vertex_count * vertex_size);
+    if (e == cudaSuccess)
+        e = cudaMemcpy(m->vtx.p, vertices, vbytes, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && indices)
+    {
+        m->idxSize = index_size;
+        m->idxCount = index_count;
+        e = m->idx.ensure((size_t)index_count * index_size);
+        if (e == cudaSuccess)
+            e = cudaMemcpy(m->idx.p, indices, (size_t)index_count * index_size, cudaMemcpyHostToDevice);
+    }
+    if (e != cudaSuccess)
+    {
+        delete m;
+        return fail(U3D_ERR_CUDA, std::string("mesh upload: ") + cudaGetErrorString(e));
+    }
+    *out = m;
+    return U3D_OK;
+}
+
+void u3d_mesh_destroy(u3d_mesh* m)
+{
+    if (!m)
+        return;
+    cudaSetDevice(m->ctx->device);
+    delete m;
+}
+
+int u3d_occluders_create(u3d_ctx* ctx, uint32_t n, const float* world_aabb6, const float* model12, u3d_mesh* const* meshes, uint32_t num_meshes,
+    const uint32_t* mesh_of_occluder, const uint32_t* index_start, const uint32_t* index_count, int cull_mode, u3d_occluders** out)
+{
+    if (!ctx || !out || (n && (!world_aabb6 || !model12 || !meshes || !num_meshes)))
+        return fail(U3D_ERR_INVALID, "u3d_occluders_create: NULL argument");
+    if (cull_mode < 0 || cull_mode > 2)
+        return fail(U3D_ERR_INVALID, "u3d_occluders_create: bad cull mode");
+    *out = nullptr;
+    CU_CHECK(cudaSetDevice(ctx->device));
+    std::vector<MeshDev> table(std::max<uint32_t>(num_meshes, 1));
+    for (uint32_t i = 0; i < num_meshes; ++i)
+    {
+        if (!meshes[i])
+            return fail(U3D_ERR_INVALID, "u3d_occluders_create: NULL mesh");
+        table[i] = meshes[i]->dev();
+    }
+    std::vector<uint32_t> mesh(std::max<uint32_t>(n, 1)), start(std::max<uint32_t>(n, 1)), count(std::max<uint32_t>(n, 1));
+    uint32_t totalItems = 0;
+    uint64_t totalTris = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t mi = mesh_of_occluder ? mesh_of_occluder[i] : 0;
+        if (mi >= num_meshes)
+            return fail(U3D_ERR_INVALID, "u3d_occluders_create: mesh index out of range");
+        const u3d_mesh* m = meshes[mi];
+        const uint32_t avail = m->idxSize ? m->idxCount : m->vertexCount;
+        const uint32_t st = index_start ? index_start[i] : 0;
+        const uint32_t ct = index_count ? index_count[i] : avail;
+        if ((uint64_t)st + ct > avail)
+            return fail(U3D_ERR_INVALID, "u3d_occluders_create: draw range exceeds the mesh");
+        mesh[i] = mi;
+        start[i] = st;
+        count[i] = ct;
+        const uint32_t tris = ct / 3;
+        totalTris += tris;
+        totalItems += (tris + kItemTris - 1) / kItemTris;
+    }
+    u3d_occluders* o = new (std::nothrow) u3d_occluders();
+    if (!o)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    o->ctx = ctx;
+    o->n = n;
+    o->cullMode = cull_mode;
+    o->totalItems = totalItems;
+    o->totalTris = totalTris;
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto& buf, const void* src, size_t count_, size_t elem) -> cudaError_t {
+        cudaError_t e2 = buf.ensure(std::max<size_t>(count_, 1));
+        if (e2 != cudaSuccess || !count_)
+            return e2;
+        return cudaMemcpy(buf.p, src, count_ * elem, cudaMemcpyHostToDevice);
+    };
+    if ((e = up(o->aabb6, world_aabb6, (size_t)n * 6, 4)) || (e = up(o->model12, model12, (size_t)n * 12, 4)) || (e = up(o->mesh, mesh.data(), n, 4)) ||
+        (e = up(o->start, start.data(), n, 4)) || (e = up(o->count, count.data(), n, 4)) ||
+        (e = up(o->meshTable, table.data(), table.size(), sizeof(MeshDev))))
+    {
+        delete o;
+        return fail(U3D_ERR_CUDA, std::string("occluder upload: ") + cudaGetErrorString(e));
+    }
+    *out = o;
+    return U3D_OK;
+}
+
+void u3d_occluders_destroy(u3d_occluders* o)
+{
+    if (!o)
+        return;
+    cudaSetDevice(o->ctx->device);
+    delete o;
+}
+
+// ---- OcclusionBuffer drop-in ------------------------------------------------------------------------------------------------
+int u3d_ob_create(u3d_ctx* ctx, u3d_ob** out)
+{
+    if (!ctx || !out)
+        return fail(U3D_ERR_INVALID, "u3d_ob_create: NULL argument");
+    u3d_ob* ob = new (std::nothrow) u3d_ob();
+    if (!ob)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    ob->ctx = ctx;
+    *out = ob;
+    return U3D_OK;
+}
+
+void u3d_ob_destroy(u3d_ob* ob)
+{
+    if (!ob)
+        return;
+    cudaSetDevice(ob->ctx->device);
+    delete ob;
+}
+
+static int ob_upload_view(u3d_ob* ob)
+{
+    if (!ob->allocated)
+        return U3D_OK;
+    ViewConst vc{};
+    std::memcpy(vc.vp, ob->viewProj, sizeof(vc.vp));
+    vc.drawableFlags = 0xFF;
+    vc.viewMask = 0xFFFFFFFFu;
+    vc.cullMode = ob->cullMode;
+    vc.queryMode = QUERY_OCCLUDED;
+    vc.useOcclusion = 1;
+    CU_CHECK(cudaMemcpyAsync(ob->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, ob->ctx->stream));
+    CU_CHECK(cudaStreamSynchronize(ob->ctx->stream)); // vc lives on this stack frame
+    return U3D_OK;
+}
+
+int u3d_ob_set_size(u3d_ob* ob, int width, int height, int threaded)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "u3d_ob_set_size: NULL argument");
+    if (height & 1) // OB.cpp:63-65
+        ++height;
+    if (width == ob->width && height == ob->height && ob->allocated)
+        return 1;
+    if (width <= 0 || height <= 0)
+        return 0;
+    if (width & (width - 1))
+    {
+        g_err = "Requested occlusion buffer width is not a power of two"; // OB.cpp:73-77
+        return 0;
+    }
+    if (width < 2 || width > 8192 || height > 16384)
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_ob_set_size: supported sizes are 2..8192 x 2..16384");
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    ob->width = width;
+    ob->height = height;
+    ob->threaded = threaded != 0;
+    int rc = ob->vs.alloc(ob->ctx, width, height, 1, 1, 1);
+    if (rc < 0)
+        return rc;
+    ob->allocated = true;
+    ob->hierarchyDirty = true;
+    return 1;
+}
+
+int u3d_ob_set_view(u3d_ob* ob, const float view12[12], const float projection16[16], float near_clip, float far_clip, int reverse_culling)
+{
+    if (!ob || !view12 || !projection16)
+        return fail(U3D_ERR_INVALID, "u3d_ob_set_view: NULL argument");
+    std::memcpy(ob->view, view12, sizeof(ob->view));
+    std::memcpy(ob->proj, projection16, sizeof(ob->proj));
+    mul_proj_view(ob->proj, ob->view, ob->viewProj);
+    ob->nearClip = near_clip;
+    ob->farClip = far_clip;
+    ob->reverseCulling = reverse_culling != 0;
+    return U3D_OK;
+}
+
+int u3d_ob_set_max_triangles(u3d_ob* ob, uint32_t triangles)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    ob->maxTriangles = triangles;
+    return U3D_OK;
+}
+
+int u3d_ob_set_cull_mode(u3d_ob* ob, int mode)
+{
+    if (!ob || mode < 0 || mode > 2)
+        return fail(U3D_ERR_INVALID, "u3d_ob_set_cull_mode: bad argument");
+    ob->cullMode = flip_cull(mode, ob->reverseCulling);
+    return U3D_OK;
+}
+
+int u3d_ob_reset(u3d_ob* ob)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    ob->numTriangles = 0;
+    ob->batches.clear();
+    return U3D_OK;
+}
+
+int u3d_ob_clear(u3d_ob* ob)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    ob->numTriangles = 0;
+    ob->batches.clear();
+    if (ob->allocated)
+    {
+        CU_CHECK(cudaSetDevice(ob->ctx->device));
+        launch_clear(ob->vs.depth.p, (size_t)ob->width * ob->height, ob->ctx->stream);
+        CU_CHECK(cudaGetLastError());
+    }
+    ob->hierarchyDirty = true;
+    return U3D_OK;
+}
+
+static int ob_push(u3d_ob* ob, const float* model, const void* vtx, uint32_t vsize, const void* idx, uint32_t isize, uint32_t start, uint32_t count,
+    const u3d_mesh* mesh)
+{
+    HostBatchRec r{};
+    std::memcpy(r.model, model, sizeof(r.model));
+    r.vtx = vtx;
+    r.vtxSize = vsize;
+    r.idx = idx;
+    r.idxSize = isize;
+    r.start = start;
+    r.count = count;
+    r.mesh = mesh;
+    ob->batches.push_back(r);
+    ob->numTriangles += count / 3;
+    return ob->numTriangles <= ob->maxTriangles ? 1 : 0;
+}
+
+int u3d_ob_add_triangles(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size, uint32_t vertex_start, uint32_t vertex_count)
+{
+    if (!ob || !model12 || !vertex_data)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles: NULL argument");
+    if (vertex_size < 12 || (vertex_size & 3))
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_ob_add_triangles: vertex_size must be >= 12 and a multiple of 4");
+    return ob_push(ob, model12, vertex_data, vertex_size, nullptr, 0, vertex_start, vertex_count, nullptr);
+}
+
+int u3d_ob_add_triangles_indexed(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size, const void* index_data,
+    uint32_t index_size, uint32_t index_start, uint32_t index_count)
+{
+    if (!ob || !model12 || !vertex_data || !index_data)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_indexed: NULL argument");
+    if (vertex_size < 12 || (vertex_size & 3))
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_ob_add_triangles_indexed: vertex_size must be >= 12 and a multiple of 4");
+    if (index_size != 2 && index_size != 4)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_indexed: index_size must be 2 or 4");
+    return ob_push(ob, model12, vertex_data, vertex_size, index_data, index_size, index_start, index_count, nullptr);
+}
+
+int u3d_ob_add_triangles_mesh(u3d_ob* ob, const float model12[12], const u3d_mesh* mesh, uint32_t start, uint32_t count)
+{
+    if (!ob || !model12 || !mesh)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_mesh: NULL argument");
+    const uint32_t avail = mesh->idxSize ? mesh->idxCount : mesh->vertexCount;
+    if ((uint64_t)start + count > avail)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_mesh: range exceeds the mesh");
+    return ob_push(ob, model12, nullptr, mesh->stride, nullptr, mesh->idxSize, start, count, mesh);
+}
+
+int u3d_ob_draw_triangles(u3d_ob* ob)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    if (!ob->allocated || ob->batches.empty())
+    {
+        ob->batches.clear(); // OB.cpp:231
+        return U3D_OK;
+    }
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    cudaStream_t st = ob->ctx->stream;
+    const size_t nb = ob->batches.size();
+
+    // Stage the caller's geometry: one contiguous blob = [vertex ranges][index ranges], deduplicated by host pointer.
+    struct VRange { size_t bytes; size_t offset; };
+    std::map<const void*, VRange> vranges;
+    std::vector<size_t> idxOffset(nb, 0);
+    size_t total = 0;
+    std::vector<uint32_t> tris(nb);
+    for (size_t i = 0; i < nb; ++i)
+    {
+        const HostBatchRec& r = ob->batches[i];
+        tris[i] = r.count / 3;
+        if (r.mesh || !tris[i])
+            continue;
+        uint32_t maxVertex = 0;
+        if (!r.idx)
+            maxVertex = r.start + 3 * tris[i] - 1;
+        else if (r.idxSize == 2)
+        {
+            const uint16_t* ix = (const uint16_t*)r.idx + r.start;
+            for (uint32_t k = 0; k < 3 * tris[i]; ++k)
+                maxVertex = std::max<uint32_t>(maxVertex, ix[k]);
+        }
+        else
+        {
+            const uint32_t* ix = (const uint32_t*)r.idx + r.start;
+            for (uint32_t k = 0; k < 3 * tris[i]; ++k)
+                maxVertex = std::max<uint32_t>(maxVertex, ix[k]);
+        }
+        const size_t need = (size_t)maxVertex * r.vtxSize + 12;
+        auto it = vranges.find(r.vtx);
+        if (it == vranges.end())
+            vranges[r.vtx] = VRange{need, 0};
+        else
+            it->second.bytes = std::max(it->second.bytes, need);
+    }
+    for (auto& kv : vranges)
+    {
+        kv.second.offset = total;
+        total += (kv.second.bytes + 15) & ~(size_t)15;
+    }
+    for (size_t i = 0; i < nb; ++i)
+    {
+        const HostBatchRec& r = ob->batches[i];
+        if (r.mesh || !r.idx || !tris[i])
+            continue;
+        idxOffset[i] = total;
+        total += ((size_t)3 * tris[i] * r.idxSize + 15) & ~(size_t)15;
+    }
+    std::vector<unsigned char> blob(std::max<size_t>(total, 16));
+    for (auto& kv : vranges)
+        std::memcpy(blob.data() + kv.second.offset, kv.first, kv.second.bytes);
+    for (size_t i = 0; i < nb; ++i)
+    {
+        const HostBatchRec& r = ob->batches[i];
+        if (r.mesh || !r.idx || !tris[i])
+            continue;
+        std::memcpy(blob.data() + idxOffset[i], (const unsigned char*)r.idx + (size_t)r.start * r.idxSize, (size_t)3 * tris[i] * r.idxSize);
+    }
+    CU_CHECK(ob->geom.ensure(blob.size()));
+    CU_CHECK(cudaMemcpyAsync(ob->geom.p, blob.data(), blob.size(), cudaMemcpyHostToDevice, st));
+
+    std::vector<float> models(nb * 12);
+    std::vector<MeshDev> table(nb);
+    std::vector<DrawItem> items;
+    uint64_t totalTris = 0;
+    for (size_t i = 0; i < nb; ++i)
+    {
+        const HostBatchRec& r = ob->batches[i];
+        std::memcpy(&models[12 * i], r.model, sizeof(r.model));
+        uint32_t start = r.start;
+        if (r.mesh)
+            table[i] = r.mesh->dev();
+        else if (tris[i])
+        {
+            table[i].vtx = ob->geom.p + vranges[r.vtx].offset;
+            table[i].stride = r.vtxSize;
+            table[i].idxSize = r.idxSize;
+            table[i].idx = r.idx ? (const void*)(ob->geom.p + idxOffset[i]) : nullptr;
+            if (r.idx)
+                start = 0; // staged index range begins at the batch's first index
+        }
+        for (uint32_t t0 = 0; t0 < tris[i]; t0 += kItemTris)
+        {
+            DrawItem it;
+            it.model = (uint32_t)i;
+            it.mesh = (uint32_t)i;
+            it.start = start + 3 * t0;
+            it.count = 3 * std::min<uint32_t>(tris[i] - t0, kItemTris);
+            items.push_back(it);
+        }
+        totalTris += tris[i];
+    }
+    ob->batches.clear(); // OB.cpp:231
+    if (items.empty())
+    {
+        CU_CHECK(cudaStreamSynchronize(st));
+        return U3D_OK;
+    }
+    ViewSet& vs = ob->vs;
+    CU_CHECK(ob->models.ensure(models.size()));
+    CU_CHECK(ob->meshTable.ensure(table.size()));
+    CU_CHECK(vs.items.ensure(items.size()));
+    vs.itemCap = (uint32_t)items.size();
+    // every source triangle can be clipped into several; grow on overflow
+    uint64_t poolTris = totalTris + totalTris / 2 + 256;
+    for (int attempt = 0; attempt < 8; ++attempt)
+    {
+        CU_CHECK(vs.pool.ensure(poolTris));
+        CU_CHECK(cudaMemcpyAsync(ob->models.p, models.data(), models.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemcpyAsync(ob->meshTable.p, table.data(), table.size() * sizeof(MeshDev), cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemcpyAsync(vs.items.p, items.data(), items.size() * sizeof(DrawItem), cudaMemcpyHostToDevice, st));
+        const uint32_t nItems = (uint32_t)items.size();
+        const uint32_t cap = (uint32_t)std::min<uint64_t>(poolTris, 0xFFFFFFFFu);
+        const uint64_t zero64 = 0;
+        CU_CHECK(cudaMemcpyAsync(vs.itemCount.p, &nItems, 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemcpyAsync(vs.triCap.p, &cap, 4, cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemcpyAsync(vs.triBase.p, &zero64, 8, cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
+        int rc = ob_upload_view(ob); // cullMode_ is read at draw time (OB.cpp:634)
+        if (rc < 0)
+            return rc;
+        launch_setup(vs.g, vs.views.p, 1, vs.items.p, vs.itemCap, nItems, vs.itemCount.p, ob->models.p, ob->meshTable.p, vs.pool.p, vs.triBase.p,
+            vs.triCap.p, vs.triCount.p, vs.drawnSources.p, vs.flags.p, st);
+        CU_CHECK(cudaGetLastError());
+        uint32_t res[3] = {0, 0, 0};
+        CU_CHECK(cudaMemcpyAsync(&res[0], vs.triCount.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemcpyAsync(&res[1], vs.drawnSources.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaMemcpyAsync(&res[2], vs.flags.p, 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+        if (res[2] & kFlagTriOverflow)
+        {
+            poolTris = (uint64_t)res[0] + 256; // exact requirement is known now
+            continue;
+        }
+        launch_fill_global(vs.g, 1, vs.depth.p, vs.pool.p, vs.triBase.p, vs.triCap.p, vs.triCount.p, 148 * 2, st);
+        CU_CHECK(cudaGetLastError());
+        CU_CHECK(cudaStreamSynchronize(st));
+        ob->numTriangles += res[1]; // ++numTriangles_ per drawn source triangle, OB.cpp:681-682
+        ob->hierarchyDirty = true;
+        return U3D_OK;
+    }
+    return fail(U3D_ERR_CAPACITY, "u3d_ob_draw_triangles: triangle pool kept overflowing");
+}
+
+int u3d_ob_build_depth_hierarchy(u3d_ob* ob)
+{
+    if (!ob)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    if (!ob->allocated || !ob->hierarchyDirty) // OB.cpp:236
+        return U3D_OK;
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    launch_hierarchy(ob->vs.g, 1, ob->vs.depth.p, ob->vs.mips.p, ob->ctx->stream);
+    CU_CHECK(cudaGetLastError());
+    ob->hierarchyDirty = false;
+    return U3D_OK;
+}
+
+int u3d_ob_is_visible_many(u3d_ob* ob, const float* aabb6, uint32_t n, uint8_t* out)
+{
+    if (!ob || (n && (!aabb6 || !out)))
+        return fail(U3D_ERR_INVALID, "u3d_ob_is_visible_many: NULL argument");
+    if (!ob->allocated) // OB.cpp:338-339
+    {
+        std::memset(out, 1, n);
+        return U3D_OK;
+    }
+    if (!n)
+        return U3D_OK;
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    cudaStream_t st = ob->ctx->stream;
+    int rc = ob_upload_view(ob);
+    if (rc < 0)
+        return rc;
+    CU_CHECK(ob->boxes.ensure((size_t)n * 6));
+    CU_CHECK(ob->visOut.ensure(n));
+    CU_CHECK(cudaMemcpyAsync(ob->boxes.p, aabb6, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    launch_is_visible(ob->vs.g, ob->vs.views.p, ob->vs.depth.p, ob->vs.mips.p, ob->hierarchyDirty ? 0 : 1, ob->boxes.p, (int)n, ob->visOut.p, st);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(out, ob->visOut.p, n, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    return U3D_OK;
+}
+
+int u3d_ob_is_visible(u3d_ob* ob, const float aabb6[6])
+{
+    uint8_t r = 1;
+    int rc = u3d_ob_is_visible_many(ob, aabb6, 1, &r);
+    return rc < 0 ? rc : (int)r;
+}
+
+int u3d_ob_get_buffer(u3d_ob* ob, int32_t* out_depth)
+{
+    if (!ob || !out_depth || !ob->allocated)
+        return fail(U3D_ERR_INVALID, "u3d_ob_get_buffer: NULL argument or no buffer");
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    CU_CHECK(cudaMemcpyAsync(out_depth, ob->vs.depth.p, (size_t)ob->width * ob->height * 4, cudaMemcpyDeviceToHost, ob->ctx->stream));
+    CU_CHECK(cudaStreamSynchronize(ob->ctx->stream));
+    return U3D_OK;
+}
+
+int u3d_ob_get_mip(u3d_ob* ob, int level, int32_t* out_minmax)
+{
+    if (!ob || !out_minmax || !ob->allocated || level < 0 || level >= ob->vs.g.nlev)
+        return fail(U3D_ERR_INVALID, "u3d_ob_get_mip: bad argument");
+    CU_CHECK(cudaSetDevice(ob->ctx->device));
+    const BufGeom& g = ob->vs.g;
+    CU_CHECK(cudaMemcpyAsync(out_minmax, ob->vs.mips.p + g.moff[level], (size_t)g.mw[level] * g.mh[level] * 8, cudaMemcpyDeviceToHost, ob->ctx->stream));
+    CU_CHECK(cudaStreamSynchronize(ob->ctx->stream));
+    return U3D_OK;
+}
+
+int u3d_ob_num_levels(const u3d_ob* ob) { return ob && ob->allocated ? ob->vs.g.nlev : 0; }
+
+int u3d_ob_mip_size(const u3d_ob* ob, int level, int* width, int* height)
+{
+    if (!ob || !ob->allocated || level < 0 || level >= ob->vs.g.nlev)
+        return fail(U3D_ERR_INVALID, "u3d_ob_mip_size: bad argument");
+    if (width) *width = ob->vs.g.mw[level];
+    if (height) *height = ob->vs.g.mh[level];
+    return U3D_OK;
+}
+
+int u3d_ob_get_width(const u3d_ob* ob) { return ob ? ob->width : 0; }
+int u3d_ob_get_height(const u3d_ob* ob) { return ob ? ob->height : 0; }
+uint32_t u3d_ob_get_num_triangles(const u3d_ob* ob) { return ob ? ob->numTriangles : 0; }
+uint32_t u3d_ob_get_max_triangles(const u3d_ob* ob) { return ob ? ob->maxTriangles : 0; }
+int u3d_ob_get_cull_mode(const u3d_ob* ob) { return ob ? ob->cullMode : 0; }
+int u3d_ob_is_threaded(const u3d_ob* ob) { return ob ? (int)ob->threaded : 0; }
+
+int u3d_ob_get_view_proj(const u3d_ob* ob, float out16[16])
+{
+    if (!ob || !out16)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    std::memcpy(out16, ob->viewProj, sizeof(ob->viewProj));
+    return U3D_OK;
+}
+
+int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uint32_t drawable_flags, uint32_t view_mask, int query_mode, int stage,
+    uint32_t* out_ids, uint32_t capacity, uint32_t* out_query_count, uint32_t* out_count)
+{
+    if (!scene || !planes24 || (capacity && !out_ids))
+        return fail(U3D_ERR_INVALID, "u3d_octree_query: NULL argument");
+    if (query_mode < 0 || query_mode > 2 || stage < 0 || stage > 1)
+        return fail(U3D_ERR_INVALID, "u3d_octree_query: bad mode/stage");
+    u3d_ctx* ctx = scene->ctx;
+    CU_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const bool useOb = ob && ob->allocated;
+    if (query_mode == QUERY_OCCLUDED && !useOb)
+        return fail(U3D_ERR_INVALID, "u3d_octree_query: occluded query needs an occlusion buffer with a size");
+    // scratch lives in the ob when there is one, else in a temporary
+    u3d_ob tmp;
+    u3d_ob* holder = ob ? ob : &tmp;
+    holder->ctx = ctx;
+    ViewConst vc{};
+    if (useOb)
+        std::memcpy(vc.vp, ob->viewProj, sizeof(vc.vp));
+    std::memcpy(vc.planes, planes24, sizeof(vc.planes));
+    vc.drawableFlags = drawable_flags;
+    vc.viewMask = view_mask;
+    vc.cullMode = 0;
+    vc.queryMode = query_mode;
+    vc.useOcclusion = useOb ? 1 : 0;
+    BufGeom g = useOb ? ob->vs.g : make_geom(2, 2);
+    CU_CHECK(holder->vs.views.ensure(1));
+    CU_CHECK(holder->vs.flags.ensure(1));
+    CU_CHECK(holder->octState.ensure((size_t)scene->dev.numOctants));
+    CU_CHECK(holder->outIdx.ensure(std::max<uint32_t>(capacity, 1)));
+    CU_CHECK(holder->outCounts.ensure(2));
+    CU_CHECK(cudaMemcpyAsync(holder->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemsetAsync(holder->vs.flags.p, 0, 4, st));
+    launch_cull(scene->dev, g, holder->vs.views.p, 1, useOb ? ob->vs.depth.p : nullptr, useOb ? ob->vs.mips.p : nullptr,
+        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, holder->vs.flags.p, st);
+    CU_CHECK(cudaGetLastError());
+    uint32_t counts[2] = {0, 0};
+    CU_CHECK(cudaMemcpyAsync(counts, holder->outCounts.p, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    const uint32_t n = std::min(counts[1], capacity);
+    if (n)
+    {
+        CU_CHECK(cudaMemcpyAsync(out_ids, holder->outIdx.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
+    if (out_query_count)
+        *out_query_count = counts[0];
+    if (out_count)
+        *out_count = counts[1];
+    if (counts[1] > capacity)
+        return fail(U3D_ERR_CAPACITY, "u3d_octree_query: result larger than capacity");
+    return U3D_OK;
+}
+
+// ---- batched pipeline -------------------------------------------------------------------------------------------------------
+int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, int width, int height, uint32_t max_views, uint32_t out_capacity,
+    uint64_t tri_pool, u3d_batch** out)
+{
+    if (!ctx || !scene || !out || !max_views)
+        return fail(U3D_ERR_INVALID, "u3d_batch_create: NULL/zero argument");
+    if (max_views > 65535)
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_batch_create: at most 65535 views per batch object");
+    *out = nullptr;
+    const bool hasBuffers = occluders != nullptr;
+    if (hasBuffers)
+    {
+        if (height & 1)
+            ++height;
+        if (width < 2 || height < 2 || (width & (width - 1)) || width > 8192 || height > 16384)
+            return fail(U3D_ERR_INVALID, "u3d_batch_create: width must be a power of two in 2..8192, height in 2..16384");
+    }
+    else
+    {
+        width = 2;
+        height = 2;
+    }
+    CU_CHECK(cudaSetDevice(ctx->device));
+    u3d_batch* b = new (std::nothrow) u3d_batch();
+    if (!b)
+        return fail(U3D_ERR_NOMEM, "out of host memory");
+    b->ctx = ctx;
+    b->scene = scene;
+    b->occ = occluders;
+    b->outCap = out_capacity;
+    b->hasBuffers = hasBuffers;
+    const uint32_t itemCap = hasBuffers ? std::max<uint32_t>(occluders->totalItems, 1) : 1;
+    uint64_t pool = 1;
+    if (hasBuffers)
+    {
+        // worst case = every occluder of every view; default caps the pool at 2 GiB of records and relies on the overflow report
+        const uint64_t worst = (uint64_t)max_views * (occluders->totalTris + 64);
+        pool = tri_pool ? tri_pool : std::min<uint64_t>(worst, (2ull << 30) / sizeof(TriSetup));
+    }
+    b->poolTris = pool;
+    int rc = b->vs.alloc(ctx, width, height, hasBuffers ? max_views : 1, itemCap, pool);
+    cudaError_t e = cudaSuccess;
+    if (rc >= 0)
+    {
+        // ViewSet::alloc sized views for `nviews`; frustum-only batches still need max_views view constants
+        if ((e = b->vs.views.ensure(max_views)) || (e = b->octState.ensure((size_t)max_views * scene->dev.numOctants)) ||
+            (e = b->outIdx.ensure((size_t)max_views * std::max<uint32_t>(out_capacity, 1))) || (e = b->outCounts.ensure((size_t)max_views * 2)) ||
+            (e = b->packOffsets.ensure((size_t)max_views + 1)) || (e = b->hostViews.ensure(max_views)) || (e = b->hostCounts.ensure((size_t)max_views * 2 + 2)))
+            rc = fail(U3D_ERR_CUDA, std::string("u3d_batch_create: ") + cudaGetErrorString(e));
+    }
+    if (rc < 0)
+    {
+        delete b;
+        return rc;
+    }
+    b->vs.maxViews = max_views;
+    *out = b;
+    return U3D_OK;
+}
+
+void u3d_batch_destroy(u3d_batch* b)
+{
+    if (!b)
+        return;
+    cudaSetDevice(b->ctx->device);
+    delete b;
+}
+
+int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* stream)
+{
+    if (!b || (n && !views))
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_views: NULL argument");
+    if (n > b->vs.maxViews)
+        return fail(U3D_ERR_CAPACITY, "u3d_batch_set_views: more views than max_views");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    // the pinned staging array may still be in flight from the previous call on this stream
+    CU_CHECK(cudaStreamSynchronize(st));
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const u3d_view& v = views[i];
+        ViewConst& vc = b->hostViews.p[i];
+        mul_proj_view(v.projection, v.view, vc.vp);
+        std::memcpy(vc.planes, v.planes, sizeof(vc.planes));
+        vc.drawableFlags = v.drawable_flags;
+        vc.viewMask = v.view_mask;
+        vc.cullMode = flip_cull(b->occ ? b->occ->cullMode : CULL_CCW, v.reverse_culling != 0);
+        vc.queryMode = v.query_mode;
+        vc.useOcclusion = (v.use_occlusion && b->hasBuffers) ? 1 : 0;
+        if (vc.queryMode == QUERY_OCCLUDED && !vc.useOcclusion)
+            vc.queryMode = QUERY_FRUSTUM; // View.cpp:873-883: without a buffer the plain frustum query is used
+        vc.pad[0] = vc.pad[1] = vc.pad[2] = 0;
+    }
+    b->numViews = n;
+    if (n)
+        CU_CHECK(cudaMemcpyAsync(b->vs.views.p, b->hostViews.p, (size_t)n * sizeof(ViewConst), cudaMemcpyHostToDevice, st));
+    return U3D_OK;
+}
+
+int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
+{
+    if (!b || stage < 0 || stage > 1 || part < 0 || part > 2)
+        return fail(U3D_ERR_INVALID, "u3d_batch_run: bad argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const int V = (int)b->numViews;
+    b->lastLaunches = 0;
+    if (!V)
+        return U3D_OK;
+    ViewSet& vs = b->vs;
+    if (part != 2)
+        CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
+    if (b->hasBuffers && part != 2)
+    {
+        const u3d_occluders* oc = b->occ;
+        CU_CHECK(cudaMemsetAsync(vs.itemCount.p, 0, (size_t)V * 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.submitted.p, 0, (size_t)V * 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, (size_t)V * 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
+        launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
+        launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
+        launch_scan_regions(V, vs.submitted.p, 64, b->poolTris, vs.triBase.p, vs.triCap.p, vs.flags.p, st);
+        launch_setup(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, vs.pool.p, vs.triBase.p,
+            vs.triCap.p, vs.triCount.p, vs.drawnSources.p, vs.flags.p, st);
+        launch_fill_global(vs.g, V, vs.depth.p, vs.pool.p, vs.triBase.p, vs.triCap.p, vs.triCount.p, 8, st);
+        launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, st);
+        b->lastLaunches += 5 + (uint32_t)vs.g.nlev + (oc->n ? 0 : 0);
+        CU_CHECK(cudaGetLastError());
+    }
+    if (part != 1)
+    {
+        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, vs.flags.p, st);
+        b->lastLaunches += 1;
+        CU_CHECK(cudaGetLastError());
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_run(u3d_batch* b, int stage, void* stream) { return u3d_batch_run_part(b, 0, stage, stream); }
+
+static int batch_check_flags(u3d_batch* b, cudaStream_t st)
+{
+    uint32_t flags = 0;
+    CU_CHECK(cudaMemcpyAsync(&flags, b->vs.flags.p, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (flags & (kFlagTriOverflow | kFlagPoolOverflow))
+        return fail(U3D_ERR_CAPACITY, "triangle pool too small for this batch: recreate the batch with a larger tri_pool");
+    if (flags & kFlagOutOverflow)
+        return fail(U3D_ERR_CAPACITY, "a view produced more results than out_capacity");
+    return U3D_OK;
+}
+
+int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream)
+{
+    if (!b || !counts)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_counts: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    if (b->numViews)
+        CU_CHECK(cudaMemcpyAsync(counts, b->outCounts.p, (size_t)b->numViews * 8, cudaMemcpyDeviceToHost, st));
+    return batch_check_flags(b, st);
+}
+
+} // extern "C"
+
+namespace u3d
+{
+__global__ void k_pack_offsets(int numViews, const uint32_t* __restrict__ counts, uint32_t cap, uint32_t* __restrict__ offsets)
+{
+    // single block exclusive scan of min(count, cap)
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warpSum[32];
+    if (threadIdx.x == 0)
+        carry = 0;
+    __syncthreads();
+    for (int base = 0; base < numViews; base += blockDim.x)
+    {
+        const int v = base + threadIdx.x;
+        const uint32_t c = v < numViews ? min(counts[2 * v + 1], cap) : 0;
+        uint32_t x = c;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warpSum[wid] = x;
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i)
+        {
+            if (i < wid)
+                pre += warpSum[i];
+            tot += warpSum[i];
+        }
+        if (v < numViews)
+            offsets[v] = carry + pre + x - c;
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+        offsets[numViews] = carry;
+}
+
+__global__ void k_pack_ids(const uint32_t* __restrict__ counts, uint32_t cap, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ids,
+    uint32_t* __restrict__ packed)
+{
+    const int v = blockIdx.x;
+    const uint32_t n = min(counts[2 * v + 1], cap);
+    const uint32_t* src = ids + (size_t)v * cap;
+    uint32_t* dst = packed + offsets[v];
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+        dst[i] = src[i];
+}
+} // namespace u3d
+
+extern "C"
+{
+
+int u3d_batch_read_packed(u3d_batch* b, uint32_t* offsets, uint32_t* ids, uint64_t capacity, void* stream)
+{
+    if (!b || !offsets)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_packed: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const int V = (int)b->numViews;
+    if (!V)
+    {
+        offsets[0] = 0;
+        return U3D_OK;
+    }
+    CU_CHECK(b->packed.ensure((size_t)V * std::max<uint32_t>(b->outCap, 1)));
+    k_pack_offsets<<<1, 1024, 0, st>>>(V, b->outCounts.p, b->outCap, b->packOffsets.p);
+    k_pack_ids<<<V, 256, 0, st>>>(b->outCounts.p, b->outCap, b->packOffsets.p, b->outIdx.p, b->packed.p);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaMemcpyAsync(offsets, b->packOffsets.p, (size_t)(V + 1) * 4, cudaMemcpyDeviceToHost, st));
+    int rc = batch_check_flags(b, st); // synchronises
+    if (rc < 0)
+        return rc;
+    const uint64_t total = offsets[V];
+    if (total > capacity)
+        return fail(U3D_ERR_CAPACITY, "u3d_batch_read_packed: ids capacity too small");
+    if (total && ids)
+    {
+        CU_CHECK(cudaMemcpyAsync(ids, b->packed.p, total * 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_read_view(u3d_batch* b, uint32_t view, uint32_t* ids, uint32_t capacity, uint32_t* count, void* stream)
+{
+    if (!b || view >= b->numViews)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_view: bad argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    uint32_t c[2];
+    CU_CHECK(cudaMemcpyAsync(c, b->outCounts.p + 2 * (size_t)view, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (count)
+        *count = c[1];
+    const uint32_t n = std::min(std::min(c[1], capacity), b->outCap);
+    if (n && ids)
+    {
+        CU_CHECK(cudaMemcpyAsync(ids, b->outIdx.p + (size_t)view * b->outCap, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_read_depth(u3d_batch* b, uint32_t view, int32_t* out_depth, void* stream)
+{
+    if (!b || !out_depth || view >= b->numViews || !b->hasBuffers)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_depth: bad argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const size_t n = (size_t)b->vs.g.w * b->vs.g.h;
+    CU_CHECK(cudaMemcpyAsync(out_depth, b->vs.depth.p + view * n, n * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    return U3D_OK;
+}
+
+int u3d_batch_read_mip(u3d_batch* b, uint32_t view, int level, int32_t* out_minmax, void* stream)
+{
+    if (!b || !out_minmax || view >= b->numViews || !b->hasBuffers || level < 0 || level >= b->vs.g.nlev)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_mip: bad argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const BufGeom& g = b->vs.g;
+    CU_CHECK(cudaMemcpyAsync(out_minmax, b->vs.mips.p + (size_t)view * g.mipTexels + g.moff[level], (size_t)g.mw[level] * g.mh[level] * 8,
+        cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    return U3D_OK;
+}
+
+int u3d_batch_read_tri_stats(u3d_batch* b, uint32_t* stats3, void* stream)
+{
+    if (!b || !stats3)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_tri_stats: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const uint32_t V = b->numViews;
+    if (!b->hasBuffers)
+    {
+        std::memset(stats3, 0, (size_t)V * 12);
+        return U3D_OK;
+    }
+    std::vector<uint32_t> sub(V), drawn(V), setup(V);
+    CU_CHECK(cudaMemcpyAsync(sub.data(), b->vs.submitted.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(drawn.data(), b->vs.drawnSources.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(setup.data(), b->vs.triCount.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    for (uint32_t v = 0; v < V; ++v)
+    {
+        stats3[3 * v] = sub[v];
+        stats3[3 * v + 1] = sub[v] + drawn[v];
+        stats3[3 * v + 2] = setup[v];
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int stage, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity,
+    void* stream)
+{
+    int rc = u3d_batch_set_views(b, views, n, stream);
+    if (rc < 0)
+        return rc;
+    rc = u3d_batch_run(b, stage, stream);
+    if (rc < 0)
+        return rc;
+    if (counts)
+    {
+        rc = u3d_batch_read_counts(b, counts, stream);
+        if (rc < 0)
+            return rc;
+    }
+    if (offsets)
+        rc = u3d_batch_read_packed(b, offsets, ids, capacity, stream);
+    return rc;
+}
+
+int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids_dev, uint32_t* out_capacity)
+{
+    if (!b)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    if (counts_dev) *counts_dev = b->outCounts.p;
+    if (ids_dev) *ids_dev = b->outIdx.p;
+    if (out_capacity) *out_capacity = b->outCap;
+    return U3D_OK;
+}
+
+uint32_t u3d_batch_last_launches(const u3d_batch* b) { return b ? b->lastLaunches : 0; }
+
+} // extern "C"

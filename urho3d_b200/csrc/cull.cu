@@ -1,0 +1,298 @@
+// Octree query + occlusion culling for many views at once.  Replaces, per view:
+//   Octree::GetDrawables(OctreeQuery&) -> Octant::GetDrawablesInternal        (Octree.cpp:495-499, 229-255)
+//   FrustumOctreeQuery / OccludedFrustumOctreeQuery / ShadowCasterOctreeQuery (OctreeQuery.cpp:98-118, View.cpp:116-158, 59-84)
+//   CheckVisibilityWork's occlusion predicate                                 (View.cpp:177)
+//
+// One CTA per view.  Phase 1 resolves octant states level by level (a child needs its parent's state: culled / visited /
+// visited-inside).  Phase 2 sweeps the drawables of the surviving octants in DFS order, 32 bytes per AABB read as two float4,
+// and emits the result by ballot-ranked ordered compaction, so the output sequence equals the reference's result_ order.
+// Frustum survivors are queued in shared memory so that the expensive occlusion test always runs on dense warps.
+#include "u3d_device.cuh"
+#include "u3d_kernels.h"
+
+namespace u3d
+{
+
+struct CullShared
+{
+    ViewConst vc;
+    uint32_t pre[kCullThreads + 1];   // exclusive scan of drawable counts of the current octant chunk
+    uint32_t ring[2 * kCullThreads];  // frustum survivors waiting for the occlusion test (DFS slots)
+    uint32_t warpTot[kCullThreads / 32];
+    uint32_t ringCount;
+    uint32_t outCursor;
+    uint32_t queryCount;
+};
+
+/// Block-wide exclusive scan of one value per thread; returns the exclusive prefix, total through `total`.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* warpTot, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t x = val;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o)
+            x += y;
+    }
+    __syncthreads(); // warpTot may still be read from the previous use
+    if (lane == 31)
+        warpTot[wid] = x;
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kCullThreads / 32; ++i)
+    {
+        const uint32_t t = warpTot[i];
+        if (i < wid)
+            pre += t;
+        tot += t;
+    }
+    total = tot;
+    return pre + x - val;
+}
+
+/// Ordered block compaction of one predicate per thread: rank among the block's true predicates + their number.
+__device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uint32_t& total)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t bal = __ballot_sync(0xffffffffu, pred);
+    __syncthreads();
+    if (lane == 0)
+        warpTot[wid] = __popc(bal);
+    __syncthreads();
+    uint32_t pre = 0, tot = 0;
+#pragma unroll
+    for (int i = 0; i < kCullThreads / 32; ++i)
+    {
+        const uint32_t t = warpTot[i];
+        if (i < wid)
+            pre += t;
+        tot += t;
+    }
+    total = tot;
+    return pre + __popc(bal & ((1u << lane) - 1u));
+}
+
+__global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
+    const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
+    uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
+{
+    __shared__ CullShared sh;
+    const int v = blockIdx.x;
+    const int tid = threadIdx.x;
+
+    // view constants -> shared
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(views + v);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.vc);
+        for (int i = tid; i < (int)(sizeof(ViewConst) / 4); i += kCullThreads)
+            dst[i] = src[i];
+        if (tid == 0)
+        {
+            sh.ringCount = 0;
+            sh.outCursor = 0;
+            sh.queryCount = 0;
+        }
+    }
+    __syncthreads();
+    const ViewConst& vc = sh.vc;
+    const bool occl = vc.useOcclusion != 0;
+    const bool occludedQuery = occl && vc.queryMode == QUERY_OCCLUDED;
+    const int* depth = depthAll + (size_t)v * g.w * g.h;
+    const int2* mips = mipAll + (size_t)v * g.mipTexels;
+    unsigned char* state = octStateAll + (size_t)v * sc.numOctants;
+    uint32_t* out = outIdx + (size_t)v * outCap;
+
+    // ---------------- phase 1: octant states (0 culled, 1 visited, 2 visited with inside == true) ----------------
+    if (tid == 0)
+        state[0] = 1; // the root is never tested (Octree.cpp:231)
+    __syncthreads();
+    for (int lv = 1; lv < sc.numLevels; ++lv)
+    {
+        const int a = sc.levelStart[lv], b = sc.levelStart[lv + 1];
+        for (int i = a + tid; i < b; i += kCullThreads)
+        {
+            const int o = sc.bfs[i];
+            const float4 mn = sc.octMin[o];
+            const unsigned char ps = state[__float_as_int(mn.w)];
+            unsigned char st = 0;
+            if (ps)
+            {
+                const float4 mx = sc.octMax[o];
+                bool inside = ps == 2;
+                int res;
+                if (inside)
+                    res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
+                else
+                    res = frustum_test<false>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
+                if (occludedQuery && res != OUTSIDE && !ob_is_visible(g, vc.vp, depth, mips, mipsValid != 0, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z))
+                    res = OUTSIDE;
+                if (res != OUTSIDE)
+                    st = (res == INSIDE) ? 2 : 1;
+            }
+            state[o] = st;
+        }
+        __syncthreads();
+    }
+
+    // ---------------- phase 2: drawables of surviving octants, DFS order ----------------
+    const bool shadowQuery = vc.queryMode == QUERY_SHADOWCASTER;
+    const bool needOcclusion = stage == STAGE_VISIBLE && occl;
+
+    // Occlusion stage over `n` queued survivors starting at ring[0]; emits in order.
+    auto drain = [&](uint32_t n) {
+        bool vis = false;
+        uint32_t d = 0;
+        if ((uint32_t)tid < n)
+        {
+            d = sh.ring[tid];
+            const float4 mn = sc.drwMin[d];
+            if (!(__float_as_uint(mn.w) & kMetaOccludee))
+                vis = true; // !drawable->IsOccludee(), View.cpp:177
+            else
+            {
+                const float4 mx = sc.drwMax[d];
+                vis = ob_is_visible(g, vc.vp, depth, mips, mipsValid != 0, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+            }
+        }
+        uint32_t tot;
+        const uint32_t rank = block_rank(vis, sh.warpTot, tot);
+        const uint32_t base = sh.outCursor;
+        if (vis)
+        {
+            if (base + rank < outCap)
+                out[base + rank] = sc.drwId[d];
+        }
+        __syncthreads();
+        // shift the queue down by n
+        uint32_t keep0 = 0, keep1 = 0;
+        const uint32_t rc = sh.ringCount;
+        if (tid + n < rc) keep0 = sh.ring[tid + n];
+        if (tid + kCullThreads + n < rc) keep1 = sh.ring[tid + kCullThreads + n];
+        __syncthreads();
+        if (tid + n < rc) sh.ring[tid] = keep0;
+        if (tid + kCullThreads + n < rc) sh.ring[tid + kCullThreads] = keep1;
+        if (tid == 0)
+        {
+            sh.outCursor = base + tot;
+            sh.ringCount = rc - n;
+        }
+        __syncthreads();
+    };
+
+    for (int chunk = 0; chunk < sc.numOctants; chunk += kCullThreads)
+    {
+        const int o = chunk + tid;
+        uint32_t cnt = 0;
+        if (o < sc.numOctants && state[o])
+            cnt = (uint32_t)sc.octCount[o];
+        uint32_t total;
+        const uint32_t pre = block_exclusive_scan(cnt, sh.warpTot, total);
+        sh.pre[tid] = pre;
+        if (tid == 0)
+            sh.pre[kCullThreads] = total;
+        __syncthreads();
+        if (!total)
+            continue;
+
+        for (uint32_t base = 0; base < total; base += kCullThreads)
+        {
+            const uint32_t j = base + tid;
+            bool pass = false;
+            uint32_t d = 0;
+            if (j < total)
+            {
+                // owning octant: largest i with pre[i] <= j (octants with zero drawables share a prefix; take the last)
+                uint32_t lo = 0, hi = kCullThreads;
+                while (hi - lo > 1)
+                {
+                    const uint32_t m = (lo + hi) >> 1;
+                    if (sh.pre[m] <= j) lo = m; else hi = m;
+                }
+                const int oo = chunk + (int)lo;
+                d = (uint32_t)__float_as_int(sc.octMax[oo].w) + (j - sh.pre[lo]);
+                const bool inside = state[oo] == 2;
+                const float4 mn = sc.drwMin[d];
+                const float4 mx = sc.drwMax[d];
+                const uint32_t meta = __float_as_uint(mn.w);
+                // FrustumOctreeQuery::TestDrawables (OctreeQuery.cpp:106-118) / ShadowCasterOctreeQuery (View.cpp:70-82)
+                if ((meta & 0xFFu & vc.drawableFlags) && (__float_as_uint(mx.w) & vc.viewMask) && (!shadowQuery || (meta & kMetaCastShadows)))
+                    pass = inside || frustum_test<true>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+            }
+            uint32_t tot;
+            const uint32_t rank = block_rank(pass, sh.warpTot, tot);
+            if (!needOcclusion)
+            {
+                const uint32_t ob = sh.outCursor;
+                if (pass && ob + rank < outCap)
+                    out[ob + rank] = sc.drwId[d];
+                __syncthreads();
+                if (tid == 0)
+                {
+                    sh.outCursor = ob + tot;
+                    sh.queryCount += tot;
+                }
+                __syncthreads();
+            }
+            else
+            {
+                const uint32_t rc = sh.ringCount;
+                if (pass)
+                    sh.ring[rc + rank] = d;
+                __syncthreads();
+                if (tid == 0)
+                {
+                    sh.ringCount = rc + tot;
+                    sh.queryCount += tot;
+                }
+                __syncthreads();
+                if (sh.ringCount >= kCullThreads)
+                    drain(kCullThreads);
+            }
+        }
+    }
+    if (needOcclusion)
+    {
+        while (sh.ringCount)
+            drain(min(sh.ringCount, (uint32_t)kCullThreads));
+    }
+    __syncthreads();
+    if (tid == 0)
+    {
+        outCounts[2 * v] = sh.queryCount;
+        outCounts[2 * v + 1] = sh.outCursor;
+        if (sh.outCursor > outCap)
+            atomicOr(flags, kFlagOutOverflow);
+    }
+}
+
+__global__ void k_is_visible(BufGeom g, const ViewConst* __restrict__ view, const int* __restrict__ depth, const int2* __restrict__ mips, int mipsValid,
+    const float* __restrict__ aabb6, int n, unsigned char* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const float* b = aabb6 + 6 * (size_t)i;
+    out[i] = ob_is_visible(g, view->vp, depth, mips, mipsValid != 0, b[0], b[1], b[2], b[3], b[4], b[5]) ? 1 : 0;
+}
+
+void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, uint32_t* flags, cudaStream_t s)
+{
+    if (!numViews)
+        return;
+    k_cull_views<<<numViews, kCullThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+}
+
+void launch_is_visible(const BufGeom& g, const ViewConst* view, const int* depth, const int2* mips, int mipsValid, const float* aabb6, int n,
+    unsigned char* out, cudaStream_t s)
+{
+    if (!n)
+        return;
+    k_is_visible<<<(n + 127) / 128, 128, 0, s>>>(g, view, depth, mips, mipsValid, aabb6, n, out);
+}
+
+} // namespace u3d

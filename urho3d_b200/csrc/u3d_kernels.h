@@ -1,0 +1,55 @@
+// Host-visible declarations of the kernel launchers (raster.cu, cull.cu) used by the C-ABI layer (capi.cu).
+#pragma once
+#include "u3d_device.cuh"
+
+namespace u3d
+{
+
+constexpr int kItemTris = 256;      // triangles per draw item; bigger batches are split so no block owns a huge mesh
+constexpr int kSetupItems = 32;     // draw items per set-up block
+constexpr int kSetupThreads = 256;
+constexpr int kCullThreads = 512;
+
+// bits of the per-batch device flag word
+constexpr uint32_t kFlagTriOverflow = 1u;   // a view's triangle region was too small
+constexpr uint32_t kFlagPoolOverflow = 2u;  // the triangle pool cannot hold all regions
+constexpr uint32_t kFlagOutOverflow = 4u;   // a view produced more results than the output capacity
+
+/// Flattened octree + drawables resident in HBM (DFS pre-order = the order Octant::GetDrawablesInternal visits, Octree.cpp:229-255).
+struct SceneDev
+{
+    int numOctants;
+    int numDrawables;
+    int numLevels;                 // deepest octant level + 1
+    const float4* octMin;          // xyz = cullingBox_.min_, w = parent (int bits; -1 for the root)
+    const float4* octMax;          // xyz = cullingBox_.max_, w = first drawable (int bits)
+    const int* octCount;           // drawables owned by the octant
+    const int* bfs;                // octant indices sorted by level (stable)
+    const int* levelStart;         // numLevels + 1 offsets into bfs
+    const float4* drwMin;          // xyz = world AABB min, w = drawableFlags | kMetaOccludee | kMetaCastShadows (uint bits)
+    const float4* drwMax;          // xyz = world AABB max, w = viewMask (uint bits)
+    const uint32_t* drwId;         // caller's drawable id for each DFS slot
+};
+
+void launch_clear(int* depth, size_t nInts, cudaStream_t s);
+void launch_select(const ViewConst* views, int numViews, int numOcc, const float* occAabb6, const uint32_t* occMesh, const uint32_t* occStart,
+    const uint32_t* occCount, DrawItem* items, uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, cudaStream_t s);
+void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,
+    cudaStream_t s);
+void launch_setup(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems, const uint32_t* itemCount,
+    const float* models, const MeshDev* meshes, TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap, uint32_t* triCount,
+    uint32_t* drawnSources, uint32_t* flags, cudaStream_t s);
+void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,
+    const uint32_t* triCount, int blocksPerView, cudaStream_t s);
+void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, cudaStream_t s);
+
+/// Octree query (+ optional CheckVisibility predicate) for every view.  octState: numViews x numOctants bytes of scratch.
+void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
+    uint32_t* flags, cudaStream_t s);
+
+/// OcclusionBuffer::IsVisible for n boxes against view 0's buffer.
+void launch_is_visible(const BufGeom& g, const ViewConst* view, const int* depth, const int2* mips, int mipsValid, const float* aabb6, int n,
+    unsigned char* out, cudaStream_t s);
+
+} // namespace u3d
