@@ -1,0 +1,415 @@
+#!/usr/bin/env python
+"""bench.py -- views/sec of the per-frame visibility path (occluder raster -> depth hierarchy -> octree query -> visibility).
+
+Workload = BASELINE.json configs[2] ("C3", the configuration the metric is quoted on): 4,096 independent agent cameras over a
+1M-drawable / 4,000-occluder scene, 256x256 occlusion buffers, views sharded over the ranks.
+A step = one pass of the whole path over the 4,096-view batch.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--views V]
+    torchrun --nproc-per-node N bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` = views/s with inputs resident in HBM (device time, CUDA events, max over ranks);
+`e2e` = the same through one C-ABI call per step with host buffers in and out; `roofline` = the dominant kernel against the
+measured HBM peak; `cpu_baseline` = the reference's own CPU code (oracle/_ref) on this box's host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WIDTH, HEIGHT = 256, 256
+METRIC = "views/sec (1M drawables, 256x256 occlusion)"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--views", type=int, default=4096)
+    ap.add_argument("--drawables", type=int, default=1_000_000)
+    ap.add_argument("--occluders", type=int, default=4000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
+    return ap.parse_args()
+
+
+def build_inputs(args):
+    from urho3d_b200 import scenes
+    extent = scenes.CONFIGS["C3"]["extent"]
+    sc = scenes.Scene(args.drawables, args.occluders, extent)
+    views = scenes.agent_cameras(args.views, extent, WIDTH, HEIGHT)
+    return sc, views
+
+
+def config_dict(args, world):
+    return {"workload": "C3: %d agent cameras x %d drawables, %d box occluders (12 tris each), %dx%d occlusion buffers, depth hierarchy, "
+                        "occluded octree query + visibility predicate" % (args.views, args.drawables, args.occluders, WIDTH, HEIGHT),
+            "views": args.views, "drawables": args.drawables, "occluders": args.occluders, "buffer": [WIDTH, HEIGHT],
+            "sharding": "views interleaved over %d rank(s)" % world,
+            "cache": "L2 flushed between timed steps (256 MiB write); per-step working set (depth+mips+triangles) also exceeds L2"}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# CPU reference arm (oracle/_ref = the UNMODIFIED reference compiled from /root/reference; falls back to the C oracle port)
+# ------------------------------------------------------------------------------------------------------------------------------
+def _ref_worker(ref, sc, views, conn):
+    """Persistent worker: waits for (lo, hi) ranges, runs the reference over those views, answers (seconds, visible, triangles)."""
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            os._exit(0)
+        lo, hi = msg
+        t0 = time.perf_counter()
+        nvis = 0
+        tris = 0
+        for i in range(lo, hi):
+            ref.set_view_raw(views[i])
+            vis, counts, _ = ref.run_view(sc)
+            nvis += len(vis)
+            tris += int(counts[0])
+        conn.send((time.perf_counter() - t0, nvis, tris))
+
+
+class CpuReference:
+    """Runs the reference's CPU path over a bounded sample of the workload, one process per host core (the views are independent;
+    this is the most favourable way to use all host threads -- the reference itself walks its views one after another on the main thread,
+    Renderer.cpp:673-686).  Workers are forked once, after the reference scene has been built, and reused for every step."""
+
+    def __init__(self, sc, views, sample):
+        import multiprocessing as mp
+        from oracle import refbind
+        self.sc = sc
+        self.views = views[:sample]
+        self.cores = max(1, min(os.cpu_count() or 1, 64, len(self.views)))
+        self.kind = "reference" if refbind.available() else "port"
+        self.workers = []
+        if self.kind == "reference":
+            ref = refbind.Ref(0)
+            ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
+            ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+            ref.ob_set_size(WIDTH, HEIGHT)
+            ctx = mp.get_context("fork")
+            for _ in range(self.cores):
+                parent, child = ctx.Pipe(True)
+                p = ctx.Process(target=_ref_worker, args=(ref, sc, self.views, child), daemon=True)
+                p.start()
+                child.close()
+                self.workers.append((p, parent))
+
+    def close(self):
+        for p, conn in self.workers:
+            try:
+                conn.send(None)
+            except OSError:
+                pass
+        for p, _ in self.workers:
+            p.join(timeout=5)
+        self.workers = []
+
+    def step(self):
+        """One pass over the sample.  Returns (wall seconds, views, visible total, submitted triangles)."""
+        n = len(self.views)
+        if self.kind == "port":
+            return self._step_port()
+        t0 = time.perf_counter()
+        for w, (_, conn) in enumerate(self.workers):
+            conn.send((n * w // self.cores, n * (w + 1) // self.cores))
+        nvis = tris = 0
+        for _, conn in self.workers:
+            _, a, b = conn.recv()
+            nvis += a
+            tris += b
+        return time.perf_counter() - t0, n, nvis, tris
+
+    def _step_port(self):
+        from oracle import oraclebind
+        from urho3d_b200 import capi
+        if not hasattr(self, "_port"):
+            t = capi.Octree(self.sc.octree_min, self.sc.octree_max, self.sc.octree_levels)
+            t.add(self.sc.aabb, self.sc.flags, self.sc.view_mask, self.sc.occludee, self.sc.cast_shadows)
+            tree = oraclebind.OracleTree(t.flatten(), self.sc.aabb, self.sc.flags, self.sc.view_mask, self.sc.occludee, self.sc.cast_shadows)
+            ob = oraclebind.OracleOB()
+            ob.set_size(WIDTH, HEIGHT)
+            self._port = (tree, ob)
+            self.views = self.views[:256]
+            self.cores = 1
+        tree, ob = self._port
+        t0 = time.perf_counter()
+        nvis = tris = 0
+        for v in self.views:
+            tris += ob.draw_scene_view(self.sc, v)
+            cand = tree.query(1, v.planes, ob, as_ids=False)
+            nvis += len(tree.check_visibility(ob, cand))
+        return time.perf_counter() - t0, len(self.views), nvis, tris
+
+    def describe(self):
+        return "%d of the workload's views, split over %d single-threaded processes, each running the %s per view: Clear, AddTriangles for " \
+               "every occluder passing IsInsideFast, DrawTriangles, BuildDepthHierarchy, OccludedFrustumOctreeQuery, IsVisible predicate" % (
+                   len(self.views), self.cores, "compiled reference classes (oracle/_ref)" if self.kind == "reference" else "C oracle port")
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    sc, views = build_inputs(args)
+    cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
+    for _ in range(max(args.warmup, 1)):
+        cpu.step()
+    total = 0.0
+    nviews = 0
+    tris = 0
+    for _ in range(args.steps):
+        dt, n, _, t = cpu.step()
+        total += dt
+        nviews += n
+        tris += t
+    value = nviews / total
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32",
+            "data": "synthetic", "config": config_dict(args, 1), "occluder_mtri_per_s": tris / total / 1e6,
+            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
+            "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    cpu.close()
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        rows = [r for t, r in self.rows if t0 <= t <= t1] or [r for _, r in self.rows]
+        sm, mx, reasons = [], [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------------------
+def mip_texels(w, h):
+    tot = 0
+    while True:
+        w, h = (w + 1) // 2, (h + 1) // 2
+        tot += w * h
+        if w <= 8 and h <= 8:
+            return tot
+
+
+class _DevArray:
+    """Expose a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, shape, typestr="<i4"):
+        self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from urho3d_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    args.warmup = max(args.warmup, 3)
+
+    sc, views = build_inputs(args)
+    my_ids = list(range(rank, args.views, world))
+    my_views = [views[i] for i in my_ids]
+    V = len(my_views)
+
+    ctx = capi.Context(local_rank)
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    gscene = capi.GpuScene(ctx, octree=tree)
+    mesh = capi.Mesh(ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    out_cap = 32768
+    batch = capi.Batch(ctx, gscene, occ, WIDTH, HEIGHT, V, out_cap, tri_pool=V * 14000)
+    packed = capi.pack_views(my_views)
+    # a non-default torch stream: its handle is passed to every C-ABI call, and torch.cuda.Event records on the same stream
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+    assert stream != 0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    # device-resident leg ----------------------------------------------------------------------------------------------------
+    batch.set_views(packed, stream)
+    counts_dev = ids_dev = None
+    if world > 1:
+        cptr, iptr, cap = capi._vp(), capi._vp(), capi.C.c_uint32()
+        capi._chk(capi.lib().u3d_batch_device_results(batch.h, capi.C.byref(cptr), capi.C.byref(iptr), capi.C.byref(cap)))
+        counts_dev = torch.as_tensor(_DevArray(cptr.value, (V, 2)), device="cuda")
+        gathered_counts = torch.empty((world * V, 2), dtype=counts_dev.dtype, device="cuda")
+
+    def step_device():
+        batch.run(capi.STAGE_VISIBLE, stream)
+        if world > 1:
+            # the only collective of the path: gather per-view counts (visible sets follow the same pattern)
+            dist.all_gather_into_tensor(gathered_counts, counts_dev)
+
+    for _ in range(args.warmup):
+        flush.zero_()
+        step_device()
+    torch.cuda.synchronize()
+    counts = batch.counts(stream)  # also checks the overflow flags
+    stats = batch.tri_stats(stream)
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    t_begin = time.perf_counter()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    launches = 0
+    for k in range(args.steps):
+        flush.zero_()
+        starts[k].record()
+        step_device()
+        ends[k].record()
+        launches += batch.last_launches()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t_end = time.perf_counter()
+    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
+    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(total_ms.item())
+    clocks = sampler.stop(t_begin, t_end) if sampler else None
+
+    # per-phase device times (events after each kernel phase), same inputs
+    phase_ms = {}
+    for _ in range(3):
+        flush.zero_()
+        torch.cuda.synchronize()
+        for name, ms in batch.run_timed(capi.STAGE_VISIBLE, stream).items():
+            phase_ms.setdefault(name, []).append(ms)
+    phase_ms = {k: statistics.median(v) for k, v in phase_ms.items()}
+
+    # e2e leg: one C-ABI call per step, host buffers in (views) and out (counts + packed visible ids) ---------------------------------
+    h_counts = torch.empty((V, 2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    h_offsets = torch.empty(V + 1, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    h_ids = torch.empty(int(counts[:, 1].sum() * 1.25) + 1024, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+    h_views = torch.empty(packed.nbytes, dtype=torch.uint8).pin_memory().numpy()
+    h_views[:] = packed.view(np.uint8).reshape(-1)
+    h_packed = h_views.view(capi.VIEW_DTYPE)
+    for _ in range(2):
+        batch.cull_views(h_packed, capi.STAGE_VISIBLE, stream, h_counts, h_offsets, h_ids)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        batch.cull_views(h_packed, capi.STAGE_VISIBLE, stream, h_counts, h_offsets, h_ids)
+    torch.cuda.synchronize()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    assert np.array_equal(h_counts, counts), "e2e leg disagrees with the device-resident leg"
+    h2d = packed.nbytes
+    d2h = h_counts.nbytes + h_offsets.nbytes + int(h_offsets[-1]) * 4
+    tot = torch.tensor([h2d, d2h, int(stats[:, 0].sum()), int(counts[:, 1].sum()), int(counts[:, 0].sum())], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tot)
+    h2d, d2h, sub_tris, n_vis, n_cand = [float(x) for x in tot.tolist()]
+
+    if rank == 0:
+        value = args.views * args.steps / (total_ms * 1e-3)
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+        else:
+            peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+        N, M = gscene.num_drawables, gscene.num_octants
+        mips = mip_texels(WIDTH, HEIGHT)
+        vis_per_view = n_vis / args.views
+        tri_per_view = sub_tris / args.views
+        # algorithmic bytes per view, SURVEY 8(d)
+        b_cull = 32.0 * N + 32.0 * M + 4.0 * vis_per_view + 4.0 + 4.0 * WIDTH * HEIGHT + 8.0 * mips
+        b_tri = 3 * 2 + 36 + 48.0 / 12.0
+        alg = {"cull": b_cull, "setup": tri_per_view * b_tri, "fill": 4.0 * WIDTH * HEIGHT, "hierarchy": 4.0 * WIDTH * HEIGHT + 8.0 * mips,
+               "clear": 4.0 * WIDTH * HEIGHT, "select": 24.0 * args.occluders, "scan": 8.0}
+        dom = max(phase_ms, key=phase_ms.get)
+        achieved = alg[dom] * V / (phase_ms[dom] * 1e-3) / 1e9
+        phases = {k: {"ms": round(phase_ms[k], 4), "alg_GBps": round(alg[k] * V / max(phase_ms[k], 1e-6) / 1e6, 1)} for k in phase_ms}
+        line = {"metric": METRIC, "value": value, "unit": "views/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32",
+                "data": "synthetic", "config": config_dict(args, world),
+                "occluder_mtri_per_s": sub_tris * args.steps / (total_ms * 1e-3) / 1e6,
+                "per_view": {"submitted_tris": tri_per_view, "query_result": n_cand / args.views, "visible": vis_per_view, "octants": M},
+                "e2e": {"value": args.views * args.steps / e2e_s, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches,
+                "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                             "peak_source": peak_src, "algorithmic_bytes_per_view": alg[dom], "views_per_launch": V,
+                             "note": "algorithmic bytes use SURVEY 8(d)'s flat-scan convention; see DESIGN.md for measured DRAM traffic"},
+                "phases_rank0": phases, "clocks": clocks}
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
+            dt, n, nvis_cpu, _ = cpu.step()
+            line["cpu_baseline"] = {"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()}
+            cpu.close()
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

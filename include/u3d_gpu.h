@@ -181,6 +181,10 @@ U3D_API int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n,
 U3D_API int u3d_batch_run(u3d_batch* b, int stage, void* stream);
 /* Parts of the pipeline, for measurement: 1 = raster+hierarchy only, 2 = cull only (buffers from a previous run). */
 U3D_API int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream);
+/* u3d_batch_run with a CUDA event after each phase; synchronises and returns the device time of each phase in milliseconds:
+ * 0 clear, 1 occluder select, 2 region scan, 3 triangle set-up, 4 depth fill, 5 depth hierarchy, 6 octree query + visibility. */
+#define U3D_NUM_PHASES 7
+U3D_API int u3d_batch_run_timed(u3d_batch* b, int stage, void* stream, float* phase_ms);
 /* Results.  counts = n x 2 uint32: (query result size, emitted count).  Synchronises `stream`; reports pool/output overflow. */
 U3D_API int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream);
 /* Emitted ids of every view packed back to back; offsets has n+1 entries.  capacity in ids.  Synchronises. */

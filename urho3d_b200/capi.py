@@ -89,6 +89,7 @@ SIGNATURES = {
     "u3d_batch_set_views": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "u3d_batch_run": (C.c_int, [_vp, C.c_int, _vp]),
     "u3d_batch_run_part": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "u3d_batch_run_timed": (C.c_int, [_vp, C.c_int, _vp, _f]),
     "u3d_batch_read_counts": (C.c_int, [_vp, _u32, _vp]),
     "u3d_batch_read_packed": (C.c_int, [_vp, _u32, _u32, C.c_uint64, _vp]),
     "u3d_batch_read_view": (C.c_int, [_vp, C.c_uint32, _u32, C.c_uint32, _u32, _vp]),
@@ -405,6 +406,14 @@ class Batch:
 
     def run(self, stage=STAGE_VISIBLE, stream=None, part=0):
         _chk(lib().u3d_batch_run_part(self.h, part, stage, stream))
+
+    PHASES = ("clear", "select", "scan", "setup", "fill", "hierarchy", "cull")
+
+    def run_timed(self, stage=STAGE_VISIBLE, stream=None):
+        """Run with a CUDA event after each phase; returns dict phase -> device milliseconds (synchronises)."""
+        ms = np.zeros(len(self.PHASES), np.float32)
+        _chk(lib().u3d_batch_run_timed(self.h, stage, stream, _p(ms, _f)))
+        return dict(zip(self.PHASES, ms.tolist()))
 
     def counts(self, stream=None):
         out = np.zeros((self.n, 2), np.uint32)

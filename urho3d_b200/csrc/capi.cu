@@ -265,6 +265,15 @@ struct u3d_batch
     PinnedBuf<uint32_t> hostCounts;
     uint32_t lastLaunches{};
     bool hasBuffers{};
+    cudaEvent_t ev[U3D_NUM_PHASES + 1]{};
+    bool timed{};      // record an event after every phase of the next run
+    bool haveEvents{};
+    ~u3d_batch()
+    {
+        if (haveEvents)
+            for (auto& e : ev)
+                cudaEventDestroy(e);
+    }
 };
 
 // -----------------------------------------------------------------------------------------------------------------------------
@@ -1230,6 +1239,10 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
     if (!V)
         return U3D_OK;
     ViewSet& vs = b->vs;
+    const bool timed = b->timed;
+    b->timed = false;
+    auto mark = [&](int phase) -> cudaError_t { return timed ? cudaEventRecord(b->ev[phase], st) : cudaSuccess; };
+    CU_CHECK(mark(0));
     if (part != 2)
         CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
     if (b->hasBuffers && part != 2)
@@ -1240,21 +1253,54 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, (size_t)V * 4, st));
         CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
         launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
+        CU_CHECK(mark(1));
         launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
+        CU_CHECK(mark(2));
         launch_scan_regions(V, vs.submitted.p, 64, b->poolTris, vs.triBase.p, vs.triCap.p, vs.flags.p, st);
+        CU_CHECK(mark(3));
         launch_setup(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, vs.pool.p, vs.triBase.p,
             vs.triCap.p, vs.triCount.p, vs.drawnSources.p, vs.flags.p, st);
+        CU_CHECK(mark(4));
         launch_fill_global(vs.g, V, vs.depth.p, vs.pool.p, vs.triBase.p, vs.triCap.p, vs.triCount.p, 8, st);
+        CU_CHECK(mark(5));
         launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, st);
-        b->lastLaunches += 5 + (uint32_t)vs.g.nlev + (oc->n ? 0 : 0);
+        b->lastLaunches += 5 + (uint32_t)vs.g.nlev;
         CU_CHECK(cudaGetLastError());
     }
+    else
+    {
+        for (int p = 1; p <= 5; ++p)
+            CU_CHECK(mark(p));
+    }
+    CU_CHECK(mark(6));
     if (part != 1)
     {
         launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, vs.flags.p, st);
         b->lastLaunches += 1;
         CU_CHECK(cudaGetLastError());
     }
+    CU_CHECK(mark(7));
+    return U3D_OK;
+}
+
+int u3d_batch_run_timed(u3d_batch* b, int stage, void* stream, float* phase_ms)
+{
+    if (!b || !phase_ms)
+        return fail(U3D_ERR_INVALID, "u3d_batch_run_timed: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    if (!b->haveEvents)
+    {
+        for (auto& e : b->ev)
+            CU_CHECK(cudaEventCreate(&e));
+        b->haveEvents = true;
+    }
+    b->timed = true;
+    int rc = u3d_batch_run_part(b, 0, stage, stream);
+    if (rc < 0)
+        return rc;
+    CU_CHECK(cudaStreamSynchronize(b->ctx->pick(stream)));
+    for (int p = 0; p < U3D_NUM_PHASES; ++p)
+        CU_CHECK(cudaEventElapsedTime(&phase_ms[p], b->ev[p], b->ev[p + 1]));
     return U3D_OK;
 }
 
