@@ -78,6 +78,8 @@ typedef struct u3d_view
 
 U3D_API const char* u3d_last_error(void);
 U3D_API int u3d_abi_version(void);
+/* Test hook.  "force_irregular" = 1 routes every set-up triangle of the batched path through the general (global-memory) fill. */
+U3D_API int u3d_debug_set_option(const char* name, int value);
 
 /* ---- context -------------------------------------------------------------------------------------------------------------- */
 U3D_API int u3d_ctx_create(int device, u3d_ctx** out);

@@ -40,6 +40,7 @@ typedef struct OrcOB
     int cull, reverse;
     unsigned num_tris, max_tris;
     int dirty;
+    unsigned long long px_tested, px_written; /* statistics only */
 } OrcOB;
 
 /* x86 cvttss2si/cvttsd2si semantics made explicit: out-of-range and NaN give INT_MIN (SURVEY hard part 2). */
@@ -121,6 +122,7 @@ int orc_ob_height(const OrcOB* ob) { return ob->h; }
 int orc_ob_num_levels(const OrcOB* ob) { return ob->nlev; }
 unsigned orc_ob_num_triangles(const OrcOB* ob) { return ob->num_tris; }
 int orc_ob_cull_mode(const OrcOB* ob) { return ob->cull; }
+void orc_ob_pixel_stats(const OrcOB* ob, unsigned long long* tested, unsigned long long* written) { *tested = ob->px_tested; *written = ob->px_written; }
 
 /* Matrix4 * Matrix3x4, Matrix4.cpp:43-63 (a = 4x4 row-major, b = 3x4 row-major). */
 static void mul44_34(const float* a, const float* b, float* o)
@@ -210,8 +212,12 @@ static void depth_min(OrcOB* ob, int64_t off, int z)
 {
     if (off < 0 || off >= (int64_t)ob->w * ob->h)
         return;
+    ++ob->px_tested;
     if (z < ob->depth[off])
+    {
         ob->depth[off] = z;
+        ++ob->px_written;
+    }
 }
 
 typedef struct { int x, xstep, z, zstep; } EdgeI;
@@ -232,29 +238,48 @@ static EdgeI make_edge(float dzdx, float dzdy, V3 top, V3 bot, int top_y)
 }
 
 /* One half of the triangle: rows [y0, y1), span from `left` to `right`, depth walks along `left`. OB.cpp:897-1001 */
+static void edge_skip(EdgeI* e, int64_t rows)
+{
+    /* `rows` incremental steps at once; additions wrap, so a 32-bit modular multiply gives the same state */
+    e->x = (int)((uint32_t)e->x + (uint32_t)rows * (uint32_t)e->xstep);
+    e->z = (int)((uint32_t)e->z + (uint32_t)rows * (uint32_t)e->zstep);
+}
+
 static void fill_half(OrcOB* ob, int y0, int y1, EdgeI* left, EdgeI* right, int dzdx_i)
 {
-    /* Rows whose linear span could touch [0,w*h): |x>>16| <= 32768, so rows far outside can be skipped without
-     * changing the visible plane; the edges are still stepped for them. */
+    /* Rows whose linear span could touch [0,w*h): |x>>16| <= 32768, so rows far outside cannot change the visible plane.
+     * They are skipped (float garbage can make the row range billions long); the edges are advanced as if stepped. */
     int64_t guard = 32768 / ob->w + 2;
-    for (int64_t y = y0; y < y1; ++y)
+    int64_t lo = y0, hi = y1;
+    if (hi <= lo)
+        return;
+    if (lo < -guard)
+        lo = -guard;
+    if (hi > (int64_t)ob->h + guard)
+        hi = (int64_t)ob->h + guard;
+    if (hi < lo)
+        hi = lo = (y1 < lo ? y1 : lo);
+    if (lo > y1)
+        lo = hi = y1;
+    edge_skip(left, lo - y0);
+    edge_skip(right, lo - y0);
+    for (int64_t y = lo; y < hi; ++y)
     {
-        if (y >= -guard && y <= (int64_t)ob->h + guard)
+        int z = left->z;
+        int64_t xs = left->x >> 16;
+        int64_t xe = right->x >> 16;
+        int64_t row = y * ob->w;
+        for (int64_t x = xs; x < xe; ++x)
         {
-            int z = left->z;
-            int64_t xs = left->x >> 16;
-            int64_t xe = right->x >> 16;
-            int64_t row = y * ob->w;
-            for (int64_t x = xs; x < xe; ++x)
-            {
-                depth_min(ob, row + x, z);
-                z = wrap_add(z, dzdx_i);
-            }
+            depth_min(ob, row + x, z);
+            z = wrap_add(z, dzdx_i);
         }
         left->x = wrap_add(left->x, left->xstep);
         left->z = wrap_add(left->z, left->zstep);
         right->x = wrap_add(right->x, right->xstep);
     }
+    edge_skip(left, (int64_t)y1 - hi);
+    edge_skip(right, (int64_t)y1 - hi);
 }
 
 /* DrawTriangle2D, OB.cpp:815-1002 */

@@ -275,3 +275,81 @@ def test_million_drawables_slice(gpu_ctx):
         ob.close()
     for o in (occ, mesh, gs, tree):
         o.close()
+
+
+def test_general_path_for_every_triangle(gpu_ctx):
+    """Force every triangle through the irregular (global-memory, linear-addressing) path of the batched pipeline."""
+    w, h = 256, 160
+    sc = helpers.small_scene(n=3000, k=128, extent=80.0, seed=5)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = helpers.stress_views(80.0, w, h, 6, seed=12)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    capi.debug_set_option("force_irregular", 1)
+    try:
+        counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    finally:
+        capi.debug_set_option("force_irregular", 0)
+    for i, v in enumerate(views):
+        sub, cand, vis = oracle_view(sc, otree, ob, v)
+        assert np.array_equal(batch.depth(i), ob.depth())
+        for a, b in zip(batch.mips(i), ob.mips()):
+            assert np.array_equal(a, b)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], vis)
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+def test_garbage_geometry_does_not_crash_and_matches(gpu_ctx):
+    """Huge / non-finite / degenerate vertices: conversions follow x86 (INT_MIN), spans may spill across rows (linear addressing),
+    nothing may hang or fault, and whatever lands inside the plane must equal the oracle."""
+    w, h = 64, 64
+    rs = np.random.RandomState(3)
+    v = camera.make_view([0, 0, 0], 0, 0, 60.0, 1.0, 0.1, 100.0)
+    base = rs.uniform(-3, 3, size=(60, 3)).astype(np.float32)
+    base[:, 2] += 6.0
+    vtx = base.copy()
+    vtx[3] = [1e30, 0, 5]
+    vtx[7] = [0, -1e30, 5]
+    vtx[11] = [np.inf, 1, 5]
+    vtx[13] = [np.nan, 1, 5]
+    vtx[17] = [1e20, 1e20, 1e20]
+    vtx[20] = vtx[21]                      # zero-area
+    vtx[25:28] = [[0, 0, 1e-30]] * 3       # at the eye
+    vtx[30] = [1e6, -1e6, 0.2]             # sliver through the near plane
+    model = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32)
+    tree = capi.Octree()
+    tree.add(np.array([[-1, -1, 5, 1, 1, 7]], np.float32))
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    mesh = capi.Mesh(gpu_ctx, vtx, 12, None)
+    occ = capi.Occluders(gpu_ctx, np.array([[-1, -1, 5, 1, 1, 7]], np.float32), model.reshape(1, 12), [mesh], cull_mode=0)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, 1, 16)
+    batch.cull_views(capi.pack_views([v]), capi.STAGE_VISIBLE)
+    ob = oraclebind.OracleOB()
+    ob.set_size(w, h)
+    ob.set_view(v)
+    ob.set_max_triangles(1 << 30)
+    ob.clear()
+    ob.set_cull_mode(0)
+    ob.draw_batch(model, vtx, 12, None, 0, 60)
+    ob.build_hierarchy()
+    assert np.array_equal(batch.depth(0), ob.depth())
+    for a, b in zip(batch.mips(0), ob.mips()):
+        assert np.array_equal(a, b)
+    assert batch.tri_stats()[0, 1] == ob.num_triangles()
+    # the drop-in object takes the same geometry through AddTriangles/DrawTriangles
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    gob.SetSize(w, h)
+    gob.SetView(v)
+    gob.SetMaxTriangles(1 << 30)
+    gob.Clear()
+    gob.SetCullMode(0)
+    gob.AddTriangles(model, vtx, 12, None, 0, 60)
+    gob.DrawTriangles()
+    assert np.array_equal(gob.GetBuffer(), ob.depth())
+    for o in (gob, batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

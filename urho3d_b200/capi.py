@@ -38,6 +38,7 @@ assert VIEW_DTYPE.itemsize == C.sizeof(U3DView) == 240
 SIGNATURES = {
     "u3d_last_error": (C.c_char_p, []),
     "u3d_abi_version": (C.c_int, []),
+    "u3d_debug_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "u3d_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "u3d_ctx_destroy": (None, [_vp]),
     "u3d_ctx_device": (C.c_int, [_vp]),
@@ -124,6 +125,10 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def debug_set_option(name, value):
+    _chk(lib().u3d_debug_set_option(name.encode(), int(value)))
 
 
 def _chk(rc):

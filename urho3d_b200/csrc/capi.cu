@@ -15,6 +15,7 @@
 using namespace u3d;
 
 static thread_local std::string g_err;
+static int g_forceIrregular = 0; // u3d_debug_set_option("force_irregular")
 
 static int fail(int code, const std::string& msg)
 {
@@ -192,12 +193,48 @@ struct ViewSet
     DevBuf<TriSetup> pool;
     DevBuf<DrawItem> items;
     uint32_t itemCap{};
-    int alloc(u3d_ctx* c, int w, int h, uint32_t nviews, uint32_t itemCapPerView, uint64_t poolTris)
+    // tile path
+    TileGeom tg{};
+    bool useTiles{};
+    DevBuf<uint32_t> binIdx, binCount, irrTotal, irrOfView;
+    DevBuf<unsigned long long> irrList;
+    uint32_t irrCap{};
+    RasterDev raster_dev(bool tiles, int writeMips)
+    {
+        RasterDev rd{};
+        rd.pool = pool.p;
+        rd.triBase = triBase.p;
+        rd.triCap = triCap.p;
+        rd.triCount = triCount.p;
+        rd.drawnSources = drawnSources.p;
+        rd.flags = flags.p;
+        rd.binIdx = tiles ? binIdx.p : nullptr;
+        rd.binCount = tiles ? binCount.p : nullptr;
+        rd.irrList = irrList.p;
+        rd.irrCap = irrCap;
+        rd.irrTotal = irrTotal.p;
+        rd.irrOfView = irrOfView.p;
+        rd.writeMips = writeMips;
+        rd.forceIrregular = g_forceIrregular;
+        return rd;
+    }
+    int alloc(u3d_ctx* c, int w, int h, uint32_t nviews, uint32_t itemCapPerView, uint64_t poolTris, bool tiles = false)
     {
         ctx = c;
         g = make_geom(w, h);
+        tg = make_tile_geom(g);
+        useTiles = tiles && g.w >= 4;
         maxViews = nviews;
         itemCap = itemCapPerView;
+        if (useTiles)
+        {
+            irrCap = 1u << 20;
+            CU_CHECK(binIdx.ensure(std::max<uint64_t>(poolTris, 1) * tg.numTiles));
+            CU_CHECK(binCount.ensure((size_t)nviews * tg.numTiles));
+            CU_CHECK(irrList.ensure(irrCap));
+            CU_CHECK(irrTotal.ensure(1));
+            CU_CHECK(irrOfView.ensure(nviews));
+        }
         CU_CHECK(views.ensure(nviews));
         CU_CHECK(depth.ensure((size_t)nviews * w * h));
         CU_CHECK(mips.ensure((size_t)nviews * g.mipTexels));
@@ -283,6 +320,16 @@ extern "C"
 const char* u3d_last_error(void) { return g_err.c_str(); }
 int u3d_abi_version(void) { return 1; }
 
+int u3d_debug_set_option(const char* name, int value)
+{
+    if (name && std::strcmp(name, "force_irregular") == 0)
+    {
+        g_forceIrregular = value;
+        return U3D_OK;
+    }
+    return fail(U3D_ERR_INVALID, "u3d_debug_set_option: unknown option");
+}
+
 int u3d_ctx_create(int device, u3d_ctx** out)
 {
     if (!out)
@@ -303,7 +350,9 @@ int u3d_ctx_create(int device, u3d_ctx** out)
     if (!c)
         return fail(U3D_ERR_NOMEM, "out of host memory");
     c->device = device;
-    e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    e = init_tile_kernel();
+    if (e == cudaSuccess)
+        e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess)
     {
         delete c;
@@ -958,8 +1007,7 @@ int u3d_ob_draw_triangles(u3d_ob* ob)
         int rc = ob_upload_view(ob); // cullMode_ is read at draw time (OB.cpp:634)
         if (rc < 0)
             return rc;
-        launch_setup(vs.g, vs.views.p, 1, vs.items.p, vs.itemCap, nItems, vs.itemCount.p, ob->models.p, ob->meshTable.p, vs.pool.p, vs.triBase.p,
-            vs.triCap.p, vs.triCount.p, vs.drawnSources.p, vs.flags.p, st);
+        launch_setup(vs.g, vs.tg, vs.views.p, 1, vs.items.p, vs.itemCap, nItems, vs.itemCount.p, ob->models.p, ob->meshTable.p, vs.raster_dev(false, 0), st);
         CU_CHECK(cudaGetLastError());
         uint32_t res[3] = {0, 0, 0};
         CU_CHECK(cudaMemcpyAsync(&res[0], vs.triCount.p, 4, cudaMemcpyDeviceToHost, st));
@@ -988,7 +1036,7 @@ int u3d_ob_build_depth_hierarchy(u3d_ob* ob)
     if (!ob->allocated || !ob->hierarchyDirty) // OB.cpp:236
         return U3D_OK;
     CU_CHECK(cudaSetDevice(ob->ctx->device));
-    launch_hierarchy(ob->vs.g, 1, ob->vs.depth.p, ob->vs.mips.p, ob->ctx->stream);
+    launch_hierarchy(ob->vs.g, 1, ob->vs.depth.p, ob->vs.mips.p, 0, ob->ctx->stream);
     CU_CHECK(cudaGetLastError());
     ob->hierarchyDirty = false;
     return U3D_OK;
@@ -1169,7 +1217,7 @@ int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, i
         pool = tri_pool ? tri_pool : std::min<uint64_t>(worst, (2ull << 30) / sizeof(TriSetup));
     }
     b->poolTris = pool;
-    int rc = b->vs.alloc(ctx, width, height, hasBuffers ? max_views : 1, itemCap, pool);
+    int rc = b->vs.alloc(ctx, width, height, hasBuffers ? max_views : 1, itemCap, pool, hasBuffers);
     cudaError_t e = cudaSuccess;
     if (rc >= 0)
     {
@@ -1252,19 +1300,40 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         CU_CHECK(cudaMemsetAsync(vs.submitted.p, 0, (size_t)V * 4, st));
         CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, (size_t)V * 4, st));
         CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
-        launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
+        if (vs.useTiles)
+        {
+            CU_CHECK(cudaMemsetAsync(vs.binCount.p, 0, (size_t)V * vs.tg.numTiles * 4, st));
+            CU_CHECK(cudaMemsetAsync(vs.irrTotal.p, 0, 4, st));
+            CU_CHECK(cudaMemsetAsync(vs.irrOfView.p, 0, (size_t)V * 4, st));
+        }
+        else
+        {
+            launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
+            b->lastLaunches += 1;
+        }
         CU_CHECK(mark(1));
         launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
         CU_CHECK(mark(2));
         launch_scan_regions(V, vs.submitted.p, 64, b->poolTris, vs.triBase.p, vs.triCap.p, vs.flags.p, st);
         CU_CHECK(mark(3));
-        launch_setup(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, vs.pool.p, vs.triBase.p,
-            vs.triCap.p, vs.triCount.p, vs.drawnSources.p, vs.flags.p, st);
+        launch_setup(vs.g, vs.tg, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p,
+            vs.raster_dev(vs.useTiles, 1), st);
         CU_CHECK(mark(4));
-        launch_fill_global(vs.g, V, vs.depth.p, vs.pool.p, vs.triBase.p, vs.triCap.p, vs.triCount.p, 8, st);
+        int firstLevel = 0;
+        if (vs.useTiles)
+        {
+            launch_fill_tiles(vs.g, vs.tg, V, vs.depth.p, vs.mips.p, vs.raster_dev(true, 1), st);
+            firstLevel = vs.tg.fused;
+            b->lastLaunches += 3;
+        }
+        else
+        {
+            launch_fill_global(vs.g, V, vs.depth.p, vs.pool.p, vs.triBase.p, vs.triCap.p, vs.triCount.p, 8, st);
+            b->lastLaunches += 1;
+        }
         CU_CHECK(mark(5));
-        launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, st);
-        b->lastLaunches += 5 + (uint32_t)vs.g.nlev;
+        launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, firstLevel, st);
+        b->lastLaunches += 3 + (uint32_t)(vs.g.nlev - firstLevel);
         CU_CHECK(cudaGetLastError());
     }
     else
@@ -1311,6 +1380,8 @@ static int batch_check_flags(u3d_batch* b, cudaStream_t st)
     uint32_t flags = 0;
     CU_CHECK(cudaMemcpyAsync(&flags, b->vs.flags.p, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
+    if (flags & kFlagIrrOverflow)
+        return fail(U3D_ERR_CAPACITY, "more than 2^20 irregular triangles in one batch (degenerate input)");
     if (flags & (kFlagTriOverflow | kFlagPoolOverflow))
         return fail(U3D_ERR_CAPACITY, "triangle pool too small for this batch: recreate the batch with a larger tri_pool");
     if (flags & kFlagOutOverflow)

@@ -130,63 +130,148 @@ __device__ __forceinline__ EdgeI make_edge(float dzdx, float dzdy, const V3& top
     return e;
 }
 
-/// ViewportTransform x3 + SignedArea + cull test + DrawTriangle2D's set-up part (OB.cpp:629-637, 815-899).
-/// Returns true when the reference would have called DrawTriangle2D (drawOk), and writes the record if the triangle has rows.
-__device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, const V4& c0, const V4& c1, const V4& c2, TriSetup& out, bool& hasRows)
+/// Where a set-up thread puts its records: the view's region of the triangle pool plus (tile path) the view's bins.
+struct EmitCtx
 {
-    V3 p[3];
-    p[0] = viewport_transform(g, c0);
-    p[1] = viewport_transform(g, c1);
-    p[2] = viewport_transform(g, c2);
-    const float aX = p[0].x - p[1].x, aY = p[0].y - p[1].y, bX = p[2].x - p[1].x, bY = p[2].y - p[1].y;
+    TriSetup* region;
+    uint32_t cap;
+    uint32_t* counter;       // triCount[v]
+    uint32_t* flags;
+    // tile path (binIdx == nullptr: general path only)
+    uint32_t* binIdx;        // numTiles x cap entries for this view
+    uint32_t* binCount;      // numTiles counters for this view
+    unsigned long long* irrList;
+    uint32_t irrCap;
+    uint32_t* irrTotal;
+    uint32_t* irrOfView;
+    uint32_t view;
+    int w, h, tileW, tilesX, tilesY;
+    int forceIrregular;
+};
+
+/// Append one record to the view's region; on the tile path also classify it and bin it.
+/// "Regular" = every span of the triangle lies inside its own row of the buffer (0 <= row < h, 0 <= xl, xr <= w for all rows),
+/// which the closed form makes checkable at the end rows of each half because x is affine in the row.  Anything else
+/// (the reference's "3D clipping is not exact" case, OB.cpp:87-90, or float garbage) goes to the general path.
+__device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
+{
+    const uint32_t slot = atomicAdd(ec.counter, 1u);
+    if (slot >= ec.cap)
+    {
+        atomicOr(ec.flags, kFlagTriOverflow);
+        return;
+    }
+    int4* dst = reinterpret_cast<int4*>(ec.region + slot);
+    dst[0] = make_int4(ts.y0, ts.y1, ts.y2, ts.dzdx);
+    dst[1] = make_int4(ts.tlx, ts.tlxs, ts.tlz, ts.tlzs);
+    dst[2] = make_int4(ts.trx, ts.trxs, ts.blx, ts.blxs);
+    dst[3] = make_int4(ts.blz, ts.blzs, ts.brx, ts.brxs);
+    if (!ec.binIdx)
+        return;
+
+    bool regular = !ec.forceIrregular && ts.y0 >= 0 && ts.y2 <= ec.h && ts.y0 < ts.y2 && ts.y1 >= ts.y0 && ts.y1 <= ts.y2;
+    const long long xLimit = ((long long)ec.w << 16) + 65535;
+    long long xmin = xLimit, xmax = 0;
+    auto edge_range = [&](int x, int xs, int rows) {
+        const long long a = x, b = (long long)x + (long long)(rows - 1) * xs;
+        if (a < 0 || a > xLimit || b < 0 || b > xLimit)
+            regular = false;
+        xmin = min(xmin, min(a, b));
+        xmax = max(xmax, max(a, b));
+    };
+    if (regular)
+    {
+        const int nt = ts.y1 - ts.y0, nb = ts.y2 - ts.y1;
+        if (nt > 0)
+        {
+            edge_range(ts.tlx, ts.tlxs, nt);
+            edge_range(ts.trx, ts.trxs, nt);
+        }
+        if (nb > 0)
+        {
+            edge_range(ts.blx, ts.blxs, nb);
+            edge_range(ts.brx, ts.brxs, nb);
+        }
+    }
+    if (!regular)
+    {
+        const uint32_t n = atomicAdd(ec.irrTotal, 1u);
+        if (n < ec.irrCap)
+        {
+            ec.irrList[n] = ((unsigned long long)ec.view << 32) | slot;
+            atomicAdd(ec.irrOfView, 1u);
+        }
+        else
+            atomicOr(ec.flags, kFlagIrrOverflow);
+        return;
+    }
+    const int x0 = (int)(xmin >> 16), x1 = (int)(xmax >> 16); // pixels touched lie in [x0, x1)
+    if (x1 <= x0)
+        return; // no pixel in any row
+    const int width = x1 - x0, height = ts.y2 - ts.y0;
+    uint32_t cls = kClsWide;
+    if (width <= 8)
+        cls = height <= 4 ? kClsSmall : kClsNarrow;
+    const int txa = x0 / ec.tileW, txb = min((x1 - 1) / ec.tileW, ec.tilesX - 1);
+    const int tya = ts.y0 / kTileH, tyb = min((ts.y2 - 1) / kTileH, ec.tilesY - 1);
+    for (int ty = tya; ty <= tyb; ++ty)
+        for (int tx = txa; tx <= txb; ++tx)
+        {
+            const int tile = ty * ec.tilesX + tx;
+            const uint32_t pos = atomicAdd(&ec.binCount[tile], 1u);
+            if (pos < ec.cap)
+                ec.binIdx[(size_t)tile * ec.cap + pos] = slot | (cls << 30);
+        }
+}
+
+/// ViewportTransform x3 + SignedArea + cull test + DrawTriangle2D's set-up part (OB.cpp:629-637, 815-899).
+/// Returns true when the reference would have called DrawTriangle2D (drawOk); emits the record if the triangle has rows.
+__device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, const V4& c0, const V4& c1, const V4& c2, const EmitCtx& ec)
+{
+    const V3 p0 = viewport_transform(g, c0);
+    const V3 p1 = viewport_transform(g, c1);
+    const V3 p2 = viewport_transform(g, c2);
+    const float aX = p0.x - p1.x, aY = p0.y - p1.y, bX = p2.x - p1.x, bY = p2.y - p1.y;
     const bool clockwise = (aX * bY - aY * bX) < 0.0f; // SignedArea, OB.cpp:569-576
-    hasRows = false;
     if (!(cullMode == CULL_NONE || (cullMode == CULL_CCW && clockwise) || (cullMode == CULL_CW && !clockwise)))
         return false;
 
-    // Y sort, OB.cpp:820-872
-    int top, mid, bot;
+    // Y sort, OB.cpp:820-872 (written with selects so the vertices stay in registers)
+    V3 vt, vm, vb;
     bool midRight;
-    if (p[0].y < p[1].y)
+    if (p0.y < p1.y)
     {
-        if (p[2].y < p[0].y) { top = 2; mid = 0; bot = 1; midRight = true; }
-        else
-        {
-            top = 0;
-            if (p[1].y < p[2].y) { mid = 1; bot = 2; midRight = true; }
-            else { mid = 2; bot = 1; midRight = false; }
-        }
+        if (p2.y < p0.y) { vt = p2; vm = p0; vb = p1; midRight = true; }
+        else if (p1.y < p2.y) { vt = p0; vm = p1; vb = p2; midRight = true; }
+        else { vt = p0; vm = p2; vb = p1; midRight = false; }
     }
     else
     {
-        if (p[2].y < p[1].y) { top = 2; mid = 1; bot = 0; midRight = false; }
-        else
-        {
-            top = 1;
-            if (p[0].y < p[2].y) { mid = 0; bot = 2; midRight = false; }
-            else { mid = 2; bot = 0; midRight = true; }
-        }
+        if (p2.y < p1.y) { vt = p2; vm = p1; vb = p0; midRight = false; }
+        else if (p0.y < p2.y) { vt = p1; vm = p0; vb = p2; midRight = false; }
+        else { vt = p1; vm = p2; vb = p0; midRight = true; }
     }
-    const V3 vt = p[top], vm = p[mid], vb = p[bot];
     const int topY = trunc_x86(vt.y), midY = trunc_x86(vm.y), botY = trunc_x86(vb.y);
     if (topY == botY)
-        return true; // degenerate: reference returns from DrawTriangle2D but drawOk is already set
+        return true; // degenerate: the reference returns from DrawTriangle2D, but drawOk is already set
     if (!clockwise)
         midRight = !midRight;
 
     // Gradients, OB.cpp:762-778
-    const float invdX = 1.0f / (((p[1].x - p[2].x) * (p[0].y - p[2].y)) - ((p[0].x - p[2].x) * (p[1].y - p[2].y)));
+    const float invdX = 1.0f / (((p1.x - p2.x) * (p0.y - p2.y)) - ((p0.x - p2.x) * (p1.y - p2.y)));
     const float invdY = -invdX;
-    const float dzdx = invdX * (((p[1].z - p[2].z) * (p[0].y - p[2].y)) - ((p[0].z - p[2].z) * (p[1].y - p[2].y)));
-    const float dzdy = invdY * (((p[1].z - p[2].z) * (p[0].x - p[2].x)) - ((p[0].z - p[2].z) * (p[1].x - p[2].x)));
+    const float dzdx = invdX * (((p1.z - p2.z) * (p0.y - p2.y)) - ((p0.z - p2.z) * (p1.y - p2.y)));
+    const float dzdy = invdY * (((p1.z - p2.z) * (p0.x - p2.x)) - ((p0.z - p2.z) * (p1.x - p2.x)));
 
+    TriSetup out;
     out.y0 = topY;
     out.y1 = midY;
     out.y2 = botY;
     out.dzdx = trunc_x86(dzdx);
     const EdgeI lng = make_edge(dzdx, dzdy, vt, vb, topY);
     // long edge advanced to the first row of the bottom half (it is stepped once per top-half row, OB.cpp:915-916)
-    const uint32_t kTop = (uint32_t)midY - (uint32_t)topY;
+    // (no top-half rows -> no steps: the reference's row loop simply does not run when middleY <= topY)
+    const uint32_t kTop = midY > topY ? (uint32_t)midY - (uint32_t)topY : 0u;
     const int lngBx = (int)((uint32_t)lng.x + kTop * (uint32_t)lng.xs);
     const int lngBz = (int)((uint32_t)lng.z + kTop * (uint32_t)lng.zs);
     EdgeI et = {0, 0, 0, 0}, eb = {0, 0, 0, 0};
@@ -204,7 +289,7 @@ __device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, c
         out.tlx = et.x; out.tlxs = et.xs; out.tlz = et.z; out.tlzs = et.zs; out.trx = lng.x; out.trxs = lng.xs;
         out.blx = eb.x; out.blxs = eb.xs; out.blz = eb.z; out.blzs = eb.zs; out.brx = lngBx; out.brxs = lng.xs;
     }
-    hasRows = true;
+    emit_tri(ec, out);
     return true;
 }
 
@@ -278,19 +363,8 @@ __device__ __noinline__ void clip_plane(float px, float py, float pz, float pw, 
     }
 }
 
-/// Append one record to the view's region (warp-uncoordinated; callers are divergent).
-__device__ __forceinline__ void emit_tri(const TriSetup& ts, TriSetup* __restrict__ region, uint32_t cap, uint32_t* __restrict__ counter, uint32_t* __restrict__ flags)
-{
-    const uint32_t slot = atomicAdd(counter, 1u);
-    if (slot < cap)
-        region[slot] = ts;
-    else
-        atomicOr(flags, kFlagTriOverflow);
-}
-
 /// Slow path of DrawTriangle (OB.cpp:640-679): clip against the flagged planes, then set up every surviving piece.
-__device__ __noinline__ bool clip_and_setup(const BufGeom& g, int cullMode, unsigned clipMask, V4 c0, V4 c1, V4 c2, TriSetup* region,
-    uint32_t cap, uint32_t* counter, uint32_t* flags)
+__device__ __noinline__ bool clip_and_setup(const BufGeom& g, int cullMode, unsigned clipMask, V4 c0, V4 c1, V4 c2, const EmitCtx& ec)
 {
     V4 vv[64 * 3];
     vv[0] = c0;
@@ -309,135 +383,152 @@ __device__ __noinline__ bool clip_and_setup(const BufGeom& g, int cullMode, unsi
     {
         if (!((live >> i) & 1))
             continue;
-        TriSetup ts;
-        bool rows;
-        if (setup_triangle(g, cullMode, vv[3 * i], vv[3 * i + 1], vv[3 * i + 2], ts, rows))
-        {
+        if (setup_triangle(g, cullMode, vv[3 * i], vv[3 * i + 1], vv[3 * i + 2], ec))
             drawOk = true;
-            if (rows)
-                emit_tri(ts, region, cap, counter, flags);
-        }
     }
     return drawOk;
 }
 
-/// One block = kSetupItems draw items of one view; threads sweep the flat triangle index space of those items.
-/// DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
-__global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, const ViewConst* __restrict__ views,
+/// Blocks of a view sweep its draw items in slices of kSetupItems; inside a slice the threads sweep the flat triangle index
+/// space of those items.  DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
+__global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
     const DrawItem* __restrict__ items, uint32_t itemCap, const uint32_t* __restrict__ itemCount, const float* __restrict__ models,
-    const MeshDev* __restrict__ meshes, TriSetup* __restrict__ pool, const uint64_t* __restrict__ triBase, const uint32_t* __restrict__ triCap,
-    uint32_t* __restrict__ triCount, uint32_t* __restrict__ drawnSources, uint32_t* __restrict__ flags)
+    const MeshDev* __restrict__ meshes, RasterDev rd)
 {
     const int v = blockIdx.y;
     const uint32_t nItems = itemCount[v];
-    const uint32_t itemBase = blockIdx.x * kSetupItems;
-    if (itemBase >= nItems)
-        return;
-    const uint32_t nLocal = min((uint32_t)kSetupItems, nItems - itemBase);
 
     __shared__ float sMvp[kSetupItems][16];
     __shared__ DrawItem sItem[kSetupItems];
     __shared__ uint32_t sPre[kSetupItems + 1];
 
     const ViewConst& vc = views[v];
-    if (threadIdx.x < nLocal)
-        sItem[threadIdx.x] = items[(size_t)v * itemCap + itemBase + threadIdx.x];
-    __syncthreads();
-    // modelViewProj = viewProj_ * model  (Matrix4 * Matrix3x4, Matrix4.cpp:43-63)
-    for (uint32_t e = threadIdx.x; e < nLocal * 16; e += blockDim.x)
-    {
-        const uint32_t it = e >> 4, r = (e >> 2) & 3, c = e & 3;
-        const float* a = vc.vp + 4 * r;
-        const float* b = models + 12 * (size_t)sItem[it].model;
-        float val;
-        if (c < 3)
-            val = a[0] * b[c] + a[1] * b[4 + c] + a[2] * b[8 + c];
-        else
-            val = a[0] * b[3] + a[1] * b[7] + a[2] * b[11] + a[3];
-        sMvp[it][4 * r + c] = val;
-    }
-    if (threadIdx.x == 0)
-    {
-        uint32_t acc = 0;
-        for (uint32_t i = 0; i < nLocal; ++i)
-        {
-            sPre[i] = acc;
-            acc += sItem[i].count / 3;
-        }
-        sPre[nLocal] = acc;
-    }
-    __syncthreads();
-
-    const uint32_t total = sPre[nLocal];
-    TriSetup* region = pool + triBase[v];
-    const uint32_t cap = triCap[v];
     const int cullMode = vc.cullMode;
-    uint32_t drawn = 0;
-    for (uint32_t t = threadIdx.x; t < total; t += blockDim.x)
-    {
-        // owning item: largest i with sPre[i] <= t
-        uint32_t lo = 0, hi = nLocal;
-        while (hi - lo > 1)
-        {
-            const uint32_t m = (lo + hi) >> 1;
-            if (sPre[m] <= t) lo = m; else hi = m;
-        }
-        const DrawItem& it = sItem[lo];
-        const MeshDev mesh = meshes[it.mesh];
-        const uint32_t first = it.start + 3 * (t - sPre[lo]);
-        uint32_t i0, i1, i2;
-        if (mesh.idx == nullptr)
-        {
-            i0 = first; i1 = first + 1; i2 = first + 2;
-        }
-        else if (mesh.idxSize == 2)
-        {
-            const unsigned short* ix = (const unsigned short*)mesh.idx;
-            i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
-        }
-        else
-        {
-            const unsigned* ix = (const unsigned*)mesh.idx;
-            i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
-        }
-        const float* p0 = (const float*)(mesh.vtx + (size_t)i0 * mesh.stride);
-        const float* p1 = (const float*)(mesh.vtx + (size_t)i1 * mesh.stride);
-        const float* p2 = (const float*)(mesh.vtx + (size_t)i2 * mesh.stride);
-        const float* mvp = sMvp[lo];
-        const V4 c0 = model_transform(mvp, p0[0], p0[1], p0[2]);
-        const V4 c1 = model_transform(mvp, p1[0], p1[1], p1[2]);
-        const V4 c2 = model_transform(mvp, p2[0], p2[1], p2[2]);
+    EmitCtx ec;
+    ec.region = rd.pool + rd.triBase[v];
+    ec.cap = rd.triCap[v];
+    ec.counter = rd.triCount + v;
+    ec.flags = rd.flags;
+    ec.binIdx = rd.binIdx ? rd.binIdx + rd.triBase[v] * (size_t)tg.numTiles : nullptr;
+    ec.binCount = rd.binCount ? rd.binCount + (size_t)v * tg.numTiles : nullptr;
+    ec.irrList = rd.irrList;
+    ec.irrCap = rd.irrCap;
+    ec.irrTotal = rd.irrTotal;
+    ec.irrOfView = rd.irrOfView ? rd.irrOfView + v : nullptr;
+    ec.view = (uint32_t)v;
+    ec.w = g.w;
+    ec.h = g.h;
+    ec.tileW = tg.tileW;
+    ec.tilesX = tg.tilesX;
+    ec.tilesY = tg.tilesY;
+    ec.forceIrregular = rd.forceIrregular;
 
-        // clip masks, OB.cpp:596-620
-        unsigned m0 = 0, m1 = 0, m2 = 0;
-        if (c0.x > c0.w) m0 |= 1; if (c0.x < -c0.w) m0 |= 2; if (c0.y > c0.w) m0 |= 4; if (c0.y < -c0.w) m0 |= 8; if (c0.z > c0.w) m0 |= 16; if (c0.z < 0.0f) m0 |= 32;
-        if (c1.x > c1.w) m1 |= 1; if (c1.x < -c1.w) m1 |= 2; if (c1.y > c1.w) m1 |= 4; if (c1.y < -c1.w) m1 |= 8; if (c1.z > c1.w) m1 |= 16; if (c1.z < 0.0f) m1 |= 32;
-        if (c2.x > c2.w) m2 |= 1; if (c2.x < -c2.w) m2 |= 2; if (c2.y > c2.w) m2 |= 4; if (c2.y < -c2.w) m2 |= 8; if (c2.z > c2.w) m2 |= 16; if (c2.z < 0.0f) m2 |= 32;
-        if (m0 & m1 & m2)
-            continue;
-        const unsigned clipMask = m0 | m1 | m2;
-        bool drawOk;
-        if (!clipMask)
+    uint32_t drawn = 0;
+    for (uint32_t itemBase = blockIdx.x * kSetupItems; itemBase < nItems; itemBase += gridDim.x * kSetupItems)
+    {
+        const uint32_t nLocal = min((uint32_t)kSetupItems, nItems - itemBase);
+        __syncthreads(); // previous slice fully consumed
+        if (threadIdx.x < nLocal)
+            sItem[threadIdx.x] = items[(size_t)v * itemCap + itemBase + threadIdx.x];
+        __syncthreads();
+        // modelViewProj = viewProj_ * model  (Matrix4 * Matrix3x4, Matrix4.cpp:43-63)
+        for (uint32_t e = threadIdx.x; e < nLocal * 16; e += blockDim.x)
         {
-            TriSetup ts;
-            bool rows;
-            drawOk = setup_triangle(g, cullMode, c0, c1, c2, ts, rows);
-            if (drawOk && rows)
-                emit_tri(ts, region, cap, &triCount[v], flags);
+            const uint32_t it = e >> 4, r = (e >> 2) & 3, c = e & 3;
+            const float* a = vc.vp + 4 * r;
+            const float* b = models + 12 * (size_t)sItem[it].model;
+            float val;
+            if (c < 3)
+                val = a[0] * b[c] + a[1] * b[4 + c] + a[2] * b[8 + c];
+            else
+                val = a[0] * b[3] + a[1] * b[7] + a[2] * b[11] + a[3];
+            sMvp[it][4 * r + c] = val;
         }
-        else
-            drawOk = clip_and_setup(g, cullMode, clipMask, c0, c1, c2, region, cap, &triCount[v], flags);
-        drawn += drawOk ? 1u : 0u;
+        if (threadIdx.x < 32)
+        {
+            // exclusive scan of the items' triangle counts (kSetupItems <= 64: two elements per lane)
+            uint32_t acc = 0;
+            for (uint32_t base = 0; base < kSetupItems; base += 32)
+            {
+                const uint32_t i = base + threadIdx.x;
+                const uint32_t c = i < nLocal ? sItem[i].count / 3 : 0;
+                uint32_t x = c;
+                for (int o = 1; o < 32; o <<= 1)
+                {
+                    const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                    if ((int)threadIdx.x >= o)
+                        x += y;
+                }
+                if (i < kSetupItems)
+                    sPre[i] = acc + x - c;
+                acc += __shfl_sync(0xffffffffu, x, 31);
+            }
+            if (threadIdx.x == 0)
+                sPre[kSetupItems] = acc;
+        }
+        __syncthreads();
+
+        const uint32_t total = sPre[kSetupItems];
+        for (uint32_t t = threadIdx.x; t < total; t += blockDim.x)
+        {
+            // owning item: largest i < nLocal with sPre[i] <= t
+            uint32_t lo = 0, hi = nLocal;
+            while (hi - lo > 1)
+            {
+                const uint32_t m = (lo + hi) >> 1;
+                if (sPre[m] <= t) lo = m; else hi = m;
+            }
+            const DrawItem& it = sItem[lo];
+            const MeshDev mesh = meshes[it.mesh];
+            const uint32_t first = it.start + 3 * (t - sPre[lo]);
+            uint32_t i0, i1, i2;
+            if (mesh.idx == nullptr)
+            {
+                i0 = first; i1 = first + 1; i2 = first + 2;
+            }
+            else if (mesh.idxSize == 2)
+            {
+                const unsigned short* ix = (const unsigned short*)mesh.idx;
+                i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+            }
+            else
+            {
+                const unsigned* ix = (const unsigned*)mesh.idx;
+                i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+            }
+            const float* p0 = (const float*)(mesh.vtx + (size_t)i0 * mesh.stride);
+            const float* p1 = (const float*)(mesh.vtx + (size_t)i1 * mesh.stride);
+            const float* p2 = (const float*)(mesh.vtx + (size_t)i2 * mesh.stride);
+            const float* mvp = sMvp[lo];
+            const V4 c0 = model_transform(mvp, p0[0], p0[1], p0[2]);
+            const V4 c1 = model_transform(mvp, p1[0], p1[1], p1[2]);
+            const V4 c2 = model_transform(mvp, p2[0], p2[1], p2[2]);
+
+            // clip masks, OB.cpp:596-620
+            unsigned m0 = 0, m1 = 0, m2 = 0;
+            if (c0.x > c0.w) m0 |= 1; if (c0.x < -c0.w) m0 |= 2; if (c0.y > c0.w) m0 |= 4; if (c0.y < -c0.w) m0 |= 8; if (c0.z > c0.w) m0 |= 16; if (c0.z < 0.0f) m0 |= 32;
+            if (c1.x > c1.w) m1 |= 1; if (c1.x < -c1.w) m1 |= 2; if (c1.y > c1.w) m1 |= 4; if (c1.y < -c1.w) m1 |= 8; if (c1.z > c1.w) m1 |= 16; if (c1.z < 0.0f) m1 |= 32;
+            if (c2.x > c2.w) m2 |= 1; if (c2.x < -c2.w) m2 |= 2; if (c2.y > c2.w) m2 |= 4; if (c2.y < -c2.w) m2 |= 8; if (c2.z > c2.w) m2 |= 16; if (c2.z < 0.0f) m2 |= 32;
+            if (m0 & m1 & m2)
+                continue;
+            const unsigned clipMask = m0 | m1 | m2;
+            bool drawOk;
+            if (!clipMask)
+                drawOk = setup_triangle(g, cullMode, c0, c1, c2, ec);
+            else
+                drawOk = clip_and_setup(g, cullMode, clipMask, c0, c1, c2, ec);
+            drawn += drawOk ? 1u : 0u;
+        }
     }
     // ++numTriangles_ per source triangle that drew anything (OB.cpp:681-682)
     for (int o = 16; o; o >>= 1)
         drawn += __shfl_xor_sync(0xffffffffu, drawn, o);
     if ((threadIdx.x & 31) == 0 && drawn)
-        atomicAdd(&drawnSources[v], drawn);
+        atomicAdd(&rd.drawnSources[v], drawn);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// fill (general path): one warp per set-up triangle, lanes across the span, atomicMin straight into the view's plane in
+// fill, general path: one warp per set-up triangle, lanes across the span, atomicMin straight into the view's plane in
 // global memory with the reference's linear addressing (row + x may spill into the neighbouring row, SURVEY hard part 4).
 // Handles every record, including the irregular ones the tile path refuses.
 // ---------------------------------------------------------------------------------------------------------------
@@ -468,6 +559,15 @@ __device__ __forceinline__ void fill_half_global(int* __restrict__ depth, int w,
     }
 }
 
+__device__ __forceinline__ void fill_tri_global(int* __restrict__ depth, int w, int h, const TriSetup& ts, int lane)
+{
+    if (ts.y0 != ts.y1)
+        fill_half_global(depth, w, h, ts.y0, ts.y1, ts.tlx, ts.tlxs, ts.tlz, ts.tlzs, ts.trx, ts.trxs, ts.dzdx, lane);
+    if (ts.y1 != ts.y2)
+        fill_half_global(depth, w, h, ts.y1, ts.y2, ts.blx, ts.blxs, ts.blz, ts.blzs, ts.brx, ts.brxs, ts.dzdx, lane);
+}
+
+/// Every record of every view (the OcclusionBuffer drop-in path, which accumulates into an existing plane).
 __global__ void __launch_bounds__(256) k_fill_global(BufGeom g, int* __restrict__ depthAll, const TriSetup* __restrict__ pool,
     const uint64_t* __restrict__ triBase, const uint32_t* __restrict__ triCap, const uint32_t* __restrict__ triCount)
 {
@@ -480,10 +580,290 @@ __global__ void __launch_bounds__(256) k_fill_global(BufGeom g, int* __restrict_
     for (uint32_t t = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); t < n; t += gridDim.x * warpsPerBlock)
     {
         const TriSetup ts = region[t];
-        if (ts.y0 != ts.y1)
-            fill_half_global(depth, g.w, g.h, ts.y0, ts.y1, ts.tlx, ts.tlxs, ts.tlz, ts.tlzs, ts.trx, ts.trxs, ts.dzdx, lane);
-        if (ts.y1 != ts.y2)
-            fill_half_global(depth, g.w, g.h, ts.y1, ts.y2, ts.blx, ts.blxs, ts.blz, ts.blzs, ts.brx, ts.brxs, ts.dzdx, lane);
+        fill_tri_global(depth, g.w, g.h, ts, lane);
+    }
+}
+
+/// Tile path, pre-pass 1: views that own irregular triangles get their plane cleared in global memory (the tile kernel then starts
+/// from that plane instead of from the clear value).
+__global__ void k_irregular_clear(BufGeom g, int* __restrict__ depthAll, const uint32_t* __restrict__ irrOfView)
+{
+    const int v = blockIdx.y;
+    if (!irrOfView[v])
+        return;
+    int* depth = depthAll + (size_t)v * g.w * g.h;
+    const int n = g.w * g.h;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        depth[i] = kClearDepth;
+}
+
+/// Tile path, pre-pass 2: the irregular triangles themselves, through the general path.
+__global__ void __launch_bounds__(256) k_irregular_fill(BufGeom g, int* __restrict__ depthAll, const TriSetup* __restrict__ pool,
+    const uint64_t* __restrict__ triBase, const unsigned long long* __restrict__ irrList, uint32_t irrCap, const uint32_t* __restrict__ irrTotal)
+{
+    const uint32_t n = min(*irrTotal, irrCap);
+    const int lane = threadIdx.x & 31;
+    const uint32_t warpsPerBlock = blockDim.x >> 5;
+    for (uint32_t i = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); i < n; i += gridDim.x * warpsPerBlock)
+    {
+        const unsigned long long e = irrList[i];
+        const uint32_t v = (uint32_t)(e >> 32), slot = (uint32_t)e;
+        const TriSetup ts = pool[triBase[v] + slot];
+        fill_tri_global(depthAll + (size_t)v * g.w * g.h, g.w, g.h, ts, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// fill, tile path: one CTA per (view, screen tile).  The tile's integer depth lives in shared memory; the CTA walks the tile's
+// bin of regular triangles, composites with shared-memory atomicMin, then writes the tile to HBM once and reduces it to the
+// first `fused` levels of the depth hierarchy while it is still on chip (BuildDepthHierarchy, OB.cpp:234-329).
+// ---------------------------------------------------------------------------------------------------------------
+struct HalfRow { int xl, xr; uint32_t z0; };
+
+/// Span of row y of a regular triangle (closed form, see TriSetup).
+__device__ __forceinline__ HalfRow tri_row(const TriSetup& ts, int y)
+{
+    HalfRow r;
+    if (y < ts.y1)
+    {
+        const uint32_t k = (uint32_t)(y - ts.y0);
+        r.xl = (int)((uint32_t)ts.tlx + k * (uint32_t)ts.tlxs) >> 16;
+        r.xr = (int)((uint32_t)ts.trx + k * (uint32_t)ts.trxs) >> 16;
+        r.z0 = (uint32_t)ts.tlz + k * (uint32_t)ts.tlzs;
+    }
+    else
+    {
+        const uint32_t k = (uint32_t)(y - ts.y1);
+        r.xl = (int)((uint32_t)ts.blx + k * (uint32_t)ts.blxs) >> 16;
+        r.xr = (int)((uint32_t)ts.brx + k * (uint32_t)ts.brxs) >> 16;
+        r.z0 = (uint32_t)ts.blz + k * (uint32_t)ts.blzs;
+    }
+    return r;
+}
+
+__device__ __forceinline__ TriSetup load_tri(const TriSetup* p)
+{
+    const int4* q = reinterpret_cast<const int4*>(p);
+    const int4 a = q[0], b = q[1], c = q[2], d = q[3];
+    TriSetup ts;
+    ts.y0 = a.x; ts.y1 = a.y; ts.y2 = a.z; ts.dzdx = a.w;
+    ts.tlx = b.x; ts.tlxs = b.y; ts.tlz = b.z; ts.tlzs = b.w;
+    ts.trx = c.x; ts.trxs = c.y; ts.blx = c.z; ts.blxs = c.w;
+    ts.blz = d.x; ts.blzs = d.y; ts.brx = d.z; ts.brxs = d.w;
+    return ts;
+}
+
+__device__ __forceinline__ TriSetup bcast_tri(const TriSetup& t, int src)
+{
+    TriSetup r;
+    r.y0 = __shfl_sync(0xffffffffu, t.y0, src); r.y1 = __shfl_sync(0xffffffffu, t.y1, src);
+    r.y2 = __shfl_sync(0xffffffffu, t.y2, src); r.dzdx = __shfl_sync(0xffffffffu, t.dzdx, src);
+    r.tlx = __shfl_sync(0xffffffffu, t.tlx, src); r.tlxs = __shfl_sync(0xffffffffu, t.tlxs, src);
+    r.tlz = __shfl_sync(0xffffffffu, t.tlz, src); r.tlzs = __shfl_sync(0xffffffffu, t.tlzs, src);
+    r.trx = __shfl_sync(0xffffffffu, t.trx, src); r.trxs = __shfl_sync(0xffffffffu, t.trxs, src);
+    r.blx = __shfl_sync(0xffffffffu, t.blx, src); r.blxs = __shfl_sync(0xffffffffu, t.blxs, src);
+    r.blz = __shfl_sync(0xffffffffu, t.blz, src); r.blzs = __shfl_sync(0xffffffffu, t.blzs, src);
+    r.brx = __shfl_sync(0xffffffffu, t.brx, src); r.brxs = __shfl_sync(0xffffffffu, t.brxs, src);
+    return r;
+}
+
+__device__ __forceinline__ void tile_min(int* tile, int idx, int z)
+{
+    if (z < tile[idx])
+        atomicMin(tile + idx, z);
+}
+
+__global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
+{
+    extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
+    __shared__ uint32_t sNext;
+
+    const int v = blockIdx.y;
+    const int tIdx = blockIdx.x;
+    const int tx0 = (tIdx % tg.tilesX) * tg.tileW, ty0 = (tIdx / tg.tilesX) * kTileH;
+    const int tw = tg.tileW;
+    const int rows = min(kTileH, g.h - ty0); // valid rows of this tile
+    const int tid = threadIdx.x, lane = tid & 31;
+    int* depth = depthAll + (size_t)v * g.w * g.h;
+    const bool fromGlobal = rd.irrOfView[v] != 0;
+
+    // ---- initialise ----
+    {
+        const int n4 = (tw * kTileH) >> 2;
+        int4* t4 = reinterpret_cast<int4*>(tile);
+        const int tw4 = tw >> 2;
+        for (int i = tid; i < n4; i += kTileThreads)
+        {
+            int4 val = make_int4(kClearDepth, kClearDepth, kClearDepth, kClearDepth);
+            const int r = i / tw4;
+            if (fromGlobal && r < rows)
+                val = *reinterpret_cast<const int4*>(depth + (size_t)(ty0 + r) * g.w + tx0 + ((i % tw4) << 2));
+            t4[i] = val;
+        }
+        if (tid == 0)
+            sNext = 0;
+    }
+    __syncthreads();
+
+    // ---- composite the bin ----
+    const uint32_t cap = rd.triCap[v];
+    const uint32_t nBin = min(rd.binCount[(size_t)v * tg.numTiles + tIdx], cap);
+    const uint32_t* bin = rd.binIdx + (rd.triBase[v] * (size_t)tg.numTiles + (size_t)tIdx * cap);
+    const TriSetup* region = rd.pool + rd.triBase[v];
+    const int ty1 = ty0 + rows, tx1 = tx0 + tw;
+    for (;;)
+    {
+        uint32_t base = 0;
+        if (lane == 0)
+            base = atomicAdd(&sNext, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= nBin)
+            break;
+        const uint32_t mine = base + lane < nBin ? bin[base + lane] : 0xFFFFFFFFu;
+        const uint32_t cls = mine >> 30; // 3 = no entry
+        // every lane fetches its own record first (one L2 round trip for the whole group); cooperative triangles are then
+        // broadcast from the owning lane's registers
+        TriSetup my;
+        if (cls != 3u)
+            my = load_tri(region + (mine & 0x3FFFFFFFu));
+        // small triangles: one per lane
+        if (cls == kClsSmall)
+        {
+            const int ya = max(my.y0, ty0), yb = min(my.y2, ty1);
+            for (int y = ya; y < yb; ++y)
+            {
+                const HalfRow r = tri_row(my, y);
+                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                int* trow = tile + (y - ty0) * tw - tx0;
+                for (int x = xa; x < xb; ++x)
+                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)my.dzdx));
+            }
+        }
+        // narrow triangles: the warp takes one at a time, one row per lane
+        uint32_t todo = __ballot_sync(0xffffffffu, cls == kClsNarrow);
+        while (todo)
+        {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const TriSetup ts = bcast_tri(my, src);
+            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+            for (int y = ya + lane; y < yb; y += 32)
+            {
+                const HalfRow r = tri_row(ts, y);
+                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                int* trow = tile + (y - ty0) * tw - tx0;
+                for (int x = xa; x < xb; ++x)
+                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+            }
+        }
+        // wide triangles: the warp takes one at a time, row by row, lanes across the span
+        todo = __ballot_sync(0xffffffffu, cls == kClsWide);
+        while (todo)
+        {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const TriSetup ts = bcast_tri(my, src);
+            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+            for (int y = ya; y < yb; ++y)
+            {
+                const HalfRow r = tri_row(ts, y);
+                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                int* trow = tile + (y - ty0) * tw - tx0;
+                for (int x = xa + lane; x < xb; x += 32)
+                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- write the tile's depth to HBM ----
+    {
+        const int tw4 = tw >> 2;
+        const int n4 = tw4 * rows;
+        const int4* t4 = reinterpret_cast<const int4*>(tile);
+        for (int i = tid; i < n4; i += kTileThreads)
+        {
+            const int r = i / tw4, c4 = i % tw4;
+            *reinterpret_cast<int4*>(depth + (size_t)(ty0 + r) * g.w + tx0 + (c4 << 2)) = t4[i];
+        }
+    }
+    if (!tg.fused || !rd.writeMips)
+        return;
+
+    // ---- fused depth hierarchy ----
+    // Level 0 is computed in place: every thread first pulls its inputs into registers, then (after a barrier) the (min,max) pairs
+    // overwrite the front of the tile.  Further levels go to fresh regions behind it.
+    int2* mips = mipAll + (size_t)v * g.mipTexels;
+    int2* lv0 = reinterpret_cast<int2*>(tile);
+    constexpr int kPerThread = (256 / 2) * (kTileH / 2) / kTileThreads; // level-0 texels per thread for the widest tile
+    {
+        const int lw = tw >> 1;                          // texels per row of this tile at level 0
+        const int lrows = (rows + 1) >> 1;               // texel rows of this tile at level 0
+        const int n = lw * lrows;
+        int2 acc[kPerThread];
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j)
+        {
+            const int i = tid + j * kTileThreads;
+            if (i < n)
+            {
+                const int x = i % lw, y = i / lw;
+                const int2 a = *reinterpret_cast<const int2*>(tile + (2 * y) * tw + 2 * x);
+                int mn = min(a.x, a.y), mx = max(a.x, a.y);
+                if (2 * y + 1 < rows) // the buffer's last row pair may be a single row only when h is odd; heights are even, kept for safety
+                {
+                    const int2 b = *reinterpret_cast<const int2*>(tile + (2 * y + 1) * tw + 2 * x);
+                    mn = min(mn, min(b.x, b.y));
+                    mx = max(mx, max(b.x, b.y));
+                }
+                acc[j] = make_int2(mn, mx);
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < kPerThread; ++j)
+        {
+            const int i = tid + j * kTileThreads;
+            if (i < n)
+            {
+                const int x = i % lw, y = i / lw;
+                lv0[i] = acc[j];
+                mips[g.moff[0] + (size_t)((ty0 >> 1) + y) * g.mw[0] + (tx0 >> 1) + x] = acc[j];
+            }
+        }
+        __syncthreads();
+    }
+    int2* prev = lv0;
+    int prevW = tw >> 1, prevRows = (rows + 1) >> 1;
+    int2* next = lv0 + (tw >> 1) * (kTileH >> 1);
+    for (int lv = 1; lv < tg.fused; ++lv)
+    {
+        const int lw = tw >> (lv + 1);
+        const int gy0 = ty0 >> (lv + 1), gx0 = tx0 >> (lv + 1);
+        // rows of this level that belong to the tile: those whose children rows exist in prev
+        const int lrows = (prevRows + 1) >> 1;
+        const int prevGlobalH = g.mh[lv - 1], prevGy0 = ty0 >> lv;
+        const int n = lw * lrows;
+        for (int i = tid; i < n; i += kTileThreads)
+        {
+            const int x = i % lw, y = i / lw;
+            const int2 a = prev[(2 * y) * prevW + 2 * x], b = prev[(2 * y) * prevW + 2 * x + 1];
+            int mn = min(a.x, b.x), mx = max(a.y, b.y);
+            if (prevGy0 + 2 * y + 1 < prevGlobalH) // odd previous height: the last row reduces a single row (OB.cpp:297-324)
+            {
+                const int2 c = prev[(2 * y + 1) * prevW + 2 * x], d = prev[(2 * y + 1) * prevW + 2 * x + 1];
+                mn = min(mn, min(c.x, d.x));
+                mx = max(mx, max(c.y, d.y));
+            }
+            const int2 o = make_int2(mn, mx);
+            next[i] = o;
+            mips[g.moff[lv] + (size_t)(gy0 + y) * g.mw[lv] + gx0 + x] = o;
+        }
+        __syncthreads();
+        prev = next;
+        prevW = lw;
+        prevRows = lrows;
+        next = next + lw * (kTileH >> (lv + 1));
     }
 }
 
@@ -529,6 +909,22 @@ __global__ void k_mip_level(BufGeom g, int lv, const int* __restrict__ depthAll,
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
+TileGeom make_tile_geom(const BufGeom& g)
+{
+    TileGeom t{};
+    t.tileW = g.w < 256 ? g.w : 256;
+    t.tilesX = g.w / t.tileW;
+    t.tilesY = (g.h + kTileH - 1) / kTileH;
+    t.numTiles = t.tilesX * t.tilesY;
+    // levels that can be reduced inside one tile: both tile dimensions must cover whole texels of the level
+    int f = 0;
+    while (f < g.nlev && (2 << f) <= t.tileW && (2 << f) <= kTileH)
+        ++f;
+    // the in-place level-0 pass keeps its inputs in registers: needs tileW >= 4 for the int4 paths
+    t.fused = t.tileW >= 4 ? f : 0;
+    return t;
+}
+
 void launch_clear(int* depth, size_t nInts, cudaStream_t s)
 {
     if (!nInts)
@@ -560,14 +956,16 @@ void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack
     k_scan_regions<<<1, 1024, 0, s>>>(numViews, submitted, slack, poolCap, triBase, triCap, flags);
 }
 
-void launch_setup(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems, const uint32_t* itemCount,
-    const float* models, const MeshDev* meshes, TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap, uint32_t* triCount,
-    uint32_t* drawnSources, uint32_t* flags, cudaStream_t s)
+void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
+    const uint32_t* itemCount, const float* models, const MeshDev* meshes, const RasterDev& rd, cudaStream_t s)
 {
     if (!maxItems || !numViews)
         return;
-    dim3 grid((maxItems + kSetupItems - 1) / kSetupItems, numViews);
-    k_setup_triangles<<<grid, kSetupThreads, 0, s>>>(g, views, items, itemCap, itemCount, models, meshes, pool, triBase, triCap, triCount, drawnSources, flags);
+    uint32_t slices = (maxItems + kSetupItems - 1) / kSetupItems;
+    // a few blocks per view sweep its item slices; single views get as many blocks as they have slices
+    const uint32_t perView = numViews >= 148 ? 8u : 1024u;
+    dim3 grid(slices < perView ? slices : perView, numViews);
+    k_setup_triangles<<<grid, kSetupThreads, 0, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd);
 }
 
 void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,
@@ -579,11 +977,25 @@ void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSet
     k_fill_global<<<grid, 256, 0, s>>>(g, depth, pool, triBase, triCap, triCount);
 }
 
-void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, cudaStream_t s)
+cudaError_t init_tile_kernel()
+{
+    return cudaFuncSetAttribute(k_fill_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kTileH * 4);
+}
+
+void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* depth, int2* mips, const RasterDev& rd, cudaStream_t s)
 {
     if (!numViews)
         return;
-    for (int lv = 0; lv < g.nlev; ++lv)
+    k_irregular_clear<<<dim3(4, numViews), 256, 0, s>>>(g, depth, rd.irrOfView);
+    k_irregular_fill<<<148, 256, 0, s>>>(g, depth, rd.pool, rd.triBase, rd.irrList, rd.irrCap, rd.irrTotal);
+    k_fill_tiles<<<dim3(tg.numTiles, numViews), kTileThreads, (size_t)tg.tileW * kTileH * 4, s>>>(g, tg, depth, mips, rd);
+}
+
+void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s)
+{
+    if (!numViews)
+        return;
+    for (int lv = firstLevel; lv < g.nlev; ++lv)
     {
         const int n = g.mw[lv] * g.mh[lv];
         dim3 grid((n + 255) / 256, numViews);

@@ -191,7 +191,9 @@ __device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp,
         return false;
     }
 
-    // Quadtree descent.  Stack entries: level (5 bits) | x (13 bits) | y (14 bits).
+    // Quadtree descent.  A texel is conclusive unless min < z <= max ("mixed").  A mixed texel that lies completely inside the rect
+    // proves visibility (its max is a pixel of the rect); only mixed texels cut by the rect's border are refined, so the walk
+    // costs O(perimeter) instead of the reference's O(area) per level.  Stack entries: level (5 bits) | x (13 bits) | y (14 bits).
     uint32_t stack[3 * kMaxLevels + 4];
     const int top_lv = g.nlev - 1;
     const int sh0 = top_lv + 1;
@@ -209,10 +211,16 @@ __device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp,
                     return true;      // every pixel under this texel is at least as far as z, and the texel overlaps the rect
                 if (z > t.y)
                     continue;         // every pixel under this texel is nearer than z
+                // pixels covered by this texel: [x << s, ((x+1) << s) - 1] x [y << s, ...] clipped to the buffer, s = lv + 1
+                const int s = lv + 1;
+                const int px0 = x << s, py0 = y << s;
+                const int px1 = min(((x + 1) << s) - 1, g.w - 1), py1 = min(((y + 1) << s) - 1, g.h - 1);
+                if (px0 >= left && px1 <= right && py0 >= top && py1 <= bottom)
+                    return true;      // mixed and fully inside the rect: the pixel holding max is in the rect and z <= max
                 if (lv == 0)
                 {
-                    const int x0 = max(2 * x, left), x1 = min(2 * x + 1, right);
-                    const int y0 = max(2 * y, top), y1 = min(2 * y + 1, bottom);
+                    const int x0 = max(px0, left), x1 = min(px1, right);
+                    const int y0 = max(py0, top), y1 = min(py1, bottom);
                     for (int py = y0; py <= y1; ++py)
                         for (int px = x0; px <= x1; ++px)
                             if (z <= depth[py * g.w + px])

@@ -6,7 +6,7 @@ namespace u3d
 {
 
 constexpr int kItemTris = 256;      // triangles per draw item; bigger batches are split so no block owns a huge mesh
-constexpr int kSetupItems = 32;     // draw items per set-up block
+constexpr int kSetupItems = 64;     // draw items per set-up slice (64 boxes = 768 triangles = 3 full sweeps of 256 threads)
 constexpr int kSetupThreads = 256;
 constexpr int kCullThreads = 512;
 
@@ -14,6 +14,39 @@ constexpr int kCullThreads = 512;
 constexpr uint32_t kFlagTriOverflow = 1u;   // a view's triangle region was too small
 constexpr uint32_t kFlagPoolOverflow = 2u;  // the triangle pool cannot hold all regions
 constexpr uint32_t kFlagOutOverflow = 4u;   // a view produced more results than the output capacity
+constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the general-path list holds
+
+// tile path
+constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
+constexpr int kTileThreads = 512;
+constexpr uint32_t kClsSmall = 0;   // bbox <= 8 x 4: one lane rasterises it
+constexpr uint32_t kClsNarrow = 1;  // bbox <= 8 wide: one warp, one row per lane
+constexpr uint32_t kClsWide = 2;    // one warp, row by row, lanes across the span
+
+struct TileGeom
+{
+    int tileW, tilesX, tilesY, numTiles;
+    int fused;   // hierarchy levels reduced inside the tile kernel
+};
+
+/// Device pointers of the rasteriser's per-batch state.
+struct RasterDev
+{
+    TriSetup* pool;
+    const uint64_t* triBase;     // per view: first record of its region in pool
+    const uint32_t* triCap;      // per view: region capacity
+    uint32_t* triCount;          // per view: records emitted
+    uint32_t* drawnSources;      // per view: source triangles that drew (numTriangles_ bookkeeping)
+    uint32_t* flags;
+    uint32_t* binIdx;            // per view: numTiles x triCap entries (slot | class << 30); nullptr = general path only
+    uint32_t* binCount;          // numViews x numTiles
+    unsigned long long* irrList; // (view << 32 | slot) of triangles the tile path refuses
+    uint32_t irrCap;
+    uint32_t* irrTotal;
+    uint32_t* irrOfView;         // per view
+    int writeMips;
+    int forceIrregular;          // test hook: send every triangle through the general path
+};
 
 /// Flattened octree + drawables resident in HBM (DFS pre-order = the order Octant::GetDrawablesInternal visits, Octree.cpp:229-255).
 struct SceneDev
@@ -36,12 +69,15 @@ void launch_select(const ViewConst* views, int numViews, int numOcc, const float
     const uint32_t* occCount, DrawItem* items, uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, cudaStream_t s);
 void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,
     cudaStream_t s);
-void launch_setup(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems, const uint32_t* itemCount,
-    const float* models, const MeshDev* meshes, TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap, uint32_t* triCount,
-    uint32_t* drawnSources, uint32_t* flags, cudaStream_t s);
+void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
+    const uint32_t* itemCount, const float* models, const MeshDev* meshes, const RasterDev& rd, cudaStream_t s);
 void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,
     const uint32_t* triCount, int blocksPerView, cudaStream_t s);
-void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, cudaStream_t s);
+TileGeom make_tile_geom(const BufGeom& g);
+cudaError_t init_tile_kernel();
+/// irregular pre-pass (2 launches) + tile kernel (1 launch)
+void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* depth, int2* mips, const RasterDev& rd, cudaStream_t s);
+void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s);
 
 /// Octree query (+ optional CheckVisibility predicate) for every view.  octState: numViews x numOctants bytes of scratch.
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
