@@ -13,13 +13,19 @@
 namespace u3d
 {
 
+constexpr int kRing = 4096;             // work-queue entries held in shared memory between evaluation passes
+constexpr int kRingGroups = kRing / 32;
+
 struct CullShared
 {
     ViewConst vc;
     uint32_t pre[kCullThreads + 1];   // exclusive scan of drawable counts of the current octant chunk
-    uint32_t ring[2 * kCullThreads];  // frustum survivors waiting for the occlusion test (DFS slots)
+    uint32_t ring[kRing];             // octants waiting for TestOctant / frustum survivors waiting for the occlusion test
+    uint32_t visWord[kRingGroups];    // one ballot word per group of 32 queued drawables
+    uint32_t groupOff[kRingGroups];
     uint32_t warpTot[kCullThreads / 32];
     uint32_t ringCount;
+    uint32_t nextGroup;
     uint32_t outCursor;
     uint32_t queryCount;
 };
@@ -40,16 +46,18 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t*
     if (lane == 31)
         warpTot[wid] = x;
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
+    // every warp scans the (<= 32) warp totals with shuffles
+    const uint32_t t = lane < kCullThreads / 32 ? warpTot[lane] : 0;
+    uint32_t y = t;
 #pragma unroll
-    for (int i = 0; i < kCullThreads / 32; ++i)
+    for (int o = 1; o < 32; o <<= 1)
     {
-        const uint32_t t = warpTot[i];
-        if (i < wid)
-            pre += t;
-        tot += t;
+        const uint32_t z = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= o)
+            y += z;
     }
-    total = tot;
+    total = __shfl_sync(0xffffffffu, y, 31);
+    const uint32_t pre = __shfl_sync(0xffffffffu, y - t, wid);
     return pre + x - val;
 }
 
@@ -62,16 +70,17 @@ __device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uin
     if (lane == 0)
         warpTot[wid] = __popc(bal);
     __syncthreads();
-    uint32_t pre = 0, tot = 0;
+    const uint32_t t = lane < kCullThreads / 32 ? warpTot[lane] : 0;
+    uint32_t y = t;
 #pragma unroll
-    for (int i = 0; i < kCullThreads / 32; ++i)
+    for (int o = 1; o < 32; o <<= 1)
     {
-        const uint32_t t = warpTot[i];
-        if (i < wid)
-            pre += t;
-        tot += t;
+        const uint32_t z = __shfl_up_sync(0xffffffffu, y, o);
+        if (lane >= o)
+            y += z;
     }
-    total = tot;
+    total = __shfl_sync(0xffffffffu, y, 31);
+    const uint32_t pre = __shfl_sync(0xffffffffu, y - t, wid);
     return pre + __popc(bal & ((1u << lane) - 1u));
 }
 
@@ -81,7 +90,7 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
 {
     __shared__ CullShared sh;
     const int v = blockIdx.x;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31;
 
     // view constants -> shared
     {
@@ -92,6 +101,7 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
         if (tid == 0)
         {
             sh.ringCount = 0;
+            sh.nextGroup = 0;
             sh.outCursor = 0;
             sh.queryCount = 0;
         }
@@ -100,85 +110,156 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
     const ViewConst& vc = sh.vc;
     const bool occl = vc.useOcclusion != 0;
     const bool occludedQuery = occl && vc.queryMode == QUERY_OCCLUDED;
+    const bool useMips = mipsValid != 0;
     const int* depth = depthAll + (size_t)v * g.w * g.h;
     const int2* mips = mipAll + (size_t)v * g.mipTexels;
     unsigned char* state = octStateAll + (size_t)v * sc.numOctants;
     uint32_t* out = outIdx + (size_t)v * outCap;
 
     // ---------------- phase 1: octant states (0 culled, 1 visited, 2 visited with inside == true) ----------------
+    // Per level: a sweep queues the octants whose parent survived (dense queue, order irrelevant); warps then pull groups of 32 from
+    // the queue and run TestOctant, so the expensive test never runs on mostly-idle warps.
+    auto eval_octants = [&]() {
+        __syncthreads();
+        const uint32_t n = sh.ringCount;
+        for (;;)
+        {
+            uint32_t grp = 0;
+            if (lane == 0)
+                grp = atomicAdd(&sh.nextGroup, 1u);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+            if (grp * 32 >= n)
+                break;
+            const uint32_t idx = grp * 32 + lane;
+            if (idx < n)
+            {
+                const uint32_t e = sh.ring[idx];
+                const int o = (int)(e & 0x7FFFFFFFu);
+                const float4 mn = sc.octMin[o];
+                const float4 mx = sc.octMax[o];
+                int res;
+                if (e >> 31)
+                    res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
+                else
+                    res = frustum_test<false>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
+                if (occludedQuery && res != OUTSIDE && !ob_is_visible(g, vc.vp, depth, mips, useMips, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z))
+                    res = OUTSIDE;
+                state[o] = res == OUTSIDE ? 0 : (res == INSIDE ? 2 : 1);
+            }
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            sh.ringCount = 0;
+            sh.nextGroup = 0;
+        }
+        __syncthreads();
+    };
+
     if (tid == 0)
         state[0] = 1; // the root is never tested (Octree.cpp:231)
     __syncthreads();
     for (int lv = 1; lv < sc.numLevels; ++lv)
     {
         const int a = sc.levelStart[lv], b = sc.levelStart[lv + 1];
-        for (int i = a + tid; i < b; i += kCullThreads)
+        int sweeps = 0;
+        for (int base = a; base < b; base += kCullThreads)
         {
-            const int o = sc.bfs[i];
-            const float4 mn = sc.octMin[o];
-            const unsigned char ps = state[__float_as_int(mn.w)];
-            unsigned char st = 0;
-            if (ps)
+            const int i = base + tid;
+            bool need = false;
+            uint32_t e = 0;
+            if (i < b)
             {
-                const float4 mx = sc.octMax[o];
-                bool inside = ps == 2;
-                int res;
-                if (inside)
-                    res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
+                const int o = sc.bfs[i];
+                const unsigned char ps = state[__float_as_int(sc.octMin[o].w)];
+                if (ps)
+                {
+                    need = true;
+                    e = (uint32_t)o | (ps == 2 ? 0x80000000u : 0u);
+                }
                 else
-                    res = frustum_test<false>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
-                // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
-                if (occludedQuery && res != OUTSIDE && !ob_is_visible(g, vc.vp, depth, mips, mipsValid != 0, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z))
-                    res = OUTSIDE;
-                if (res != OUTSIDE)
-                    st = (res == INSIDE) ? 2 : 1;
+                    state[o] = 0;
             }
-            state[o] = st;
+            const uint32_t bal = __ballot_sync(0xffffffffu, need);
+            if (bal)
+            {
+                uint32_t pos = 0;
+                if (lane == 0)
+                    pos = atomicAdd(&sh.ringCount, (uint32_t)__popc(bal));
+                pos = __shfl_sync(0xffffffffu, pos, 0);
+                if (need)
+                    sh.ring[pos + __popc(bal & ((1u << lane) - 1u))] = e;
+            }
+            if (++sweeps == kRing / kCullThreads) // the queue could be full after this many sweeps
+            {
+                eval_octants();
+                sweeps = 0;
+            }
         }
-        __syncthreads();
+        eval_octants(); // children need these states
     }
 
     // ---------------- phase 2: drawables of surviving octants, DFS order ----------------
     const bool shadowQuery = vc.queryMode == QUERY_SHADOWCASTER;
     const bool needOcclusion = stage == STAGE_VISIBLE && occl;
 
-    // Occlusion stage over `n` queued survivors starting at ring[0]; emits in order.
-    auto drain = [&](uint32_t n) {
-        bool vis = false;
-        uint32_t d = 0;
-        if ((uint32_t)tid < n)
+    // Occlusion test over the queued frustum survivors (warps pull groups of 32), then ordered emission.
+    auto eval_drawables = [&]() {
+        __syncthreads();
+        const uint32_t n = sh.ringCount;
+        for (;;)
         {
-            d = sh.ring[tid];
-            const float4 mn = sc.drwMin[d];
-            if (!(__float_as_uint(mn.w) & kMetaOccludee))
-                vis = true; // !drawable->IsOccludee(), View.cpp:177
-            else
+            uint32_t grp = 0;
+            if (lane == 0)
+                grp = atomicAdd(&sh.nextGroup, 1u);
+            grp = __shfl_sync(0xffffffffu, grp, 0);
+            if (grp * 32 >= n)
+                break;
+            const uint32_t idx = grp * 32 + lane;
+            bool vis = false;
+            if (idx < n)
             {
-                const float4 mx = sc.drwMax[d];
-                vis = ob_is_visible(g, vc.vp, depth, mips, mipsValid != 0, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                const uint32_t d = sh.ring[idx];
+                const float4 mn = sc.drwMin[d];
+                if (!(__float_as_uint(mn.w) & kMetaOccludee))
+                    vis = true; // !drawable->IsOccludee(), View.cpp:177
+                else
+                {
+                    const float4 mx = sc.drwMax[d];
+                    vis = ob_is_visible(g, vc.vp, depth, mips, useMips, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                }
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, vis);
+            if (lane == 0)
+                sh.visWord[grp] = word;
+        }
+        __syncthreads();
+        const uint32_t nGroups = (n + 31) >> 5;
+        // exclusive scan of the groups' popcounts (kRingGroups <= kCullThreads)
+        uint32_t total;
+        const uint32_t cnt = (uint32_t)tid < nGroups ? (uint32_t)__popc(sh.visWord[tid]) : 0u;
+        const uint32_t off = block_exclusive_scan(cnt, sh.warpTot, total);
+        if ((uint32_t)tid < nGroups)
+            sh.groupOff[tid] = off;
+        __syncthreads();
+        const uint32_t cursor = sh.outCursor;
+        for (uint32_t grp = tid >> 5; grp < nGroups; grp += kCullThreads / 32)
+        {
+            const uint32_t word = sh.visWord[grp];
+            if ((word >> lane) & 1u)
+            {
+                const uint32_t pos = cursor + sh.groupOff[grp] + __popc(word & ((1u << lane) - 1u));
+                if (pos < outCap)
+                    out[pos] = sc.drwId[sh.ring[grp * 32 + lane]];
             }
         }
-        uint32_t tot;
-        const uint32_t rank = block_rank(vis, sh.warpTot, tot);
-        const uint32_t base = sh.outCursor;
-        if (vis)
-        {
-            if (base + rank < outCap)
-                out[base + rank] = sc.drwId[d];
-        }
         __syncthreads();
-        // shift the queue down by n
-        uint32_t keep0 = 0, keep1 = 0;
-        const uint32_t rc = sh.ringCount;
-        if (tid + n < rc) keep0 = sh.ring[tid + n];
-        if (tid + kCullThreads + n < rc) keep1 = sh.ring[tid + kCullThreads + n];
-        __syncthreads();
-        if (tid + n < rc) sh.ring[tid] = keep0;
-        if (tid + kCullThreads + n < rc) sh.ring[tid + kCullThreads] = keep1;
         if (tid == 0)
         {
-            sh.outCursor = base + tot;
-            sh.ringCount = rc - n;
+            sh.outCursor = cursor + total;
+            sh.ringCount = 0;
+            sh.nextGroup = 0;
         }
         __syncthreads();
     };
@@ -249,16 +330,13 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
                     sh.queryCount += tot;
                 }
                 __syncthreads();
-                if (sh.ringCount >= kCullThreads)
-                    drain(kCullThreads);
+                if (sh.ringCount + kCullThreads > kRing)
+                    eval_drawables();
             }
         }
     }
-    if (needOcclusion)
-    {
-        while (sh.ringCount)
-            drain(min(sh.ringCount, (uint32_t)kCullThreads));
-    }
+    if (needOcclusion && sh.ringCount)
+        eval_drawables();
     __syncthreads();
     if (tid == 0)
     {

@@ -677,6 +677,8 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
 {
     extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
     __shared__ uint32_t sNext;
+    __shared__ uint32_t sWideCount;
+    __shared__ int4 sWide[4 * kWideCap];
 
     const int v = blockIdx.y;
     const int tIdx = blockIdx.x;
@@ -701,7 +703,10 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             t4[i] = val;
         }
         if (tid == 0)
+        {
             sNext = 0;
+            sWideCount = 0;
+        }
     }
     __syncthreads();
 
@@ -756,8 +761,24 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
                     tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
             }
         }
-        // wide triangles: the warp takes one at a time, row by row, lanes across the span
-        todo = __ballot_sync(0xffffffffu, cls == kClsWide);
+        // wide triangles are parked in shared memory and rasterised by the whole CTA afterwards (rows interleaved over the warps),
+        // so that one big occluder cannot leave 15 warps waiting on the 16th; if the parking lot is full the warp does it alone
+        bool alone = false;
+        if (cls == kClsWide)
+        {
+            const uint32_t pos = atomicAdd(&sWideCount, 1u);
+            if (pos < kWideCap)
+            {
+                int4* dst = sWide + 4 * pos;
+                dst[0] = make_int4(my.y0, my.y1, my.y2, my.dzdx);
+                dst[1] = make_int4(my.tlx, my.tlxs, my.tlz, my.tlzs);
+                dst[2] = make_int4(my.trx, my.trxs, my.blx, my.blxs);
+                dst[3] = make_int4(my.blz, my.blzs, my.brx, my.brxs);
+            }
+            else
+                alone = true;
+        }
+        todo = __ballot_sync(0xffffffffu, alone);
         while (todo)
         {
             const int src = __ffs(todo) - 1;
@@ -765,6 +786,24 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             const TriSetup ts = bcast_tri(my, src);
             const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
             for (int y = ya; y < yb; ++y)
+            {
+                const HalfRow r = tri_row(ts, y);
+                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                int* trow = tile + (y - ty0) * tw - tx0;
+                for (int x = xa + lane; x < xb; x += 32)
+                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+            }
+        }
+    }
+    __syncthreads();
+    {
+        const uint32_t nWide = min(sWideCount, (uint32_t)kWideCap);
+        const int wid = tid >> 5;
+        for (uint32_t i = 0; i < nWide; ++i)
+        {
+            const TriSetup ts = load_tri(reinterpret_cast<const TriSetup*>(sWide + 4 * i));
+            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+            for (int y = ya + wid; y < yb; y += kTileThreads / 32)
             {
                 const HalfRow r = tri_row(ts, y);
                 const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);

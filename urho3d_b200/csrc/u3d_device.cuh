@@ -195,7 +195,11 @@ __device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp,
     // proves visibility (its max is a pixel of the rect); only mixed texels cut by the rect's border are refined, so the walk
     // costs O(perimeter) instead of the reference's O(area) per level.  Stack entries: level (5 bits) | x (13 bits) | y (14 bits).
     uint32_t stack[3 * kMaxLevels + 4];
-    const int top_lv = g.nlev - 1;
+    // Start at the level whose texels are about the size of the rect (at most 2 x 2 texels overlap it) instead of at the coarsest
+    // one: any set of texels covering the rect evaluates the same predicate, and small boxes skip the useless coarse levels.
+    const int extent = max(right - left, bottom - top) + 1;
+    int top_lv = extent <= 2 ? 0 : (32 - __clz(extent - 1)) - 1;
+    top_lv = min(top_lv, g.nlev - 1);
     const int sh0 = top_lv + 1;
     for (int ry = top >> sh0; ry <= (bottom >> sh0); ++ry)
         for (int rx = left >> sh0; rx <= (right >> sh0); ++rx)

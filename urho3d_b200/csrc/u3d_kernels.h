@@ -19,6 +19,7 @@ constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the
 // tile path
 constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
 constexpr int kTileThreads = 512;
+constexpr int kWideCap = 192;       // wide triangles parked per tile for CTA-wide rasterisation (12 KiB)
 constexpr uint32_t kClsSmall = 0;   // bbox <= 8 x 4: one lane rasterises it
 constexpr uint32_t kClsNarrow = 1;  // bbox <= 8 wide: one warp, one row per lane
 constexpr uint32_t kClsWide = 2;    // one warp, row by row, lanes across the span
