@@ -229,8 +229,8 @@ struct ViewSet
         if (useTiles)
         {
             irrCap = 1u << 20;
-            CU_CHECK(binIdx.ensure(std::max<uint64_t>(poolTris, 1) * tg.numTiles));
-            CU_CHECK(binCount.ensure((size_t)nviews * tg.numTiles));
+            CU_CHECK(binIdx.ensure(std::max<uint64_t>(poolTris, 1) * tg.numTiles * kNumCls));
+            CU_CHECK(binCount.ensure((size_t)nviews * tg.numTiles * kNumCls));
             CU_CHECK(irrList.ensure(irrCap));
             CU_CHECK(irrTotal.ensure(1));
             CU_CHECK(irrOfView.ensure(nviews));
@@ -1302,7 +1302,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
         if (vs.useTiles)
         {
-            CU_CHECK(cudaMemsetAsync(vs.binCount.p, 0, (size_t)V * vs.tg.numTiles * 4, st));
+            CU_CHECK(cudaMemsetAsync(vs.binCount.p, 0, (size_t)V * vs.tg.numTiles * kNumCls * 4, st));
             CU_CHECK(cudaMemsetAsync(vs.irrTotal.p, 0, 4, st));
             CU_CHECK(cudaMemsetAsync(vs.irrOfView.p, 0, (size_t)V * 4, st));
         }

@@ -13,8 +13,11 @@
 namespace u3d
 {
 
-constexpr int kRing = 4096;             // work-queue entries held in shared memory between evaluation passes
+constexpr int kRing = 2048;             // work-queue entries held in shared memory between evaluation passes
 constexpr int kRingGroups = kRing / 32;
+constexpr int kWStack = 256;            // per-warp texel stack of the cooperative range test
+constexpr int kHeavyExtent = 32;        // rects larger than this (pixels) are tested by a whole warp
+constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 
 struct CullShared
 {
@@ -24,6 +27,10 @@ struct CullShared
     uint32_t visWord[kRingGroups];    // one ballot word per group of 32 queued drawables
     uint32_t groupOff[kRingGroups];
     uint32_t warpTot[kCullThreads / 32];
+    uint32_t wstack[kCullThreads / 32][kWStack];
+    uint4 heavy[kHeavyCap];           // (left | top << 16, right | bottom << 16, z, queue index | result bits << 30)
+    uint32_t heavyCount;
+    uint32_t heavyNext;
     uint32_t ringCount;
     uint32_t nextGroup;
     uint32_t outCursor;
@@ -84,6 +91,89 @@ __device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uin
     return pre + __popc(bal & ((1u << lane) - 1u));
 }
 
+/// Stage A of an evaluation pass, one box per lane: project, answer small rects on the spot, park large rects in the CTA's heavy queue
+/// (tag = queue index | caller bits).  Returns the lane's answer; `parked` tells that the answer will come from stage B instead.
+/// If the queue is full the warp walks the box at once.  Every lane of the warp must call.
+__device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
+    bool active, const float4& mn, const float4& mx, uint32_t tag, CullShared& sh, bool& parked)
+{
+    const int lane = threadIdx.x & 31;
+    BoxRect r;
+    r.left = r.top = r.right = r.bottom = r.z = 0;
+    bool vis = false, heavy = false;
+    parked = false;
+    if (active)
+    {
+        if (ob_project(g, vp, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, r))
+            vis = true;
+        else if (useMips && max(r.right - r.left, r.bottom - r.top) >= kHeavyExtent)
+            heavy = true;
+        else
+            vis = range_visible_thread(g, depth, mips, useMips, r);
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, heavy);
+    if (todo)
+    {
+        uint32_t pos = 0;
+        if (lane == 0)
+            pos = atomicAdd(&sh.heavyCount, (uint32_t)__popc(todo));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (heavy)
+        {
+            const uint32_t mine = pos + __popc(todo & ((1u << lane) - 1u));
+            if (mine < kHeavyCap)
+            {
+                sh.heavy[mine] = make_uint4((uint32_t)r.left | ((uint32_t)r.top << 16), (uint32_t)r.right | ((uint32_t)r.bottom << 16), (uint32_t)r.z, tag);
+                parked = true;
+                heavy = false;
+            }
+        }
+        todo = __ballot_sync(0xffffffffu, heavy); // the ones that did not fit
+        while (todo)
+        {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            BoxRect rr;
+            rr.left = __shfl_sync(0xffffffffu, r.left, src);
+            rr.top = __shfl_sync(0xffffffffu, r.top, src);
+            rr.right = __shfl_sync(0xffffffffu, r.right, src);
+            rr.bottom = __shfl_sync(0xffffffffu, r.bottom, src);
+            rr.z = __shfl_sync(0xffffffffu, r.z, src);
+            const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], kWStack);
+            if (lane == src)
+                vis = v;
+        }
+    }
+    return vis;
+}
+
+/// Stage B: warps take parked boxes one at a time and walk them cooperatively.  `apply(tag, visible)` is run by lane 0.
+template <class Apply> __device__ __forceinline__ void visible_stage_b(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips,
+    CullShared& sh, Apply apply)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(sh.heavyCount, (uint32_t)kHeavyCap);
+    for (;;)
+    {
+        uint32_t i = 0;
+        if (lane == 0)
+            i = atomicAdd(&sh.heavyNext, 1u);
+        i = __shfl_sync(0xffffffffu, i, 0);
+        if (i >= n)
+            break;
+        const uint4 e = sh.heavy[i];
+        BoxRect rr;
+        rr.left = (int)(e.x & 0xFFFFu);
+        rr.top = (int)(e.x >> 16);
+        rr.right = (int)(e.y & 0xFFFFu);
+        rr.bottom = (int)(e.y >> 16);
+        rr.z = (int)e.z;
+        const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], kWStack);
+        if (lane == 0)
+            apply(e.w, v);
+    }
+}
+
 __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
     uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
@@ -104,6 +194,8 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
             sh.nextGroup = 0;
             sh.outCursor = 0;
             sh.queryCount = 0;
+            sh.heavyCount = 0;
+            sh.heavyNext = 0;
         }
     }
     __syncthreads();
@@ -131,28 +223,43 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
             if (grp * 32 >= n)
                 break;
             const uint32_t idx = grp * 32 + lane;
+            int o = 0, res = OUTSIDE;
+            float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
             if (idx < n)
             {
                 const uint32_t e = sh.ring[idx];
-                const int o = (int)(e & 0x7FFFFFFFu);
-                const float4 mn = sc.octMin[o];
-                const float4 mx = sc.octMax[o];
-                int res;
+                o = (int)(e & 0x7FFFFFFFu);
+                mn = sc.octMin[o];
+                mx = sc.octMax[o];
                 if (e >> 31)
                     res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
                 else
                     res = frustum_test<false>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
-                // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
-                if (occludedQuery && res != OUTSIDE && !ob_is_visible(g, vc.vp, depth, mips, useMips, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z))
-                    res = OUTSIDE;
-                state[o] = res == OUTSIDE ? 0 : (res == INSIDE ? 2 : 1);
             }
+            // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
+            bool parked = false;
+            if (occludedQuery)
+            {
+                const bool vis = visible_stage_a(g, vc.vp, depth, mips, useMips, res != OUTSIDE, mn, mx, (uint32_t)o | ((uint32_t)res << 30), sh, parked);
+                if (!vis)
+                    res = OUTSIDE;
+            }
+            if (idx < n && !parked)
+                state[o] = res == OUTSIDE ? 0 : (res == INSIDE ? 2 : 1);
         }
+        __syncthreads();
+        if (sh.heavyCount)
+            visible_stage_b(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+                const int res = (int)(tag >> 30);
+                state[tag & 0x3FFFFFFFu] = !vis ? 0 : (res == INSIDE ? 2 : 1);
+            });
         __syncthreads();
         if (tid == 0)
         {
             sh.ringCount = 0;
             sh.nextGroup = 0;
+            sh.heavyCount = 0;
+            sh.heavyNext = 0;
         }
         __syncthreads();
     };
@@ -217,24 +324,36 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
             if (grp * 32 >= n)
                 break;
             const uint32_t idx = grp * 32 + lane;
-            bool vis = false;
+            bool vis = false, test = false;
+            float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
             if (idx < n)
             {
                 const uint32_t d = sh.ring[idx];
-                const float4 mn = sc.drwMin[d];
+                mn = sc.drwMin[d];
                 if (!(__float_as_uint(mn.w) & kMetaOccludee))
                     vis = true; // !drawable->IsOccludee(), View.cpp:177
                 else
                 {
-                    const float4 mx = sc.drwMax[d];
-                    vis = ob_is_visible(g, vc.vp, depth, mips, useMips, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                    mx = sc.drwMax[d];
+                    test = true;
                 }
             }
+            bool parked = false;
+            if (visible_stage_a(g, vc.vp, depth, mips, useMips, test, mn, mx, idx, sh, parked))
+                vis = true;
             const uint32_t word = __ballot_sync(0xffffffffu, vis);
             if (lane == 0)
                 sh.visWord[grp] = word;
         }
         __syncthreads();
+        if (sh.heavyCount)
+        {
+            visible_stage_b(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+                if (vis)
+                    atomicOr(&sh.visWord[tag >> 5], 1u << (tag & 31u));
+            });
+            __syncthreads();
+        }
         const uint32_t nGroups = (n + 31) >> 5;
         // exclusive scan of the groups' popcounts (kRingGroups <= kCullThreads)
         uint32_t total;
@@ -260,6 +379,8 @@ __global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeo
             sh.outCursor = cursor + total;
             sh.ringCount = 0;
             sh.nextGroup = 0;
+            sh.heavyCount = 0;
+            sh.heavyNext = 0;
         }
         __syncthreads();
     };

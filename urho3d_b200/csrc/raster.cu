@@ -37,17 +37,42 @@ __global__ void k_select_occluders(const ViewConst* __restrict__ views, int numO
 {
     const int v = blockIdx.y;
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= numOcc)
-        return;
-    const float* b = occAabb6 + 6 * (size_t)k;
-    if (frustum_test<true>(views[v].planes, b[0], b[1], b[2], b[3], b[4], b[5]) == OUTSIDE)
-        return;
-    const uint32_t tris = occCount[k] / 3;
-    if (!tris)
-        return;
+    const int lane = threadIdx.x & 31;
+    __shared__ float sPlanes[24];
+    if (threadIdx.x < 24)
+        sPlanes[threadIdx.x] = views[v].planes[threadIdx.x];
+    __syncthreads();
+    uint32_t tris = 0;
+    if (k < numOcc)
+    {
+        const float* b = occAabb6 + 6 * (size_t)k;
+        if (frustum_test<true>(sPlanes, b[0], b[1], b[2], b[3], b[4], b[5]) != OUTSIDE)
+            tris = occCount[k] / 3;
+    }
     const uint32_t nsub = (tris + kItemTris - 1) / kItemTris;
-    const uint32_t base = atomicAdd(&itemCount[v], nsub);
-    atomicAdd(&submitted[v], tris);
+    // one atomic per warp: inclusive scans of the item and triangle counts
+    uint32_t sumItems = nsub, sumTris = tris;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1)
+    {
+        const uint32_t a = __shfl_up_sync(0xffffffffu, sumItems, o);
+        const uint32_t c = __shfl_up_sync(0xffffffffu, sumTris, o);
+        if (lane >= o)
+        {
+            sumItems += a;
+            sumTris += c;
+        }
+    }
+    const uint32_t totItems = __shfl_sync(0xffffffffu, sumItems, 31), totTris = __shfl_sync(0xffffffffu, sumTris, 31);
+    if (!totItems)
+        return;
+    uint32_t base = 0;
+    if (lane == 31)
+    {
+        base = atomicAdd(&itemCount[v], totItems);
+        atomicAdd(&submitted[v], totTris);
+    }
+    base = __shfl_sync(0xffffffffu, base, 31) + sumItems - nsub;
     for (uint32_t s = 0; s < nsub; ++s)
     {
         if (base + s >= itemCap)
@@ -209,18 +234,26 @@ __device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
     if (x1 <= x0)
         return; // no pixel in any row
     const int width = x1 - x0, height = ts.y2 - ts.y0;
-    uint32_t cls = kClsWide;
-    if (width <= 8)
-        cls = height <= 4 ? kClsSmall : kClsNarrow;
+    // class = who rasterises it in the tile kernel; hint (top bits of the entry) = lane layout for the warp class
+    uint32_t cls, hint = 0;
+    if (width <= 8 && height <= 8)
+        cls = kClsLane;
+    else if ((long long)width * height <= 4096)
+    {
+        cls = kClsWarp;
+        hint = width <= 8 ? 0u : (width <= 16 ? 1u : 2u);
+    }
+    else
+        cls = kClsCta;
     const int txa = x0 / ec.tileW, txb = min((x1 - 1) / ec.tileW, ec.tilesX - 1);
     const int tya = ts.y0 / kTileH, tyb = min((ts.y2 - 1) / kTileH, ec.tilesY - 1);
     for (int ty = tya; ty <= tyb; ++ty)
         for (int tx = txa; tx <= txb; ++tx)
         {
             const int tile = ty * ec.tilesX + tx;
-            const uint32_t pos = atomicAdd(&ec.binCount[tile], 1u);
+            const uint32_t pos = atomicAdd(&ec.binCount[tile * kNumCls + cls], 1u);
             if (pos < ec.cap)
-                ec.binIdx[(size_t)tile * ec.cap + pos] = slot | (cls << 30);
+                ec.binIdx[((size_t)tile * kNumCls + cls) * ec.cap + pos] = slot | (hint << 30);
         }
 }
 
@@ -409,8 +442,8 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     ec.cap = rd.triCap[v];
     ec.counter = rd.triCount + v;
     ec.flags = rd.flags;
-    ec.binIdx = rd.binIdx ? rd.binIdx + rd.triBase[v] * (size_t)tg.numTiles : nullptr;
-    ec.binCount = rd.binCount ? rd.binCount + (size_t)v * tg.numTiles : nullptr;
+    ec.binIdx = rd.binIdx ? rd.binIdx + rd.triBase[v] * (size_t)tg.numTiles * kNumCls : nullptr;
+    ec.binCount = rd.binCount ? rd.binCount + (size_t)v * tg.numTiles * kNumCls : nullptr;
     ec.irrList = rd.irrList;
     ec.irrCap = rd.irrCap;
     ec.irrTotal = rd.irrTotal;
@@ -676,9 +709,7 @@ __device__ __forceinline__ void tile_min(int* tile, int idx, int z)
 __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
 {
     extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
-    __shared__ uint32_t sNext;
-    __shared__ uint32_t sWideCount;
-    __shared__ int4 sWide[4 * kWideCap];
+    __shared__ uint32_t sNext[2];
 
     const int v = blockIdx.y;
     const int tIdx = blockIdx.x;
@@ -704,104 +735,105 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         }
         if (tid == 0)
         {
-            sNext = 0;
-            sWideCount = 0;
+            sNext[0] = 0;
+            sNext[1] = 0;
         }
     }
     __syncthreads();
 
-    // ---- composite the bin ----
+    // ---- composite the three bins of this tile ----
     const uint32_t cap = rd.triCap[v];
-    const uint32_t nBin = min(rd.binCount[(size_t)v * tg.numTiles + tIdx], cap);
-    const uint32_t* bin = rd.binIdx + (rd.triBase[v] * (size_t)tg.numTiles + (size_t)tIdx * cap);
+    const uint32_t* binCount = rd.binCount + ((size_t)v * tg.numTiles + tIdx) * kNumCls;
+    const uint32_t* binBase = rd.binIdx + (rd.triBase[v] * (size_t)tg.numTiles + (size_t)tIdx * cap) * kNumCls;
     const TriSetup* region = rd.pool + rd.triBase[v];
     const int ty1 = ty0 + rows, tx1 = tx0 + tw;
-    for (;;)
+    const uint32_t nLane = min(binCount[kClsLane], cap), nWarp = min(binCount[kClsWarp], cap), nCta = min(binCount[kClsCta], cap);
+
+    // (1) tiny triangles (bbox <= 8 x 8): one per lane, groups of 32 handed out dynamically
     {
-        uint32_t base = 0;
-        if (lane == 0)
-            base = atomicAdd(&sNext, 32u);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (base >= nBin)
-            break;
-        const uint32_t mine = base + lane < nBin ? bin[base + lane] : 0xFFFFFFFFu;
-        const uint32_t cls = mine >> 30; // 3 = no entry
-        // every lane fetches its own record first (one L2 round trip for the whole group); cooperative triangles are then
-        // broadcast from the owning lane's registers
-        TriSetup my;
-        if (cls != 3u)
-            my = load_tri(region + (mine & 0x3FFFFFFFu));
-        // small triangles: one per lane
-        if (cls == kClsSmall)
+        const uint32_t* bin = binBase + (size_t)kClsLane * cap;
+        for (;;)
         {
-            const int ya = max(my.y0, ty0), yb = min(my.y2, ty1);
-            for (int y = ya; y < yb; ++y)
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(&sNext[0], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= nLane)
+                break;
+            if (base + lane < nLane)
             {
-                const HalfRow r = tri_row(my, y);
-                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
-                int* trow = tile + (y - ty0) * tw - tx0;
-                for (int x = xa; x < xb; ++x)
-                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)my.dzdx));
-            }
-        }
-        // narrow triangles: the warp takes one at a time, one row per lane
-        uint32_t todo = __ballot_sync(0xffffffffu, cls == kClsNarrow);
-        while (todo)
-        {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const TriSetup ts = bcast_tri(my, src);
-            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
-            for (int y = ya + lane; y < yb; y += 32)
-            {
-                const HalfRow r = tri_row(ts, y);
-                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
-                int* trow = tile + (y - ty0) * tw - tx0;
-                for (int x = xa; x < xb; ++x)
-                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
-            }
-        }
-        // wide triangles are parked in shared memory and rasterised by the whole CTA afterwards (rows interleaved over the warps),
-        // so that one big occluder cannot leave 15 warps waiting on the 16th; if the parking lot is full the warp does it alone
-        bool alone = false;
-        if (cls == kClsWide)
-        {
-            const uint32_t pos = atomicAdd(&sWideCount, 1u);
-            if (pos < kWideCap)
-            {
-                int4* dst = sWide + 4 * pos;
-                dst[0] = make_int4(my.y0, my.y1, my.y2, my.dzdx);
-                dst[1] = make_int4(my.tlx, my.tlxs, my.tlz, my.tlzs);
-                dst[2] = make_int4(my.trx, my.trxs, my.blx, my.blxs);
-                dst[3] = make_int4(my.blz, my.blzs, my.brx, my.brxs);
-            }
-            else
-                alone = true;
-        }
-        todo = __ballot_sync(0xffffffffu, alone);
-        while (todo)
-        {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const TriSetup ts = bcast_tri(my, src);
-            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
-            for (int y = ya; y < yb; ++y)
-            {
-                const HalfRow r = tri_row(ts, y);
-                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
-                int* trow = tile + (y - ty0) * tw - tx0;
-                for (int x = xa + lane; x < xb; x += 32)
-                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+                const TriSetup ts = load_tri(region + (bin[base + lane] & 0x3FFFFFFFu));
+                const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+                for (int y = ya; y < yb; ++y)
+                {
+                    const HalfRow r = tri_row(ts, y);
+                    const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                    int* trow = tile + (y - ty0) * tw - tx0;
+                    for (int x = xa; x < xb; ++x)
+                        tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+                }
             }
         }
     }
-    __syncthreads();
+    // (2) medium triangles: one warp each; the 32 lanes form a block of rows x columns chosen from the triangle's width
     {
-        const uint32_t nWide = min(sWideCount, (uint32_t)kWideCap);
-        const int wid = tid >> 5;
-        for (uint32_t i = 0; i < nWide; ++i)
+        const uint32_t* bin = binBase + (size_t)kClsWarp * cap;
+        for (;;)
         {
-            const TriSetup ts = load_tri(reinterpret_cast<const TriSetup*>(sWide + 4 * i));
+            uint32_t base = 0;
+            if (lane == 0)
+                base = atomicAdd(&sNext[1], 32u);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (base >= nWarp)
+                break;
+            const uint32_t cnt = min(32u, nWarp - base);
+            // every lane fetches one record (one L2 round trip per 32 triangles); the warp then walks them from registers
+            uint32_t mine = 0;
+            TriSetup my;
+            if (lane < cnt)
+            {
+                mine = bin[base + lane];
+                my = load_tri(region + (mine & 0x3FFFFFFFu));
+            }
+            for (uint32_t k = 0; k < cnt; ++k)
+            {
+                const TriSetup ts = bcast_tri(my, (int)k);
+                const uint32_t hint = __shfl_sync(0xffffffffu, mine, (int)k) >> 30;
+                const int colsLog = hint == 0 ? 3 : (hint == 1 ? 4 : 5);
+                const int cols = 1 << colsLog, rowsPer = 32 >> colsLog;
+                const int lr = lane >> colsLog, lc = lane & (cols - 1);
+                const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+                for (int yb0 = ya; yb0 < yb; yb0 += rowsPer)
+                {
+                    const int y = yb0 + lr;
+                    HalfRow r;
+                    r.xl = 0; r.xr = 0; r.z0 = 0;
+                    int xa = 0, xb = 0;
+                    if (y < yb)
+                    {
+                        r = tri_row(ts, y);
+                        xa = max(r.xl, tx0);
+                        xb = min(r.xr, tx1);
+                    }
+                    int* trow = tile + (y - ty0) * tw - tx0;
+                    int x = xa + lc;
+                    while (__any_sync(0xffffffffu, x < xb))
+                    {
+                        if (x < xb)
+                            tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
+                        x += cols;
+                    }
+                }
+            }
+        }
+    }
+    // (3) large triangles: the whole CTA, rows interleaved over the warps, lanes across the span
+    {
+        const uint32_t* bin = binBase + (size_t)kClsCta * cap;
+        const int wid = tid >> 5;
+        for (uint32_t i = 0; i < nCta; ++i)
+        {
+            const TriSetup ts = load_tri(region + (bin[i] & 0x3FFFFFFFu));
             const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
             for (int y = ya + wid; y < yb; y += kTileThreads / 32)
             {

@@ -140,12 +140,16 @@ template <bool FAST> __device__ __forceinline__ int frustum_test(const float* pl
     return (FAST || allInside) ? INSIDE : INTERSECTS;
 }
 
-/// OcclusionBuffer::IsVisible, OB.cpp:336-456, as the exact predicate it computes (SURVEY hard part 5):
-/// after the near-plane / off-screen early-outs, "visible" <=> exists pixel p in the clamped rect with z <= depth[p].
-/// The reference walks every mip texel overlapping the rect level by level; here a quadtree descent visits only texels
-/// whose [min,max] straddles z.  useMips = false reproduces the depthHierarchyDirty_ path (pixel scan, OB.cpp:440-455).
-__device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips,
-    bool useMips, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
+/// Screen rect + biased integer depth of a box (the float part of OcclusionBuffer::IsVisible, OB.cpp:341-402).
+struct BoxRect
+{
+    int left, top, right, bottom; // clamped, inclusive
+    int z;
+};
+
+/// Returns true when the reference answers "visible" before touching the buffer (near-plane crossing OB.cpp:359/370, rect off screen
+/// :386-389); otherwise fills `r`.
+__device__ __forceinline__ bool ob_project(const BufGeom& g, const float* vp, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, BoxRect& r)
 {
     float minX = 0.f, maxX = 0.f, minY = 0.f, maxY = 0.f, minZ = 0.f;
 #pragma unroll
@@ -180,68 +184,233 @@ __device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp,
     if (top < 0) top = 0;
     if (right >= g.w) right = g.w - 1;
     if (bottom >= g.h) bottom = g.h - 1;
-    const int z = (int)((uint32_t)round_x86(minZ) - (uint32_t)kFixedBias);
+    r.left = left;
+    r.top = top;
+    r.right = right;
+    r.bottom = bottom;
+    r.z = (int)((uint32_t)round_x86(minZ) - (uint32_t)kFixedBias);
+    return false;
+}
 
+/// Level at which at most 2 x 2 texels overlap the rect (texel size >= rect extent), clamped to the coarsest level.
+__device__ __forceinline__ int start_level(const BufGeom& g, const BoxRect& r)
+{
+    const int extent = max(r.right - r.left, r.bottom - r.top) + 1;
+    const int lv = extent <= 2 ? 0 : (32 - __clz(extent - 1)) - 1;
+    return min(lv, g.nlev - 1);
+}
+
+__device__ __forceinline__ uint32_t pack_texel(int lv, int x, int y) { return ((uint32_t)lv << 27) | ((uint32_t)x << 14) | (uint32_t)y; }
+
+/// One texel of the walk.  Returns 1 = proves visible, 0 = nothing visible under it (inside the rect), 2 = must be refined.
+/// A texel is conclusive unless min < z <= max ("mixed"); a mixed texel that lies completely inside the rect proves visibility
+/// (the pixel holding its max is in the rect), so only mixed texels cut by the rect's border are refined.
+__device__ __forceinline__ int classify_texel(const BufGeom& g, const int2* __restrict__ mips, const BoxRect& r, int lv, int x, int y)
+{
+    const int2 t = mips[g.moff[lv] + y * g.mw[lv] + x];
+    if (r.z <= t.x)
+        return 1;
+    if (r.z > t.y)
+        return 0;
+    const int s = lv + 1;
+    const int px0 = x << s, py0 = y << s;
+    const int px1 = min(((x + 1) << s) - 1, g.w - 1), py1 = min(((y + 1) << s) - 1, g.h - 1);
+    if (px0 >= r.left && px1 <= r.right && py0 >= r.top && py1 <= r.bottom)
+        return 1;
+    return 2;
+}
+
+/// Pixels of a level-0 texel that lie in the rect.
+__device__ __forceinline__ bool texel_pixels_visible(const BufGeom& g, const int* __restrict__ depth, const BoxRect& r, int x, int y)
+{
+    const int x0 = max(2 * x, r.left), x1 = min(min(2 * x + 1, r.right), g.w - 1);
+    const int y0 = max(2 * y, r.top), y1 = min(min(2 * y + 1, r.bottom), g.h - 1);
+    for (int py = y0; py <= y1; ++py)
+        for (int px = x0; px <= x1; ++px)
+            if (r.z <= depth[py * g.w + px])
+                return true;
+    return false;
+}
+
+/// The buffer part of OcclusionBuffer::IsVisible (OB.cpp:404-455) as the exact predicate it computes (SURVEY hard part 5):
+/// "visible" <=> exists pixel p in the rect with z <= depth[p].  The reference rescans every overlapping texel level by level;
+/// here a depth-first walk refines only border-cut mixed texels, starting at the level matched to the rect's size.
+/// useMips = false reproduces the depthHierarchyDirty_ path (pixel scan, OB.cpp:440-455).
+__device__ __forceinline__ bool range_visible_thread(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
+    const BoxRect& r)
+{
     if (!useMips)
     {
-        for (int y = top; y <= bottom; ++y)
-            for (int x = left; x <= right; ++x)
-                if (z <= depth[y * g.w + x])
+        for (int y = r.top; y <= r.bottom; ++y)
+            for (int x = r.left; x <= r.right; ++x)
+                if (r.z <= depth[y * g.w + x])
                     return true;
         return false;
     }
-
-    // Quadtree descent.  A texel is conclusive unless min < z <= max ("mixed").  A mixed texel that lies completely inside the rect
-    // proves visibility (its max is a pixel of the rect); only mixed texels cut by the rect's border are refined, so the walk
-    // costs O(perimeter) instead of the reference's O(area) per level.  Stack entries: level (5 bits) | x (13 bits) | y (14 bits).
     uint32_t stack[3 * kMaxLevels + 4];
-    // Start at the level whose texels are about the size of the rect (at most 2 x 2 texels overlap it) instead of at the coarsest
-    // one: any set of texels covering the rect evaluates the same predicate, and small boxes skip the useless coarse levels.
-    const int extent = max(right - left, bottom - top) + 1;
-    int top_lv = extent <= 2 ? 0 : (32 - __clz(extent - 1)) - 1;
-    top_lv = min(top_lv, g.nlev - 1);
+    const int top_lv = start_level(g, r);
     const int sh0 = top_lv + 1;
-    for (int ry = top >> sh0; ry <= (bottom >> sh0); ++ry)
-        for (int rx = left >> sh0; rx <= (right >> sh0); ++rx)
+    for (int ry = r.top >> sh0; ry <= (r.bottom >> sh0); ++ry)
+        for (int rx = r.left >> sh0; rx <= (r.right >> sh0); ++rx)
         {
             int sp = 0;
-            stack[sp++] = ((uint32_t)top_lv << 27) | ((uint32_t)rx << 14) | (uint32_t)ry;
+            stack[sp++] = pack_texel(top_lv, rx, ry);
             while (sp)
             {
                 const uint32_t e = stack[--sp];
                 const int lv = (int)(e >> 27), x = (int)((e >> 14) & 0x1FFF), y = (int)(e & 0x3FFF);
-                const int2 t = mips[g.moff[lv] + y * g.mw[lv] + x];
-                if (z <= t.x)
-                    return true;      // every pixel under this texel is at least as far as z, and the texel overlaps the rect
-                if (z > t.y)
-                    continue;         // every pixel under this texel is nearer than z
-                // pixels covered by this texel: [x << s, ((x+1) << s) - 1] x [y << s, ...] clipped to the buffer, s = lv + 1
-                const int s = lv + 1;
-                const int px0 = x << s, py0 = y << s;
-                const int px1 = min(((x + 1) << s) - 1, g.w - 1), py1 = min(((y + 1) << s) - 1, g.h - 1);
-                if (px0 >= left && px1 <= right && py0 >= top && py1 <= bottom)
-                    return true;      // mixed and fully inside the rect: the pixel holding max is in the rect and z <= max
+                const int c = classify_texel(g, mips, r, lv, x, y);
+                if (c == 1)
+                    return true;
+                if (c == 0)
+                    continue;
                 if (lv == 0)
                 {
-                    const int x0 = max(px0, left), x1 = min(px1, right);
-                    const int y0 = max(py0, top), y1 = min(py1, bottom);
-                    for (int py = y0; py <= y1; ++py)
-                        for (int px = x0; px <= x1; ++px)
-                            if (z <= depth[py * g.w + px])
-                                return true;
+                    if (texel_pixels_visible(g, depth, r, x, y))
+                        return true;
                 }
                 else
                 {
                     const int cl = lv - 1, sh = lv; // child level texel = pixel >> (cl + 1) = pixel >> lv
-                    const int x0 = max(2 * x, left >> sh), x1 = min(min(2 * x + 1, right >> sh), g.mw[cl] - 1);
-                    const int y0 = max(2 * y, top >> sh), y1 = min(min(2 * y + 1, bottom >> sh), g.mh[cl] - 1);
+                    const int x0 = max(2 * x, r.left >> sh), x1 = min(min(2 * x + 1, r.right >> sh), g.mw[cl] - 1);
+                    const int y0 = max(2 * y, r.top >> sh), y1 = min(min(2 * y + 1, r.bottom >> sh), g.mh[cl] - 1);
                     for (int cy = y0; cy <= y1; ++cy)
                         for (int cx = x0; cx <= x1; ++cx)
-                            stack[sp++] = ((uint32_t)cl << 27) | ((uint32_t)cx << 14) | (uint32_t)cy;
+                            stack[sp++] = pack_texel(cl, cx, cy);
                 }
             }
         }
     return false;
+}
+
+/// Same predicate evaluated by a whole warp for ONE rect (all lanes pass the same r): the pending texels sit on a per-warp stack in
+/// shared memory and are classified 32 at a time, so a box whose border cuts hundreds of mixed texels costs tens of steps instead
+/// of hundreds of dependent loads on one lane.  `wstack` has `cap` entries; if it would overflow, the surplus subtrees are walked
+/// by single lanes.  Must be called by all 32 lanes.
+__device__ __forceinline__ bool range_visible_warp(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r,
+    uint32_t* wstack, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const int top_lv = start_level(g, r);
+    const int sh0 = top_lv + 1;
+    const int rx0 = r.left >> sh0, ry0 = r.top >> sh0;
+    const int nx = (r.right >> sh0) - rx0 + 1, ny = (r.bottom >> sh0) - ry0 + 1;
+    int n = nx * ny; // <= 64: the coarsest level is at most 8 x 8 texels, finer start levels give at most 2 x 2
+    __syncwarp();
+    for (int i = lane; i < n; i += 32)
+        wstack[i] = pack_texel(top_lv, rx0 + i % nx, ry0 + i / nx);
+    __syncwarp();
+    while (n > 0)
+    {
+        const int take = min(n, 32);
+        n -= take;
+        uint32_t e = 0;
+        int c = 0, lv = 0, x = 0, y = 0;
+        if (lane < take)
+        {
+            e = wstack[n + lane];
+            lv = (int)(e >> 27);
+            x = (int)((e >> 14) & 0x1FFF);
+            y = (int)(e & 0x3FFF);
+            c = classify_texel(g, mips, r, lv, x, y);
+            if (c == 2 && lv == 0)
+                c = texel_pixels_visible(g, depth, r, x, y) ? 1 : 0;
+        }
+        if (__any_sync(0xffffffffu, c == 1))
+            return true;
+        // children of the texels that must be refined
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cl = 0;
+        if (c == 2)
+        {
+            cl = lv - 1;
+            const int sh = lv;
+            x0 = max(2 * x, r.left >> sh);
+            x1 = min(min(2 * x + 1, r.right >> sh), g.mw[cl] - 1);
+            y0 = max(2 * y, r.top >> sh);
+            y1 = min(min(2 * y + 1, r.bottom >> sh), g.mh[cl] - 1);
+        }
+        const int kids = c == 2 ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
+        int off = kids;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o)
+                off += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        off -= kids;
+        __syncwarp();
+        bool spill = false;
+        if (kids)
+        {
+            if (n + off + kids <= cap)
+            {
+                int k = n + off;
+                for (int cy = y0; cy <= y1; ++cy)
+                    for (int cx = x0; cx <= x1; ++cx)
+                        wstack[k++] = pack_texel(cl, cx, cy);
+            }
+            else
+                spill = true;
+        }
+        // lanes whose children did not fit walk their subtree alone (rare: only perimeters far beyond the stack size)
+        bool lonely = false;
+        if (spill)
+        {
+            BoxRect sub = r;
+            // restrict the rect to this texel's footprint: same predicate over the part of the rect under the texel
+            const int s = lv + 1;
+            sub.left = max(r.left, x << s);
+            sub.top = max(r.top, y << s);
+            sub.right = min(r.right, ((x + 1) << s) - 1);
+            sub.bottom = min(r.bottom, ((y + 1) << s) - 1);
+            lonely = range_visible_thread(g, depth, mips, true, sub);
+        }
+        if (__any_sync(0xffffffffu, lonely))
+            return true;
+        // stack grows by the children that fitted: those of lanes in prefix order up to the first spilling lane are contiguous only
+        // if no earlier lane spilled; recompute the kept total
+        const uint32_t spillMask = __ballot_sync(0xffffffffu, spill);
+        if (spillMask == 0)
+            n += total;
+        else
+        {
+            // compact: lanes that kept their children re-push them densely
+            int keep = spill ? 0 : kids;
+            int koff = keep;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const int t = __shfl_up_sync(0xffffffffu, koff, o);
+                if (lane >= o)
+                    koff += t;
+            }
+            const int ktotal = __shfl_sync(0xffffffffu, koff, 31);
+            koff -= keep;
+            __syncwarp();
+            if (keep)
+            {
+                int k = n + koff;
+                for (int cy = y0; cy <= y1; ++cy)
+                    for (int cx = x0; cx <= x1; ++cx)
+                        wstack[k++] = pack_texel(cl, cx, cy);
+            }
+            n += ktotal;
+        }
+        __syncwarp();
+    }
+    return false;
+}
+
+/// OcclusionBuffer::IsVisible, OB.cpp:336-456, evaluated by one thread.
+__device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips,
+    bool useMips, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
+{
+    BoxRect r;
+    if (ob_project(g, vp, mnx, mny, mnz, mxx, mxy, mxz, r))
+        return true;
+    return range_visible_thread(g, depth, mips, useMips, r);
 }
 
 } // namespace u3d

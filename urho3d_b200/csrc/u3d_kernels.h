@@ -19,10 +19,10 @@ constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the
 // tile path
 constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
 constexpr int kTileThreads = 512;
-constexpr int kWideCap = 192;       // wide triangles parked per tile for CTA-wide rasterisation (12 KiB)
-constexpr uint32_t kClsSmall = 0;   // bbox <= 8 x 4: one lane rasterises it
-constexpr uint32_t kClsNarrow = 1;  // bbox <= 8 wide: one warp, one row per lane
-constexpr uint32_t kClsWide = 2;    // one warp, row by row, lanes across the span
+constexpr uint32_t kClsLane = 0;    // bbox <= 8 x 8: one lane rasterises it
+constexpr uint32_t kClsWarp = 1;    // bbox area <= 4096: one warp, lanes form a rows x columns block
+constexpr uint32_t kClsCta = 2;     // larger: the whole CTA, rows interleaved over the warps
+constexpr int kNumCls = 3;          // every tile has one bin per class
 
 struct TileGeom
 {
@@ -39,8 +39,8 @@ struct RasterDev
     uint32_t* triCount;          // per view: records emitted
     uint32_t* drawnSources;      // per view: source triangles that drew (numTriangles_ bookkeeping)
     uint32_t* flags;
-    uint32_t* binIdx;            // per view: numTiles x triCap entries (slot | class << 30); nullptr = general path only
-    uint32_t* binCount;          // numViews x numTiles
+    uint32_t* binIdx;            // per view: numTiles x kNumCls x triCap entries (slot | hint << 30); nullptr = general path only
+    uint32_t* binCount;          // numViews x numTiles x kNumCls
     unsigned long long* irrList; // (view << 32 | slot) of triangles the tile path refuses
     uint32_t irrCap;
     uint32_t* irrTotal;
