@@ -196,6 +196,9 @@ U3D_API int u3d_batch_read_depth(u3d_batch* b, uint32_t view, int32_t* out_depth
 U3D_API int u3d_batch_read_mip(u3d_batch* b, uint32_t view, int level, int32_t* out_minmax, void* stream);
 /* Per view: (submitted triangles, numTriangles_ as the reference counts it = submitted + source triangles that drew, set-up triangles). */
 U3D_API int u3d_batch_read_tri_stats(u3d_batch* b, uint32_t* stats3, void* stream);
+/* Diagnostic: the set-up triangle records of one view (16 ints each: y0,y1,y2,dzdx, top half lx,lxs,lz,lzs,rx,rxs, bottom half the same),
+ * in arbitrary order.  *count = records held. */
+U3D_API int u3d_batch_read_setup_records(u3d_batch* b, uint32_t view, int32_t* out16, uint32_t capacity, uint32_t* count, void* stream);
 /* One call, host buffers in and out (the e2e path): set_views + run + read_counts + read_packed. */
 U3D_API int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int stage, uint32_t* counts, uint32_t* offsets, uint32_t* ids,
     uint64_t capacity, void* stream);

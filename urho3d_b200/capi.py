@@ -97,6 +97,7 @@ SIGNATURES = {
     "u3d_batch_read_depth": (C.c_int, [_vp, C.c_uint32, _i32, _vp]),
     "u3d_batch_read_mip": (C.c_int, [_vp, C.c_uint32, C.c_int, _i32, _vp]),
     "u3d_batch_read_tri_stats": (C.c_int, [_vp, _u32, _vp]),
+    "u3d_batch_read_setup_records": (C.c_int, [_vp, C.c_uint32, _i32, C.c_uint32, _u32, _vp]),
     "u3d_batch_cull_views": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _u32, _u32, _u32, C.c_uint64, _vp]),
     "u3d_batch_device_results": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u32]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
@@ -470,6 +471,13 @@ class Batch:
         out = np.zeros((self.n, 3), np.uint32)
         _chk(lib().u3d_batch_read_tri_stats(self.h, _p(out, _u32), stream))
         return out
+
+    def setup_records(self, view, stream=None):
+        c = C.c_uint32()
+        _chk(lib().u3d_batch_read_setup_records(self.h, view, None, 0, C.byref(c), stream))
+        out = np.zeros((max(c.value, 1), 16), np.int32)
+        _chk(lib().u3d_batch_read_setup_records(self.h, view, _p(out, _i32), c.value, C.byref(c), stream))
+        return out[:c.value]
 
     def last_launches(self):
         return lib().u3d_batch_last_launches(self.h)

@@ -1562,6 +1562,30 @@ int u3d_batch_read_tri_stats(u3d_batch* b, uint32_t* stats3, void* stream)
     return U3D_OK;
 }
 
+int u3d_batch_read_setup_records(u3d_batch* b, uint32_t view, int32_t* out16, uint32_t capacity, uint32_t* count, void* stream)
+{
+    if (!b || view >= b->numViews || !b->hasBuffers)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_setup_records: bad argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    uint32_t n = 0, cap = 0;
+    uint64_t base = 0;
+    CU_CHECK(cudaMemcpyAsync(&n, b->vs.triCount.p + view, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(&cap, b->vs.triCap.p + view, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(&base, b->vs.triBase.p + view, 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    n = std::min(n, cap);
+    if (count)
+        *count = n;
+    const uint32_t m = std::min(n, capacity);
+    if (m && out16)
+    {
+        CU_CHECK(cudaMemcpyAsync(out16, b->vs.pool.p + base, (size_t)m * sizeof(TriSetup), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
+    return U3D_OK;
+}
+
 int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int stage, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity,
     void* stream)
 {

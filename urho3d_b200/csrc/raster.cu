@@ -236,12 +236,15 @@ __device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
     const int width = x1 - x0, height = ts.y2 - ts.y0;
     // class = who rasterises it in the tile kernel; hint (top bits of the entry) = lane layout for the warp class
     uint32_t cls, hint = 0;
-    if (width <= 8 && height <= 8)
+    const long long area = (long long)width * height;
+    if (area <= 64)
         cls = kClsLane;
-    else if ((long long)width * height <= 4096)
+    else if (area <= 16384)
     {
+        // lanes per row: each lane walks about 8 pixels of its row; the rest of the warp covers more rows at once
         cls = kClsWarp;
-        hint = width <= 8 ? 0u : (width <= 16 ? 1u : 2u);
+        while (hint < 5 && (8 << hint) < width)
+            ++hint;
     }
     else
         cls = kClsCta;
@@ -253,22 +256,25 @@ __device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
             const int tile = ty * ec.tilesX + tx;
             const uint32_t pos = atomicAdd(&ec.binCount[tile * kNumCls + cls], 1u);
             if (pos < ec.cap)
-                ec.binIdx[((size_t)tile * kNumCls + cls) * ec.cap + pos] = slot | (hint << 30);
+                ec.binIdx[((size_t)tile * kNumCls + cls) * ec.cap + pos] = slot | (hint << 29);
         }
 }
 
-/// ViewportTransform x3 + SignedArea + cull test + DrawTriangle2D's set-up part (OB.cpp:629-637, 815-899).
-/// Returns true when the reference would have called DrawTriangle2D (drawOk); emits the record if the triangle has rows.
-__device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, const V4& c0, const V4& c1, const V4& c2, const EmitCtx& ec)
+/// ViewportTransform x3 + SignedArea + cull test (OB.cpp:629-634).  Returns true when the reference would call DrawTriangle2D.
+__device__ __forceinline__ bool project_and_cull(const BufGeom& g, int cullMode, const V4& c0, const V4& c1, const V4& c2, V3& p0, V3& p1, V3& p2,
+    bool& clockwise)
 {
-    const V3 p0 = viewport_transform(g, c0);
-    const V3 p1 = viewport_transform(g, c1);
-    const V3 p2 = viewport_transform(g, c2);
+    p0 = viewport_transform(g, c0);
+    p1 = viewport_transform(g, c1);
+    p2 = viewport_transform(g, c2);
     const float aX = p0.x - p1.x, aY = p0.y - p1.y, bX = p2.x - p1.x, bY = p2.y - p1.y;
-    const bool clockwise = (aX * bY - aY * bX) < 0.0f; // SignedArea, OB.cpp:569-576
-    if (!(cullMode == CULL_NONE || (cullMode == CULL_CCW && clockwise) || (cullMode == CULL_CW && !clockwise)))
-        return false;
+    clockwise = (aX * bY - aY * bX) < 0.0f; // SignedArea, OB.cpp:569-576
+    return cullMode == CULL_NONE || (cullMode == CULL_CCW && clockwise) || (cullMode == CULL_CW && !clockwise);
+}
 
+/// DrawTriangle2D's set-up part (OB.cpp:815-899) for a triangle that passed the cull test; emits the record if it has rows.
+__device__ __forceinline__ void raster_setup(const V3& p0, const V3& p1, const V3& p2, bool clockwise, const EmitCtx& ec)
+{
     // Y sort, OB.cpp:820-872 (written with selects so the vertices stay in registers)
     V3 vt, vm, vb;
     bool midRight;
@@ -286,7 +292,7 @@ __device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, c
     }
     const int topY = trunc_x86(vt.y), midY = trunc_x86(vm.y), botY = trunc_x86(vb.y);
     if (topY == botY)
-        return true; // degenerate: the reference returns from DrawTriangle2D, but drawOk is already set
+        return; // degenerate: the reference returns from DrawTriangle2D (drawOk is already set by the caller)
     if (!clockwise)
         midRight = !midRight;
 
@@ -323,6 +329,15 @@ __device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, c
         out.blx = eb.x; out.blxs = eb.xs; out.blz = eb.z; out.blzs = eb.zs; out.brx = lngBx; out.brxs = lng.xs;
     }
     emit_tri(ec, out);
+}
+
+__device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, const V4& c0, const V4& c1, const V4& c2, const EmitCtx& ec)
+{
+    V3 p0, p1, p2;
+    bool clockwise;
+    if (!project_and_cull(g, cullMode, c0, c1, c2, p0, p1, p2, clockwise))
+        return false;
+    raster_setup(p0, p1, p2, clockwise, ec);
     return true;
 }
 
@@ -434,6 +449,14 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     __shared__ float sMvp[kSetupItems][16];
     __shared__ DrawItem sItem[kSetupItems];
     __shared__ uint32_t sPre[kSetupItems + 1];
+    __shared__ float sSurv[kSetupThreads][11]; // unclipped survivors of stage 1: three screen vertices + winding (odd stride: no bank conflicts)
+    __shared__ float sClip[kSetupThreads][13]; // triangles for the clipper: three clip-space vertices + plane mask
+    __shared__ uint32_t sCount[2];
+    if (threadIdx.x == 0)
+    {
+        sCount[0] = 0;
+        sCount[1] = 0;
+    }
 
     const ViewConst& vc = views[v];
     const int cullMode = vc.cullMode;
@@ -502,55 +525,115 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
         __syncthreads();
 
         const uint32_t total = sPre[kSetupItems];
-        for (uint32_t t = threadIdx.x; t < total; t += blockDim.x)
+        for (uint32_t tBase = 0; tBase < total; tBase += blockDim.x)
         {
-            // owning item: largest i < nLocal with sPre[i] <= t
-            uint32_t lo = 0, hi = nLocal;
-            while (hi - lo > 1)
+            // ---- stage 1: fetch, transform, clip masks, project, cull.  Survivors are compacted into shared memory so that the
+            //      expensive edge set-up (stage 2) and the rare clipper (stage 3) run on dense warps ----
+            const uint32_t t = tBase + threadIdx.x;
+            int kind = 0; // 0 nothing, 1 unclipped survivor, 2 needs clipping
+            V4 c0, c1, c2;
+            V3 p0, p1, p2;
+            bool clockwise = false;
+            unsigned clipMask = 0;
+            if (t < total)
             {
-                const uint32_t m = (lo + hi) >> 1;
-                if (sPre[m] <= t) lo = m; else hi = m;
-            }
-            const DrawItem& it = sItem[lo];
-            const MeshDev mesh = meshes[it.mesh];
-            const uint32_t first = it.start + 3 * (t - sPre[lo]);
-            uint32_t i0, i1, i2;
-            if (mesh.idx == nullptr)
-            {
-                i0 = first; i1 = first + 1; i2 = first + 2;
-            }
-            else if (mesh.idxSize == 2)
-            {
-                const unsigned short* ix = (const unsigned short*)mesh.idx;
-                i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
-            }
-            else
-            {
-                const unsigned* ix = (const unsigned*)mesh.idx;
-                i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
-            }
-            const float* p0 = (const float*)(mesh.vtx + (size_t)i0 * mesh.stride);
-            const float* p1 = (const float*)(mesh.vtx + (size_t)i1 * mesh.stride);
-            const float* p2 = (const float*)(mesh.vtx + (size_t)i2 * mesh.stride);
-            const float* mvp = sMvp[lo];
-            const V4 c0 = model_transform(mvp, p0[0], p0[1], p0[2]);
-            const V4 c1 = model_transform(mvp, p1[0], p1[1], p1[2]);
-            const V4 c2 = model_transform(mvp, p2[0], p2[1], p2[2]);
+                // owning item: largest i < nLocal with sPre[i] <= t
+                uint32_t lo = 0, hi = nLocal;
+                while (hi - lo > 1)
+                {
+                    const uint32_t m = (lo + hi) >> 1;
+                    if (sPre[m] <= t) lo = m; else hi = m;
+                }
+                const DrawItem& it = sItem[lo];
+                const MeshDev mesh = meshes[it.mesh];
+                const uint32_t first = it.start + 3 * (t - sPre[lo]);
+                uint32_t i0, i1, i2;
+                if (mesh.idx == nullptr)
+                {
+                    i0 = first; i1 = first + 1; i2 = first + 2;
+                }
+                else if (mesh.idxSize == 2)
+                {
+                    const unsigned short* ix = (const unsigned short*)mesh.idx;
+                    i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+                }
+                else
+                {
+                    const unsigned* ix = (const unsigned*)mesh.idx;
+                    i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+                }
+                const float* q0 = (const float*)(mesh.vtx + (size_t)i0 * mesh.stride);
+                const float* q1 = (const float*)(mesh.vtx + (size_t)i1 * mesh.stride);
+                const float* q2 = (const float*)(mesh.vtx + (size_t)i2 * mesh.stride);
+                const float* mvp = sMvp[lo];
+                c0 = model_transform(mvp, q0[0], q0[1], q0[2]);
+                c1 = model_transform(mvp, q1[0], q1[1], q1[2]);
+                c2 = model_transform(mvp, q2[0], q2[1], q2[2]);
 
-            // clip masks, OB.cpp:596-620
-            unsigned m0 = 0, m1 = 0, m2 = 0;
-            if (c0.x > c0.w) m0 |= 1; if (c0.x < -c0.w) m0 |= 2; if (c0.y > c0.w) m0 |= 4; if (c0.y < -c0.w) m0 |= 8; if (c0.z > c0.w) m0 |= 16; if (c0.z < 0.0f) m0 |= 32;
-            if (c1.x > c1.w) m1 |= 1; if (c1.x < -c1.w) m1 |= 2; if (c1.y > c1.w) m1 |= 4; if (c1.y < -c1.w) m1 |= 8; if (c1.z > c1.w) m1 |= 16; if (c1.z < 0.0f) m1 |= 32;
-            if (c2.x > c2.w) m2 |= 1; if (c2.x < -c2.w) m2 |= 2; if (c2.y > c2.w) m2 |= 4; if (c2.y < -c2.w) m2 |= 8; if (c2.z > c2.w) m2 |= 16; if (c2.z < 0.0f) m2 |= 32;
-            if (m0 & m1 & m2)
-                continue;
-            const unsigned clipMask = m0 | m1 | m2;
-            bool drawOk;
-            if (!clipMask)
-                drawOk = setup_triangle(g, cullMode, c0, c1, c2, ec);
-            else
-                drawOk = clip_and_setup(g, cullMode, clipMask, c0, c1, c2, ec);
-            drawn += drawOk ? 1u : 0u;
+                // clip masks, OB.cpp:596-620
+                unsigned m0 = 0, m1 = 0, m2 = 0;
+                if (c0.x > c0.w) m0 |= 1; if (c0.x < -c0.w) m0 |= 2; if (c0.y > c0.w) m0 |= 4; if (c0.y < -c0.w) m0 |= 8; if (c0.z > c0.w) m0 |= 16; if (c0.z < 0.0f) m0 |= 32;
+                if (c1.x > c1.w) m1 |= 1; if (c1.x < -c1.w) m1 |= 2; if (c1.y > c1.w) m1 |= 4; if (c1.y < -c1.w) m1 |= 8; if (c1.z > c1.w) m1 |= 16; if (c1.z < 0.0f) m1 |= 32;
+                if (c2.x > c2.w) m2 |= 1; if (c2.x < -c2.w) m2 |= 2; if (c2.y > c2.w) m2 |= 4; if (c2.y < -c2.w) m2 |= 8; if (c2.z > c2.w) m2 |= 16; if (c2.z < 0.0f) m2 |= 32;
+                if (!(m0 & m1 & m2))
+                {
+                    clipMask = m0 | m1 | m2;
+                    if (clipMask)
+                        kind = 2;
+                    else if (project_and_cull(g, cullMode, c0, c1, c2, p0, p1, p2, clockwise))
+                        kind = 1;
+                }
+            }
+            {
+                const int lane = threadIdx.x & 31;
+                const uint32_t b1 = __ballot_sync(0xffffffffu, kind == 1), b2 = __ballot_sync(0xffffffffu, kind == 2);
+                uint32_t pos1 = 0, pos2 = 0;
+                if (lane == 0)
+                {
+                    if (b1) pos1 = atomicAdd(&sCount[0], (uint32_t)__popc(b1));
+                    if (b2) pos2 = atomicAdd(&sCount[1], (uint32_t)__popc(b2));
+                }
+                pos1 = __shfl_sync(0xffffffffu, pos1, 0);
+                pos2 = __shfl_sync(0xffffffffu, pos2, 0);
+                const uint32_t below = (1u << lane) - 1u;
+                if (kind == 1)
+                {
+                    float* d = sSurv[pos1 + __popc(b1 & below)];
+                    d[0] = p0.x; d[1] = p0.y; d[2] = p0.z; d[3] = p1.x; d[4] = p1.y; d[5] = p1.z; d[6] = p2.x; d[7] = p2.y; d[8] = p2.z;
+                    d[9] = clockwise ? 1.0f : 0.0f;
+                }
+                else if (kind == 2)
+                {
+                    float* d = sClip[pos2 + __popc(b2 & below)];
+                    d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c0.w; d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c1.w;
+                    d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c2.w; d[12] = __uint_as_float(clipMask);
+                }
+            }
+            __syncthreads();
+            const uint32_t nSurv = sCount[0], nClip = sCount[1];
+            drawn += (threadIdx.x < nSurv) ? 1u : 0u; // every unclipped survivor reaches DrawTriangle2D: drawOk
+            // ---- stage 2: edge set-up + emit, dense ----
+            if (threadIdx.x < nSurv)
+            {
+                const float* d = sSurv[threadIdx.x];
+                const V3 a = {d[0], d[1], d[2]}, b = {d[3], d[4], d[5]}, c = {d[6], d[7], d[8]};
+                raster_setup(a, b, c, d[9] != 0.0f, ec);
+            }
+            // ---- stage 3: triangles that cross a clip plane ----
+            if (threadIdx.x < nClip)
+            {
+                const float* d = sClip[threadIdx.x];
+                const V4 a = {d[0], d[1], d[2], d[3]}, b = {d[4], d[5], d[6], d[7]}, c = {d[8], d[9], d[10], d[11]};
+                if (clip_and_setup(g, cullMode, __float_as_uint(d[12]), a, b, c, ec))
+                    ++drawn;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0)
+            {
+                sCount[0] = 0;
+                sCount[1] = 0;
+            }
+            __syncthreads();
         }
     }
     // ++numTriangles_ per source triangle that drew anything (OB.cpp:681-682)
@@ -720,6 +803,32 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
     int* depth = depthAll + (size_t)v * g.w * g.h;
     const bool fromGlobal = rd.irrOfView[v] != 0;
 
+    // ---- tiles nothing was binned to: constant depth and constant mips, no shared-memory round trip ----
+    {
+        const uint32_t* bc = rd.binCount + ((size_t)v * tg.numTiles + tIdx) * kNumCls;
+        if (!fromGlobal && (bc[0] | bc[1] | bc[2]) == 0)
+        {
+            const int tw4 = tw >> 2;
+            const int4 c4 = make_int4(kClearDepth, kClearDepth, kClearDepth, kClearDepth);
+            for (int i = tid; i < tw4 * rows; i += kTileThreads)
+                *reinterpret_cast<int4*>(depth + (size_t)(ty0 + i / tw4) * g.w + tx0 + ((i % tw4) << 2)) = c4;
+            if (tg.fused && rd.writeMips)
+            {
+                int2* mips = mipAll + (size_t)v * g.mipTexels;
+                const int2 c2 = make_int2(kClearDepth, kClearDepth);
+                for (int lv = 0; lv < tg.fused; ++lv)
+                {
+                    const int lw = tw >> (lv + 1);
+                    const int gy0 = ty0 >> (lv + 1), gx0 = tx0 >> (lv + 1);
+                    const int lrows = min(g.mh[lv] - gy0, kTileH >> (lv + 1));
+                    for (int i = tid; i < lw * lrows; i += kTileThreads)
+                        mips[g.moff[lv] + (size_t)(gy0 + i / lw) * g.mw[lv] + gx0 + i % lw] = c2;
+                }
+            }
+            return;
+        }
+    }
+
     // ---- initialise ----
     {
         const int n4 = (tw * kTileH) >> 2;
@@ -749,7 +858,8 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
     const int ty1 = ty0 + rows, tx1 = tx0 + tw;
     const uint32_t nLane = min(binCount[kClsLane], cap), nWarp = min(binCount[kClsWarp], cap), nCta = min(binCount[kClsCta], cap);
 
-    // (1) tiny triangles (bbox <= 8 x 8): one per lane, groups of 32 handed out dynamically
+    // (1) small triangles (bbox area <= 64; 86 % of the triangles of the benchmark scene): one per lane, groups of 32 handed out
+    //     dynamically
     {
         const uint32_t* bin = binBase + (size_t)kClsLane * cap;
         for (;;)
@@ -762,7 +872,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
                 break;
             if (base + lane < nLane)
             {
-                const TriSetup ts = load_tri(region + (bin[base + lane] & 0x3FFFFFFFu));
+                const TriSetup ts = load_tri(region + (bin[base + lane] & 0x1FFFFFFFu));
                 const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
                 for (int y = ya; y < yb; ++y)
                 {
@@ -775,53 +885,44 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             }
         }
     }
-    // (2) medium triangles: one warp each; the 32 lanes form a block of rows x columns chosen from the triangle's width
+    // (2) medium triangles: one warp each.  The warp is laid out as (32 / L) rows x L lanes per row, L chosen at set-up so that every
+    //     lane walks about 8 pixels of its row; groups of 8 triangles are handed out so that short bins still use all warps.
     {
         const uint32_t* bin = binBase + (size_t)kClsWarp * cap;
         for (;;)
         {
             uint32_t base = 0;
             if (lane == 0)
-                base = atomicAdd(&sNext[1], 32u);
+                base = atomicAdd(&sNext[1], (uint32_t)kWarpGroup);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= nWarp)
                 break;
-            const uint32_t cnt = min(32u, nWarp - base);
-            // every lane fetches one record (one L2 round trip per 32 triangles); the warp then walks them from registers
+            const uint32_t cnt = min((uint32_t)kWarpGroup, nWarp - base);
+            // lanes 0..cnt-1 fetch one record each (one L2 round trip per group); the warp then walks them from registers
             uint32_t mine = 0;
             TriSetup my;
             if (lane < cnt)
             {
                 mine = bin[base + lane];
-                my = load_tri(region + (mine & 0x3FFFFFFFu));
+                my = load_tri(region + (mine & 0x1FFFFFFFu));
             }
             for (uint32_t k = 0; k < cnt; ++k)
             {
                 const TriSetup ts = bcast_tri(my, (int)k);
-                const uint32_t hint = __shfl_sync(0xffffffffu, mine, (int)k) >> 30;
-                const int colsLog = hint == 0 ? 3 : (hint == 1 ? 4 : 5);
-                const int cols = 1 << colsLog, rowsPer = 32 >> colsLog;
-                const int lr = lane >> colsLog, lc = lane & (cols - 1);
+                const int lanesLog = (int)(__shfl_sync(0xffffffffu, mine, (int)k) >> 29);
+                const int perRow = 1 << lanesLog, rowsPer = 32 >> lanesLog;
+                const int lr = lane >> lanesLog, lc = lane & (perRow - 1);
                 const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
                 for (int yb0 = ya; yb0 < yb; yb0 += rowsPer)
                 {
                     const int y = yb0 + lr;
-                    HalfRow r;
-                    r.xl = 0; r.xr = 0; r.z0 = 0;
-                    int xa = 0, xb = 0;
                     if (y < yb)
                     {
-                        r = tri_row(ts, y);
-                        xa = max(r.xl, tx0);
-                        xb = min(r.xr, tx1);
-                    }
-                    int* trow = tile + (y - ty0) * tw - tx0;
-                    int x = xa + lc;
-                    while (__any_sync(0xffffffffu, x < xb))
-                    {
-                        if (x < xb)
+                        const HalfRow r = tri_row(ts, y);
+                        const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                        int* trow = tile + (y - ty0) * tw - tx0;
+                        for (int x = xa + lc; x < xb; x += perRow)
                             tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
-                        x += cols;
                     }
                 }
             }
@@ -833,7 +934,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         const int wid = tid >> 5;
         for (uint32_t i = 0; i < nCta; ++i)
         {
-            const TriSetup ts = load_tri(region + (bin[i] & 0x3FFFFFFFu));
+            const TriSetup ts = load_tri(region + (bin[i] & 0x1FFFFFFFu));
             const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
             for (int y = ya + wid; y < yb; y += kTileThreads / 32)
             {

@@ -19,10 +19,11 @@ constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the
 // tile path
 constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
 constexpr int kTileThreads = 512;
-constexpr uint32_t kClsLane = 0;    // bbox <= 8 x 8: one lane rasterises it
-constexpr uint32_t kClsWarp = 1;    // bbox area <= 4096: one warp, lanes form a rows x columns block
-constexpr uint32_t kClsCta = 2;     // larger: the whole CTA, rows interleaved over the warps
-constexpr int kNumCls = 3;          // every tile has one bin per class
+constexpr uint32_t kClsLane = 0;      // bbox area <= 64: one lane rasterises it
+constexpr uint32_t kClsWarp = 1;      // bbox area <= 16384: one warp, laid out as rows x lanes-per-row
+constexpr uint32_t kClsCta = 2;       // larger: the whole CTA, rows interleaved over the warps
+constexpr int kNumCls = 3;            // every tile has one bin per class
+constexpr int kWarpGroup = 8;         // warp-class triangles handed to a warp at a time
 
 struct TileGeom
 {
@@ -39,7 +40,7 @@ struct RasterDev
     uint32_t* triCount;          // per view: records emitted
     uint32_t* drawnSources;      // per view: source triangles that drew (numTriangles_ bookkeeping)
     uint32_t* flags;
-    uint32_t* binIdx;            // per view: numTiles x kNumCls x triCap entries (slot | hint << 30); nullptr = general path only
+    uint32_t* binIdx;            // per view: numTiles x kNumCls x triCap entries (slot | hint << 29); nullptr = general path only
     uint32_t* binCount;          // numViews x numTiles x kNumCls
     unsigned long long* irrList; // (view << 32 | slot) of triangles the tile path refuses
     uint32_t irrCap;
