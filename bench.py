@@ -288,18 +288,23 @@ def main():
 
     # device-resident leg ----------------------------------------------------------------------------------------------------
     batch.set_views(packed, stream)
-    counts_dev = ids_dev = None
+    gathered = {}
     if world > 1:
-        cptr, iptr, cap = capi._vp(), capi._vp(), capi.C.c_uint32()
-        capi._chk(capi.lib().u3d_batch_device_results(batch.h, capi.C.byref(cptr), capi.C.byref(iptr), capi.C.byref(cap)))
-        counts_dev = torch.as_tensor(_DevArray(cptr.value, (V, 2)), device="cuda")
-        gathered_counts = torch.empty((world * V, 2), dtype=counts_dev.dtype, device="cuda")
+        from urho3d_b200 import sharding
+        cptr, _, _ = batch.device_results()
+        counts_dev = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")
+        id_cap = V * out_cap
 
     def step_device():
         batch.run(capi.STAGE_VISIBLE, stream)
         if world > 1:
-            # the only collective of the path: gather per-view counts (visible sets follow the same pattern)
-            dist.all_gather_into_tensor(gathered_counts, counts_dev)
+            # the only exchange of the path: gather per-view counts and the visible sets of every rank over NCCL
+            _, pptr = batch.pack_device(stream)
+            packed_dev = torch.as_tensor(_DevArray(pptr, (id_cap,)), device="cuda")
+            total = int(counts_dev[:, 1].sum().item())
+            gathered["res"] = sharding.gather_results(counts_dev, packed_dev[:total], args.views, rank, world)
+            return 2
+        return 0
 
     for _ in range(args.warmup):
         flush.zero_()
@@ -319,9 +324,9 @@ def main():
     for k in range(args.steps):
         flush.zero_()
         starts[k].record()
-        step_device()
+        extra = step_device()
         ends[k].record()
-        launches += batch.last_launches()
+        launches += batch.last_launches() + extra
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

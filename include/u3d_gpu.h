@@ -204,6 +204,9 @@ U3D_API int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n
     uint64_t capacity, void* stream);
 /* Device pointers of the result arrays (for NCCL gathers): counts = max_views x 2 uint32, ids = max_views x out_capacity uint32. */
 U3D_API int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids_dev, uint32_t* out_capacity);
+/* Pack the emitted ids of all views back to back ON THE DEVICE (two launches on `stream`, no synchronisation) and return the device
+ * pointers: offsets = n+1 uint32, packed = sum of counts uint32.  This is what a rank hands to the NCCL gather. */
+U3D_API int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void** packed_dev);
 /* Kernel launches issued by the last u3d_batch_run / run_part on this batch. */
 U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
 

@@ -1,0 +1,384 @@
+// GPUCompute -- C++ host module that puts the reference's own class API on top of the C-ABI of libu3dgpu.so (include/u3d_gpu.h).
+//
+// Drop-in intent: the classes below keep the method names, argument meaning and return conventions of
+//   OcclusionBuffer                    Source/Urho3D/Graphics/OcclusionBuffer.h:91-226
+//   Octree::GetDrawables(OctreeQuery&) Source/Urho3D/Graphics/Octree.h:190, Octree.cpp:495-499
+//   OctreeQuery / FrustumOctreeQuery   Source/Urho3D/Graphics/OctreeQuery.h:40-70, 140-158
+//   OccludedFrustumOctreeQuery         Source/Urho3D/Graphics/View.cpp:116-158 (file-local there; promoted here)
+//   ShadowCasterOctreeQuery            Source/Urho3D/Graphics/View.cpp:59-84
+// so that View::DrawOccluders / View::GetDrawables / CheckVisibilityWork can be re-pointed with the edits shown in INTEGRATION.md.
+// The module is header-only and engine-agnostic: matrices, boxes and frusta are passed as plain float arrays (Matrix3x4::Data(),
+// Matrix4::Data(), BoundingBox min_/max_, Frustum::planes_); when compiled inside the engine (URHO3D_API defined) thin overloads taking
+// Camera*, Matrix3x4, BoundingBox and Frustum are enabled.
+//
+// There is no CPU fallback: every compute call ends in a CUDA kernel launch or returns false / throws GpuError at construction.
+#pragma once
+
+#include "../../include/u3d_gpu.h"
+
+#include <chrono>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+namespace Urho3D
+{
+namespace GPUCompute
+{
+
+/// Raised only by constructors (no usable device, out of memory); the per-frame API reports through return values like the reference.
+struct GpuError : std::runtime_error
+{
+    explicit GpuError(const std::string& what) : std::runtime_error(what) {}
+};
+
+inline void Check(int rc, const char* what)
+{
+    if (rc < 0)
+        throw GpuError(std::string(what) + ": " + u3d_last_error());
+}
+
+/// One CUDA device.  Create one per GPU (one process per GPU in the multi-GPU layout).
+class GpuContext
+{
+public:
+    explicit GpuContext(int device = 0) { Check(u3d_ctx_create(device, &ctx_), "u3d_ctx_create"); }
+    ~GpuContext() { u3d_ctx_destroy(ctx_); }
+    GpuContext(const GpuContext&) = delete;
+    GpuContext& operator=(const GpuContext&) = delete;
+    u3d_ctx* Handle() const { return ctx_; }
+
+private:
+    u3d_ctx* ctx_{};
+};
+
+/// CullMode, GraphicsDefs.h
+enum GpuCullMode { GPU_CULL_NONE = U3D_CULL_NONE, GPU_CULL_CCW = U3D_CULL_CCW, GPU_CULL_CW = U3D_CULL_CW };
+
+/// Occluder geometry kept resident in HBM (extension: avoids re-uploading vertex/index buffers every frame).
+class GpuMesh
+{
+public:
+    GpuMesh(GpuContext& ctx, const void* vertexData, unsigned vertexSize, unsigned vertexCount, const void* indexData, unsigned indexSize,
+        unsigned indexCount)
+    {
+        Check(u3d_mesh_create(ctx.Handle(), vertexData, vertexSize, vertexCount, indexData, indexSize, indexCount, &mesh_), "u3d_mesh_create");
+    }
+    ~GpuMesh() { u3d_mesh_destroy(mesh_); }
+    GpuMesh(const GpuMesh&) = delete;
+    GpuMesh& operator=(const GpuMesh&) = delete;
+    u3d_mesh* Handle() const { return mesh_; }
+
+private:
+    u3d_mesh* mesh_{};
+};
+
+/// Drop-in for class OcclusionBuffer (OcclusionBuffer.h:91-226).  Same call sequence as View::DrawOccluders (View.cpp:2231-2274).
+class GpuOcclusionBuffer
+{
+public:
+    explicit GpuOcclusionBuffer(GpuContext& ctx) { Check(u3d_ob_create(ctx.Handle(), &ob_), "u3d_ob_create"); }
+    ~GpuOcclusionBuffer() { u3d_ob_destroy(ob_); }
+    GpuOcclusionBuffer(const GpuOcclusionBuffer&) = delete;
+    GpuOcclusionBuffer& operator=(const GpuOcclusionBuffer&) = delete;
+
+    /// Set occlusion buffer size (OcclusionBuffer.cpp:61-113): odd heights are rounded up, non power-of-two widths are refused.
+    bool SetSize(int width, int height, bool threaded)
+    {
+        const bool ok = u3d_ob_set_size(ob_, width, height, threaded ? 1 : 0) > 0;
+        if (ok)
+            host_.assign((size_t)GetWidth() * GetHeight(), 0);
+        return ok;
+    }
+    /// Set camera view to render from (OcclusionBuffer.cpp:115-127), from the values the Camera getters return.
+    void SetView(const float* view3x4, const float* projection4x4, float nearClip, float farClip, bool reverseCulling)
+    {
+        std::memcpy(view_, view3x4, sizeof(view_));
+        std::memcpy(projection_, projection4x4, sizeof(projection_));
+        u3d_ob_set_view(ob_, view3x4, projection4x4, nearClip, farClip, reverseCulling ? 1 : 0);
+    }
+    void SetMaxTriangles(unsigned triangles) { u3d_ob_set_max_triangles(ob_, triangles); }
+    void SetCullMode(GpuCullMode mode) { u3d_ob_set_cull_mode(ob_, (int)mode); }
+    void Reset() { u3d_ob_reset(ob_); }
+    void Clear() { u3d_ob_clear(ob_); }
+    /// Submit non-indexed geometry.  Return true if the triangle budget was not exceeded (the batch is queued either way, as in the reference).
+    bool AddTriangles(const float* model3x4, const void* vertexData, unsigned vertexSize, unsigned vertexStart, unsigned vertexCount)
+    {
+        return u3d_ob_add_triangles(ob_, model3x4, vertexData, vertexSize, vertexStart, vertexCount) > 0;
+    }
+    /// Submit indexed geometry.
+    bool AddTriangles(const float* model3x4, const void* vertexData, unsigned vertexSize, const void* indexData, unsigned indexSize,
+        unsigned indexStart, unsigned indexCount)
+    {
+        return u3d_ob_add_triangles_indexed(ob_, model3x4, vertexData, vertexSize, indexData, indexSize, indexStart, indexCount) > 0;
+    }
+    /// Submit geometry that already lives on the GPU.
+    bool AddTriangles(const float* model3x4, const GpuMesh& mesh, unsigned start, unsigned count)
+    {
+        return u3d_ob_add_triangles_mesh(ob_, model3x4, mesh.Handle(), start, count) > 0;
+    }
+    /// Draw submitted batches.
+    void DrawTriangles() { u3d_ob_draw_triangles(ob_); }
+    /// Build reduced size mip levels.
+    void BuildDepthHierarchy() { u3d_ob_build_depth_hierarchy(ob_); }
+    void ResetUseTimer() { useTimer_ = std::chrono::steady_clock::now(); }
+    /// Return highest level depth values (a host copy refreshed by this call; the reference returns its own storage).
+    int* GetBuffer()
+    {
+        if (host_.empty() || u3d_ob_get_buffer(ob_, host_.data()) < 0)
+            return nullptr;
+        return host_.data();
+    }
+    const float* GetView() const { return view_; }
+    const float* GetProjection() const { return projection_; }
+    int GetWidth() const { return u3d_ob_get_width(ob_); }
+    int GetHeight() const { return u3d_ob_get_height(ob_); }
+    unsigned GetNumTriangles() const { return u3d_ob_get_num_triangles(ob_); }
+    unsigned GetMaxTriangles() const { return u3d_ob_get_max_triangles(ob_); }
+    GpuCullMode GetCullMode() const { return (GpuCullMode)u3d_ob_get_cull_mode(ob_); }
+    bool IsThreaded() const { return u3d_ob_is_threaded(ob_) != 0; }
+    /// Test a bounding box (min.xyz, max.xyz) for visibility.  One launch + synchronisation per call: prefer the batched forms.
+    bool IsVisible(const float* boxMinMax6) const { return u3d_ob_is_visible(ob_, boxMinMax6) != 0; }
+    /// Many boxes at once (extension).
+    bool IsVisible(const float* boxesMinMax6, unsigned count, unsigned char* out) const { return u3d_ob_is_visible_many(ob_, boxesMinMax6, count, out) >= 0; }
+    unsigned GetUseTimer() const
+    {
+        return (unsigned)std::chrono::duration_cast<std::chrono::milliseconds>(std::chrono::steady_clock::now() - useTimer_).count();
+    }
+    /// Mip level `level` as (min,max) pairs, for tests.
+    bool GetMip(int level, std::vector<int>& out, int& width, int& height)
+    {
+        if (u3d_ob_mip_size(ob_, level, &width, &height) < 0)
+            return false;
+        out.resize((size_t)width * height * 2);
+        return u3d_ob_get_mip(ob_, level, out.data()) >= 0;
+    }
+    int GetNumLevels() const { return u3d_ob_num_levels(ob_); }
+    u3d_ob* Handle() const { return ob_; }
+
+#ifdef URHO3D_API
+    // In-engine overloads with the reference's exact signatures.
+    void SetView(Camera* camera)
+    {
+        if (!camera)
+            return;
+        SetView(camera->GetView().Data(), camera->GetProjection().Data(), camera->GetNearClip(), camera->GetFarClip(), camera->GetReverseCulling());
+    }
+    void SetCullMode(CullMode mode) { SetCullMode((GpuCullMode)mode); }
+    bool AddTriangles(const Matrix3x4& model, const void* vertexData, unsigned vertexSize, unsigned vertexStart, unsigned vertexCount)
+    {
+        return AddTriangles(model.Data(), vertexData, vertexSize, vertexStart, vertexCount);
+    }
+    bool AddTriangles(const Matrix3x4& model, const void* vertexData, unsigned vertexSize, const void* indexData, unsigned indexSize,
+        unsigned indexStart, unsigned indexCount)
+    {
+        return AddTriangles(model.Data(), vertexData, vertexSize, indexData, indexSize, indexStart, indexCount);
+    }
+    bool IsVisible(const BoundingBox& worldSpaceBox) const
+    {
+        const float b[6] = {worldSpaceBox.min_.x_, worldSpaceBox.min_.y_, worldSpaceBox.min_.z_, worldSpaceBox.max_.x_, worldSpaceBox.max_.y_,
+            worldSpaceBox.max_.z_};
+        return IsVisible(b);
+    }
+#endif
+
+private:
+    u3d_ob* ob_{};
+    std::vector<int> host_;
+    float view_[12]{};
+    float projection_[16]{};
+    std::chrono::steady_clock::time_point useTimer_{std::chrono::steady_clock::now()};
+};
+
+/// Base of the GPU-evaluable queries (OctreeQuery.h:40-70).  result_ receives drawable ids in the reference's result_ order.
+struct GpuOctreeQuery
+{
+    GpuOctreeQuery(std::vector<unsigned>& result, unsigned char drawableFlags, unsigned viewMask) :
+        result_(result), drawableFlags_(drawableFlags), viewMask_(viewMask)
+    {
+    }
+    virtual ~GpuOctreeQuery() = default;
+    virtual int Mode() const = 0;
+    virtual const GpuOcclusionBuffer* Buffer() const { return nullptr; }
+
+    std::vector<unsigned>& result_;
+    unsigned char drawableFlags_;
+    unsigned viewMask_;
+    float planes_[24]{}; // Frustum::planes_: 6 x (normal.xyz, d)
+};
+
+/// FrustumOctreeQuery (OctreeQuery.h:140-158).
+struct GpuFrustumOctreeQuery : GpuOctreeQuery
+{
+    GpuFrustumOctreeQuery(std::vector<unsigned>& result, const float* planes6x4, unsigned char drawableFlags = 0xFF, unsigned viewMask = 0xFFFFFFFFu) :
+        GpuOctreeQuery(result, drawableFlags, viewMask)
+    {
+        std::memcpy(planes_, planes6x4, sizeof(planes_));
+    }
+    int Mode() const override { return U3D_QUERY_FRUSTUM; }
+};
+
+/// OccludedFrustumOctreeQuery (View.cpp:116-158).
+struct GpuOccludedFrustumOctreeQuery : GpuFrustumOctreeQuery
+{
+    GpuOccludedFrustumOctreeQuery(std::vector<unsigned>& result, const float* planes6x4, GpuOcclusionBuffer* buffer, unsigned char drawableFlags = 0xFF,
+        unsigned viewMask = 0xFFFFFFFFu) :
+        GpuFrustumOctreeQuery(result, planes6x4, drawableFlags, viewMask), buffer_(buffer)
+    {
+    }
+    int Mode() const override { return U3D_QUERY_OCCLUDED; }
+    const GpuOcclusionBuffer* Buffer() const override { return buffer_; }
+    GpuOcclusionBuffer* buffer_;
+};
+
+/// ShadowCasterOctreeQuery (View.cpp:59-84).
+struct GpuShadowCasterOctreeQuery : GpuFrustumOctreeQuery
+{
+    using GpuFrustumOctreeQuery::GpuFrustumOctreeQuery;
+    int Mode() const override { return U3D_QUERY_SHADOWCASTER; }
+};
+
+/// Mirror of the reference Octree for the query path: host structure kept by the reference's insertion rules, flattened into a
+/// GPU-resident SoA on Sync().  Insert / move / remove stay on the host exactly as SURVEY 2a prescribes.
+class GpuOctree
+{
+public:
+    GpuOctree(GpuContext& ctx, const float* boxMin3, const float* boxMax3, unsigned numLevels) : ctx_(ctx)
+    {
+        Check(u3d_octree_create(boxMin3, boxMax3, numLevels, &tree_), "u3d_octree_create");
+    }
+    ~GpuOctree()
+    {
+        u3d_scene_destroy(scene_);
+        u3d_octree_destroy(tree_);
+    }
+    GpuOctree(const GpuOctree&) = delete;
+    GpuOctree& operator=(const GpuOctree&) = delete;
+
+    /// Octree::InsertDrawable (Octree.cpp:134-166).  Returns the drawable id used in query results.
+    unsigned InsertDrawable(const float* worldBoxMinMax6, unsigned char drawableFlags, unsigned viewMask, bool occludee, bool castShadows)
+    {
+        const uint8_t oc = occludee, cs = castShadows;
+        uint32_t id = 0;
+        Check(u3d_octree_add(tree_, 1, worldBoxMinMax6, &drawableFlags, &viewMask, &oc, &cs, &id), "u3d_octree_add");
+        dirty_ = true;
+        return id;
+    }
+    /// Many drawables at once (arrays may be null for the defaults).
+    unsigned InsertDrawables(unsigned count, const float* worldBoxes, const unsigned char* drawableFlags, const unsigned* viewMasks,
+        const unsigned char* occludee, const unsigned char* castShadows)
+    {
+        uint32_t id = 0;
+        Check(u3d_octree_add(tree_, count, worldBoxes, drawableFlags, viewMasks, occludee, castShadows, &id), "u3d_octree_add");
+        dirty_ = true;
+        return id;
+    }
+    /// A drawable moved or was resized: the reinsertion rule of Octree::Update (Octree.cpp:440-472).
+    void UpdateDrawable(unsigned id, const float* worldBoxMinMax6)
+    {
+        u3d_octree_update(tree_, id, worldBoxMinMax6);
+        dirty_ = true;
+    }
+    void RemoveDrawable(unsigned id)
+    {
+        u3d_octree_remove(tree_, id);
+        dirty_ = true;
+    }
+    /// Re-flatten and upload if anything changed since the last query (the analogue of Octree::Update being called once per frame,
+    /// Renderer.cpp:1475-1524).
+    void Sync()
+    {
+        if (!dirty_ && scene_)
+            return;
+        u3d_scene_destroy(scene_);
+        scene_ = nullptr;
+        Check(u3d_scene_create(ctx_.Handle(), tree_, &scene_), "u3d_scene_create");
+        u3d_scene_counts(scene_, &numOctants_, &numDrawables_);
+        dirty_ = false;
+    }
+    /// Octree::GetDrawables(OctreeQuery&) (Octree.cpp:495-499): clears query.result_, then fills it in pre-order DFS order.
+    void GetDrawables(GpuOctreeQuery& query)
+    {
+        Sync();
+        query.result_.clear();
+        query.result_.resize(numDrawables_ ? numDrawables_ : 1);
+        uint32_t queryCount = 0, count = 0;
+        const GpuOcclusionBuffer* buffer = query.Buffer();
+        const int rc = u3d_octree_query(scene_, buffer ? buffer->Handle() : nullptr, query.planes_, query.drawableFlags_, query.viewMask_, query.Mode(),
+            U3D_STAGE_QUERY, query.result_.data(), (uint32_t)query.result_.size(), &queryCount, &count);
+        query.result_.resize(rc < 0 ? 0 : count);
+    }
+    /// GetDrawables followed by CheckVisibilityWork's occlusion predicate (View.cpp:177) in one pass: what View::GetDrawables needs.
+    void GetVisibleDrawables(GpuOctreeQuery& query, unsigned* queryResultSize = nullptr)
+    {
+        Sync();
+        query.result_.clear();
+        query.result_.resize(numDrawables_ ? numDrawables_ : 1);
+        uint32_t queryCount = 0, count = 0;
+        const GpuOcclusionBuffer* buffer = query.Buffer();
+        const int rc = u3d_octree_query(scene_, buffer ? buffer->Handle() : nullptr, query.planes_, query.drawableFlags_, query.viewMask_, query.Mode(),
+            U3D_STAGE_VISIBLE, query.result_.data(), (uint32_t)query.result_.size(), &queryCount, &count);
+        query.result_.resize(rc < 0 ? 0 : count);
+        if (queryResultSize)
+            *queryResultSize = queryCount;
+    }
+    unsigned GetNumOctants() const { return numOctants_; }
+    unsigned GetNumDrawables() const { return numDrawables_; }
+    u3d_scene* Scene()
+    {
+        Sync();
+        return scene_;
+    }
+    u3d_octree* Tree() const { return tree_; }
+
+private:
+    GpuContext& ctx_;
+    u3d_octree* tree_{};
+    u3d_scene* scene_{};
+    uint32_t numOctants_{}, numDrawables_{};
+    bool dirty_{true};
+};
+
+/// The batched many-view entry point (new): V views per call through raster + hierarchy + octree query + visibility.
+class GpuViewBatch
+{
+public:
+    GpuViewBatch(GpuContext& ctx, GpuOctree& octree, u3d_occluders* occluders, int width, int height, unsigned maxViews, unsigned outCapacity,
+        unsigned long long triPool = 0)
+    {
+        Check(u3d_batch_create(ctx.Handle(), octree.Scene(), occluders, width, height, maxViews, outCapacity, triPool, &batch_), "u3d_batch_create");
+        counts_.resize((size_t)maxViews * 2);
+        offsets_.resize((size_t)maxViews + 1);
+    }
+    ~GpuViewBatch() { u3d_batch_destroy(batch_); }
+    GpuViewBatch(const GpuViewBatch&) = delete;
+    GpuViewBatch& operator=(const GpuViewBatch&) = delete;
+
+    /// Visible drawable ids of every view, packed; Offsets()[v]..Offsets()[v+1] delimit view v.  Returns false on failure (u3d_last_error()).
+    bool CullViews(const u3d_view* views, unsigned count, std::vector<unsigned>& ids, bool visibilityPredicate = true)
+    {
+        const int stage = visibilityPredicate ? U3D_STAGE_VISIBLE : U3D_STAGE_QUERY;
+        if (u3d_batch_set_views(batch_, views, count, nullptr) < 0 || u3d_batch_run(batch_, stage, nullptr) < 0 ||
+            u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
+            return false;
+        unsigned long long total = 0;
+        for (unsigned v = 0; v < count; ++v)
+            total += counts_[2 * v + 1];
+        ids.resize(total ? total : 1);
+        if (u3d_batch_read_packed(batch_, offsets_.data(), ids.data(), ids.size(), nullptr) < 0)
+            return false;
+        ids.resize(total);
+        return true;
+    }
+    const std::vector<unsigned>& Offsets() const { return offsets_; }
+    const std::vector<unsigned>& Counts() const { return counts_; }
+    u3d_batch* Handle() const { return batch_; }
+
+private:
+    u3d_batch* batch_{};
+    std::vector<unsigned> counts_, offsets_;
+};
+
+} // namespace GPUCompute
+} // namespace Urho3D

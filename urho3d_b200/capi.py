@@ -100,6 +100,7 @@ SIGNATURES = {
     "u3d_batch_read_setup_records": (C.c_int, [_vp, C.c_uint32, _i32, C.c_uint32, _u32, _vp]),
     "u3d_batch_cull_views": (C.c_int, [_vp, _vp, C.c_uint32, C.c_int, _u32, _u32, _u32, C.c_uint64, _vp]),
     "u3d_batch_device_results": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u32]),
+    "u3d_batch_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
 }
 
@@ -478,6 +479,18 @@ class Batch:
         out = np.zeros((max(c.value, 1), 16), np.int32)
         _chk(lib().u3d_batch_read_setup_records(self.h, view, _p(out, _i32), c.value, C.byref(c), stream))
         return out[:c.value]
+
+    def device_results(self):
+        """Raw device pointers (counts [max_views][2], ids [max_views][out_capacity]) for zero-copy use by torch / NCCL."""
+        c, i, cap = _vp(), _vp(), C.c_uint32()
+        _chk(lib().u3d_batch_device_results(self.h, C.byref(c), C.byref(i), C.byref(cap)))
+        return c.value, i.value, cap.value
+
+    def pack_device(self, stream=None):
+        """Pack the visible ids on the device; returns device pointers (offsets [n+1], packed ids)."""
+        o, p = _vp(), _vp()
+        _chk(lib().u3d_batch_pack_device(self.h, stream, C.byref(o), C.byref(p)))
+        return o.value, p.value
 
     def last_launches(self):
         return lib().u3d_batch_last_launches(self.h)

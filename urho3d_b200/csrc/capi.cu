@@ -1491,6 +1491,27 @@ int u3d_batch_read_packed(u3d_batch* b, uint32_t* offsets, uint32_t* ids, uint64
     return U3D_OK;
 }
 
+int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void** packed_dev)
+{
+    if (!b)
+        return fail(U3D_ERR_INVALID, "u3d_batch_pack_device: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const int V = (int)b->numViews;
+    CU_CHECK(b->packed.ensure((size_t)std::max(V, 1) * std::max<uint32_t>(b->outCap, 1)));
+    if (V)
+    {
+        k_pack_offsets<<<1, 1024, 0, st>>>(V, b->outCounts.p, b->outCap, b->packOffsets.p);
+        k_pack_ids<<<V, 256, 0, st>>>(b->outCounts.p, b->outCap, b->packOffsets.p, b->outIdx.p, b->packed.p);
+        CU_CHECK(cudaGetLastError());
+    }
+    if (offsets_dev)
+        *offsets_dev = b->packOffsets.p;
+    if (packed_dev)
+        *packed_dev = b->packed.p;
+    return U3D_OK;
+}
+
 int u3d_batch_read_view(u3d_batch* b, uint32_t view, uint32_t* ids, uint32_t capacity, uint32_t* count, void* stream)
 {
     if (!b || view >= b->numViews)
