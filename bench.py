@@ -288,21 +288,24 @@ def main():
 
     # device-resident leg ----------------------------------------------------------------------------------------------------
     batch.set_views(packed, stream)
-    gathered = {}
+    gather = None
     if world > 1:
         from urho3d_b200 import sharding
+        # size the gather buffers from one untimed pass (no host synchronisation is needed inside the timed steps)
+        batch.run(capi.STAGE_VISIBLE, stream)
+        c0 = batch.counts(stream)
+        cap_t = torch.tensor([int(c0[:, 1].sum() * 1.25) + 4096], dtype=torch.int64, device="cuda")
+        dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
         cptr, _, _ = batch.device_results()
         counts_dev = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")
-        id_cap = V * out_cap
+        gather = sharding.RawGather(args.views, world, min(int(cap_t.item()), V * out_cap), torch.device("cuda", local_rank))
 
     def step_device():
         batch.run(capi.STAGE_VISIBLE, stream)
         if world > 1:
-            # the only exchange of the path: gather per-view counts and the visible sets of every rank over NCCL
+            # the only exchange of the path: every rank's per-view counts and packed visible sets, all-gathered over NCCL
             _, pptr = batch.pack_device(stream)
-            packed_dev = torch.as_tensor(_DevArray(pptr, (id_cap,)), device="cuda")
-            total = int(counts_dev[:, 1].sum().item())
-            gathered["res"] = sharding.gather_results(counts_dev, packed_dev[:total], args.views, rank, world)
+            gather.run(counts_dev, torch.as_tensor(_DevArray(pptr, (V * out_cap,)), device="cuda"))
             return 2
         return 0
 
@@ -312,6 +315,10 @@ def main():
     torch.cuda.synchronize()
     counts = batch.counts(stream)  # also checks the overflow flags
     stats = batch.tri_stats(stream)
+    if gather is not None:
+        assert not gather.overflowed(), "gather buffers too small"
+        g_counts, _, _ = gather.reorder()
+        assert np.array_equal(g_counts[rank::world].cpu().numpy().astype(np.uint32), counts), "gathered counts disagree with the local ones"
 
     if world > 1:
         dist.barrier()

@@ -46,6 +46,14 @@ def _worker(rank, world, port, n_views, q):
     counts = torch.tensor([[c, len(v)] for c, v in res], dtype=torch.int32).reshape(-1, 2)
     ids = torch.from_numpy(np.concatenate([v for _, v in res]) if res else np.zeros(0, np.int32))
     g_counts, g_off, g_ids = sharding.gather_results(counts, ids, n_views, rank, world)
+    # the sync-free variant used in the steady state must give the same answer
+    raw = sharding.RawGather(n_views, world, 40000, torch.device("cpu"))
+    padded = torch.zeros(40000, dtype=torch.int32)
+    padded[:ids.shape[0]] = ids
+    raw.run(counts, padded)
+    assert not raw.overflowed()
+    r_counts, r_off, r_ids = raw.reorder()
+    assert torch.equal(r_counts, g_counts) and torch.equal(r_off, g_off) and torch.equal(r_ids, g_ids)
     if rank == 0:
         q.put((g_counts.numpy(), g_off.numpy(), g_ids.numpy()))
     dist.barrier()

@@ -174,7 +174,7 @@ template <class Apply> __device__ __forceinline__ void visible_stage_b(const Buf
     }
 }
 
-__global__ void __launch_bounds__(kCullThreads) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
+__global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
     uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
 {
