@@ -449,8 +449,12 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     __shared__ float sMvp[kSetupItems][16];
     __shared__ DrawItem sItem[kSetupItems];
     __shared__ uint32_t sPre[kSetupItems + 1];
-    __shared__ float sSurv[kSetupThreads][11]; // unclipped survivors of stage 1: three screen vertices + winding (odd stride: no bank conflicts)
-    __shared__ float sClip[kSetupThreads][13]; // triangles for the clipper: three clip-space vertices + plane mask
+    // queues between the stages (dynamic shared memory): unclipped survivors of stage 1 (three screen vertices + winding, odd stride
+    // against bank conflicts) and triangles for the clipper (three clip-space vertices + plane mask).  Each holds 2 x blockDim entries
+    // and is drained 256 at a time, so stages 2 and 3 always run on full warps.
+    extern __shared__ float sQueues[];
+    float (*sSurv)[11] = reinterpret_cast<float (*)[11]>(sQueues);
+    float (*sClip)[13] = reinterpret_cast<float (*)[13]>(sQueues + 2 * kSetupThreads * 11);
     __shared__ uint32_t sCount[2];
     if (threadIdx.x == 0)
     {
@@ -480,6 +484,53 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     ec.forceIrregular = rd.forceIrregular;
 
     uint32_t drawn = 0;
+    // stage 2: edge set-up + emit for the first n queued survivors (n <= blockDim), then close the gap.  Every unclipped survivor
+    // reaches DrawTriangle2D, i.e. counts as drawn (drawOk).
+    auto drain_survivors = [&](uint32_t n) {
+        const uint32_t total = sCount[0];
+        float keep[11];
+        const bool mover = threadIdx.x + n < total;
+        if (threadIdx.x < n)
+        {
+            const float* d = sSurv[threadIdx.x];
+            const V3 a = {d[0], d[1], d[2]}, b = {d[3], d[4], d[5]}, c = {d[6], d[7], d[8]};
+            raster_setup(a, b, c, d[9] != 0.0f, ec);
+            ++drawn;
+        }
+        if (mover)
+            for (int i = 0; i < 10; ++i)
+                keep[i] = sSurv[threadIdx.x + n][i];
+        __syncthreads();
+        if (mover)
+            for (int i = 0; i < 10; ++i)
+                sSurv[threadIdx.x][i] = keep[i];
+        if (threadIdx.x == 0)
+            sCount[0] = total - n;
+        __syncthreads();
+    };
+    // stage 3: the clipper for the first n queued triangles
+    auto drain_clipped = [&](uint32_t n) {
+        const uint32_t total = sCount[1];
+        float keep[13];
+        const bool mover = threadIdx.x + n < total;
+        if (threadIdx.x < n)
+        {
+            const float* d = sClip[threadIdx.x];
+            const V4 a = {d[0], d[1], d[2], d[3]}, b = {d[4], d[5], d[6], d[7]}, c = {d[8], d[9], d[10], d[11]};
+            if (clip_and_setup(g, cullMode, __float_as_uint(d[12]), a, b, c, ec))
+                ++drawn;
+        }
+        if (mover)
+            for (int i = 0; i < 13; ++i)
+                keep[i] = sClip[threadIdx.x + n][i];
+        __syncthreads();
+        if (mover)
+            for (int i = 0; i < 13; ++i)
+                sClip[threadIdx.x][i] = keep[i];
+        if (threadIdx.x == 0)
+            sCount[1] = total - n;
+        __syncthreads();
+    };
     for (uint32_t itemBase = blockIdx.x * kSetupItems; itemBase < nItems; itemBase += gridDim.x * kSetupItems)
     {
         const uint32_t nLocal = min((uint32_t)kSetupItems, nItems - itemBase);
@@ -610,32 +661,18 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
                 }
             }
             __syncthreads();
-            const uint32_t nSurv = sCount[0], nClip = sCount[1];
-            drawn += (threadIdx.x < nSurv) ? 1u : 0u; // every unclipped survivor reaches DrawTriangle2D: drawOk
-            // ---- stage 2: edge set-up + emit, dense ----
-            if (threadIdx.x < nSurv)
-            {
-                const float* d = sSurv[threadIdx.x];
-                const V3 a = {d[0], d[1], d[2]}, b = {d[3], d[4], d[5]}, c = {d[6], d[7], d[8]};
-                raster_setup(a, b, c, d[9] != 0.0f, ec);
-            }
-            // ---- stage 3: triangles that cross a clip plane ----
-            if (threadIdx.x < nClip)
-            {
-                const float* d = sClip[threadIdx.x];
-                const V4 a = {d[0], d[1], d[2], d[3]}, b = {d[4], d[5], d[6], d[7]}, c = {d[8], d[9], d[10], d[11]};
-                if (clip_and_setup(g, cullMode, __float_as_uint(d[12]), a, b, c, ec))
-                    ++drawn;
-            }
-            __syncthreads();
-            if (threadIdx.x == 0)
-            {
-                sCount[0] = 0;
-                sCount[1] = 0;
-            }
-            __syncthreads();
+            // ---- stage 2 / 3 whenever a queue holds a full block of work ----
+            if (sCount[0] >= kSetupThreads)
+                drain_survivors(kSetupThreads);
+            if (sCount[1] >= kSetupThreads)
+                drain_clipped(kSetupThreads);
         }
     }
+    __syncthreads();
+    if (sCount[0])
+        drain_survivors(sCount[0]);
+    if (sCount[1])
+        drain_clipped(sCount[1]);
     // ++numTriangles_ per source triangle that drew anything (OB.cpp:681-682)
     for (int o = 16; o; o >>= 1)
         drawn += __shfl_xor_sync(0xffffffffu, drawn, o);
@@ -1137,7 +1174,7 @@ void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, 
     // a few blocks per view sweep its item slices; single views get as many blocks as they have slices
     const uint32_t perView = numViews >= 148 ? 8u : 1024u;
     dim3 grid(slices < perView ? slices : perView, numViews);
-    k_setup_triangles<<<grid, kSetupThreads, 0, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd);
+    k_setup_triangles<<<grid, kSetupThreads, kSetupQueueBytes, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd);
 }
 
 void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,
@@ -1151,6 +1188,9 @@ void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSet
 
 cudaError_t init_tile_kernel()
 {
+    cudaError_t e = cudaFuncSetAttribute(k_setup_triangles, cudaFuncAttributeMaxDynamicSharedMemorySize, kSetupQueueBytes);
+    if (e != cudaSuccess)
+        return e;
     return cudaFuncSetAttribute(k_fill_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, 256 * kTileH * 4);
 }
 

@@ -8,6 +8,7 @@ namespace u3d
 constexpr int kItemTris = 256;      // triangles per draw item; bigger batches are split so no block owns a huge mesh
 constexpr int kSetupItems = 64;     // draw items per set-up slice (64 boxes = 768 triangles = 3 full sweeps of 256 threads)
 constexpr int kSetupThreads = 256;
+constexpr int kSetupQueueBytes = 2 * kSetupThreads * (11 + 13) * 4; // survivor + clipper queues of k_setup_triangles
 constexpr int kCullThreads = 512;
 
 // bits of the per-batch device flag word
