@@ -199,6 +199,9 @@ struct ViewSet
     DevBuf<uint32_t> binIdx, binCount, irrTotal, irrOfView;
     DevBuf<unsigned long long> irrList;
     uint32_t irrCap{};
+    DevBuf<float> clipQueue;
+    DevBuf<uint32_t> clipCount;
+    uint32_t clipCap{};
     RasterDev raster_dev(bool tiles, int writeMips)
     {
         RasterDev rd{};
@@ -214,6 +217,9 @@ struct ViewSet
         rd.irrCap = irrCap;
         rd.irrTotal = irrTotal.p;
         rd.irrOfView = irrOfView.p;
+        rd.clipQueue = clipQueue.p;
+        rd.clipCap = clipCap;
+        rd.clipCount = clipCount.p;
         rd.writeMips = writeMips;
         rd.forceIrregular = g_forceIrregular;
         return rd;
@@ -247,6 +253,10 @@ struct ViewSet
         CU_CHECK(flags.ensure(1));
         CU_CHECK(items.ensure((size_t)nviews * std::max<uint32_t>(itemCap, 1)));
         CU_CHECK(pool.ensure(std::max<uint64_t>(poolTris, 1)));
+        // triangles that cross a clip plane are a fraction of the submitted ones; an overflow is reported, not dropped silently
+        clipCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(poolTris / 4, 4096), 0x7FFFFFFFu);
+        CU_CHECK(clipQueue.ensure((size_t)clipCap * kClipEntryFloats));
+        CU_CHECK(clipCount.ensure(1));
         return 0;
     }
 };
@@ -987,6 +997,9 @@ int u3d_ob_draw_triangles(u3d_ob* ob)
     CU_CHECK(ob->meshTable.ensure(table.size()));
     CU_CHECK(vs.items.ensure(items.size()));
     vs.itemCap = (uint32_t)items.size();
+    // any submitted triangle may need the clipper
+    vs.clipCap = (uint32_t)std::min<uint64_t>(totalTris + 1, 0x7FFFFFFFu);
+    CU_CHECK(vs.clipQueue.ensure((size_t)vs.clipCap * kClipEntryFloats));
     // every source triangle can be clipped into several; grow on overflow
     uint64_t poolTris = totalTris + totalTris / 2 + 256;
     for (int attempt = 0; attempt < 8; ++attempt)
@@ -1003,6 +1016,7 @@ int u3d_ob_draw_triangles(u3d_ob* ob)
         CU_CHECK(cudaMemcpyAsync(vs.triBase.p, &zero64, 8, cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, 4, st));
         CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.clipCount.p, 0, 4, st));
         CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
         int rc = ob_upload_view(ob); // cullMode_ is read at draw time (OB.cpp:634)
         if (rc < 0)
@@ -1300,6 +1314,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         CU_CHECK(cudaMemsetAsync(vs.submitted.p, 0, (size_t)V * 4, st));
         CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, (size_t)V * 4, st));
         CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
+        CU_CHECK(cudaMemsetAsync(vs.clipCount.p, 0, 4, st));
         if (vs.useTiles)
         {
             CU_CHECK(cudaMemsetAsync(vs.binCount.p, 0, (size_t)V * vs.tg.numTiles * kNumCls * 4, st));
@@ -1380,6 +1395,8 @@ static int batch_check_flags(u3d_batch* b, cudaStream_t st)
     uint32_t flags = 0;
     CU_CHECK(cudaMemcpyAsync(&flags, b->vs.flags.p, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
+    if (flags & kFlagClipOverflow)
+        return fail(U3D_ERR_CAPACITY, "clipper queue too small for this batch: recreate the batch with a larger tri_pool");
     if (flags & kFlagIrrOverflow)
         return fail(U3D_ERR_CAPACITY, "more than 2^20 irregular triangles in one batch (degenerate input)");
     if (flags & (kFlagTriOverflow | kFlagPoolOverflow))

@@ -437,33 +437,8 @@ __device__ __noinline__ bool clip_and_setup(const BufGeom& g, int cullMode, unsi
     return drawOk;
 }
 
-/// Blocks of a view sweep its draw items in slices of kSetupItems; inside a slice the threads sweep the flat triangle index
-/// space of those items.  DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
-__global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
-    const DrawItem* __restrict__ items, uint32_t itemCap, const uint32_t* __restrict__ itemCount, const float* __restrict__ models,
-    const MeshDev* __restrict__ meshes, RasterDev rd)
+__device__ __forceinline__ EmitCtx make_emit_ctx(const BufGeom& g, const TileGeom& tg, const RasterDev& rd, int v)
 {
-    const int v = blockIdx.y;
-    const uint32_t nItems = itemCount[v];
-
-    __shared__ float sMvp[kSetupItems][16];
-    __shared__ DrawItem sItem[kSetupItems];
-    __shared__ uint32_t sPre[kSetupItems + 1];
-    // queues between the stages (dynamic shared memory): unclipped survivors of stage 1 (three screen vertices + winding, odd stride
-    // against bank conflicts) and triangles for the clipper (three clip-space vertices + plane mask).  Each holds 2 x blockDim entries
-    // and is drained 256 at a time, so stages 2 and 3 always run on full warps.
-    extern __shared__ float sQueues[];
-    float (*sSurv)[11] = reinterpret_cast<float (*)[11]>(sQueues);
-    float (*sClip)[13] = reinterpret_cast<float (*)[13]>(sQueues + 2 * kSetupThreads * 11);
-    __shared__ uint32_t sCount[2];
-    if (threadIdx.x == 0)
-    {
-        sCount[0] = 0;
-        sCount[1] = 0;
-    }
-
-    const ViewConst& vc = views[v];
-    const int cullMode = vc.cullMode;
     EmitCtx ec;
     ec.region = rd.pool + rd.triBase[v];
     ec.cap = rd.triCap[v];
@@ -482,6 +457,54 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     ec.tilesX = tg.tilesX;
     ec.tilesY = tg.tilesY;
     ec.forceIrregular = rd.forceIrregular;
+    return ec;
+}
+
+/// The clipper as its own launch: one thread per triangle that crosses a clip plane (queued by k_setup_triangles), dense over all views,
+/// so that the slow path (<= 64 triangles of scratch in local memory) never stalls the set-up blocks.  DrawTriangle's else-branch, OB.cpp:640-679.
+__global__ void __launch_bounds__(128) k_clip_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views, RasterDev rd)
+{
+    const uint32_t n = min(*rd.clipCount, rd.clipCap);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        const float4* d = reinterpret_cast<const float4*>(rd.clipQueue + (size_t)i * kClipEntryFloats);
+        const float4 a = d[0], b = d[1], c = d[2], m = d[3];
+        const int v = (int)__float_as_uint(m.y);
+        const EmitCtx ec = make_emit_ctx(g, tg, rd, v);
+        const V4 c0 = {a.x, a.y, a.z, a.w}, c1 = {b.x, b.y, b.z, b.w}, c2 = {c.x, c.y, c.z, c.w};
+        if (clip_and_setup(g, views[v].cullMode, __float_as_uint(m.x), c0, c1, c2, ec))
+            atomicAdd(&rd.drawnSources[v], 1u);
+    }
+}
+
+/// Blocks of a view sweep its draw items in slices of kSetupItems; inside a slice the threads sweep the flat triangle index
+/// space of those items.  DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
+__global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
+    const DrawItem* __restrict__ items, uint32_t itemCap, const uint32_t* __restrict__ itemCount, const float* __restrict__ models,
+    const MeshDev* __restrict__ meshes, RasterDev rd)
+{
+    const int v = blockIdx.y;
+    const uint32_t nItems = itemCount[v];
+
+    __shared__ float sMvp[kSetupItems][16];
+    __shared__ DrawItem sItem[kSetupItems];
+    __shared__ uint32_t sPre[kSetupItems + 1];
+    // queues between the stages (dynamic shared memory): unclipped survivors of stage 1 (three screen vertices + winding, odd stride
+    // against bank conflicts) and triangles for the clipper (three clip-space vertices + plane mask).  Each holds 2 x blockDim entries
+    // and is drained 256 at a time, so stages 2 and 3 always run on full warps.
+    extern __shared__ float sQueues[];
+    float (*sSurv)[11] = reinterpret_cast<float (*)[11]>(sQueues);
+    __shared__ uint32_t sCount[2];
+    if (threadIdx.x == 0)
+    {
+        sCount[0] = 0;
+        sCount[1] = 0;
+    }
+
+    const ViewConst& vc = views[v];
+    const int cullMode = vc.cullMode;
+    const EmitCtx ec = make_emit_ctx(g, tg, rd, v);
+
 
     uint32_t drawn = 0;
     // stage 2: edge set-up + emit for the first n queued survivors (n <= blockDim), then close the gap.  Every unclipped survivor
@@ -506,29 +529,6 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
                 sSurv[threadIdx.x][i] = keep[i];
         if (threadIdx.x == 0)
             sCount[0] = total - n;
-        __syncthreads();
-    };
-    // stage 3: the clipper for the first n queued triangles
-    auto drain_clipped = [&](uint32_t n) {
-        const uint32_t total = sCount[1];
-        float keep[13];
-        const bool mover = threadIdx.x + n < total;
-        if (threadIdx.x < n)
-        {
-            const float* d = sClip[threadIdx.x];
-            const V4 a = {d[0], d[1], d[2], d[3]}, b = {d[4], d[5], d[6], d[7]}, c = {d[8], d[9], d[10], d[11]};
-            if (clip_and_setup(g, cullMode, __float_as_uint(d[12]), a, b, c, ec))
-                ++drawn;
-        }
-        if (mover)
-            for (int i = 0; i < 13; ++i)
-                keep[i] = sClip[threadIdx.x + n][i];
-        __syncthreads();
-        if (mover)
-            for (int i = 0; i < 13; ++i)
-                sClip[threadIdx.x][i] = keep[i];
-        if (threadIdx.x == 0)
-            sCount[1] = total - n;
         __syncthreads();
     };
     for (uint32_t itemBase = blockIdx.x * kSetupItems; itemBase < nItems; itemBase += gridDim.x * kSetupItems)
@@ -642,7 +642,7 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
                 if (lane == 0)
                 {
                     if (b1) pos1 = atomicAdd(&sCount[0], (uint32_t)__popc(b1));
-                    if (b2) pos2 = atomicAdd(&sCount[1], (uint32_t)__popc(b2));
+                    if (b2) pos2 = atomicAdd(rd.clipCount, (uint32_t)__popc(b2)); // global queue for the clipper kernel
                 }
                 pos1 = __shfl_sync(0xffffffffu, pos1, 0);
                 pos2 = __shfl_sync(0xffffffffu, pos2, 0);
@@ -655,24 +655,28 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
                 }
                 else if (kind == 2)
                 {
-                    float* d = sClip[pos2 + __popc(b2 & below)];
-                    d[0] = c0.x; d[1] = c0.y; d[2] = c0.z; d[3] = c0.w; d[4] = c1.x; d[5] = c1.y; d[6] = c1.z; d[7] = c1.w;
-                    d[8] = c2.x; d[9] = c2.y; d[10] = c2.z; d[11] = c2.w; d[12] = __uint_as_float(clipMask);
+                    const uint32_t slot = pos2 + __popc(b2 & below);
+                    if (slot < rd.clipCap)
+                    {
+                        float4* d = reinterpret_cast<float4*>(rd.clipQueue + (size_t)slot * kClipEntryFloats);
+                        d[0] = make_float4(c0.x, c0.y, c0.z, c0.w);
+                        d[1] = make_float4(c1.x, c1.y, c1.z, c1.w);
+                        d[2] = make_float4(c2.x, c2.y, c2.z, c2.w);
+                        d[3] = make_float4(__uint_as_float(clipMask), __uint_as_float((uint32_t)v), 0.0f, 0.0f);
+                    }
+                    else
+                        atomicOr(rd.flags, kFlagClipOverflow);
                 }
             }
             __syncthreads();
-            // ---- stage 2 / 3 whenever a queue holds a full block of work ----
+            // ---- stage 2 whenever the queue holds a full block of work ----
             if (sCount[0] >= kSetupThreads)
                 drain_survivors(kSetupThreads);
-            if (sCount[1] >= kSetupThreads)
-                drain_clipped(kSetupThreads);
         }
     }
     __syncthreads();
     if (sCount[0])
         drain_survivors(sCount[0]);
-    if (sCount[1])
-        drain_clipped(sCount[1]);
     // ++numTriangles_ per source triangle that drew anything (OB.cpp:681-682)
     for (int o = 16; o; o >>= 1)
         drawn += __shfl_xor_sync(0xffffffffu, drawn, o);
@@ -1175,6 +1179,7 @@ void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, 
     const uint32_t perView = numViews >= 148 ? 8u : 1024u;
     dim3 grid(slices < perView ? slices : perView, numViews);
     k_setup_triangles<<<grid, kSetupThreads, kSetupQueueBytes, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd);
+    k_clip_triangles<<<148 * 8, 128, 0, s>>>(g, tg, views, rd);
 }
 
 void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,

@@ -8,7 +8,8 @@ namespace u3d
 constexpr int kItemTris = 256;      // triangles per draw item; bigger batches are split so no block owns a huge mesh
 constexpr int kSetupItems = 64;     // draw items per set-up slice (64 boxes = 768 triangles = 3 full sweeps of 256 threads)
 constexpr int kSetupThreads = 256;
-constexpr int kSetupQueueBytes = 2 * kSetupThreads * (11 + 13) * 4; // survivor + clipper queues of k_setup_triangles
+constexpr int kSetupQueueBytes = 2 * kSetupThreads * 11 * 4; // survivor queue of k_setup_triangles
+constexpr int kClipEntryFloats = 16;  // clipper queue entry: three clip-space vertices, plane mask, view
 constexpr int kCullThreads = 512;
 
 // bits of the per-batch device flag word
@@ -16,6 +17,7 @@ constexpr uint32_t kFlagTriOverflow = 1u;   // a view's triangle region was too 
 constexpr uint32_t kFlagPoolOverflow = 2u;  // the triangle pool cannot hold all regions
 constexpr uint32_t kFlagOutOverflow = 4u;   // a view produced more results than the output capacity
 constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the general-path list holds
+constexpr uint32_t kFlagClipOverflow = 16u;  // more plane-crossing triangles than the clipper queue holds
 
 // tile path
 constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
@@ -47,6 +49,9 @@ struct RasterDev
     uint32_t irrCap;
     uint32_t* irrTotal;
     uint32_t* irrOfView;         // per view
+    float* clipQueue;            // kClipEntryFloats per triangle that needs the clipper
+    uint32_t clipCap;
+    uint32_t* clipCount;
     int writeMips;
     int forceIrregular;          // test hook: send every triangle through the general path
 };
