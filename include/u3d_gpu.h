@@ -80,6 +80,8 @@ U3D_API const char* u3d_last_error(void);
 U3D_API int u3d_abi_version(void);
 /* Test hook.  "force_irregular" = 1 routes every set-up triangle of the batched path through the general (global-memory) fill. */
 U3D_API int u3d_debug_set_option(const char* name, int value);
+/* Diagnostic: after u3d_debug_set_option("cull_prof", 1), clock64 sums of the cull kernel's phases over all CTAs (8 slots). */
+U3D_API int u3d_debug_read_cull_prof(unsigned long long* out8);
 
 /* ---- context -------------------------------------------------------------------------------------------------------------- */
 U3D_API int u3d_ctx_create(int device, u3d_ctx** out);

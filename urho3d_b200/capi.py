@@ -39,6 +39,7 @@ SIGNATURES = {
     "u3d_last_error": (C.c_char_p, []),
     "u3d_abi_version": (C.c_int, []),
     "u3d_debug_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "u3d_debug_read_cull_prof": (C.c_int, [C.POINTER(C.c_uint64)]),
     "u3d_ctx_create": (C.c_int, [C.c_int, C.POINTER(_vp)]),
     "u3d_ctx_destroy": (None, [_vp]),
     "u3d_ctx_device": (C.c_int, [_vp]),
@@ -131,6 +132,12 @@ def lib():
 
 def debug_set_option(name, value):
     _chk(lib().u3d_debug_set_option(name.encode(), int(value)))
+
+
+def read_cull_prof():
+    out = np.zeros(8, np.uint64)
+    _chk(lib().u3d_debug_read_cull_prof(out.ctypes.data_as(C.POINTER(C.c_uint64))))
+    return out
 
 
 def _chk(rc):

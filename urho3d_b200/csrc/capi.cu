@@ -155,6 +155,7 @@ struct u3d_scene
     SceneDev dev{};
     DevBuf<float4> octMin, octMax, drwMin, drwMax;
     DevBuf<int> octCount, bfs, levelStart;
+    DevBuf<int2> octChild;
     DevBuf<uint32_t> drwId;
 };
 
@@ -337,7 +338,20 @@ int u3d_debug_set_option(const char* name, int value)
         g_forceIrregular = value;
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "cull_prof") == 0)
+    {
+        cull_prof_enable(value);
+        return U3D_OK;
+    }
     return fail(U3D_ERR_INVALID, "u3d_debug_set_option: unknown option");
+}
+
+int u3d_debug_read_cull_prof(unsigned long long* out8)
+{
+    if (!out8)
+        return fail(U3D_ERR_INVALID, "NULL argument");
+    cull_prof_read(out8);
+    return U3D_OK;
 }
 
 int u3d_ctx_create(int device, u3d_ctx** out)
@@ -517,8 +531,24 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
             bfs[cur[level[i]]++] = (int)i;
     }
     for (uint32_t i = 1; i < M; ++i)
-        if (level[parent[i]] >= level[i])
-            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: parent level must be smaller than child level");
+        if (level[parent[i]] + 1 != level[i])
+            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: a child's level must be its parent's level + 1");
+    if (M > (256u * 32u << 9))
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_scene_create_flat: more than 4M octants");
+    // children of an octant are contiguous in the level-sorted list (stable sort of a DFS order): record where
+    std::vector<int2> child(M, make_int2(0, 0));
+    for (uint32_t p = 0; p < M; ++p)
+    {
+        const int o = bfs[p];
+        if (o == 0)
+            continue;
+        int2& c = child[parent[o]];
+        if (c.y == 0)
+            c.x = (int)p;
+        else if (c.x + c.y != (int)p)
+            return fail(U3D_ERR_INVALID, "u3d_scene_create_flat: octants are not in DFS pre-order (children not contiguous per level)");
+        ++c.y;
+    }
 
     u3d_scene* s = new (std::nothrow) u3d_scene();
     if (!s)
@@ -532,7 +562,7 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
     };
     std::vector<int> cnt(count, count + M);
     cudaError_t e = cudaSuccess;
-    if ((e = up(s->octMin, omin)) || (e = up(s->octMax, omax)) || (e = up(s->octCount, cnt)) || (e = up(s->bfs, bfs)) ||
+    if ((e = up(s->octMin, omin)) || (e = up(s->octMax, omax)) || (e = up(s->octCount, cnt)) || (e = up(s->bfs, bfs)) || (e = up(s->octChild, child)) ||
         (e = up(s->levelStart, levelStart)) || (e = up(s->drwMin, dmin)) || (e = up(s->drwMax, dmax)) || (e = up(s->drwId, ids)))
     {
         delete s;
@@ -545,6 +575,7 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
     s->dev.octMax = s->octMax.p;
     s->dev.octCount = s->octCount.p;
     s->dev.bfs = s->bfs.p;
+    s->dev.octChild = s->octChild.p;
     s->dev.levelStart = s->levelStart.p;
     s->dev.drwMin = s->drwMin.p;
     s->dev.drwMax = s->drwMax.p;

@@ -23,6 +23,7 @@ struct CullShared
 {
     ViewConst vc;
     uint32_t pre[kCullThreads + 1];   // exclusive scan of drawable counts of the current octant chunk
+    uint32_t first[kCullThreads];     // first drawable of each octant of the chunk | inside << 31
     uint32_t ring[kRing];             // octants waiting for TestOctant / frustum survivors waiting for the occlusion test
     uint32_t visWord[kRingGroups];    // one ballot word per group of 32 queued drawables
     uint32_t groupOff[kRingGroups];
@@ -174,6 +175,20 @@ template <class Apply> __device__ __forceinline__ void visible_stage_b(const Buf
     }
 }
 
+// Optional in-kernel phase timers (test/diagnostic hook, off by default): clock64 deltas of thread 0 summed over all CTAs.
+__device__ unsigned long long g_cullProf[8];
+__device__ int g_cullProfOn;
+#define CULL_PROF_MARK(slot)                                                                  \
+    do                                                                                        \
+    {                                                                                         \
+        if (profOn && tid == 0)                                                               \
+        {                                                                                     \
+            const long long now_ = clock64();                                                 \
+            atomicAdd(&g_cullProf[slot], (unsigned long long)(now_ - profT));                  \
+            profT = now_;                                                                     \
+        }                                                                                     \
+    } while (0)
+
 __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
     uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
@@ -181,6 +196,8 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
     __shared__ CullShared sh;
     const int v = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
+    const bool profOn = g_cullProfOn != 0;
+    long long profT = profOn ? clock64() : 0;
 
     // view constants -> shared
     {
@@ -208,6 +225,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
     unsigned char* state = octStateAll + (size_t)v * sc.numOctants;
     uint32_t* out = outIdx + (size_t)v * outCap;
 
+    CULL_PROF_MARK(0);
     // ---------------- phase 1: octant states (0 culled, 1 visited, 2 visited with inside == true) ----------------
     // Per level: a sweep queues the octants whose parent survived (dense queue, order irrelevant); warps then pull groups of 32 from
     // the queue and run TestOctant, so the expensive test never runs on mostly-idle warps.
@@ -300,11 +318,15 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
             }
             if (++sweeps == kRing / kCullThreads) // the queue could be full after this many sweeps
             {
+                CULL_PROF_MARK(1);
                 eval_octants();
+                CULL_PROF_MARK(2);
                 sweeps = 0;
             }
         }
+        CULL_PROF_MARK(1);
         eval_octants(); // children need these states
+        CULL_PROF_MARK(2);
     }
 
     // ---------------- phase 2: drawables of surviving octants, DFS order ----------------
@@ -387,16 +409,25 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
 
     for (int chunk = 0; chunk < sc.numOctants; chunk += kCullThreads)
     {
+        // per octant of the chunk: state, drawable count and first drawable (three independent loads), then a scan of the counts
         const int o = chunk + tid;
-        uint32_t cnt = 0;
-        if (o < sc.numOctants && state[o])
-            cnt = (uint32_t)sc.octCount[o];
+        uint32_t cnt = 0, firstWord = 0;
+        if (o < sc.numOctants)
+        {
+            const unsigned char st = state[o];
+            const uint32_t c = (uint32_t)sc.octCount[o];
+            const uint32_t f = (uint32_t)__float_as_int(sc.octMax[o].w);
+            cnt = st ? c : 0u;
+            firstWord = f | (st == 2 ? 0x80000000u : 0u);
+        }
         uint32_t total;
         const uint32_t pre = block_exclusive_scan(cnt, sh.warpTot, total);
         sh.pre[tid] = pre;
+        sh.first[tid] = firstWord;
         if (tid == 0)
             sh.pre[kCullThreads] = total;
         __syncthreads();
+        CULL_PROF_MARK(3);
         if (!total)
             continue;
 
@@ -414,9 +445,9 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                     const uint32_t m = (lo + hi) >> 1;
                     if (sh.pre[m] <= j) lo = m; else hi = m;
                 }
-                const int oo = chunk + (int)lo;
-                d = (uint32_t)__float_as_int(sc.octMax[oo].w) + (j - sh.pre[lo]);
-                const bool inside = state[oo] == 2;
+                const uint32_t fw = sh.first[lo];
+                d = (fw & 0x7FFFFFFFu) + (j - sh.pre[lo]);
+                const bool inside = (fw >> 31) != 0;
                 const float4 mn = sc.drwMin[d];
                 const float4 mx = sc.drwMax[d];
                 const uint32_t meta = __float_as_uint(mn.w);
@@ -452,12 +483,18 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                 }
                 __syncthreads();
                 if (sh.ringCount + kCullThreads > kRing)
+                {
+                    CULL_PROF_MARK(4);
                     eval_drawables();
+                    CULL_PROF_MARK(5);
+                }
             }
         }
     }
+    CULL_PROF_MARK(4);
     if (needOcclusion && sh.ringCount)
         eval_drawables();
+    CULL_PROF_MARK(5);
     __syncthreads();
     if (tid == 0)
     {
@@ -484,6 +521,18 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     if (!numViews)
         return;
     k_cull_views<<<numViews, kCullThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+}
+
+void cull_prof_enable(int on)
+{
+    cudaMemcpyToSymbol(g_cullProfOn, &on, sizeof(int));
+    unsigned long long zero[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    cudaMemcpyToSymbol(g_cullProf, zero, sizeof(zero));
+}
+
+void cull_prof_read(unsigned long long* out8)
+{
+    cudaMemcpyFromSymbol(out8, g_cullProf, 8 * sizeof(unsigned long long));
 }
 
 void launch_is_visible(const BufGeom& g, const ViewConst* view, const int* depth, const int2* mips, int mipsValid, const float* aabb6, int n,

@@ -65,6 +65,7 @@ struct SceneDev
     const float4* octMin;          // xyz = cullingBox_.min_, w = parent (int bits; -1 for the root)
     const float4* octMax;          // xyz = cullingBox_.max_, w = first drawable (int bits)
     const int* octCount;           // drawables owned by the octant
+    const int2* octChild;          // x = position of the first child in bfs[], y = number of children (children are contiguous there)
     const int* bfs;                // octant indices sorted by level (stable)
     const int* levelStart;         // numLevels + 1 offsets into bfs
     const float4* drwMin;          // xyz = world AABB min, w = drawableFlags | kMetaOccludee | kMetaCastShadows (uint bits)
@@ -91,6 +92,11 @@ void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mi
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
     uint32_t* flags, cudaStream_t s);
+
+/// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
+/// 3 chunk set-up, 4 frustum rounds, 5 drawable occlusion tests + emission).
+void cull_prof_enable(int on);
+void cull_prof_read(unsigned long long* out8);
 
 /// OcclusionBuffer::IsVisible for n boxes against view 0's buffer.
 void launch_is_visible(const BufGeom& g, const ViewConst* view, const int* depth, const int2* mips, int mipsValid, const float* aabb6, int n,
