@@ -16,6 +16,7 @@ using namespace u3d;
 
 static thread_local std::string g_err;
 static int g_forceIrregular = 0; // u3d_debug_set_option("force_irregular")
+static int g_laneAreaMax = kLaneAreaMax, g_warpAreaMax = kWarpAreaMax; // tuning hooks "lane_area_max" / "warp_area_max"
 
 static int fail(int code, const std::string& msg)
 {
@@ -223,6 +224,8 @@ struct ViewSet
         rd.clipCount = clipCount.p;
         rd.writeMips = writeMips;
         rd.forceIrregular = g_forceIrregular;
+        rd.laneAreaMax = g_laneAreaMax;
+        rd.warpAreaMax = g_warpAreaMax;
         return rd;
     }
     int alloc(u3d_ctx* c, int w, int h, uint32_t nviews, uint32_t itemCapPerView, uint64_t poolTris, bool tiles = false)
@@ -336,6 +339,16 @@ int u3d_debug_set_option(const char* name, int value)
     if (name && std::strcmp(name, "force_irregular") == 0)
     {
         g_forceIrregular = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "lane_area_max") == 0)
+    {
+        g_laneAreaMax = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "warp_area_max") == 0)
+    {
+        g_warpAreaMax = value;
         return U3D_OK;
     }
     if (name && std::strcmp(name, "cull_prof") == 0)

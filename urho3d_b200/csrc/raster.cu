@@ -172,6 +172,7 @@ struct EmitCtx
     uint32_t view;
     int w, h, tileW, tilesX, tilesY;
     int forceIrregular;
+    int laneAreaMax, warpAreaMax;
 };
 
 /// Append one record to the view's region; on the tile path also classify it and bin it.
@@ -237,9 +238,9 @@ __device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
     // class = who rasterises it in the tile kernel; hint (top bits of the entry) = lane layout for the warp class
     uint32_t cls, hint = 0;
     const long long area = (long long)width * height;
-    if (area <= 64)
+    if (area <= ec.laneAreaMax)
         cls = kClsLane;
-    else if (area <= 16384)
+    else if (area <= ec.warpAreaMax)
     {
         // lanes per row: each lane walks about 8 pixels of its row; the rest of the warp covers more rows at once
         cls = kClsWarp;
@@ -457,6 +458,8 @@ __device__ __forceinline__ EmitCtx make_emit_ctx(const BufGeom& g, const TileGeo
     ec.tilesX = tg.tilesX;
     ec.tilesY = tg.tilesY;
     ec.forceIrregular = rd.forceIrregular;
+    ec.laneAreaMax = rd.laneAreaMax;
+    ec.warpAreaMax = rd.warpAreaMax;
     return ec;
 }
 

@@ -26,6 +26,8 @@ constexpr uint32_t kClsLane = 0;      // bbox area <= 64: one lane rasterises it
 constexpr uint32_t kClsWarp = 1;      // bbox area <= 16384: one warp, laid out as rows x lanes-per-row
 constexpr uint32_t kClsCta = 2;       // larger: the whole CTA, rows interleaved over the warps
 constexpr int kNumCls = 3;            // every tile has one bin per class
+constexpr int kLaneAreaMax = 256;     // bbox area up to which one lane rasterises a triangle
+constexpr int kWarpAreaMax = 2048;    // ... up to which one warp does; larger ones take the whole CTA
 constexpr int kWarpGroup = 8;         // warp-class triangles handed to a warp at a time
 
 struct TileGeom
@@ -54,6 +56,7 @@ struct RasterDev
     uint32_t* clipCount;
     int writeMips;
     int forceIrregular;          // test hook: send every triangle through the general path
+    int laneAreaMax, warpAreaMax; // bbox-area limits of the lane and warp size classes
 };
 
 /// Flattened octree + drawables resident in HBM (DFS pre-order = the order Octant::GetDrawablesInternal visits, Octree.cpp:229-255).
