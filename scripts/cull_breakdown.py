@@ -31,7 +31,7 @@ capi.debug_set_option("cull_prof", 1)
 b.run(capi.STAGE_VISIBLE, s, part=2); torch.cuda.synchronize()
 prof = capi.read_cull_prof().astype(np.float64)
 capi.debug_set_option("cull_prof", 0)
-names = ["prologue", "octant sweeps", "octant tests", "chunk set-up", "frustum rounds", "drawable tests+emit", "-", "-"]
+names = ["prologue", "octant sweeps", "octant tests lv>=7", "chunk set-up", "frustum rounds", "drawable tests+emit", "octant tests lv<=5", "octant tests lv 6"]
 print("in-kernel phase share (thread-0 clocks summed over CTAs):")
 for n, p in zip(names, prof):
     if p: print("   %-22s %5.1f%%   %8.0f cycles per view" % (n, 100 * p / prof.sum(), p / V))

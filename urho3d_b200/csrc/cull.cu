@@ -326,7 +326,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
         }
         CULL_PROF_MARK(1);
         eval_octants(); // children need these states
-        CULL_PROF_MARK(2);
+        CULL_PROF_MARK(lv <= 5 ? 6 : (lv == 6 ? 7 : 2));
     }
 
     // ---------------- phase 2: drawables of surviving octants, DFS order ----------------
