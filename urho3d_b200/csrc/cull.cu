@@ -19,16 +19,16 @@ constexpr int kWStack = 256;            // per-warp texel stack of the cooperati
 constexpr int kHeavyExtent = 32;        // rects larger than this (pixels) are tested by a whole warp
 constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 
-struct CullShared
+template <int T> struct CullShared
 {
     ViewConst vc;
-    uint32_t pre[kCullThreads + 1];   // exclusive scan of drawable counts of the current octant chunk
-    uint32_t first[kCullThreads];     // first drawable of each octant of the chunk | inside << 31
+    uint32_t pre[T + 1];   // exclusive scan of drawable counts of the current octant chunk
+    uint32_t first[T];     // first drawable of each octant of the chunk | inside << 31
     uint32_t ring[kRing];             // octants waiting for TestOctant / frustum survivors waiting for the occlusion test
     uint32_t visWord[kRingGroups];    // one ballot word per group of 32 queued drawables
     uint32_t groupOff[kRingGroups];
-    uint32_t warpTot[kCullThreads / 32];
-    uint32_t wstack[kCullThreads / 32][kWStack];
+    uint32_t warpTot[T / 32];
+    uint32_t wstack[T / 32][T >= 1024 ? kWStack / 2 : kWStack];
     uint4 heavy[kHeavyCap];           // (left | top << 16, right | bottom << 16, z, queue index | result bits << 30)
     uint32_t heavyCount;
     uint32_t heavyNext;
@@ -39,7 +39,7 @@ struct CullShared
 };
 
 /// Block-wide exclusive scan of one value per thread; returns the exclusive prefix, total through `total`.
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* warpTot, uint32_t& total)
+template <int T> __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t* warpTot, uint32_t& total)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     uint32_t x = val;
@@ -55,7 +55,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t*
         warpTot[wid] = x;
     __syncthreads();
     // every warp scans the (<= 32) warp totals with shuffles
-    const uint32_t t = lane < kCullThreads / 32 ? warpTot[lane] : 0;
+    const uint32_t t = lane < T / 32 ? warpTot[lane] : 0;
     uint32_t y = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -70,7 +70,7 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t val, uint32_t*
 }
 
 /// Ordered block compaction of one predicate per thread: rank among the block's true predicates + their number.
-__device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uint32_t& total)
+template <int T> __device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uint32_t& total)
 {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t bal = __ballot_sync(0xffffffffu, pred);
@@ -78,7 +78,7 @@ __device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uin
     if (lane == 0)
         warpTot[wid] = __popc(bal);
     __syncthreads();
-    const uint32_t t = lane < kCullThreads / 32 ? warpTot[lane] : 0;
+    const uint32_t t = lane < T / 32 ? warpTot[lane] : 0;
     uint32_t y = t;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1)
@@ -95,8 +95,8 @@ __device__ __forceinline__ uint32_t block_rank(bool pred, uint32_t* warpTot, uin
 /// Stage A of an evaluation pass, one box per lane: project, answer small rects on the spot, park large rects in the CTA's heavy queue
 /// (tag = queue index | caller bits).  Returns the lane's answer; `parked` tells that the answer will come from stage B instead.
 /// If the queue is full the warp walks the box at once.  Every lane of the warp must call.
-__device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
-    bool active, const float4& mn, const float4& mx, uint32_t tag, CullShared& sh, bool& parked)
+template <int T> __device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
+    bool active, const float4& mn, const float4& mx, uint32_t tag, CullShared<T>& sh, bool& parked)
 {
     const int lane = threadIdx.x & 31;
     BoxRect r;
@@ -140,7 +140,7 @@ __device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* v
             rr.right = __shfl_sync(0xffffffffu, r.right, src);
             rr.bottom = __shfl_sync(0xffffffffu, r.bottom, src);
             rr.z = __shfl_sync(0xffffffffu, r.z, src);
-            const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], kWStack);
+            const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], (int)(sizeof(sh.wstack[0]) / sizeof(uint32_t)));
             if (lane == src)
                 vis = v;
         }
@@ -149,8 +149,8 @@ __device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* v
 }
 
 /// Stage B: warps take parked boxes one at a time and walk them cooperatively.  `apply(tag, visible)` is run by lane 0.
-template <class Apply> __device__ __forceinline__ void visible_stage_b(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips,
-    CullShared& sh, Apply apply)
+template <int T, class Apply> __device__ __forceinline__ void visible_stage_b(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips,
+    CullShared<T>& sh, Apply apply)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n = min(sh.heavyCount, (uint32_t)kHeavyCap);
@@ -169,7 +169,7 @@ template <class Apply> __device__ __forceinline__ void visible_stage_b(const Buf
         rr.right = (int)(e.y & 0xFFFFu);
         rr.bottom = (int)(e.y >> 16);
         rr.z = (int)e.z;
-        const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], kWStack);
+        const bool v = range_visible_warp(g, depth, mips, rr, sh.wstack[threadIdx.x >> 5], (int)(sizeof(sh.wstack[0]) / sizeof(uint32_t)));
         if (lane == 0)
             apply(e.w, v);
     }
@@ -189,11 +189,11 @@ __device__ int g_cullProfOn;
         }                                                                                     \
     } while (0)
 
-__global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
+template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
     uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
 {
-    __shared__ CullShared sh;
+    __shared__ CullShared<T> sh;
     const int v = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const bool profOn = g_cullProfOn != 0;
@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
     {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(views + v);
         uint32_t* dst = reinterpret_cast<uint32_t*>(&sh.vc);
-        for (int i = tid; i < (int)(sizeof(ViewConst) / 4); i += kCullThreads)
+        for (int i = tid; i < (int)(sizeof(ViewConst) / 4); i += T)
             dst[i] = src[i];
         if (tid == 0)
         {
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
             bool parked = false;
             if (occludedQuery)
             {
-                const bool vis = visible_stage_a(g, vc.vp, depth, mips, useMips, res != OUTSIDE, mn, mx, (uint32_t)o | ((uint32_t)res << 30), sh, parked);
+                const bool vis = visible_stage_a<T>(g, vc.vp, depth, mips, useMips, res != OUTSIDE, mn, mx, (uint32_t)o | ((uint32_t)res << 30), sh, parked);
                 if (!vis)
                     res = OUTSIDE;
             }
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
         }
         __syncthreads();
         if (sh.heavyCount)
-            visible_stage_b(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+            visible_stage_b<T>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
                 const int res = (int)(tag >> 30);
                 state[tag & 0x3FFFFFFFu] = !vis ? 0 : (res == INSIDE ? 2 : 1);
             });
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
     {
         const int a = sc.levelStart[lv], b = sc.levelStart[lv + 1];
         int sweeps = 0;
-        for (int base = a; base < b; base += kCullThreads)
+        for (int base = a; base < b; base += T)
         {
             const int i = base + tid;
             bool need = false;
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                 if (need)
                     sh.ring[pos + __popc(bal & ((1u << lane) - 1u))] = e;
             }
-            if (++sweeps == kRing / kCullThreads) // the queue could be full after this many sweeps
+            if (++sweeps == kRing / T) // the queue could be full after this many sweeps
             {
                 CULL_PROF_MARK(1);
                 eval_octants();
@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                 }
             }
             bool parked = false;
-            if (visible_stage_a(g, vc.vp, depth, mips, useMips, test, mn, mx, idx, sh, parked))
+            if (visible_stage_a<T>(g, vc.vp, depth, mips, useMips, test, mn, mx, idx, sh, parked))
                 vis = true;
             const uint32_t word = __ballot_sync(0xffffffffu, vis);
             if (lane == 0)
@@ -370,22 +370,22 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
         __syncthreads();
         if (sh.heavyCount)
         {
-            visible_stage_b(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+            visible_stage_b<T>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
                 if (vis)
                     atomicOr(&sh.visWord[tag >> 5], 1u << (tag & 31u));
             });
             __syncthreads();
         }
         const uint32_t nGroups = (n + 31) >> 5;
-        // exclusive scan of the groups' popcounts (kRingGroups <= kCullThreads)
+        // exclusive scan of the groups' popcounts (kRingGroups <= T)
         uint32_t total;
         const uint32_t cnt = (uint32_t)tid < nGroups ? (uint32_t)__popc(sh.visWord[tid]) : 0u;
-        const uint32_t off = block_exclusive_scan(cnt, sh.warpTot, total);
+        const uint32_t off = block_exclusive_scan<T>(cnt, sh.warpTot, total);
         if ((uint32_t)tid < nGroups)
             sh.groupOff[tid] = off;
         __syncthreads();
         const uint32_t cursor = sh.outCursor;
-        for (uint32_t grp = tid >> 5; grp < nGroups; grp += kCullThreads / 32)
+        for (uint32_t grp = tid >> 5; grp < nGroups; grp += T / 32)
         {
             const uint32_t word = sh.visWord[grp];
             if ((word >> lane) & 1u)
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
         __syncthreads();
     };
 
-    for (int chunk = 0; chunk < sc.numOctants; chunk += kCullThreads)
+    for (int chunk = 0; chunk < sc.numOctants; chunk += T)
     {
         // per octant of the chunk: state, drawable count and first drawable (three independent loads), then a scan of the counts
         const int o = chunk + tid;
@@ -421,17 +421,17 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
             firstWord = f | (st == 2 ? 0x80000000u : 0u);
         }
         uint32_t total;
-        const uint32_t pre = block_exclusive_scan(cnt, sh.warpTot, total);
+        const uint32_t pre = block_exclusive_scan<T>(cnt, sh.warpTot, total);
         sh.pre[tid] = pre;
         sh.first[tid] = firstWord;
         if (tid == 0)
-            sh.pre[kCullThreads] = total;
+            sh.pre[T] = total;
         __syncthreads();
         CULL_PROF_MARK(3);
         if (!total)
             continue;
 
-        for (uint32_t base = 0; base < total; base += kCullThreads)
+        for (uint32_t base = 0; base < total; base += T)
         {
             const uint32_t j = base + tid;
             bool pass = false;
@@ -439,7 +439,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
             if (j < total)
             {
                 // owning octant: largest i with pre[i] <= j (octants with zero drawables share a prefix; take the last)
-                uint32_t lo = 0, hi = kCullThreads;
+                uint32_t lo = 0, hi = T;
                 while (hi - lo > 1)
                 {
                     const uint32_t m = (lo + hi) >> 1;
@@ -456,7 +456,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                     pass = inside || frustum_test<true>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
             }
             uint32_t tot;
-            const uint32_t rank = block_rank(pass, sh.warpTot, tot);
+            const uint32_t rank = block_rank<T>(pass, sh.warpTot, tot);
             if (!needOcclusion)
             {
                 const uint32_t ob = sh.outCursor;
@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(kCullThreads, 3) k_cull_views(SceneDev sc, Buf
                     sh.queryCount += tot;
                 }
                 __syncthreads();
-                if (sh.ringCount + kCullThreads > kRing)
+                if (sh.ringCount + T > kRing)
                 {
                     CULL_PROF_MARK(4);
                     eval_drawables();
@@ -520,7 +520,12 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
 {
     if (!numViews)
         return;
-    k_cull_views<<<numViews, kCullThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+    // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
+    // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.67 ms; 4096 views 7.0 ms vs 9.2 ms).
+    if (numViews > kCullSmallBatch)
+        k_cull_views<512, 3><<<numViews, 512, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+    else
+        k_cull_views<1024, 1><<<numViews, 1024, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
 }
 
 void cull_prof_enable(int on)

@@ -10,7 +10,7 @@ constexpr int kSetupItems = 64;     // draw items per set-up slice (64 boxes = 7
 constexpr int kSetupThreads = 256;
 constexpr int kSetupQueueBytes = 2 * kSetupThreads * 11 * 4; // survivor queue of k_setup_triangles
 constexpr int kClipEntryFloats = 16;  // clipper queue entry: three clip-space vertices, plane mask, view
-constexpr int kCullThreads = 512;
+constexpr int kCullSmallBatch = 640;  // views per launch up to which the one-CTA-per-SM cull variant is used
 
 // bits of the per-batch device flag word
 constexpr uint32_t kFlagTriOverflow = 1u;   // a view's triangle region was too small
