@@ -16,6 +16,7 @@ namespace u3d
 constexpr int kRing = 2048;             // work-queue entries held in shared memory between evaluation passes
 constexpr int kRingGroups = kRing / 32;
 constexpr int kWStack = 256;            // per-warp texel stack of the cooperative range test
+constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks of >= 512 octants = 4M octants
 constexpr int kHeavyExtent = 32;        // rects larger than this (pixels) are tested by a whole warp
 constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 
@@ -32,6 +33,8 @@ template <int T> struct CullShared
     uint4 heavy[kHeavyCap];           // (left | top << 16, right | bottom << 16, z, queue index | result bits << 30)
     uint32_t heavyCount;
     uint32_t heavyNext;
+    uint32_t bfsBits[kChunkWords];    // chunks (of T entries) of the level-sorted octant list that hold a child of a surviving octant
+    uint32_t dfsBits[kChunkWords];    // chunks of the DFS octant list that hold a surviving octant
     uint32_t ringCount;
     uint32_t nextGroup;
     uint32_t outCursor;
@@ -229,6 +232,21 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
     // ---------------- phase 1: octant states (0 culled, 1 visited, 2 visited with inside == true) ----------------
     // Per level: a sweep queues the octants whose parent survived (dense queue, order irrelevant); warps then pull groups of 32 from
     // the queue and run TestOctant, so the expensive test never runs on mostly-idle warps.
+    // A surviving octant flags the chunk it sits in (phase 2 skips chunks without survivors) and the chunk(s) its children sit in
+    // (the next level's sweep skips chunks without candidates).  Skipped octants keep the 0 their state was cleared to.
+    constexpr int kShift = T == 1024 ? 10 : 9; // log2(T)
+    static_assert((1 << kShift) == T, "chunk size must equal the block size");
+    auto mark_alive = [&](int o) {
+        atomicOr(&sh.dfsBits[o >> (kShift + 5)], 1u << ((o >> kShift) & 31));
+        const int2 ch = sc.octChild[o];
+        if (ch.y)
+        {
+            const int c0 = ch.x >> kShift, c1 = (ch.x + ch.y - 1) >> kShift;
+            atomicOr(&sh.bfsBits[c0 >> 5], 1u << (c0 & 31));
+            if (c1 != c0)
+                atomicOr(&sh.bfsBits[c1 >> 5], 1u << (c1 & 31));
+        }
+    };
     auto eval_octants = [&]() {
         __syncthreads();
         const uint32_t n = sh.ringCount;
@@ -262,14 +280,21 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                 if (!vis)
                     res = OUTSIDE;
             }
-            if (idx < n && !parked)
-                state[o] = res == OUTSIDE ? 0 : (res == INSIDE ? 2 : 1);
+            if (idx < n && !parked && res != OUTSIDE)
+            {
+                state[o] = res == INSIDE ? 2 : 1;
+                mark_alive(o);
+            }
         }
         __syncthreads();
         if (sh.heavyCount)
             visible_stage_b<T>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
                 const int res = (int)(tag >> 30);
-                state[tag & 0x3FFFFFFFu] = !vis ? 0 : (res == INSIDE ? 2 : 1);
+                if (vis)
+                {
+                    state[tag & 0x3FFFFFFFu] = res == INSIDE ? 2 : 1;
+                    mark_alive((int)(tag & 0x3FFFFFFFu));
+                }
             });
         __syncthreads();
         if (tid == 0)
@@ -282,19 +307,32 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
         __syncthreads();
     };
 
+    for (int i = tid; i < kChunkWords; i += T)
+    {
+        sh.bfsBits[i] = 0;
+        sh.dfsBits[i] = 0;
+    }
+    __syncthreads();
     if (tid == 0)
+    {
         state[0] = 1; // the root is never tested (Octree.cpp:231)
+        mark_alive(0);
+    }
     __syncthreads();
     for (int lv = 1; lv < sc.numLevels; ++lv)
     {
         const int a = sc.levelStart[lv], b = sc.levelStart[lv + 1];
+        if (a == b)
+            continue;
         int sweeps = 0;
-        for (int base = a; base < b; base += T)
+        for (int chunk = a >> kShift; chunk <= ((b - 1) >> kShift); ++chunk)
         {
-            const int i = base + tid;
+            if (!((sh.bfsBits[chunk >> 5] >> (chunk & 31)) & 1u))
+                continue; // no surviving octant has a child in this chunk
+            const int i = (chunk << kShift) + tid;
             bool need = false;
             uint32_t e = 0;
-            if (i < b)
+            if (i >= a && i < b)
             {
                 const int o = sc.bfs[i];
                 const unsigned char ps = state[__float_as_int(sc.octMin[o].w)];
@@ -303,8 +341,6 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                     need = true;
                     e = (uint32_t)o | (ps == 2 ? 0x80000000u : 0u);
                 }
-                else
-                    state[o] = 0;
             }
             const uint32_t bal = __ballot_sync(0xffffffffu, need);
             if (bal)
@@ -409,6 +445,8 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
 
     for (int chunk = 0; chunk < sc.numOctants; chunk += T)
     {
+        if (!((sh.dfsBits[chunk >> (kShift + 5)] >> ((chunk >> kShift) & 31)) & 1u))
+            continue; // no surviving octant in this chunk
         // per octant of the chunk: state, drawable count and first drawable (three independent loads), then a scan of the counts
         const int o = chunk + tid;
         uint32_t cnt = 0, firstWord = 0;
@@ -520,6 +558,7 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
 {
     if (!numViews)
         return;
+    cudaMemsetAsync(octState, 0, (size_t)numViews * sc.numOctants, s); // octants the sweeps skip must read as culled
     // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
     // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.67 ms; 4096 views 7.0 ms vs 9.2 ms).
     if (numViews > kCullSmallBatch)
