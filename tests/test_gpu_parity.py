@@ -353,3 +353,75 @@ def test_garbage_geometry_does_not_crash_and_matches(gpu_ctx):
     for o in (gob, batch, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+def test_config5_city_mesh_2048(gpu_ctx):
+    """BASELINE config 5 shape: one 250k-triangle u32-indexed mesh (12-byte stride) into a 2048x2048 buffer (8 hierarchy levels: the last
+    two come from the generic level kernel, 256 tiles, CTA-class triangles) and an occluded query over 400k boxes, 1 view.
+    (4M boxes are exercised by the bench-size run in profiles/; the oracle side of this test is what bounds the size here.)"""
+    w = h = 2048
+    vtx, idx = scenes.city_mesh(250_000, 500.0)
+    sc = scenes.Scene(400_000, 4, 500.0, seed=55)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, vtx, 12, idx)
+    ident = np.array([[1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0]], np.float32)
+    occ = capi.Occluders(gpu_ctx, np.array([[-500, 0, -500, 500, 40, 500]], np.float32), ident, [mesh], cull_mode=capi.CULL_CCW)
+    v = camera.make_view([20.0, 30.0, -480.0], 10.0, 12.0, 50.0, 1.0, 0.5, 1200.0)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, 1, sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views([v]), capi.STAGE_VISIBLE)
+    ob.set_view(v)
+    ob.set_max_triangles(1 << 30)
+    ob.clear()
+    ob.set_cull_mode(capi.CULL_CCW)
+    ob.draw_batch(ident[0], vtx, 12, idx, 0, idx.shape[0])
+    ob.build_hierarchy()
+    assert np.array_equal(batch.depth(0), ob.depth())
+    gm, om = batch.mips(0), ob.mips()
+    assert len(gm) == len(om) == 8
+    for a, b in zip(gm, om):
+        assert np.array_equal(a, b)
+    assert batch.tri_stats()[0, 1] == ob.num_triangles()
+    cand = otree.query(1, v.planes, ob, as_ids=False)
+    vis = otree.order[otree.check_visibility(ob, cand)]
+    assert counts[0, 0] == len(cand) and np.array_equal(ids[offsets[0]:offsets[1]], vis)
+    assert 0 < len(vis) <= len(cand) < sc.n
+    # the drop-in object draws the same mesh through AddTriangles / DrawTriangles (general path) and must agree as well
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    gob.SetSize(w, h)
+    gob.SetView(v)
+    gob.SetMaxTriangles(1 << 30)
+    gob.Clear()
+    gob.SetCullMode(capi.CULL_CCW)
+    gob.AddTriangles(ident[0], vtx, 12, idx, 0, idx.shape[0])
+    gob.DrawTriangles()
+    gob.BuildDepthHierarchy()
+    assert np.array_equal(gob.GetBuffer(), ob.depth())
+    assert gob.GetNumTriangles() == ob.num_triangles()
+    for a, b in zip(gob.GetMips(), om):
+        assert np.array_equal(a, b)
+    for o in (gob, batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+def test_config4_two_million_shadow_views(gpu_ctx):
+    """BASELINE config 4: 4 ortho cascades + 64 point lights x 6 faces = 388 frustum-only ShadowCasterOctreeQuery views over 2M drawables.
+    All 388 run on the GPU; a sample of them is checked against the oracle sequence, the rest by count against the plain frustum query."""
+    cfg = scenes.CONFIGS["C4"]
+    sc = scenes.Scene(cfg["n"], 4, cfg["extent"], seed=4)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, _ = helpers.make_oracle(sc, flat, 8, 8)
+    views = scenes.shadow_views(cfg["extent"], n_point_lights=64)
+    assert len(views) == 388
+    batch = capi.Batch(gpu_ctx, gs, None, 0, 0, len(views), sc.n)  # the 1000-unit cascade sees most of the scene
+    batch.set_views(capi.pack_views(views, query_mode=capi.QUERY_SHADOWCASTER, use_occlusion=False))
+    batch.run(capi.STAGE_VISIBLE)
+    counts = batch.counts()
+    offsets, ids = batch.packed(capacity=int(counts[:, 1].sum()))
+    for i in list(range(0, 8)) + list(range(8, 388, 37)):
+        want = otree.query(2, views[i].planes, None)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], want), "view %d" % i
+    assert counts[:, 1].sum() == offsets[-1] and counts[:4, 1].min() > 0
+    for o in (batch, gs, tree):
+        o.close()
