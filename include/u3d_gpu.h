@@ -49,7 +49,10 @@ enum
 enum
 {
     U3D_STAGE_QUERY = 0,    /* Octree::GetDrawables result_ (Octree.cpp:495-499), DFS order */
-    U3D_STAGE_VISIBLE = 1   /* ... filtered by CheckVisibilityWork's predicate !occludee || IsVisible(box) (View.cpp:177), same order */
+    U3D_STAGE_VISIBLE = 1,  /* ... filtered by CheckVisibilityWork's predicate !occludee || IsVisible(box) (View.cpp:177), same order */
+    U3D_STAGE_INVIEW = 2    /* ... and by the draw-distance test (View.cpp:179-186, Drawable::UpdateBatches distance Drawable.cpp:134-137,
+                               Camera::GetDistance Camera.cpp:487-496); also reduces the view-space Z range of the geometries that stay
+                               (View.cpp:198-211, 926-951): read it with u3d_batch_read_z_ranges */
 };
 
 typedef struct u3d_ctx u3d_ctx;             /* one per GPU */
@@ -73,6 +76,8 @@ typedef struct u3d_view
     int32_t reverse_culling; /* Camera::GetReverseCulling() */
     int32_t query_mode;      /* U3D_QUERY_* */
     int32_t use_occlusion;   /* 0: no occlusion buffer for this view (frustum-only query; predicate passes everything) */
+    int32_t orthographic;    /* Camera::IsOrthographic(): selects the distance formula of Camera::GetDistance (U3D_STAGE_INVIEW only) */
+    float camera_position[3];/* Camera node world position, used by Camera::GetDistance for perspective cameras (U3D_STAGE_INVIEW only) */
     int32_t reserved;
 } u3d_view;
 
@@ -98,6 +103,8 @@ U3D_API void u3d_octree_destroy(u3d_octree* t);
 U3D_API int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask,
     const uint8_t* occludee, const uint8_t* cast_shadows, uint32_t* first_id);
 /* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472). */
+/* Drawable::SetDrawDistance for n drawables starting at first_id (0 = unlimited, the default; used by U3D_STAGE_INVIEW). */
+U3D_API int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, const float* draw_distance);
 U3D_API int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6]);
 /* Octree::RemoveDrawable path (Octree.h:66-74, DecDrawableCount :123-136). */
 U3D_API int u3d_octree_remove(u3d_octree* t, uint32_t id);
@@ -114,6 +121,8 @@ U3D_API int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
 U3D_API int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t num_octants, const int32_t* parent, const int32_t* level, const float* culling_box6,
     const int32_t* first, const int32_t* count, uint32_t num_slots, const int32_t* order, const float* aabb6, const uint8_t* drawable_flags,
     const uint32_t* view_mask, const uint8_t* occludee, const uint8_t* cast_shadows, u3d_scene** out);
+/* Per-drawable draw distances (indexed by drawable id, 0 = unlimited) for a scene made with u3d_scene_create_flat. */
+U3D_API int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_distance);
 U3D_API void u3d_scene_destroy(u3d_scene* s);
 U3D_API int u3d_scene_counts(const u3d_scene* s, uint32_t* num_octants, uint32_t* num_drawables);
 
@@ -193,6 +202,8 @@ U3D_API int u3d_batch_run_timed(u3d_batch* b, int stage, void* stream, float* ph
 U3D_API int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream);
 /* Emitted ids of every view packed back to back; offsets has n+1 entries.  capacity in ids.  Synchronises. */
 U3D_API int u3d_batch_read_packed(u3d_batch* b, uint32_t* offsets, uint32_t* ids, uint64_t capacity, void* stream);
+/* After a run with U3D_STAGE_INVIEW: n x 2 floats (minZ, maxZ) = View::minZ_/maxZ_ of every view (View.cpp:926-951). */
+U3D_API int u3d_batch_read_z_ranges(u3d_batch* b, float* minmax, void* stream);
 U3D_API int u3d_batch_read_view(u3d_batch* b, uint32_t view, uint32_t* ids, uint32_t capacity, uint32_t* count, void* stream);
 U3D_API int u3d_batch_read_depth(u3d_batch* b, uint32_t view, int32_t* out_depth, void* stream);
 U3D_API int u3d_batch_read_mip(u3d_batch* b, uint32_t view, int level, int32_t* out_minmax, void* stream);

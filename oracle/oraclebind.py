@@ -59,6 +59,7 @@ def lib():
         L.orc_frustum_test.argtypes = [_f, _f, C.c_int]
         L.orc_query.argtypes = [C.POINTER(_Tree), C.c_int, _f, C.c_void_p, C.c_uint, C.c_uint, _i]
         L.orc_check_visibility.argtypes = [C.POINTER(_Tree), C.c_void_p, _i, C.c_int, _i]
+        L.orc_check_in_view.argtypes = [C.POINTER(_Tree), C.c_void_p, _f, _f, C.c_int, _f, _i, C.c_int, _i, _f]
         _lib = L
     return _lib
 
@@ -195,3 +196,15 @@ class OracleTree:
         out = np.zeros(max(len(cand), 1), np.int32)
         n = lib().orc_check_visibility(C.byref(self.t), ob.h if ob is not None else None, _p(cand, _i), len(cand), _p(out, _i))
         return out[:n].copy()
+
+    def check_in_view(self, ob, cand_pos, view, cam_pos, ortho=False, draw_dist=None):
+        """View.cpp:177-211.  draw_dist is per drawable id (original order).  Returns (DFS positions in view, (minZ, maxZ))."""
+        cand = np.ascontiguousarray(cand_pos, dtype=np.int32)
+        out = np.zeros(max(len(cand), 1), np.int32)
+        mm = np.zeros(2, np.float32)
+        v12 = np.ascontiguousarray(view, dtype=np.float32)
+        cp = np.ascontiguousarray(cam_pos, dtype=np.float32)
+        dd = None if draw_dist is None else np.ascontiguousarray(np.asarray(draw_dist, np.float32)[self.order])
+        n = lib().orc_check_in_view(C.byref(self.t), ob.h if ob is not None else None, _p(v12, _f), _p(cp, _f), int(ortho), _p(dd, _f), _p(cand, _i),
+                                    len(cand), _p(out, _i), _p(mm, _f))
+        return out[:n].copy(), mm

@@ -480,6 +480,58 @@ int ref_check_visibility(void* h, int useBuffer, int* outIdx, int cap)
     return m;
 }
 
+/// The part of CheckVisibilityWork (View.cpp:160-227) that decides what is in view and the Z range, over the last ref_query() result, one
+/// thread, with the reference's own math types.  The view matrix and camera position are injected (the harness runs without a Camera node
+/// in raw mode): distance = Camera::GetDistance (Camera.cpp:487-496) evaluated on those values.  Returns the number in view.
+int ref_check_in_view(void* h, int useBuffer, const float* view12, const float* camPos3, int ortho, const float* drawDistance /* by id */,
+    int* outIdx, int cap, float* minmax2)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    OcclusionBuffer* buffer = useBuffer ? r->buffer_.Get() : nullptr;
+    Matrix3x4 viewMatrix(view12);
+    Vector3 cameraPos(camPos3);
+    Vector3 viewZ = Vector3(viewMatrix.m20_, viewMatrix.m21_, viewMatrix.m22_);
+    Vector3 absViewZ = viewZ.Abs();
+    float minZ = M_INFINITY, maxZ = 0.0f;
+    int m = 0;
+    for (unsigned i = 0; i < r->result_.Size(); ++i)
+    {
+        auto* drawable = static_cast<TestDrawable*>(r->result_[i]);
+        if (!buffer || !drawable->IsOccludee() || buffer->IsVisible(drawable->GetWorldBoundingBox()))
+        {
+            const BoundingBox& geomBox = drawable->GetWorldBoundingBox();
+            float maxDistance = drawDistance ? drawDistance[drawable->id_] : 0.0f;
+            if (maxDistance > 0.0f)
+            {
+                Vector3 worldPos = geomBox.Center();
+                float distance = !ortho ? (worldPos - cameraPos).Length() : Abs((viewMatrix * worldPos).z_);
+                if (distance > maxDistance)
+                    continue;
+            }
+            if (drawable->GetDrawableFlags() & DRAWABLE_GEOMETRY)
+            {
+                Vector3 center = geomBox.Center();
+                Vector3 edge = geomBox.Size() * 0.5f;
+                if (edge.LengthSquared() < M_LARGE_VALUE * M_LARGE_VALUE)
+                {
+                    float viewCenterZ = viewZ.DotProduct(center) + viewMatrix.m23_;
+                    float viewEdgeZ = absViewZ.DotProduct(edge);
+                    minZ = Min(minZ, viewCenterZ - viewEdgeZ);
+                    maxZ = Max(maxZ, viewCenterZ + viewEdgeZ);
+                }
+            }
+            if (m < cap)
+                outIdx[m] = drawable->id_;
+            ++m;
+        }
+    }
+    if (minZ == M_INFINITY)
+        minZ = 0.0f;
+    minmax2[0] = minZ;
+    minmax2[1] = maxZ;
+    return m;
+}
+
 /// One whole view, the way View::GetDrawables runs it with threaded occlusion (View.cpp:2258-2273, :873-878, :885-921):
 /// select occluders by frustum.IsInsideFast(worldBox) in scene order, Clear, AddTriangles each,
 /// DrawTriangles, BuildDepthHierarchy, occluded query, visibility predicate.  Camera must be set already.

@@ -64,6 +64,7 @@ class Ref:
         L.ref_run_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int,
                                    C.c_uint, C.c_uint, _i, C.c_int, _i, C.POINTER(C.c_double)]
         L.ref_num_threads.argtypes = [C.c_void_p]
+        L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
         self.h = L.ref_create(int(worker_threads))
         self._keep = []
         self.n = 0
@@ -220,6 +221,16 @@ class Ref:
                                   scene.cull_mode, flags, view_mask, _p(out, _i), out.shape[0], _p(counts, _i),
                                   times.ctypes.data_as(C.POINTER(C.c_double)))
         return out[:n].copy(), counts, times
+
+    def check_in_view(self, view, cam_pos, ortho=False, draw_dist=None, use_buffer=True):
+        """View.cpp:177-211 over the last query() result.  Returns (ids in view, (minZ, maxZ))."""
+        out = np.zeros(max(self.n, 1), np.int32)
+        mm = np.zeros(2, np.float32)
+        v12 = np.ascontiguousarray(view, dtype=np.float32)
+        cp = np.ascontiguousarray(cam_pos, dtype=np.float32)
+        dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, dtype=np.float32)
+        n = self.lib.ref_check_in_view(self.h, int(use_buffer), _p(v12, _f), _p(cp, _f), int(ortho), _p(dd, _f), _p(out, _i), out.shape[0], _p(mm, _f))
+        return out[:n].copy(), mm
 
     def num_threads(self):
         return self.lib.ref_num_threads(self.h)

@@ -712,3 +712,56 @@ int orc_check_visibility(const OrcTree* t, const OrcOB* ob, const int* cand, int
     }
     return n;
 }
+
+/* The rest of CheckVisibilityWork that decides what is "in view" (View.cpp:177-211): occlusion predicate, draw-distance test on
+ * Drawable::UpdateBatches' distance (Drawable.cpp:134-137, Camera::GetDistance Camera.cpp:487-496), and the view-space Z range of the
+ * geometries that stay, merged as View::GetDrawables does (View.cpp:893-894, 926-951).  draw_dist is in DFS order (NULL = all 0).
+ * The orthographic distance follows the operation order of the reference's default URHO3D_SSE build of Matrix3x4 * Vector3
+ * (Matrix3x4.h:256-274): (m20*x + m22*z) + (m21*y + m23). */
+int orc_check_in_view(const OrcTree* t, const OrcOB* ob, const float* view12, const float* cam_pos3, int ortho, const float* draw_dist,
+    const int* cand, int ncand, int* out, float* minmax2)
+{
+    int n = 0;
+    float min_z = (float)HUGE_VAL, max_z = 0.0f;
+    const float vz0 = view12[8], vz1 = view12[9], vz2 = view12[10], vz3 = view12[11];
+    for (int i = 0; i < ncand; ++i)
+    {
+        int d = cand[i];
+        const float* b = t->aabb6 + 6 * (size_t)d;
+        if (!(!ob || !t->occludee[d] || orc_ob_is_visible(ob, b)))
+            continue;
+        float cx = (b[3] + b[0]) * 0.5f, cy = (b[4] + b[1]) * 0.5f, cz = (b[5] + b[2]) * 0.5f;
+        float max_distance = draw_dist ? draw_dist[d] : 0.0f;
+        if (max_distance > 0.0f)
+        {
+            float dist;
+            if (!ortho)
+            {
+                float dx = cx - cam_pos3[0], dy = cy - cam_pos3[1], dz = cz - cam_pos3[2];
+                dist = sqrtf(dx * dx + dy * dy + dz * dz);
+            }
+            else
+                dist = fabsf((vz0 * cx + vz2 * cz) + (vz1 * cy + vz3));
+            if (dist > max_distance)
+                continue;
+        }
+        if (t->flags[d] & 1) /* DRAWABLE_GEOMETRY */
+        {
+            float ex = (b[3] - b[0]) * 0.5f, ey = (b[4] - b[1]) * 0.5f, ez = (b[5] - b[2]) * 0.5f;
+            if (ex * ex + ey * ey + ez * ez < 100000000.0f * 100000000.0f)
+            {
+                float vc = vz0 * cx + vz1 * cy + vz2 * cz + vz3;
+                float ve = fabsf(vz0) * ex + fabsf(vz1) * ey + fabsf(vz2) * ez;
+                float lo = vc - ve, hi = vc + ve;
+                min_z = lo < min_z ? lo : min_z;
+                max_z = hi > max_z ? hi : max_z;
+            }
+        }
+        out[n++] = d;
+    }
+    if (min_z == (float)HUGE_VAL)
+        min_z = 0.0f;
+    minmax2[0] = min_z;
+    minmax2[1] = max_z;
+    return n;
+}

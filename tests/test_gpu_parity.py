@@ -425,3 +425,43 @@ def test_config4_two_million_shadow_views(gpu_ctx):
     assert counts[:, 1].sum() == offsets[-1] and counts[:4, 1].min() > 0
     for o in (batch, gs, tree):
         o.close()
+
+
+@pytest.mark.parametrize("ortho,occl", [(False, True), (True, True), (False, False)])
+def test_in_view_stage(gpu_ctx, ortho, occl):
+    """U3D_STAGE_INVIEW: occlusion predicate + draw-distance test + per-view Z range (View.cpp:177-211, 926-951), batched."""
+    w, h = 256, 160
+    sc = helpers.small_scene(n=9000, k=128, extent=90.0, seed=23)
+    rs = np.random.RandomState(6)
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.5, rs.uniform(5.0, 150.0, size=sc.n), 0.0).astype(np.float32)
+    sc.flags[::9] = 0x2
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    tree.set_draw_distances(draw_dist)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = []
+    for i in range(10):
+        pos = [rs.uniform(-60, 60), rs.uniform(5, 30) if ortho else 2.0, rs.uniform(-60, 60)]
+        views.append(camera.make_view(pos, rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), 45.0, w / h, 0.1, 300.0,
+                                      ortho=ortho, ortho_size=rs.uniform(20, 100)))
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    mode = capi.QUERY_OCCLUDED if occl else capi.QUERY_FRUSTUM
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views, query_mode=mode, use_occlusion=occl), capi.STAGE_INVIEW)
+    zr = batch.z_ranges()
+    dropped = 0
+    for i, v in enumerate(views):
+        ob.draw_scene_view(sc, v)
+        cand = otree.query(1 if occl else 0, v.planes, ob if occl else None, as_ids=False)
+        pos_in, mm = otree.check_in_view(ob if occl else None, cand, v.view, v.position, ortho, draw_dist)
+        assert counts[i, 0] == len(cand)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.order[pos_in]), "view %d" % i
+        assert np.array_equal(zr[i], mm), (i, zr[i], mm)
+        dropped += len(otree.check_visibility(ob if occl else None, cand)) - len(pos_in)
+    assert dropped > 0  # the draw-distance test really removed something
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

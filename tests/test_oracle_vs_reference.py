@@ -107,3 +107,31 @@ def test_non_indexed_and_u32_indices_and_cull_modes():
             assert np.array_equal(ob.depth(), ref.ob_depth())
             assert ob.num_triangles() == ref.ob_num_triangles()
     v.reverse_culling = False
+
+
+@pytest.mark.parametrize("ortho", [False, True])
+def test_in_view_stage_matches_reference(ortho):
+    """Rest of CheckVisibilityWork (View.cpp:177-211): draw distance + view-space Z range, oracle vs the reference's own math types."""
+    from urho3d_b200 import camera
+    w, h = 128, 80
+    sc = helpers.small_scene(n=4000, k=96, extent=80.0, seed=17)
+    rs = np.random.RandomState(5)
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.5, rs.uniform(5.0, 120.0, size=sc.n), 0.0).astype(np.float32)
+    sc.flags[::9] = 0x2  # lights: in view, but not part of the Z range
+    ref = helpers.make_ref(sc, w, h)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    for i in range(8):
+        pos = [rs.uniform(-60, 60), rs.uniform(1, 30) if ortho else 2.0, rs.uniform(-60, 60)]
+        v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), 45.0, w / h, 0.1, 300.0,
+                             ortho=ortho, ortho_size=rs.uniform(20, 100))
+        helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        want_ids, want_mm = ref.check_in_view(v.view, v.position, ortho, draw_dist)
+        got_pos, got_mm = tree.check_in_view(ob, cand, v.view, v.position, ortho, draw_dist)
+        assert np.array_equal(tree.order[got_pos], want_ids)
+        assert np.array_equal(got_mm, want_mm), (got_mm, want_mm)
+        assert len(want_ids) <= len(tree.check_visibility(ob, cand))
+    ref.close()
+    ob.close()

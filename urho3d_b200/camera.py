@@ -128,13 +128,15 @@ def frustum_planes(fov_deg, aspect, near, far, xform, ortho=False, ortho_size=20
 class CameraView:
     """Per-view inputs: view (3x4), projection (4x4), frustum planes (6x4), near/far, reverseCulling."""
 
-    def __init__(self, view, proj, planes, near, far, reverse_culling=False):
+    def __init__(self, view, proj, planes, near, far, reverse_culling=False, position=(0.0, 0.0, 0.0), ortho=False):
         self.view = np.ascontiguousarray(view, dtype=f32)
         self.proj = np.ascontiguousarray(proj, dtype=f32)
         self.planes = np.ascontiguousarray(planes, dtype=f32)
         self.near = float(near)
         self.far = float(far)
         self.reverse_culling = bool(reverse_culling)
+        self.position = np.ascontiguousarray(position, dtype=f32)  # camera node world position (Camera::GetDistance)
+        self.ortho = bool(ortho)
 
 
 def make_view(pos, yaw_deg, pitch_deg, fov_deg, aspect, near, far, ortho=False, ortho_size=20.0, zoom=1.0):
@@ -143,7 +145,7 @@ def make_view(pos, yaw_deg, pitch_deg, fov_deg, aspect, near, far, ortho=False, 
     if ortho:
         near = 0.0  # Camera::GetNearClip() reports projNearClip_, which stays 0 for orthographic cameras (Camera.cpp:676-678)
     return CameraView(inverse_rigid(xf), projection(fov_deg, aspect, near, far, ortho, ortho_size, zoom),
-                      frustum_planes(fov_deg, aspect, near, far, xf, ortho, ortho_size, zoom), near, far)
+                      frustum_planes(fov_deg, aspect, near, far, xf, ortho, ortho_size, zoom), near, far, position=pos, ortho=ortho)
 
 
 def view_proj(proj, view):

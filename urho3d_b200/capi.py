@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libu3dgpu.so")
 
 QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER = 0, 1, 2
-STAGE_QUERY, STAGE_VISIBLE = 0, 1
+STAGE_QUERY, STAGE_VISIBLE, STAGE_INVIEW = 0, 1, 2
 CULL_NONE, CULL_CCW, CULL_CW = 0, 1, 2
 ERR_CAPACITY = 4
 
@@ -26,13 +26,15 @@ class U3DView(C.Structure):
     """struct u3d_view of include/u3d_gpu.h."""
     _fields_ = [("view", C.c_float * 12), ("projection", C.c_float * 16), ("planes", C.c_float * 24), ("near_clip", C.c_float),
                 ("far_clip", C.c_float), ("drawable_flags", C.c_uint32), ("view_mask", C.c_uint32), ("reverse_culling", C.c_int32),
-                ("query_mode", C.c_int32), ("use_occlusion", C.c_int32), ("reserved", C.c_int32)]
+                ("query_mode", C.c_int32), ("use_occlusion", C.c_int32), ("orthographic", C.c_int32), ("camera_position", C.c_float * 3),
+                ("reserved", C.c_int32)]
 
 
 VIEW_DTYPE = np.dtype([("view", np.float32, 12), ("projection", np.float32, 16), ("planes", np.float32, 24), ("near_clip", np.float32),
                        ("far_clip", np.float32), ("drawable_flags", np.uint32), ("view_mask", np.uint32), ("reverse_culling", np.int32),
-                       ("query_mode", np.int32), ("use_occlusion", np.int32), ("reserved", np.int32)])
-assert VIEW_DTYPE.itemsize == C.sizeof(U3DView) == 240
+                       ("query_mode", np.int32), ("use_occlusion", np.int32), ("orthographic", np.int32), ("camera_position", np.float32, 3),
+                       ("reserved", np.int32)])
+assert VIEW_DTYPE.itemsize == C.sizeof(U3DView) == 256
 
 # name -> (restype, argtypes); the list doubles as the symbol inventory checked by tests/test_capi_symbols.py
 SIGNATURES = {
@@ -47,12 +49,14 @@ SIGNATURES = {
     "u3d_octree_create": (C.c_int, [_f, _f, C.c_uint32, C.POINTER(_vp)]),
     "u3d_octree_destroy": (None, [_vp]),
     "u3d_octree_add": (C.c_int, [_vp, C.c_uint32, _f, _u8, _u32, _u8, _u8, _u32]),
+    "u3d_octree_set_draw_distances": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _f]),
     "u3d_octree_update": (C.c_int, [_vp, C.c_uint32, _f]),
     "u3d_octree_remove": (C.c_int, [_vp, C.c_uint32]),
     "u3d_octree_counts": (C.c_int, [_vp, _u32, _u32]),
     "u3d_octree_flatten": (C.c_int, [_vp, _i32, _i32, _f, _i32, _i32, _i32]),
     "u3d_scene_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "u3d_scene_create_flat": (C.c_int, [_vp, C.c_uint32, _i32, _i32, _f, _i32, _i32, C.c_uint32, _i32, _f, _u8, _u32, _u8, _u8, C.POINTER(_vp)]),
+    "u3d_scene_set_draw_distances": (C.c_int, [_vp, C.c_uint32, _f]),
     "u3d_scene_destroy": (None, [_vp]),
     "u3d_scene_counts": (C.c_int, [_vp, _u32, _u32]),
     "u3d_mesh_create": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
@@ -94,6 +98,7 @@ SIGNATURES = {
     "u3d_batch_run_timed": (C.c_int, [_vp, C.c_int, _vp, _f]),
     "u3d_batch_read_counts": (C.c_int, [_vp, _u32, _vp]),
     "u3d_batch_read_packed": (C.c_int, [_vp, _u32, _u32, C.c_uint64, _vp]),
+    "u3d_batch_read_z_ranges": (C.c_int, [_vp, _f, _vp]),
     "u3d_batch_read_view": (C.c_int, [_vp, C.c_uint32, _u32, C.c_uint32, _u32, _vp]),
     "u3d_batch_read_depth": (C.c_int, [_vp, C.c_uint32, _i32, _vp]),
     "u3d_batch_read_mip": (C.c_int, [_vp, C.c_uint32, C.c_int, _i32, _vp]),
@@ -190,6 +195,10 @@ class Octree:
         a = _arr(aabb6, np.float32)
         _chk(lib().u3d_octree_update(self.h, idx, _p(a, _f)))
 
+    def set_draw_distances(self, draw_distance, first_id=0):
+        d = _arr(draw_distance, np.float32)
+        _chk(lib().u3d_octree_set_draw_distances(self.h, first_id, d.shape[0], _p(d, _f)))
+
     def remove(self, idx):
         _chk(lib().u3d_octree_remove(self.h, idx))
 
@@ -227,6 +236,10 @@ class GpuScene:
         m, n = C.c_uint32(), C.c_uint32()
         _chk(lib().u3d_scene_counts(self.h, C.byref(m), C.byref(n)))
         self.num_octants, self.num_drawables = m.value, n.value
+
+    def set_draw_distances(self, draw_distance):
+        d = _arr(draw_distance, np.float32)
+        _chk(lib().u3d_scene_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
 
     def query(self, planes, ob=None, flags=0xFF, view_mask=0xFFFFFFFF, mode=QUERY_FRUSTUM, stage=STAGE_QUERY, capacity=None):
         """Octree::GetDrawables with a frustum-type query (+ optional visibility predicate).  Returns (ids, query_count)."""
@@ -391,6 +404,8 @@ def pack_views(views, flags=0xFF, view_mask=0xFFFFFFFF, query_mode=QUERY_OCCLUDE
         out[i]["near_clip"] = v.near
         out[i]["far_clip"] = v.far
         out[i]["reverse_culling"] = int(v.reverse_culling)
+        out[i]["orthographic"] = int(getattr(v, "ortho", False))
+        out[i]["camera_position"] = getattr(v, "position", np.zeros(3, np.float32))
     out["drawable_flags"] = flags
     out["view_mask"] = view_mask
     out["query_mode"] = query_mode
@@ -451,6 +466,12 @@ class Batch:
         _chk(lib().u3d_batch_cull_views(self.h, packed.ctypes.data, self.n, stage, _p(counts, _u32), _p(offsets, _u32), _p(ids, _u32), ids.shape[0],
                                         stream))
         return counts, offsets, ids
+
+    def z_ranges(self, stream=None):
+        """(minZ, maxZ) per view after a STAGE_INVIEW run (View::minZ_/maxZ_)."""
+        out = np.zeros((self.n, 2), np.float32)
+        _chk(lib().u3d_batch_read_z_ranges(self.h, _p(out, _f), stream))
+        return out
 
     def view_ids(self, view, stream=None):
         out = np.zeros(max(self.out_capacity, 1), np.uint32)

@@ -158,6 +158,8 @@ struct u3d_scene
     DevBuf<int> octCount, bfs, levelStart;
     DevBuf<int2> octChild;
     DevBuf<uint32_t> drwId;
+    DevBuf<float> drwDrawDist;       // per DFS slot, 0 = unlimited
+    std::vector<uint32_t> slotOfId;  // drawable id -> DFS slot (for late per-drawable uploads)
 };
 
 struct u3d_mesh
@@ -312,6 +314,7 @@ struct u3d_batch
     uint64_t poolTris{};
     DevBuf<unsigned char> octState;
     DevBuf<uint32_t> outIdx, outCounts, packOffsets, packed;
+    DevBuf<float> zRange; // per view (minZ, maxZ)
     PinnedBuf<ViewConst> hostViews;
     PinnedBuf<uint32_t> hostCounts;
     uint32_t lastLaunches{};
@@ -441,6 +444,15 @@ int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t*
             occludee ? occludee[i] != 0 : true, cast_shadows ? cast_shadows[i] != 0 : false);
     if (first_id)
         *first_id = first;
+    return U3D_OK;
+}
+
+int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, const float* draw_distance)
+{
+    if (!t || (n && !draw_distance))
+        return fail(U3D_ERR_INVALID, "u3d_octree_set_draw_distances: NULL argument");
+    if (!t->tree.SetDrawDistances(first_id, n, draw_distance))
+        return fail(U3D_ERR_INVALID, "u3d_octree_set_draw_distances: drawable id out of range");
     return U3D_OK;
 }
 
@@ -593,6 +605,23 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
     s->dev.drwMin = s->drwMin.p;
     s->dev.drwMax = s->drwMax.p;
     s->dev.drwId = s->drwId.p;
+    {
+        cudaError_t e2 = s->drwDrawDist.ensure(std::max<uint32_t>(S, 1));
+        if (e2 == cudaSuccess)
+            e2 = cudaMemset(s->drwDrawDist.p, 0, (size_t)std::max<uint32_t>(S, 1) * 4);
+        if (e2 != cudaSuccess)
+        {
+            delete s;
+            return fail(U3D_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e2));
+        }
+        s->dev.drwDrawDist = s->drwDrawDist.p;
+        uint32_t maxId = 0;
+        for (uint32_t i = 0; i < S; ++i)
+            maxId = std::max(maxId, ids[i]);
+        s->slotOfId.assign(S ? maxId + 1 : 0, 0xFFFFFFFFu);
+        for (uint32_t i = 0; i < S; ++i)
+            s->slotOfId[ids[i]] = i;
+    }
     *out = s;
     return U3D_OK;
 }
@@ -616,8 +645,32 @@ int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
         oc[i] = dr[i].occludee;
         cs[i] = dr[i].castShadows;
     }
-    return u3d_scene_create_flat(ctx, (uint32_t)f.parent.size(), f.parent.data(), f.level.data(), f.box6.data(), f.first.data(), f.count.data(),
+    int rc = u3d_scene_create_flat(ctx, (uint32_t)f.parent.size(), f.parent.data(), f.level.data(), f.box6.data(), f.first.data(), f.count.data(),
         (uint32_t)f.order.size(), f.order.data(), aabb.data(), fl.data(), vm.data(), oc.data(), cs.data(), out);
+    if (rc < 0)
+        return rc;
+    std::vector<float> dd(std::max<size_t>(n, 1), 0.0f);
+    bool any = false;
+    for (size_t i = 0; i < n; ++i)
+    {
+        dd[i] = dr[i].drawDistance;
+        any |= dd[i] != 0.0f;
+    }
+    return any ? u3d_scene_set_draw_distances(*out, (uint32_t)n, dd.data()) : U3D_OK;
+}
+
+int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_distance)
+{
+    if (!s || (n && !draw_distance))
+        return fail(U3D_ERR_INVALID, "u3d_scene_set_draw_distances: NULL argument");
+    CU_CHECK(cudaSetDevice(s->ctx->device));
+    const uint32_t S = (uint32_t)s->dev.numDrawables;
+    std::vector<float> bySlot(std::max<uint32_t>(S, 1), 0.0f);
+    for (uint32_t id = 0; id < n && id < s->slotOfId.size(); ++id)
+        if (s->slotOfId[id] != 0xFFFFFFFFu)
+            bySlot[s->slotOfId[id]] = draw_distance[id];
+    CU_CHECK(cudaMemcpy(s->drwDrawDist.p, bySlot.data(), (size_t)std::max<uint32_t>(S, 1) * 4, cudaMemcpyHostToDevice));
+    return U3D_OK;
 }
 
 void u3d_scene_destroy(u3d_scene* s)
@@ -1215,7 +1268,7 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
     CU_CHECK(cudaMemcpyAsync(holder->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(holder->vs.flags.p, 0, 4, st));
     launch_cull(scene->dev, g, holder->vs.views.p, 1, useOb ? ob->vs.depth.p : nullptr, useOb ? ob->vs.mips.p : nullptr,
-        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, holder->vs.flags.p, st);
+        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr, holder->vs.flags.p, st);
     CU_CHECK(cudaGetLastError());
     uint32_t counts[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(counts, holder->outCounts.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1282,7 +1335,7 @@ int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, i
         // ViewSet::alloc sized views for `nviews`; frustum-only batches still need max_views view constants
         if ((e = b->vs.views.ensure(max_views)) || (e = b->octState.ensure((size_t)max_views * scene->dev.numOctants)) ||
             (e = b->outIdx.ensure((size_t)max_views * std::max<uint32_t>(out_capacity, 1))) || (e = b->outCounts.ensure((size_t)max_views * 2)) ||
-            (e = b->packOffsets.ensure((size_t)max_views + 1)) || (e = b->hostViews.ensure(max_views)) || (e = b->hostCounts.ensure((size_t)max_views * 2 + 2)))
+            (e = b->packOffsets.ensure((size_t)max_views + 1)) || (e = b->zRange.ensure((size_t)max_views * 2)) || (e = b->hostViews.ensure(max_views)) || (e = b->hostCounts.ensure((size_t)max_views * 2 + 2)))
             rc = fail(U3D_ERR_CUDA, std::string("u3d_batch_create: ") + cudaGetErrorString(e));
     }
     if (rc < 0)
@@ -1326,7 +1379,15 @@ int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* s
         vc.useOcclusion = (v.use_occlusion && b->hasBuffers) ? 1 : 0;
         if (vc.queryMode == QUERY_OCCLUDED && !vc.useOcclusion)
             vc.queryMode = QUERY_FRUSTUM; // View.cpp:873-883: without a buffer the plain frustum query is used
-        vc.pad[0] = vc.pad[1] = vc.pad[2] = 0;
+        vc.ortho = v.orthographic != 0;
+        vc.viewZ[0] = v.view[8];
+        vc.viewZ[1] = v.view[9];
+        vc.viewZ[2] = v.view[10];
+        vc.viewZ[3] = v.view[11];
+        vc.camPos[0] = v.camera_position[0];
+        vc.camPos[1] = v.camera_position[1];
+        vc.camPos[2] = v.camera_position[2];
+        vc.pad = 0;
     }
     b->numViews = n;
     if (n)
@@ -1336,7 +1397,7 @@ int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* s
 
 int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
 {
-    if (!b || stage < 0 || stage > 1 || part < 0 || part > 2)
+    if (!b || stage < 0 || stage > 2 || part < 0 || part > 2)
         return fail(U3D_ERR_INVALID, "u3d_batch_run: bad argument");
     CU_CHECK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->pick(stream);
@@ -1403,7 +1464,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
     CU_CHECK(mark(6));
     if (part != 1)
     {
-        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, vs.flags.p, st);
+        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p, vs.flags.p, st);
         b->lastLaunches += 1;
         CU_CHECK(cudaGetLastError());
     }
@@ -1570,6 +1631,20 @@ int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void**
         *offsets_dev = b->packOffsets.p;
     if (packed_dev)
         *packed_dev = b->packed.p;
+    return U3D_OK;
+}
+
+int u3d_batch_read_z_ranges(u3d_batch* b, float* minmax, void* stream)
+{
+    if (!b || !minmax)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_z_ranges: NULL argument");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    if (b->numViews)
+    {
+        CU_CHECK(cudaMemcpyAsync(minmax, b->zRange.p, (size_t)b->numViews * 8, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
     return U3D_OK;
 }
 

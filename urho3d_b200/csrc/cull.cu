@@ -194,7 +194,7 @@ __device__ int g_cullProfOn;
 
 template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
-    uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, uint32_t* __restrict__ flags)
+    uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags)
 {
     __shared__ CullShared<T> sh;
     const int v = blockIdx.x;
@@ -367,7 +367,10 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
 
     // ---------------- phase 2: drawables of surviving octants, DFS order ----------------
     const bool shadowQuery = vc.queryMode == QUERY_SHADOWCASTER;
-    const bool needOcclusion = stage == STAGE_VISIBLE && occl;
+    const bool needOcclusion = stage >= STAGE_VISIBLE && occl;
+    const bool inViewStage = stage == STAGE_INVIEW;
+    const bool useQueue = needOcclusion || inViewStage; // survivors go through the evaluation pass
+    float zMin = __int_as_float(0x7f800000), zMax = 0.0f; // PerThreadSceneResult::minZ_/maxZ_ start values, View.cpp:893-894
 
     // Occlusion test over the queued frustum survivors (warps pull groups of 32), then ordered emission.
     auto eval_drawables = [&]() {
@@ -388,12 +391,35 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
             {
                 const uint32_t d = sh.ring[idx];
                 mn = sc.drwMin[d];
-                if (!(__float_as_uint(mn.w) & kMetaOccludee))
-                    vis = true; // !drawable->IsOccludee(), View.cpp:177
+                mx = sc.drwMax[d];
+                if (!needOcclusion || !(__float_as_uint(mn.w) & kMetaOccludee))
+                    vis = true; // !buffer || !drawable->IsOccludee(), View.cpp:177
                 else
-                {
-                    mx = sc.drwMax[d];
                     test = true;
+                if (inViewStage)
+                {
+                    // Drawable::UpdateBatches distance (Drawable.cpp:134-137) and the draw-distance test (View.cpp:179-186).
+                    // Independent of the occlusion answer, so it is applied up front: a drawable beyond its draw distance is not in view.
+                    const float maxDistance = sc.drwDrawDist[d];
+                    if (maxDistance > 0.0f)
+                    {
+                        const float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f; // BoundingBox::Center
+                        float dist;
+                        if (!vc.ortho)
+                        {
+                            const float dx = cx - vc.camPos[0], dy = cy - vc.camPos[1], dz = cz - vc.camPos[2];
+                            dist = sqrtf(dx * dx + dy * dy + dz * dz); // (worldPos - cameraPos).Length(), Camera.cpp:487-493
+                        }
+                        else
+                            // Abs((GetView() * worldPos).z_), Camera.cpp:495, with the operation order of the reference's default (URHO3D_SSE)
+                            // build of Matrix3x4 * Vector3 (Matrix3x4.h:256-274): (m20*x + m22*z) + (m21*y + m23)
+                            dist = fabsf((vc.viewZ[0] * cx + vc.viewZ[2] * cz) + (vc.viewZ[1] * cy + vc.viewZ[3]));
+                        if (dist > maxDistance)
+                        {
+                            vis = false;
+                            test = false;
+                        }
+                    }
                 }
             }
             bool parked = false;
@@ -426,9 +452,29 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
             const uint32_t word = sh.visWord[grp];
             if ((word >> lane) & 1u)
             {
+                const uint32_t d = sh.ring[grp * 32 + lane];
                 const uint32_t pos = cursor + sh.groupOff[grp] + __popc(word & ((1u << lane) - 1u));
                 if (pos < outCap)
-                    out[pos] = sc.drwId[sh.ring[grp * 32 + lane]];
+                    out[pos] = sc.drwId[d];
+                if (inViewStage)
+                {
+                    // view-space Z range of the geometries in view, View.cpp:198-211
+                    const float4 mn = sc.drwMin[d];
+                    if (__float_as_uint(mn.w) & 1u) // DRAWABLE_GEOMETRY
+                    {
+                        const float4 mx = sc.drwMax[d];
+                        const float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
+                        const float ex = (mx.x - mn.x) * 0.5f, ey = (mx.y - mn.y) * 0.5f, ez = (mx.z - mn.z) * 0.5f;
+                        if (ex * ex + ey * ey + ez * ez < 100000000.0f * 100000000.0f) // M_LARGE_VALUE, MathDefs.h:55
+                        {
+                            const float viewCenterZ = vc.viewZ[0] * cx + vc.viewZ[1] * cy + vc.viewZ[2] * cz + vc.viewZ[3];
+                            const float viewEdgeZ = fabsf(vc.viewZ[0]) * ex + fabsf(vc.viewZ[1]) * ey + fabsf(vc.viewZ[2]) * ez;
+                            const float lo = viewCenterZ - viewEdgeZ, hi = viewCenterZ + viewEdgeZ;
+                            zMin = lo < zMin ? lo : zMin;
+                            zMax = hi > zMax ? hi : zMax;
+                        }
+                    }
+                }
             }
         }
         __syncthreads();
@@ -495,7 +541,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
             }
             uint32_t tot;
             const uint32_t rank = block_rank<T>(pass, sh.warpTot, tot);
-            if (!needOcclusion)
+            if (!useQueue)
             {
                 const uint32_t ob = sh.outCursor;
                 if (pass && ob + rank < outCap)
@@ -530,9 +576,39 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
         }
     }
     CULL_PROF_MARK(4);
-    if (needOcclusion && sh.ringCount)
+    if (useQueue && sh.ringCount)
         eval_drawables();
     CULL_PROF_MARK(5);
+    if (inViewStage && zRangeAll)
+    {
+        // min / max over the block (order-independent, so the result equals the reference's merge of per-thread results, View.cpp:926-951)
+        for (int o = 16; o; o >>= 1)
+        {
+            const float a = __shfl_xor_sync(0xffffffffu, zMin, o), b = __shfl_xor_sync(0xffffffffu, zMax, o);
+            zMin = a < zMin ? a : zMin;
+            zMax = b > zMax ? b : zMax;
+        }
+        __syncthreads();
+        float* red = reinterpret_cast<float*>(sh.ring);
+        if (lane == 0)
+        {
+            red[2 * (tid >> 5)] = zMin;
+            red[2 * (tid >> 5) + 1] = zMax;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < T / 32; ++w)
+            {
+                zMin = red[2 * w] < zMin ? red[2 * w] : zMin;
+                zMax = red[2 * w + 1] > zMax ? red[2 * w + 1] : zMax;
+            }
+            if (zMin == __int_as_float(0x7f800000))
+                zMin = 0.0f; // View.cpp:950-951
+            zRangeAll[2 * v] = zMin;
+            zRangeAll[2 * v + 1] = zMax;
+        }
+    }
     __syncthreads();
     if (tid == 0)
     {
@@ -554,7 +630,7 @@ __global__ void k_is_visible(BufGeom g, const ViewConst* __restrict__ view, cons
 }
 
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
-    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, uint32_t* flags, cudaStream_t s)
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, cudaStream_t s)
 {
     if (!numViews)
         return;
@@ -562,9 +638,9 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
     // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.67 ms; 4096 views 7.0 ms vs 9.2 ms).
     if (numViews > kCullSmallBatch)
-        k_cull_views<512, 3><<<numViews, 512, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+        k_cull_views<512, 3><<<numViews, 512, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, zRange, flags);
     else
-        k_cull_views<1024, 1><<<numViews, 1024, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, flags);
+        k_cull_views<1024, 1><<<numViews, 1024, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, zRange, flags);
 }
 
 void cull_prof_enable(int on)

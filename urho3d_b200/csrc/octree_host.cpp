@@ -188,6 +188,7 @@ uint32_t HostOctree::AddDrawable(const float* box6, uint8_t flags, uint32_t view
     d.castShadows = castShadows;
     d.octant = -1;
     d.present = true;
+    d.drawDistance = 0.0f;
     drawables_.push_back(d);
     const uint32_t id = (uint32_t)drawables_.size() - 1;
     Insert(0, id);

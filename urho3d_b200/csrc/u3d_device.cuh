@@ -22,7 +22,7 @@ constexpr int kMaxLevels = 16;
 enum : int { CULL_NONE = 0, CULL_CCW = 1, CULL_CW = 2 };
 enum : int { OUTSIDE = 0, INTERSECTS = 1, INSIDE = 2 };
 enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2 };
-enum : int { STAGE_QUERY = 0, STAGE_VISIBLE = 1 };
+enum : int { STAGE_QUERY = 0, STAGE_VISIBLE = 1, STAGE_INVIEW = 2 };
 
 // Per-drawable meta bits packed into the first pad word of the 32-byte AABB record (BoundingBox.h:326-330 layout).
 constexpr uint32_t kMetaOccludee = 1u << 8;
@@ -48,7 +48,10 @@ struct ViewConst
     int cullMode;        // effective mode after the reverseCulling flip (OB.cpp:134-144)
     int queryMode;       // QUERY_*
     int useOcclusion;    // 0: no buffer (frustum only)
-    int pad[3];
+    int ortho;           // Camera::IsOrthographic()
+    float viewZ[4];      // third row of the view matrix (m20, m21, m22, m23): view-space Z of a point
+    float camPos[3];     // camera world position
+    int pad;
 };
 
 /// One set-up triangle, self-contained per half (closed form of the incremental loops OB.cpp:897-1001):

@@ -31,6 +31,7 @@ struct HDrawable
     uint32_t viewMask;
     bool occludee, castShadows, present;
     int octant;
+    float drawDistance{0.0f};
 };
 
 /// See octree_host.cpp.
@@ -42,6 +43,14 @@ public:
     uint32_t AddDrawable(const float* box6, uint8_t flags, uint32_t viewMask, bool occludee, bool castShadows);
     bool UpdateDrawable(uint32_t id, const float* box6);
     bool RemoveDrawable(uint32_t id);
+    bool SetDrawDistances(uint32_t first, uint32_t n, const float* d)
+    {
+        if ((uint64_t)first + n > drawables_.size())
+            return false;
+        for (uint32_t i = 0; i < n; ++i)
+            drawables_[first + i].drawDistance = d[i];
+        return true;
+    }
     void Flatten(FlatOctree& f) const;
     const std::vector<HDrawable>& Drawables() const { return drawables_; }
     unsigned NumLevels() const { return numLevels_; }

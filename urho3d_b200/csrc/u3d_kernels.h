@@ -74,6 +74,7 @@ struct SceneDev
     const float4* drwMin;          // xyz = world AABB min, w = drawableFlags | kMetaOccludee | kMetaCastShadows (uint bits)
     const float4* drwMax;          // xyz = world AABB max, w = viewMask (uint bits)
     const uint32_t* drwId;         // caller's drawable id for each DFS slot
+    const float* drwDrawDist;      // Drawable::GetDrawDistance per DFS slot (0 = unlimited)
 };
 
 void launch_clear(int* depth, size_t nInts, cudaStream_t s);
@@ -94,7 +95,7 @@ void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mi
 /// Octree query (+ optional CheckVisibility predicate) for every view.  octState: numViews x numOctants bytes of scratch.
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
-    uint32_t* flags, cudaStream_t s);
+    float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags, cudaStream_t s);
 
 /// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
 /// 3 chunk set-up, 4 frustum rounds, 5 drawable occlusion tests + emission).
