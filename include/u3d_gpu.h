@@ -102,7 +102,8 @@ U3D_API void u3d_octree_destroy(u3d_octree* t);
  * NULL arrays mean DRAWABLE_GEOMETRY / DEFAULT_VIEWMASK / occludee / no shadows.  Ids are assigned consecutively; *first_id = first. */
 U3D_API int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask,
     const uint8_t* occludee, const uint8_t* cast_shadows, uint32_t* first_id);
-/* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472). */
+/* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472).  Returns 1 when the flattened layout did not
+ * change (the drawable stayed in its octant: u3d_scene_update_boxes is enough), 0 when it did (re-create the scene). */
 /* Drawable::SetDrawDistance for n drawables starting at first_id (0 = unlimited, the default; used by U3D_STAGE_INVIEW). */
 U3D_API int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, const float* draw_distance);
 U3D_API int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6]);
@@ -123,6 +124,9 @@ U3D_API int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t num_octants, const int3
     const uint32_t* view_mask, const uint8_t* occludee, const uint8_t* cast_shadows, u3d_scene** out);
 /* Per-drawable draw distances (indexed by drawable id, 0 = unlimited) for a scene made with u3d_scene_create_flat. */
 U3D_API int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_distance);
+/* Dirty-range maintenance: new world boxes for n drawables whose octant did not change (u3d_octree_update returned 1); only their
+ * 2 x 12 bytes are rewritten in HBM, the layout and the meta words stay. */
+U3D_API int u3d_scene_update_boxes(u3d_scene* s, uint32_t n, const uint32_t* ids, const float* aabb6, void* stream);
 U3D_API void u3d_scene_destroy(u3d_scene* s);
 U3D_API int u3d_scene_counts(const u3d_scene* s, uint32_t* num_octants, uint32_t* num_drawables);
 

@@ -248,6 +248,40 @@ void ref_add_drawables(void* h, int n, const float* aabb6, const unsigned char* 
 
 int ref_num_drawables(void* h) { return (int)reinterpret_cast<Ref*>(h)->drawables_.size(); }
 
+/// Drawables moved / resized: what Drawable::OnMarkedDirty does (Drawable.cpp:374-383: world box dirty + Octree::QueueUpdate), followed by
+/// the per-frame Octree::Update (Octree.cpp:364-475), whose reinsertion loop decides which drawables change octant.
+void ref_move_drawables(void* h, int n, const int* ids, const float* aabb6)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    for (int i = 0; i < n; ++i)
+    {
+        TestDrawable* d = r->drawables_[ids[i]];
+        if (!d)
+            continue;
+        const float* b = aabb6 + 6 * (size_t)i;
+        d->fixedWorldBox_ = BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]));
+        d->worldBoundingBoxDirty_ = true;
+        if (!d->updateQueued_)
+            r->octree_->QueueUpdate(d);
+    }
+    FrameInfo frame;
+    frame.frameNumber_ = 1;
+    frame.timeStep_ = 0.0f;
+    frame.camera_ = nullptr;
+    r->octree_->Update(frame);
+}
+
+/// A drawable leaves the scene: Node::Remove -> Drawable::OnSceneSet(nullptr) -> RemoveFromOctree (Drawable.cpp:366-420).
+void ref_remove_drawable(void* h, int id)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    TestDrawable* d = r->drawables_[id];
+    if (!d)
+        return;
+    r->drawables_[id] = nullptr;
+    d->GetNode()->Remove();
+}
+
 int ref_octree_num_octants(void* h)
 {
     auto* r = reinterpret_cast<Ref*>(h);

@@ -64,6 +64,8 @@ class Ref:
         L.ref_run_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int,
                                    C.c_uint, C.c_uint, _i, C.c_int, _i, C.POINTER(C.c_double)]
         L.ref_num_threads.argtypes = [C.c_void_p]
+        L.ref_move_drawables.argtypes = [C.c_void_p, C.c_int, _i, _f]
+        L.ref_remove_drawable.argtypes = [C.c_void_p, C.c_int]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
         self.h = L.ref_create(int(worker_threads))
         self._keep = []
@@ -86,6 +88,14 @@ class Ref:
         arrs = [None if a is None else np.ascontiguousarray(a) for a in (flags, view_mask, occludee, cast_shadows)]
         self.lib.ref_add_drawables(self.h, n, _p(aabb6, _f), _p(arrs[0], _u8), _p(arrs[1], _u32), _p(arrs[2], _u8), _p(arrs[3], _u8))
         self.n += n
+
+    def move_drawables(self, ids, aabb6):
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        a = np.ascontiguousarray(aabb6, dtype=np.float32)
+        self.lib.ref_move_drawables(self.h, len(ids), _p(ids, _i), _p(a, _f))
+
+    def remove_drawable(self, idx):
+        self.lib.ref_remove_drawable(self.h, int(idx))
 
     def flatten(self):
         """DFS pre-order dump: parent, level, cullingBox(6), first, count per octant; order = drawable ids in DFS order."""

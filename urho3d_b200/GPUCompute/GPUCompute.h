@@ -277,8 +277,14 @@ public:
     /// A drawable moved or was resized: the reinsertion rule of Octree::Update (Octree.cpp:440-472).
     void UpdateDrawable(unsigned id, const float* worldBoxMinMax6)
     {
-        u3d_octree_update(tree_, id, worldBoxMinMax6);
-        dirty_ = true;
+        if (u3d_octree_update(tree_, id, worldBoxMinMax6) == 1 && !dirty_)
+        {
+            // stayed in its octant: only its box has to be refreshed in HBM
+            pendingIds_.push_back(id);
+            pendingBoxes_.insert(pendingBoxes_.end(), worldBoxMinMax6, worldBoxMinMax6 + 6);
+        }
+        else
+            dirty_ = true;
     }
     void RemoveDrawable(unsigned id)
     {
@@ -290,7 +296,17 @@ public:
     void Sync()
     {
         if (!dirty_ && scene_)
+        {
+            if (!pendingIds_.empty())
+            {
+                Check(u3d_scene_update_boxes(scene_, (uint32_t)pendingIds_.size(), pendingIds_.data(), pendingBoxes_.data(), nullptr), "u3d_scene_update_boxes");
+                pendingIds_.clear();
+                pendingBoxes_.clear();
+            }
             return;
+        }
+        pendingIds_.clear();
+        pendingBoxes_.clear();
         u3d_scene_destroy(scene_);
         scene_ = nullptr;
         Check(u3d_scene_create(ctx_.Handle(), tree_, &scene_), "u3d_scene_create");
@@ -338,6 +354,8 @@ private:
     u3d_scene* scene_{};
     uint32_t numOctants_{}, numDrawables_{};
     bool dirty_{true};
+    std::vector<uint32_t> pendingIds_;
+    std::vector<float> pendingBoxes_;
 };
 
 /// The batched many-view entry point (new): V views per call through raster + hierarchy + octree query + visibility.

@@ -57,6 +57,7 @@ SIGNATURES = {
     "u3d_scene_create": (C.c_int, [_vp, _vp, C.POINTER(_vp)]),
     "u3d_scene_create_flat": (C.c_int, [_vp, C.c_uint32, _i32, _i32, _f, _i32, _i32, C.c_uint32, _i32, _f, _u8, _u32, _u8, _u8, C.POINTER(_vp)]),
     "u3d_scene_set_draw_distances": (C.c_int, [_vp, C.c_uint32, _f]),
+    "u3d_scene_update_boxes": (C.c_int, [_vp, C.c_uint32, _u32, _f, _vp]),
     "u3d_scene_destroy": (None, [_vp]),
     "u3d_scene_counts": (C.c_int, [_vp, _u32, _u32]),
     "u3d_mesh_create": (C.c_int, [_vp, _vp, C.c_uint32, C.c_uint32, _vp, C.c_uint32, C.c_uint32, C.POINTER(_vp)]),
@@ -192,8 +193,9 @@ class Octree:
         return first.value
 
     def update(self, idx, aabb6):
+        """Returns True when the drawable stayed in its octant (the flattened layout is unchanged)."""
         a = _arr(aabb6, np.float32)
-        _chk(lib().u3d_octree_update(self.h, idx, _p(a, _f)))
+        return bool(_chk(lib().u3d_octree_update(self.h, idx, _p(a, _f))))
 
     def set_draw_distances(self, draw_distance, first_id=0):
         d = _arr(draw_distance, np.float32)
@@ -240,6 +242,12 @@ class GpuScene:
     def set_draw_distances(self, draw_distance):
         d = _arr(draw_distance, np.float32)
         _chk(lib().u3d_scene_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
+
+    def update_boxes(self, ids, aabb6, stream=None):
+        """Rewrite the world boxes of drawables that moved inside their octant (no re-flatten)."""
+        i = _arr(ids, np.uint32)
+        a = _arr(aabb6, np.float32)
+        _chk(lib().u3d_scene_update_boxes(self.h, i.shape[0], _p(i, _u32), _p(a, _f), stream))
 
     def query(self, planes, ob=None, flags=0xFF, view_mask=0xFFFFFFFF, mode=QUERY_FRUSTUM, stage=STAGE_QUERY, capacity=None):
         """Octree::GetDrawables with a frustum-type query (+ optional visibility predicate).  Returns (ids, query_count)."""

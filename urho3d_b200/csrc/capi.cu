@@ -159,6 +159,8 @@ struct u3d_scene
     DevBuf<int2> octChild;
     DevBuf<uint32_t> drwId;
     DevBuf<float> drwDrawDist;       // per DFS slot, 0 = unlimited
+    DevBuf<uint32_t> updSlots;       // staging of u3d_scene_update_boxes
+    DevBuf<float> updBoxes;
     std::vector<uint32_t> slotOfId;  // drawable id -> DFS slot (for late per-drawable uploads)
 };
 
@@ -460,7 +462,10 @@ int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6])
 {
     if (!t || !aabb6)
         return fail(U3D_ERR_INVALID, "u3d_octree_update: NULL argument");
-    return t->tree.UpdateDrawable(id, aabb6) ? U3D_OK : fail(U3D_ERR_INVALID, "u3d_octree_update: unknown drawable id");
+    const uint64_t before = t->tree.StructureVersion();
+    if (!t->tree.UpdateDrawable(id, aabb6))
+        return fail(U3D_ERR_INVALID, "u3d_octree_update: unknown drawable id");
+    return t->tree.StructureVersion() == before ? 1 : 0;
 }
 
 int u3d_octree_remove(u3d_octree* t, uint32_t id)
@@ -670,6 +675,31 @@ int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_dis
         if (s->slotOfId[id] != 0xFFFFFFFFu)
             bySlot[s->slotOfId[id]] = draw_distance[id];
     CU_CHECK(cudaMemcpy(s->drwDrawDist.p, bySlot.data(), (size_t)std::max<uint32_t>(S, 1) * 4, cudaMemcpyHostToDevice));
+    return U3D_OK;
+}
+
+int u3d_scene_update_boxes(u3d_scene* s, uint32_t n, const uint32_t* ids, const float* aabb6, void* stream)
+{
+    if (!s || (n && (!ids || !aabb6)))
+        return fail(U3D_ERR_INVALID, "u3d_scene_update_boxes: NULL argument");
+    if (!n)
+        return U3D_OK;
+    CU_CHECK(cudaSetDevice(s->ctx->device));
+    cudaStream_t st = s->ctx->pick(stream);
+    std::vector<uint32_t> slots(n);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (ids[i] >= s->slotOfId.size() || s->slotOfId[ids[i]] == 0xFFFFFFFFu)
+            return fail(U3D_ERR_INVALID, "u3d_scene_update_boxes: drawable id is not in the scene");
+        slots[i] = s->slotOfId[ids[i]];
+    }
+    CU_CHECK(s->updSlots.ensure(n));
+    CU_CHECK(s->updBoxes.ensure((size_t)n * 6));
+    CU_CHECK(cudaMemcpyAsync(s->updSlots.p, slots.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(s->updBoxes.p, aabb6, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    launch_update_boxes(s->drwMin.p, s->drwMax.p, s->updSlots.p, s->updBoxes.p, n, st);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaStreamSynchronize(st)); // host staging vectors go out of scope
     return U3D_OK;
 }
 

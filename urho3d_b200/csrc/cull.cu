@@ -643,6 +643,28 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
         k_cull_views<1024, 1><<<numViews, 1024, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, zRange, flags);
 }
 
+/// World boxes of drawables that moved without leaving their octant: rewrite xyz of their two float4 records, keep the meta words.
+__global__ void k_update_boxes(float4* __restrict__ drwMin, float4* __restrict__ drwMax, const uint32_t* __restrict__ slots, const float* __restrict__ boxes,
+    uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const uint32_t s = slots[i];
+    const float* b = boxes + 6 * (size_t)i;
+    float4 mn = drwMin[s], mx = drwMax[s];
+    mn.x = b[0]; mn.y = b[1]; mn.z = b[2];
+    mx.x = b[3]; mx.y = b[4]; mx.z = b[5];
+    drwMin[s] = mn;
+    drwMax[s] = mx;
+}
+
+void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s)
+{
+    if (n)
+        k_update_boxes<<<(n + 255) / 256, 256, 0, s>>>(drwMin, drwMax, slots, boxes, n);
+}
+
 void cull_prof_enable(int on)
 {
     cudaMemcpyToSymbol(g_cullProfOn, &on, sizeof(int));

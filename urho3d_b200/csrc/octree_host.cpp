@@ -43,6 +43,7 @@ HostOctree::HostOctree(const float* mn, const float* mx, unsigned levels)
 void HostOctree::SetSize(const float* mn, const float* mx, unsigned levels)
 {
     // Octree::SetSize (Octree.cpp:340-353): drawables fall back to the root and are re-queued; here callers rebuild.
+    ++version_;
     octants_.clear();
     freeList_.clear();
     octants_.emplace_back();
@@ -86,6 +87,7 @@ int HostOctree::GetOrCreateChild(int oi, unsigned index)
         }
     }
     const unsigned level = octants_[oi].level + 1;
+    ++version_;
     const int ci = NewOctant(); // may reallocate octants_
     InitOctant(octants_[ci], mn, mx, level, oi, index);
     octants_[oi].children[index] = ci;
@@ -154,6 +156,7 @@ void HostOctree::Insert(int oi, uint32_t id)
             if (old != oi)
             {
                 // add first, then remove (Octree.cpp:148-153)
+                ++version_;
                 d.octant = oi;
                 octants_[oi].drawables.push_back(id);
                 IncCount(oi);
@@ -217,6 +220,7 @@ bool HostOctree::RemoveDrawable(uint32_t id)
     if (id >= drawables_.size() || !drawables_[id].present)
         return false;
     HDrawable& d = drawables_[id];
+    ++version_;
     if (d.octant >= 0)
     {
         auto& v = octants_[d.octant].drawables;

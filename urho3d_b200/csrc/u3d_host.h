@@ -54,6 +54,8 @@ public:
     void Flatten(FlatOctree& f) const;
     const std::vector<HDrawable>& Drawables() const { return drawables_; }
     unsigned NumLevels() const { return numLevels_; }
+    /// Bumped whenever an octant's drawable list changes or an octant is created / deleted (i.e. when the flattened layout changes).
+    uint64_t StructureVersion() const { return version_; }
 
 private:
     void InitOctant(HOctant& o, const float* mn, const float* mx, unsigned level, int parent, unsigned index);
@@ -69,6 +71,7 @@ private:
     std::vector<int> freeList_;
     std::vector<HDrawable> drawables_;
     unsigned numLevels_{8};
+    uint64_t version_{0};
 };
 
 } // namespace u3d

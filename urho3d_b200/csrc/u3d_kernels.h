@@ -97,6 +97,8 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
     float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags, cudaStream_t s);
 
+void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s);
+
 /// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
 /// 3 chunk set-up, 4 frustum rounds, 5 drawable occlusion tests + emission).
 void cull_prof_enable(int on);
