@@ -356,6 +356,11 @@ int u3d_debug_set_option(const char* name, int value)
         g_warpAreaMax = value;
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "heavy_extent") == 0)
+    {
+        cull_set_heavy_extent(value);
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "cull_prof") == 0)
     {
         cull_prof_enable(value);

@@ -17,7 +17,8 @@ constexpr int kRing = 2048;             // work-queue entries held in shared mem
 constexpr int kRingGroups = kRing / 32;
 constexpr int kWStack = 256;            // per-warp texel stack of the cooperative range test
 constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks of >= 512 octants = 4M octants
-constexpr int kHeavyExtent = 32;        // rects larger than this (pixels) are tested by a whole warp
+constexpr int kHeavyExtentDefault = 96;
+__device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)        // rects larger than this (pixels) are tested by a whole warp
 constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 
 template <int T> struct CullShared
@@ -110,7 +111,7 @@ template <int T> __device__ __forceinline__ bool visible_stage_a(const BufGeom& 
     {
         if (ob_project(g, vp, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, r))
             vis = true;
-        else if (useMips && max(r.right - r.left, r.bottom - r.top) >= kHeavyExtent)
+        else if (useMips && max(r.right - r.left, r.bottom - r.top) >= g_heavyExtent)
             heavy = true;
         else
             vis = range_visible_thread(g, depth, mips, useMips, r);
@@ -663,6 +664,11 @@ void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, 
 {
     if (n)
         k_update_boxes<<<(n + 255) / 256, 256, 0, s>>>(drwMin, drwMax, slots, boxes, n);
+}
+
+void cull_set_heavy_extent(int px)
+{
+    cudaMemcpyToSymbol(g_heavyExtent, &px, sizeof(int));
 }
 
 void cull_prof_enable(int on)

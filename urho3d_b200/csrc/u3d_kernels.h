@@ -102,6 +102,7 @@ void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, 
 /// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
 /// 3 chunk set-up, 4 frustum rounds, 5 drawable occlusion tests + emission).
 void cull_prof_enable(int on);
+void cull_set_heavy_extent(int px);
 void cull_prof_read(unsigned long long* out8);
 
 /// OcclusionBuffer::IsVisible for n boxes against view 0's buffer.
