@@ -10,6 +10,14 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+    # The tests bind libu3dgpu.so (the product) and liboracle.so (the checker).  Build whichever is missing so that the suite does not
+    # depend on build() having been called first; nvcc / gcc cross-compile without a GPU.  A failed build fails the tests loudly.
+    import subprocess
+    lib = os.path.join(ROOT, "urho3d_b200", "lib", "libu3dgpu.so")
+    if not os.path.exists(lib):
+        subprocess.check_call(["make", "-s", "-j8", "-C", os.path.join(ROOT, "urho3d_b200", "csrc")])
+    if not os.path.exists(os.path.join(ROOT, "oracle", "liboracle.so")):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle")])
 
 
 @pytest.fixture(scope="session")
