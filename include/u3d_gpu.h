@@ -43,7 +43,11 @@ enum
 {
     U3D_QUERY_FRUSTUM = 0,       /* FrustumOctreeQuery, OctreeQuery.h:140-158 / OctreeQuery.cpp:98-118 */
     U3D_QUERY_OCCLUDED = 1,      /* OccludedFrustumOctreeQuery, View.cpp:116-158 */
-    U3D_QUERY_SHADOWCASTER = 2   /* ShadowCasterOctreeQuery, View.cpp:59-84 */
+    U3D_QUERY_SHADOWCASTER = 2,  /* ShadowCasterOctreeQuery, View.cpp:59-84 */
+    /* shape queries (OctreeQuery.h:72-138, OctreeQuery.cpp:32-96); their parameters travel in the 24 floats of `planes`: */
+    U3D_QUERY_SPHERE = 3,        /* SphereOctreeQuery: planes[0..3] = centre.xyz, radius (Sphere::IsInside / IsInsideFast, Math/Sphere.cpp:136-256) */
+    U3D_QUERY_BOX = 4,           /* BoxOctreeQuery:    planes[0..5] = min.xyz, max.xyz */
+    U3D_QUERY_POINT = 5          /* PointOctreeQuery:  planes[0..2] = point */
 };
 /* what is emitted */
 enum

@@ -185,7 +185,9 @@ class OracleTree:
                        _p(self.aabb, _f), _p(self.flags, _u8), _p(self.view_mask, _u32), _p(self.occludee, _u8), _p(self.cast_shadows, _u8))
 
     def query(self, mode, planes, ob=None, flags=0xFF, view_mask=0xFFFFFFFF, as_ids=True):
-        p = np.ascontiguousarray(planes, dtype=np.float32)
+        p = np.zeros(24, np.float32)
+        flat_p = np.asarray(planes, np.float32).reshape(-1)
+        p[:flat_p.shape[0]] = flat_p
         out = np.zeros(max(len(self.order), 1), np.int32)
         n = lib().orc_query(C.byref(self.t), mode, _p(p, _f), ob.h if ob is not None else None, flags, view_mask, _p(out, _i))
         pos = out[:n].copy()

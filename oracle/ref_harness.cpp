@@ -33,6 +33,7 @@
 #include <Urho3D/Graphics/OctreeQuery.h>
 #include <Urho3D/Scene/Node.h>
 #include <Urho3D/Scene/Scene.h>
+#include <Urho3D/Math/Sphere.h>
 
 using namespace Urho3D;
 
@@ -463,6 +464,33 @@ int ref_query(void* h, int mode, unsigned flags, unsigned viewMask, int* outIdx,
     else
     {
         FrustumOctreeQuery q(r->result_, fr, (unsigned char)flags, viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    int n = (int)r->result_.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+        outIdx[i] = static_cast<TestDrawable*>(r->result_[i])->id_;
+    return n;
+}
+
+/// Octree::GetDrawables with the reference's own SphereOctreeQuery (shape 3: params = centre.xyz, radius), BoxOctreeQuery (4: min.xyz, max.xyz)
+/// or PointOctreeQuery (5: xyz), OctreeQuery.h:72-138.
+int ref_query_shape(void* h, int shape, const float* params, unsigned flags, unsigned viewMask, int* outIdx, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    if (shape == 3)
+    {
+        SphereOctreeQuery q(r->result_, Sphere(Vector3(params[0], params[1], params[2]), params[3]), (unsigned char)flags, viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    else if (shape == 4)
+    {
+        BoxOctreeQuery q(r->result_, BoundingBox(Vector3(params[0], params[1], params[2]), Vector3(params[3], params[4], params[5])), (unsigned char)flags,
+            viewMask);
+        r->octree_->GetDrawables(q);
+    }
+    else
+    {
+        PointOctreeQuery q(r->result_, Vector3(params[0], params[1], params[2]), (unsigned char)flags, viewMask);
         r->octree_->GetDrawables(q);
     }
     int n = (int)r->result_.Size();

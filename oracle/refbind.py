@@ -64,6 +64,7 @@ class Ref:
         L.ref_run_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int,
                                    C.c_uint, C.c_uint, _i, C.c_int, _i, C.POINTER(C.c_double)]
         L.ref_num_threads.argtypes = [C.c_void_p]
+        L.ref_query_shape.argtypes = [C.c_void_p, C.c_int, _f, C.c_uint, C.c_uint, _i, C.c_int]
         L.ref_move_drawables.argtypes = [C.c_void_p, C.c_int, _i, _f]
         L.ref_remove_drawable.argtypes = [C.c_void_p, C.c_int]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
@@ -214,6 +215,15 @@ class Ref:
         """mode 0 FrustumOctreeQuery, 1 OccludedFrustumOctreeQuery, 2 ShadowCasterOctreeQuery -> drawable ids (DFS order)."""
         out = np.zeros(max(self.n, 1), np.int32)
         n = self.lib.ref_query(self.h, mode, flags, view_mask, _p(out, _i), out.shape[0])
+        return out[:n].copy()
+
+    def query_shape(self, shape, params, flags=0xFF, view_mask=0xFFFFFFFF):
+        """shape 3 SphereOctreeQuery (centre.xyz, radius), 4 BoxOctreeQuery (min, max), 5 PointOctreeQuery (xyz)."""
+        p = np.zeros(8, np.float32)
+        fp = np.asarray(params, np.float32).reshape(-1)
+        p[:fp.shape[0]] = fp
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = self.lib.ref_query_shape(self.h, shape, _p(p, _f), flags, view_mask, _p(out, _i), out.shape[0])
         return out[:n].copy()
 
     def check_visibility(self, use_buffer=True):

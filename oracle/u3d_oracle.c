@@ -642,10 +642,64 @@ typedef struct
     const unsigned char* cast_shadows;
 } OrcTree;
 
-enum { Q_FRUSTUM = 0, Q_OCCLUDED = 1, Q_SHADOWCASTER = 2 };
+enum { Q_FRUSTUM = 0, Q_OCCLUDED = 1, Q_SHADOWCASTER = 2, Q_SPHERE = 3, Q_BOX = 4, Q_POINT = 5 };
 
-/* Octree::GetDrawables(query) for FrustumOctreeQuery (OctreeQuery.cpp:98-118), OccludedFrustumOctreeQuery (View.cpp:116-158)
- * and ShadowCasterOctreeQuery (View.cpp:59-84).  Writes DFS positions of the result; returns their number. */
+/* Sphere::IsInside / IsInsideFast(BoundingBox), Math/Sphere.cpp:136-256.  s = centre.xyz, radius. */
+static int sphere_test(const float* s, const float* b, int fast)
+{
+    float r2 = s[3] * s[3], d2 = 0.0f, t;
+    for (int a = 0; a < 3; ++a)
+    {
+        if (s[a] < b[a]) { t = s[a] - b[a]; d2 += t * t; }
+        else if (s[a] > b[3 + a]) { t = s[a] - b[3 + a]; d2 += t * t; }
+    }
+    if (d2 >= r2)
+        return OUTSIDE;
+    if (fast)
+        return INSIDE;
+    float lo[3] = {b[0] - s[0], b[1] - s[1], b[2] - s[2]}, hi[3] = {b[3] - s[0], b[4] - s[1], b[5] - s[2]};
+    /* corner walk of the reference: ---, +--, ++-, -+-, -++, --+, +-+, +++ */
+    static const int sel[8][3] = {{0, 0, 0}, {1, 0, 0}, {1, 1, 0}, {0, 1, 0}, {0, 1, 1}, {0, 0, 1}, {1, 0, 1}, {1, 1, 1}};
+    for (int c = 0; c < 8; ++c)
+    {
+        float x = sel[c][0] ? hi[0] : lo[0], y = sel[c][1] ? hi[1] : lo[1], z = sel[c][2] ? hi[2] : lo[2];
+        if (x * x + y * y + z * z >= r2)
+            return INTERSECTS;
+    }
+    return INSIDE;
+}
+
+/* BoundingBox::IsInside / IsInsideFast(BoundingBox) with q as `this`, BoundingBox.h:295-315. */
+static int box_test(const float* q, const float* b, int fast)
+{
+    if (b[3] < q[0] || b[0] > q[3] || b[4] < q[1] || b[1] > q[4] || b[5] < q[2] || b[2] > q[5])
+        return OUTSIDE;
+    if (!fast && (b[0] < q[0] || b[3] > q[3] || b[1] < q[1] || b[4] > q[4] || b[2] < q[2] || b[5] > q[5]))
+        return INTERSECTS;
+    return INSIDE;
+}
+
+/* BoundingBox::IsInside(Vector3) with b as `this`, BoundingBox.h:285-292. */
+static int point_test(const float* p, const float* b)
+{
+    if (p[0] < b[0] || p[0] > b[3] || p[1] < b[1] || p[1] > b[4] || p[2] < b[2] || p[2] > b[5])
+        return OUTSIDE;
+    return INSIDE;
+}
+
+static int shape_test(int mode, const float* params, const float* b, int fast)
+{
+    if (mode == Q_SPHERE)
+        return sphere_test(params, b, fast);
+    if (mode == Q_BOX)
+        return box_test(params, b, fast);
+    if (mode == Q_POINT)
+        return point_test(params, b);
+    return orc_frustum_test(params, b, fast);
+}
+
+/* Octree::GetDrawables(query) for FrustumOctreeQuery (OctreeQuery.cpp:98-118), OccludedFrustumOctreeQuery (View.cpp:116-158),
+ * ShadowCasterOctreeQuery (View.cpp:59-84) and the Sphere / Box / Point queries (OctreeQuery.cpp:32-96; parameters in planes24).  Writes DFS positions of the result; returns their number. */
 int orc_query(const OrcTree* t, int mode, const float* planes24, const OrcOB* ob, unsigned flags, unsigned view_mask, int* out)
 {
     /* iterative pre-order walk: state[i] 0 = culled, 1 = visited with inside=false, 2 = visited with inside=true */
@@ -677,7 +731,7 @@ int orc_query(const OrcTree* t, int mode, const float* planes24, const OrcOB* ob
                 }
             }
             else
-                res = inside ? INSIDE : orc_frustum_test(planes24, box, 0);
+                res = inside ? INSIDE : shape_test(mode, planes24, box, 0);
             if (res == OUTSIDE)
             {
                 state[i] = 0;
@@ -692,7 +746,7 @@ int orc_query(const OrcTree* t, int mode, const float* planes24, const OrcOB* ob
             if (mode == Q_SHADOWCASTER && !t->cast_shadows[d])
                 continue;
             if ((t->flags[d] & flags) && (t->view_mask[d] & view_mask))
-                if (inside || orc_frustum_test(planes24, t->aabb6 + 6 * (size_t)d, 1) != OUTSIDE)
+                if (inside || shape_test(mode, planes24, t->aabb6 + 6 * (size_t)d, 1) != OUTSIDE)
                     out[nout++] = d;
         }
     }

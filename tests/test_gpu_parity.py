@@ -504,3 +504,34 @@ def scenes_with_boxes(sc, boxes):
     c = copy.copy(sc)
     c.aabb = boxes
     return c
+
+
+def test_sphere_box_point_queries(gpu_ctx):
+    """U3D_QUERY_SPHERE / BOX / POINT through u3d_octree_query and through the batched entry point."""
+    sc = helpers.small_scene(n=20000, k=4, extent=150.0, seed=29)
+    sc.flags[::7] = 0x2
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, _ = helpers.make_oracle(sc, flat, 8, 8)
+    rs = np.random.RandomState(3)
+    from test_oracle_vs_reference import shape_cases
+    cases = shape_cases(rs, 150.0, n=10)
+    total = 0
+    for shape, params in cases:
+        want = otree.query(shape, params, None)
+        got, qc = gs.query(params, None, mode=shape)
+        assert qc == len(want) and np.array_equal(got, want), (shape, params)
+        total += len(want)
+    assert total > 0
+    # batched: one "view" per query
+    packed = np.zeros(len(cases), capi.VIEW_DTYPE)
+    for i, (shape, params) in enumerate(cases):
+        packed[i]["planes"][:len(params)] = params
+        packed[i]["query_mode"] = shape
+    packed["drawable_flags"] = 0xFF
+    packed["view_mask"] = 0xFFFFFFFF
+    batch = capi.Batch(gpu_ctx, gs, None, 0, 0, len(cases), sc.n)
+    counts, offsets, ids = batch.cull_views(packed, capi.STAGE_QUERY)
+    for i, (shape, params) in enumerate(cases):
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.query(shape, params, None))
+    for o in (batch, gs, tree):
+        o.close()

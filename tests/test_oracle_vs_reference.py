@@ -135,3 +135,33 @@ def test_in_view_stage_matches_reference(ortho):
         assert len(want_ids) <= len(tree.check_visibility(ob, cand))
     ref.close()
     ob.close()
+
+
+def shape_cases(rs, extent, n=12):
+    out = []
+    for _ in range(n):
+        c = rs.uniform(-extent, extent, 3) * [1, 0.02, 1] + [0, 1, 0]
+        out.append((3, np.array([c[0], c[1], c[2], rs.choice([0.5, 5.0, 40.0, 300.0, 3000.0])], np.float32)))
+        e = rs.uniform(0.5, extent, 3) * rs.choice([0.05, 0.3, 1.0, 30.0])
+        out.append((4, np.concatenate([c - e, c + e]).astype(np.float32)))
+        out.append((5, c.astype(np.float32)))
+    return out
+
+
+def test_sphere_box_point_queries_match_reference():
+    """SphereOctreeQuery / BoxOctreeQuery / PointOctreeQuery (OctreeQuery.cpp:32-96) through the reference's own classes vs the oracle."""
+    sc = helpers.small_scene(n=6000, k=4, extent=120.0, seed=29)
+    sc.flags[::7] = 0x2
+    ref = helpers.make_ref(sc, 64, 64)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), 64, 64)
+    rs = np.random.RandomState(3)
+    total = 0
+    for shape, params in shape_cases(rs, 120.0):
+        for flags in (0xFF, 0x1):
+            want = ref.query_shape(shape, params, flags)
+            got = tree.query(shape, params, None, flags)
+            assert np.array_equal(got, want), (shape, params)
+            total += len(want)
+    assert total > 0
+    ref.close()
+    ob.close()

@@ -10,7 +10,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libu3dgpu.so")
 
-QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER = 0, 1, 2
+QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT = 0, 1, 2, 3, 4, 5
 STAGE_QUERY, STAGE_VISIBLE, STAGE_INVIEW = 0, 1, 2
 CULL_NONE, CULL_CCW, CULL_CW = 0, 1, 2
 ERR_CAPACITY = 4
@@ -253,7 +253,9 @@ class GpuScene:
         """Octree::GetDrawables with a frustum-type query (+ optional visibility predicate).  Returns (ids, query_count)."""
         cap = self.num_drawables if capacity is None else capacity
         out = np.zeros(max(cap, 1), np.uint32)
-        p = _arr(planes, np.float32)
+        p = np.zeros(24, np.float32)
+        flat_p = np.asarray(planes, np.float32).reshape(-1)
+        p[:flat_p.shape[0]] = flat_p  # 6 planes, or the parameters of a sphere / box / point query
         qc, c = C.c_uint32(), C.c_uint32()
         _chk(lib().u3d_octree_query(self.h, ob.h if ob is not None else None, _p(p, _f), flags, view_mask, mode, stage, _p(out, _u32), cap,
                                     C.byref(qc), C.byref(c)))

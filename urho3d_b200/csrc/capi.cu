@@ -1273,7 +1273,7 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
 {
     if (!scene || !planes24 || (capacity && !out_ids))
         return fail(U3D_ERR_INVALID, "u3d_octree_query: NULL argument");
-    if (query_mode < 0 || query_mode > 2 || stage < 0 || stage > 1)
+    if (query_mode < 0 || query_mode > 5 || stage < 0 || stage > 1)
         return fail(U3D_ERR_INVALID, "u3d_octree_query: bad mode/stage");
     u3d_ctx* ctx = scene->ctx;
     CU_CHECK(cudaSetDevice(ctx->device));

@@ -271,7 +271,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                 if (e >> 31)
                     res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
                 else
-                    res = frustum_test<false>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+                    res = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
             }
             // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
             bool parked = false;
@@ -538,7 +538,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                 const uint32_t meta = __float_as_uint(mn.w);
                 // FrustumOctreeQuery::TestDrawables (OctreeQuery.cpp:106-118) / ShadowCasterOctreeQuery (View.cpp:70-82)
                 if ((meta & 0xFFu & vc.drawableFlags) && (__float_as_uint(mx.w) & vc.viewMask) && (!shadowQuery || (meta & kMetaCastShadows)))
-                    pass = inside || frustum_test<true>(vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+                    pass = inside || shape_test<true>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
             }
             uint32_t tot;
             const uint32_t rank = block_rank<T>(pass, sh.warpTot, tot);

@@ -21,7 +21,7 @@ constexpr int kMaxLevels = 16;
 
 enum : int { CULL_NONE = 0, CULL_CCW = 1, CULL_CW = 2 };
 enum : int { OUTSIDE = 0, INTERSECTS = 1, INSIDE = 2 };
-enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2 };
+enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2, QUERY_SPHERE = 3, QUERY_BOX = 4, QUERY_POINT = 5 };
 enum : int { STAGE_QUERY = 0, STAGE_VISIBLE = 1, STAGE_INVIEW = 2 };
 
 // Per-drawable meta bits packed into the first pad word of the 32-byte AABB record (BoundingBox.h:326-330 layout).
@@ -141,6 +141,56 @@ template <bool FAST> __device__ __forceinline__ int frustum_test(const float* pl
             allInside = false;
     }
     return (FAST || allInside) ? INSIDE : INTERSECTS;
+}
+
+/// Octant / drawable test of every GPU-evaluable OctreeQuery.  FAST = the drawable form (IsInsideFast), else the 3-way octant form.
+/// Frustum-type queries (QUERY_FRUSTUM / OCCLUDED / SHADOWCASTER) use the 6 planes; the shape queries carry their parameters in the
+/// same 24 floats: sphere = (centre.xyz, radius)  Sphere::IsInside / IsInsideFast (Math/Sphere.cpp:136-256);
+/// box = (min.xyz, max.xyz)  BoundingBox::IsInside / IsInsideFast (BoundingBox.h:295-315) with the QUERY's box as `this`;
+/// point = (xyz)  BoundingBox::IsInside(point) with the octant / drawable box as `this` (BoundingBox.h:285-292; OctreeQuery.cpp:32-52).
+template <bool FAST> __device__ __forceinline__ int shape_test(int mode, const float* p, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
+{
+    if (mode <= QUERY_SHADOWCASTER)
+        return frustum_test<FAST>(p, mnx, mny, mnz, mxx, mxy, mxz);
+    if (mode == QUERY_SPHERE)
+    {
+        const float cx = p[0], cy = p[1], cz = p[2];
+        const float radiusSquared = p[3] * p[3];
+        float distSquared = 0.0f, temp;
+        if (cx < mnx) { temp = cx - mnx; distSquared += temp * temp; }
+        else if (cx > mxx) { temp = cx - mxx; distSquared += temp * temp; }
+        if (cy < mny) { temp = cy - mny; distSquared += temp * temp; }
+        else if (cy > mxy) { temp = cy - mxy; distSquared += temp * temp; }
+        if (cz < mnz) { temp = cz - mnz; distSquared += temp * temp; }
+        else if (cz > mxz) { temp = cz - mxz; distSquared += temp * temp; }
+        if (distSquared >= radiusSquared)
+            return OUTSIDE;
+        if (FAST)
+            return INSIDE;
+        const float ax = mnx - cx, ay = mny - cy, az = mnz - cz, bx = mxx - cx, by = mxy - cy, bz = mxz - cz;
+        // corner order of the reference: ---, +--, ++-, -+-, -++, --+, +-+, +++
+        if (ax * ax + ay * ay + az * az >= radiusSquared) return INTERSECTS;
+        if (bx * bx + ay * ay + az * az >= radiusSquared) return INTERSECTS;
+        if (bx * bx + by * by + az * az >= radiusSquared) return INTERSECTS;
+        if (ax * ax + by * by + az * az >= radiusSquared) return INTERSECTS;
+        if (ax * ax + by * by + bz * bz >= radiusSquared) return INTERSECTS;
+        if (ax * ax + ay * ay + bz * bz >= radiusSquared) return INTERSECTS;
+        if (bx * bx + ay * ay + bz * bz >= radiusSquared) return INTERSECTS;
+        if (bx * bx + by * by + bz * bz >= radiusSquared) return INTERSECTS;
+        return INSIDE;
+    }
+    if (mode == QUERY_BOX)
+    {
+        if (mxx < p[0] || mnx > p[3] || mxy < p[1] || mny > p[4] || mxz < p[2] || mnz > p[5])
+            return OUTSIDE;
+        if (!FAST && (mnx < p[0] || mxx > p[3] || mny < p[1] || mxy > p[4] || mnz < p[2] || mxz > p[5]))
+            return INTERSECTS;
+        return INSIDE;
+    }
+    // QUERY_POINT
+    if (p[0] < mnx || p[0] > mxx || p[1] < mny || p[1] > mxy || p[2] < mnz || p[2] > mxz)
+        return OUTSIDE;
+    return INSIDE;
 }
 
 /// Screen rect + biased integer depth of a box (the float part of OcclusionBuffer::IsVisible, OB.cpp:341-402).
