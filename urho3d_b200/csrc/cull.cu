@@ -13,22 +13,22 @@
 namespace u3d
 {
 
-constexpr int kRing = 2048;             // work-queue entries held in shared memory between evaluation passes
-constexpr int kRingGroups = kRing / 32;
+constexpr int kCullBigRing = 16384;      // queue entries of the one-CTA-per-SM launch shape
 constexpr int kWStack = 256;            // per-warp texel stack of the cooperative range test
 constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks of >= 512 octants = 4M octants
 constexpr int kHeavyExtentDefault = 96;
 __device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)        // rects larger than this (pixels) are tested by a whole warp
 constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 
-template <int T> struct CullShared
+/// T = threads per CTA, R = work-queue entries held in shared memory between evaluation passes.
+template <int T, int R> struct CullShared
 {
     ViewConst vc;
     uint32_t pre[T + 1];   // exclusive scan of drawable counts of the current octant chunk
     uint32_t first[T];     // first drawable of each octant of the chunk | inside << 31
-    uint32_t ring[kRing];             // octants waiting for TestOctant / frustum survivors waiting for the occlusion test
-    uint32_t visWord[kRingGroups];    // one ballot word per group of 32 queued drawables
-    uint32_t groupOff[kRingGroups];
+    uint32_t ring[R];             // octants waiting for TestOctant / frustum survivors waiting for the occlusion test
+    uint32_t visWord[R / 32];    // one ballot word per group of 32 queued drawables
+    uint32_t groupOff[R / 32];
     uint32_t warpTot[T / 32];
     uint32_t wstack[T / 32][T >= 1024 ? kWStack / 2 : kWStack];
     uint4 heavy[kHeavyCap];           // (left | top << 16, right | bottom << 16, z, queue index | result bits << 30)
@@ -99,8 +99,8 @@ template <int T> __device__ __forceinline__ uint32_t block_rank(bool pred, uint3
 /// Stage A of an evaluation pass, one box per lane: project, answer small rects on the spot, park large rects in the CTA's heavy queue
 /// (tag = queue index | caller bits).  Returns the lane's answer; `parked` tells that the answer will come from stage B instead.
 /// If the queue is full the warp walks the box at once.  Every lane of the warp must call.
-template <int T> __device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
-    bool active, const float4& mn, const float4& mx, uint32_t tag, CullShared<T>& sh, bool& parked)
+template <int T, int R> __device__ __forceinline__ bool visible_stage_a(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips, bool useMips,
+    bool active, const float4& mn, const float4& mx, uint32_t tag, CullShared<T, R>& sh, bool& parked)
 {
     const int lane = threadIdx.x & 31;
     BoxRect r;
@@ -153,8 +153,8 @@ template <int T> __device__ __forceinline__ bool visible_stage_a(const BufGeom& 
 }
 
 /// Stage B: warps take parked boxes one at a time and walk them cooperatively.  `apply(tag, visible)` is run by lane 0.
-template <int T, class Apply> __device__ __forceinline__ void visible_stage_b(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips,
-    CullShared<T>& sh, Apply apply)
+template <int T, int R, class Apply> __device__ __forceinline__ void visible_stage_b(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips,
+    CullShared<T, R>& sh, Apply apply)
 {
     const int lane = threadIdx.x & 31;
     const uint32_t n = min(sh.heavyCount, (uint32_t)kHeavyCap);
@@ -193,11 +193,13 @@ __device__ int g_cullProfOn;
         }                                                                                     \
     } while (0)
 
-template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
+template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
     uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags)
 {
-    __shared__ CullShared<T> sh;
+    static_assert(R / 32 <= T && R % T == 0, "queue size must be a multiple of the block size and at most 32 entries per thread");
+    extern __shared__ __align__(16) unsigned char cullSmem[];
+    CullShared<T, R>& sh = *reinterpret_cast<CullShared<T, R>*>(cullSmem);
     const int v = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31;
     const bool profOn = g_cullProfOn != 0;
@@ -277,7 +279,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
             bool parked = false;
             if (occludedQuery)
             {
-                const bool vis = visible_stage_a<T>(g, vc.vp, depth, mips, useMips, res != OUTSIDE, mn, mx, (uint32_t)o | ((uint32_t)res << 30), sh, parked);
+                const bool vis = visible_stage_a<T, R>(g, vc.vp, depth, mips, useMips, res != OUTSIDE, mn, mx, (uint32_t)o | ((uint32_t)res << 30), sh, parked);
                 if (!vis)
                     res = OUTSIDE;
             }
@@ -289,7 +291,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
         }
         __syncthreads();
         if (sh.heavyCount)
-            visible_stage_b<T>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+            visible_stage_b<T, R>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
                 const int res = (int)(tag >> 30);
                 if (vis)
                 {
@@ -353,7 +355,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                 if (need)
                     sh.ring[pos + __popc(bal & ((1u << lane) - 1u))] = e;
             }
-            if (++sweeps == kRing / T) // the queue could be full after this many sweeps
+            if (++sweeps == R / T) // the queue could be full after this many sweeps
             {
                 CULL_PROF_MARK(1);
                 eval_octants();
@@ -424,7 +426,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                 }
             }
             bool parked = false;
-            if (visible_stage_a<T>(g, vc.vp, depth, mips, useMips, test, mn, mx, idx, sh, parked))
+            if (visible_stage_a<T, R>(g, vc.vp, depth, mips, useMips, test, mn, mx, idx, sh, parked))
                 vis = true;
             const uint32_t word = __ballot_sync(0xffffffffu, vis);
             if (lane == 0)
@@ -433,14 +435,14 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
         __syncthreads();
         if (sh.heavyCount)
         {
-            visible_stage_b<T>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
+            visible_stage_b<T, R>(g, depth, mips, sh, [&](uint32_t tag, bool vis) {
                 if (vis)
                     atomicOr(&sh.visWord[tag >> 5], 1u << (tag & 31u));
             });
             __syncthreads();
         }
         const uint32_t nGroups = (n + 31) >> 5;
-        // exclusive scan of the groups' popcounts (kRingGroups <= T)
+        // exclusive scan of the groups' popcounts (R / 32 <= T)
         uint32_t total;
         const uint32_t cnt = (uint32_t)tid < nGroups ? (uint32_t)__popc(sh.visWord[tid]) : 0u;
         const uint32_t off = block_exclusive_scan<T>(cnt, sh.warpTot, total);
@@ -567,7 +569,7 @@ template <int T, int MINB> __global__ void __launch_bounds__(T, MINB) k_cull_vie
                     sh.queryCount += tot;
                 }
                 __syncthreads();
-                if (sh.ringCount + T > kRing)
+                if (sh.ringCount + T > R)
                 {
                     CULL_PROF_MARK(4);
                     eval_drawables();
@@ -639,9 +641,20 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
     // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.67 ms; 4096 views 7.0 ms vs 9.2 ms).
     if (numViews > kCullSmallBatch)
-        k_cull_views<512, 3><<<numViews, 512, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, zRange, flags);
+        k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
+            outCap, outCounts, zRange, flags);
     else
-        k_cull_views<1024, 1><<<numViews, 1024, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx, outCap, outCounts, zRange, flags);
+    {
+        // one CTA per SM has the whole shared memory: a 16K-entry queue means one evaluation pass per ~16K survivors instead of one per 1-2K
+        static bool attrSet = false;
+        if (!attrSet)
+        {
+            cudaFuncSetAttribute(k_cull_views<1024, 1, kCullBigRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<1024, kCullBigRing>));
+            attrSet = true;
+        }
+        k_cull_views<1024, 1, kCullBigRing><<<numViews, 1024, sizeof(CullShared<1024, kCullBigRing>), s>>>(sc, g, views, depth, mips, mipsValid, octState,
+            stage, outIdx, outCap, outCounts, zRange, flags);
+    }
 }
 
 /// World boxes of drawables that moved without leaving their octant: rewrite xyz of their two float4 records, keep the meta words.
