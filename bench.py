@@ -42,6 +42,7 @@ def parse():
     ap.add_argument("--drawables", type=int, default=1_000_000)
     ap.add_argument("--occluders", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--inflight", type=int, default=2, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
     return ap.parse_args()
 
@@ -59,7 +60,9 @@ def config_dict(args, world):
                         "occluded octree query + visibility predicate" % (args.views, args.drawables, args.occluders, WIDTH, HEIGHT),
             "views": args.views, "drawables": args.drawables, "occluders": args.occluders, "buffer": [WIDTH, HEIGHT],
             "sharding": "views interleaved over %d rank(s)" % world,
-            "cache": "L2 flushed between timed steps (256 MiB write); per-step working set (depth+mips+triangles) also exceeds L2"}
+            "pipelining": "%d batch slots on separate streams; step k runs in slot k %% %d" % (max(1, args.inflight), max(1, args.inflight)),
+            "cache": "L2 flushed before every timed step (256 MiB write, inside the timed region); per-step working set (depth+mips+triangles) "
+                     "also exceeds L2"}
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -289,63 +292,111 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 
     # device-resident leg ----------------------------------------------------------------------------------------------------
+    # `inflight` result slots, each a u3d_batch on its own stream: step k runs in slot k % inflight, so the tail of one step's kernels (a few
+    # CTAs left on a mostly idle GPU) and, for N>1, its NCCL gather overlap the next step's kernels.  All K steps start after the start event
+    # and finish before the end event.
+    inflight = max(1, args.inflight)
+    do_gather = world > 1 and not os.environ.get("U3D_BENCH_NO_GATHER")  # diagnostic only: a run without the gather is not a bench value
     batch.set_views(packed, stream)
-    gather = None
-    packed_views = {}
+    slots = [dict(batch=batch, tstream=tstream)]
+    for _ in range(inflight - 1):
+        st_i = torch.cuda.Stream()
+        b_i = capi.Batch(ctx, gscene, occ, WIDTH, HEIGHT, V, out_cap, tri_pool=V * 14000)
+        b_i.set_views(packed, st_i.cuda_stream)
+        slots.append(dict(batch=b_i, tstream=st_i))
+    for sl in slots:
+        sl["stream"] = sl["tstream"].cuda_stream
+        sl["done"] = None
+        sl["batch"].set_pipelined(inflight > 1)
+    comm = None
     if world > 1:
         from urho3d_b200 import sharding
-        # size the gather buffers from one untimed pass (no host synchronisation is needed inside the timed steps)
+        # The gather buffers are sized from one untimed pass, so no host synchronisation is needed inside the timed steps.
         batch.run(capi.STAGE_VISIBLE, stream)
         c0 = batch.counts(stream)
         cap_t = torch.tensor([int(c0[:, 1].sum() * 1.25) + 4096], dtype=torch.int64, device="cuda")
         dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
-        cptr, _, _ = batch.device_results()
-        counts_dev = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")
-        gather = sharding.RawGather(args.views, world, min(int(cap_t.item()), V * out_cap), torch.device("cuda", local_rank))
+        cap = min(int(cap_t.item()), V * out_cap)
+        comm = torch.cuda.Stream()  # one stream for every slot's collectives: all ranks issue them in the same order
+        for sl in slots:
+            cptr, _, _ = sl["batch"].device_results()
+            sl["counts"] = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")
+            sl["batch"].run(capi.STAGE_VISIBLE, sl["stream"])
+            _, pptr = sl["batch"].pack_device(sl["stream"])  # allocates the packed buffer once; its address is stable afterwards
+            sl["packed"] = torch.as_tensor(_DevArray(pptr, (V * out_cap,)), device="cuda")
+            sl["gather"] = sharding.RawGather(args.views, world, cap, torch.device("cuda", local_rank))
+    torch.cuda.synchronize()
 
-    def step_device():
-        batch.run(capi.STAGE_VISIBLE, stream)
-        if world > 1:
-            # the only exchange of the path: every rank's per-view counts and packed visible sets, all-gathered over NCCL
-            _, pptr = batch.pack_device(stream)
-            if pptr not in packed_views:  # the device buffer is allocated once; wrap it once
-                packed_views[pptr] = torch.as_tensor(_DevArray(pptr, (V * out_cap,)), device="cuda")
-            gather.run(counts_dev, packed_views[pptr])
-            return 2
-        return 0
+    def step_device(k):
+        sl = slots[k % len(slots)]
+        ts = sl["tstream"]
+        with torch.cuda.stream(ts):
+            if sl["done"] is not None:
+                ts.wait_event(sl["done"])  # this slot's previous gather has read its buffers
+            flush.zero_()
+            sl["batch"].run(capi.STAGE_VISIBLE, sl["stream"])
+            extra = 0
+            if do_gather:
+                # the only exchange of the path: every rank's per-view counts and packed visible sets, all-gathered over NCCL
+                sl["batch"].pack_device(sl["stream"])
+                ready = torch.cuda.Event()
+                ready.record(ts)
+                comm.wait_event(ready)
+                with torch.cuda.stream(comm):
+                    sl["gather"].run(sl["counts"], sl["packed"])
+                    sl["done"] = torch.cuda.Event()
+                    sl["done"].record(comm)
+                extra = 2
+        return sl["batch"].last_launches() + extra
+
+    def fork(ev):
+        for sl in slots[1:]:
+            sl["tstream"].wait_event(ev)
+
+    def join():
+        # the main stream waits for everything the slots (and the gathers) were given
+        for sl in slots:
+            if sl["done"] is not None:
+                tstream.wait_event(sl["done"])
+            if sl["tstream"] is not tstream:
+                e = torch.cuda.Event()
+                e.record(sl["tstream"])
+                tstream.wait_event(e)
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     t_clock0 = time.perf_counter()
-    for _ in range(args.warmup):
-        flush.zero_()
-        step_device()
+    for k in range(max(args.warmup, len(slots))):
+        step_device(k)
+    join()
     torch.cuda.synchronize()
     counts = batch.counts(stream)  # also checks the overflow flags
     stats = batch.tri_stats(stream)
-    if gather is not None:
-        assert not gather.overflowed(), "gather buffers too small"
-        g_counts, _, _ = gather.reorder()
-        assert np.array_equal(g_counts[rank::world].cpu().numpy().astype(np.uint32), counts), "gathered counts disagree with the local ones"
+    for sl in slots[1:]:
+        assert np.array_equal(sl["batch"].counts(sl["stream"]), counts), "slots disagree"
+    if do_gather:
+        for sl in slots:
+            assert not sl["gather"].overflowed(), "gather buffers too small"
+            g_counts, _, _ = sl["gather"].reorder()
+            assert np.array_equal(g_counts[rank::world].cpu().numpy().astype(np.uint32), counts), "gathered counts disagree with the local ones"
 
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
-    starts = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
-    ends = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    # One event pair around the K steps.  The L2 flush before each step (a 256 MiB write, ~0.04 ms) is inside the timed region.
+    ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
+    ev_start.record(tstream)
+    fork(ev_start)
     for k in range(args.steps):
-        flush.zero_()
-        starts[k].record()
-        extra = step_device()
-        ends[k].record()
-        launches += batch.last_launches() + extra
+        launches += step_device(k)
+    join()
+    ev_end.record(tstream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     t_end = time.perf_counter()
-    step_ms = [s.elapsed_time(e) for s, e in zip(starts, ends)]
-    total_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device="cuda")
+    total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
@@ -360,27 +411,55 @@ def main():
             phase_ms.setdefault(name, []).append(ms)
     phase_ms = {k: statistics.median(v) for k, v in phase_ms.items()}
 
-    # e2e leg: one C-ABI call per step, host buffers in (views) and out (counts + packed visible ids) ---------------------------------
-    h_counts = torch.empty((V, 2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    h_offsets = torch.empty(V + 1, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    h_ids = torch.empty(int(counts[:, 1].sum() * 1.25) + 1024, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
-    h_views = torch.empty(packed.nbytes, dtype=torch.uint8).pin_memory().numpy()
-    h_views[:] = packed.view(np.uint8).reshape(-1)
-    h_packed = h_views.view(capi.VIEW_DTYPE)
-    for _ in range(2):
-        batch.cull_views(h_packed, capi.STAGE_VISIBLE, stream, h_counts, h_offsets, h_ids)
+    # e2e leg: one C-ABI call per step, host buffers in (views) and out (counts + packed visible ids).  One host thread per slot, as an engine
+    # with worker threads would submit batches: each call is synchronous (returns with the results in host memory), calls of different slots
+    # overlap on the device.  Wall clock over all K calls. ------------------------------------------------------------------------------
+    import threading
+    n_ids = int(counts[:, 1].sum() * 1.25) + 1024
+    for sl in slots:
+        sl["h_counts"] = torch.empty((V, 2), dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        sl["h_offsets"] = torch.empty(V + 1, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        sl["h_ids"] = torch.empty(n_ids, dtype=torch.int32).pin_memory().numpy().view(np.uint32)
+        h_views = torch.empty(packed.nbytes, dtype=torch.uint8).pin_memory().numpy()
+        h_views[:] = packed.view(np.uint8).reshape(-1)
+        sl["h_packed"] = h_views.view(capi.VIEW_DTYPE)
+
+    def e2e_call(sl):
+        sl["batch"].cull_views(sl["h_packed"], capi.STAGE_VISIBLE, sl["stream"], sl["h_counts"], sl["h_offsets"], sl["h_ids"])
+
+    def e2e_worker(t, steps, errs):
+        try:
+            torch.cuda.set_device(local_rank)
+            for k in range(t, steps, len(slots)):
+                e2e_call(slots[t])
+        except Exception as e:  # noqa: BLE001 - re-raised on the main thread
+            errs.append(e)
+
+    def e2e_run(steps):
+        errs = []
+        threads = [threading.Thread(target=e2e_worker, args=(t, steps, errs)) for t in range(len(slots))]
+        t0 = time.perf_counter()
+        for th in threads:
+            th.start()
+        for th in threads:
+            th.join()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if errs:
+            raise errs[0]
+        return dt
+
+    e2e_run(2 * len(slots))
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        batch.cull_views(h_packed, capi.STAGE_VISIBLE, stream, h_counts, h_offsets, h_ids)
-    torch.cuda.synchronize()
-    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    e2e_s = torch.tensor([e2e_run(args.steps)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_s.item())
-    assert np.array_equal(h_counts, counts), "e2e leg disagrees with the device-resident leg"
+    h_counts, h_offsets = slots[0]["h_counts"], slots[0]["h_offsets"]
+    for sl in slots:
+        assert np.array_equal(sl["h_counts"], counts), "e2e leg disagrees with the device-resident leg"
     if sampler:
         # keep the same load on for >= 1.5 s in total so that nvidia-smi (100 ms period) gets enough samples under load
         while time.perf_counter() - t_clock0 < 1.5:

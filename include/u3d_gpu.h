@@ -230,6 +230,10 @@ U3D_API int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids
 U3D_API int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void** packed_dev);
 /* Kernel launches issued by the last u3d_batch_run / run_part on this batch. */
 U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
+/* Hint that the caller keeps several batches in flight on different streams (e.g. one per worker thread, or frame k+1 submitted while frame k
+ * drains).  Results are unchanged; kernels pick the launch shape with the best aggregate throughput instead of the lowest latency of a lone
+ * batch.  No reference counterpart (the reference runs one view at a time on the main thread, View.cpp:779-809). */
+U3D_API int u3d_batch_set_pipelined(u3d_batch* b, int on);
 
 #ifdef __cplusplus
 }

@@ -535,3 +535,47 @@ def test_sphere_box_point_queries(gpu_ctx):
         assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.query(shape, params, None))
     for o in (batch, gs, tree):
         o.close()
+
+
+def test_pipelined_batches_from_two_threads(gpu_ctx):
+    """Two batches over one scene, each driven by its own host thread on its own stream with the pipelined hint set: every call returns the
+    same visible sets as the oracle, whatever the overlap on the device."""
+    import threading
+
+    import torch
+
+    w = h = 128
+    nviews = 48
+    sc = helpers.small_scene(n=12000, k=120, extent=100.0, seed=91)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    sets = [scenes.agent_cameras(nviews, 100.0, w, h, seed=5), helpers.stress_views(100.0, w, h, nviews, seed=6)]
+    want = [[oracle_view(sc, otree, ob, v)[2] for v in vs] for vs in sets]
+    batches = [capi.Batch(gpu_ctx, gs, occ, w, h, nviews, sc.n) for _ in sets]
+    streams = [torch.cuda.Stream() for _ in sets]
+    errs = []
+
+    def worker(t):
+        try:
+            batches[t].set_pipelined(True)
+            packed = capi.pack_views(sets[t])
+            for _ in range(6):
+                counts, offsets, ids = batches[t].cull_views(packed, capi.STAGE_VISIBLE, streams[t].cuda_stream)
+                for i in range(nviews):
+                    assert counts[i, 1] == len(want[t][i])
+                    assert np.array_equal(ids[offsets[i]:offsets[i + 1]], want[t][i]), "thread %d view %d" % (t, i)
+        except BaseException as e:  # noqa: BLE001 - re-raised below
+            errs.append(e)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(len(sets))]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    if errs:
+        raise errs[0]
+    for o in (*batches, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

@@ -109,6 +109,7 @@ SIGNATURES = {
     "u3d_batch_device_results": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), _u32]),
     "u3d_batch_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
+    "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
 }
 
 _lib = None
@@ -532,6 +533,10 @@ class Batch:
 
     def last_launches(self):
         return lib().u3d_batch_last_launches(self.h)
+
+    def set_pipelined(self, on=True):
+        """Several batches in flight on different streams: prefer aggregate throughput over single-batch latency (results unchanged)."""
+        _chk(lib().u3d_batch_set_pipelined(self.h, 1 if on else 0))
 
     def close(self):
         if self.h:

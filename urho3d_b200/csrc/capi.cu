@@ -322,6 +322,7 @@ struct u3d_batch
     uint32_t lastLaunches{};
     bool hasBuffers{};
     cudaEvent_t ev[U3D_NUM_PHASES + 1]{};
+    bool pipelined{};  // u3d_batch_set_pipelined
     bool timed{};      // record an event after every phase of the next run
     bool haveEvents{};
     ~u3d_batch()
@@ -1303,7 +1304,7 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
     CU_CHECK(cudaMemcpyAsync(holder->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(holder->vs.flags.p, 0, 4, st));
     launch_cull(scene->dev, g, holder->vs.views.p, 1, useOb ? ob->vs.depth.p : nullptr, useOb ? ob->vs.mips.p : nullptr,
-        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr, holder->vs.flags.p, st);
+        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr, holder->vs.flags.p, false, st);
     CU_CHECK(cudaGetLastError());
     uint32_t counts[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(counts, holder->outCounts.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1499,7 +1500,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
     CU_CHECK(mark(6));
     if (part != 1)
     {
-        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p, vs.flags.p, st);
+        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p, vs.flags.p, b->pipelined, st);
         b->lastLaunches += 1;
         CU_CHECK(cudaGetLastError());
     }
@@ -1809,5 +1810,13 @@ int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids_dev, ui
 }
 
 uint32_t u3d_batch_last_launches(const u3d_batch* b) { return b ? b->lastLaunches : 0; }
+
+int u3d_batch_set_pipelined(u3d_batch* b, int on)
+{
+    if (!b)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_pipelined: NULL argument");
+    b->pipelined = on != 0;
+    return U3D_OK;
+}
 
 } // extern "C"

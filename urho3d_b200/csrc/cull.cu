@@ -633,14 +633,16 @@ __global__ void k_is_visible(BufGeom g, const ViewConst* __restrict__ view, cons
 }
 
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
-    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, cudaStream_t s)
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, bool pipelined, cudaStream_t s)
 {
     if (!numViews)
         return;
     cudaMemsetAsync(octState, 0, (size_t)numViews * sc.numOctants, s); // octants the sweeps skip must read as culled
     // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
-    // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.67 ms; 4096 views 7.0 ms vs 9.2 ms).
-    if (numViews > kCullSmallBatch)
+    // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.46 ms; 4096 views 6.4 ms vs 9.2 ms).
+    // When the caller keeps several batches in flight (`pipelined`) other launches fill that wave, and the first shape wins again
+    // (3 x 512 views in flight: 1.57 -> 1.35 ms per batch).
+    if (numViews > kCullSmallBatch || pipelined)
         k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
             outCap, outCounts, zRange, flags);
     else

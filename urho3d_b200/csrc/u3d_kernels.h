@@ -95,7 +95,8 @@ void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mi
 /// Octree query (+ optional CheckVisibility predicate) for every view.  octState: numViews x numOctants bytes of scratch.
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
-    float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags, cudaStream_t s);
+    float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags,
+    bool pipelined /* other launches share the GPU: prefer the shape with the best aggregate throughput */, cudaStream_t s);
 
 void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s);
 
