@@ -42,7 +42,9 @@ def parse():
     ap.add_argument("--drawables", type=int, default=1_000_000)
     ap.add_argument("--occluders", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=2, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
+    ap.add_argument("--inflight", type=int, default=4, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
+    ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
+                    help="N>1 result exchange: p2p = our fused pack+store kernel over NVLink peer memory (u3d_gather_*), nccl = library all-gather")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
     return ap.parse_args()
 
@@ -60,6 +62,8 @@ def config_dict(args, world):
                         "occluded octree query + visibility predicate" % (args.views, args.drawables, args.occluders, WIDTH, HEIGHT),
             "views": args.views, "drawables": args.drawables, "occluders": args.occluders, "buffer": [WIDTH, HEIGHT],
             "sharding": "views interleaved over %d rank(s)" % world,
+            "exchange": ("none (1 rank)" if world == 1 else "fused pack + NVLink peer-memory stores + flags (u3d_batch_push_results), every step"
+                         if args.gather == "p2p" else "NCCL all_gather_into_tensor of counts and packed ids, every step"),
             "pipelining": "%d batch slots on separate streams; step k runs in slot k %% %d" % (max(1, args.inflight), max(1, args.inflight)),
             "cache": "L2 flushed before every timed step (256 MiB write, inside the timed region); per-step working set (depth+mips+triangles) "
                      "also exceeds L2"}
@@ -276,6 +280,9 @@ def main():
     V = len(my_views)
 
     ctx = capi.Context(local_rank)
+    for kv in filter(None, os.environ.get("U3D_DEBUG_OPTS", "").split(",")):  # tuning sweeps only, e.g. "heavy_extent=64"
+        name, val = kv.split("=")
+        capi.debug_set_option(name, int(val))
     tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
     tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
     gscene = capi.GpuScene(ctx, octree=tree)
@@ -318,7 +325,16 @@ def main():
         dist.all_reduce(cap_t, op=dist.ReduceOp.MAX)
         cap = min(int(cap_t.item()), V * out_cap)
         comm = torch.cuda.Stream()  # one stream for every slot's collectives: all ranks issue them in the same order
+        per = (args.views + world - 1) // world
         for sl in slots:
+            if args.gather == "p2p":
+                # receive block of this slot on every rank; the 64-byte IPC handles are exchanged once, outside the timed region
+                g = capi.Gather(ctx, world, rank, per, cap)
+                handles = [None] * world
+                dist.all_gather_object(handles, g.export())
+                g.connect(handles)
+                sl["gather"] = g
+                continue
             cptr, _, _ = sl["batch"].device_results()
             sl["counts"] = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")
             sl["batch"].run(capi.STAGE_VISIBLE, sl["stream"])
@@ -336,8 +352,21 @@ def main():
             flush.zero_()
             sl["batch"].run(capi.STAGE_VISIBLE, sl["stream"])
             extra = 0
-            if do_gather:
-                # the only exchange of the path: every rank's per-view counts and packed visible sets, all-gathered over NCCL
+            if do_gather and args.gather == "p2p":
+                # the only exchange of the path: this rank's counts and packed visible sets are stored into every rank's receive
+                # block by our own kernel (pack + NVLink peer stores + arrival flag); the comm stream waits for all ranks' flags and releases
+                g = sl["gather"]
+                g.push(sl["batch"], sl["stream"])
+                pushed = torch.cuda.Event()
+                pushed.record(ts)
+                comm.wait_event(pushed)  # program order only: the flags carry the real dependency
+                g.wait(comm.cuda_stream)
+                g.release(comm.cuda_stream)
+                sl["done"] = torch.cuda.Event()
+                sl["done"].record(comm)
+                extra = 5
+            elif do_gather:
+                # library baseline: every rank's per-view counts and packed visible sets, all-gathered over NCCL
                 sl["batch"].pack_device(sl["stream"])
                 ready = torch.cuda.Event()
                 ready.record(ts)
@@ -373,7 +402,19 @@ def main():
     stats = batch.tri_stats(stream)
     for sl in slots[1:]:
         assert np.array_equal(sl["batch"].counts(sl["stream"]), counts), "slots disagree"
-    if do_gather:
+    if do_gather and args.gather == "p2p":
+        all_counts = [torch.zeros((V, 2), dtype=torch.int64, device="cuda") for _ in range(world)] if V * world == args.views else None
+        if all_counts is not None:
+            dist.all_gather(all_counts, torch.from_numpy(counts.astype(np.int64)).cuda())
+        for sl in slots:
+            g_counts, g_offsets, g_ids = sl["gather"].read(comm.cuda_stream)  # raises on overflow / timeout
+            assert np.array_equal(g_counts[rank, :V], counts), "exchanged counts disagree with the local ones"
+            if all_counts is not None:  # every other rank's counts arrived as that rank computed them
+                for r in range(world):
+                    assert np.array_equal(g_counts[r, :V], all_counts[r].cpu().numpy().astype(np.uint32)), "rank %d counts differ" % r
+            off, ids_local = sl["batch"].packed(sl["stream"], capacity=int(counts[:, 1].sum()))
+            assert np.array_equal(g_offsets[rank, :V + 1], off) and np.array_equal(g_ids[rank, :off[-1]], ids_local), "exchanged ids differ"
+    elif do_gather:
         for sl in slots:
             assert not sl["gather"].overflowed(), "gather buffers too small"
             g_counts, _, _ = sl["gather"].reorder()

@@ -235,6 +235,42 @@ U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
  * batch.  No reference counterpart (the reference runs one view at a time on the main thread, View.cpp:779-809). */
 U3D_API int u3d_batch_set_pipelined(u3d_batch* b, int on);
 
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU result exchange.  Views shard over the GPUs of one box, one process (rank) per GPU, the scene is replicated and
+ * raster / cull need no communication; the only exchange is the gather of per-view counts and visible sets.  No reference counterpart
+ * (the reference renders every view on one CPU, Renderer.cpp:673-686).  Instead of handing packed lists to a library all-gather,
+ * u3d_batch_push_results packs the emitted ids of the batch and stores them, in the same kernel, straight into the receive block of
+ * EVERY rank through NVLink peer memory, then raises a per-rank arrival flag; consumers wait on the flags on their own stream.  No host
+ * synchronisation anywhere.  All ranks must call push / wait / release the same number of times, in the same order.
+ *
+ * Receive block of a rank (device pointers from u3d_gather_buffers), identical on every rank once an epoch has arrived:
+ *   counts  [world][views_per_rank][2]   uint32   (query result size, emitted count) of view slot s of rank r
+ *   offsets [world][views_per_rank + 1]  uint32   packed offset of each view inside its rank's ids region; [n] = total
+ *   ids     [world][ids_capacity]        uint32   packed emitted ids of rank r
+ * With interleaved sharding (view v on rank v % world, slot v / world) view v is found at counts[v % world][v / world]. */
+typedef struct u3d_gather u3d_gather;
+#define U3D_IPC_HANDLE_BYTES 64
+U3D_API int u3d_gather_create(u3d_ctx* ctx, int world, int rank, uint32_t views_per_rank, uint64_t ids_capacity_per_rank, u3d_gather** out);
+U3D_API void u3d_gather_destroy(u3d_gather* g);
+/* Inter-process set-up: every rank exports a 64-byte handle of its block, the host exchanges them by any means (the Python host uses
+ * torch.distributed.all_gather_object) and hands all `world` handles, in rank order, to connect. */
+U3D_API int u3d_gather_export(u3d_gather* g, void* handle64);
+U3D_API int u3d_gather_connect(u3d_gather* g, const void* handles);
+/* Same for exchange objects that live in ONE process (one host thread per GPU, or several logical ranks on one GPU in tests). */
+U3D_API int u3d_gather_connect_local(u3d_gather* g, u3d_gather* const* all_ranks);
+/* Pack + store to every rank + signal, on `stream` after the batch's run (3 launches: release wait, offset scan, fused push). */
+U3D_API int u3d_batch_push_results(u3d_batch* b, u3d_gather* g, void* stream);
+/* Make `stream` wait (on the device) until every rank's results of the last pushed epoch have arrived in this rank's block. */
+U3D_API int u3d_gather_wait(u3d_gather* g, void* stream);
+/* Tell every producer, on `stream`, that this rank has consumed the epoch it last waited for (its regions may be overwritten). */
+U3D_API int u3d_gather_release(u3d_gather* g, void* stream);
+U3D_API int u3d_gather_buffers(u3d_gather* g, void** counts_dev, void** offsets_dev, void** ids_dev, uint32_t* views_per_rank,
+    uint64_t* ids_capacity_per_rank);
+/* Host copies of the receive block (any pointer may be NULL); synchronises `stream` and reports like u3d_gather_status. */
+U3D_API int u3d_gather_read(u3d_gather* g, uint32_t* counts, uint32_t* offsets, uint32_t* ids, void* stream);
+/* Synchronises `stream`; -U3D_ERR_CAPACITY if some rank's ids region overflowed, -U3D_ERR_CUDA if a wait timed out (a peer died). */
+U3D_API int u3d_gather_status(u3d_gather* g, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -579,3 +579,65 @@ def test_pipelined_batches_from_two_threads(gpu_ctx):
     for o in (*batches, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [1, 2, 3])
+def test_peer_memory_result_exchange(gpu_ctx, world):
+    """The multi-GPU exchange (u3d_gather_*: fused pack + stores into every rank's receive block + arrival flags) with `world` logical ranks
+    living in this process on one device: after push / wait every rank's block holds every rank's counts, packed offsets and visible ids,
+    equal to the oracle's sets in global view order; repeated epochs (with release) and a too-small ids region behave as documented."""
+    import torch
+
+    w = h = 128
+    nviews = 31  # not a multiple of world: the last rank slots stay short
+    sc = helpers.small_scene(n=9000, k=100, extent=100.0, seed=17)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = scenes.agent_cameras(nviews, 100.0, w, h, seed=8)
+    want = [oracle_view(sc, otree, ob, v)[2] for v in views]
+    per = (nviews + world - 1) // world
+    from urho3d_b200 import sharding
+    shards = [sharding.shard_views(nviews, r, world) for r in range(world)]
+    batches, gathers, streams = [], [], []
+    cap = sum(len(x) for x in want) + 16
+    for r in range(world):
+        b = capi.Batch(gpu_ctx, gs, occ, w, h, per, sc.n)
+        b.set_views(capi.pack_views([views[i] for i in shards[r]]))
+        batches.append(b)
+        gathers.append(capi.Gather(gpu_ctx, world, r, per, cap))
+        streams.append(torch.cuda.Stream())
+    for g in gathers:
+        g.connect_local(gathers)
+    for epoch in range(3):
+        for r in range(world):
+            batches[r].run(capi.STAGE_VISIBLE, streams[r].cuda_stream)
+            gathers[r].push(batches[r], streams[r].cuda_stream)
+        for r in range(world):
+            gathers[r].wait(streams[r].cuda_stream)
+        for r in range(world):
+            counts, offsets, ids = gathers[r].read(streams[r].cuda_stream)
+            for v in range(nviews):
+                src, slot = v % world, v // world
+                assert counts[src, slot, 1] == len(want[v])
+                o = offsets[src, slot]
+                assert np.array_equal(ids[src, o:o + len(want[v])], want[v]), "epoch %d rank %d view %d" % (epoch, r, v)
+            assert offsets[0, len(shards[0])] == sum(len(want[v]) for v in shards[0])
+        for r in range(world):
+            gathers[r].release(streams[r].cuda_stream)
+    # capacity: a region that cannot hold a rank's ids is reported, not silently truncated
+    small = [capi.Gather(gpu_ctx, world, r, per, 8) for r in range(world)]
+    for g in small:
+        g.connect_local(small)
+    for r in range(world):
+        small[r].push(batches[r], streams[r].cuda_stream)
+    for r in range(world):
+        small[r].wait(streams[r].cuda_stream)
+    with pytest.raises(capi.U3DError) as e:
+        small[0].status(streams[0].cuda_stream)
+    assert e.value.code == 4
+    for o in (*small, *gathers, *batches, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

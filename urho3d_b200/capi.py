@@ -110,6 +110,17 @@ SIGNATURES = {
     "u3d_batch_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
     "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
+    "u3d_gather_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
+    "u3d_gather_destroy": (None, [_vp]),
+    "u3d_gather_export": (C.c_int, [_vp, _vp]),
+    "u3d_gather_connect": (C.c_int, [_vp, _vp]),
+    "u3d_gather_connect_local": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "u3d_batch_push_results": (C.c_int, [_vp, _vp, _vp]),
+    "u3d_gather_wait": (C.c_int, [_vp, _vp]),
+    "u3d_gather_release": (C.c_int, [_vp, _vp]),
+    "u3d_gather_buffers": (C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp), C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)]),
+    "u3d_gather_read": (C.c_int, [_vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), _vp]),
+    "u3d_gather_status": (C.c_int, [_vp, _vp]),
 }
 
 _lib = None
@@ -541,4 +552,67 @@ class Batch:
     def close(self):
         if self.h:
             lib().u3d_batch_destroy(self.h)
+            self.h = None
+
+
+class Gather:
+    """Result exchange of one batch slot over NVLink peer memory (u3d_gather_*): every rank's packed visible sets and counts land in every
+    rank's receive block, written by the producers' own kernel."""
+
+    IPC_HANDLE_BYTES = 64
+
+    def __init__(self, ctx, world, rank, views_per_rank, ids_capacity_per_rank):
+        h = _vp()
+        _chk(lib().u3d_gather_create(ctx.h, world, rank, views_per_rank, ids_capacity_per_rank, C.byref(h)))
+        self.h = h
+        self.ctx = ctx
+        self.world, self.rank = world, rank
+        self.per, self.cap = max(int(views_per_rank), 1), max(int(ids_capacity_per_rank), 1)
+
+    def export(self):
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        _chk(lib().u3d_gather_export(self.h, C.cast(buf, _vp)))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: the export() bytes of every rank, in rank order (inter-process, CUDA IPC)."""
+        blob = b"".join(handles)
+        assert len(blob) == self.world * self.IPC_HANDLE_BYTES
+        buf = C.create_string_buffer(blob, len(blob))
+        _chk(lib().u3d_gather_connect(self.h, C.cast(buf, _vp)))
+
+    def connect_local(self, gathers):
+        """gathers: the Gather objects of every rank, in rank order, all living in this process."""
+        arr = (_vp * self.world)(*[g.h for g in gathers])
+        _chk(lib().u3d_gather_connect_local(self.h, arr))
+
+    def push(self, batch, stream=None):
+        _chk(lib().u3d_batch_push_results(batch.h, self.h, stream))
+
+    def wait(self, stream=None):
+        _chk(lib().u3d_gather_wait(self.h, stream))
+
+    def release(self, stream=None):
+        _chk(lib().u3d_gather_release(self.h, stream))
+
+    def status(self, stream=None):
+        _chk(lib().u3d_gather_status(self.h, stream))
+
+    def device_buffers(self):
+        """Device pointers (counts [world][per][2], offsets [world][per + 1], ids [world][cap])."""
+        c, o, i = _vp(), _vp(), _vp()
+        _chk(lib().u3d_gather_buffers(self.h, C.byref(c), C.byref(o), C.byref(i), None, None))
+        return c.value, o.value, i.value
+
+    def read(self, stream=None, ids=True):
+        """Host copies of the receive block (synchronises): counts [world, per, 2], offsets [world, per + 1], ids [world, cap]."""
+        c = np.zeros((self.world, self.per, 2), np.uint32)
+        o = np.zeros((self.world, self.per + 1), np.uint32)
+        i = np.zeros((self.world, self.cap), np.uint32) if ids else None
+        _chk(lib().u3d_gather_read(self.h, _p(c, _u32), _p(o, _u32), _p(i, _u32), stream))
+        return c, o, i
+
+    def close(self):
+        if self.h:
+            lib().u3d_gather_destroy(self.h)
             self.h = None

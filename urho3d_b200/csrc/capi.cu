@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <map>
 #include <new>
 #include <string>
@@ -360,6 +361,11 @@ int u3d_debug_set_option(const char* name, int value)
     if (name && std::strcmp(name, "heavy_extent") == 0)
     {
         cull_set_heavy_extent(value);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "walk_pool") == 0)
+    {
+        cull_set_walk_pool(value);
         return U3D_OK;
     }
     if (name && std::strcmp(name, "cull_prof") == 0)
@@ -1667,6 +1673,355 @@ int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void**
         *offsets_dev = b->packOffsets.p;
     if (packed_dev)
         *packed_dev = b->packed.p;
+    return U3D_OK;
+}
+
+} // extern "C" (result exchange kernels follow)
+
+// -----------------------------------------------------------------------------------------------------------------------------
+// Multi-GPU result exchange over NVLink peer memory (the one exchange step of the path).
+//
+// Every rank owns one symmetric block per exchange object:
+//   arrive[kMaxRanks] | ack[kMaxRanks] | status | pad | counts[world][per][2] | offsets[world][per + 1] | ids[world][cap]
+// A producer packs the visible ids of its views back to back and STORES them straight into region [rank] of every rank's block
+// (plain P2P stores through NVLink / NVSwitch; its own block is just another destination), then raises arrive[rank] = epoch in
+// every block with a system-scope release.  A consumer waits until all arrive[] flags of its own block reached the epoch, reads,
+// and acknowledges by writing ack[rank] = epoch into every producer's block; a producer does not overwrite epoch e before every
+// consumer has acknowledged it.  No NCCL call, no host synchronisation, one kernel for pack + transfer + signal.
+// -----------------------------------------------------------------------------------------------------------------------------
+namespace u3d
+{
+constexpr int kMaxRanks = 64;
+constexpr uint32_t kGatherTimeout = 1u, kGatherOverflow = 2u;
+
+struct GatherLayout
+{
+    uint32_t per;       // views per rank (upper bound)
+    uint64_t cap;       // packed ids per rank
+    int world;
+    __host__ __device__ size_t countsOff() const { return (size_t)(2 * kMaxRanks + 64) * 4; }
+    __host__ __device__ size_t offsetsOff() const { return countsOff() + (size_t)world * per * 8; }
+    __host__ __device__ size_t idsOff() const { return (offsetsOff() + (size_t)world * (per + 1) * 4 + 255) & ~(size_t)255; }
+    __host__ __device__ size_t bytes() const { return idsOff() + (size_t)world * cap * 4; }
+};
+
+struct PeerTable
+{
+    unsigned char* block[kMaxRanks];
+};
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v)
+{
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+/// One thread per rank: spin until flags[r] >= epoch (epochs only grow).  Gives up after `timeoutNs` and records it in *status
+/// instead of hanging the device when a peer died.
+__global__ void k_gather_wait(const uint32_t* __restrict__ flags, int world, uint32_t epoch, uint32_t* __restrict__ status, unsigned long long timeoutNs)
+{
+    const int r = threadIdx.x;
+    if (r >= world)
+        return;
+    const unsigned long long t0 = global_timer_ns();
+    while ((int)(ld_acquire_sys(flags + r) - epoch) < 0)
+    {
+        __nanosleep(200);
+        if (global_timer_ns() - t0 > timeoutNs)
+        {
+            atomicOr(status, kGatherTimeout);
+            return;
+        }
+    }
+}
+
+/// One thread per rank: flag[myRank] = epoch in every rank's block.
+__global__ void k_gather_signal(PeerTable peers, int world, int myRank, size_t flagOff, uint32_t epoch)
+{
+    const int r = threadIdx.x;
+    if (r >= world)
+        return;
+    __threadfence_system();
+    st_release_sys(reinterpret_cast<uint32_t*>(peers.block[r] + flagOff) + myRank, epoch);
+}
+
+/// Fused pack + all-gather: block v copies the emitted ids of view v to offset offsets[v] of region [myRank] in EVERY rank's block
+/// (coalesced 4-byte stores, 128 B per warp and destination), writes the view's counts and packed offset beside them, and the last
+/// block to finish raises the arrival flags.
+__global__ void __launch_bounds__(256) k_push_results(PeerTable peers, GatherLayout lay, int myRank, int numViews, const uint32_t* __restrict__ counts,
+    uint32_t outCap, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ids, uint32_t epoch, uint32_t* __restrict__ doneCounter)
+{
+    const int v = blockIdx.x;
+    const int world = lay.world;
+    const uint32_t n = min(counts[2 * v + 1], outCap);
+    const uint32_t off = offsets[v];
+    uint32_t m = n;
+    if ((uint64_t)off + n > lay.cap)
+    {
+        m = off < lay.cap ? (uint32_t)(lay.cap - off) : 0u;
+        if (threadIdx.x < world) // every consumer must learn that this rank's region is truncated
+            atomicOr(reinterpret_cast<uint32_t*>(peers.block[threadIdx.x]) + 2 * kMaxRanks, kGatherOverflow);
+    }
+    const uint32_t* src = ids + (size_t)v * outCap;
+    // each element is loaded once and stored to every destination
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+    {
+        const uint32_t x = src[i];
+        for (int r = 0; r < world; ++r)
+        {
+            const int dst = (myRank + r) % world; // start with the own block, spread the ranks over the links
+            reinterpret_cast<uint32_t*>(peers.block[dst] + lay.idsOff())[(size_t)myRank * lay.cap + off + i] = x;
+        }
+    }
+    if (threadIdx.x < world)
+    {
+        const int dst = threadIdx.x;
+        uint32_t* c = reinterpret_cast<uint32_t*>(peers.block[dst] + lay.countsOff()) + ((size_t)myRank * lay.per + v) * 2;
+        c[0] = counts[2 * v];
+        c[1] = counts[2 * v + 1];
+        uint32_t* o = reinterpret_cast<uint32_t*>(peers.block[dst] + lay.offsetsOff()) + (size_t)myRank * (lay.per + 1);
+        o[v] = off;
+        if (v == numViews - 1)
+            o[numViews] = offsets[numViews];
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ bool last;
+    if (threadIdx.x == 0)
+        last = atomicAdd(doneCounter, 1u) == (uint32_t)numViews - 1u;
+    __syncthreads();
+    if (last)
+    {
+        if (threadIdx.x == 0)
+            *doneCounter = 0;
+        if (threadIdx.x < world)
+        {
+            __threadfence_system();
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.block[threadIdx.x]) + myRank, epoch);
+        }
+    }
+}
+} // namespace u3d
+
+struct u3d_gather
+{
+    u3d_ctx* ctx{};
+    int world{}, rank{};
+    GatherLayout lay{};
+    unsigned char* block{};       // own block (cudaMalloc)
+    PeerTable peers{};
+    bool opened[kMaxRanks]{};     // peers.block[r] came from cudaIpcOpenMemHandle
+    DevBuf<uint32_t> doneCounter;
+    uint32_t epoch{};             // last epoch pushed by this rank
+    uint32_t waited{};            // last epoch waited for
+    bool connected{};
+    unsigned long long timeoutNs{5000000000ull};
+};
+
+extern "C"
+{
+
+int u3d_gather_create(u3d_ctx* ctx, int world, int rank, uint32_t views_per_rank, uint64_t ids_capacity_per_rank, u3d_gather** out)
+{
+    if (!ctx || !out || world < 1 || world > kMaxRanks || rank < 0 || rank >= world)
+        return fail(U3D_ERR_INVALID, "u3d_gather_create: bad argument");
+    CU_CHECK(cudaSetDevice(ctx->device));
+    std::unique_ptr<u3d_gather> g(new u3d_gather);
+    g->ctx = ctx;
+    g->world = world;
+    g->rank = rank;
+    g->lay.per = std::max<uint32_t>(views_per_rank, 1);
+    g->lay.cap = std::max<uint64_t>(ids_capacity_per_rank, 1);
+    g->lay.world = world;
+    CU_CHECK(cudaMalloc((void**)&g->block, g->lay.bytes()));
+    CU_CHECK(cudaMemset(g->block, 0, g->lay.idsOff()));
+    CU_CHECK(g->doneCounter.ensure(1));
+    CU_CHECK(cudaMemset(g->doneCounter.p, 0, 4));
+    CU_CHECK(cudaDeviceSynchronize());
+    g->peers.block[rank] = g->block;
+    *out = g.release();
+    return U3D_OK;
+}
+
+void u3d_gather_destroy(u3d_gather* g)
+{
+    if (!g)
+        return;
+    cudaSetDevice(g->ctx->device);
+    cudaDeviceSynchronize();
+    for (int r = 0; r < g->world; ++r)
+        if (g->opened[r])
+            cudaIpcCloseMemHandle(g->peers.block[r]);
+    cudaFree(g->block);
+    delete g;
+}
+
+int u3d_gather_export(u3d_gather* g, void* handle)
+{
+    if (!g || !handle)
+        return fail(U3D_ERR_INVALID, "u3d_gather_export: NULL argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == U3D_IPC_HANDLE_BYTES, "IPC handle size");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    cudaIpcMemHandle_t h;
+    CU_CHECK(cudaIpcGetMemHandle(&h, g->block));
+    std::memcpy(handle, &h, sizeof(h));
+    return U3D_OK;
+}
+
+int u3d_gather_connect(u3d_gather* g, const void* handles)
+{
+    if (!g || !handles)
+        return fail(U3D_ERR_INVALID, "u3d_gather_connect: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    for (int r = 0; r < g->world; ++r)
+    {
+        if (r == g->rank)
+            continue;
+        cudaIpcMemHandle_t h;
+        std::memcpy(&h, (const unsigned char*)handles + (size_t)r * sizeof(h), sizeof(h));
+        void* p = nullptr;
+        CU_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        g->peers.block[r] = (unsigned char*)p;
+        g->opened[r] = true;
+    }
+    g->connected = true;
+    return U3D_OK;
+}
+
+int u3d_gather_connect_local(u3d_gather* g, u3d_gather* const* all)
+{
+    if (!g || !all)
+        return fail(U3D_ERR_INVALID, "u3d_gather_connect_local: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    for (int r = 0; r < g->world; ++r)
+    {
+        if (!all[r] || all[r]->world != g->world || all[r]->rank != r || all[r]->lay.per != g->lay.per || all[r]->lay.cap != g->lay.cap)
+            return fail(U3D_ERR_INVALID, "u3d_gather_connect_local: exchange objects do not match");
+        if (all[r]->ctx->device != g->ctx->device)
+        {
+            int can = 0;
+            CU_CHECK(cudaDeviceCanAccessPeer(&can, g->ctx->device, all[r]->ctx->device));
+            if (!can)
+                return fail(U3D_ERR_UNSUPPORTED, "u3d_gather_connect_local: no peer access between the devices");
+            cudaError_t e = cudaDeviceEnablePeerAccess(all[r]->ctx->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                CU_CHECK(e);
+            cudaGetLastError();
+        }
+        g->peers.block[r] = all[r]->block;
+    }
+    g->connected = true;
+    return U3D_OK;
+}
+
+int u3d_batch_push_results(u3d_batch* b, u3d_gather* g, void* stream)
+{
+    if (!b || !g)
+        return fail(U3D_ERR_INVALID, "u3d_batch_push_results: NULL argument");
+    if (!g->connected && g->world > 1)
+        return fail(U3D_ERR_INVALID, "u3d_batch_push_results: exchange object is not connected");
+    if (b->numViews > g->lay.per)
+        return fail(U3D_ERR_CAPACITY, "u3d_batch_push_results: more views than the exchange object was created for");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    const int V = (int)b->numViews;
+    const uint32_t epoch = ++g->epoch;
+    // every consumer has released the previous contents of this rank's regions (ack[] of the own block)
+    if (epoch > 1)
+        k_gather_wait<<<1, kMaxRanks, 0, st>>>(reinterpret_cast<uint32_t*>(g->block) + kMaxRanks, g->world, epoch - 1, reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks,
+            g->timeoutNs);
+    if (V)
+    {
+        k_pack_offsets<<<1, 1024, 0, st>>>(V, b->outCounts.p, b->outCap, b->packOffsets.p);
+        k_push_results<<<V, 256, 0, st>>>(g->peers, g->lay, g->rank, V, b->outCounts.p, b->outCap, b->packOffsets.p, b->outIdx.p, epoch, g->doneCounter.p);
+    }
+    else
+        k_gather_signal<<<1, kMaxRanks, 0, st>>>(g->peers, g->world, g->rank, 0, epoch);
+    CU_CHECK(cudaGetLastError());
+    return U3D_OK;
+}
+
+int u3d_gather_wait(u3d_gather* g, void* stream)
+{
+    if (!g)
+        return fail(U3D_ERR_INVALID, "u3d_gather_wait: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    cudaStream_t st = g->ctx->pick(stream);
+    g->waited = g->epoch;
+    k_gather_wait<<<1, kMaxRanks, 0, st>>>(reinterpret_cast<uint32_t*>(g->block), g->world, g->waited, reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks, g->timeoutNs);
+    CU_CHECK(cudaGetLastError());
+    return U3D_OK;
+}
+
+int u3d_gather_release(u3d_gather* g, void* stream)
+{
+    if (!g)
+        return fail(U3D_ERR_INVALID, "u3d_gather_release: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    cudaStream_t st = g->ctx->pick(stream);
+    k_gather_signal<<<1, kMaxRanks, 0, st>>>(g->peers, g->world, g->rank, (size_t)kMaxRanks * 4, g->waited);
+    CU_CHECK(cudaGetLastError());
+    return U3D_OK;
+}
+
+int u3d_gather_buffers(u3d_gather* g, void** counts_dev, void** offsets_dev, void** ids_dev, uint32_t* views_per_rank, uint64_t* ids_capacity_per_rank)
+{
+    if (!g)
+        return fail(U3D_ERR_INVALID, "u3d_gather_buffers: NULL argument");
+    if (counts_dev)
+        *counts_dev = g->block + g->lay.countsOff();
+    if (offsets_dev)
+        *offsets_dev = g->block + g->lay.offsetsOff();
+    if (ids_dev)
+        *ids_dev = g->block + g->lay.idsOff();
+    if (views_per_rank)
+        *views_per_rank = g->lay.per;
+    if (ids_capacity_per_rank)
+        *ids_capacity_per_rank = g->lay.cap;
+    return U3D_OK;
+}
+
+int u3d_gather_read(u3d_gather* g, uint32_t* counts, uint32_t* offsets, uint32_t* ids, void* stream)
+{
+    if (!g)
+        return fail(U3D_ERR_INVALID, "u3d_gather_read: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    cudaStream_t st = g->ctx->pick(stream);
+    if (counts)
+        CU_CHECK(cudaMemcpyAsync(counts, g->block + g->lay.countsOff(), (size_t)g->world * g->lay.per * 8, cudaMemcpyDeviceToHost, st));
+    if (offsets)
+        CU_CHECK(cudaMemcpyAsync(offsets, g->block + g->lay.offsetsOff(), (size_t)g->world * (g->lay.per + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (ids)
+        CU_CHECK(cudaMemcpyAsync(ids, g->block + g->lay.idsOff(), (size_t)g->world * g->lay.cap * 4, cudaMemcpyDeviceToHost, st));
+    return u3d_gather_status(g, stream);
+}
+
+int u3d_gather_status(u3d_gather* g, void* stream)
+{
+    if (!g)
+        return fail(U3D_ERR_INVALID, "u3d_gather_status: NULL argument");
+    CU_CHECK(cudaSetDevice(g->ctx->device));
+    cudaStream_t st = g->ctx->pick(stream);
+    uint32_t status = 0;
+    CU_CHECK(cudaMemcpyAsync(&status, reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    if (status & kGatherTimeout)
+        return fail(U3D_ERR_CUDA, "result exchange timed out waiting for a peer rank");
+    if (status & kGatherOverflow)
+        return fail(U3D_ERR_CAPACITY, "result exchange: ids_capacity_per_rank too small for this batch");
     return U3D_OK;
 }
 

@@ -456,6 +456,153 @@ __device__ __forceinline__ bool range_visible_warp(const BufGeom& g, const int* 
     return false;
 }
 
+__device__ __forceinline__ uint32_t pack_pool(int box, int lv, int x, int y)
+{
+    return ((uint32_t)box << 27) | ((uint32_t)lv << 24) | ((uint32_t)x << 12) | (uint32_t)y;
+}
+
+/// Same predicate for up to 32 rects at once, one per lane (`need` = this lane has a rect to test): the pending texels of ALL the
+/// warp's boxes share one per-warp stack in shared memory and are classified 32 at a time, each lane fetching the rect of the box
+/// its texel belongs to by shuffle.  Most boxes are decided by their first <= 4 texels, a few have long border walks: pooled, both
+/// kinds run on dense warps, whereas one walk per lane leaves ~3/4 of the lanes idle.  Entries of boxes that were decided in the
+/// meantime are dropped when popped.  Children that do not fit on the stack are walked by their lane alone.
+/// Requires level < 8 and mip dimensions < 4096 (buffers up to 8192 x 8192).  Must be called by all 32 lanes.
+__device__ __forceinline__ bool range_visible_pool(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r,
+    bool need, uint32_t* wstack, int cap)
+{
+    const int lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t visMask = 0;
+    const uint32_t needMask = __ballot_sync(0xffffffffu, need);
+    if (!needMask)
+        return false;
+    int n = 0;
+    __syncwarp();
+    // top-level texels of every box (at most 2 x 2 unless the start level was clamped to the coarsest one)
+    {
+        const int top_lv = start_level(g, r);
+        const int sh0 = top_lv + 1;
+        const int rx0 = r.left >> sh0, ry0 = r.top >> sh0;
+        const int nx = (r.right >> sh0) - rx0 + 1, ny = (r.bottom >> sh0) - ry0 + 1;
+        const int kids = need ? nx * ny : 0;
+        int off = kids;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o)
+                off += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        off -= kids;
+        if (total <= cap)
+        {
+            if (kids)
+            {
+                int k = off;
+                for (int cy = 0; cy < ny; ++cy)
+                    for (int cx = 0; cx < nx; ++cx)
+                        wstack[k++] = pack_pool(lane, top_lv, rx0 + cx, ry0 + cy);
+            }
+            n = total;
+        }
+        else
+        {
+            // cannot happen with the queue sizes in use (32 boxes x <= 4 x 4 texels below the heavy threshold); walk per lane
+            const bool v = need && range_visible_thread(g, depth, mips, true, r);
+            return v;
+        }
+    }
+    __syncwarp();
+    while (n > 0)
+    {
+        const int take = min(n, 32);
+        n -= take;
+        uint32_t e = 0;
+        if (lane < take)
+            e = wstack[n + lane];
+        const int b = (int)(e >> 27);
+        BoxRect rb;
+        rb.left = __shfl_sync(0xffffffffu, r.left, b);
+        rb.top = __shfl_sync(0xffffffffu, r.top, b);
+        rb.right = __shfl_sync(0xffffffffu, r.right, b);
+        rb.bottom = __shfl_sync(0xffffffffu, r.bottom, b);
+        rb.z = __shfl_sync(0xffffffffu, r.z, b);
+        const int lv = (int)((e >> 24) & 7u), x = (int)((e >> 12) & 0xFFFu), y = (int)(e & 0xFFFu);
+        int c = 0;
+        if (lane < take && !((visMask >> b) & 1u))
+        {
+            c = classify_texel(g, mips, rb, lv, x, y);
+            if (c == 2 && lv == 0)
+                c = texel_pixels_visible(g, depth, rb, x, y) ? 1 : 0;
+        }
+        visMask |= __reduce_or_sync(0xffffffffu, c == 1 ? (1u << b) : 0u);
+        if ((visMask & needMask) == needMask)
+            break;
+        // children of the texels that must be refined (unless another texel of the same box has just proved it visible)
+        int x0 = 0, x1 = -1, y0 = 0, y1 = -1, cl = 0;
+        const bool refine = c == 2 && !((visMask >> b) & 1u);
+        if (refine)
+        {
+            cl = lv - 1;
+            const int sh = lv;
+            x0 = max(2 * x, rb.left >> sh);
+            x1 = min(min(2 * x + 1, rb.right >> sh), g.mw[cl] - 1);
+            y0 = max(2 * y, rb.top >> sh);
+            y1 = min(min(2 * y + 1, rb.bottom >> sh), g.mh[cl] - 1);
+        }
+        const int kids = refine ? (x1 - x0 + 1) * (y1 - y0 + 1) : 0;
+        const uint32_t anyKids = __ballot_sync(0xffffffffu, kids != 0);
+        if (!anyKids)
+            continue;
+        int off = kids;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, off, o);
+            if (lane >= o)
+                off += t;
+        }
+        off -= kids;
+        // lanes whose children fit (in prefix order) push them; the first lane that does not fit and all later ones walk alone
+        const bool fits = n + off + kids <= cap;
+        const uint32_t spillMask = __ballot_sync(0xffffffffu, kids != 0 && !fits);
+        __syncwarp();
+        if (kids && fits)
+        {
+            int k = n + off;
+            for (int cy = y0; cy <= y1; ++cy)
+                for (int cx = x0; cx <= x1; ++cx)
+                    wstack[k++] = pack_pool(b, cl, cx, cy);
+        }
+        if (!spillMask)
+            n += __shfl_sync(0xffffffffu, off + kids, 31);
+        else
+        {
+            // prefix order: every lane before the first spilling one fitted, so the kept entries are contiguous up to that lane's offset
+            const int firstSpill = __ffs(spillMask) - 1;
+            const int keptEnd = __shfl_sync(0xffffffffu, off, firstSpill);
+            // later lanes that "fit" by the test above wrote beyond keptEnd only if an earlier lane spilled: treat them as spilled too
+            bool lonely = false;
+            if (kids && lane >= firstSpill)
+            {
+                BoxRect sub = rb;
+                const int s = lv + 1;
+                sub.left = max(rb.left, x << s);
+                sub.top = max(rb.top, y << s);
+                sub.right = min(rb.right, ((x + 1) << s) - 1);
+                sub.bottom = min(rb.bottom, ((y + 1) << s) - 1);
+                lonely = range_visible_thread(g, depth, mips, true, sub);
+            }
+            visMask |= __reduce_or_sync(0xffffffffu, lonely ? (1u << b) : 0u);
+            n += keptEnd;
+        }
+        __syncwarp();
+    }
+    (void)lt;
+    return need && ((visMask >> lane) & 1u);
+}
+
 /// OcclusionBuffer::IsVisible, OB.cpp:336-456, evaluated by one thread.
 __device__ __forceinline__ bool ob_is_visible(const BufGeom& g, const float* vp, const int* __restrict__ depth, const int2* __restrict__ mips,
     bool useMips, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
