@@ -42,7 +42,7 @@ def parse():
     ap.add_argument("--drawables", type=int, default=1_000_000)
     ap.add_argument("--occluders", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=4, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
+    ap.add_argument("--inflight", type=int, default=6, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 result exchange: p2p = our fused pack+store kernel over NVLink peer memory (u3d_gather_*), nccl = library all-gather")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")

@@ -47,7 +47,10 @@ enum
     /* shape queries (OctreeQuery.h:72-138, OctreeQuery.cpp:32-96); their parameters travel in the 24 floats of `planes`: */
     U3D_QUERY_SPHERE = 3,        /* SphereOctreeQuery: planes[0..3] = centre.xyz, radius (Sphere::IsInside / IsInsideFast, Math/Sphere.cpp:136-256) */
     U3D_QUERY_BOX = 4,           /* BoxOctreeQuery:    planes[0..5] = min.xyz, max.xyz */
-    U3D_QUERY_POINT = 5          /* PointOctreeQuery:  planes[0..2] = point */
+    U3D_QUERY_POINT = 5,         /* PointOctreeQuery:  planes[0..2] = point */
+    /* ray queries (Octree.cpp:257-309): planes[0..6] = origin.xyz, direction.xyz, maxDistance; every octant incl. the root is tested */
+    U3D_QUERY_RAY = 6,           /* RayOctreeQuery walk of Octree::Raycast: drawables with Ray::HitDistance(worldBox) < maxDistance */
+    U3D_QUERY_RAY_CANDIDATES = 7 /* RaycastSingle's first pass (GetDrawablesOnlyInternal): all drawables of the octants the ray touches */
 };
 /* what is emitted */
 enum
@@ -187,6 +190,28 @@ U3D_API int u3d_ob_get_view_proj(const u3d_ob* ob, float out16[16]);          /*
  * *out_query_count = size of the query result, *out_count = number emitted for `stage` (may exceed capacity: -U3D_ERR_CAPACITY). */
 U3D_API int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uint32_t drawable_flags, uint32_t view_mask, int query_mode,
     int stage, uint32_t* out_ids, uint32_t capacity, uint32_t* out_query_count, uint32_t* out_count);
+
+/* ---- ray queries ----------------------------------------------------------------------------------------- */
+/* RayQueryResult (OctreeQuery.h:189-224) at RAY_AABB level, i.e. what Drawable::ProcessRayQuery fills in (Drawable.cpp:118-132):
+ * position = origin + distance * direction, normal = -direction, subObject = M_MAX_UNSIGNED (not stored). */
+typedef struct u3d_ray_hit
+{
+    float position[3];
+    float normal[3];
+    float distance;
+    uint32_t drawable;
+} u3d_ray_hit;
+/* Octree::Raycast (single = 0, Octree.cpp:501-508) or Octree::RaycastSingle (single = 1, Octree.cpp:510-548) for n_rays rays at once, with
+ * a RayOctreeQuery of level RAY_AABB.  rays7 = n x (origin.xyz, direction.xyz, maxDistance); direction is used as given (Ray's constructor
+ * normalises, Ray::direction_ is what is meant here); maxDistance may be INFINITY.  The octree walk and the hit distances run on the GPU
+ * (one CTA per ray); the final ordering uses the reference's own Sort procedure (Container/Sort.h) so ties come out in its order.
+ * hits = n x capacity records, counts[i] = result size of ray i.  With single = 1 `capacity` must also hold every candidate drawable of
+ * the octants a ray touches (they are sorted to find the winner); -U3D_ERR_CAPACITY otherwise.  Synchronises `stream`. */
+U3D_API int u3d_scene_raycast(u3d_scene* scene, uint32_t n_rays, const float* rays7, uint32_t drawable_flags, uint32_t view_mask, int single,
+    uint32_t capacity, uint32_t* counts, u3d_ray_hit* hits, void* stream);
+/* The reference's Sort (Container/Sort.h:70-141) over float keys with a payload, compare = `key <` (CompareDrawables, Drawable.h:419-422;
+ * CompareRayQueryResults, Octree.cpp:66-69).  Host code, no GPU needed; exposed because its tie order is part of observable results. */
+U3D_API int u3d_sort_by_key(uint32_t n, float* keys, uint32_t* values);
 
 /* ---- batched many-view entry point (new) ----------------------------------------------------------------------- */
 /* Buffers for up to max_views views of width x height.  occluders may be NULL (frustum-only views, BASELINE config 4).

@@ -193,6 +193,16 @@ class OracleTree:
         pos = out[:n].copy()
         return self.order[pos] if as_ids else pos
 
+    def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
+        """Octree::Raycast / RaycastSingle at RAY_AABB level.  Returns (drawable ids, distances) in result_ order."""
+        ray = np.array(list(origin) + list(direction) + [max_distance], np.float32)
+        pos = np.zeros(max(len(self.order), 1), np.int32)
+        dist = np.zeros(max(len(self.order), 1), np.float32)
+        L = lib()
+        L.orc_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f]
+        n = L.orc_raycast(C.byref(self.t), _p(ray, _f), flags, view_mask, int(single), _p(pos, _i), _p(dist, _f))
+        return self.order[pos[:n]], dist[:n].copy()
+
     def check_visibility(self, ob, cand_pos):
         cand = np.ascontiguousarray(cand_pos, dtype=np.int32)
         out = np.zeros(max(len(cand), 1), np.int32)
@@ -210,3 +220,22 @@ class OracleTree:
         n = lib().orc_check_in_view(C.byref(self.t), ob.h if ob is not None else None, _p(v12, _f), _p(cp, _f), int(ortho), _p(dd, _f), _p(cand, _i),
                                     len(cand), _p(out, _i), _p(mm, _f))
         return out[:n].copy(), mm
+
+
+def sort_by_key(keys, vals):
+    """The restated Sort of Container/Sort.h over (key, payload) pairs."""
+    k = np.ascontiguousarray(keys, np.float32).copy()
+    v = np.ascontiguousarray(vals, np.int32).copy()
+    L = lib()
+    L.orc_sort_by_key.argtypes = [C.c_int, _f, _i]
+    L.orc_sort_by_key(len(k), _p(k, _f), _p(v, _i))
+    return k, v
+
+
+def ray_hit_distance(ray6, box6):
+    L = lib()
+    L.orc_ray_hit_distance.argtypes = [_f, _f]
+    L.orc_ray_hit_distance.restype = C.c_float
+    r = np.ascontiguousarray(ray6, np.float32)
+    b = np.ascontiguousarray(box6, np.float32)
+    return float(L.orc_ray_hit_distance(_p(r, _f), _p(b, _f)))

@@ -34,6 +34,8 @@
 #include <Urho3D/Scene/Node.h>
 #include <Urho3D/Scene/Scene.h>
 #include <Urho3D/Math/Sphere.h>
+#include <Urho3D/Math/Ray.h>
+#include <Urho3D/Container/Sort.h>
 
 using namespace Urho3D;
 
@@ -640,6 +642,61 @@ int ref_run_view(void* h, int numOccluders, const float* occAabb6, const float* 
         times4[0] = t1 - t0; times4[1] = t2 - t1; times4[2] = t3 - t2; times4[3] = t4 - t3;
     }
     return nvis;
+}
+
+/// Octree::Raycast (single == 0) / Octree::RaycastSingle (single != 0) with the reference's own RayOctreeQuery at RAY_AABB level
+/// (Octree.cpp:501-548; the test drawable keeps Drawable::ProcessRayQuery, Drawable.cpp:118-132).  ray7 = origin, direction (used as given: no
+/// normalisation, Ray::direction_ is assigned directly), maxDistance.  Returns the result size; ids / distances / positions in result_ order.
+int ref_raycast(void* h, const float* ray7, unsigned flags, unsigned viewMask, int single, int* outIdx, float* outDist, float* outPos3, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Ray ray;
+    ray.origin_ = Vector3(ray7[0], ray7[1], ray7[2]);
+    ray.direction_ = Vector3(ray7[3], ray7[4], ray7[5]);
+    PODVector<RayQueryResult> results;
+    RayOctreeQuery q(results, ray, RAY_AABB, ray7[6], (unsigned char)flags, viewMask);
+    if (single)
+        r->octree_->RaycastSingle(q);
+    else
+        r->octree_->Raycast(q);
+    int n = (int)results.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+    {
+        outIdx[i] = static_cast<TestDrawable*>(results[i].drawable_)->id_;
+        outDist[i] = results[i].distance_;
+        if (outPos3)
+        {
+            outPos3[3 * i] = results[i].position_.x_;
+            outPos3[3 * i + 1] = results[i].position_.y_;
+            outPos3[3 * i + 2] = results[i].position_.z_;
+        }
+    }
+    return n;
+}
+
+/// The reference's Sort (Container/Sort.h) over float keys with an index payload, compare = key less-than (as CompareDrawables /
+/// CompareRayQueryResults do).  Used to pin the restated sort.
+namespace
+{
+struct KeyIdx { float key; int idx; };
+bool KeyLess(const KeyIdx& a, const KeyIdx& b) { return a.key < b.key; }
+}
+void ref_sort_by_key(int n, float* keys, int* vals)
+{
+    PODVector<KeyIdx> v;
+    v.Resize((unsigned)n);
+    for (int i = 0; i < n; ++i)
+    {
+        v[i].key = keys[i];
+        v[i].idx = vals[i];
+    }
+    if (n)
+        Sort(v.Begin(), v.End(), KeyLess);
+    for (int i = 0; i < n; ++i)
+    {
+        keys[i] = v[i].key;
+        vals[i] = v[i].idx;
+    }
 }
 
 }

@@ -67,6 +67,8 @@ class Ref:
         L.ref_query_shape.argtypes = [C.c_void_p, C.c_int, _f, C.c_uint, C.c_uint, _i, C.c_int]
         L.ref_move_drawables.argtypes = [C.c_void_p, C.c_int, _i, _f]
         L.ref_remove_drawable.argtypes = [C.c_void_p, C.c_int]
+        L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
+        L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
         self.h = L.ref_create(int(worker_threads))
         self._keep = []
@@ -225,6 +227,23 @@ class Ref:
         out = np.zeros(max(self.n, 1), np.int32)
         n = self.lib.ref_query_shape(self.h, shape, _p(p, _f), flags, view_mask, _p(out, _i), out.shape[0])
         return out[:n].copy()
+
+    def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
+        """Octree::Raycast / RaycastSingle, RAY_AABB level.  Returns (ids, distances, positions) in result_ order."""
+        ray = np.array(list(origin) + list(direction) + [max_distance], np.float32)
+        cap = max(self.n, 1)
+        ids = np.zeros(cap, np.int32)
+        dist = np.zeros(cap, np.float32)
+        pos = np.zeros((cap, 3), np.float32)
+        n = self.lib.ref_raycast(self.h, _p(ray, _f), flags, view_mask, int(single), _p(ids, _i), _p(dist, _f), _p(pos, _f), cap)
+        return ids[:n].copy(), dist[:n].copy(), pos[:n].copy()
+
+    def sort_by_key(self, keys, vals):
+        """The reference's Sort (Container/Sort.h) with a key less-than compare; returns (sorted keys, payload in sorted order)."""
+        k = np.ascontiguousarray(keys, np.float32).copy()
+        v = np.ascontiguousarray(vals, np.int32).copy()
+        self.lib.ref_sort_by_key(len(k), _p(k, _f), _p(v, _i))
+        return k, v
 
     def check_visibility(self, use_buffer=True):
         out = np.zeros(max(self.n, 1), np.int32)

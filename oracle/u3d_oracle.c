@@ -819,3 +819,168 @@ int orc_check_in_view(const OrcTree* t, const OrcOB* ob, const float* view12, co
     minmax2[1] = max_z;
     return n;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Ray queries: Octree::Raycast / RaycastSingle at RAY_AABB level (Octree.cpp:257-282, 284-309, 501-548; Drawable::ProcessRayQuery,
+ * Drawable.cpp:118-132; Ray::HitDistance(BoundingBox), Math/Ray.cpp:71-148).  TEST INFRASTRUCTURE ONLY.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+static int in_range(float v, float lo, float hi) { return v >= lo && v <= hi; }
+
+/* Ray::HitDistance(const BoundingBox&), Math/Ray.cpp:71-148.  ray6 = origin.xyz, direction.xyz; b = min.xyz, max.xyz. */
+float orc_ray_hit_distance(const float* ray6, const float* b)
+{
+    const float* o = ray6;
+    const float* d = ray6 + 3;
+    if (b[0] == INFINITY) /* !box.Defined(), BoundingBox.h:258-261 */
+        return INFINITY;
+    if (!(o[0] < b[0] || o[0] > b[3] || o[1] < b[1] || o[1] > b[4] || o[2] < b[2] || o[2] > b[5]))
+        return 0.0f; /* origin inside the box */
+    float dist = INFINITY;
+    for (int axis = 0; axis < 3; ++axis)
+    {
+        const int u = (axis + 1) % 3, w = (axis + 2) % 3;
+        for (int side = 0; side < 2; ++side)
+        {
+            /* min face when coming from below it, max face when coming from above it */
+            const float face = side == 0 ? b[axis] : b[3 + axis];
+            const int towards = side == 0 ? (o[axis] < face && d[axis] > 0.0f) : (o[axis] > face && d[axis] < 0.0f);
+            if (!towards)
+                continue;
+            const float x = (face - o[axis]) / d[axis];
+            if (x < dist)
+            {
+                const float pu = o[u] + x * d[u], pw = o[w] + x * d[w];
+                if (in_range(pu, b[u], b[3 + u]) && in_range(pw, b[w], b[3 + w]))
+                    dist = x;
+            }
+        }
+    }
+    return dist;
+}
+
+/* Sort() of Container/Sort.h:70-141 applied to (key, payload) pairs with `a.key < b.key` as the compare: median-of-three quicksort
+ * (Hoare partition) down to partitions of 16, then one insertion sort over the whole range.  Not stable; the order of equal keys is a
+ * property of this exact procedure, which is why it is restated instead of calling qsort. */
+typedef struct { float key; int val; } KeyVal;
+
+static void kv_quick(KeyVal* a, long begin, long end)
+{
+    while (end - begin > 16)
+    {
+        long pivot = begin + (end - begin) / 2;
+        if (a[begin].key < a[pivot].key && a[end - 1].key < a[begin].key)
+            pivot = begin;
+        else if (a[end - 1].key < a[pivot].key && a[begin].key < a[end - 1].key)
+            pivot = end - 1;
+        long i = begin - 1, j = end;
+        const KeyVal pv = a[pivot];
+        for (;;)
+        {
+            while (pv.key < a[--j].key) {}
+            while (a[++i].key < pv.key) {}
+            if (i < j)
+            {
+                const KeyVal t = a[i];
+                a[i] = a[j];
+                a[j] = t;
+            }
+            else
+                break;
+        }
+        kv_quick(a, begin, j + 1);
+        begin = j + 1;
+    }
+}
+
+static void kv_sort(KeyVal* a, long n)
+{
+    kv_quick(a, 0, n);
+    for (long i = 1; i < n; ++i)
+    {
+        const KeyVal t = a[i];
+        long j = i;
+        while (j > 0 && t.key < a[j - 1].key)
+        {
+            a[j] = a[j - 1];
+            --j;
+        }
+        a[j] = t;
+    }
+}
+
+/* Exposed for the tests of the product's own host-side sort. */
+void orc_sort_by_key(int n, float* keys, int* vals)
+{
+    KeyVal* a = (KeyVal*)malloc(sizeof(KeyVal) * (size_t)(n > 0 ? n : 1));
+    for (int i = 0; i < n; ++i)
+    {
+        a[i].key = keys[i];
+        a[i].val = vals[i];
+    }
+    kv_sort(a, n);
+    for (int i = 0; i < n; ++i)
+    {
+        keys[i] = a[i].key;
+        vals[i] = a[i].val;
+    }
+    free(a);
+}
+
+/* Octree::Raycast (single = 0) / RaycastSingle (single = 1) with a RAY_AABB-level query.  ray7 = origin.xyz, direction.xyz, maxDistance.
+ * Writes DFS positions and distances in result_ order; returns the result size. */
+int orc_raycast(const OrcTree* t, const float* ray7, unsigned flags, unsigned view_mask, int single, int* out_pos, float* out_dist)
+{
+    const float maxd = ray7[6];
+    unsigned char* state = (unsigned char*)malloc((size_t)t->m);
+    KeyVal* hits = (KeyVal*)malloc(sizeof(KeyVal) * (size_t)(t->n > 0 ? t->n : 1));
+    long nh = 0;
+    for (int i = 0; i < t->m; ++i)
+    {
+        /* every octant is tested, the root included (Octree.cpp:257-261) */
+        if (i > 0 && !state[t->parent[i]])
+        {
+            state[i] = 0;
+            continue;
+        }
+        const float od = orc_ray_hit_distance(ray7, t->box6 + 6 * (size_t)i);
+        if (od >= maxd)
+        {
+            state[i] = 0;
+            continue;
+        }
+        state[i] = 1;
+        for (int d = t->first[i]; d < t->first[i] + t->count[i]; ++d)
+        {
+            if (!((t->flags[d] & flags) && (t->view_mask[d] & view_mask)))
+                continue;
+            const float dist = orc_ray_hit_distance(ray7, t->aabb6 + 6 * (size_t)d);
+            if (single || dist < maxd) /* RaycastSingle collects first (GetDrawablesOnlyInternal), Raycast tests at once (ProcessRayQuery) */
+            {
+                hits[nh].key = dist;
+                hits[nh].val = d;
+                ++nh;
+            }
+        }
+    }
+    kv_sort(hits, nh);
+    int n = 0;
+    if (!single)
+    {
+        for (long i = 0; i < nh; ++i, ++n)
+        {
+            out_pos[n] = hits[i].val;
+            out_dist[n] = hits[i].key;
+        }
+    }
+    else if (nh && hits[0].key < maxd)
+    {
+        /* the first sorted candidate passes `sortValue < Min(closestHit, maxDistance)` and sets closestHit to its own distance; every later
+         * one has sortValue >= closestHit and ends the loop (Octree.cpp:528-541) */
+        out_pos[0] = hits[0].val;
+        out_dist[0] = hits[0].key;
+        n = 1;
+    }
+    free(hits);
+    free(state);
+    return n;
+}

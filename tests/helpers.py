@@ -51,3 +51,28 @@ def host_flatten(scene):
     t.add(scene.aabb, scene.flags, scene.view_mask, scene.occludee, scene.cast_shadows)
     flat = t.flatten()
     return t, flat
+
+
+def random_rays(extent, count, seed=1, stacked_boxes=None):
+    """Rays for Octree::Raycast tests: from inside / outside the populated region, axis-parallel ones (zero direction components), rays
+    starting inside boxes (distance 0 ties) and a few with a finite maxDistance.  Returns [(origin, direction, max_distance)]."""
+    rs = np.random.RandomState(seed)
+    rays = []
+    for i in range(count):
+        o = np.array([rs.uniform(-extent, extent), rs.uniform(0.2, 6.0), rs.uniform(-extent, extent)], np.float32)
+        kind = i % 5
+        if kind == 0:
+            d = np.array([1.0, 0.0, 0.0], np.float32) * (1 if rs.uniform() < 0.5 else -1)
+        elif kind == 1:
+            d = np.array([0.0, -1.0, 0.0], np.float32)
+            o[1] = 50.0
+        else:
+            d = rs.normal(size=3).astype(np.float32)
+            d[1] *= np.float32(0.15)
+            d = (d / np.float32(np.sqrt(np.float32((d * d).sum())))).astype(np.float32)
+        if kind == 4 and stacked_boxes is not None:
+            b = stacked_boxes[rs.randint(len(stacked_boxes))]
+            o = ((b[:3] + b[3:]) * np.float32(0.5)).astype(np.float32)
+        maxd = np.float32(np.inf) if i % 3 else np.float32(rs.uniform(5.0, 2.0 * extent))
+        rays.append((o, d, maxd))
+    return rays

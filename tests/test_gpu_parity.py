@@ -641,3 +641,37 @@ def test_peer_memory_result_exchange(gpu_ctx, world):
     for o in (*small, *gathers, *batches, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+def test_raycasts_match_oracle(gpu_ctx):
+    """Octree::Raycast / RaycastSingle (RAY_AABB level) for a batch of rays: ids, bit-equal distances and positions in the reference's result
+    order (ties included), with filters, finite maxDistance, rays from inside boxes, a ray that misses the octree, and the capacity error."""
+    sc = helpers.small_scene(n=20000, k=8, extent=120.0, seed=31)
+    sc.aabb[300:400] = sc.aabb[500:600]  # stacked duplicates: equal distances
+    rs = np.random.RandomState(6)
+    sc.flags[rs.uniform(size=sc.n) < 0.2] = 2
+    sc.view_mask[rs.uniform(size=sc.n) < 0.2] = 0x2
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, 8, 8)
+    rays = helpers.random_rays(120.0, 200, seed=12, stacked_boxes=sc.aabb[300:400])
+    rays.append((np.array([0.0, 5000.0, 0.0], np.float32), np.array([0.0, 1.0, 0.0], np.float32), np.float32(np.inf)))  # starts above, points away
+    rays7 = np.array([list(o) + list(d) + [m] for o, d, m in rays], np.float32)
+    total = 0
+    for flags, mask in ((0xFF, 0xFFFFFFFF), (0x1, 0x1)):
+        for single in (False, True):
+            got = gs.raycast(rays7, flags, mask, single, capacity=8192)
+            for i, (o, d, m) in enumerate(rays):
+                wid, wdist = otree.raycast(o, d, m, flags, mask, single)
+                h = got[i]
+                assert np.array_equal(h["drawable"], wid.astype(np.uint32)), "ray %d single %d" % (i, single)
+                assert np.array_equal(h["distance"].view(np.uint32), wdist.view(np.uint32))
+                pos = (o[None, :] + wdist[:, None] * d[None, :]).astype(np.float32)
+                assert np.array_equal(h["position"], pos) and np.array_equal(h["normal"], np.broadcast_to(-d, pos.shape))
+                total += len(wid)
+    assert total > 1000 and len(got[-1]) == 0
+    with pytest.raises(capi.U3DError) as e:
+        gs.raycast(rays7[:8], capacity=1)
+    assert e.value.code == 4
+    for o in (gs, tree):
+        o.close()
+    ob.close()

@@ -82,3 +82,18 @@ def test_moves_and_removals_match_reference():
         assert nb == sc.n - len(removed)
     t.close()
     ref.close()
+
+
+def test_host_sort_follows_the_reference_sort():
+    """u3d_sort_by_key (host code of the product: orders ray hits and, later, occluders) leaves ties exactly where the reference's Sort does."""
+    ref = refbind.Ref(0)
+    rs = np.random.RandomState(11)
+    for n in list(range(0, 36)) + [64, 333, 4096]:
+        for distinct in (2, 9, 10 ** 6):
+            keys = rs.randint(0, distinct, size=n).astype(np.float32)
+            keys[rs.uniform(size=n) < 0.05] = np.inf
+            vals = np.arange(n, dtype=np.int32)
+            rk, rv = ref.sort_by_key(keys, vals)
+            gk, gv = capi.sort_by_key(keys, vals.astype(np.uint32))
+            assert np.array_equal(rk, gk) and np.array_equal(rv.astype(np.uint32), gv), (n, distinct)
+    ref.close()

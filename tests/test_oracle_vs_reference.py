@@ -165,3 +165,46 @@ def test_sphere_box_point_queries_match_reference():
     assert total > 0
     ref.close()
     ob.close()
+
+
+def test_sort_restatement_matches_reference_sort():
+    """The restated Container/Sort.h procedure gives the reference's order, ties included (few distinct keys, all sizes around the 16 threshold)."""
+    ref = refbind.Ref(0)
+    rs = np.random.RandomState(2)
+    for n in list(range(0, 40)) + [100, 257, 1000, 5000]:
+        for distinct in (3, 17, 10 ** 6):
+            keys = rs.randint(0, distinct, size=n).astype(np.float32)
+            vals = np.arange(n, dtype=np.int32)
+            rk, rv = ref.sort_by_key(keys, vals)
+            ok, ov = oraclebind.sort_by_key(keys, vals)
+            assert np.array_equal(rk, ok) and np.array_equal(rv, ov), (n, distinct)
+            assert np.all(np.diff(ok) >= 0)
+    ref.close()
+
+
+def test_raycast_matches_reference():
+    """Octree::Raycast and RaycastSingle (RAY_AABB level) against the oracle: ids and bit-equal distances in result_ order, with flag / mask
+    filters, finite maxDistance, rays starting inside boxes (distance-0 ties, whose order is the unstable sort's) and stacked duplicates."""
+    sc = helpers.small_scene(n=6000, k=8, extent=60.0, seed=23)
+    # duplicate some boxes so that equal distances occur
+    sc.aabb[100:160] = sc.aabb[200:260]
+    rs = np.random.RandomState(4)
+    sc.flags[rs.uniform(size=sc.n) < 0.2] = 2
+    sc.view_mask[rs.uniform(size=sc.n) < 0.2] = 0x2
+    ref = helpers.make_ref(sc, 64, 64)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, 64, 64)
+    nonempty = 0
+    for o, d, maxd in helpers.random_rays(60.0, 60, seed=9, stacked_boxes=sc.aabb[100:160]):
+        for flags, mask in ((0xFF, 0xFFFFFFFF), (0x1, 0xFFFFFFFF), (0xFF, 0x1)):
+            for single in (False, True):
+                rid, rdist, rpos = ref.raycast(o, d, maxd, flags, mask, single)
+                oid, odist = tree.raycast(o, d, maxd, flags, mask, single)
+                assert np.array_equal(rid, oid), (o, d, maxd, flags, mask, single)
+                assert np.array_equal(rdist.view(np.uint32), odist.view(np.uint32))
+                nonempty += len(rid) > 0
+                if single:
+                    assert len(rid) <= 1
+    assert nonempty > 100
+    ref.close()
+    ob.close()

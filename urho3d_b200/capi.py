@@ -10,7 +10,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "lib", "libu3dgpu.so")
 
-QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT = 0, 1, 2, 3, 4, 5
+RAY_HIT_DTYPE = np.dtype([("position", np.float32, 3), ("normal", np.float32, 3), ("distance", np.float32), ("drawable", np.uint32)])
+QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT, QUERY_RAY, QUERY_RAY_CANDIDATES = 0, 1, 2, 3, 4, 5, 6, 7
 STAGE_QUERY, STAGE_VISIBLE, STAGE_INVIEW = 0, 1, 2
 CULL_NONE, CULL_CCW, CULL_CW = 0, 1, 2
 ERR_CAPACITY = 4
@@ -110,6 +111,8 @@ SIGNATURES = {
     "u3d_batch_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
     "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
+    "u3d_scene_raycast": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
+    "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "u3d_gather_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
     "u3d_gather_destroy": (None, [_vp]),
     "u3d_gather_export": (C.c_int, [_vp, _vp]),
@@ -146,6 +149,14 @@ def lib():
             fn.argtypes = args
         _lib = L
     return _lib
+
+
+def sort_by_key(keys, values):
+    """The reference's Sort procedure (Container/Sort.h) over float keys with a uint32 payload; host code."""
+    k = np.ascontiguousarray(keys, np.float32).copy()
+    v = np.ascontiguousarray(values, np.uint32).copy()
+    _chk(lib().u3d_sort_by_key(len(k), _p(k, _f), _p(v, _u32)))
+    return k, v
 
 
 def debug_set_option(name, value):
@@ -254,6 +265,16 @@ class GpuScene:
     def set_draw_distances(self, draw_distance):
         d = _arr(draw_distance, np.float32)
         _chk(lib().u3d_scene_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
+
+    def raycast(self, rays7, flags=0xFF, view_mask=0xFFFFFFFF, single=False, capacity=4096, stream=None):
+        """Octree::Raycast / RaycastSingle (RAY_AABB) for many rays.  rays7: n x (origin, direction, maxDistance).
+        Returns a list of structured arrays (RAY_HIT_DTYPE), one per ray, in result_ order."""
+        rays = np.ascontiguousarray(rays7, np.float32).reshape(-1, 7)
+        n = rays.shape[0]
+        counts = np.zeros(max(n, 1), np.uint32)
+        hits = np.zeros((max(n, 1), capacity), RAY_HIT_DTYPE)
+        _chk(lib().u3d_scene_raycast(self.h, n, _p(rays, _f), flags, view_mask, int(single), capacity, _p(counts, _u32), hits.ctypes.data, stream))
+        return [hits[i, :counts[i]].copy() for i in range(n)]
 
     def update_boxes(self, ids, aabb6, stream=None):
         """Rewrite the world boxes of drawables that moved inside their octant (no re-flatten)."""

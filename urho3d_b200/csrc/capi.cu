@@ -163,6 +163,16 @@ struct u3d_scene
     DevBuf<uint32_t> updSlots;       // staging of u3d_scene_update_boxes
     DevBuf<float> updBoxes;
     std::vector<uint32_t> slotOfId;  // drawable id -> DFS slot (for late per-drawable uploads)
+    // ray queries (u3d_scene_raycast): device copy of slotOfId + scratch, all grow-only
+    DevBuf<uint32_t> slotOfIdDev;
+    bool slotOfIdUploaded{};
+    DevBuf<ViewConst> rayViews;
+    DevBuf<unsigned char> rayOctState;
+    DevBuf<uint32_t> rayIdx, rayCounts, rayFlags;
+    DevBuf<float> rayDist;
+    std::vector<ViewConst> rayHost;
+    std::vector<uint32_t> rayHostIdx, rayHostCounts;
+    std::vector<float> rayHostDist;
 };
 
 struct u3d_mesh
@@ -1327,6 +1337,170 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
         *out_count = counts[1];
     if (counts[1] > capacity)
         return fail(U3D_ERR_CAPACITY, "u3d_octree_query: result larger than capacity");
+    return U3D_OK;
+}
+
+// ---- ray queries ------------------------------------------------------------------------------------------------------------
+} // extern "C"
+
+namespace
+{
+struct RayKey
+{
+    float key;
+    uint32_t val;
+};
+
+/// The reference's Sort (Container/Sort.h:70-141) for (key, payload) records ordered by `key <`: quicksort passes with a median-of-three
+/// pivot and Hoare partitioning while a range is longer than 16, then one insertion sort over everything.  Not stable: where keys tie, the
+/// result order is whatever this procedure leaves, and Octree::Raycast / RaycastSingle expose that order, so it is followed step by step.
+void urho_quick_pass(RayKey* a, long lo, long hi)
+{
+    while (hi - lo > 16)
+    {
+        long p = lo + (hi - lo) / 2;
+        if (a[lo].key < a[p].key && a[hi - 1].key < a[lo].key)
+            p = lo;
+        else if (a[hi - 1].key < a[p].key && a[lo].key < a[hi - 1].key)
+            p = hi - 1;
+        const RayKey pivot = a[p];
+        long i = lo - 1, j = hi;
+        for (;;)
+        {
+            do
+                --j;
+            while (pivot.key < a[j].key);
+            do
+                ++i;
+            while (a[i].key < pivot.key);
+            if (i >= j)
+                break;
+            std::swap(a[i], a[j]);
+        }
+        urho_quick_pass(a, lo, j + 1);
+        lo = j + 1;
+    }
+}
+
+void urho_sort(RayKey* a, long n)
+{
+    urho_quick_pass(a, 0, n);
+    for (long i = 1; i < n; ++i)
+    {
+        const RayKey t = a[i];
+        long j = i;
+        for (; j > 0 && t.key < a[j - 1].key; --j)
+            a[j] = a[j - 1];
+        a[j] = t;
+    }
+}
+} // namespace
+
+extern "C"
+{
+
+int u3d_sort_by_key(uint32_t n, float* keys, uint32_t* values)
+{
+    if (n && (!keys || !values))
+        return fail(U3D_ERR_INVALID, "u3d_sort_by_key: NULL argument");
+    std::vector<RayKey> a(n);
+    for (uint32_t i = 0; i < n; ++i)
+        a[i] = RayKey{keys[i], values[i]};
+    urho_sort(a.data(), (long)n);
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        keys[i] = a[i].key;
+        values[i] = a[i].val;
+    }
+    return U3D_OK;
+}
+
+int u3d_scene_raycast(u3d_scene* s, uint32_t n_rays, const float* rays7, uint32_t drawable_flags, uint32_t view_mask, int single, uint32_t capacity,
+    uint32_t* counts, u3d_ray_hit* hits, void* stream)
+{
+    if (!s || (n_rays && (!rays7 || !counts)) || (capacity && !hits))
+        return fail(U3D_ERR_INVALID, "u3d_scene_raycast: NULL argument");
+    if (!n_rays)
+        return U3D_OK;
+    if (n_rays > 65535)
+        return fail(U3D_ERR_UNSUPPORTED, "u3d_scene_raycast: at most 65535 rays per call");
+    u3d_ctx* ctx = s->ctx;
+    CU_CHECK(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->pick(stream);
+    // RaycastSingle needs EVERY candidate of the touched octants (its winner is decided by the sort); size the device lists accordingly
+    const uint32_t devCap = std::max<uint32_t>(capacity, 1);
+    if (!s->slotOfIdUploaded)
+    {
+        CU_CHECK(s->slotOfIdDev.ensure(std::max<size_t>(s->slotOfId.size(), 1)));
+        if (!s->slotOfId.empty())
+            CU_CHECK(cudaMemcpyAsync(s->slotOfIdDev.p, s->slotOfId.data(), s->slotOfId.size() * 4, cudaMemcpyHostToDevice, st));
+        s->slotOfIdUploaded = true;
+    }
+    s->rayHost.assign(n_rays, ViewConst{});
+    for (uint32_t i = 0; i < n_rays; ++i)
+    {
+        ViewConst& vc = s->rayHost[i];
+        std::memcpy(vc.planes, rays7 + 7 * (size_t)i, 7 * sizeof(float));
+        vc.drawableFlags = drawable_flags;
+        vc.viewMask = view_mask;
+        vc.queryMode = single ? QUERY_RAY_CANDIDATES : QUERY_RAY;
+    }
+    CU_CHECK(s->rayViews.ensure(n_rays));
+    CU_CHECK(s->rayOctState.ensure((size_t)n_rays * s->dev.numOctants));
+    CU_CHECK(s->rayIdx.ensure((size_t)n_rays * devCap));
+    CU_CHECK(s->rayDist.ensure((size_t)n_rays * devCap));
+    CU_CHECK(s->rayCounts.ensure((size_t)n_rays * 2));
+    CU_CHECK(s->rayFlags.ensure(1));
+    CU_CHECK(cudaMemcpyAsync(s->rayViews.p, s->rayHost.data(), (size_t)n_rays * sizeof(ViewConst), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemsetAsync(s->rayFlags.p, 0, 4, st));
+    const BufGeom g = make_geom(2, 2);
+    launch_cull(s->dev, g, s->rayViews.p, (int)n_rays, nullptr, nullptr, 0, s->rayOctState.p, STAGE_QUERY, s->rayIdx.p, devCap, s->rayCounts.p, nullptr,
+        s->rayFlags.p, false, st);
+    launch_ray_distances(s->dev, s->rayViews.p, (int)n_rays, s->slotOfIdDev.p, s->rayIdx.p, devCap, s->rayCounts.p, s->rayDist.p, st);
+    CU_CHECK(cudaGetLastError());
+    s->rayHostCounts.resize((size_t)n_rays * 2);
+    CU_CHECK(cudaMemcpyAsync(s->rayHostCounts.data(), s->rayCounts.p, (size_t)n_rays * 8, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    bool overflow = false;
+    for (uint32_t i = 0; i < n_rays; ++i)
+        overflow |= s->rayHostCounts[2 * i + 1] > devCap;
+    s->rayHostIdx.resize((size_t)n_rays * devCap);
+    s->rayHostDist.resize((size_t)n_rays * devCap);
+    CU_CHECK(cudaMemcpyAsync(s->rayHostIdx.data(), s->rayIdx.p, (size_t)n_rays * devCap * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaMemcpyAsync(s->rayHostDist.data(), s->rayDist.p, (size_t)n_rays * devCap * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    std::vector<RayKey> keys;
+    for (uint32_t i = 0; i < n_rays; ++i)
+    {
+        const float* ray = rays7 + 7 * (size_t)i;
+        const uint32_t m = std::min(s->rayHostCounts[2 * i + 1], devCap);
+        keys.resize(m);
+        for (uint32_t k = 0; k < m; ++k)
+            keys[k] = RayKey{s->rayHostDist[(size_t)i * devCap + k], s->rayHostIdx[(size_t)i * devCap + k]};
+        // Octree::Raycast: Sort(result_, CompareRayQueryResults), Octree.cpp:507; RaycastSingle: Sort(drawables, CompareDrawables), Octree.cpp:525
+        urho_sort(keys.data(), (long)m);
+        uint32_t nOut = m;
+        if (single)
+            // the first sorted candidate is the only one that can pass `sortValue < Min(closestHit, maxDistance)` (Octree.cpp:528-541)
+            nOut = (m && keys[0].key < ray[6]) ? 1u : 0u;
+        counts[i] = nOut;
+        for (uint32_t k = 0; k < nOut && k < capacity; ++k)
+        {
+            u3d_ray_hit& h = hits[(size_t)i * capacity + k];
+            const float dist = keys[k].key;
+            // RayQueryResult of Drawable::ProcessRayQuery, Drawable.cpp:123-130
+            h.position[0] = ray[0] + dist * ray[3];
+            h.position[1] = ray[1] + dist * ray[4];
+            h.position[2] = ray[2] + dist * ray[5];
+            h.normal[0] = -ray[3];
+            h.normal[1] = -ray[4];
+            h.normal[2] = -ray[5];
+            h.distance = dist;
+            h.drawable = keys[k].val;
+        }
+    }
+    if (overflow)
+        return fail(U3D_ERR_CAPACITY, "u3d_scene_raycast: a ray produced more hits/candidates than capacity");
     return U3D_OK;
 }
 

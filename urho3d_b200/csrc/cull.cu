@@ -328,8 +328,18 @@ template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_c
     __syncthreads();
     if (tid == 0)
     {
-        state[0] = 1; // the root is never tested (Octree.cpp:231)
-        mark_alive(0);
+        // the root is never tested by OctreeQuery walks (Octree.cpp:231); the ray walk tests every octant (Octree.cpp:257-261)
+        bool rootAlive = true;
+        if (vc.queryMode >= QUERY_RAY)
+        {
+            const float4 mn = sc.octMin[0], mx = sc.octMax[0];
+            rootAlive = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+        }
+        if (rootAlive)
+        {
+            state[0] = 1;
+            mark_alive(0);
+        }
     }
     __syncthreads();
     for (int lv = 1; lv < sc.numLevels; ++lv)
@@ -689,6 +699,29 @@ void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, 
 {
     if (n)
         k_update_boxes<<<(n + 255) / 256, 256, 0, s>>>(drwMin, drwMax, slots, boxes, n);
+}
+
+/// Hit distances of the drawables a ray query emitted: one block per ray, Ray::HitDistance (Math/Ray.cpp:71-148) of each emitted drawable's
+/// world box, in emission order (Drawable::ProcessRayQuery's distance_, Drawable.cpp:120; RaycastSingle's sort value, Octree.cpp:519-523).
+__global__ void k_ray_distances(SceneDev sc, const ViewConst* __restrict__ views, const uint32_t* __restrict__ slotOfId, const uint32_t* __restrict__ outIdx,
+    uint32_t outCap, const uint32_t* __restrict__ outCounts, float* __restrict__ outDist)
+{
+    const int v = blockIdx.x;
+    const uint32_t n = min(outCounts[2 * v + 1], outCap);
+    const float* ray = views[v].planes;
+    for (uint32_t i = threadIdx.x; i < n; i += blockDim.x)
+    {
+        const uint32_t d = slotOfId[outIdx[(size_t)v * outCap + i]];
+        const float4 mn = sc.drwMin[d], mx = sc.drwMax[d];
+        outDist[(size_t)v * outCap + i] = ray_hit_distance(ray, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+    }
+}
+
+void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
+    const uint32_t* outCounts, float* outDist, cudaStream_t s)
+{
+    if (numRays)
+        k_ray_distances<<<numRays, 128, 0, s>>>(sc, views, slotOfId, outIdx, outCap, outCounts, outDist);
 }
 
 void cull_set_walk_pool(int on)

@@ -21,7 +21,8 @@ constexpr int kMaxLevels = 16;
 
 enum : int { CULL_NONE = 0, CULL_CCW = 1, CULL_CW = 2 };
 enum : int { OUTSIDE = 0, INTERSECTS = 1, INSIDE = 2 };
-enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2, QUERY_SPHERE = 3, QUERY_BOX = 4, QUERY_POINT = 5 };
+enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2, QUERY_SPHERE = 3, QUERY_BOX = 4, QUERY_POINT = 5, QUERY_RAY = 6,
+    QUERY_RAY_CANDIDATES = 7 };
 enum : int { STAGE_QUERY = 0, STAGE_VISIBLE = 1, STAGE_INVIEW = 2 };
 
 // Per-drawable meta bits packed into the first pad word of the 32-byte AABB record (BoundingBox.h:326-330 layout).
@@ -143,11 +144,61 @@ template <bool FAST> __device__ __forceinline__ int frustum_test(const float* pl
     return (FAST || allInside) ? INSIDE : INTERSECTS;
 }
 
+/// Ray::HitDistance(const BoundingBox&), Math/Ray.cpp:71-148: 0 when the origin is inside, else the nearest entry through one of the
+/// (at most three) faces turned towards the origin, +inf for a miss or an undefined box.  ray = origin.xyz, direction.xyz.
+__device__ __forceinline__ float ray_hit_distance(const float* ray, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
+{
+    const float inf = __int_as_float(0x7f800000);
+    const float ox = ray[0], oy = ray[1], oz = ray[2], dx = ray[3], dy = ray[4], dz = ray[5];
+    if (mnx == inf)
+        return inf;
+    if (!(ox < mnx || ox > mxx || oy < mny || oy > mxy || oz < mnz || oz > mxz))
+        return 0.0f;
+    float dist = inf;
+    // x faces
+    if ((ox < mnx && dx > 0.0f) || (ox > mxx && dx < 0.0f))
+    {
+        const float x = ((ox < mnx ? mnx : mxx) - ox) / dx;
+        if (x < dist)
+        {
+            const float py = oy + x * dy, pz = oz + x * dz;
+            if (py >= mny && py <= mxy && pz >= mnz && pz <= mxz)
+                dist = x;
+        }
+    }
+    // y faces
+    if ((oy < mny && dy > 0.0f) || (oy > mxy && dy < 0.0f))
+    {
+        const float x = ((oy < mny ? mny : mxy) - oy) / dy;
+        if (x < dist)
+        {
+            const float px = ox + x * dx, pz = oz + x * dz;
+            if (px >= mnx && px <= mxx && pz >= mnz && pz <= mxz)
+                dist = x;
+        }
+    }
+    // z faces
+    if ((oz < mnz && dz > 0.0f) || (oz > mxz && dz < 0.0f))
+    {
+        const float x = ((oz < mnz ? mnz : mxz) - oz) / dz;
+        if (x < dist)
+        {
+            const float px = ox + x * dx, py = oy + x * dy;
+            if (px >= mnx && px <= mxx && py >= mny && py <= mxy)
+                dist = x;
+        }
+    }
+    return dist;
+}
+
 /// Octant / drawable test of every GPU-evaluable OctreeQuery.  FAST = the drawable form (IsInsideFast), else the 3-way octant form.
 /// Frustum-type queries (QUERY_FRUSTUM / OCCLUDED / SHADOWCASTER) use the 6 planes; the shape queries carry their parameters in the
 /// same 24 floats: sphere = (centre.xyz, radius)  Sphere::IsInside / IsInsideFast (Math/Sphere.cpp:136-256);
 /// box = (min.xyz, max.xyz)  BoundingBox::IsInside / IsInsideFast (BoundingBox.h:295-315) with the QUERY's box as `this`;
-/// point = (xyz)  BoundingBox::IsInside(point) with the octant / drawable box as `this` (BoundingBox.h:285-292; OctreeQuery.cpp:32-52).
+/// point = (xyz)  BoundingBox::IsInside(point) with the octant / drawable box as `this` (BoundingBox.h:285-292; OctreeQuery.cpp:32-52);
+/// ray = (origin.xyz, direction.xyz, maxDistance)  RayOctreeQuery: HitDistance(box) < maxDistance for octants (Octree.cpp:257-261, never
+/// "inside") and, in QUERY_RAY, for drawables (Drawable::ProcessRayQuery, Drawable.cpp:118-121); QUERY_RAY_CANDIDATES passes every drawable
+/// of a touched octant (GetDrawablesOnlyInternal, Octree.cpp:284-309: RaycastSingle's candidate pass).
 template <bool FAST> __device__ __forceinline__ int shape_test(int mode, const float* p, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
 {
     if (mode <= QUERY_SHADOWCASTER)
@@ -186,6 +237,15 @@ template <bool FAST> __device__ __forceinline__ int shape_test(int mode, const f
         if (!FAST && (mnx < p[0] || mxx > p[3] || mny < p[1] || mxy > p[4] || mnz < p[2] || mxz > p[5]))
             return INTERSECTS;
         return INSIDE;
+    }
+    if (mode == QUERY_RAY || mode == QUERY_RAY_CANDIDATES)
+    {
+        if (FAST && mode == QUERY_RAY_CANDIDATES)
+            return INSIDE;
+        const float d = ray_hit_distance(p, mnx, mny, mnz, mxx, mxy, mxz);
+        if (d >= p[6])
+            return OUTSIDE;
+        return FAST ? INSIDE : INTERSECTS;
     }
     // QUERY_POINT
     if (p[0] < mnx || p[0] > mxx || p[1] < mny || p[1] > mxy || p[2] < mnz || p[2] > mxz)

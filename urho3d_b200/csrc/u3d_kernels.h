@@ -98,6 +98,10 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags,
     bool pipelined /* other launches share the GPU: prefer the shape with the best aggregate throughput */, cudaStream_t s);
 
+/// Ray::HitDistance of every drawable a QUERY_RAY / QUERY_RAY_CANDIDATES run emitted (slotOfId: drawable id -> DFS slot).
+void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
+    const uint32_t* outCounts, float* outDist, cudaStream_t s);
+
 void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s);
 
 /// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
