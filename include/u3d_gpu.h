@@ -253,6 +253,21 @@ U3D_API int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids
 /* Pack the emitted ids of all views back to back ON THE DEVICE (two launches on `stream`, no synchronisation) and return the device
  * pointers: offsets = n+1 uint32, packed = sum of counts uint32.  This is what a rank hands to the NCCL gather. */
 U3D_API int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev, void** packed_dev);
+/* Occluder selection by the reference's heuristics instead of "every occluder whose box is in the frustum":
+ * View::UpdateOccluders (View.cpp:2171-2229: draw-distance test on Drawable::UpdateBatches' distance, screen-size threshold
+ * Renderer::GetOccluderSizeThreshold(), sort key density / size, Sort) followed by the triangle budget of View::DrawOccluders' threaded
+ * branch (View.cpp:2258-2270 with OcclusionBuffer::AddTriangles' return value, OB.cpp:164-198: submission stops after the first
+ * occluder that takes numTriangles_ past max_triangles = View::maxOccluderTriangles_).  Candidates are the occluder table's entries
+ * passing IsInsideFast, in table order (the reference: ZoneOccluderOctreeQuery result order, View.cpp:87-113).
+ * camera3 = n x (Camera::GetHalfViewSize(), Camera::GetOrthoSize(), Camera::GetFarClip()) for the views last set; call again after
+ * every u3d_batch_set_views.  Where the budget cut separates occluders with EQUAL sort keys the reference's own (unstable) Sort
+ * procedure is replayed on the device, so the selected set is the reference's.  At most 4096 candidates per view survive the size
+ * threshold (-U3D_ERR_CAPACITY at the next read otherwise).  enable = 0 returns to the default rule. */
+U3D_API int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold, uint32_t max_triangles, const float* camera3, void* stream);
+/* Drawable::GetDrawDistance() of every occluder (0 = unlimited, the default), used by the policy above (View.cpp:2186-2188). */
+U3D_API int u3d_occluders_set_draw_distances(u3d_occluders* o, uint32_t n, const float* draw_distance);
+/* Occluders submitted for `view` by the last run, in submission order (diagnostic / tests; synchronises). */
+U3D_API int u3d_batch_read_occluder_selection(u3d_batch* b, uint32_t view, uint32_t* occluder_ids, uint32_t capacity, uint32_t* count, void* stream);
 /* Kernel launches issued by the last u3d_batch_run / run_part on this batch. */
 U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
 /* Hint that the caller keeps several batches in flight on different streams (e.g. one per worker thread, or frame k+1 submitted while frame k

@@ -142,6 +142,19 @@ class OracleOB:
             res.append(out)
         return res
 
+    def draw_scene_view_selected(self, scene, view, selected, max_triangles):
+        """DrawOccluders' threaded branch over an explicit (sorted, budget-trimmed) occluder list.  Returns submitted triangles."""
+        self.set_view(view)
+        self.set_max_triangles(int(max_triangles))
+        self.clear()
+        sub = 0
+        for i in selected:
+            self.set_cull_mode(scene.cull_mode)
+            self.draw_batch(scene.occ_model[i], scene.mesh_vtx, scene.mesh_stride, scene.mesh_idx, 0, scene.mesh_idx.shape[0])
+            sub += scene.mesh_idx.shape[0] // 3
+        self.build_hierarchy()
+        return sub
+
     def draw_scene_view(self, scene, view):
         """Threaded-branch view set-up (View.cpp:2258-2273): select occluders by IsInsideFast in scene order, draw all, build mips.
         Returns number of submitted triangles."""
@@ -220,6 +233,27 @@ class OracleTree:
         n = lib().orc_check_in_view(C.byref(self.t), ob.h if ob is not None else None, _p(v12, _f), _p(cp, _f), int(ortho), _p(dd, _f), _p(cand, _i),
                                     len(cand), _p(out, _i), _p(mm, _f))
         return out[:n].copy(), mm
+
+
+def select_occluders(scene, view, size_threshold, max_triangles, draw_dist=None, num_triangles=None):
+    """View::UpdateOccluders + DrawOccluders' budget.  Returns (sorted occluder indices, sort values, number submitted under the budget)."""
+    k = scene.k
+    tris = np.full(k, scene.mesh_idx.shape[0] // 3, np.uint32) if num_triangles is None else np.ascontiguousarray(num_triangles, np.uint32)
+    dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, np.float32)
+    aabb = np.ascontiguousarray(scene.occ_aabb, np.float32)
+    planes = np.ascontiguousarray(view.planes, np.float32)
+    v12 = np.ascontiguousarray(view.view, np.float32)
+    cp = np.ascontiguousarray(view.position, np.float32)
+    out = np.zeros(max(k, 1), np.int32)
+    keys = np.zeros(max(k, 1), np.float32)
+    sub = C.c_int()
+    L = lib()
+    L.orc_select_occluders.argtypes = [C.c_int, _f, C.POINTER(C.c_uint), _f, _f, _f, _f, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_uint,
+                                       _i, _f, C.POINTER(C.c_int)]
+    n = L.orc_select_occluders(k, _p(aabb, _f), tris.ctypes.data_as(C.POINTER(C.c_uint)), _p(dd, _f), _p(planes, _f), _p(v12, _f), _p(cp, _f),
+                               int(view.ortho), view.half_view_size, view.ortho_size, view.far, size_threshold, int(max_triangles), _p(out, _i),
+                               _p(keys, _f), C.byref(sub))
+    return out[:n].copy(), keys[:n].copy(), sub.value
 
 
 def sort_by_key(keys, vals):

@@ -699,4 +699,101 @@ void ref_sort_by_key(int n, float* keys, int* vals)
     }
 }
 
+/// View::UpdateOccluders (View.cpp:2171-2229) restated on the reference's own math types, BoundingBox / Vector3 / Matrix3x4 arithmetic and Sort
+/// (View.cpp itself needs the GL back-end and cannot be compiled here).  Candidates = table entries whose box passes the query frustum's
+/// IsInsideFast, in table order.  Camera quantities are injected like in ref_check_in_view: distance_ = Camera::GetDistance (Camera.cpp:487-496).
+/// Returns the number of occluders kept; outIdx / outKeys = occluder indices and sort values in sorted order.
+namespace
+{
+struct OccKey { float sortValue; int index; };
+bool OccKeyLess(const OccKey& a, const OccKey& b) { return a.sortValue < b.sortValue; } // CompareDrawables, Drawable.h:419-422
+}
+int ref_select_occluders(void* h, int numOccluders, const float* occAabb6, const unsigned* numTriangles, const float* drawDistance, const float* view12,
+    const float* camPos3, int ortho, float halfViewSize, float orthoSize, float farClip, float occluderSizeThreshold, int* outIdx, float* outKeys, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    const Frustum& fr = r->QueryFrustum();
+    Matrix3x4 viewMatrix(view12);
+    Vector3 cameraPos(camPos3);
+    float invOrthoSize = 1.0f / orthoSize;
+    PODVector<OccKey> occluders;
+    for (int i = 0; i < numOccluders; ++i)
+    {
+        const float* b = occAabb6 + 6 * (size_t)i;
+        BoundingBox box(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]));
+        if (fr.IsInsideFast(box) == OUTSIDE)
+            continue;
+        Vector3 worldPos = box.Center();
+        float distance = !ortho ? (worldPos - cameraPos).Length() : Abs((viewMatrix * worldPos).z_);
+        float maxDistance = drawDistance ? drawDistance[i] : 0.0f;
+        if (maxDistance <= 0.0f || distance <= maxDistance)
+        {
+            float diagonal = box.Size().Length();
+            float compare;
+            if (!ortho)
+            {
+                float cameraMaxDistanceFraction = distance / farClip;
+                compare = diagonal * halfViewSize / (distance * cameraMaxDistanceFraction);
+                if (box.IsInside(cameraPos))
+                    compare *= diagonal;
+            }
+            else
+                compare = diagonal * invOrthoSize;
+            if (compare < occluderSizeThreshold)
+                continue;
+            float density = numTriangles[i] / diagonal;
+            OccKey k;
+            k.sortValue = density / compare;
+            k.index = i;
+            occluders.Push(k);
+        }
+    }
+    if (occluders.Size())
+        Sort(occluders.Begin(), occluders.End(), OccKeyLess);
+    int n = (int)occluders.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+    {
+        outIdx[i] = occluders[i].index;
+        outKeys[i] = occluders[i].sortValue;
+    }
+    return n;
+}
+
+/// View::DrawOccluders, threaded branch (View.cpp:2233-2234, 2258-2273), over an already sorted occluder list, then the query and the
+/// visibility predicate as ref_run_view.  outCounts4 = submitted triangles, query result size, visible, activeOccluders_.
+int ref_run_view_selected(void* h, int numSelected, const int* selected, const float* occModel12, const void* vtx, unsigned vtxSize, const void* idx,
+    unsigned idxSize, unsigned idxCount, int cullMode, unsigned maxTriangles, unsigned flags, unsigned viewMask, int* outVisible, int cap, int* outCounts4)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    OcclusionBuffer* ob = r->buffer_;
+    if (!r->rawFrustum_)
+        ob->SetView(r->camera_);
+    ob->SetMaxTriangles(maxTriangles);
+    ob->Clear();
+    unsigned submitted = 0, active = 0;
+    for (int i = 0; i < numSelected; ++i)
+    {
+        ++active;
+        ob->SetCullMode((CullMode)cullMode);
+        bool success = ob->AddTriangles(Matrix3x4(occModel12 + 12 * (size_t)selected[i]), vtx, vtxSize, idx, idxSize, 0, idxCount);
+        submitted += idxCount / 3;
+        if (!success)
+            break;
+    }
+    ob->DrawTriangles();
+    ob->BuildDepthHierarchy();
+    const Frustum& fr = r->QueryFrustum();
+    OccludedQuery q(r->result_, fr, ob, (unsigned char)flags, viewMask);
+    r->octree_->GetDrawables(q);
+    int nvis = ref_check_visibility(h, 1, outVisible, cap);
+    if (outCounts4)
+    {
+        outCounts4[0] = (int)submitted;
+        outCounts4[1] = (int)r->result_.Size();
+        outCounts4[2] = nvis;
+        outCounts4[3] = (int)active;
+    }
+    return nvis;
+}
+
 }

@@ -67,6 +67,9 @@ class Ref:
         L.ref_query_shape.argtypes = [C.c_void_p, C.c_int, _f, C.c_uint, C.c_uint, _i, C.c_int]
         L.ref_move_drawables.argtypes = [C.c_void_p, C.c_int, _i, _f]
         L.ref_remove_drawable.argtypes = [C.c_void_p, C.c_int]
+        L.ref_select_occluders.argtypes = [C.c_void_p, C.c_int, _f, _u32, _f, _f, _f, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _i, _f, C.c_int]
+        L.ref_run_view_selected.argtypes = [C.c_void_p, C.c_int, _i, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
+                                            C.c_uint, C.c_uint, _i, C.c_int, _i]
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
         L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
@@ -227,6 +230,34 @@ class Ref:
         out = np.zeros(max(self.n, 1), np.int32)
         n = self.lib.ref_query_shape(self.h, shape, _p(p, _f), flags, view_mask, _p(out, _i), out.shape[0])
         return out[:n].copy()
+
+    def select_occluders(self, scene, view, size_threshold, draw_dist=None, num_triangles=None):
+        """View::UpdateOccluders over the scene's occluder table for the frustum last set.  Returns (occluder indices, sort values), sorted."""
+        k = scene.k
+        tris = np.full(k, scene.mesh_idx.shape[0] // 3, np.uint32) if num_triangles is None else np.ascontiguousarray(num_triangles, np.uint32)
+        dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, np.float32)
+        aabb = np.ascontiguousarray(scene.occ_aabb, np.float32)
+        v12 = np.ascontiguousarray(view.view, np.float32)
+        cp = np.ascontiguousarray(view.position, np.float32)
+        out = np.zeros(max(k, 1), np.int32)
+        keys = np.zeros(max(k, 1), np.float32)
+        n = self.lib.ref_select_occluders(self.h, k, _p(aabb, _f), _p(tris, _u32), _p(dd, _f), _p(v12, _f), _p(cp, _f), int(view.ortho),
+                                          view.half_view_size, view.ortho_size, view.far, size_threshold, _p(out, _i), _p(keys, _f), out.shape[0])
+        return out[:n].copy(), keys[:n].copy()
+
+    def run_view_selected(self, scene, selected, max_triangles, flags=0xFF, view_mask=0xFFFFFFFF):
+        """DrawOccluders' threaded branch over a sorted occluder list with the triangle budget, then query + predicate.
+        Returns (visible ids, (submitted tris, query size, visible, activeOccluders))."""
+        out = np.zeros(max(self.n, 1), np.int32)
+        counts = np.zeros(4, np.int32)
+        sel = np.ascontiguousarray(selected, np.int32)
+        model = np.ascontiguousarray(scene.occ_model, np.float32)
+        vtx = np.ascontiguousarray(scene.mesh_vtx)
+        idx = np.ascontiguousarray(scene.mesh_idx)
+        n = self.lib.ref_run_view_selected(self.h, len(sel), _p(sel, _i), _p(model, _f), vtx.ctypes.data, scene.mesh_stride, idx.ctypes.data,
+                                           idx.itemsize, idx.shape[0], scene.cull_mode, int(max_triangles), flags, view_mask, _p(out, _i), out.shape[0],
+                                           _p(counts, _i))
+        return out[:n].copy(), counts
 
     def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
         """Octree::Raycast / RaycastSingle, RAY_AABB level.  Returns (ids, distances, positions) in result_ order."""

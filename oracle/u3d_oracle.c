@@ -984,3 +984,74 @@ int orc_raycast(const OrcTree* t, const float* ray7, unsigned flags, unsigned vi
     free(state);
     return n;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * Occluder selection: View::UpdateOccluders (View.cpp:2171-2229) + the triangle budget of View::DrawOccluders' threaded branch
+ * (View.cpp:2258-2270, OcclusionBuffer::AddTriangles' return value OB.cpp:178-179, 196-197).  TEST INFRASTRUCTURE ONLY.
+ * cam = view12 (3x4), cam_pos3, ortho, half_view_size, ortho_size, far_clip.  Candidates: table entries passing IsInsideFast, table order.
+ * Writes the sorted occluder indices / sort values; *submitted_n = how many of them the budget lets through.  Returns the sorted count.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+int orc_select_occluders(int num_occ, const float* occ_aabb6, const unsigned* num_tris, const float* draw_dist, const float* planes24,
+    const float* view12, const float* cam_pos3, int ortho, float half_view_size, float ortho_size, float far_clip, float size_threshold,
+    unsigned max_triangles, int* out_idx, float* out_keys, int* submitted_n)
+{
+    KeyVal* a = (KeyVal*)malloc(sizeof(KeyVal) * (size_t)(num_occ > 0 ? num_occ : 1));
+    long n = 0;
+    const float inv_ortho = 1.0f / ortho_size;
+    const float vz0 = view12[8], vz1 = view12[9], vz2 = view12[10], vz3 = view12[11];
+    for (int i = 0; i < num_occ; ++i)
+    {
+        const float* b = occ_aabb6 + 6 * (size_t)i;
+        if (orc_frustum_test(planes24, b, 1) == OUTSIDE)
+            continue;
+        float cx = (b[3] + b[0]) * 0.5f, cy = (b[4] + b[1]) * 0.5f, cz = (b[5] + b[2]) * 0.5f;
+        float distance;
+        if (!ortho)
+        {
+            float dx = cx - cam_pos3[0], dy = cy - cam_pos3[1], dz = cz - cam_pos3[2];
+            distance = sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        else
+            distance = fabsf((vz0 * cx + vz2 * cz) + (vz1 * cy + vz3));
+        float max_distance = draw_dist ? draw_dist[i] : 0.0f;
+        if (!(max_distance <= 0.0f || distance <= max_distance))
+            continue;
+        float sx = b[3] - b[0], sy = b[4] - b[1], sz = b[5] - b[2];
+        float diagonal = sqrtf(sx * sx + sy * sy + sz * sz);
+        float compare;
+        if (!ortho)
+        {
+            float fraction = distance / far_clip;
+            compare = diagonal * half_view_size / (distance * fraction);
+            const float* p = cam_pos3;
+            if (!(p[0] < b[0] || p[0] > b[3] || p[1] < b[1] || p[1] > b[4] || p[2] < b[2] || p[2] > b[5]))
+                compare *= diagonal;
+        }
+        else
+            compare = diagonal * inv_ortho;
+        if (compare < size_threshold)
+            continue;
+        float density = (float)num_tris[i] / diagonal;
+        a[n].key = density / compare;
+        a[n].val = i;
+        ++n;
+    }
+    kv_sort(a, n);
+    unsigned long long total = 0;
+    int sub = 0;
+    for (long i = 0; i < n; ++i)
+    {
+        out_idx[i] = a[i].val;
+        out_keys[i] = a[i].key;
+    }
+    for (long i = 0; i < n; ++i)
+    {
+        ++sub;
+        total += num_tris[a[i].val];
+        if (total > max_triangles)
+            break;
+    }
+    *submitted_n = sub;
+    free(a);
+    return (int)n;
+}

@@ -41,6 +41,7 @@ void orc_ob_read_mip(const OrcOB*, int, int*);
 unsigned orc_ob_num_triangles(const OrcOB*);
 int orc_query(const OrcTree*, int, const float*, const OrcOB*, unsigned, unsigned, int*);
 int orc_check_visibility(const OrcTree*, const OrcOB*, const int*, int, int*);
+int orc_raycast(const OrcTree*, const float*, unsigned, unsigned, int, int*, float*);
 }
 
 using namespace Urho3D::GPUCompute;
@@ -197,6 +198,26 @@ int main()
         for (int i = 0; i < 50; ++i)
             EXPECT(buffer.IsVisible(&boxes[6 * (i * 37 % N)]) == (orc_ob_is_visible(ob, &boxes[6 * (i * 37 % N)]) != 0));
         std::printf("view %d: %u triangles, query %d, visible %d, frustum-only %d\n", viewNo, buffer.GetNumTriangles(), nc, nv, nf);
+    }
+
+    // Octree::Raycast / RaycastSingle with a RAY_AABB-level RayOctreeQuery (Octree.cpp:501-548)
+    {
+        std::vector<GpuRayQueryResult> hits;
+        const float origin[3] = {-90.0f, 1.0f, -85.0f};
+        const float direction[3] = {0.70710678f, 0.0f, 0.70710678f};
+        GpuRayOctreeQuery rq(hits, origin, direction, 400.0f);
+        octree.Raycast(rq);
+        const float ray7[7] = {origin[0], origin[1], origin[2], direction[0], direction[1], direction[2], 400.0f};
+        std::vector<int> pos(S);
+        std::vector<float> dist(S);
+        const int nr = orc_raycast(&otree, ray7, 0xFF, 0xFFFFFFFFu, 0, pos.data(), dist.data());
+        EXPECT((int)hits.size() == nr && nr > 0);
+        for (int i = 0; i < nr && i < (int)hits.size(); ++i)
+            EXPECT((int)hits[i].drawable == order[pos[i]] && std::memcmp(&hits[i].distance, &dist[i], 4) == 0);
+        octree.RaycastSingle(rq);
+        const int ns = orc_raycast(&otree, ray7, 0xFF, 0xFFFFFFFFu, 1, pos.data(), dist.data());
+        EXPECT((int)hits.size() == ns && ns == 1 && (int)hits[0].drawable == order[pos[0]]);
+        std::printf("raycast: %d hits, closest drawable %u at %f\n", nr, hits.empty() ? 0u : hits[0].drawable, hits.empty() ? 0.0 : (double)hits[0].distance);
     }
 
     // a drawable moves: host mirror re-flattened on the next query

@@ -675,3 +675,68 @@ def test_raycasts_match_oracle(gpu_ctx):
     for o in (gs, tree):
         o.close()
     ob.close()
+
+
+@pytest.mark.parametrize("ortho", [False, True])
+def test_occluder_heuristics_and_budget(gpu_ctx, ortho):
+    """SURVEY 8f row 3 on the device: View::UpdateOccluders' selection + DrawOccluders' triangle budget per view.  The set of submitted
+    occluders, the submitted-triangle count, the depth plane and the visible set equal the oracle's, including budgets that cut between
+    occluders with EQUAL sort keys (there the reference's unstable Sort decides, and the device replays it)."""
+    w = h = 128
+    sc = helpers.small_scene(n=6000, k=300, extent=90.0, seed=41)
+    sc.occ_aabb[50:90] = sc.occ_aabb[100:140]
+    sc.occ_model[50:90] = sc.occ_model[100:140]
+    rs = np.random.RandomState(3)
+    draw_dist = np.where(rs.uniform(size=sc.k) < 0.3, rs.uniform(20.0, 120.0, size=sc.k), 0.0).astype(np.float32)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    occ.set_draw_distances(draw_dist)
+    tri = sc.mesh_idx.shape[0] // 3
+    views = []
+    for i in range(20):
+        pos = [rs.uniform(-90, 90), rs.uniform(1.0, 30.0), rs.uniform(-90, 90)]
+        if i % 5 == 0:
+            b = sc.occ_aabb[rs.randint(sc.k)]
+            pos = list((b[:3] + b[3:]) * 0.5)
+        views.append(camera.make_view(pos, rs.uniform(0, 360), rs.uniform(-30, 10), 45.0, 1.0, 0.1, rs.choice([150.0, 400.0]), ortho=ortho,
+                                      ortho_size=rs.choice([20.0, 60.0])))
+    cam3 = np.array([[v.half_view_size, v.ortho_size, v.far] for v in views], np.float32)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    batch.set_views(capi.pack_views(views))
+    tie_cuts = 0
+    # a budget per round; the last rounds put the cut of view `target` exactly between two equal keys
+    budgets = [(0.025, 5000), (0.1, 30 * tri), (0.0, 7 * tri + 5), (0.025, 1 << 30)]
+    for target in range(len(views)):
+        oidx, okeys, _ = oraclebind.select_occluders(sc, views[target], 0.0, 1 << 30, draw_dist)
+        ties = np.nonzero(okeys[1:] == okeys[:-1])[0]
+        if len(ties):
+            budgets.append((0.0, int(ties[0]) * tri + tri - 1))
+    assert len(budgets) > 6
+    for thr, budget in budgets:
+        batch.set_occluder_policy(thr, budget, cam3)
+        batch.run(capi.STAGE_VISIBLE)
+        counts = batch.counts()
+        stats = batch.tri_stats()
+        offsets, ids = batch.packed(capacity=int(counts[:, 1].sum()))
+        for i, v in enumerate(views):
+            oidx, okeys, nsub = oraclebind.select_occluders(sc, v, thr, budget, draw_dist)
+            got = batch.occluder_selection(i)
+            assert sorted(got.tolist()) == sorted(oidx[:nsub].tolist()), "view %d thr %g budget %d" % (i, thr, budget)
+            assert stats[i, 0] == nsub * tri
+            if nsub < len(oidx) and okeys[nsub - 1] == okeys[nsub]:
+                tie_cuts += 1
+            ob.draw_scene_view_selected(sc, v, oidx[:nsub], budget)
+            assert np.array_equal(batch.depth(i), ob.depth())
+            cand = otree.query(1, v.planes, ob, as_ids=False)
+            assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.order[otree.check_visibility(ob, cand)])
+    assert tie_cuts > 0
+    # back to the default rule
+    batch.set_occluder_policy(0, 0, None, enable=False)
+    batch.run(capi.STAGE_VISIBLE)
+    ob.draw_scene_view(sc, views[0])
+    assert np.array_equal(batch.depth(0), ob.depth())
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

@@ -208,3 +208,45 @@ def test_raycast_matches_reference():
     assert nonempty > 100
     ref.close()
     ob.close()
+
+
+@pytest.mark.parametrize("ortho", [False, True])
+def test_occluder_selection_matches_reference(ortho):
+    """View::UpdateOccluders (draw distance, size threshold, density key, Sort) and the triangle budget of DrawOccluders' threaded branch:
+    oracle list == the harness's restatement on the reference's math types and Sort, ties included (duplicated occluders), and the view drawn
+    from that list gives the same buffer, query result and visible set."""
+    from urho3d_b200 import camera
+    w, h = 128, 128
+    sc = helpers.small_scene(n=3000, k=300, extent=90.0, seed=41)
+    sc.occ_aabb[50:90] = sc.occ_aabb[100:140]     # equal sort keys
+    sc.occ_model[50:90] = sc.occ_model[100:140]
+    rs = np.random.RandomState(3)
+    draw_dist = np.where(rs.uniform(size=sc.k) < 0.3, rs.uniform(20.0, 120.0, size=sc.k), 0.0).astype(np.float32)
+    ref = helpers.make_ref(sc, w, h)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    tri = sc.mesh_idx.shape[0] // 3
+    nonempty = cuts = 0
+    for i in range(24):
+        pos = [rs.uniform(-90, 90), rs.uniform(1.0, 30.0), rs.uniform(-90, 90)]
+        if i % 6 == 0:  # camera inside an occluder's box
+            b = sc.occ_aabb[rs.randint(sc.k)]
+            pos = list((b[:3] + b[3:]) * 0.5)
+        v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(-30, 10), 45.0, 1.0, 0.1, rs.choice([150.0, 400.0]), ortho=ortho,
+                             ortho_size=rs.choice([20.0, 60.0]))
+        ref.set_view_raw(v)
+        for thr, budget in ((0.025, 5000), (0.1, 30 * tri), (0.0, 7 * tri + 5), (0.025, 1 << 30)):
+            ridx, rkeys = ref.select_occluders(sc, v, thr, draw_dist)
+            oidx, okeys, nsub = oraclebind.select_occluders(sc, v, thr, budget, draw_dist)
+            assert np.array_equal(ridx, oidx) and np.array_equal(rkeys.view(np.uint32), okeys.view(np.uint32)), (i, thr)
+            vis, counts = ref.run_view_selected(sc, ridx, budget)
+            assert counts[3] == nsub and counts[0] == nsub * tri
+            ob.draw_scene_view_selected(sc, v, oidx[:nsub], budget)
+            assert np.array_equal(ob.depth(), ref.ob_depth())
+            cand = tree.query(1, v.planes, ob, as_ids=False)
+            assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+            nonempty += len(oidx) > 0
+            cuts += nsub < len(oidx)
+    assert nonempty > 40 and cuts > 10
+    ref.close()
+    ob.close()

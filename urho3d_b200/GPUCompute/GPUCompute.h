@@ -17,6 +17,7 @@
 #include "../../include/u3d_gpu.h"
 
 #include <chrono>
+#include <cmath>
 #include <cstring>
 #include <stdexcept>
 #include <string>
@@ -239,6 +240,27 @@ struct GpuShadowCasterOctreeQuery : GpuFrustumOctreeQuery
     int Mode() const override { return U3D_QUERY_SHADOWCASTER; }
 };
 
+/// RayQueryResult (OctreeQuery.h:189-224) as Drawable::ProcessRayQuery fills it at RAY_AABB level (Drawable.cpp:118-132).
+using GpuRayQueryResult = u3d_ray_hit;
+
+/// RayOctreeQuery (OctreeQuery.h:226-260) with level_ fixed to RAY_AABB (per-triangle levels need the drawables' geometry: out of scope).
+/// origin / direction are Ray::origin_ / Ray::direction_ (the caller normalises, as Ray's constructor does).
+struct GpuRayOctreeQuery
+{
+    GpuRayOctreeQuery(std::vector<GpuRayQueryResult>& result, const float* origin3, const float* direction3, float maxDistance = INFINITY,
+        unsigned char drawableFlags = 0xFF, unsigned viewMask = 0xFFFFFFFFu) :
+        result_(result), drawableFlags_(drawableFlags), viewMask_(viewMask), maxDistance_(maxDistance)
+    {
+        std::memcpy(origin_, origin3, sizeof(origin_));
+        std::memcpy(direction_, direction3, sizeof(direction_));
+    }
+    std::vector<GpuRayQueryResult>& result_;
+    float origin_[3], direction_[3];
+    unsigned char drawableFlags_;
+    unsigned viewMask_;
+    float maxDistance_;
+};
+
 /// Mirror of the reference Octree for the query path: host structure kept by the reference's insertion rules, flattened into a
 /// GPU-resident SoA on Sync().  Insert / move / remove stay on the host exactly as SURVEY 2a prescribes.
 class GpuOctree
@@ -339,6 +361,10 @@ public:
         if (queryResultSize)
             *queryResultSize = queryCount;
     }
+    /// Octree::Raycast(RayOctreeQuery&) (Octree.cpp:501-508): every hit, sorted by distance with the reference's Sort procedure.
+    void Raycast(GpuRayOctreeQuery& query) { RaycastImpl(query, false); }
+    /// Octree::RaycastSingle(RayOctreeQuery&) (Octree.cpp:510-548): the closest hit only.
+    void RaycastSingle(GpuRayOctreeQuery& query) { RaycastImpl(query, true); }
     unsigned GetNumOctants() const { return numOctants_; }
     unsigned GetNumDrawables() const { return numDrawables_; }
     u3d_scene* Scene()
@@ -349,6 +375,19 @@ public:
     u3d_octree* Tree() const { return tree_; }
 
 private:
+    void RaycastImpl(GpuRayOctreeQuery& query, bool single)
+    {
+        Sync();
+        const uint32_t cap = numDrawables_ ? numDrawables_ : 1;
+        query.result_.clear();
+        query.result_.resize(cap);
+        const float ray[7] = {query.origin_[0], query.origin_[1], query.origin_[2], query.direction_[0], query.direction_[1], query.direction_[2],
+            query.maxDistance_};
+        uint32_t count = 0;
+        const int rc = u3d_scene_raycast(scene_, 1, ray, query.drawableFlags_, query.viewMask_, single ? 1 : 0, cap, &count, query.result_.data(), nullptr);
+        query.result_.resize(rc < 0 ? 0 : count);
+    }
+
     GpuContext& ctx_;
     u3d_octree* tree_{};
     u3d_scene* scene_{};

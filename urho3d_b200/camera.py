@@ -137,6 +137,8 @@ class CameraView:
         self.reverse_culling = bool(reverse_culling)
         self.position = np.ascontiguousarray(position, dtype=f32)  # camera node world position (Camera::GetDistance)
         self.ortho = bool(ortho)
+        self.half_view_size = 1.0  # Camera::GetHalfViewSize(); make_view fills it in
+        self.ortho_size = 20.0     # Camera::GetOrthoSize() (DEFAULT_ORTHOSIZE, Camera.cpp:39)
 
 
 def make_view(pos, yaw_deg, pitch_deg, fov_deg, aspect, near, far, ortho=False, ortho_size=20.0, zoom=1.0):
@@ -144,8 +146,15 @@ def make_view(pos, yaw_deg, pitch_deg, fov_deg, aspect, near, far, ortho=False, 
     xf = world_transform(pos, q)
     if ortho:
         near = 0.0  # Camera::GetNearClip() reports projNearClip_, which stays 0 for orthographic cameras (Camera.cpp:676-678)
-    return CameraView(inverse_rigid(xf), projection(fov_deg, aspect, near, far, ortho, ortho_size, zoom),
-                      frustum_planes(fov_deg, aspect, near, far, xf, ortho, ortho_size, zoom), near, far, position=pos, ortho=ortho)
+    cv = CameraView(inverse_rigid(xf), projection(fov_deg, aspect, near, far, ortho, ortho_size, zoom),
+                    frustum_planes(fov_deg, aspect, near, far, xf, ortho, ortho_size, zoom), near, far, position=pos, ortho=ortho)
+    # Camera::GetHalfViewSize (Camera.cpp:479-485) and GetOrthoSize: inputs of View::UpdateOccluders' size heuristic
+    if not ortho:
+        cv.half_view_size = float(f32(np.tan(f32(f32(f32(fov_deg) * f32(np.pi / 180.0)) * f32(0.5)))) / f32(zoom))
+    else:
+        cv.half_view_size = float(f32(f32(ortho_size) * f32(0.5)) / f32(zoom))
+    cv.ortho_size = float(f32(ortho_size))
+    return cv
 
 
 def view_proj(proj, view):

@@ -113,6 +113,9 @@ SIGNATURES = {
     "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
     "u3d_scene_raycast": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
     "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "u3d_batch_set_occluder_policy": (C.c_int, [_vp, C.c_int, C.c_float, C.c_uint32, C.POINTER(C.c_float), _vp]),
+    "u3d_occluders_set_draw_distances": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
+    "u3d_batch_read_occluder_selection": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), _vp]),
     "u3d_gather_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
     "u3d_gather_destroy": (None, [_vp]),
     "u3d_gather_export": (C.c_int, [_vp, _vp]),
@@ -327,6 +330,10 @@ class Occluders:
                                         C.byref(h)))
         self.h = h
         self.n = n
+
+    def set_draw_distances(self, draw_distance):
+        d = np.ascontiguousarray(draw_distance, np.float32)
+        _chk(lib().u3d_occluders_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
 
     def close(self):
         if self.h:
@@ -562,6 +569,18 @@ class Batch:
         o, p = _vp(), _vp()
         _chk(lib().u3d_batch_pack_device(self.h, stream, C.byref(o), C.byref(p)))
         return o.value, p.value
+
+    def set_occluder_policy(self, size_threshold, max_triangles, camera3, stream=None, enable=True):
+        """View::UpdateOccluders heuristics + DrawOccluders' triangle budget.  camera3: n x (halfViewSize, orthoSize, farClip)."""
+        cam = None if camera3 is None else np.ascontiguousarray(camera3, np.float32).reshape(-1, 3)
+        _chk(lib().u3d_batch_set_occluder_policy(self.h, int(enable), float(size_threshold), int(max_triangles), _p(cam, _f), stream))
+
+    def occluder_selection(self, view, stream=None):
+        cap = 65536
+        out = np.zeros(cap, np.uint32)
+        c = C.c_uint32()
+        _chk(lib().u3d_batch_read_occluder_selection(self.h, view, _p(out, _u32), cap, C.byref(c), stream))
+        return out[:c.value].astype(np.int64)
 
     def last_launches(self):
         return lib().u3d_batch_last_launches(self.h)

@@ -192,6 +192,7 @@ struct u3d_occluders
     uint32_t totalItems{};
     uint64_t totalTris{};
     DevBuf<float> aabb6, model12;
+    DevBuf<float> drawDist;           // Drawable::GetDrawDistance per occluder (u3d_occluders_set_draw_distances); empty = unlimited
     DevBuf<uint32_t> mesh, start, count;
     DevBuf<MeshDev> meshTable;
 };
@@ -333,6 +334,12 @@ struct u3d_batch
     uint32_t lastLaunches{};
     bool hasBuffers{};
     cudaEvent_t ev[U3D_NUM_PHASES + 1]{};
+    // u3d_batch_set_occluder_policy: View::UpdateOccluders heuristics + triangle budget instead of "every occluder in the frustum"
+    bool rankOccluders{};
+    float sizeThreshold{};
+    uint32_t maxTriangles{};
+    DevBuf<float4> camParams;
+    std::vector<float4> camHost;
     bool pipelined{};  // u3d_batch_set_pipelined
     bool timed{};      // record an event after every phase of the next run
     bool haveEvents{};
@@ -1648,7 +1655,11 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             b->lastLaunches += 1;
         }
         CU_CHECK(mark(1));
-        launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
+        if (b->rankOccluders)
+            launch_select_ranked(vs.views.p, b->camParams.p, V, (int)oc->n, oc->aabb6.p, oc->drawDist.n ? oc->drawDist.p : nullptr, oc->mesh.p, oc->start.p,
+                oc->count.p, b->sizeThreshold, b->maxTriangles, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, vs.flags.p, st);
+        else
+            launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
         CU_CHECK(mark(2));
         launch_scan_regions(V, vs.submitted.p, 64, b->poolTris, vs.triBase.p, vs.triCap.p, vs.flags.p, st);
         CU_CHECK(mark(3));
@@ -1724,6 +1735,8 @@ static int batch_check_flags(u3d_batch* b, cudaStream_t st)
         return fail(U3D_ERR_CAPACITY, "triangle pool too small for this batch: recreate the batch with a larger tri_pool");
     if (flags & kFlagOutOverflow)
         return fail(U3D_ERR_CAPACITY, "a view produced more results than out_capacity");
+    if (flags & kFlagRankOverflow)
+        return fail(U3D_ERR_CAPACITY, "a view has more than 4096 occluder candidates after the size threshold (ranked selection)");
     return U3D_OK;
 }
 
@@ -2196,6 +2209,82 @@ int u3d_gather_status(u3d_gather* g, void* stream)
         return fail(U3D_ERR_CUDA, "result exchange timed out waiting for a peer rank");
     if (status & kGatherOverflow)
         return fail(U3D_ERR_CAPACITY, "result exchange: ids_capacity_per_rank too small for this batch");
+    return U3D_OK;
+}
+
+int u3d_occluders_set_draw_distances(u3d_occluders* o, uint32_t n, const float* draw_distance)
+{
+    if (!o || !draw_distance || n != o->n)
+        return fail(U3D_ERR_INVALID, "u3d_occluders_set_draw_distances: bad argument");
+    CU_CHECK(cudaSetDevice(o->ctx->device));
+    CU_CHECK(o->drawDist.ensure(std::max<uint32_t>(n, 1)));
+    CU_CHECK(cudaMemcpy(o->drawDist.p, draw_distance, (size_t)n * 4, cudaMemcpyHostToDevice));
+    return U3D_OK;
+}
+
+int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold, uint32_t max_triangles, const float* camera3, void* stream)
+{
+    if (!b || (enable && !camera3 && b->numViews))
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: NULL argument");
+    if (!b->hasBuffers)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: the batch has no occluders");
+    b->rankOccluders = enable != 0;
+    if (!enable)
+        return U3D_OK;
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    static bool attr = false;
+    if (!attr)
+    {
+        CU_CHECK(init_rank_kernel());
+        attr = true;
+    }
+    b->sizeThreshold = size_threshold;
+    b->maxTriangles = max_triangles;
+    const uint32_t V = b->numViews;
+    b->camHost.resize(std::max<uint32_t>(V, 1));
+    for (uint32_t v = 0; v < V; ++v)
+        // halfViewSize, invOrthoSize = 1.0f / camera->GetOrthoSize() (View.cpp:2175), farClip
+        b->camHost[v] = make_float4(camera3[3 * v], 1.0f / camera3[3 * v + 1], camera3[3 * v + 2], 0.0f);
+    CU_CHECK(b->camParams.ensure(std::max<uint32_t>(b->vs.maxViews, 1)));
+    if (V)
+    {
+        CU_CHECK(cudaMemcpyAsync(b->camParams.p, b->camHost.data(), (size_t)V * sizeof(float4), cudaMemcpyHostToDevice, st));
+        CU_CHECK(cudaStreamSynchronize(st)); // camHost is reused by the next call
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_read_occluder_selection(u3d_batch* b, uint32_t view, uint32_t* occluder_ids, uint32_t capacity, uint32_t* count, void* stream)
+{
+    if (!b || view >= b->numViews || !count || (capacity && !occluder_ids))
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_occluder_selection: bad argument");
+    if (!b->hasBuffers)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_occluder_selection: the batch has no occluders");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    uint32_t n = 0;
+    CU_CHECK(cudaMemcpyAsync(&n, b->vs.itemCount.p + view, 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    n = std::min(n, b->vs.itemCap);
+    std::vector<DrawItem> items(n);
+    if (n)
+    {
+        CU_CHECK(cudaMemcpyAsync(items.data(), b->vs.items.p + (size_t)view * b->vs.itemCap, (size_t)n * sizeof(DrawItem), cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        if (i && items[i].model == items[i - 1].model)
+            continue; // later <= 256-triangle slices of the same occluder (an occluder is submitted at most once per view)
+        if (m < capacity)
+            occluder_ids[m] = items[i].model;
+        ++m;
+    }
+    *count = m;
+    if (m > capacity)
+        return fail(U3D_ERR_CAPACITY, "u3d_batch_read_occluder_selection: capacity too small");
     return U3D_OK;
 }
 

@@ -86,6 +86,358 @@ __global__ void k_select_occluders(const ViewConst* __restrict__ views, int numO
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Occluder selection with the reference's heuristics: View::UpdateOccluders (View.cpp:2171-2229) -- draw-distance test,
+// screen-size threshold, density sort key, Sort() -- followed by the triangle budget of View::DrawOccluders' threaded branch
+// (View.cpp:2258-2270: occluders are submitted in sorted order until one AddTriangles reports numTriangles_ > maxTriangles_; that
+// occluder is still queued, OB.cpp:178-179).  One CTA per view; candidates = occluders passing IsInsideFast, in table order.
+// The sort is a shared-memory bitonic sort on (key, candidate number).  The reference's Sort is not stable, but the depth buffer only
+// depends on WHICH occluders are drawn, and that set is independent of the order of equal keys unless the budget cut separates two
+// equal keys (or a key is NaN); only then one thread repeats the reference's exact Sort procedure (Container/Sort.h:70-141).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kRankThreads = 256;
+
+__device__ __forceinline__ uint32_t sortable_bits(float f)
+{
+    if (f == 0.0f)
+        f = 0.0f; // -0 and +0 compare equal
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+
+__device__ __forceinline__ float from_sortable_bits(uint32_t s)
+{
+    return __uint_as_float((s & 0x80000000u) ? (s & 0x7FFFFFFFu) : ~s);
+}
+
+/// Block-wide bitonic sort of `P` (power of two) 64-bit keys in shared memory, ascending.
+__device__ __forceinline__ void bitonic_sort_u64(unsigned long long* a, int P)
+{
+    for (int k = 2; k <= P; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1)
+        {
+            __syncthreads();
+            for (int t = threadIdx.x; t < P / 2; t += blockDim.x)
+            {
+                const int i = 2 * t - (t & (j - 1)); // element with bit j clear
+                const int l = i + j;
+                const bool up = (i & k) == 0;
+                const unsigned long long x = a[i], y = a[l];
+                if ((x > y) == up)
+                {
+                    a[i] = y;
+                    a[l] = x;
+                }
+            }
+        }
+    __syncthreads();
+}
+
+/// Container/Sort.h's procedure on (float key, payload) packed as key bits << 32 | payload, run by ONE thread (rare tie-at-the-cut path).
+__device__ void exact_reference_sort(unsigned long long* a, int n)
+{
+    auto key = [&](int i) { return from_sortable_bits((uint32_t)(a[i] >> 32)); };
+    int stackLo[32], stackHi[32];
+    int sp = 0;
+    stackLo[0] = 0;
+    stackHi[0] = n;
+    sp = 1;
+    while (sp)
+    {
+        --sp;
+        int lo = stackLo[sp], hi = stackHi[sp];
+        while (hi - lo > 16)
+        {
+            int p = lo + (hi - lo) / 2;
+            if (key(lo) < key(p) && key(hi - 1) < key(lo))
+                p = lo;
+            else if (key(hi - 1) < key(p) && key(lo) < key(hi - 1))
+                p = hi - 1;
+            const float pv = key(p);
+            int i = lo - 1, j = hi;
+            for (;;)
+            {
+                do
+                    --j;
+                while (pv < key(j));
+                do
+                    ++i;
+                while (key(i) < pv);
+                if (i >= j)
+                    break;
+                const unsigned long long t = a[i];
+                a[i] = a[j];
+                a[j] = t;
+            }
+            // the reference recurses into [lo, j + 1) and continues with [j + 1, hi): the two ranges are independent, so the order in which
+            // they are processed does not change the result.  Push the smaller one (bounded stack), continue with the larger one.
+            const int leftLen = j + 1 - lo, rightLen = hi - (j + 1);
+            if (leftLen < rightLen)
+            {
+                if (sp < 32) { stackLo[sp] = lo; stackHi[sp] = j + 1; ++sp; }
+                lo = j + 1;
+            }
+            else
+            {
+                if (sp < 32) { stackLo[sp] = j + 1; stackHi[sp] = hi; ++sp; }
+                hi = j + 1;
+            }
+        }
+    }
+    for (int i = 1; i < n; ++i)
+    {
+        const unsigned long long t = a[i];
+        const float tk = from_sortable_bits((uint32_t)(t >> 32));
+        int j = i;
+        for (; j > 0 && tk < key(j - 1); --j)
+            a[j] = a[j - 1];
+        a[j] = t;
+    }
+}
+
+__global__ void __launch_bounds__(kRankThreads) k_select_ranked(const ViewConst* __restrict__ views, const float4* __restrict__ camParams, int numOcc,
+    const float* __restrict__ occAabb6, const float* __restrict__ occDrawDist, const uint32_t* __restrict__ occMesh, const uint32_t* __restrict__ occStart,
+    const uint32_t* __restrict__ occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* __restrict__ items, uint32_t itemCap,
+    uint32_t* __restrict__ itemCount, uint32_t* __restrict__ submitted, uint32_t* __restrict__ flags)
+{
+    extern __shared__ __align__(16) unsigned char rankSmem[];
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(rankSmem); // kRankCap entries: sortable key bits << 32 | candidate number
+    uint32_t* candOcc = reinterpret_cast<uint32_t*>(keys + kRankCap);           // candidate number -> occluder
+    __shared__ ViewConst vc;
+    __shared__ float4 cam;
+    __shared__ uint32_t warpTot[kRankThreads / 32], warpTris[kRankThreads / 32];
+    __shared__ uint32_t sCount, sCut, sCarryT, sCarryI, sAmbiguous;
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < (int)(sizeof(ViewConst) / 4); i += kRankThreads)
+        reinterpret_cast<uint32_t*>(&vc)[i] = reinterpret_cast<const uint32_t*>(views + v)[i];
+    if (tid == 0)
+    {
+        cam = camParams[v];
+        sCount = 0;
+        sAmbiguous = 0;
+    }
+    __syncthreads();
+    const float halfViewSize = cam.x, invOrthoSize = cam.y, farClip = cam.z;
+
+    // ---- candidates in table order: frustum test, draw distance, size threshold, sort key ----
+    for (int base = 0; base < numOcc; base += kRankThreads)
+    {
+        const int k = base + tid;
+        bool keep = false;
+        float sortValue = 0.0f;
+        if (k < numOcc)
+        {
+            const float* b = occAabb6 + 6 * (size_t)k;
+            const float mnx = b[0], mny = b[1], mnz = b[2], mxx = b[3], mxy = b[4], mxz = b[5];
+            if (frustum_test<true>(vc.planes, mnx, mny, mnz, mxx, mxy, mxz) != OUTSIDE)
+            {
+                // Drawable::UpdateBatches distance (Drawable.cpp:134-138), Camera::GetDistance (Camera.cpp:487-496)
+                const float cx = (mxx + mnx) * 0.5f, cy = (mxy + mny) * 0.5f, cz = (mxz + mnz) * 0.5f;
+                float distance;
+                if (!vc.ortho)
+                {
+                    const float dx = cx - vc.camPos[0], dy = cy - vc.camPos[1], dz = cz - vc.camPos[2];
+                    distance = sqrtf(dx * dx + dy * dy + dz * dz);
+                }
+                else
+                    distance = fabsf((vc.viewZ[0] * cx + vc.viewZ[2] * cz) + (vc.viewZ[1] * cy + vc.viewZ[3]));
+                const float maxDistance = occDrawDist ? occDrawDist[k] : 0.0f;
+                if (maxDistance <= 0.0f || distance <= maxDistance) // View.cpp:2187-2188
+                {
+                    const float sx = mxx - mnx, sy = mxy - mny, sz = mxz - mnz;
+                    const float diagonal = sqrtf(sx * sx + sy * sy + sz * sz); // box.Size().Length()
+                    float compare;
+                    if (!vc.ortho)
+                    {
+                        const float cameraMaxDistanceFraction = distance / farClip;
+                        compare = diagonal * halfViewSize / (distance * cameraMaxDistanceFraction);
+                        const float px = vc.camPos[0], py = vc.camPos[1], pz = vc.camPos[2];
+                        if (!(px < mnx || px > mxx || py < mny || py > mxy || pz < mnz || pz > mxz)) // box.IsInside(cameraPos)
+                            compare *= diagonal;
+                    }
+                    else
+                        compare = diagonal * invOrthoSize;
+                    if (!(compare < sizeThreshold)) // View.cpp:2208-2209
+                    {
+                        const float density = (float)(occCount[k] / 3) / diagonal;
+                        sortValue = density / compare;
+                        keep = true;
+                    }
+                }
+            }
+        }
+        // ordered compaction
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0)
+            warpTot[wid] = __popc(bal);
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        for (int w = 0; w < kRankThreads / 32; ++w)
+        {
+            if (w < wid)
+                pre += warpTot[w];
+            tot += warpTot[w];
+        }
+        const uint32_t pos = sCount + pre + __popc(bal & ((1u << lane) - 1u));
+        if (keep)
+        {
+            if (pos < (uint32_t)kRankCap)
+            {
+                keys[pos] = ((unsigned long long)sortable_bits(sortValue) << 32) | pos;
+                candOcc[pos] = (uint32_t)k;
+            }
+            if (sortValue != sortValue)
+                sAmbiguous = 1; // NaN keys: only the exact procedure tells where they end up
+        }
+        __syncthreads();
+        if (tid == 0)
+            sCount += tot;
+        __syncthreads();
+    }
+    uint32_t n = sCount;
+    if (n > (uint32_t)kRankCap)
+    {
+        if (tid == 0)
+            atomicOr(flags, kFlagRankOverflow);
+        n = kRankCap;
+    }
+    int P = 1;
+    while (P < (int)n)
+        P <<= 1;
+    for (int i = n + tid; i < P; i += kRankThreads)
+        keys[i] = ~0ull;
+    bitonic_sort_u64(keys, P);
+
+    // ---- budget: occluder i is submitted iff the triangles submitted before it do not exceed maxTriangles ----
+    auto find_cut = [&]() {
+        if (tid == 0)
+        {
+            sCarryT = 0;
+            sCut = n;
+        }
+        __syncthreads();
+        for (uint32_t base = 0; base < n; base += kRankThreads)
+        {
+            const uint32_t i = base + tid;
+            const uint32_t t = i < n ? occCount[candOcc[(uint32_t)keys[i]]] / 3 : 0;
+            uint32_t x = t;
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+                if (lane >= o)
+                    x += y;
+            }
+            if (lane == 31)
+                warpTot[wid] = x;
+            __syncthreads();
+            uint32_t pre = 0, tot = 0;
+            for (int w = 0; w < kRankThreads / 32; ++w)
+            {
+                if (w < wid)
+                    pre += warpTot[w];
+                tot += warpTot[w];
+            }
+            const unsigned long long before = (unsigned long long)sCarryT + pre + x - t; // exclusive prefix
+            if (i < n && before > maxTriangles)
+                atomicMin(&sCut, i);
+            __syncthreads();
+            if (tid == 0)
+                sCarryT = (uint32_t)min((unsigned long long)sCarryT + tot, 0xFFFFFFFFull);
+            __syncthreads();
+        }
+    };
+    find_cut();
+    if (tid == 0 && sCut > 0 && sCut < n)
+    {
+        const float a = from_sortable_bits((uint32_t)(keys[sCut - 1] >> 32)), b = from_sortable_bits((uint32_t)(keys[sCut] >> 32));
+        if (a == b)
+            sAmbiguous = 1;
+    }
+    __syncthreads();
+    if (sAmbiguous)
+    {
+        // back to candidate order (sort by the low word), then the reference's own procedure on one thread
+        for (uint32_t i = tid; i < n; i += kRankThreads)
+            keys[i] = (keys[i] << 32) | (keys[i] >> 32);
+        bitonic_sort_u64(keys, P); // padding (~0) stays at the end
+        for (uint32_t i = tid; i < n; i += kRankThreads)
+            keys[i] = (keys[i] << 32) | (keys[i] >> 32);
+        __syncthreads();
+        if (tid == 0)
+            exact_reference_sort(keys, (int)n);
+        __syncthreads();
+        find_cut();
+    }
+    const uint32_t cut = sCut;
+
+    // ---- draw items of the submitted occluders, in sorted order ----
+    if (tid == 0)
+    {
+        sCarryT = 0;
+        sCarryI = 0;
+    }
+    __syncthreads();
+    for (uint32_t base = 0; base < cut; base += kRankThreads)
+    {
+        const uint32_t i = base + tid;
+        uint32_t k = 0, tris = 0;
+        if (i < cut)
+        {
+            k = candOcc[(uint32_t)keys[i]];
+            tris = occCount[k] / 3;
+        }
+        const uint32_t nsub = (tris + kItemTris - 1) / kItemTris;
+        uint32_t x = nsub, y = tris;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, x, o), c = __shfl_up_sync(0xffffffffu, y, o);
+            if (lane >= o)
+            {
+                x += a;
+                y += c;
+            }
+        }
+        if (lane == 31)
+        {
+            warpTot[wid] = x;
+            warpTris[wid] = y;
+        }
+        __syncthreads();
+        uint32_t pre = 0, tot = 0, totT = 0;
+        for (int w = 0; w < kRankThreads / 32; ++w)
+        {
+            if (w < wid)
+                pre += warpTot[w];
+            tot += warpTot[w];
+            totT += warpTris[w];
+        }
+        const uint32_t first = sCarryI + pre + x - nsub;
+        for (uint32_t sidx = 0; sidx < nsub; ++sidx)
+        {
+            if (first + sidx >= itemCap)
+                break;
+            DrawItem it;
+            it.model = k;
+            it.mesh = occMesh[k];
+            it.start = occStart[k] + 3 * sidx * kItemTris;
+            it.count = 3 * min(tris - sidx * kItemTris, (uint32_t)kItemTris);
+            items[(size_t)v * itemCap + first + sidx] = it;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            sCarryI += tot;
+            sCarryT += totT;
+        }
+        __syncthreads();
+    }
+    if (tid == 0)
+    {
+        itemCount[v] = min(sCarryI, itemCap);
+        submitted[v] = sCarryT;
+    }
+}
+
 /// Per-view triangle regions inside the pool: exclusive scan of (submitted + slack).  One block.
 __global__ void k_scan_regions(int numViews, const uint32_t* __restrict__ submitted, uint32_t slack, uint64_t poolCap,
     uint64_t* __restrict__ triBase, uint32_t* __restrict__ triCap, uint32_t* __restrict__ flags)
@@ -1164,6 +1516,21 @@ void launch_select(const ViewConst* views, int numViews, int numOcc, const float
         return;
     dim3 grid((numOcc + 127) / 128, numViews);
     k_select_occluders<<<grid, 128, 0, s>>>(views, numOcc, occAabb6, occMesh, occStart, occCount, items, itemCap, itemCount, submitted);
+}
+
+cudaError_t init_rank_kernel()
+{
+    return cudaFuncSetAttribute(k_select_ranked, cudaFuncAttributeMaxDynamicSharedMemorySize, kRankCap * 12);
+}
+
+void launch_select_ranked(const ViewConst* views, const float4* camParams, int numViews, int numOcc, const float* occAabb6, const float* occDrawDist,
+    const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* items,
+    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, cudaStream_t s)
+{
+    if (!numOcc || !numViews)
+        return;
+    k_select_ranked<<<numViews, kRankThreads, kRankCap * 12, s>>>(views, camParams, numOcc, occAabb6, occDrawDist, occMesh, occStart, occCount, sizeThreshold,
+        maxTriangles, items, itemCap, itemCount, submitted, flags);
 }
 
 void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,

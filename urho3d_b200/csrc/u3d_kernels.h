@@ -17,6 +17,8 @@ constexpr uint32_t kFlagTriOverflow = 1u;   // a view's triangle region was too 
 constexpr uint32_t kFlagPoolOverflow = 2u;  // the triangle pool cannot hold all regions
 constexpr uint32_t kFlagOutOverflow = 4u;   // a view produced more results than the output capacity
 constexpr uint32_t kFlagIrrOverflow = 8u;   // more irregular triangles than the general-path list holds
+constexpr uint32_t kFlagRankOverflow = 32u;  // a view has more occluder candidates than the ranked selection holds (kRankCap)
+constexpr int kRankCap = 4096;               // occluder candidates per view in k_select_ranked's shared-memory sort
 constexpr uint32_t kFlagClipOverflow = 16u;  // more plane-crossing triangles than the clipper queue holds
 
 // tile path
@@ -80,6 +82,11 @@ struct SceneDev
 void launch_clear(int* depth, size_t nInts, cudaStream_t s);
 void launch_select(const ViewConst* views, int numViews, int numOcc, const float* occAabb6, const uint32_t* occMesh, const uint32_t* occStart,
     const uint32_t* occCount, DrawItem* items, uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, cudaStream_t s);
+/// View::UpdateOccluders heuristics + DrawOccluders' triangle budget per view (camParams: halfViewSize, 1 / orthoSize, farClip per view).
+cudaError_t init_rank_kernel();
+void launch_select_ranked(const ViewConst* views, const float4* camParams, int numViews, int numOcc, const float* occAabb6, const float* occDrawDist,
+    const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* items,
+    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, cudaStream_t s);
 void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,
     cudaStream_t s);
 void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
