@@ -326,14 +326,40 @@ def main():
         cap = min(int(cap_t.item()), V * out_cap)
         comm = torch.cuda.Stream()  # one stream for every slot's collectives: all ranks issue them in the same order
         per = (args.views + world - 1) // world
+        if args.gather == "p2p":
+            # receive block of every slot on every rank; the 64-byte IPC handles are exchanged once, outside the timed region.  If peer memory
+            # cannot be mapped on this box (no P2P between the devices, IPC disabled in the container) every rank falls back to the NCCL gather.
+            def agreed(flag):
+                t = torch.tensor([1 if flag else 0], dtype=torch.int32, device="cuda")
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                return bool(t.item())
+
+            exported = []
+            try:  # local: allocate and export
+                for sl in slots:
+                    g = capi.Gather(ctx, world, rank, per, cap)
+                    exported.append((g, g.export()))
+                ok = True
+            except capi.U3DError as e:
+                sys.stderr.write("rank %d: peer-memory exchange unavailable (%s)\n" % (rank, e))
+                ok = False
+            if agreed(ok):
+                all_handles = [None] * world
+                dist.all_gather_object(all_handles, [h for _, h in exported])  # collective: every rank takes part
+                try:  # local: map the peers' blocks
+                    for i, (g, _) in enumerate(exported):
+                        g.connect([all_handles[r][i] for r in range(world)])
+                        slots[i]["gather"] = g
+                except capi.U3DError as e:
+                    sys.stderr.write("rank %d: peer-memory exchange unavailable (%s)\n" % (rank, e))
+                    ok = False
+                ok = agreed(ok)
+            else:
+                ok = False
+            if not ok:
+                args.gather = "nccl"
         for sl in slots:
             if args.gather == "p2p":
-                # receive block of this slot on every rank; the 64-byte IPC handles are exchanged once, outside the timed region
-                g = capi.Gather(ctx, world, rank, per, cap)
-                handles = [None] * world
-                dist.all_gather_object(handles, g.export())
-                g.connect(handles)
-                sl["gather"] = g
                 continue
             cptr, _, _ = sl["batch"].device_results()
             sl["counts"] = torch.as_tensor(_DevArray(cptr, (V, 2)), device="cuda")

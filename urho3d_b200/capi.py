@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libu3dgpu.so")
+LIB_PATH = os.environ.get("U3D_LIB") or os.path.join(HERE, "lib", "libu3dgpu.so")  # U3D_LIB: build variants in tuning sweeps
 
 RAY_HIT_DTYPE = np.dtype([("position", np.float32, 3), ("normal", np.float32, 3), ("distance", np.float32), ("drawable", np.uint32)])
 QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT, QUERY_RAY, QUERY_RAY_CANDIDATES = 0, 1, 2, 3, 4, 5, 6, 7

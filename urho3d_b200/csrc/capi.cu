@@ -380,6 +380,11 @@ int u3d_debug_set_option(const char* name, int value)
         cull_set_heavy_extent(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "cull_ring") == 0)
+    {
+        cull_set_ring(value);
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "walk_pool") == 0)
     {
         cull_set_walk_pool(value);

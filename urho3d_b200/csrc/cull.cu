@@ -14,11 +14,18 @@ namespace u3d
 {
 
 constexpr int kCullBigRing = 16384;      // queue entries of the one-CTA-per-SM launch shape
-constexpr int kWStack = 256;            // per-warp texel stack of the cooperative range test
+#ifndef U3D_WSTACK
+#define U3D_WSTACK 128
+#endif
+constexpr int kWStackEntries = U3D_WSTACK; // per-warp texel stack of the cooperative range test
 constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks of >= 512 octants = 4M octants
 constexpr int kHeavyExtentDefault = 96;
 __device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)        // rects larger than this (pixels) are tested by a whole warp
-constexpr int kHeavyCap = 512;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
+static int g_cullRingHost = 4096;       // queue entries of the three-CTAs-per-SM shape (2048 / 4096 / 8192)
+#ifndef U3D_HEAVYCAP
+#define U3D_HEAVYCAP 512
+#endif
+constexpr int kHeavyCap = U3D_HEAVYCAP;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
 __device__ int g_walkPool = 0;          // off by default (measured slower: 8.1 vs 6.4 ms, the pass is latency- not issue-bound); 1: the boxes of a warp share one texel stack (range_visible_pool); 0: one walk per lane (tuning hook)
 
 /// T = threads per CTA, R = work-queue entries held in shared memory between evaluation passes.
@@ -31,7 +38,7 @@ template <int T, int R> struct CullShared
     uint32_t visWord[R / 32];    // one ballot word per group of 32 queued drawables
     uint32_t groupOff[R / 32];
     uint32_t warpTot[T / 32];
-    uint32_t wstack[T / 32][T >= 1024 ? kWStack / 2 : kWStack];
+    uint32_t wstack[T / 32][kWStackEntries];
     uint4 heavy[kHeavyCap];           // (left | top << 16, right | bottom << 16, z, queue index | result bits << 30)
     uint32_t heavyCount;
     uint32_t heavyNext;
@@ -663,8 +670,34 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     // When the caller keeps several batches in flight (`pipelined`) other launches fill that wave, and the first shape wins again
     // (3 x 512 views in flight: 1.57 -> 1.35 ms per batch).
     if (numViews > kCullSmallBatch || pipelined)
-        k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
-            outCap, outCounts, zRange, flags);
+    {
+        // queue entries per CTA (tuning hook "cull_ring"): a larger queue means fewer evaluation passes (each ends in block-wide barriers)
+        if (g_cullRingHost == 8192)
+        {
+            static bool a8 = false;
+            if (!a8)
+            {
+                cudaFuncSetAttribute(k_cull_views<512, 3, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 8192>));
+                a8 = true;
+            }
+            k_cull_views<512, 3, 8192><<<numViews, 512, sizeof(CullShared<512, 8192>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
+                outCap, outCounts, zRange, flags);
+        }
+        else if (g_cullRingHost == 4096)
+        {
+            static bool a4 = false;
+            if (!a4)
+            {
+                cudaFuncSetAttribute(k_cull_views<512, 3, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 4096>));
+                a4 = true;
+            }
+            k_cull_views<512, 3, 4096><<<numViews, 512, sizeof(CullShared<512, 4096>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
+                outCap, outCounts, zRange, flags);
+        }
+        else
+            k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
+                outCap, outCounts, zRange, flags);
+    }
     else
     {
         // one CTA per SM has the whole shared memory: a 16K-entry queue means one evaluation pass per ~16K survivors instead of one per 1-2K
@@ -722,6 +755,11 @@ void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRay
 {
     if (numRays)
         k_ray_distances<<<numRays, 128, 0, s>>>(sc, views, slotOfId, outIdx, outCap, outCounts, outDist);
+}
+
+void cull_set_ring(int entries)
+{
+    g_cullRingHost = entries;
 }
 
 void cull_set_walk_pool(int on)

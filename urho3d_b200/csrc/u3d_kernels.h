@@ -116,6 +116,7 @@ void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, 
 void cull_prof_enable(int on);
 void cull_set_heavy_extent(int px);
 void cull_set_walk_pool(int on);
+void cull_set_ring(int entries);
 void cull_prof_read(unsigned long long* out8);
 
 /// OcclusionBuffer::IsVisible for n boxes against view 0's buffer.
