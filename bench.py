@@ -35,14 +35,14 @@ METRIC = "views/sec (1M drawables, 256x256 occlusion)"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--views", type=int, default=4096)
     ap.add_argument("--drawables", type=int, default=1_000_000)
     ap.add_argument("--occluders", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=6, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
+    ap.add_argument("--inflight", type=int, default=8, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 result exchange: p2p = our fused pack+store kernel over NVLink peer memory (u3d_gather_*), nccl = library all-gather")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
@@ -579,6 +579,7 @@ def main():
                 "phases_rank0": phases, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
+            cpu.step()  # warm-up pass (page faults of the forked workers, caches), as the --impl reference arm does
             dt, n, nvis_cpu, _ = cpu.step()
             line["cpu_baseline"] = {"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()}
             cpu.close()

@@ -416,8 +416,13 @@ public:
     bool CullViews(const u3d_view* views, unsigned count, std::vector<unsigned>& ids, bool visibilityPredicate = true)
     {
         const int stage = visibilityPredicate ? U3D_STAGE_VISIBLE : U3D_STAGE_QUERY;
-        if (u3d_batch_set_views(batch_, views, count, nullptr) < 0 || u3d_batch_run(batch_, stage, nullptr) < 0 ||
-            u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
+        if (u3d_batch_set_views(batch_, views, count, nullptr) < 0)
+            return false;
+        if (policy_ && camera3_.size() < 3 * (size_t)count)
+            return false;
+        if (u3d_batch_set_occluder_policy(batch_, policy_ ? 1 : 0, sizeThreshold_, maxTriangles_, policy_ ? camera3_.data() : nullptr, nullptr) < 0)
+            return false;
+        if (u3d_batch_run(batch_, stage, nullptr) < 0 || u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
             return false;
         unsigned long long total = 0;
         for (unsigned v = 0; v < count; ++v)
@@ -428,6 +433,17 @@ public:
         ids.resize(total);
         return true;
     }
+    /// Occluder selection of View::UpdateOccluders + the budget of View::DrawOccluders' threaded branch (View.cpp:2171-2229, 2258-2270) for the
+    /// views given to the next CullViews call.  camera3 = per view (Camera::GetHalfViewSize(), GetOrthoSize(), GetFarClip());
+    /// sizeThreshold = Renderer::GetOccluderSizeThreshold(), maxTriangles = Renderer::GetMaxOccluderTriangles().
+    void SetOccluderPolicy(float sizeThreshold, unsigned maxTriangles, const float* camera3, unsigned count)
+    {
+        policy_ = true;
+        sizeThreshold_ = sizeThreshold;
+        maxTriangles_ = maxTriangles;
+        camera3_.assign(camera3, camera3 + 3 * (size_t)count);
+    }
+    void ClearOccluderPolicy() { policy_ = false; }
     const std::vector<unsigned>& Offsets() const { return offsets_; }
     const std::vector<unsigned>& Counts() const { return counts_; }
     u3d_batch* Handle() const { return batch_; }
@@ -435,6 +451,45 @@ public:
 private:
     u3d_batch* batch_{};
     std::vector<unsigned> counts_, offsets_;
+    bool policy_{};
+    float sizeThreshold_{};
+    unsigned maxTriangles_{};
+    std::vector<float> camera3_;
+};
+
+/// Result exchange between the GPUs of one box: every rank's per-view counts and visible sets land in every rank's receive block,
+/// stored there by the producing rank's own kernel through NVLink peer memory (u3d_gather_*).  One object per batch slot and rank.
+class GpuResultExchange
+{
+public:
+    GpuResultExchange(GpuContext& ctx, int world, int rank, unsigned viewsPerRank, unsigned long long idsCapacityPerRank)
+    {
+        Check(u3d_gather_create(ctx.Handle(), world, rank, viewsPerRank, idsCapacityPerRank, &gather_), "u3d_gather_create");
+    }
+    ~GpuResultExchange() { u3d_gather_destroy(gather_); }
+    GpuResultExchange(const GpuResultExchange&) = delete;
+    GpuResultExchange& operator=(const GpuResultExchange&) = delete;
+
+    /// 64-byte handle of this rank's block for the other processes; Connect takes all ranks' handles in rank order.
+    void Export(void* handle64) { Check(u3d_gather_export(gather_, handle64), "u3d_gather_export"); }
+    void Connect(const void* handlesOfAllRanks) { Check(u3d_gather_connect(gather_, handlesOfAllRanks), "u3d_gather_connect"); }
+    /// Ranks living in one process (one host thread per GPU).
+    void ConnectLocal(GpuResultExchange* const* allRanks, int world)
+    {
+        std::vector<u3d_gather*> h((size_t)world);
+        for (int r = 0; r < world; ++r)
+            h[(size_t)r] = allRanks[r]->gather_;
+        Check(u3d_gather_connect_local(gather_, h.data()), "u3d_gather_connect_local");
+    }
+    /// After the batch's run, on its stream: pack + store into every rank's block + signal.
+    bool Push(GpuViewBatch& batch, void* stream = nullptr) { return u3d_batch_push_results(batch.Handle(), gather_, stream) >= 0; }
+    /// Device-side wait for every rank's results / acknowledgement that they were consumed.
+    bool Wait(void* stream = nullptr) { return u3d_gather_wait(gather_, stream) >= 0; }
+    bool Release(void* stream = nullptr) { return u3d_gather_release(gather_, stream) >= 0; }
+    u3d_gather* Handle() const { return gather_; }
+
+private:
+    u3d_gather* gather_{};
 };
 
 } // namespace GPUCompute
