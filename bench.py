@@ -28,7 +28,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 WIDTH, HEIGHT = 256, 256
-CULL_DRAM_BYTES_PER_VIEW = 131.4e6 / 1184  # ncu --set full capture of k_cull_views<512,3>, profiles/r01_k_cull_views.txt
+CULL_DRAM_BYTES_PER_VIEW = 149.95e6 / 1184  # ncu --set full capture of k_cull_views<512,3,4096>, profiles/r01_k_cull_views.txt
+FLUSH_BYTES = 160 << 20  # > the 126 MB L2
 METRIC = "views/sec (1M drawables, 256x256 occlusion)"
 
 
@@ -65,8 +66,8 @@ def config_dict(args, world):
             "exchange": ("none (1 rank)" if world == 1 else "fused pack + NVLink peer-memory stores + flags (u3d_batch_push_results), every step"
                          if args.gather == "p2p" else "NCCL all_gather_into_tensor of counts and packed ids, every step"),
             "pipelining": "%d batch slots on separate streams; step k runs in slot k %% %d" % (max(1, args.inflight), max(1, args.inflight)),
-            "cache": "L2 flushed before every timed step (256 MiB write, inside the timed region); per-step working set (depth+mips+triangles) "
-                     "also exceeds L2"}
+            "cache": "L2 flushed before every timed step (%d MiB write > 126 MB L2, inside the timed region); per-step working set "
+                     "(depth+mips+triangles) also exceeds L2" % (FLUSH_BYTES >> 20)}
 
 
 # ------------------------------------------------------------------------------------------------------------------------------
@@ -296,7 +297,7 @@ def main():
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
     assert stream != 0
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
 
     # device-resident leg ----------------------------------------------------------------------------------------------------
     # `inflight` result slots, each a u3d_batch on its own stream: step k runs in slot k % inflight, so the tail of one step's kernels (a few
@@ -450,7 +451,7 @@ def main():
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = time.perf_counter()
-    # One event pair around the K steps.  The L2 flush before each step (a 256 MiB write, ~0.04 ms) is inside the timed region.
+    # One event pair around the K steps.  The L2 flush before each step (a 160 MiB write, ~0.045 ms) is inside the timed region.
     ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches = 0
     ev_start.record(tstream)
@@ -571,11 +572,11 @@ def main():
                 "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (CULL_DRAM_BYTES_PER_VIEW * V if dom == "cull" else None),
                              "peak_source": peak_src, "algorithmic_bytes_per_view": alg[dom], "views_per_launch": V,
-                             "traffic_source": "profiles/r01_k_cull_views.txt: dram__bytes_read.sum + dram__bytes_write.sum = 131.4 MB for a 1184-view launch, "
+                             "traffic_source": "profiles/r01_k_cull_views.txt: dram__bytes_read.sum + dram__bytes_write.sum = 150.0 MB for a 1184-view launch, "
                                                "scaled to this launch's views",
                              "note": "algorithmic bytes use SURVEY 8(d)'s flat-scan convention (every AABB read once per view); the octree pass skips "
-                                     "~99% of them and the scene SoA is L2-resident, so frac > 1 and DRAM traffic is ~300x lower: the kernel is "
-                                     "instruction-issue bound (ncu: issue-active 64%, 19 active lanes/instruction), see DESIGN.md 4"},
+                                     "~99% of them and the scene SoA is L2-resident, so frac > 1 and DRAM traffic is ~260x lower: the kernel is "
+                                     "latency / instruction-issue bound (ncu: issue-active 62%, 19 active lanes/instruction, barrier stalls), see DESIGN.md 4"},
                 "phases_rank0": phases, "clocks": clocks}
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
