@@ -740,3 +740,92 @@ def test_occluder_heuristics_and_budget(gpu_ctx, ortho):
     for o in (batch, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+def test_full_size_properties(gpu_ctx):
+    """BASELINE config 3 at full scene size (1M drawables, 4000 occluders, 256x256) over 320 views, checked through properties that need no
+    oracle pass: (a) every launch shape / queue size / walk variant of the cull kernel and a shuffled view order give identical sequences;
+    (b) the visible sequence is an order-preserving subsequence of the occluded query result, which is one of the frustum query result;
+    (c) without occluders the occluded query and the predicate pass everything the frustum query finds; (d) the heuristic occluder policy with
+    an unlimited budget and zero threshold draws the same buffers as the default rule; (e) a second run over the same slot changes nothing."""
+    cfg = scenes.CONFIGS["C3"]
+    sc = scenes.Scene(cfg["n"], cfg["k"], cfg["extent"])
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    none = capi.Occluders(gpu_ctx, sc.occ_aabb[:1] + 1.0e6, sc.occ_model[:1], [mesh], cull_mode=sc.cull_mode)  # one occluder far outside
+    V = 320
+    w = h = 256
+    views = scenes.agent_cameras(V, cfg["extent"], w, h, seed=77)
+    packed = capi.pack_views(views)
+
+    def run(batch, pk, stage=capi.STAGE_VISIBLE):
+        batch.set_views(pk)
+        batch.run(stage)
+        c = batch.counts()
+        off, ids = batch.packed(capacity=int(c[:, 1].sum()))
+        return c, off, ids
+
+    cap = 450000  # a 45-degree frustum reaching across the 1000 x 1000 region holds up to ~0.4M of the 1M drawables
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, V, cap)
+    c0, off0, ids0 = run(batch, packed)
+    depth0 = batch.depth(5).copy()
+    assert c0[:, 1].min() > 0 and (c0[:, 1] <= c0[:, 0]).all() and (c0[:, 1] < c0[:, 0]).any()
+    # (e) idempotence
+    c1, off1, ids1 = run(batch, packed)
+    assert np.array_equal(c0, c1) and np.array_equal(ids0, ids1)
+    # (a) launch shapes and tuning variants
+    for opt, val, restore in (("cull_ring", 2048, 4096), ("cull_ring", 8192, 4096), ("walk_pool", 1, 0), ("heavy_extent", 24, 96)):
+        capi.debug_set_option(opt, val)
+        try:
+            batch.set_pipelined(True)
+            c2, off2, ids2 = run(batch, packed)
+        finally:
+            capi.debug_set_option(opt, restore)
+            batch.set_pipelined(False)
+        assert np.array_equal(c0, c2) and np.array_equal(ids0, ids2), opt
+    batch.set_pipelined(True)   # 320 views: three-CTA shape instead of the one-CTA-per-SM shape
+    c2, off2, ids2 = run(batch, packed)
+    batch.set_pipelined(False)
+    assert np.array_equal(c0, c2) and np.array_equal(ids0, ids2)
+    perm = np.random.RandomState(1).permutation(V)
+    c3, off3, ids3 = run(batch, packed[perm])
+    assert np.array_equal(c3, c0[perm])
+    for j in (0, 17, V - 1):
+        assert np.array_equal(ids3[off3[j]:off3[j + 1]], ids0[off0[perm[j]]:off0[perm[j] + 1]])
+    # (b) subsequence chain: visible <= occluded query <= frustum query
+    cq, offq, idsq = run(batch, packed, capi.STAGE_QUERY)
+    cf, offf, idsf = run(batch, capi.pack_views(views, query_mode=capi.QUERY_FRUSTUM, use_occlusion=False), capi.STAGE_QUERY)
+
+    def is_subsequence(a, b):
+        index_of = {int(x): i for i, x in enumerate(b)}
+        last = -1
+        for x in a:
+            i = index_of.get(int(x), -1)
+            if i <= last:
+                return False
+            last = i
+        return True
+
+    assert np.array_equal(cq[:, 0], c0[:, 0]) and (cq[:, 1] == cq[:, 0]).all() and (cf[:, 0] >= cq[:, 0]).all()
+    for j in range(0, V, 16):
+        vis = ids0[off0[j]:off0[j + 1]]
+        qry = idsq[offq[j]:offq[j + 1]]
+        fru = idsf[offf[j]:offf[j + 1]]
+        assert is_subsequence(vis, qry) and is_subsequence(qry, fru), j
+    # (c) no occluder in sight: nothing is culled by occlusion
+    b2 = capi.Batch(gpu_ctx, gs, none, w, h, V, cap)
+    cn, offn, idsn = run(b2, packed)
+    assert np.array_equal(cn[:, 0], cf[:, 0]) and np.array_equal(cn[:, 1], cf[:, 1]) and np.array_equal(idsn, idsf)
+    assert (b2.depth(3) == 16777216).all()
+    b2.close()
+    # (d) heuristic selection without limits == default rule
+    batch.set_views(packed)
+    cam3 = np.array([[v.half_view_size, v.ortho_size, v.far] for v in views], np.float32)
+    batch.set_occluder_policy(0.0, 1 << 30, cam3)
+    batch.run(capi.STAGE_VISIBLE)
+    c4 = batch.counts()
+    off4, ids4 = batch.packed(capacity=int(c4[:, 1].sum()))
+    assert np.array_equal(c4, c0) and np.array_equal(ids4, ids0) and np.array_equal(batch.depth(5), depth0)
+    for o in (batch, none, occ, mesh, gs, tree):
+        o.close()
