@@ -50,7 +50,9 @@ enum
     U3D_QUERY_POINT = 5,         /* PointOctreeQuery:  planes[0..2] = point */
     /* ray queries (Octree.cpp:257-309): planes[0..6] = origin.xyz, direction.xyz, maxDistance; every octant incl. the root is tested */
     U3D_QUERY_RAY = 6,           /* RayOctreeQuery walk of Octree::Raycast: drawables with Ray::HitDistance(worldBox) < maxDistance */
-    U3D_QUERY_RAY_CANDIDATES = 7 /* RaycastSingle's first pass (GetDrawablesOnlyInternal): all drawables of the octants the ray touches */
+    U3D_QUERY_RAY_CANDIDATES = 7,/* RaycastSingle's first pass (GetDrawablesOnlyInternal): all drawables of the octants the ray touches */
+    U3D_QUERY_ZONE_OCCLUDER = 8  /* ZoneOccluderOctreeQuery, View.cpp:87-113: frustum walk; a drawable passes when its flags are exactly DRAWABLE_ZONE,
+                                    or exactly DRAWABLE_GEOMETRY with IsOccluder() set (u3d_*_set_occluder_flags); drawable_flags is not consulted */
 };
 /* what is emitted */
 enum
@@ -113,6 +115,8 @@ U3D_API int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const 
  * change (the drawable stayed in its octant: u3d_scene_update_boxes is enough), 0 when it did (re-create the scene). */
 /* Drawable::SetDrawDistance for n drawables starting at first_id (0 = unlimited, the default; used by U3D_STAGE_INVIEW). */
 U3D_API int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, const float* draw_distance);
+/* Drawable::SetOccluder for n drawables starting at first_id (default: not an occluder; used by U3D_QUERY_ZONE_OCCLUDER). */
+U3D_API int u3d_octree_set_occluder_flags(u3d_octree* t, uint32_t first_id, uint32_t n, const uint8_t* is_occluder);
 U3D_API int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6]);
 /* Octree::RemoveDrawable path (Octree.h:66-74, DecDrawableCount :123-136). */
 U3D_API int u3d_octree_remove(u3d_octree* t, uint32_t id);
@@ -131,6 +135,8 @@ U3D_API int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t num_octants, const int3
     const uint32_t* view_mask, const uint8_t* occludee, const uint8_t* cast_shadows, u3d_scene** out);
 /* Per-drawable draw distances (indexed by drawable id, 0 = unlimited) for a scene made with u3d_scene_create_flat. */
 U3D_API int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_distance);
+/* Drawable::IsOccluder() per drawable id for a scene made with u3d_scene_create_flat (in place: one bit of each record's meta word). */
+U3D_API int u3d_scene_set_occluder_flags(u3d_scene* s, uint32_t n, const uint8_t* is_occluder);
 /* Dirty-range maintenance: new world boxes for n drawables whose octant did not change (u3d_octree_update returned 1); only their
  * 2 x 12 bytes are rewritten in HBM, the layout and the meta words stay. */
 U3D_API int u3d_scene_update_boxes(u3d_scene* s, uint32_t n, const uint32_t* ids, const float* aabb6, void* stream);

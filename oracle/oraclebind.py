@@ -206,6 +206,16 @@ class OracleTree:
         pos = out[:n].copy()
         return self.order[pos] if as_ids else pos
 
+    def query_zone_occluder(self, planes, is_occluder, view_mask=0xFFFFFFFF):
+        """ZoneOccluderOctreeQuery (View.cpp:87-113).  is_occluder is per drawable id.  Returns drawable ids in result_ order."""
+        p = np.ascontiguousarray(planes, np.float32).reshape(-1)
+        occ = np.ascontiguousarray(np.asarray(is_occluder, np.uint8)[self.order])
+        out = np.zeros(max(len(self.order), 1), np.int32)
+        L = lib()
+        L.orc_query_zone_occluder.argtypes = [C.c_void_p, _f, _u8, C.c_uint, _i]
+        n = L.orc_query_zone_occluder(C.byref(self.t), _p(p, _f), _p(occ, _u8), view_mask, _p(out, _i))
+        return self.order[out[:n]]
+
     def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
         """Octree::Raycast / RaycastSingle at RAY_AABB level.  Returns (drawable ids, distances) in result_ order."""
         ray = np.array(list(origin) + list(direction) + [max_distance], np.float32)

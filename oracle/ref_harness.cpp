@@ -68,6 +68,28 @@ public:
     int id_{};
 };
 
+/// Behavioural restatement of View.cpp:87-113 (class is file-local there): zones and occluders inside a frustum.
+class ZoneOccluderQuery : public FrustumOctreeQuery
+{
+public:
+    ZoneOccluderQuery(PODVector<Drawable*>& result, const Frustum& frustum, unsigned char flags, unsigned mask) :
+        FrustumOctreeQuery(result, frustum, flags, mask) {}
+
+    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
+    {
+        while (start != end)
+        {
+            Drawable* drawable = *start++;
+            unsigned char flags = drawable->GetDrawableFlags();
+            if ((flags == DRAWABLE_ZONE || (flags == DRAWABLE_GEOMETRY && drawable->IsOccluder())) && (drawable->GetViewMask() & viewMask_))
+            {
+                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
+                    result_.Push(drawable);
+            }
+        }
+    }
+};
+
 /// Behavioural restatement of View.cpp:116-158 (class is file-local there).
 class OccludedQuery : public FrustumOctreeQuery
 {
@@ -794,6 +816,20 @@ int ref_run_view_selected(void* h, int numSelected, const int* selected, const f
         outCounts4[3] = (int)active;
     }
     return nvis;
+}
+
+/// Drawable::SetOccluder for every test drawable (by id), then Octree::GetDrawables with the zone / occluder query of View.cpp:803-807.
+int ref_query_zone_occluder(void* h, const unsigned char* isOccluder, unsigned viewMask, int* outIdx, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    for (unsigned i = 0; i < r->drawables_.size(); ++i)
+        r->drawables_[i]->SetOccluder(isOccluder[i] != 0);
+    ZoneOccluderQuery q(r->result_, r->QueryFrustum(), DRAWABLE_GEOMETRY | DRAWABLE_ZONE, viewMask);
+    r->octree_->GetDrawables(q);
+    int n = (int)r->result_.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+        outIdx[i] = static_cast<TestDrawable*>(r->result_[i])->id_;
+    return n;
 }
 
 }

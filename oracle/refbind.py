@@ -70,6 +70,7 @@ class Ref:
         L.ref_select_occluders.argtypes = [C.c_void_p, C.c_int, _f, _u32, _f, _f, _f, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _i, _f, C.c_int]
         L.ref_run_view_selected.argtypes = [C.c_void_p, C.c_int, _i, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
                                             C.c_uint, C.c_uint, _i, C.c_int, _i]
+        L.ref_query_zone_occluder.argtypes = [C.c_void_p, _u8, C.c_uint, _i, C.c_int]
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
         L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
@@ -258,6 +259,13 @@ class Ref:
                                            idx.itemsize, idx.shape[0], scene.cull_mode, int(max_triangles), flags, view_mask, _p(out, _i), out.shape[0],
                                            _p(counts, _i))
         return out[:n].copy(), counts
+
+    def query_zone_occluder(self, is_occluder, view_mask=0xFFFFFFFF):
+        """ZoneOccluderOctreeQuery over the frustum last set; is_occluder per drawable id."""
+        occ = np.ascontiguousarray(is_occluder, np.uint8)
+        out = np.zeros(max(self.n, 1), np.int32)
+        n = self.lib.ref_query_zone_occluder(self.h, _p(occ, _u8), view_mask, _p(out, _i), out.shape[0])
+        return out[:n].copy()
 
     def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
         """Octree::Raycast / RaycastSingle, RAY_AABB level.  Returns (ids, distances, positions) in result_ order."""

@@ -1055,3 +1055,44 @@ int orc_select_occluders(int num_occ, const float* occ_aabb6, const unsigned* nu
     free(a);
     return (int)n;
 }
+
+/* Octree::GetDrawables with ZoneOccluderOctreeQuery (View.cpp:87-113): FrustumOctreeQuery's octant test (OctreeQuery.cpp:98-104); a drawable
+ * passes when its flags are exactly DRAWABLE_ZONE (4), or exactly DRAWABLE_GEOMETRY (1) with IsOccluder(), and its view mask matches, and it
+ * is inside the frustum (octant inside, or IsInsideFast).  occluder[] is per DFS slot.  TEST INFRASTRUCTURE ONLY. */
+int orc_query_zone_occluder(const OrcTree* t, const float* planes24, const unsigned char* occluder, unsigned view_mask, int* out)
+{
+    unsigned char* state = (unsigned char*)malloc((size_t)t->m);
+    int nout = 0;
+    for (int i = 0; i < t->m; ++i)
+    {
+        int inside = 0;
+        if (i > 0)
+        {
+            unsigned char ps = state[t->parent[i]];
+            if (!ps)
+            {
+                state[i] = 0;
+                continue;
+            }
+            inside = ps == 2;
+            int res = inside ? INSIDE : orc_frustum_test(planes24, t->box6 + 6 * (size_t)i, 0);
+            if (res == OUTSIDE)
+            {
+                state[i] = 0;
+                continue;
+            }
+            if (res == INSIDE)
+                inside = 1;
+        }
+        state[i] = inside ? 2 : 1;
+        for (int d = t->first[i]; d < t->first[i] + t->count[i]; ++d)
+        {
+            const unsigned char f = t->flags[d];
+            if ((f == 4 || (f == 1 && occluder[d])) && (t->view_mask[d] & view_mask))
+                if (inside || orc_frustum_test(planes24, t->aabb6 + 6 * (size_t)d, 1) != OUTSIDE)
+                    out[nout++] = d;
+        }
+    }
+    free(state);
+    return nout;
+}

@@ -829,3 +829,47 @@ def test_full_size_properties(gpu_ctx):
     assert np.array_equal(c4, c0) and np.array_equal(ids4, ids0) and np.array_equal(batch.depth(5), depth0)
     for o in (batch, none, occ, mesh, gs, tree):
         o.close()
+
+
+def test_zone_occluder_query(gpu_ctx):
+    """U3D_QUERY_ZONE_OCCLUDER (ZoneOccluderOctreeQuery, View.cpp:87-113) through u3d_octree_query and the batched entry point, occluder flags set
+    on the host mirror (u3d_octree_set_occluder_flags) and in place on the device (u3d_scene_set_occluder_flags)."""
+    sc = helpers.small_scene(n=15000, k=8, extent=100.0, seed=61)
+    rs = np.random.RandomState(8)
+    sc.flags[:] = rs.choice([1, 2, 4, 5, 8], size=sc.n, p=[0.6, 0.1, 0.1, 0.1, 0.1]).astype(np.uint8)
+    sc.view_mask[rs.uniform(size=sc.n) < 0.2] = 0x2
+    occluder = (rs.uniform(size=sc.n) < 0.3).astype(np.uint8)
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    tree.set_occluder_flags(occluder)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, 8, 8)
+    views = scenes.agent_cameras(10, 100.0, 64, 64, seed=3) + helpers.stress_views(100.0, 64, 64, 6, seed=4)
+    total = 0
+    for mask in (0xFFFFFFFF, 0x1):
+        batch = capi.Batch(gpu_ctx, gs, None, 0, 0, len(views), sc.n)
+        batch.set_views(capi.pack_views(views, view_mask=mask, query_mode=capi.QUERY_ZONE_OCCLUDER, use_occlusion=False))
+        batch.run(capi.STAGE_QUERY)
+        counts = batch.counts()
+        offsets, ids = batch.packed(capacity=int(counts[:, 1].sum()))
+        for i, v in enumerate(views):
+            want = otree.query_zone_occluder(v.planes, occluder, mask)
+            assert np.array_equal(ids[offsets[i]:offsets[i + 1]], want), "view %d" % i
+            single, _ = gs.query(v.planes, None, 0xFF, mask, capi.QUERY_ZONE_OCCLUDER, capi.STAGE_QUERY)
+            assert np.array_equal(single, want)
+            total += len(want)
+        batch.close()
+    assert total > 1000
+    # flip the flags in place on the device
+    occluder2 = (1 - occluder).astype(np.uint8)
+    gs.set_occluder_flags(occluder2)
+    want = otree.query_zone_occluder(views[0].planes, occluder2, 0xFFFFFFFF)
+    got, _ = gs.query(views[0].planes, None, 0xFF, 0xFFFFFFFF, capi.QUERY_ZONE_OCCLUDER, capi.STAGE_QUERY)
+    assert np.array_equal(got, want) and len(want) > 0
+    # the other queries do not see the occluder bit
+    f1, _ = gs.query(views[0].planes, None, 0xFF, 0xFFFFFFFF, capi.QUERY_FRUSTUM, capi.STAGE_QUERY)
+    assert np.array_equal(f1, otree.query(0, views[0].planes, None))
+    for o in (gs, tree):
+        o.close()
+    ob.close()

@@ -250,3 +250,26 @@ def test_occluder_selection_matches_reference(ortho):
     assert nonempty > 40 and cuts > 10
     ref.close()
     ob.close()
+
+
+def test_zone_occluder_query_matches_reference():
+    """ZoneOccluderOctreeQuery (View.cpp:87-113): exact-flag match (DRAWABLE_ZONE, or DRAWABLE_GEOMETRY with IsOccluder()), view mask, frustum."""
+    sc = helpers.small_scene(n=5000, k=8, extent=80.0, seed=61)
+    rs = np.random.RandomState(8)
+    sc.flags[:] = rs.choice([1, 2, 4, 5, 8], size=sc.n, p=[0.6, 0.1, 0.1, 0.1, 0.1]).astype(np.uint8)  # 5 = geometry|zone: matches neither test
+    sc.view_mask[rs.uniform(size=sc.n) < 0.2] = 0x2
+    occluder = (rs.uniform(size=sc.n) < 0.3).astype(np.uint8)
+    ref = helpers.make_ref(sc, 64, 64)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, 64, 64)
+    total = 0
+    for v in scenes.agent_cameras(12, 80.0, 64, 64, seed=3) + helpers.stress_views(80.0, 64, 64, 6, seed=4):
+        ref.set_view_raw(v)
+        for mask in (0xFFFFFFFF, 0x1):
+            want = ref.query_zone_occluder(occluder, mask)
+            got = tree.query_zone_occluder(v.planes, occluder, mask)
+            assert np.array_equal(want, got)
+            total += len(want)
+    assert total > 500
+    ref.close()
+    ob.close()

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("U3D_LIB") or os.path.join(HERE, "lib", "libu3dgpu.so")  # U3D_LIB: build variants in tuning sweeps
 
 RAY_HIT_DTYPE = np.dtype([("position", np.float32, 3), ("normal", np.float32, 3), ("distance", np.float32), ("drawable", np.uint32)])
-QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT, QUERY_RAY, QUERY_RAY_CANDIDATES = 0, 1, 2, 3, 4, 5, 6, 7
+QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT, QUERY_RAY, QUERY_RAY_CANDIDATES, QUERY_ZONE_OCCLUDER = 0, 1, 2, 3, 4, 5, 6, 7, 8
 STAGE_QUERY, STAGE_VISIBLE, STAGE_INVIEW = 0, 1, 2
 CULL_NONE, CULL_CCW, CULL_CW = 0, 1, 2
 ERR_CAPACITY = 4
@@ -111,6 +111,8 @@ SIGNATURES = {
     "u3d_batch_pack_device": (C.c_int, [_vp, _vp, C.POINTER(_vp), C.POINTER(_vp)]),
     "u3d_batch_last_launches": (C.c_uint32, [_vp]),
     "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
+    "u3d_octree_set_occluder_flags": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
+    "u3d_scene_set_occluder_flags": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint8)]),
     "u3d_scene_raycast": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
     "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "u3d_batch_set_occluder_policy": (C.c_int, [_vp, C.c_int, C.c_float, C.c_uint32, C.POINTER(C.c_float), _vp]),
@@ -223,6 +225,10 @@ class Octree:
         a = _arr(aabb6, np.float32)
         return bool(_chk(lib().u3d_octree_update(self.h, idx, _p(a, _f))))
 
+    def set_occluder_flags(self, is_occluder, first_id=0):
+        f = np.ascontiguousarray(is_occluder, np.uint8)
+        _chk(lib().u3d_octree_set_occluder_flags(self.h, first_id, f.shape[0], f.ctypes.data_as(C.POINTER(C.c_uint8))))
+
     def set_draw_distances(self, draw_distance, first_id=0):
         d = _arr(draw_distance, np.float32)
         _chk(lib().u3d_octree_set_draw_distances(self.h, first_id, d.shape[0], _p(d, _f)))
@@ -268,6 +274,10 @@ class GpuScene:
     def set_draw_distances(self, draw_distance):
         d = _arr(draw_distance, np.float32)
         _chk(lib().u3d_scene_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
+
+    def set_occluder_flags(self, is_occluder):
+        f = np.ascontiguousarray(is_occluder, np.uint8)
+        _chk(lib().u3d_scene_set_occluder_flags(self.h, f.shape[0], f.ctypes.data_as(C.POINTER(C.c_uint8))))
 
     def raycast(self, rays7, flags=0xFF, view_mask=0xFFFFFFFF, single=False, capacity=4096, stream=None):
         """Octree::Raycast / RaycastSingle (RAY_AABB) for many rays.  rays7: n x (origin, direction, maxDistance).

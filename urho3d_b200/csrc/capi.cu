@@ -492,6 +492,15 @@ int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, 
     return U3D_OK;
 }
 
+int u3d_octree_set_occluder_flags(u3d_octree* t, uint32_t first_id, uint32_t n, const uint8_t* is_occluder)
+{
+    if (!t || (n && !is_occluder))
+        return fail(U3D_ERR_INVALID, "u3d_octree_set_occluder_flags: NULL argument");
+    if (!t->tree.SetOccluderFlags(first_id, n, is_occluder))
+        return fail(U3D_ERR_INVALID, "u3d_octree_set_occluder_flags: drawable id out of range");
+    return U3D_OK;
+}
+
 int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6])
 {
     if (!t || !aabb6)
@@ -695,7 +704,39 @@ int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
         dd[i] = dr[i].drawDistance;
         any |= dd[i] != 0.0f;
     }
-    return any ? u3d_scene_set_draw_distances(*out, (uint32_t)n, dd.data()) : U3D_OK;
+    if (any)
+    {
+        rc = u3d_scene_set_draw_distances(*out, (uint32_t)n, dd.data());
+        if (rc < 0)
+            return rc;
+    }
+    std::vector<uint8_t> occl(std::max<size_t>(n, 1), 0);
+    any = false;
+    for (size_t i = 0; i < n; ++i)
+    {
+        occl[i] = dr[i].occluder;
+        any |= dr[i].occluder;
+    }
+    return any ? u3d_scene_set_occluder_flags(*out, (uint32_t)n, occl.data()) : U3D_OK;
+}
+
+int u3d_scene_set_occluder_flags(u3d_scene* s, uint32_t n, const uint8_t* is_occluder)
+{
+    if (!s || (n && !is_occluder))
+        return fail(U3D_ERR_INVALID, "u3d_scene_set_occluder_flags: NULL argument");
+    CU_CHECK(cudaSetDevice(s->ctx->device));
+    const uint32_t S = (uint32_t)s->dev.numDrawables;
+    std::vector<unsigned char> bySlot(std::max<uint32_t>(S, 1), 0);
+    for (uint32_t id = 0; id < n && id < s->slotOfId.size(); ++id)
+        if (s->slotOfId[id] != 0xFFFFFFFFu)
+            bySlot[s->slotOfId[id]] = is_occluder[id] ? 1 : 0;
+    DevBuf<unsigned char> staging;
+    CU_CHECK(staging.ensure(std::max<uint32_t>(S, 1)));
+    CU_CHECK(cudaMemcpy(staging.p, bySlot.data(), std::max<uint32_t>(S, 1), cudaMemcpyHostToDevice));
+    launch_set_occluder_bits(s->drwMin.p, staging.p, S, s->ctx->stream);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaStreamSynchronize(s->ctx->stream));
+    return U3D_OK;
 }
 
 int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* draw_distance)
@@ -1302,7 +1343,7 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
 {
     if (!scene || !planes24 || (capacity && !out_ids))
         return fail(U3D_ERR_INVALID, "u3d_octree_query: NULL argument");
-    if (query_mode < 0 || query_mode > 5 || stage < 0 || stage > 1)
+    if (query_mode < 0 || (query_mode > 5 && query_mode != QUERY_ZONE_OCCLUDER) || stage < 0 || stage > 1)
         return fail(U3D_ERR_INVALID, "u3d_octree_query: bad mode/stage");
     u3d_ctx* ctx = scene->ctx;
     CU_CHECK(cudaSetDevice(ctx->device));
@@ -2238,12 +2279,7 @@ int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold
         return U3D_OK;
     CU_CHECK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->pick(stream);
-    static bool attr = false;
-    if (!attr)
-    {
-        CU_CHECK(init_rank_kernel());
-        attr = true;
-    }
+    CU_CHECK(init_rank_kernel()); // per device context; cheap
     b->sizeThreshold = size_threshold;
     b->maxTriangles = max_triangles;
     const uint32_t V = b->numViews;

@@ -22,6 +22,9 @@ constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks
 constexpr int kHeavyExtentDefault = 96;
 __device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)        // rects larger than this (pixels) are tested by a whole warp
 static int g_cullRingHost = 4096;       // queue entries of the three-CTAs-per-SM shape (2048 / 4096 / 8192)
+#ifndef U3D_WALK_POOL
+#define U3D_WALK_POOL 0
+#endif
 #ifndef U3D_HEAVYCAP
 #define U3D_HEAVYCAP 512
 #endif
@@ -115,7 +118,11 @@ template <int T, int R> __device__ __forceinline__ bool visible_stage_a(const Bu
     r.left = r.top = r.right = r.bottom = r.z = 0;
     bool vis = false, heavy = false, pooled = false;
     parked = false;
+#if U3D_WALK_POOL
     const bool pool = useMips && g_walkPool && g.nlev <= 8 && g.mw[0] < 4096;
+#else
+    const bool pool = false; // the pooled walk is compiled out by default (measured slower; build with -DU3D_WALK_POOL=1 to compare)
+#endif
     if (active)
     {
         if (ob_project(g, vp, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, r))
@@ -127,12 +134,14 @@ template <int T, int R> __device__ __forceinline__ bool visible_stage_a(const Bu
         else
             vis = range_visible_thread(g, depth, mips, useMips, r);
     }
+#if U3D_WALK_POOL
     if (pool)
     {
         const bool pv = range_visible_pool(g, depth, mips, r, pooled, sh.wstack[threadIdx.x >> 5], (int)(sizeof(sh.wstack[0]) / sizeof(uint32_t)));
         if (pooled)
             vis = pv;
     }
+#endif
     uint32_t todo = __ballot_sync(0xffffffffu, heavy);
     if (todo)
     {
@@ -566,7 +575,10 @@ template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_c
                 const float4 mx = sc.drwMax[d];
                 const uint32_t meta = __float_as_uint(mn.w);
                 // FrustumOctreeQuery::TestDrawables (OctreeQuery.cpp:106-118) / ShadowCasterOctreeQuery (View.cpp:70-82)
-                if ((meta & 0xFFu & vc.drawableFlags) && (__float_as_uint(mx.w) & vc.viewMask) && (!shadowQuery || (meta & kMetaCastShadows)))
+                // ZoneOccluderOctreeQuery (View.cpp:99-112) replaces the flag test: flags == DRAWABLE_ZONE, or == DRAWABLE_GEOMETRY with IsOccluder()
+                const bool flagsOk = vc.queryMode != QUERY_ZONE_OCCLUDER ? (meta & 0xFFu & vc.drawableFlags) != 0
+                                                                         : ((meta & 0xFFu) == 4u || ((meta & 0xFFu) == 1u && (meta & kMetaOccluder)));
+                if (flagsOk && (__float_as_uint(mx.w) & vc.viewMask) && (!shadowQuery || (meta & kMetaCastShadows)))
                     pass = inside || shape_test<true>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
             }
             uint32_t tot;
@@ -674,23 +686,14 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
         // queue entries per CTA (tuning hook "cull_ring"): a larger queue means fewer evaluation passes (each ends in block-wide barriers)
         if (g_cullRingHost == 8192)
         {
-            static bool a8 = false;
-            if (!a8)
-            {
-                cudaFuncSetAttribute(k_cull_views<512, 3, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 8192>));
-                a8 = true;
-            }
+            cudaFuncSetAttribute(k_cull_views<512, 3, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 8192>));
             k_cull_views<512, 3, 8192><<<numViews, 512, sizeof(CullShared<512, 8192>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
                 outCap, outCounts, zRange, flags);
         }
         else if (g_cullRingHost == 4096)
         {
-            static bool a4 = false;
-            if (!a4)
-            {
-                cudaFuncSetAttribute(k_cull_views<512, 3, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 4096>));
-                a4 = true;
-            }
+            // set per launch (~1 us): the attribute belongs to the current device's context, and one process may drive several devices
+            cudaFuncSetAttribute(k_cull_views<512, 3, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 4096>));
             k_cull_views<512, 3, 4096><<<numViews, 512, sizeof(CullShared<512, 4096>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
                 outCap, outCounts, zRange, flags);
         }
@@ -701,12 +704,7 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
     else
     {
         // one CTA per SM has the whole shared memory: a 16K-entry queue means one evaluation pass per ~16K survivors instead of one per 1-2K
-        static bool attrSet = false;
-        if (!attrSet)
-        {
-            cudaFuncSetAttribute(k_cull_views<1024, 1, kCullBigRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<1024, kCullBigRing>));
-            attrSet = true;
-        }
+        cudaFuncSetAttribute(k_cull_views<1024, 1, kCullBigRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<1024, kCullBigRing>));
         k_cull_views<1024, 1, kCullBigRing><<<numViews, 1024, sizeof(CullShared<1024, kCullBigRing>), s>>>(sc, g, views, depth, mips, mipsValid, octState,
             stage, outIdx, outCap, outCounts, zRange, flags);
     }
@@ -755,6 +753,23 @@ void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRay
 {
     if (numRays)
         k_ray_distances<<<numRays, 128, 0, s>>>(sc, views, slotOfId, outIdx, outCap, outCounts, outDist);
+}
+
+/// Drawable::SetOccluder for the drawables in `slots`: sets / clears kMetaOccluder in the meta word of their records.
+__global__ void k_set_occluder_bits(float4* __restrict__ drwMin, const unsigned char* __restrict__ bySlot, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    uint32_t meta = __float_as_uint(drwMin[i].w);
+    meta = bySlot[i] ? (meta | kMetaOccluder) : (meta & ~kMetaOccluder);
+    drwMin[i].w = __uint_as_float(meta);
+}
+
+void launch_set_occluder_bits(float4* drwMin, const unsigned char* bySlot, uint32_t n, cudaStream_t s)
+{
+    if (n)
+        k_set_occluder_bits<<<(n + 255) / 256, 256, 0, s>>>(drwMin, bySlot, n);
 }
 
 void cull_set_ring(int entries)

@@ -22,12 +22,13 @@ constexpr int kMaxLevels = 16;
 enum : int { CULL_NONE = 0, CULL_CCW = 1, CULL_CW = 2 };
 enum : int { OUTSIDE = 0, INTERSECTS = 1, INSIDE = 2 };
 enum : int { QUERY_FRUSTUM = 0, QUERY_OCCLUDED = 1, QUERY_SHADOWCASTER = 2, QUERY_SPHERE = 3, QUERY_BOX = 4, QUERY_POINT = 5, QUERY_RAY = 6,
-    QUERY_RAY_CANDIDATES = 7 };
+    QUERY_RAY_CANDIDATES = 7, QUERY_ZONE_OCCLUDER = 8 };
 enum : int { STAGE_QUERY = 0, STAGE_VISIBLE = 1, STAGE_INVIEW = 2 };
 
 // Per-drawable meta bits packed into the first pad word of the 32-byte AABB record (BoundingBox.h:326-330 layout).
 constexpr uint32_t kMetaOccludee = 1u << 8;
 constexpr uint32_t kMetaCastShadows = 1u << 9;
+constexpr uint32_t kMetaOccluder = 1u << 10;   // Drawable::IsOccluder() (ZoneOccluderOctreeQuery, View.cpp:106)
 
 /// Geometry of one occlusion buffer and its mip chain (OB.cpp:61-113); identical for every view of a batch.
 struct BufGeom
@@ -201,7 +202,7 @@ __device__ __forceinline__ float ray_hit_distance(const float* ray, float mnx, f
 /// of a touched octant (GetDrawablesOnlyInternal, Octree.cpp:284-309: RaycastSingle's candidate pass).
 template <bool FAST> __device__ __forceinline__ int shape_test(int mode, const float* p, float mnx, float mny, float mnz, float mxx, float mxy, float mxz)
 {
-    if (mode <= QUERY_SHADOWCASTER)
+    if (mode <= QUERY_SHADOWCASTER || mode == QUERY_ZONE_OCCLUDER)
         return frustum_test<FAST>(p, mnx, mny, mnz, mxx, mxy, mxz);
     if (mode == QUERY_SPHERE)
     {

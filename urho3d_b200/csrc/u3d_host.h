@@ -32,6 +32,7 @@ struct HDrawable
     bool occludee, castShadows, present;
     int octant;
     float drawDistance{0.0f};
+    bool occluder{false};
 };
 
 /// See octree_host.cpp.
@@ -49,6 +50,14 @@ public:
             return false;
         for (uint32_t i = 0; i < n; ++i)
             drawables_[first + i].drawDistance = d[i];
+        return true;
+    }
+    bool SetOccluderFlags(uint32_t first, uint32_t n, const uint8_t* f)
+    {
+        if ((uint64_t)first + n > drawables_.size())
+            return false;
+        for (uint32_t i = 0; i < n; ++i)
+            drawables_[first + i].occluder = f[i] != 0;
         return true;
     }
     void Flatten(FlatOctree& f) const;

@@ -109,6 +109,7 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
 void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
     const uint32_t* outCounts, float* outDist, cudaStream_t s);
 
+void launch_set_occluder_bits(float4* drwMin, const unsigned char* bySlot, uint32_t n, cudaStream_t s);
 void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s);
 
 /// Diagnostic: in-kernel phase timers of k_cull_views (clock64 sums over all CTAs; slots: 0 prologue, 1 octant sweeps, 2 octant tests,
