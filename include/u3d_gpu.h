@@ -274,6 +274,35 @@ U3D_API int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_t
 U3D_API int u3d_occluders_set_draw_distances(u3d_occluders* o, uint32_t n, const float* draw_distance);
 /* Occluders submitted for `view` by the last run, in submission order (diagnostic / tests; synchronises). */
 U3D_API int u3d_batch_read_occluder_selection(u3d_batch* b, uint32_t view, uint32_t* occluder_ids, uint32_t capacity, uint32_t* count, void* stream);
+/* ---- shadow casters ----
+ * One shadow split of View::ProcessShadowCasters (View.cpp:2379-2407).  The frusta are computed by the host with the engine's own code:
+ * light_view = shadowCamera->GetView(); shadow_camera_frustum = shadowCamera->GetFrustum() planes (point lights: the cube face);
+ * light_view_frustum = planes of cullCamera->GetSplitFrustum(...).Transformed(light_view) (View.cpp:2396-2401);
+ * light_view_frustum_max_z = BoundingBox(lightViewFrustum).max_.z_; skip = 1 for a degenerate split frustum (View.cpp:2406-2407). */
+typedef struct u3d_shadow_split
+{
+    float light_view[12];
+    float shadow_camera_frustum[24];
+    float light_view_frustum[24];
+    float light_view_frustum_max_z;
+    float shadow_far_clip;        /* shadowCamera->GetFarClip() */
+    int32_t shadow_orthographic;  /* shadowCamera->IsOrthographic() */
+    int32_t light_type;           /* LightType (Light.h): 0 LIGHT_DIRECTIONAL, 1 LIGHT_SPOT, 2 LIGHT_POINT */
+    uint32_t light_mask;          /* light->GetLightMask() */
+    int32_t skip;
+    int32_t reserved[2];
+} u3d_shadow_split;
+/* Per-drawable View::GetShadowMask(drawable) (drawable & zone shadow mask, View.h:297-300) and Drawable::GetShadowDistance(), indexed by
+ * drawable id; NULL = 0xFFFFFFFF / 0 (unlimited).  Draw distances come from u3d_*_set_draw_distances. */
+U3D_API int u3d_scene_set_shadow_params(u3d_scene* s, uint32_t n, const uint32_t* shadow_mask, const float* shadow_distance);
+/* The per-drawable loop of View::ProcessShadowCasters + View::IsShadowCasterVisible (View.cpp:2409-2489) over the list every view of the batch
+ * emitted in its last run (directional cascades: a U3D_QUERY_SHADOWCASTER view per split, View.cpp:2365-2366; spot / point lights: the
+ * light's lit-geometry query, one view per split or cube face), splits[v] describing view v.  Lists are filtered in place, order kept; read
+ * them with u3d_batch_read_counts / read_packed.  main_* = the cull camera (Drawable::UpdateBatches' distance for the shadow / draw distance
+ * test); in_view[id] != 0 = Drawable::IsInView(frame_) after the main view's visibility pass (perspective lights' shortcut, View.cpp:2464);
+ * ids >= n_in_view count as not in view.  Synchronises `stream`. */
+U3D_API int u3d_batch_process_shadow_casters(u3d_batch* b, const u3d_shadow_split* splits, const float main_view12[12],
+    const float main_camera_position[3], int main_orthographic, const uint8_t* in_view, uint32_t n_in_view, void* stream);
 /* Kernel launches issued by the last u3d_batch_run / run_part on this batch. */
 U3D_API uint32_t u3d_batch_last_launches(const u3d_batch* b);
 /* Hint that the caller keeps several batches in flight on different streams (e.g. one per worker thread, or frame k+1 submitted while frame k

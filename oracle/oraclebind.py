@@ -266,6 +266,29 @@ def select_occluders(scene, view, size_threshold, max_triangles, draw_dist=None,
     return out[:n].copy(), keys[:n].copy(), sub.value
 
 
+def process_shadow_casters(ids, aabb6, cast_shadows, split, light_type, light_mask, shadow_mask, shadow_distance, draw_distance, in_view, main_view,
+                           main_pos, main_ortho=False):
+    """View::ProcessShadowCasters' per-drawable filter (View.cpp:2409-2489) over `ids` (arrays indexed by drawable id); returns the kept ids."""
+    ids = np.ascontiguousarray(ids, np.int32)
+    out = np.zeros(max(len(ids), 1), np.int32)
+    bb = np.ascontiguousarray(aabb6, np.float32)
+    cs = np.ascontiguousarray(cast_shadows, np.uint8)
+    sm = np.ascontiguousarray(shadow_mask, np.uint32)
+    sd = np.ascontiguousarray(shadow_distance, np.float32)
+    dd = np.ascontiguousarray(draw_distance, np.float32)
+    iv = np.ascontiguousarray(in_view, np.uint8)
+    mv = np.ascontiguousarray(main_view, np.float32).reshape(-1)
+    mp = np.ascontiguousarray(main_pos, np.float32)
+    L = lib()
+    L.orc_process_shadow_casters.argtypes = [C.c_int, _i, _f, _u8, _f, _f, _f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint,
+                                             C.POINTER(C.c_uint), _f, _f, _u8, _f, _f, C.c_int, _i]
+    n = L.orc_process_shadow_casters(len(ids), _p(ids, _i), _p(bb, _f), _p(cs, _u8), _p(split["light_view"], _f), _p(split["shadow_planes"], _f),
+                                     _p(split["lvf_planes"], _f), split["lvf_max_z"], split["shadow_far"], int(split["shadow_ortho"]), light_type,
+                                     light_mask, sm.ctypes.data_as(C.POINTER(C.c_uint)), _p(sd, _f), _p(dd, _f), _p(iv, _u8), _p(mv, _f), _p(mp, _f),
+                                     int(main_ortho), _p(out, _i))
+    return out[:n].copy()
+
+
 def sort_by_key(keys, vals):
     """The restated Sort of Container/Sort.h over (key, payload) pairs."""
     k = np.ascontiguousarray(keys, np.float32).copy()

@@ -832,4 +832,118 @@ int ref_query_zone_occluder(void* h, const unsigned char* isOccluder, unsigned v
     return n;
 }
 
+/// Inputs of View::ProcessShadowCasters for one shadow split, computed with the reference's own Camera / Frustum / BoundingBox code
+/// (View.cpp:2385-2407): the cull camera's split frustum clamped to [nearZ, farZ], transformed into the shadow camera's view space.
+/// cam = pos3, rot4 (w,x,y,z), fov, aspect, near, far, ortho, orthoSize  (10 + 2 floats: see refbind.shadow_split_setup).
+/// Outputs: shadow camera view (12), shadow camera frustum planes (24), light-view frustum planes (24), light-view frustum box max z,
+/// shadow camera far clip; returns 1 when the split frustum is degenerate (vertices_[0] == vertices_[4], View.cpp:2406-2407).
+int ref_shadow_split_setup(void* h, const float* mainCam12, const float* shadowCam12, float nearZ, float farZ, float* lightView12,
+    float* shadowPlanes24, float* lightViewFrustumPlanes24, float* lightViewFrustumMaxZ, float* shadowFarClip)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Context* c = r->context_;
+    auto make = [&](const float* p, SharedPtr<Node>& node) -> Camera* {
+        node = new Node(c);
+        node->SetTransform(Vector3(p), Quaternion(p[3], p[4], p[5], p[6]));
+        Camera* cam = node->CreateComponent<Camera>();
+        cam->SetOrthographic(p[10] != 0.0f);
+        cam->SetFov(p[7]);
+        cam->SetNearClip(p[8]);
+        cam->SetFarClip(p[9]);
+        if (p[10] != 0.0f)
+            cam->SetOrthoSize(p[11]);
+        cam->SetAspectRatio(1.0f);
+        return cam;
+    };
+    SharedPtr<Node> mainNode, shadowNode;
+    Camera* cullCamera = make(mainCam12, mainNode);
+    Camera* shadowCamera = make(shadowCam12, shadowNode);
+    const Matrix3x4& lightView = shadowCamera->GetView();
+    Frustum lightViewFrustum = cullCamera->GetSplitFrustum(nearZ, farZ).Transformed(lightView);
+    BoundingBox lightViewFrustumBox(lightViewFrustum);
+    memcpy(lightView12, lightView.Data(), 12 * sizeof(float));
+    const Frustum& sf = shadowCamera->GetFrustum();
+    for (unsigned i = 0; i < NUM_FRUSTUM_PLANES; ++i)
+    {
+        shadowPlanes24[4 * i] = sf.planes_[i].normal_.x_;
+        shadowPlanes24[4 * i + 1] = sf.planes_[i].normal_.y_;
+        shadowPlanes24[4 * i + 2] = sf.planes_[i].normal_.z_;
+        shadowPlanes24[4 * i + 3] = sf.planes_[i].d_;
+        lightViewFrustumPlanes24[4 * i] = lightViewFrustum.planes_[i].normal_.x_;
+        lightViewFrustumPlanes24[4 * i + 1] = lightViewFrustum.planes_[i].normal_.y_;
+        lightViewFrustumPlanes24[4 * i + 2] = lightViewFrustum.planes_[i].normal_.z_;
+        lightViewFrustumPlanes24[4 * i + 3] = lightViewFrustum.planes_[i].d_;
+    }
+    *lightViewFrustumMaxZ = lightViewFrustumBox.max_.z_;
+    *shadowFarClip = shadowCamera->GetFarClip();
+    return lightViewFrustum.vertices_[0] == lightViewFrustum.vertices_[4] ? 1 : 0;
+}
+
+/// The per-drawable part of View::ProcessShadowCasters + View::IsShadowCasterVisible (View.cpp:2409-2489) restated on the reference's math types
+/// (BoundingBox::Transformed, Frustum::IsInsideFast, Ray, Vector3), over `numIn` drawable ids in order.  Per-drawable state the engine keeps on
+/// the Drawable is injected: shadow mask (View::GetShadowMask), shadow / draw distance, in-view flag (Drawable::IsInView(frame_)); distance_ is
+/// Camera::GetDistance of the cull camera (mainView12 / mainPos3 / mainOrtho, as ref_check_in_view).  Returns the shadow casters kept, in order.
+int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float* lightView12, const float* shadowPlanes24,
+    const float* lightViewFrustumPlanes24, float lightViewFrustumMaxZ, float shadowFarClip, int shadowOrtho, int lightType, unsigned lightMask,
+    const unsigned* shadowMask, const float* shadowDistance, const float* drawDistanceArr, const unsigned char* inView, const float* mainView12,
+    const float* mainPos3, int mainOrtho, int* outIds)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Matrix3x4 lightView(lightView12);
+    Matrix3x4 mainView(mainView12);
+    Vector3 cameraPos(mainPos3);
+    Frustum shadowCameraFrustum, lightViewFrustum;
+    for (unsigned i = 0; i < NUM_FRUSTUM_PLANES; ++i)
+    {
+        shadowCameraFrustum.planes_[i].Define(Vector4(shadowPlanes24[4 * i], shadowPlanes24[4 * i + 1], shadowPlanes24[4 * i + 2], shadowPlanes24[4 * i + 3]));
+        lightViewFrustum.planes_[i].Define(Vector4(lightViewFrustumPlanes24[4 * i], lightViewFrustumPlanes24[4 * i + 1], lightViewFrustumPlanes24[4 * i + 2],
+            lightViewFrustumPlanes24[4 * i + 3]));
+    }
+    int n = 0;
+    for (int k = 0; k < numIn; ++k)
+    {
+        const int id = inIds[k];
+        TestDrawable* drawable = r->drawables_[id];
+        if (!drawable->GetCastShadows())
+            continue;
+        if (!(shadowMask[id] & lightMask))
+            continue;
+        if (lightType == 2 /* LIGHT_POINT */ && shadowCameraFrustum.IsInsideFast(drawable->GetWorldBoundingBox()) == OUTSIDE)
+            continue;
+        float maxShadowDistance = shadowDistance[id];
+        float drawDistance = drawDistanceArr[id];
+        if (drawDistance > 0.0f && (maxShadowDistance <= 0.0f || drawDistance < maxShadowDistance))
+            maxShadowDistance = drawDistance;
+        Vector3 worldPos = drawable->GetWorldBoundingBox().Center();
+        float distance = !mainOrtho ? (worldPos - cameraPos).Length() : Abs((mainView * worldPos).z_);
+        if (maxShadowDistance > 0.0f && distance > maxShadowDistance)
+            continue;
+        BoundingBox lightViewBox = drawable->GetWorldBoundingBox().Transformed(lightView);
+        bool visible;
+        if (shadowOrtho)
+        {
+            lightViewBox.max_.z_ = Max(lightViewBox.max_.z_, lightViewFrustumMaxZ);
+            visible = lightViewFrustum.IsInsideFast(lightViewBox) != OUTSIDE;
+        }
+        else if (inView[id])
+            visible = true;
+        else
+        {
+            Vector3 center = lightViewBox.Center();
+            Ray extrusionRay(center, center);
+            float extrusionDistance = shadowFarClip;
+            float originalDistance = Clamp(center.Length(), M_EPSILON, extrusionDistance);
+            float sizeFactor = extrusionDistance / originalDistance;
+            Vector3 newCenter = extrusionDistance * extrusionRay.direction_;
+            Vector3 newHalfSize = lightViewBox.Size() * sizeFactor * 0.5f;
+            BoundingBox extrudedBox(newCenter - newHalfSize, newCenter + newHalfSize);
+            lightViewBox.Merge(extrudedBox);
+            visible = lightViewFrustum.IsInsideFast(lightViewBox) != OUTSIDE;
+        }
+        if (visible)
+            outIds[n++] = id;
+    }
+    return n;
+}
+
 }

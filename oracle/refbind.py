@@ -71,6 +71,9 @@ class Ref:
         L.ref_run_view_selected.argtypes = [C.c_void_p, C.c_int, _i, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
                                             C.c_uint, C.c_uint, _i, C.c_int, _i]
         L.ref_query_zone_occluder.argtypes = [C.c_void_p, _u8, C.c_uint, _i, C.c_int]
+        L.ref_shadow_split_setup.argtypes = [C.c_void_p, _f, _f, C.c_float, C.c_float, _f, _f, _f, _f, _f]
+        L.ref_process_shadow_casters.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, _f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint, _u32, _f, _f, _u8,
+                                                 _f, _f, C.c_int, _i]
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
         L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
@@ -265,6 +268,37 @@ class Ref:
         occ = np.ascontiguousarray(is_occluder, np.uint8)
         out = np.zeros(max(self.n, 1), np.int32)
         n = self.lib.ref_query_zone_occluder(self.h, _p(occ, _u8), view_mask, _p(out, _i), out.shape[0])
+        return out[:n].copy()
+
+    def shadow_split_setup(self, main_cam, shadow_cam, near_z, far_z):
+        """main_cam / shadow_cam: 12 floats (pos3, rot4 wxyz, fov, near, far, ortho, orthoSize), aspect 1.  Returns a dict with the split inputs of
+        View::ProcessShadowCasters computed by the reference's Camera / Frustum code."""
+        m = np.ascontiguousarray(main_cam, np.float32)
+        sh = np.ascontiguousarray(shadow_cam, np.float32)
+        lv = np.zeros(12, np.float32)
+        sp = np.zeros(24, np.float32)
+        lp = np.zeros(24, np.float32)
+        mz = np.zeros(1, np.float32)
+        fc = np.zeros(1, np.float32)
+        deg = self.lib.ref_shadow_split_setup(self.h, _p(m, _f), _p(sh, _f), near_z, far_z, _p(lv, _f), _p(sp, _f), _p(lp, _f), _p(mz, _f), _p(fc, _f))
+        return dict(light_view=lv, shadow_planes=sp, lvf_planes=lp, lvf_max_z=float(mz[0]), shadow_far=float(fc[0]), degenerate=bool(deg),
+                    shadow_ortho=bool(sh[10] != 0))
+
+    def process_shadow_casters(self, ids, split, light_type, light_mask, shadow_mask, shadow_distance, draw_distance, in_view, main_view, main_pos,
+                               main_ortho=False):
+        """The per-drawable loop of View::ProcessShadowCasters (View.cpp:2409-2450) over `ids`; returns the shadow casters in order."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.zeros(max(len(ids), 1), np.int32)
+        sm = np.ascontiguousarray(shadow_mask, np.uint32)
+        sd = np.ascontiguousarray(shadow_distance, np.float32)
+        dd = np.ascontiguousarray(draw_distance, np.float32)
+        iv = np.ascontiguousarray(in_view, np.uint8)
+        mv = np.ascontiguousarray(main_view, np.float32).reshape(-1)
+        mp = np.ascontiguousarray(main_pos, np.float32)
+        n = self.lib.ref_process_shadow_casters(self.h, len(ids), _p(ids, _i), _p(split["light_view"], _f), _p(split["shadow_planes"], _f),
+                                                _p(split["lvf_planes"], _f), split["lvf_max_z"], split["shadow_far"], int(split["shadow_ortho"]),
+                                                light_type, light_mask, _p(sm, _u32), _p(sd, _f), _p(dd, _f), _p(iv, _u8), _p(mv, _f), _p(mp, _f),
+                                                int(main_ortho), _p(out, _i))
         return out[:n].copy()
 
     def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):

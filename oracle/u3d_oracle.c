@@ -1096,3 +1096,99 @@ int orc_query_zone_occluder(const OrcTree* t, const float* planes24, const unsig
     free(state);
     return nout;
 }
+
+/* ---------------------------------------------------------------------------------------------------------------------------
+ * View::ProcessShadowCasters' per-drawable filter + View::IsShadowCasterVisible (View.cpp:2409-2489).  TEST INFRASTRUCTURE ONLY.
+ * Arithmetic follows the reference's default (URHO3D_SSE) build: BoundingBox::Transformed (BoundingBox.cpp:131-156) sums each row as
+ * (m0*cx + m2*cz) + (m1*cy + m3), Matrix3x4 * Vector3 likewise (Matrix3x4.h:256-274).  All per-drawable arrays are indexed by drawable id.
+ * ------------------------------------------------------------------------------------------------------------------------- */
+static void box_transformed(const float* b, const float* m, float* out6)
+{
+    const float cx = (b[0] + b[3]) * 0.5f, cy = (b[1] + b[4]) * 0.5f, cz = (b[2] + b[5]) * 0.5f;
+    const float hx = cx - b[0], hy = cy - b[1], hz = cz - b[2];
+    for (int r = 0; r < 3; ++r)
+    {
+        const float* row = m + 4 * r;
+        const float c = (row[0] * cx + row[2] * cz) + (row[1] * cy + row[3]);
+        const float d = (fabsf(row[0] * hx) + fabsf(row[2] * hz)) + (fabsf(row[1] * hy) + 0.0f);
+        out6[r] = c - d;
+        out6[3 + r] = c + d;
+    }
+}
+
+int orc_process_shadow_casters(int num_in, const int* in_ids, const float* aabb6, const unsigned char* cast_shadows, const float* light_view12,
+    const float* shadow_planes24, const float* lvf_planes24, float lvf_max_z, float shadow_far_clip, int shadow_ortho, int light_type,
+    unsigned light_mask, const unsigned* shadow_mask, const float* shadow_distance, const float* draw_distance, const unsigned char* in_view,
+    const float* main_view12, const float* main_pos3, int main_ortho, int* out_ids)
+{
+    int n = 0;
+    const float vz0 = main_view12[8], vz1 = main_view12[9], vz2 = main_view12[10], vz3 = main_view12[11];
+    for (int k = 0; k < num_in; ++k)
+    {
+        const int id = in_ids[k];
+        const float* b = aabb6 + 6 * (size_t)id;
+        if (!cast_shadows[id])
+            continue;
+        if (!(shadow_mask[id] & light_mask))
+            continue;
+        if (light_type == 2 && orc_frustum_test(shadow_planes24, b, 1) == OUTSIDE)
+            continue;
+        float max_shadow = shadow_distance[id];
+        const float draw = draw_distance[id];
+        if (draw > 0.0f && (max_shadow <= 0.0f || draw < max_shadow))
+            max_shadow = draw;
+        const float cx = (b[3] + b[0]) * 0.5f, cy = (b[4] + b[1]) * 0.5f, cz = (b[5] + b[2]) * 0.5f;
+        float distance;
+        if (!main_ortho)
+        {
+            const float dx = cx - main_pos3[0], dy = cy - main_pos3[1], dz = cz - main_pos3[2];
+            distance = sqrtf(dx * dx + dy * dy + dz * dz);
+        }
+        else
+            distance = fabsf((vz0 * cx + vz2 * cz) + (vz1 * cy + vz3));
+        if (max_shadow > 0.0f && distance > max_shadow)
+            continue;
+        float lv[6];
+        box_transformed(b, light_view12, lv);
+        int visible;
+        if (shadow_ortho)
+        {
+            lv[5] = lv[5] > lvf_max_z ? lv[5] : lvf_max_z;
+            visible = orc_frustum_test(lvf_planes24, lv, 1) != OUTSIDE;
+        }
+        else if (in_view[id])
+            visible = 1;
+        else
+        {
+            const float ccx = (lv[3] + lv[0]) * 0.5f, ccy = (lv[4] + lv[1]) * 0.5f, ccz = (lv[5] + lv[2]) * 0.5f;
+            const float len2 = ccx * ccx + ccy * ccy + ccz * ccz;
+            float dirx = ccx, diry = ccy, dirz = ccz; /* Ray(center, center): direction_ = center.Normalized(), Vector3.h:425-435 */
+            if (!(fabsf(len2 - 1.0f) <= 0.000001f) && len2 > 0.0f)
+            {
+                const float inv = 1.0f / sqrtf(len2);
+                dirx = ccx * inv;
+                diry = ccy * inv;
+                dirz = ccz * inv;
+            }
+            const float extrusion = shadow_far_clip;
+            float original = sqrtf(len2);
+            if (original < 0.000001f)
+                original = 0.000001f;
+            else if (original > extrusion)
+                original = extrusion;
+            const float factor = extrusion / original;
+            const float ncx = dirx * extrusion, ncy = diry * extrusion, ncz = dirz * extrusion;
+            const float hx = (lv[3] - lv[0]) * factor * 0.5f, hy = (lv[4] - lv[1]) * factor * 0.5f, hz = (lv[5] - lv[2]) * factor * 0.5f;
+            const float e[6] = {ncx - hx, ncy - hy, ncz - hz, ncx + hx, ncy + hy, ncz + hz};
+            for (int a = 0; a < 3; ++a)
+            {
+                lv[a] = lv[a] < e[a] ? lv[a] : e[a];
+                lv[3 + a] = lv[3 + a] > e[3 + a] ? lv[3 + a] : e[3 + a];
+            }
+            visible = orc_frustum_test(lvf_planes24, lv, 1) != OUTSIDE;
+        }
+        if (visible)
+            out_ids[n++] = id;
+    }
+    return n;
+}

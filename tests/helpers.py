@@ -76,3 +76,45 @@ def random_rays(extent, count, seed=1, stacked_boxes=None):
         maxd = np.float32(np.inf) if i % 3 else np.float32(rs.uniform(5.0, 2.0 * extent))
         rays.append((o, d, maxd))
     return rays
+
+
+def shadow_scenarios(ref, extent, count, seed=5, shared_main=False):
+    """Main (cull) camera + shadow camera pairs for View::ProcessShadowCasters tests: directional cascades (orthographic shadow camera, light type
+    0), spot lights (perspective, type 1) and point-light cube faces (90 degree perspective, type 2).  The split inputs come from the reference's
+    own Camera / Frustum code (oracle/_ref: ref.shadow_split_setup), so they are plain inputs for every implementation.
+    Returns a list of dicts: split (see refbind.shadow_split_setup), light_type, main_view (12), main_pos (3), main view object."""
+    from urho3d_b200 import camera
+    rs = np.random.RandomState(seed)
+    out = []
+    main = None
+    for i in range(count):
+        if main is None or not shared_main:  # one frame has one cull camera: shared_main keeps it for every split
+            main = ([rs.uniform(-extent, extent) * 0.5, rs.uniform(1.0, 6.0), rs.uniform(-extent, extent) * 0.5], rs.uniform(0, 360),
+                    rs.uniform(-5, 25), float(rs.choice([120.0, 300.0])))
+        mpos, myaw, mpitch, mfar = main
+        mq = camera.quat_from_euler(mpitch, myaw, 0.0)
+        main_cam = np.array(list(mpos) + list(mq) + [45.0, 0.1, mfar, 0.0, 20.0], np.float32)
+        mv = camera.make_view(mpos, myaw, mpitch, 45.0, 1.0, 0.1, mfar)
+        kind = i % 3
+        if kind == 0:    # directional cascade: orthographic camera above the scene looking down at an angle
+            spos = [mpos[0] + rs.uniform(-30, 30), rs.uniform(80.0, 200.0), mpos[2] + rs.uniform(-30, 30)]
+            sq = camera.quat_from_euler(rs.uniform(40, 80), rs.uniform(0, 360), 0.0)
+            shadow_cam = np.array(list(spos) + list(sq) + [45.0, 0.0, 400.0, 1.0, float(rs.choice([40.0, 120.0, 300.0]))], np.float32)
+            near_z, far_z = float(rs.choice([0.0, 10.0])), float(rs.choice([40.0, 150.0, 1000.0]))
+        elif kind == 1:  # spot light
+            spos = [mpos[0] + rs.uniform(-40, 40), rs.uniform(3.0, 25.0), mpos[2] + rs.uniform(-40, 40)]
+            sq = camera.quat_from_euler(rs.uniform(10, 70), rs.uniform(0, 360), 0.0)
+            shadow_cam = np.array(list(spos) + list(sq) + [float(rs.choice([30.0, 60.0])), 0.5, float(rs.uniform(30, 90)), 0.0, 20.0], np.float32)
+            near_z, far_z = 0.0, float(rs.choice([60.0, 1000.0]))
+        else:            # one face of a point light's cube
+            spos = [mpos[0] + rs.uniform(-40, 40), rs.uniform(1.0, 8.0), mpos[2] + rs.uniform(-40, 40)]
+            pitch, yaw = [(0.0, 90.0), (0.0, -90.0), (-90.0, 0.0), (90.0, 0.0), (0.0, 0.0), (0.0, 180.0)][rs.randint(6)]
+            sq = camera.quat_from_euler(pitch, yaw, 0.0)
+            rng = float(rs.uniform(20, 60))
+            shadow_cam = np.array(list(spos) + list(sq) + [90.0, 0.01 * rng, rng, 0.0, 20.0], np.float32)
+            near_z, far_z = 0.0, 1000.0
+        split = ref.shadow_split_setup(main_cam, shadow_cam, near_z, far_z)
+        if split["degenerate"]:
+            continue
+        out.append(dict(split=split, light_type=kind, main_view=mv.view.reshape(-1).copy(), main_pos=np.array(mpos, np.float32), view=mv))
+    return out

@@ -873,3 +873,69 @@ def test_zone_occluder_query(gpu_ctx):
     for o in (gs, tree):
         o.close()
     ob.close()
+
+
+def test_process_shadow_casters(gpu_ctx):
+    """SURVEY 8f row 4: View::ProcessShadowCasters + IsShadowCasterVisible on the device, one split per batch view (directional cascades, spot
+    lights, point-light cube faces), over the lists a frustum query emitted; the filtered sequences equal the oracle's (which is pinned to the
+    reference's math in tests/test_oracle_vs_reference.py).  The split inputs come from the reference's own Camera / Frustum code."""
+    from oracle import refbind
+    if not refbind.available():
+        pytest.skip("oracle/_ref/libu3dref.so not built")
+    sc = helpers.small_scene(n=20000, k=8, extent=100.0, seed=71)
+    rs = np.random.RandomState(9)
+    shadow_mask = np.where(rs.uniform(size=sc.n) < 0.15, 0x2, 0xFFFFFFFF).astype(np.uint32)
+    shadow_dist = np.where(rs.uniform(size=sc.n) < 0.3, rs.uniform(10.0, 80.0, size=sc.n), 0.0).astype(np.float32)
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.3, rs.uniform(10.0, 80.0, size=sc.n), 0.0).astype(np.float32)
+    in_view = (rs.uniform(size=sc.n) < 0.3).astype(np.uint8)
+    ref = refbind.Ref(0)
+    scen = helpers.shadow_scenarios(ref, 100.0, 36, seed=6, shared_main=True)
+    ref.close()
+    assert len(scen) >= 24 and {s["light_type"] for s in scen} == {0, 1, 2}
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    tree.set_draw_distances(draw_dist)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    gs.set_shadow_params(shadow_mask, shadow_dist)
+    otree, ob = helpers.make_oracle(sc, flat, 8, 8)
+    views = []
+    for s in scen:
+        planes = s["split"]["shadow_planes"].reshape(6, 4)
+        views.append(camera.CameraView(s["split"]["light_view"].reshape(3, 4), np.eye(4, dtype=np.float32), planes, 0.1, s["split"]["shadow_far"]))
+    batch = capi.Batch(gpu_ctx, gs, None, 0, 0, len(views), sc.n)
+    kept = dropped = 0
+    for light_mask in (0xFFFFFFFF, 0x1):
+        splits = np.zeros(len(scen), capi.SHADOW_SPLIT_DTYPE)
+        for i, s in enumerate(scen):
+            sp = s["split"]
+            splits[i]["light_view"] = sp["light_view"]
+            splits[i]["shadow_camera_frustum"] = sp["shadow_planes"]
+            splits[i]["light_view_frustum"] = sp["lvf_planes"]
+            splits[i]["light_view_frustum_max_z"] = sp["lvf_max_z"]
+            splits[i]["shadow_far_clip"] = sp["shadow_far"]
+            splits[i]["shadow_orthographic"] = int(sp["shadow_ortho"])
+            splits[i]["light_type"] = s["light_type"]
+            splits[i]["light_mask"] = light_mask
+        splits[3]["skip"] = 1
+        batch.set_views(capi.pack_views(views, query_mode=capi.QUERY_FRUSTUM, use_occlusion=False))
+        batch.run(capi.STAGE_QUERY)
+        before = batch.counts()
+        batch.process_shadow_casters(splits, scen[0]["main_view"], scen[0]["main_pos"], False, in_view)
+        counts = batch.counts()
+        assert np.array_equal(counts[:, 0], before[:, 0])  # the query result size stays, the emitted list shrinks
+        offsets, ids = batch.packed(capacity=int(counts[:, 1].sum()))
+        for i, s in enumerate(scen):
+            cand = otree.query(0, s["split"]["shadow_planes"], None)
+            assert before[i, 1] == len(cand)
+            want = oraclebind.process_shadow_casters(cand, sc.aabb, sc.cast_shadows, s["split"], s["light_type"], light_mask, shadow_mask,
+                                                     shadow_dist, draw_dist, in_view, s["main_view"], s["main_pos"])
+            if i == 3:
+                want = want[:0]
+            assert np.array_equal(ids[offsets[i]:offsets[i + 1]], want), "split %d type %d" % (i, s["light_type"])
+            kept += len(want)
+            dropped += len(cand) - len(want)
+    assert kept > 2000 and dropped > 2000
+    for o in (batch, gs, tree):
+        o.close()
+    ob.close()

@@ -273,3 +273,33 @@ def test_zone_occluder_query_matches_reference():
     assert total > 500
     ref.close()
     ob.close()
+
+
+def test_process_shadow_casters_matches_reference():
+    """View::ProcessShadowCasters' per-drawable filter + IsShadowCasterVisible (View.cpp:2409-2489): the oracle against the harness's restatement on
+    the reference's BoundingBox::Transformed / Frustum::IsInsideFast / Ray / Vector3 code, for directional (orthographic extrusion), spot and point
+    (perspective extrusion, in-view shortcut, cube-face frustum test) splits, with shadow masks, shadow / draw distances and cast-shadow flags."""
+    sc = helpers.small_scene(n=8000, k=8, extent=100.0, seed=71)
+    rs = np.random.RandomState(9)
+    shadow_mask = np.where(rs.uniform(size=sc.n) < 0.15, 0x2, 0xFFFFFFFF).astype(np.uint32)
+    shadow_dist = np.where(rs.uniform(size=sc.n) < 0.3, rs.uniform(10.0, 80.0, size=sc.n), 0.0).astype(np.float32)
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.3, rs.uniform(10.0, 80.0, size=sc.n), 0.0).astype(np.float32)
+    in_view = (rs.uniform(size=sc.n) < 0.3).astype(np.uint8)
+    ref = helpers.make_ref(sc, 64, 64)
+    ids_all = np.arange(sc.n, dtype=np.int32)
+    rs.shuffle(ids_all)
+    kept = dropped = 0
+    kinds = set()
+    for s in helpers.shadow_scenarios(ref, 100.0, 30):
+        for light_mask in (0xFFFFFFFF, 0x1):
+            want = ref.process_shadow_casters(ids_all, s["split"], s["light_type"], light_mask, shadow_mask, shadow_dist, draw_dist, in_view,
+                                              s["main_view"], s["main_pos"])
+            got = oraclebind.process_shadow_casters(ids_all, sc.aabb, sc.cast_shadows, s["split"], s["light_type"], light_mask, shadow_mask,
+                                                    shadow_dist, draw_dist, in_view, s["main_view"], s["main_pos"])
+            assert np.array_equal(want, got), (s["light_type"], light_mask)
+            kept += len(want)
+            dropped += sc.n - len(want)
+            if len(want):
+                kinds.add(s["light_type"])
+    assert kept > 5000 and dropped > 5000 and kinds == {0, 1, 2}
+    ref.close()

@@ -10,6 +10,9 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("U3D_LIB") or os.path.join(HERE, "lib", "libu3dgpu.so")  # U3D_LIB: build variants in tuning sweeps
 
+SHADOW_SPLIT_DTYPE = np.dtype([("light_view", np.float32, 12), ("shadow_camera_frustum", np.float32, 24), ("light_view_frustum", np.float32, 24),
+                               ("light_view_frustum_max_z", np.float32), ("shadow_far_clip", np.float32), ("shadow_orthographic", np.int32),
+                               ("light_type", np.int32), ("light_mask", np.uint32), ("skip", np.int32), ("reserved", np.int32, 2)])
 RAY_HIT_DTYPE = np.dtype([("position", np.float32, 3), ("normal", np.float32, 3), ("distance", np.float32), ("drawable", np.uint32)])
 QUERY_FRUSTUM, QUERY_OCCLUDED, QUERY_SHADOWCASTER, QUERY_SPHERE, QUERY_BOX, QUERY_POINT, QUERY_RAY, QUERY_RAY_CANDIDATES, QUERY_ZONE_OCCLUDER = 0, 1, 2, 3, 4, 5, 6, 7, 8
 STAGE_QUERY, STAGE_VISIBLE, STAGE_INVIEW = 0, 1, 2
@@ -113,6 +116,8 @@ SIGNATURES = {
     "u3d_batch_set_pipelined": (C.c_int, [_vp, C.c_int]),
     "u3d_octree_set_occluder_flags": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.POINTER(C.c_uint8)]),
     "u3d_scene_set_occluder_flags": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint8)]),
+    "u3d_scene_set_shadow_params": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_float)]),
+    "u3d_batch_process_shadow_casters": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint8), C.c_uint32, _vp]),
     "u3d_scene_raycast": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
     "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "u3d_batch_set_occluder_policy": (C.c_int, [_vp, C.c_int, C.c_float, C.c_uint32, C.POINTER(C.c_float), _vp]),
@@ -274,6 +279,12 @@ class GpuScene:
     def set_draw_distances(self, draw_distance):
         d = _arr(draw_distance, np.float32)
         _chk(lib().u3d_scene_set_draw_distances(self.h, d.shape[0], _p(d, _f)))
+
+    def set_shadow_params(self, shadow_mask=None, shadow_distance=None):
+        m = None if shadow_mask is None else np.ascontiguousarray(shadow_mask, np.uint32)
+        d = None if shadow_distance is None else np.ascontiguousarray(shadow_distance, np.float32)
+        n = len(m) if m is not None else (len(d) if d is not None else 0)
+        _chk(lib().u3d_scene_set_shadow_params(self.h, n, _p(m, _u32), _p(d, _f)))
 
     def set_occluder_flags(self, is_occluder):
         f = np.ascontiguousarray(is_occluder, np.uint8)
@@ -591,6 +602,16 @@ class Batch:
         c = C.c_uint32()
         _chk(lib().u3d_batch_read_occluder_selection(self.h, view, _p(out, _u32), cap, C.byref(c), stream))
         return out[:c.value].astype(np.int64)
+
+    def process_shadow_casters(self, splits, main_view, main_pos, main_ortho=False, in_view=None, stream=None):
+        """View::ProcessShadowCasters over the lists of the last run, in place.  splits: SHADOW_SPLIT_DTYPE array, one per view."""
+        sp = np.ascontiguousarray(splits, SHADOW_SPLIT_DTYPE)
+        assert sp.shape[0] == self.n
+        mv = np.ascontiguousarray(main_view, np.float32).reshape(-1)
+        mp = np.ascontiguousarray(main_pos, np.float32)
+        iv = None if in_view is None else np.ascontiguousarray(in_view, np.uint8)
+        _chk(lib().u3d_batch_process_shadow_casters(self.h, sp.ctypes.data, _p(mv, _f), _p(mp, _f), int(main_ortho),
+                                                    None if iv is None else iv.ctypes.data_as(C.POINTER(C.c_uint8)), 0 if iv is None else len(iv), stream))
 
     def last_launches(self):
         return lib().u3d_batch_last_launches(self.h)

@@ -163,6 +163,12 @@ struct u3d_scene
     DevBuf<uint32_t> updSlots;       // staging of u3d_scene_update_boxes
     DevBuf<float> updBoxes;
     std::vector<uint32_t> slotOfId;  // drawable id -> DFS slot (for late per-drawable uploads)
+    // View::ProcessShadowCasters inputs (u3d_scene_set_shadow_params / u3d_batch_process_shadow_casters)
+    DevBuf<uint32_t> shadowMask;      // per DFS slot; empty = 0xFFFFFFFF everywhere
+    DevBuf<float> shadowDistance;     // per DFS slot; empty = 0 (unlimited)
+    bool hasShadowParams{};
+    DevBuf<unsigned char> inView;     // per drawable id
+    DevBuf<ShadowSplitDev> splits;
     // ray queries (u3d_scene_raycast): device copy of slotOfId + scratch, all grow-only
     DevBuf<uint32_t> slotOfIdDev;
     bool slotOfIdUploaded{};
@@ -1452,6 +1458,79 @@ void urho_sort(RayKey* a, long n)
 extern "C"
 {
 
+} // extern "C"
+
+/// Device copy of the drawable id -> DFS slot map (uploaded on first use).
+static int ensure_slot_map(u3d_scene* s, cudaStream_t st)
+{
+    if (!s->slotOfIdUploaded)
+    {
+        CU_CHECK(s->slotOfIdDev.ensure(std::max<size_t>(s->slotOfId.size(), 1)));
+        if (!s->slotOfId.empty())
+            CU_CHECK(cudaMemcpyAsync(s->slotOfIdDev.p, s->slotOfId.data(), s->slotOfId.size() * 4, cudaMemcpyHostToDevice, st));
+        s->slotOfIdUploaded = true;
+    }
+    return U3D_OK;
+}
+
+extern "C"
+{
+
+int u3d_scene_set_shadow_params(u3d_scene* s, uint32_t n, const uint32_t* shadow_mask, const float* shadow_distance)
+{
+    if (!s)
+        return fail(U3D_ERR_INVALID, "u3d_scene_set_shadow_params: NULL argument");
+    CU_CHECK(cudaSetDevice(s->ctx->device));
+    const uint32_t S = std::max<uint32_t>((uint32_t)s->dev.numDrawables, 1);
+    std::vector<uint32_t> m(S, 0xFFFFFFFFu);
+    std::vector<float> d(S, 0.0f);
+    for (uint32_t id = 0; id < n && id < s->slotOfId.size(); ++id)
+        if (s->slotOfId[id] != 0xFFFFFFFFu)
+        {
+            if (shadow_mask)
+                m[s->slotOfId[id]] = shadow_mask[id];
+            if (shadow_distance)
+                d[s->slotOfId[id]] = shadow_distance[id];
+        }
+    CU_CHECK(s->shadowMask.ensure(S));
+    CU_CHECK(s->shadowDistance.ensure(S));
+    CU_CHECK(cudaMemcpy(s->shadowMask.p, m.data(), (size_t)S * 4, cudaMemcpyHostToDevice));
+    CU_CHECK(cudaMemcpy(s->shadowDistance.p, d.data(), (size_t)S * 4, cudaMemcpyHostToDevice));
+    s->hasShadowParams = true;
+    return U3D_OK;
+}
+
+int u3d_batch_process_shadow_casters(u3d_batch* b, const u3d_shadow_split* splits, const float main_view12[12], const float main_camera_position[3],
+    int main_orthographic, const uint8_t* in_view, uint32_t n_in_view, void* stream)
+{
+    static_assert(sizeof(u3d_shadow_split) == sizeof(ShadowSplitDev), "u3d_shadow_split and ShadowSplitDev must have the same layout");
+    if (!b || !splits || !main_view12 || !main_camera_position || (n_in_view && !in_view))
+        return fail(U3D_ERR_INVALID, "u3d_batch_process_shadow_casters: NULL argument");
+    if (!b->numViews)
+        return U3D_OK;
+    u3d_scene* s = b->scene;
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    int rc = ensure_slot_map(s, st);
+    if (rc < 0)
+        return rc;
+    CU_CHECK(s->splits.ensure(b->numViews));
+    CU_CHECK(cudaMemcpyAsync(s->splits.p, splits, (size_t)b->numViews * sizeof(ShadowSplitDev), cudaMemcpyHostToDevice, st));
+    if (n_in_view)
+    {
+        CU_CHECK(s->inView.ensure(n_in_view));
+        CU_CHECK(cudaMemcpyAsync(s->inView.p, in_view, n_in_view, cudaMemcpyHostToDevice, st));
+    }
+    const float4 mainPos = make_float4(main_camera_position[0], main_camera_position[1], main_camera_position[2], main_orthographic ? 1.0f : 0.0f);
+    const float4 mainViewZ = make_float4(main_view12[8], main_view12[9], main_view12[10], main_view12[11]);
+    launch_shadow_casters(s->dev, s->splits.p, (int)b->numViews, s->slotOfIdDev.p, s->hasShadowParams ? s->shadowMask.p : nullptr,
+        s->hasShadowParams ? s->shadowDistance.p : nullptr, n_in_view ? s->inView.p : nullptr, n_in_view, mainPos, mainViewZ, b->outIdx.p, b->outCap,
+        b->outCounts.p, st);
+    CU_CHECK(cudaGetLastError());
+    CU_CHECK(cudaStreamSynchronize(st)); // `splits` / `in_view` are the caller's host memory
+    return U3D_OK;
+}
+
 int u3d_sort_by_key(uint32_t n, float* keys, uint32_t* values)
 {
     if (n && (!keys || !values))
@@ -1482,13 +1561,9 @@ int u3d_scene_raycast(u3d_scene* s, uint32_t n_rays, const float* rays7, uint32_
     cudaStream_t st = ctx->pick(stream);
     // RaycastSingle needs EVERY candidate of the touched octants (its winner is decided by the sort); size the device lists accordingly
     const uint32_t devCap = std::max<uint32_t>(capacity, 1);
-    if (!s->slotOfIdUploaded)
-    {
-        CU_CHECK(s->slotOfIdDev.ensure(std::max<size_t>(s->slotOfId.size(), 1)));
-        if (!s->slotOfId.empty())
-            CU_CHECK(cudaMemcpyAsync(s->slotOfIdDev.p, s->slotOfId.data(), s->slotOfId.size() * 4, cudaMemcpyHostToDevice, st));
-        s->slotOfIdUploaded = true;
-    }
+    int rcMap = ensure_slot_map(s, st);
+    if (rcMap < 0)
+        return rcMap;
     s->rayHost.assign(n_rays, ViewConst{});
     for (uint32_t i = 0; i < n_rays; ++i)
     {

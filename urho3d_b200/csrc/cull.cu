@@ -772,6 +772,96 @@ void launch_set_occluder_bits(float4* drwMin, const unsigned char* bySlot, uint3
         k_set_occluder_bits<<<(n + 255) / 256, 256, 0, s>>>(drwMin, bySlot, n);
 }
 
+/// View::ProcessShadowCasters' per-drawable loop (View.cpp:2409-2450) over the list each view emitted: cast-shadow flag, shadow mask & light
+/// mask, the cube-face frustum for point lights, shadow / draw distance against Drawable::UpdateBatches' distance to the MAIN camera, and
+/// IsShadowCasterVisible.  One block per view (= shadow split); the list is compacted in place, order kept.
+__global__ void __launch_bounds__(256) k_shadow_casters(SceneDev sc, const ShadowSplitDev* __restrict__ splits, const uint32_t* __restrict__ slotOfId,
+    const uint32_t* __restrict__ shadowMask, const float* __restrict__ shadowDistance, const unsigned char* __restrict__ inView, uint32_t numInView,
+    float4 mainPos /* xyz, w = ortho flag */, float4 mainViewZ, uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts)
+{
+    __shared__ ShadowSplitDev sp;
+    __shared__ uint32_t warpTot[8];
+    __shared__ uint32_t sCursor;
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < (int)(sizeof(ShadowSplitDev) / 4); i += 256)
+        reinterpret_cast<uint32_t*>(&sp)[i] = reinterpret_cast<const uint32_t*>(splits + v)[i];
+    if (tid == 0)
+        sCursor = 0;
+    __syncthreads();
+    const uint32_t n = sp.skip ? 0u : min(outCounts[2 * v + 1], outCap);
+    uint32_t* ids = outIdx + (size_t)v * outCap;
+    const bool mainOrtho = mainPos.w != 0.0f;
+    for (uint32_t base = 0; base < n; base += 256)
+    {
+        const uint32_t i = base + tid;
+        bool keep = false;
+        uint32_t id = 0;
+        if (i < n)
+        {
+            id = ids[i];
+            const uint32_t d = slotOfId[id];
+            const float4 mn = sc.drwMin[d], mx = sc.drwMax[d];
+            const uint32_t meta = __float_as_uint(mn.w);
+            keep = (meta & kMetaCastShadows) != 0;
+            if (keep && shadowMask)
+                keep = (shadowMask[d] & sp.lightMask) != 0;
+            if (keep && sp.lightType == 2)
+                keep = frustum_test<true>(sp.shadowPlanes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+            if (keep)
+            {
+                float maxShadowDistance = shadowDistance ? shadowDistance[d] : 0.0f;
+                const float drawDistance = sc.drwDrawDist[d];
+                if (drawDistance > 0.0f && (maxShadowDistance <= 0.0f || drawDistance < maxShadowDistance))
+                    maxShadowDistance = drawDistance;
+                if (maxShadowDistance > 0.0f)
+                {
+                    const float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
+                    float dist;
+                    if (!mainOrtho)
+                    {
+                        const float dx = cx - mainPos.x, dy = cy - mainPos.y, dz = cz - mainPos.z;
+                        dist = sqrtf(dx * dx + dy * dy + dz * dz);
+                    }
+                    else
+                        dist = fabsf((mainViewZ.x * cx + mainViewZ.z * cz) + (mainViewZ.y * cy + mainViewZ.w));
+                    if (dist > maxShadowDistance)
+                        keep = false;
+                }
+            }
+            if (keep)
+                keep = shadow_caster_visible(sp, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, inView && id < numInView && inView[id]);
+        }
+        const uint32_t bal = __ballot_sync(0xffffffffu, keep);
+        if (lane == 0)
+            warpTot[wid] = __popc(bal);
+        __syncthreads(); // every read of this chunk is done; positions written below are <= the positions read
+        uint32_t pre = 0, tot = 0;
+        for (int w = 0; w < 8; ++w)
+        {
+            if (w < wid)
+                pre += warpTot[w];
+            tot += warpTot[w];
+        }
+        if (keep)
+            ids[sCursor + pre + __popc(bal & ((1u << lane) - 1u))] = id;
+        __syncthreads();
+        if (tid == 0)
+            sCursor += tot;
+        __syncthreads();
+    }
+    if (tid == 0)
+        outCounts[2 * v + 1] = sCursor;
+}
+
+void launch_shadow_casters(const SceneDev& sc, const ShadowSplitDev* splits, int numViews, const uint32_t* slotOfId, const uint32_t* shadowMask,
+    const float* shadowDistance, const unsigned char* inView, uint32_t numInView, float4 mainPos, float4 mainViewZ, uint32_t* outIdx, uint32_t outCap,
+    uint32_t* outCounts, cudaStream_t s)
+{
+    if (numViews)
+        k_shadow_casters<<<numViews, 256, 0, s>>>(sc, splits, slotOfId, shadowMask, shadowDistance, inView, numInView, mainPos, mainViewZ, outIdx, outCap,
+            outCounts);
+}
+
 void cull_set_ring(int entries)
 {
     g_cullRingHost = entries;

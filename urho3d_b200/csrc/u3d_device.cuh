@@ -56,6 +56,22 @@ struct ViewConst
     int pad;
 };
 
+/// One shadow split of View::ProcessShadowCasters (View.cpp:2379-2407); same layout as u3d_shadow_split (include/u3d_gpu.h).
+struct ShadowSplitDev
+{
+    float lightView[12];           // shadowCamera->GetView()
+    float shadowPlanes[24];        // shadowCamera->GetFrustum(): tested for point lights (View.cpp:2422)
+    float lvfPlanes[24];           // lightViewFrustum (scene split frustum in light view space)
+    float lvfMaxZ;                 // BoundingBox(lightViewFrustum).max_.z_
+    float shadowFarClip;           // shadowCamera->GetFarClip()
+    int shadowOrtho;               // shadowCamera->IsOrthographic()
+    int lightType;                 // 0 directional, 1 spot, 2 point
+    uint32_t lightMask;
+    int skip;                      // degenerate split frustum: no shadow casters
+    int reserved[2];
+};
+static_assert(sizeof(ShadowSplitDev) == 272, "ShadowSplitDev layout");
+
 /// One set-up triangle, self-contained per half (closed form of the incremental loops OB.cpp:897-1001):
 /// rows [y0,y1) use edge set T, rows [y1,y2) use edge set B.  For row y of a half starting at ys, k = y - ys:
 ///   xl = (lx + k*lxs) >> 16, xr = (rx + k*rxs) >> 16, depth at pixel x = lz + k*lzs + (x - xl)*dzdx,
@@ -190,6 +206,59 @@ __device__ __forceinline__ float ray_hit_distance(const float* ray, float mnx, f
         }
     }
     return dist;
+}
+
+/// View::IsShadowCasterVisible (View.cpp:2452-2489) after BoundingBox::Transformed(lightView) (BoundingBox.cpp:131-156, the default URHO3D_SSE
+/// build: each row is summed as (m0*cx + m2*cz) + (m1*cy + m3), the extents as (|m0*hx| + |m2*hz|) + (|m1*hy| + 0)).
+__device__ __forceinline__ bool shadow_caster_visible(const ShadowSplitDev& sp, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, bool inView)
+{
+    const float cx = (mnx + mxx) * 0.5f, cy = (mny + mxy) * 0.5f, cz = (mnz + mxz) * 0.5f;
+    const float hx = cx - mnx, hy = cy - mny, hz = cz - mnz;
+    float lo[3], hi[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+    {
+        const float* row = sp.lightView + 4 * r;
+        const float c = (row[0] * cx + row[2] * cz) + (row[1] * cy + row[3]);
+        const float d = (fabsf(row[0] * hx) + fabsf(row[2] * hz)) + (fabsf(row[1] * hy) + 0.0f);
+        lo[r] = c - d;
+        hi[r] = c + d;
+    }
+    if (sp.shadowOrtho)
+    {
+        // extrude up to the far edge of the frustum's light-space box
+        hi[2] = hi[2] > sp.lvfMaxZ ? hi[2] : sp.lvfMaxZ;
+        return frustum_test<true>(sp.lvfPlanes, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]) != OUTSIDE;
+    }
+    if (inView)
+        return true; // a visible object's shadow is visible too (View.cpp:2464-2465)
+    const float ccx = (hi[0] + lo[0]) * 0.5f, ccy = (hi[1] + lo[1]) * 0.5f, ccz = (hi[2] + lo[2]) * 0.5f;
+    const float len2 = ccx * ccx + ccy * ccy + ccz * ccz;
+    float dx = ccx, dy = ccy, dz = ccz; // Ray(center, center).direction_ = center.Normalized() (Vector3.h:425-435)
+    if (!(fabsf(len2 - 1.0f) <= 0.000001f) && len2 > 0.0f)
+    {
+        const float inv = 1.0f / sqrtf(len2);
+        dx = ccx * inv;
+        dy = ccy * inv;
+        dz = ccz * inv;
+    }
+    const float extrusion = sp.shadowFarClip;
+    float original = sqrtf(len2); // Clamp(center.Length(), M_EPSILON, extrusionDistance)
+    if (original < 0.000001f)
+        original = 0.000001f;
+    else if (original > extrusion)
+        original = extrusion;
+    const float factor = extrusion / original;
+    const float ncx = dx * extrusion, ncy = dy * extrusion, ncz = dz * extrusion;
+    const float ex = (hi[0] - lo[0]) * factor * 0.5f, ey = (hi[1] - lo[1]) * factor * 0.5f, ez = (hi[2] - lo[2]) * factor * 0.5f;
+    const float e0 = ncx - ex, e1 = ncy - ey, e2 = ncz - ez, e3 = ncx + ex, e4 = ncy + ey, e5 = ncz + ez;
+    lo[0] = lo[0] < e0 ? lo[0] : e0; // BoundingBox::Merge, SSE min / max semantics (BoundingBox.h:201-206)
+    lo[1] = lo[1] < e1 ? lo[1] : e1;
+    lo[2] = lo[2] < e2 ? lo[2] : e2;
+    hi[0] = hi[0] > e3 ? hi[0] : e3;
+    hi[1] = hi[1] > e4 ? hi[1] : e4;
+    hi[2] = hi[2] > e5 ? hi[2] : e5;
+    return frustum_test<true>(sp.lvfPlanes, lo[0], lo[1], lo[2], hi[0], hi[1], hi[2]) != OUTSIDE;
 }
 
 /// Octant / drawable test of every GPU-evaluable OctreeQuery.  FAST = the drawable form (IsInsideFast), else the 3-way octant form.

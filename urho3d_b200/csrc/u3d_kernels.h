@@ -109,6 +109,10 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
 void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
     const uint32_t* outCounts, float* outDist, cudaStream_t s);
 
+/// View::ProcessShadowCasters over the lists the views emitted (one split per view), in place.
+void launch_shadow_casters(const SceneDev& sc, const ShadowSplitDev* splits, int numViews, const uint32_t* slotOfId, const uint32_t* shadowMask,
+    const float* shadowDistance, const unsigned char* inView, uint32_t numInView, float4 mainPos, float4 mainViewZ, uint32_t* outIdx, uint32_t outCap,
+    uint32_t* outCounts, cudaStream_t s);
 void launch_set_occluder_bits(float4* drwMin, const unsigned char* bySlot, uint32_t n, cudaStream_t s);
 void launch_update_boxes(float4* drwMin, float4* drwMax, const uint32_t* slots, const float* boxes, uint32_t n, cudaStream_t s);
 
