@@ -268,10 +268,17 @@ U3D_API int u3d_batch_pack_device(u3d_batch* b, void* stream, void** offsets_dev
  * camera3 = n x (Camera::GetHalfViewSize(), Camera::GetOrthoSize(), Camera::GetFarClip()) for the views last set; call again after
  * every u3d_batch_set_views.  Where the budget cut separates occluders with EQUAL sort keys the reference's own (unstable) Sort
  * procedure is replayed on the device, so the selected set is the reference's.  At most 4096 candidates per view survive the size
- * threshold (-U3D_ERR_CAPACITY at the next read otherwise).  enable = 0 returns to the default rule. */
+ * threshold (-U3D_ERR_CAPACITY at the next read otherwise).  enable = 0 returns to the default rule.
+ * enable = 2 selects the NON-threaded branch of View::DrawOccluders instead (View.cpp:2236-2256; the engine's default, since
+ * Renderer::threadedOcclusion_ is off): occluders are drawn one after the other in sorted order, each one after the first only if
+ * OcclusionBuffer::IsVisible(its box) holds against what has been drawn so far (pixel scan, the hierarchy being dirty), and the budget sees
+ * numTriangles_ = submitted triangles + source triangles that drew something (OB.cpp:196-197, 681-682).  Serial per view, parallel over
+ * views; slower than mode 1 but identical to a stock engine configuration.  Equal sort keys always replay the reference's Sort here. */
 U3D_API int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold, uint32_t max_triangles, const float* camera3, void* stream);
 /* Drawable::GetDrawDistance() of every occluder (0 = unlimited, the default), used by the policy above (View.cpp:2186-2188). */
 U3D_API int u3d_occluders_set_draw_distances(u3d_occluders* o, uint32_t n, const float* draw_distance);
+/* View::activeOccluders_ of every view after a run in mode 2 (occluders that passed the IsVisible gate and were submitted). */
+U3D_API int u3d_batch_read_active_occluders(u3d_batch* b, uint32_t* active, void* stream);
 /* Occluders submitted for `view` by the last run, in submission order (diagnostic / tests; synchronises). */
 U3D_API int u3d_batch_read_occluder_selection(u3d_batch* b, uint32_t view, uint32_t* occluder_ids, uint32_t capacity, uint32_t* count, void* stream);
 /* ---- shadow casters ----

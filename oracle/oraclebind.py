@@ -142,6 +142,24 @@ class OracleOB:
             res.append(out)
         return res
 
+    def draw_scene_view_serial(self, scene, view, sorted_occluders, max_triangles):
+        """View::DrawOccluders, non-threaded branch (View.cpp:2236-2256) over a sorted occluder list: IsVisible gate after the first occluder,
+        AddTriangles + DrawTriangles per occluder, stop after the first failed budget check.  Returns (activeOccluders, numTriangles_)."""
+        self.set_view(view)
+        self.set_max_triangles(int(max_triangles))
+        self.clear()
+        active = 0
+        for j, i in enumerate(sorted_occluders):
+            if j > 0 and not self.is_visible(scene.occ_aabb[i]):
+                continue
+            active += 1
+            self.set_cull_mode(scene.cull_mode)
+            ok = self.draw_batch(scene.occ_model[i], scene.mesh_vtx, scene.mesh_stride, scene.mesh_idx, 0, scene.mesh_idx.shape[0])
+            if not ok:
+                break
+        self.build_hierarchy()
+        return active, self.num_triangles()
+
     def draw_scene_view_selected(self, scene, view, selected, max_triangles):
         """DrawOccluders' threaded branch over an explicit (sorted, budget-trimmed) occluder list.  Returns submitted triangles."""
         self.set_view(view)

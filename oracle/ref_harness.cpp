@@ -946,4 +946,50 @@ int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float
     return n;
 }
 
+/// View::DrawOccluders, NON-threaded branch (View.cpp:2233-2256, 2272-2273) with the reference's own OcclusionBuffer (created non-threaded by
+/// ref_ob_set_size(.., threaded = 0)) over an already sorted occluder list, then the query and the visibility predicate as ref_run_view.
+/// outCounts4 = numTriangles_, query result size, visible, activeOccluders_.
+int ref_run_view_serial(void* h, int numSelected, const int* selected, const float* occAabb6, const float* occModel12, const void* vtx, unsigned vtxSize,
+    const void* idx, unsigned idxSize, unsigned idxCount, int cullMode, unsigned maxTriangles, unsigned flags, unsigned viewMask, int* outVisible, int cap,
+    int* outCounts4)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    OcclusionBuffer* buffer = r->buffer_;
+    if (buffer->IsThreaded())
+        return -1;
+    if (!r->rawFrustum_)
+        buffer->SetView(r->camera_);
+    buffer->SetMaxTriangles(maxTriangles);
+    buffer->Clear();
+    unsigned active = 0;
+    for (int i = 0; i < numSelected; ++i)
+    {
+        const float* b = occAabb6 + 6 * (size_t)selected[i];
+        if (i > 0)
+        {
+            if (!buffer->IsVisible(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]))))
+                continue;
+        }
+        ++active;
+        buffer->SetCullMode((CullMode)cullMode);
+        bool success = buffer->AddTriangles(Matrix3x4(occModel12 + 12 * (size_t)selected[i]), vtx, vtxSize, idx, idxSize, 0, idxCount);
+        buffer->DrawTriangles();
+        if (!success)
+            break;
+    }
+    buffer->BuildDepthHierarchy();
+    const Frustum& fr = r->QueryFrustum();
+    OccludedQuery q(r->result_, fr, buffer, (unsigned char)flags, viewMask);
+    r->octree_->GetDrawables(q);
+    int nvis = ref_check_visibility(h, 1, outVisible, cap);
+    if (outCounts4)
+    {
+        outCounts4[0] = (int)buffer->GetNumTriangles();
+        outCounts4[1] = (int)r->result_.Size();
+        outCounts4[2] = nvis;
+        outCounts4[3] = (int)active;
+    }
+    return nvis;
+}
+
 }

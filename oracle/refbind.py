@@ -74,6 +74,8 @@ class Ref:
         L.ref_shadow_split_setup.argtypes = [C.c_void_p, _f, _f, C.c_float, C.c_float, _f, _f, _f, _f, _f]
         L.ref_process_shadow_casters.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, _f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint, _u32, _f, _f, _u8,
                                                  _f, _f, C.c_int, _i]
+        L.ref_run_view_serial.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
+                                          C.c_uint, C.c_uint, _i, C.c_int, _i]
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
         L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
@@ -300,6 +302,22 @@ class Ref:
                                                 light_type, light_mask, _p(sm, _u32), _p(sd, _f), _p(dd, _f), _p(iv, _u8), _p(mv, _f), _p(mp, _f),
                                                 int(main_ortho), _p(out, _i))
         return out[:n].copy()
+
+    def run_view_serial(self, scene, sorted_occluders, max_triangles, flags=0xFF, view_mask=0xFFFFFFFF):
+        """DrawOccluders' NON-threaded branch over a sorted occluder list, then query + predicate.
+        Returns (visible ids, (numTriangles_, query size, visible, activeOccluders_))."""
+        out = np.zeros(max(self.n, 1), np.int32)
+        counts = np.zeros(4, np.int32)
+        sel = np.ascontiguousarray(sorted_occluders, np.int32)
+        aabb = np.ascontiguousarray(scene.occ_aabb, np.float32)
+        model = np.ascontiguousarray(scene.occ_model, np.float32)
+        vtx = np.ascontiguousarray(scene.mesh_vtx)
+        idx = np.ascontiguousarray(scene.mesh_idx)
+        n = self.lib.ref_run_view_serial(self.h, len(sel), _p(sel, _i), _p(aabb, _f), _p(model, _f), vtx.ctypes.data, scene.mesh_stride,
+                                         idx.ctypes.data, idx.itemsize, idx.shape[0], scene.cull_mode, int(max_triangles), flags, view_mask,
+                                         _p(out, _i), out.shape[0], _p(counts, _i))
+        assert n >= 0, "the reference buffer was created threaded"
+        return out[:n].copy(), counts
 
     def raycast(self, origin, direction, max_distance=np.inf, flags=0xFF, view_mask=0xFFFFFFFF, single=False):
         """Octree::Raycast / RaycastSingle, RAY_AABB level.  Returns (ids, distances, positions) in result_ order."""

@@ -939,3 +939,53 @@ def test_process_shadow_casters(gpu_ctx):
     for o in (batch, gs, tree):
         o.close()
     ob.close()
+
+
+@pytest.mark.parametrize("w,h", [(128, 128), (256, 160)])
+def test_serial_occluder_branch(gpu_ctx, w, h):
+    """Occluder policy 2 = View::DrawOccluders' NON-threaded branch (the engine default) per view on the device: activeOccluders_, numTriangles_,
+    the depth plane, every mip and the visible sequence equal the oracle's serial loop (pinned to the reference's own OcclusionBuffer), with
+    budgets that stop the loop, duplicated occluders (equal sort keys: the list ORDER matters here) and stress views that clip."""
+    sc = helpers.small_scene(n=5000, k=300, extent=90.0, seed=43)
+    sc.occ_aabb[50:90] = sc.occ_aabb[100:140]
+    sc.occ_model[50:90] = sc.occ_model[100:140]
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    rs = np.random.RandomState(5)
+    tri = sc.mesh_idx.shape[0] // 3
+    views = []
+    for i in range(14):
+        pos = [rs.uniform(-90, 90), rs.uniform(1.0, 20.0), rs.uniform(-90, 90)]
+        views.append(camera.make_view(pos, rs.uniform(0, 360), rs.uniform(-25, 10), 45.0, float(w) / h, 0.1, rs.choice([150.0, 400.0])))
+    for v in helpers.stress_views(90.0, w, h, 6, seed=3):
+        v.half_view_size = float(np.float32(np.tan(np.float32(0.4))))
+        views.append(v)
+    cam3 = np.array([[v.half_view_size, v.ortho_size, v.far] for v in views], np.float32)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    batch.set_views(capi.pack_views(views))
+    skipped = cut = 0
+    for thr, budget in ((0.025, 5000), (0.0, 40 * tri), (0.025, 600), (0.025, 1 << 30)):
+        batch.set_occluder_policy(thr, budget, cam3, enable=2)
+        batch.run(capi.STAGE_VISIBLE)
+        counts = batch.counts()
+        stats = batch.tri_stats()
+        active = batch.active_occluders()
+        offsets, ids = batch.packed(capacity=int(counts[:, 1].sum()))
+        for i, v in enumerate(views):
+            oidx, _, _ = oraclebind.select_occluders(sc, v, thr, budget)
+            want_active, want_tris = ob.draw_scene_view_serial(sc, v, oidx, budget)
+            assert active[i] == want_active and stats[i, 1] == want_tris, "view %d thr %g budget %d" % (i, thr, budget)
+            assert np.array_equal(batch.depth(i), ob.depth())
+            for a, b in zip(batch.mips(i), ob.mips()):
+                assert np.array_equal(a, b)
+            cand = otree.query(1, v.planes, ob, as_ids=False)
+            assert counts[i, 0] == len(cand)
+            assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.order[otree.check_visibility(ob, cand)])
+            skipped += want_active < len(oidx)
+            cut += budget < (1 << 30) and want_tris > budget
+    assert skipped > 10 and cut > 3
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

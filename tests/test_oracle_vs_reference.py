@@ -303,3 +303,38 @@ def test_process_shadow_casters_matches_reference():
                 kinds.add(s["light_type"])
     assert kept > 5000 and dropped > 5000 and kinds == {0, 1, 2}
     ref.close()
+
+
+def test_serial_occluder_branch_matches_reference():
+    """View::DrawOccluders' NON-threaded branch (the engine's default): IsVisible-gated, one occluder at a time, budget on numTriangles_ =
+    submitted + drawn.  Oracle loop vs the reference's own OcclusionBuffer driven the same way, from the UpdateOccluders-sorted list."""
+    from urho3d_b200 import camera
+    w, h = 128, 128
+    sc = helpers.small_scene(n=3000, k=300, extent=90.0, seed=43)
+    ref = helpers.make_ref(sc, w, h)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    rs = np.random.RandomState(5)
+    tri = sc.mesh_idx.shape[0] // 3
+    skipped = cut = 0
+    for i in range(16):
+        pos = [rs.uniform(-90, 90), rs.uniform(1.0, 20.0), rs.uniform(-90, 90)]
+        v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(-25, 10), 45.0, 1.0, 0.1, rs.choice([150.0, 400.0]))
+        ref.set_view_raw(v)
+        for thr, budget in ((0.025, 5000), (0.0, 40 * tri), (0.025, 1 << 30)):
+            ridx, _ = ref.select_occluders(sc, v, thr)
+            oidx, _, _ = oraclebind.select_occluders(sc, v, thr, budget)
+            assert np.array_equal(ridx, oidx)
+            vis, counts = ref.run_view_serial(sc, ridx, budget)
+            active, ntris = ob.draw_scene_view_serial(sc, v, oidx, budget)
+            assert active == counts[3] and ntris == counts[0], (i, thr, budget)
+            assert np.array_equal(ob.depth(), ref.ob_depth())
+            for a, b in zip(ob.mips(), ref.ob_mips()):
+                assert np.array_equal(a, b)
+            cand = tree.query(1, v.planes, ob, as_ids=False)
+            assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+            skipped += active < len(oidx)
+            cut += budget < (1 << 30) and ntris > budget
+    assert skipped > 10 and cut > 3
+    ref.close()
+    ob.close()

@@ -122,6 +122,7 @@ SIGNATURES = {
     "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
     "u3d_batch_set_occluder_policy": (C.c_int, [_vp, C.c_int, C.c_float, C.c_uint32, C.POINTER(C.c_float), _vp]),
     "u3d_occluders_set_draw_distances": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
+    "u3d_batch_read_active_occluders": (C.c_int, [_vp, C.POINTER(C.c_uint32), _vp]),
     "u3d_batch_read_occluder_selection": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(C.c_uint32), _vp]),
     "u3d_gather_create": (C.c_int, [_vp, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
     "u3d_gather_destroy": (None, [_vp]),
@@ -595,6 +596,11 @@ class Batch:
         """View::UpdateOccluders heuristics + DrawOccluders' triangle budget.  camera3: n x (halfViewSize, orthoSize, farClip)."""
         cam = None if camera3 is None else np.ascontiguousarray(camera3, np.float32).reshape(-1, 3)
         _chk(lib().u3d_batch_set_occluder_policy(self.h, int(enable), float(size_threshold), int(max_triangles), _p(cam, _f), stream))
+
+    def active_occluders(self, stream=None):
+        out = np.zeros(max(self.n, 1), np.uint32)
+        _chk(lib().u3d_batch_read_active_occluders(self.h, _p(out, _u32), stream))
+        return out[:self.n]
 
     def occluder_selection(self, view, stream=None):
         cap = 65536

@@ -342,6 +342,9 @@ struct u3d_batch
     cudaEvent_t ev[U3D_NUM_PHASES + 1]{};
     // u3d_batch_set_occluder_policy: View::UpdateOccluders heuristics + triangle budget instead of "every occluder in the frustum"
     bool rankOccluders{};
+    bool serialOccluders{};           // non-threaded branch of View::DrawOccluders (policy mode 2)
+    DevBuf<uint32_t> rankList, rankCount, activeOccluders;
+    DevBuf<TriSetup> serialScratch;
     float sizeThreshold{};
     uint32_t maxTriangles{};
     DevBuf<float4> camParams;
@@ -1775,10 +1778,40 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
             b->lastLaunches += 1;
         }
+        if (b->rankOccluders && b->serialOccluders)
+        {
+            // View::DrawOccluders' non-threaded branch: sorted list -> serial per-view draw loop (general-path fill) -> whole hierarchy
+            constexpr uint32_t kSerialScratch = 2048; // set-up triangles one 256-triangle chunk of an occluder may produce
+            CU_CHECK(b->rankList.ensure((size_t)vs.maxViews * kRankCap));
+            CU_CHECK(b->rankCount.ensure(vs.maxViews));
+            CU_CHECK(b->activeOccluders.ensure(vs.maxViews));
+            CU_CHECK(b->serialScratch.ensure((size_t)vs.maxViews * kSerialScratch));
+            if (vs.useTiles)
+            {
+                launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
+                b->lastLaunches += 1;
+            }
+            CU_CHECK(mark(1));
+            launch_select_ranked(vs.views.p, b->camParams.p, V, (int)oc->n, oc->aabb6.p, oc->drawDist.n ? oc->drawDist.p : nullptr, oc->mesh.p, oc->start.p,
+                oc->count.p, b->sizeThreshold, b->maxTriangles, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, vs.flags.p, b->rankList.p,
+                b->rankCount.p, st);
+            CU_CHECK(mark(2));
+            CU_CHECK(mark(3));
+            launch_draw_occluders_serial(vs.g, vs.views.p, V, b->rankList.p, b->rankCount.p, oc->aabb6.p, oc->model12.p, oc->mesh.p, oc->start.p, oc->count.p,
+                oc->meshTable.p, b->maxTriangles, vs.depth.p, b->serialScratch.p, kSerialScratch, vs.submitted.p, vs.drawnSources.p, b->activeOccluders.p,
+                vs.flags.p, st);
+            CU_CHECK(mark(4));
+            CU_CHECK(mark(5));
+            launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, 0, st);
+            b->lastLaunches += 2 + (uint32_t)vs.g.nlev;
+            CU_CHECK(cudaGetLastError());
+        }
+        else
+        {
         CU_CHECK(mark(1));
         if (b->rankOccluders)
             launch_select_ranked(vs.views.p, b->camParams.p, V, (int)oc->n, oc->aabb6.p, oc->drawDist.n ? oc->drawDist.p : nullptr, oc->mesh.p, oc->start.p,
-                oc->count.p, b->sizeThreshold, b->maxTriangles, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, vs.flags.p, st);
+                oc->count.p, b->sizeThreshold, b->maxTriangles, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, vs.flags.p, nullptr, nullptr, st);
         else
             launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
         CU_CHECK(mark(2));
@@ -1803,6 +1836,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, firstLevel, st);
         b->lastLaunches += 3 + (uint32_t)(vs.g.nlev - firstLevel);
         CU_CHECK(cudaGetLastError());
+        }
     }
     else
     {
@@ -2349,7 +2383,10 @@ int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold
         return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: NULL argument");
     if (!b->hasBuffers)
         return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: the batch has no occluders");
+    if (enable < 0 || enable > 2)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: enable must be 0, 1 or 2");
     b->rankOccluders = enable != 0;
+    b->serialOccluders = enable == 2;
     if (!enable)
         return U3D_OK;
     CU_CHECK(cudaSetDevice(b->ctx->device));
@@ -2367,6 +2404,22 @@ int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold
     {
         CU_CHECK(cudaMemcpyAsync(b->camParams.p, b->camHost.data(), (size_t)V * sizeof(float4), cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaStreamSynchronize(st)); // camHost is reused by the next call
+    }
+    return U3D_OK;
+}
+
+int u3d_batch_read_active_occluders(u3d_batch* b, uint32_t* active, void* stream)
+{
+    if (!b || !active)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_active_occluders: NULL argument");
+    if (!b->serialOccluders || !b->activeOccluders.n)
+        return fail(U3D_ERR_INVALID, "u3d_batch_read_active_occluders: only after a run with occluder policy 2");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->pick(stream);
+    if (b->numViews)
+    {
+        CU_CHECK(cudaMemcpyAsync(active, b->activeOccluders.p, (size_t)b->numViews * 4, cudaMemcpyDeviceToHost, st));
+        CU_CHECK(cudaStreamSynchronize(st));
     }
     return U3D_OK;
 }

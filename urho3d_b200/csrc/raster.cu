@@ -198,7 +198,8 @@ __device__ void exact_reference_sort(unsigned long long* a, int n)
 __global__ void __launch_bounds__(kRankThreads) k_select_ranked(const ViewConst* __restrict__ views, const float4* __restrict__ camParams, int numOcc,
     const float* __restrict__ occAabb6, const float* __restrict__ occDrawDist, const uint32_t* __restrict__ occMesh, const uint32_t* __restrict__ occStart,
     const uint32_t* __restrict__ occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* __restrict__ items, uint32_t itemCap,
-    uint32_t* __restrict__ itemCount, uint32_t* __restrict__ submitted, uint32_t* __restrict__ flags)
+    uint32_t* __restrict__ itemCount, uint32_t* __restrict__ submitted, uint32_t* __restrict__ flags, uint32_t* __restrict__ rankList,
+    uint32_t* __restrict__ rankCount)
 {
     extern __shared__ __align__(16) unsigned char rankSmem[];
     unsigned long long* keys = reinterpret_cast<unsigned long long*>(rankSmem); // kRankCap entries: sortable key bits << 32 | candidate number
@@ -307,6 +308,41 @@ __global__ void __launch_bounds__(kRankThreads) k_select_ranked(const ViewConst*
     for (int i = n + tid; i < P; i += kRankThreads)
         keys[i] = ~0ull;
     bitonic_sort_u64(keys, P);
+
+    if (rankList)
+    {
+        // Non-threaded branch (View.cpp:2236-2256): the draw loop itself decides what is submitted, and it depends on the ORDER of the
+        // list, so equal keys (or NaN keys) always take the reference's exact Sort procedure.
+        __shared__ uint32_t sTie;
+        if (tid == 0)
+            sTie = sAmbiguous;
+        __syncthreads();
+        for (uint32_t i = tid; i + 1 < n; i += kRankThreads)
+            if ((uint32_t)(keys[i] >> 32) == (uint32_t)(keys[i + 1] >> 32))
+                sTie = 1;
+        __syncthreads();
+        if (sTie)
+        {
+            for (uint32_t i = tid; i < n; i += kRankThreads)
+                keys[i] = (keys[i] << 32) | (keys[i] >> 32);
+            bitonic_sort_u64(keys, P);
+            for (uint32_t i = tid; i < n; i += kRankThreads)
+                keys[i] = (keys[i] << 32) | (keys[i] >> 32);
+            __syncthreads();
+            if (tid == 0)
+                exact_reference_sort(keys, (int)n);
+            __syncthreads();
+        }
+        for (uint32_t i = tid; i < n; i += kRankThreads)
+            rankList[(size_t)v * kRankCap + i] = candOcc[(uint32_t)keys[i]];
+        if (tid == 0)
+        {
+            rankCount[v] = n;
+            itemCount[v] = 0;
+            submitted[v] = 0;
+        }
+        return;
+    }
 
     // ---- budget: occluder i is submitted iff the triangles submitted before it do not exceed maxTriangles ----
     auto find_cut = [&]() {
@@ -1079,6 +1115,18 @@ __device__ __forceinline__ void fill_tri_global(int* __restrict__ depth, int w, 
         fill_half_global(depth, w, h, ts.y1, ts.y2, ts.blx, ts.blxs, ts.blz, ts.blzs, ts.brx, ts.brxs, ts.dzdx, lane);
 }
 
+__device__ __forceinline__ TriSetup load_tri_global(const TriSetup* p)
+{
+    const int4* q = reinterpret_cast<const int4*>(p);
+    const int4 a = q[0], b = q[1], c = q[2], d = q[3];
+    TriSetup t;
+    t.y0 = a.x; t.y1 = a.y; t.y2 = a.z; t.dzdx = a.w;
+    t.tlx = b.x; t.tlxs = b.y; t.tlz = b.z; t.tlzs = b.w;
+    t.trx = c.x; t.trxs = c.y; t.blx = c.z; t.blxs = c.w;
+    t.blz = d.x; t.blzs = d.y; t.brx = d.z; t.brxs = d.w;
+    return t;
+}
+
 /// Every record of every view (the OcclusionBuffer drop-in path, which accumulates into an existing plane).
 __global__ void __launch_bounds__(256) k_fill_global(BufGeom g, int* __restrict__ depthAll, const TriSetup* __restrict__ pool,
     const uint64_t* __restrict__ triBase, const uint32_t* __restrict__ triCap, const uint32_t* __restrict__ triCount)
@@ -1093,6 +1141,152 @@ __global__ void __launch_bounds__(256) k_fill_global(BufGeom g, int* __restrict_
     {
         const TriSetup ts = region[t];
         fill_tri_global(depth, g.w, g.h, ts, lane);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// View::DrawOccluders, NON-threaded branch (View.cpp:2236-2256; the engine's default, Renderer::threadedOcclusion_ = false): occluders are
+// drawn one by one in sorted order, every occluder after the first is first tested with OcclusionBuffer::IsVisible against what has been
+// drawn so far (hierarchy dirty -> pixel scan, OB.cpp:404, 440-455), and the triangle budget sees numTriangles_ = submitted triangles +
+// source triangles that drew something (OB.cpp:196-197, 681-682).  The loop is inherently serial per view, so one CTA walks one view's
+// list: block-wide pixel test, then transform / clip / set-up of the occluder's triangles into a small scratch region, then one warp per
+// set-up triangle fills the view's plane in global memory (general path).  Views run in parallel.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSerialThreads = 256;
+
+__global__ void __launch_bounds__(kSerialThreads) k_draw_occluders_serial(BufGeom g, const ViewConst* __restrict__ views, const uint32_t* __restrict__ rankList,
+    const uint32_t* __restrict__ rankCount, const float* __restrict__ occAabb6, const float* __restrict__ models, const uint32_t* __restrict__ occMesh,
+    const uint32_t* __restrict__ occStart, const uint32_t* __restrict__ occCount, const MeshDev* __restrict__ meshes, uint32_t maxTriangles,
+    int* __restrict__ depthAll, TriSetup* __restrict__ scratchAll, uint32_t scratchCap, uint32_t* __restrict__ submitted, uint32_t* __restrict__ drawnSources,
+    uint32_t* __restrict__ activeOccluders, uint32_t* __restrict__ flags)
+{
+    __shared__ ViewConst vc;
+    __shared__ float sMvp[16];
+    __shared__ uint32_t sRecords, sDrawn;
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    for (int i = tid; i < (int)(sizeof(ViewConst) / 4); i += kSerialThreads)
+        reinterpret_cast<uint32_t*>(&vc)[i] = reinterpret_cast<const uint32_t*>(views + v)[i];
+    if (tid == 0)
+    {
+        sRecords = 0;
+        sDrawn = 0;
+    }
+    __syncthreads();
+    int* depth = depthAll + (size_t)v * g.w * g.h;
+    TriSetup* scratch = scratchAll + (size_t)v * scratchCap;
+    EmitCtx ec{};
+    ec.region = scratch;
+    ec.cap = scratchCap;
+    ec.counter = &sRecords;
+    ec.flags = flags;
+    ec.binIdx = nullptr; // general path only
+    ec.view = (uint32_t)v;
+    ec.w = g.w;
+    ec.h = g.h;
+    const uint32_t n = rankCount[v];
+    uint32_t numTriangles = 0, numSubmitted = 0, active = 0; // uniform across the block
+    for (uint32_t i = 0; i < n; ++i)
+    {
+        const uint32_t k = rankList[(size_t)v * kRankCap + i];
+        if (i > 0)
+        {
+            // buffer->IsVisible(occluder->GetWorldBoundingBox()) with the hierarchy dirty: every pixel of the rect (OB.cpp:440-455)
+            const float* b = occAabb6 + 6 * (size_t)k;
+            BoxRect r;
+            bool vis = ob_project(g, vc.vp, b[0], b[1], b[2], b[3], b[4], b[5], r);
+            if (!vis)
+            {
+                const int rw = r.right - r.left + 1, area = rw * (r.bottom - r.top + 1);
+                for (int p = tid; p < area && !vis; p += kSerialThreads)
+                    vis = r.z <= __ldcg(depth + (r.top + p / rw) * g.w + r.left + p % rw); // L2: the plane is updated by atomics
+            }
+            if (!__syncthreads_or(vis))
+                continue;
+        }
+        ++active;
+        const uint32_t tris = occCount[k] / 3;
+        numTriangles += tris; // AddTriangles, OB.cpp:196
+        numSubmitted += tris;
+        const bool success = numTriangles <= maxTriangles;
+        // DrawTriangles -> DrawBatch: modelViewProj = viewProj_ * model (Matrix4 * Matrix3x4, Matrix4.cpp:43-63)
+        if (tid < 16)
+        {
+            const int r = tid >> 2, c = tid & 3;
+            const float* a = vc.vp + 4 * r;
+            const float* m = models + 12 * (size_t)k;
+            sMvp[tid] = c < 3 ? a[0] * m[c] + a[1] * m[4 + c] + a[2] * m[8 + c] : a[0] * m[3] + a[1] * m[7] + a[2] * m[11] + a[3];
+        }
+        __syncthreads();
+        const MeshDev mesh = meshes[occMesh[k]];
+        const uint32_t start = occStart[k];
+        for (uint32_t tBase = 0; tBase < tris; tBase += kSerialThreads)
+        {
+            const uint32_t t = tBase + tid;
+            bool drew = false;
+            if (t < tris)
+            {
+                const uint32_t first = start + 3 * t;
+                uint32_t i0, i1, i2;
+                if (mesh.idx == nullptr)
+                {
+                    i0 = first; i1 = first + 1; i2 = first + 2;
+                }
+                else if (mesh.idxSize == 2)
+                {
+                    const unsigned short* ix = (const unsigned short*)mesh.idx;
+                    i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+                }
+                else
+                {
+                    const unsigned* ix = (const unsigned*)mesh.idx;
+                    i0 = ix[first]; i1 = ix[first + 1]; i2 = ix[first + 2];
+                }
+                const float* q0 = (const float*)(mesh.vtx + (size_t)i0 * mesh.stride);
+                const float* q1 = (const float*)(mesh.vtx + (size_t)i1 * mesh.stride);
+                const float* q2 = (const float*)(mesh.vtx + (size_t)i2 * mesh.stride);
+                const V4 c0 = model_transform(sMvp, q0[0], q0[1], q0[2]);
+                const V4 c1 = model_transform(sMvp, q1[0], q1[1], q1[2]);
+                const V4 c2 = model_transform(sMvp, q2[0], q2[1], q2[2]);
+                unsigned m0 = 0, m1 = 0, m2 = 0; // clip masks, OB.cpp:596-620
+                if (c0.x > c0.w) m0 |= 1; if (c0.x < -c0.w) m0 |= 2; if (c0.y > c0.w) m0 |= 4; if (c0.y < -c0.w) m0 |= 8; if (c0.z > c0.w) m0 |= 16; if (c0.z < 0.0f) m0 |= 32;
+                if (c1.x > c1.w) m1 |= 1; if (c1.x < -c1.w) m1 |= 2; if (c1.y > c1.w) m1 |= 4; if (c1.y < -c1.w) m1 |= 8; if (c1.z > c1.w) m1 |= 16; if (c1.z < 0.0f) m1 |= 32;
+                if (c2.x > c2.w) m2 |= 1; if (c2.x < -c2.w) m2 |= 2; if (c2.y > c2.w) m2 |= 4; if (c2.y < -c2.w) m2 |= 8; if (c2.z > c2.w) m2 |= 16; if (c2.z < 0.0f) m2 |= 32;
+                if (!(m0 & m1 & m2))
+                {
+                    const unsigned clipMask = m0 | m1 | m2;
+                    drew = clipMask ? clip_and_setup(g, vc.cullMode, clipMask, c0, c1, c2, ec) : setup_triangle(g, vc.cullMode, c0, c1, c2, ec);
+                }
+            }
+            const uint32_t bal = __ballot_sync(0xffffffffu, drew);
+            if (lane == 0 && bal)
+                atomicAdd(&sDrawn, (uint32_t)__popc(bal));
+            __syncthreads();
+            // fill what was set up so far (the scratch region holds at least one chunk's worth), one warp per record
+            const uint32_t nrec = min(sRecords, scratchCap);
+            for (uint32_t rIdx = wid; rIdx < nrec; rIdx += kSerialThreads / 32)
+            {
+                const TriSetup ts = load_tri_global(scratch + rIdx);
+                fill_tri_global(depth, g.w, g.h, ts, lane);
+            }
+            __threadfence_block();
+            __syncthreads();
+            if (tid == 0)
+                sRecords = 0;
+            __syncthreads();
+        }
+        numTriangles += sDrawn; // ++numTriangles_ per source triangle that drew something, OB.cpp:681-682
+        __syncthreads();
+        if (tid == 0)
+            sDrawn = 0;
+        __syncthreads();
+        if (!success)
+            break;
+    }
+    if (tid == 0)
+    {
+        submitted[v] = numSubmitted;
+        drawnSources[v] = numTriangles - numSubmitted;
+        activeOccluders[v] = active;
     }
 }
 
@@ -1525,12 +1719,22 @@ cudaError_t init_rank_kernel()
 
 void launch_select_ranked(const ViewConst* views, const float4* camParams, int numViews, int numOcc, const float* occAabb6, const float* occDrawDist,
     const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* items,
-    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, cudaStream_t s)
+    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, uint32_t* rankList, uint32_t* rankCount, cudaStream_t s)
 {
     if (!numOcc || !numViews)
         return;
     k_select_ranked<<<numViews, kRankThreads, kRankCap * 12, s>>>(views, camParams, numOcc, occAabb6, occDrawDist, occMesh, occStart, occCount, sizeThreshold,
-        maxTriangles, items, itemCap, itemCount, submitted, flags);
+        maxTriangles, items, itemCap, itemCount, submitted, flags, rankList, rankCount);
+}
+
+void launch_draw_occluders_serial(const BufGeom& g, const ViewConst* views, int numViews, const uint32_t* rankList, const uint32_t* rankCount,
+    const float* occAabb6, const float* models, const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, const MeshDev* meshes,
+    uint32_t maxTriangles, int* depth, TriSetup* scratch, uint32_t scratchCap, uint32_t* submitted, uint32_t* drawnSources, uint32_t* activeOccluders,
+    uint32_t* flags, cudaStream_t s)
+{
+    if (numViews)
+        k_draw_occluders_serial<<<numViews, kSerialThreads, 0, s>>>(g, views, rankList, rankCount, occAabb6, models, occMesh, occStart, occCount, meshes,
+            maxTriangles, depth, scratch, scratchCap, submitted, drawnSources, activeOccluders, flags);
 }
 
 void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,

@@ -86,7 +86,13 @@ void launch_select(const ViewConst* views, int numViews, int numOcc, const float
 cudaError_t init_rank_kernel();
 void launch_select_ranked(const ViewConst* views, const float4* camParams, int numViews, int numOcc, const float* occAabb6, const float* occDrawDist,
     const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, float sizeThreshold, uint32_t maxTriangles, DrawItem* items,
-    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, cudaStream_t s);
+    uint32_t itemCap, uint32_t* itemCount, uint32_t* submitted, uint32_t* flags, uint32_t* rankList /* null: threaded-branch budget + draw items;
+    else the full sorted list, kRankCap entries per view */, uint32_t* rankCount, cudaStream_t s);
+/// View::DrawOccluders' non-threaded branch over the sorted lists of launch_select_ranked (one CTA per view, general-path fill).
+void launch_draw_occluders_serial(const BufGeom& g, const ViewConst* views, int numViews, const uint32_t* rankList, const uint32_t* rankCount,
+    const float* occAabb6, const float* models, const uint32_t* occMesh, const uint32_t* occStart, const uint32_t* occCount, const MeshDev* meshes,
+    uint32_t maxTriangles, int* depth, TriSetup* scratch, uint32_t scratchCap, uint32_t* submitted, uint32_t* drawnSources, uint32_t* activeOccluders,
+    uint32_t* flags, cudaStream_t s);
 void launch_scan_regions(int numViews, const uint32_t* submitted, uint32_t slack, uint64_t poolCap, uint64_t* triBase, uint32_t* triCap, uint32_t* flags,
     cudaStream_t s);
 void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
