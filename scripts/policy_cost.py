@@ -25,9 +25,10 @@ occ = capi.Occluders(ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_m
 batch = capi.Batch(ctx, gs, occ, 256, 256, V, 32768, tri_pool=V * 14000)
 batch.set_views(capi.pack_views(views))
 cam3 = np.array([[v.half_view_size, v.ortho_size, v.far] for v in views], np.float32)
-for name, policy in (("default rule", None), ("heuristics thr=0.025 budget=5000", (0.025, 5000))):
+for name, policy in (("default rule", None), ("heuristics thr=0.025 budget=5000, threaded branch", (0.025, 5000, 1)),
+                     ("heuristics thr=0.025 budget=5000, non-threaded branch (serial per view)", (0.025, 5000, 2))):
     if policy:
-        batch.set_occluder_policy(policy[0], policy[1], cam3)
+        batch.set_occluder_policy(policy[0], policy[1], cam3, enable=policy[2])
     acc = {}
     for _ in range(5):
         for k, ms in batch.run_timed(capi.STAGE_VISIBLE).items():
