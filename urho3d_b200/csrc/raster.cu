@@ -1081,13 +1081,13 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
 // Handles every record, including the irregular ones the tile path refuses.
 // ---------------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void fill_half_global(int* __restrict__ depth, int w, int h, int ya, int yb, int lx, int lxs, int lz, int lzs, int rx, int rxs,
-    int dzdx, int lane)
+    int dzdx, int lane, int rowOff = 0, int rowStep = 1, bool preRead = true)
 {
     // rows whose linear span could reach [0, w*h): |x>>16| <= 32768
     const long long guard = 32768 / w + 2;
     const long long lo = max((long long)ya, -guard), hi = min((long long)yb, (long long)h + guard);
     const long long npix = (long long)w * h;
-    for (long long y = lo; y < hi; ++y)
+    for (long long y = lo + rowOff; y < hi; y += rowStep)
     {
         const uint32_t k = (uint32_t)((long long)y - ya);
         const int xl = (int)((uint32_t)lx + k * (uint32_t)lxs) >> 16;
@@ -1100,19 +1100,22 @@ __device__ __forceinline__ void fill_half_global(int* __restrict__ depth, int w,
             if (off >= 0 && off < npix)
             {
                 const int z = (int)(z0 + (uint32_t)(x - xl) * (uint32_t)dzdx);
-                if (z < depth[off])
+                // preRead = false: fire-and-forget reductions, no load latency per pixel (pays off when most pixels do get written)
+                if (!preRead || z < depth[off])
                     atomicMin(depth + off, z);
             }
         }
     }
 }
 
-__device__ __forceinline__ void fill_tri_global(int* __restrict__ depth, int w, int h, const TriSetup& ts, int lane)
+/// rowOff / rowStep: this warp takes every rowStep-th row of each half starting at rowOff (several warps share one triangle).
+__device__ __forceinline__ void fill_tri_global(int* __restrict__ depth, int w, int h, const TriSetup& ts, int lane, int rowOff = 0, int rowStep = 1,
+    bool preRead = true)
 {
     if (ts.y0 != ts.y1)
-        fill_half_global(depth, w, h, ts.y0, ts.y1, ts.tlx, ts.tlxs, ts.tlz, ts.tlzs, ts.trx, ts.trxs, ts.dzdx, lane);
+        fill_half_global(depth, w, h, ts.y0, ts.y1, ts.tlx, ts.tlxs, ts.tlz, ts.tlzs, ts.trx, ts.trxs, ts.dzdx, lane, rowOff, rowStep, preRead);
     if (ts.y1 != ts.y2)
-        fill_half_global(depth, w, h, ts.y1, ts.y2, ts.blx, ts.blxs, ts.blz, ts.blzs, ts.brx, ts.brxs, ts.dzdx, lane);
+        fill_half_global(depth, w, h, ts.y1, ts.y2, ts.blx, ts.blxs, ts.blz, ts.blzs, ts.brx, ts.brxs, ts.dzdx, lane, rowOff, rowStep, preRead);
 }
 
 __device__ __forceinline__ TriSetup load_tri_global(const TriSetup* p)
@@ -1185,24 +1188,63 @@ __global__ void __launch_bounds__(kSerialThreads) k_draw_occluders_serial(BufGeo
     ec.h = g.h;
     const uint32_t n = rankCount[v];
     uint32_t numTriangles = 0, numSubmitted = 0, active = 0; // uniform across the block
-    for (uint32_t i = 0; i < n; ++i)
+    __shared__ uint32_t sGate;
+    constexpr uint32_t kGate = 2 * (kSerialThreads / 32); // occluders tested per gate round, two per warp
+    for (uint32_t i = 0; i < n;)
     {
-        const uint32_t k = rankList[(size_t)v * kRankCap + i];
         if (i > 0)
         {
-            // buffer->IsVisible(occluder->GetWorldBoundingBox()) with the hierarchy dirty: every pixel of the rect (OB.cpp:440-455)
-            const float* b = occAabb6 + 6 * (size_t)k;
-            BoxRect r;
-            bool vis = ob_project(g, vc.vp, b[0], b[1], b[2], b[3], b[4], b[5], r);
-            if (!vis)
+            // buffer->IsVisible(occluder->GetWorldBoundingBox()) with the hierarchy dirty: every pixel of the rect (OB.cpp:440-455).
+            // The buffer only changes when an occluder is drawn, so the next kGate occluders of the list are tested at once (one warp
+            // each, lanes across the rect's pixels); everything before the first visible one is rejected exactly as the serial loop would.
+            if (tid == 0)
+                sGate = 0xFFFFFFFFu;
+            __syncthreads();
+            for (uint32_t c = wid; c < kGate; c += kSerialThreads / 32)
             {
-                const int rw = r.right - r.left + 1, area = rw * (r.bottom - r.top + 1);
-                for (int p = tid; p < area && !vis; p += kSerialThreads)
-                    vis = r.z <= __ldcg(depth + (r.top + p / rw) * g.w + r.left + p % rw); // L2: the plane is updated by atomics
+                const uint32_t j = i + c;
+                if (j >= n || sGate < c)
+                    continue; // an earlier occluder of this round is already known to be visible
+                const float* b = occAabb6 + 6 * (size_t)rankList[(size_t)v * kRankCap + j];
+                BoxRect r;
+                bool vis = ob_project(g, vc.vp, b[0], b[1], b[2], b[3], b[4], b[5], r);
+                if (!vis)
+                {
+                    const int rw = r.right - r.left + 1, area = rw * (r.bottom - r.top + 1);
+                    // 8 independent L2 loads per lane and vote (the loads bypass L1: atomics update the plane), 256 pixels per step
+                    for (int base = 0; base < area; base += 256)
+                    {
+                        bool hit = false;
+#pragma unroll
+                        for (int u = 0; u < 8; ++u)
+                        {
+                            const int p = base + 32 * u + lane;
+                            const int pc = min(p, area - 1);
+                            const int z = __ldcg(depth + (r.top + pc / rw) * g.w + r.left + pc % rw);
+                            hit |= p < area && r.z <= z;
+                        }
+                        if (__any_sync(0xffffffffu, hit))
+                        {
+                            vis = true;
+                            break;
+                        }
+                    }
+                }
+                if (vis && lane == 0)
+                    atomicMin(&sGate, c);
             }
-            if (!__syncthreads_or(vis))
+            __syncthreads();
+            const uint32_t first = sGate;
+            __syncthreads();
+            if (first == 0xFFFFFFFFu)
+            {
+                i += kGate;
                 continue;
+            }
+            i += first;
         }
+        const uint32_t k = rankList[(size_t)v * kRankCap + i];
+        ++i;
         ++active;
         const uint32_t tris = occCount[k] / 3;
         numTriangles += tris; // AddTriangles, OB.cpp:196
@@ -1261,13 +1303,21 @@ __global__ void __launch_bounds__(kSerialThreads) k_draw_occluders_serial(BufGeo
             if (lane == 0 && bal)
                 atomicAdd(&sDrawn, (uint32_t)__popc(bal));
             __syncthreads();
-            // fill what was set up so far (the scratch region holds at least one chunk's worth), one warp per record
+            // fill what was set up so far (the scratch region holds at least one chunk's worth).  The occluders that pass the gate are the
+            // near, large ones: with few records every triangle's rows are spread over all warps, otherwise one warp takes one record.
             const uint32_t nrec = min(sRecords, scratchCap);
-            for (uint32_t rIdx = wid; rIdx < nrec; rIdx += kSerialThreads / 32)
-            {
-                const TriSetup ts = load_tri_global(scratch + rIdx);
-                fill_tri_global(depth, g.w, g.h, ts, lane);
-            }
+            if (nrec <= 32)
+                for (uint32_t rIdx = 0; rIdx < nrec; ++rIdx)
+                {
+                    const TriSetup ts = load_tri_global(scratch + rIdx);
+                    fill_tri_global(depth, g.w, g.h, ts, lane, wid, kSerialThreads / 32, false);
+                }
+            else
+                for (uint32_t rIdx = wid; rIdx < nrec; rIdx += kSerialThreads / 32)
+                {
+                    const TriSetup ts = load_tri_global(scratch + rIdx);
+                    fill_tri_global(depth, g.w, g.h, ts, lane);
+                }
             __threadfence_block();
             __syncthreads();
             if (tid == 0)
