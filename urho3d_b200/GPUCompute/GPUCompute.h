@@ -240,6 +240,14 @@ struct GpuShadowCasterOctreeQuery : GpuFrustumOctreeQuery
     int Mode() const override { return U3D_QUERY_SHADOWCASTER; }
 };
 
+/// ZoneOccluderOctreeQuery (View.cpp:87-113): zones and occluders inside a frustum; drawableFlags_ is not consulted (the reference compares the
+/// drawable's flags with DRAWABLE_ZONE / DRAWABLE_GEOMETRY directly).  IsOccluder() comes from GpuOctree::SetOccluder.
+struct GpuZoneOccluderOctreeQuery : GpuFrustumOctreeQuery
+{
+    using GpuFrustumOctreeQuery::GpuFrustumOctreeQuery;
+    int Mode() const override { return U3D_QUERY_ZONE_OCCLUDER; }
+};
+
 /// RayQueryResult (OctreeQuery.h:189-224) as Drawable::ProcessRayQuery fills it at RAY_AABB level (Drawable.cpp:118-132).
 using GpuRayQueryResult = u3d_ray_hit;
 
@@ -295,6 +303,13 @@ public:
         Check(u3d_octree_add(tree_, count, worldBoxes, drawableFlags, viewMasks, occludee, castShadows, &id), "u3d_octree_add");
         dirty_ = true;
         return id;
+    }
+    /// Drawable::SetOccluder (used by GpuZoneOccluderOctreeQuery).  Takes effect at the next Sync (the scene is re-flattened).
+    void SetOccluder(unsigned id, bool enable)
+    {
+        const uint8_t f = enable;
+        Check(u3d_octree_set_occluder_flags(tree_, id, 1, &f), "u3d_octree_set_occluder_flags");
+        dirty_ = true;
     }
     /// A drawable moved or was resized: the reinsertion rule of Octree::Update (Octree.cpp:440-472).
     void UpdateDrawable(unsigned id, const float* worldBoxMinMax6)
@@ -420,7 +435,7 @@ public:
             return false;
         if (policy_ && camera3_.size() < 3 * (size_t)count)
             return false;
-        if (u3d_batch_set_occluder_policy(batch_, policy_ ? 1 : 0, sizeThreshold_, maxTriangles_, policy_ ? camera3_.data() : nullptr, nullptr) < 0)
+        if (u3d_batch_set_occluder_policy(batch_, policy_ ? (threaded_ ? 1 : 2) : 0, sizeThreshold_, maxTriangles_, policy_ ? camera3_.data() : nullptr, nullptr) < 0)
             return false;
         if (u3d_batch_run(batch_, stage, nullptr) < 0 || u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
             return false;
@@ -444,6 +459,24 @@ public:
         camera3_.assign(camera3, camera3 + 3 * (size_t)count);
     }
     void ClearOccluderPolicy() { policy_ = false; }
+    /// threaded = false selects View::DrawOccluders' non-threaded branch (the engine default, Renderer::SetThreadedOcclusion(false)).
+    void SetThreadedOcclusion(bool threaded) { threaded_ = threaded; }
+    /// View::ProcessShadowCasters over the lists of the last CullViews call (one u3d_shadow_split per view); see include/u3d_gpu.h.
+    bool ProcessShadowCasters(const u3d_shadow_split* splits, const float* mainView12, const float* mainCameraPos3, bool mainOrthographic,
+        const unsigned char* inView, unsigned numInView, unsigned count, std::vector<unsigned>& ids)
+    {
+        if (u3d_batch_process_shadow_casters(batch_, splits, mainView12, mainCameraPos3, mainOrthographic ? 1 : 0, inView, numInView, nullptr) < 0 ||
+            u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
+            return false;
+        unsigned long long total = 0;
+        for (unsigned v = 0; v < count; ++v)
+            total += counts_[2 * v + 1];
+        ids.resize(total ? total : 1);
+        if (u3d_batch_read_packed(batch_, offsets_.data(), ids.data(), ids.size(), nullptr) < 0)
+            return false;
+        ids.resize(total);
+        return true;
+    }
     const std::vector<unsigned>& Offsets() const { return offsets_; }
     const std::vector<unsigned>& Counts() const { return counts_; }
     u3d_batch* Handle() const { return batch_; }
@@ -452,6 +485,7 @@ private:
     u3d_batch* batch_{};
     std::vector<unsigned> counts_, offsets_;
     bool policy_{};
+    bool threaded_{true};
     float sizeThreshold_{};
     unsigned maxTriangles_{};
     std::vector<float> camera3_;

@@ -1834,7 +1834,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         }
         CU_CHECK(mark(5));
         launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, firstLevel, st);
-        b->lastLaunches += 3 + (uint32_t)(vs.g.nlev - firstLevel);
+        b->lastLaunches += 4 + (uint32_t)(vs.g.nlev - firstLevel); // select, region scan, set-up, clipper + one launch per unfused level
         CU_CHECK(cudaGetLastError());
         }
     }
