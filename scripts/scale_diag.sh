@@ -1,7 +1,9 @@
 #!/bin/bash
 # Diagnostic sweep for the multi-GPU step overhead (run on an N-GPU box): bash scripts/scale_diag.sh N
+# N > 1: slots in flight, peer-memory exchange vs the NCCL baseline vs no exchange at all; N = 1: what a rank's share of the batch costs alone.
 N=${1:-2}
 out=gpurun_out
+mkdir -p $out
 run() { # name, env..., -- args
   name=$1; shift
   envs=(); while [ "$1" != "--" ]; do envs+=("$1"); shift; done; shift
@@ -13,20 +15,18 @@ run() { # name, env..., -- args
   echo "$name rc=$?"
 }
 if [ "$N" -gt 1 ]; then
-  run n${N}_if2 A=1 --
+  run n${N}_default A=1 --
+  run n${N}_if4 A=1 -- --inflight 4
   run n${N}_if1 A=1 -- --inflight 1
-  run n${N}_if3 A=1 -- --inflight 3
-  run n${N}_if2_nogather U3D_BENCH_NO_GATHER=1 --
-  run n${N}_if2_ctas2 NCCL_MAX_CTAS=2 --
-  run n${N}_if2_sb0 U3D_CULL_SMALL_BATCH=0 --
+  run n${N}_nccl A=1 -- --gather nccl
+  run n${N}_nogather U3D_BENCH_NO_GATHER=1 --
+  run n${N}_nccl_ctas2 NCCL_MAX_CTAS=2 -- --gather nccl
 else
   run v4096_if1 A=1 -- --inflight 1
-  run v4096_if2 A=1 -- --inflight 2
-  run v512_if1 A=1 -- --views 512 --inflight 1
-  run v512_if2 A=1 -- --views 512 --inflight 2
-  run v512_if3 A=1 -- --views 512 --inflight 3
-  run v512_if2_sb0 U3D_CULL_SMALL_BATCH=0 -- --views 512 --inflight 2
-  run v512_if3_sb0 U3D_CULL_SMALL_BATCH=0 -- --views 512 --inflight 3
-  run v1024_if2 A=1 -- --views 1024 --inflight 2
-  run v1024_if2_sb2000 U3D_CULL_SMALL_BATCH=2000 -- --views 1024 --inflight 2
+  run v4096_if8 A=1 -- --inflight 8
+  for v in 512 1024 2048; do
+    run v${v}_if1 A=1 -- --views $v --inflight 1
+    run v${v}_if4 A=1 -- --views $v --inflight 4
+    run v${v}_if12 A=1 -- --views $v --inflight 12
+  done
 fi
