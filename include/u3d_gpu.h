@@ -168,7 +168,10 @@ U3D_API int u3d_ob_set_max_triangles(u3d_ob* ob, uint32_t triangles);         /*
 U3D_API int u3d_ob_set_cull_mode(u3d_ob* ob, int mode);                       /* SetCullMode, OB.cpp:134-144 */
 U3D_API int u3d_ob_reset(u3d_ob* ob);                                         /* Reset, OB.cpp:146-150 */
 U3D_API int u3d_ob_clear(u3d_ob* ob);                                         /* Clear, OB.cpp:152-162 */
-/* AddTriangles (non-indexed / indexed), OB.cpp:164-198.  Like the reference, only the pointers are stored until DrawTriangles. */
+/* AddTriangles (non-indexed / indexed), OB.cpp:164-198.  Like the reference, only the pointers are stored until DrawTriangles.
+ * Counts that are not a multiple of three behave as in DrawBatch (OB.cpp:464-541): non-indexed geometry draws floor(count / 3) triangles;
+ * indexed geometry draws ceil(count / 3), reading up to two indices past the stated range (so they must be readable, as for the reference);
+ * numTriangles_ grows by count / 3 either way.  The batched occluder table refuses such indexed ranges (-U3D_ERR_UNSUPPORTED). */
 U3D_API int u3d_ob_add_triangles(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size, uint32_t vertex_start,
     uint32_t vertex_count);
 U3D_API int u3d_ob_add_triangles_indexed(u3d_ob* ob, const float model12[12], const void* vertex_data, uint32_t vertex_size,

@@ -989,3 +989,92 @@ def test_serial_occluder_branch(gpu_ctx, w, h):
     for o in (batch, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+def test_empty_and_ragged_inputs(gpu_ctx):
+    """Edge cases: an octree without drawables, a view that sees nothing, a batch called with zero views, an occlusion buffer drawn with no
+    batches / with a triangle count that is not a multiple of three, zero rays, and a batch whose views have wildly different result sizes
+    (ragged packed output).  Everything is compared with the oracle where the reference defines a result."""
+    w, h = 64, 30  # odd mip heights on the way down
+    # --- scene without drawables: only the root octant
+    empty = capi.Octree()
+    es = capi.GpuScene(gpu_ctx, octree=empty)
+    assert es.num_drawables == 0 and es.num_octants == 1
+    v0 = camera.make_view([0.0, 2.0, 0.0], 30.0, -5.0, 45.0, float(w) / h, 0.1, 300.0)
+    ids, qn = es.query(v0.planes)
+    assert len(ids) == 0 and qn == 0
+    assert [len(x) for x in es.raycast(np.array([[0, 5, 0, 0, -1, 0, np.inf]], np.float32))] == [0]
+    assert es.raycast(np.zeros((0, 7), np.float32)) == []
+    be = capi.Batch(gpu_ctx, es, None, 0, 0, 4, 16)
+    be.set_views(capi.pack_views([v0, v0], query_mode=capi.QUERY_FRUSTUM, use_occlusion=False))
+    be.run(capi.STAGE_VISIBLE)
+    assert (be.counts() == 0).all()
+    off, pk = be.packed()
+    assert off.tolist() == [0, 0, 0] and len(pk) == 0
+    be.set_views(capi.pack_views([v0], query_mode=capi.QUERY_FRUSTUM, use_occlusion=False)[:0])   # zero views: a no-op
+    be.run(capi.STAGE_VISIBLE)
+    assert be.counts().shape == (0, 2)
+    be.close()
+    es.close()
+    empty.close()
+
+    # --- occlusion buffer: nothing drawn, then a draw call whose index count is 7 (two triangles + one stray index)
+    sc = helpers.small_scene(n=2000, k=24, extent=60.0, seed=13)
+    ob = oraclebind.OracleOB()
+    ob.set_size(w, h)
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    assert gob.SetSize(w, h)
+    gob.SetView(v0)
+    ob.set_view(v0)
+    gob.Clear()
+    ob.clear()
+    gob.DrawTriangles()
+    gob.BuildDepthHierarchy()
+    ob.build_hierarchy()
+    assert np.array_equal(gob.GetBuffer(), ob.depth()) and (ob.depth() == 16777216).all()
+    for a, b in zip(gob.GetMips(), ob.mips()):
+        assert np.array_equal(a, b)
+    assert gob.IsVisible(sc.aabb[0]) == bool(ob.is_visible(sc.aabb[0]))
+    gob.SetCullMode(capi.CULL_NONE)
+    ob.set_cull_mode(capi.CULL_NONE)
+    model = np.array([6, 0, 0, 0, 0, 6, 0, 2, 0, 0, 1, 20], np.float32)
+    # DrawBatch (OB.cpp:464-541): an indexed count of 7 draws three triangles (the loop runs while indices < indicesEnd, reading indices 7 and 8
+    # of the buffer too), numTriangles_ counts 7 / 3 = 2 submitted
+    r_g = gob.AddTriangles(model, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 7)
+    r_o = ob.draw_batch(model, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 7)
+    gob.DrawTriangles()
+    assert bool(r_g) == bool(r_o) and np.array_equal(gob.GetBuffer(), ob.depth()) and gob.GetNumTriangles() == ob.num_triangles()
+    # ... and a non-indexed count of 8 draws two triangles (index + 2 < drawCount)
+    flat_vtx = np.ascontiguousarray(sc.mesh_vtx.view(np.uint8).reshape(-1, sc.mesh_stride)[sc.mesh_idx[:9]]).reshape(-1)
+    r_g = gob.AddTriangles(model, flat_vtx, sc.mesh_stride, None, 0, 8)
+    r_o = ob.draw_batch(model, flat_vtx, sc.mesh_stride, None, 0, 8)
+    gob.DrawTriangles()
+    assert bool(r_g) == bool(r_o) and np.array_equal(gob.GetBuffer(), ob.depth()) and gob.GetNumTriangles() == ob.num_triangles()
+    gob.close()
+    with pytest.raises(capi.U3DError) as e:  # the batched occluder table refuses what it would draw differently
+        m0 = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+        capi.Occluders(gpu_ctx, sc.occ_aabb[:1], sc.occ_model[:1], [m0], start=np.zeros(1, np.uint32), count=np.full(1, 7, np.uint32))
+    assert e.value.code == 6
+
+    # --- ragged results: one camera sees most of the scene, others see nothing
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob2 = helpers.make_oracle(sc, flat, w, h)
+    views = [camera.make_view([0.0, 80.0, 0.0], 0.0, 89.0, 100.0, float(w) / h, 0.1, 500.0),      # looks straight down on everything
+             camera.make_view([0.0, 2.0, 0.0], 0.0, -89.0, 20.0, float(w) / h, 0.1, 300.0),        # looks at the sky
+             camera.make_view([5000.0, 2.0, 5000.0], 45.0, 0.0, 45.0, float(w) / h, 0.1, 100.0),   # far outside the octree
+             camera.make_view([10.0, 2.0, -30.0], 200.0, -3.0, 45.0, float(w) / h, 0.1, 300.0)]
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    sizes = []
+    for i, v in enumerate(views):
+        sub, cand, vis = oracle_view(sc, otree, ob2, v)
+        assert np.array_equal(batch.depth(i), ob2.depth())
+        assert counts[i, 0] == len(cand) and np.array_equal(ids[offsets[i]:offsets[i + 1]], vis), "view %d" % i
+        sizes.append(len(vis))
+    assert max(sizes) > 500 and min(sizes) == 0
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+    ob2.close()

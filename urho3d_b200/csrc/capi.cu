@@ -884,6 +884,10 @@ int u3d_occluders_create(u3d_ctx* ctx, uint32_t n, const float* world_aabb6, con
         const uint32_t ct = index_count ? index_count[i] : avail;
         if ((uint64_t)st + ct > avail)
             return fail(U3D_ERR_INVALID, "u3d_occluders_create: draw range exceeds the mesh");
+        if (m->idxSize && ct % 3)
+            // DrawBatch (OB.cpp:507-519, 525-537) would draw ceil(count / 3) triangles and read past the range; the batched kernels draw
+            // count / 3, so such a range is refused rather than drawn differently (the drop-in u3d_ob_* path follows the reference)
+            return fail(U3D_ERR_UNSUPPORTED, "u3d_occluders_create: an indexed draw range must hold whole triangles (count % 3 == 0)");
         mesh[i] = mi;
         start[i] = st;
         count[i] = ct;
@@ -1088,8 +1092,10 @@ int u3d_ob_add_triangles_mesh(u3d_ob* ob, const float model12[12], const u3d_mes
     if (!ob || !model12 || !mesh)
         return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_mesh: NULL argument");
     const uint32_t avail = mesh->idxSize ? mesh->idxCount : mesh->vertexCount;
-    if ((uint64_t)start + count > avail)
-        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_mesh: range exceeds the mesh");
+    // indexed draws touch whole triangles (see u3d_ob_draw_triangles): the last one may reach up to two indices past `count`
+    const uint64_t touched = mesh->idxSize ? ((uint64_t)count + 2) / 3 * 3 : count;
+    if ((uint64_t)start + touched > avail)
+        return fail(U3D_ERR_INVALID, "u3d_ob_add_triangles_mesh: range exceeds the mesh (indexed ranges are read in whole triangles, as the reference's DrawBatch does)");
     return ob_push(ob, model12, nullptr, mesh->stride, nullptr, mesh->idxSize, start, count, mesh);
 }
 
@@ -1115,7 +1121,11 @@ int u3d_ob_draw_triangles(u3d_ob* ob)
     for (size_t i = 0; i < nb; ++i)
     {
         const HostBatchRec& r = ob->batches[i];
-        tris[i] = r.count / 3;
+        // DrawBatch, OB.cpp:464-541: non-indexed geometry draws floor(count / 3) triangles (`while (index + 2 < drawCount)`), indexed geometry
+        // loops `while (indices < indicesEnd)` in steps of three, i.e. ceil(count / 3) triangles, reading up to two indices past the stated
+        // range when the count is not a multiple of three.  Followed as is (numTriangles_ still counts count / 3, OB.cpp:196).
+        const bool indexed = r.mesh ? r.mesh->idxSize != 0 : r.idx != nullptr;
+        tris[i] = indexed ? (r.count + 2) / 3 : r.count / 3;
         if (r.mesh || !tris[i])
             continue;
         uint32_t maxVertex = 0;
