@@ -47,6 +47,9 @@ def parse():
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 result exchange: p2p = our fused pack+store kernel over NVLink peer memory (u3d_gather_*), nccl = library all-gather")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
+    ap.add_argument("--shard", default="balanced", choices=["balanced", "interleaved"],
+                    help="N>1 view assignment: balanced = equal view counts, per-view cost proxies of one untimed pass equalised over the ranks "
+                         "(urho3d_b200.sharding.balance_views); interleaved = view v on rank v mod N")
     return ap.parse_args()
 
 
@@ -62,7 +65,9 @@ def config_dict(args, world):
     return {"workload": "C3: %d agent cameras x %d drawables, %d box occluders (12 tris each), %dx%d occlusion buffers, depth hierarchy, "
                         "occluded octree query + visibility predicate" % (args.views, args.drawables, args.occluders, WIDTH, HEIGHT),
             "views": args.views, "drawables": args.drawables, "occluders": args.occluders, "buffer": [WIDTH, HEIGHT],
-            "sharding": "views interleaved over %d rank(s)" % world,
+            "sharding": ("views interleaved over %d rank(s)" % world if world == 1 or args.shard == "interleaved" else
+                         "views cost-balanced over %d ranks: equal view counts, assignment derived from the per-view statistics (submitted / set-up "
+                         "triangles, query size, visible count) of one untimed pass, as an engine would use the previous frame's" % world),
             "exchange": ("none (1 rank)" if world == 1 else "fused pack + NVLink peer-memory stores + flags (u3d_batch_push_results), every step"
                          if args.gather == "p2p" else "NCCL all_gather_into_tensor of counts and packed ids, every step"),
             "pipelining": "%d batch slots on separate streams; step k runs in slot k %% %d" % (max(1, args.inflight), max(1, args.inflight)),
@@ -254,6 +259,29 @@ class _DevArray:
         self.__cuda_array_interface__ = {"shape": shape, "typestr": typestr, "data": (ptr, False), "version": 2}
 
 
+def balanced_shards(batch, stream, my_ids, n_views, rank, world, device):
+    """One untimed pass over this rank's (interleaved) views, per-view statistics exchanged, cost-balanced assignment derived (the same on
+    every rank).  Returns (assignment, summary of the proxies' max-over-mean before and after)."""
+    import torch
+    from urho3d_b200 import capi, sharding
+    batch.run(capi.STAGE_VISIBLE, stream)
+    n = len(my_ids)
+    c_probe = batch.counts(stream).astype(np.int64)[:n]
+    t_probe = batch.tri_stats(stream).astype(np.int64)[:n]
+    local = torch.from_numpy(np.ascontiguousarray(np.concatenate([t_probe[:, [0, 2]], c_probe], axis=1))).to(device)
+    view_stats = sharding.gather_view_stats(local, my_ids, n_views, world).cpu().numpy()
+    assignment = sharding.balance_views(view_stats, world)
+
+    def worst(parts):
+        return [round(float(max(view_stats[p, c].sum() for p in parts) / max(view_stats[:, c].sum() / world, 1.0)), 4)
+                for c in range(view_stats.shape[1])]
+
+    summary = {"proxies": ["submitted_tris", "setup_tris", "query_result", "visible"],
+               "max_over_mean_interleaved": worst([np.arange(r, n_views, world) for r in range(world)]),
+               "max_over_mean_balanced": worst(assignment)}
+    return assignment, summary
+
+
 def main():
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
@@ -298,6 +326,18 @@ def main():
     stream = tstream.cuda_stream
     assert stream != 0
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device="cuda")
+
+    # N>1: cost-balanced shards.  Views differ widely in cost (std ~ mean), so 512 interleaved views per rank leave 5-7 % between the ranks of an
+    # 8-GPU run and every step ends with the slowest one.  One untimed pass on the interleaved shards yields per-view statistics; they are
+    # exchanged and every rank derives the same balanced assignment (equal view counts, so no buffer or exchange layout changes).
+    assignment, shard_balance = None, None
+    if world > 1 and args.shard == "balanced":
+        batch.set_views(packed, stream)
+        assignment, shard_balance = balanced_shards(batch, stream, my_ids, args.views, rank, world, torch.device("cuda", local_rank))
+        my_ids = [int(i) for i in assignment[rank]]
+        assert len(my_ids) == V, "the balanced assignment keeps every rank's view count"
+        my_views = [views[i] for i in my_ids]
+        packed = capi.pack_views(my_views)
 
     # device-resident leg ----------------------------------------------------------------------------------------------------
     # `inflight` result slots, each a u3d_batch on its own stream: step k runs in slot k % inflight, so the tail of one step's kernels (a few
@@ -367,7 +407,7 @@ def main():
             sl["batch"].run(capi.STAGE_VISIBLE, sl["stream"])
             _, pptr = sl["batch"].pack_device(sl["stream"])  # allocates the packed buffer once; its address is stable afterwards
             sl["packed"] = torch.as_tensor(_DevArray(pptr, (V * out_cap,)), device="cuda")
-            sl["gather"] = sharding.RawGather(args.views, world, cap, torch.device("cuda", local_rank))
+            sl["gather"] = sharding.RawGather(args.views, world, cap, torch.device("cuda", local_rank), assignment=assignment)
     torch.cuda.synchronize()
 
     def step_device(k):
@@ -445,7 +485,7 @@ def main():
         for sl in slots:
             assert not sl["gather"].overflowed(), "gather buffers too small"
             g_counts, _, _ = sl["gather"].reorder()
-            assert np.array_equal(g_counts[rank::world].cpu().numpy().astype(np.uint32), counts), "gathered counts disagree with the local ones"
+            assert np.array_equal(g_counts[my_ids].cpu().numpy().astype(np.uint32), counts), "gathered counts disagree with the local ones"
 
     if world > 1:
         dist.barrier()
@@ -465,7 +505,11 @@ def main():
         dist.barrier()
     t_end = time.perf_counter()
     total_ms = torch.tensor([ev_start.elapsed_time(ev_end)], dtype=torch.float64, device="cuda")
+    rank_ms = None
     if world > 1:
+        every = [torch.zeros_like(total_ms) for _ in range(world)]
+        dist.all_gather(every, total_ms)
+        rank_ms = [round(float(t.item()) / args.steps, 4) for t in every]
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     total_ms = float(total_ms.item())
     clocks = None
@@ -578,6 +622,10 @@ def main():
                                      "~99% of them and the scene SoA is L2-resident, so frac > 1 and DRAM traffic is ~260x lower: the kernel is "
                                      "latency / instruction-issue bound (ncu: issue-active 62%, 19 active lanes/instruction, barrier stalls), see DESIGN.md 4"},
                 "phases_rank0": phases, "clocks": clocks}
+        if rank_ms is not None:
+            line["ms_per_step_by_rank"] = rank_ms  # the exchange couples the ranks every step, so these differ little; `value` uses the max
+        if shard_balance is not None:
+            line["shard_balance"] = shard_balance
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
             cpu.step()  # warm-up pass (page faults of the forked workers, caches), as the --impl reference arm does

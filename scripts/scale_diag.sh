@@ -16,6 +16,8 @@ run() { # name, env..., -- args
 }
 if [ "$N" -gt 1 ]; then
   run n${N}_default A=1 --
+  run n${N}_interleaved A=1 -- --shard interleaved
+  run n${N}_if12 A=1 -- --inflight 12
   run n${N}_if4 A=1 -- --inflight 4
   run n${N}_if1 A=1 -- --inflight 1
   run n${N}_nccl A=1 -- --gather nccl

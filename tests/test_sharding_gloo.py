@@ -33,7 +33,7 @@ def _visible_sets(sc, flat, views, w, h):
     return out
 
 
-def _worker(rank, world, port, n_views, q):
+def _worker(rank, world, port, n_views, q, balanced=False):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -44,10 +44,26 @@ def _worker(rank, world, port, n_views, q):
     mine = sharding.shard_views(n_views, rank, world)
     res = _visible_sets(sc, flat, [views[i] for i in mine], w, h)
     counts = torch.tensor([[c, len(v)] for c, v in res], dtype=torch.int32).reshape(-1, 2)
+    assignment = None
+    if balanced:
+        # what bench.py does for N > 1: the first (interleaved) pass's per-view statistics are exchanged, every rank derives the same
+        # cost-balanced assignment from them, and the next pass runs on the new shards
+        stats = sharding.gather_view_stats(counts.to(torch.int64), mine, n_views, world)
+        assert stats.shape == (n_views, 2)
+        assignment = sharding.balance_views(stats.numpy(), world)
+        everyone = [None] * world
+        dist.all_gather_object(everyone, [a.tolist() for a in assignment])
+        assert all(e == everyone[0] for e in everyone), "ranks derived different assignments"
+        assert [len(a) for a in assignment] == [len(sharding.shard_views(n_views, r, world)) for r in range(world)]
+        mine = assignment[rank].tolist()
+        res = _visible_sets(sc, flat, [views[i] for i in mine], w, h)
+        counts = torch.tensor([[c, len(v)] for c, v in res], dtype=torch.int32).reshape(-1, 2)
+        again = sharding.gather_view_stats(counts.to(torch.int64), mine, n_views, world)
+        assert torch.equal(again, stats), "per-view statistics do not depend on the assignment"
     ids = torch.from_numpy(np.concatenate([v for _, v in res]) if res else np.zeros(0, np.int32))
-    g_counts, g_off, g_ids = sharding.gather_results(counts, ids, n_views, rank, world)
+    g_counts, g_off, g_ids = sharding.gather_results(counts, ids, n_views, rank, world, assignment=assignment)
     # the sync-free variant used in the steady state must give the same answer
-    raw = sharding.RawGather(n_views, world, 40000, torch.device("cpu"))
+    raw = sharding.RawGather(n_views, world, 40000, torch.device("cpu"), assignment=assignment)
     padded = torch.zeros(40000, dtype=torch.int32)
     padded[:ids.shape[0]] = ids
     raw.run(counts, padded)
@@ -60,13 +76,13 @@ def _worker(rank, world, port, n_views, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n_views", [7, 8])
-def test_sharded_gather_equals_single_process(n_views):
+@pytest.mark.parametrize("n_views,balanced", [(7, False), (8, False), (7, True), (12, True)])
+def test_sharded_gather_equals_single_process(n_views, balanced):
     world = 2
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, n_views, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, n_views, q, balanced)) for r in range(world)]
     for p in procs:
         p.start()
     counts, off, ids = q.get(timeout=120)
@@ -88,3 +104,85 @@ def test_shard_views_covers_everything_once():
     for n, world in ((4096, 8), (7, 2), (3, 4)):
         got = sorted(sum((sharding.shard_views(n, r, world) for r in range(world)), []))
         assert got == list(range(n))
+
+
+def test_balance_views_equalises_every_cost_column():
+    rng = np.random.default_rng(5)
+    n = 4096
+    # heavy-tailed, partly correlated proxies like the benchmark's (triangles, query survivors, visible): std ~ mean
+    base = rng.gamma(1.0, 1.0, n)
+    costs = np.stack([base * rng.uniform(0.5, 1.5, n) * 6000, rng.gamma(0.8, 12000.0, n), base * rng.uniform(0.2, 1.8, n) * 2000], axis=1)
+    for world in (2, 4, 8):
+        parts = sharding.balance_views(costs, world)
+        assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+        assert [len(p) for p in parts] == [n // world] * world
+        assert all(np.all(np.diff(p) > 0) for p in parts)
+        for col in range(costs.shape[1]):
+            bal = np.array([costs[p, col].sum() for p in parts])
+            assert bal.max() / bal.mean() < 1.005, (world, col, bal.max() / bal.mean())
+        inter8 = max(np.array([costs[r::8, col].sum() for r in range(8)]).max() / (costs[:, col].sum() / 8) for col in range(3))
+        assert inter8 > 1.02  # the interleaved rule leaves several per cent between the ranks on such costs
+        again = sharding.balance_views(costs.copy(), world)
+        assert all(np.array_equal(a, b) for a, b in zip(parts, again))
+
+
+def test_balance_views_edge_cases():
+    # uneven division keeps the interleaved quotas; no information (or garbage) falls back to something that still covers every view once
+    for n, world in ((7, 2), (3, 4), (0, 2), (1, 8)):
+        for costs in (np.zeros((n, 3)), np.arange(n, dtype=np.float64), np.full((n, 2), np.nan)):
+            parts = sharding.balance_views(costs, world)
+            assert len(parts) == world
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))
+            assert [len(p) for p in parts] == [len(sharding.shard_views(n, r, world)) for r in range(world)]
+
+
+class _FakeBatch:
+    """Stands in for capi.Batch in bench.balanced_shards: per-view statistics of this rank's views (no GPU in the CPU suite)."""
+
+    def __init__(self, stats):
+        self.stats = stats  # [n_local, 4]: submitted, set-up, query size, visible
+
+    def run(self, stage, stream):
+        pass
+
+    def counts(self, stream):
+        return self.stats[:, 2:4].astype(np.uint32)
+
+    def tri_stats(self, stream):
+        return np.stack([self.stats[:, 0], self.stats[:, 0] + 1, self.stats[:, 1]], axis=1).astype(np.uint32)
+
+
+def _bench_worker(rank, world, port, n_views, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import bench
+    rng = np.random.default_rng(11)
+    stats = (rng.gamma(1.0, 1.0, (n_views, 4)) * np.array([6000.0, 3000.0, 10000.0, 2000.0])).astype(np.int64)
+    mine = sharding.shard_views(n_views, rank, world)
+    assignment, summary = bench.balanced_shards(_FakeBatch(stats[mine]), None, mine, n_views, rank, world, torch.device("cpu"))
+    q.put((rank, [a.tolist() for a in assignment], summary))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bench_rebalancing_step_under_gloo():
+    """bench.py's N>1 set-up step (probe pass -> exchanged statistics -> balanced assignment) with two ranks."""
+    world, n_views = 2, 200
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_bench_worker, args=(r, world, port, n_views, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = sorted((q.get(timeout=120) for _ in range(world)), key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got[0][1] == got[1][1], "both ranks must derive the same assignment"
+    parts = got[0][1]
+    assert sorted(parts[0] + parts[1]) == list(range(n_views)) and len(parts[0]) == len(parts[1]) == n_views // 2
+    summary = got[0][2]
+    assert max(summary["max_over_mean_balanced"]) < 1.01 < max(summary["max_over_mean_interleaved"])
+    import json
+    json.dumps(summary)
