@@ -43,7 +43,10 @@ def parse():
     ap.add_argument("--drawables", type=int, default=1_000_000)
     ap.add_argument("--occluders", type=int, default=4000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--inflight", type=int, default=8, help="result slots (u3d_batch objects on their own streams) the steps rotate through")
+    ap.add_argument("--inflight", type=int, default=0,
+                    help="result slots (u3d_batch objects on their own streams) the steps rotate through; 0 = 8 for shards above 1024 views, 12 below "
+                         "(a small batch leaves more of the GPU idle at the end of each of its ~25 dependent passes: measured on one GPU with lone "
+                         "512-view batches, 8 -> 12 slots: device 425 -> 430 k views/s, end to end 325 -> 355 k, profiles/r01_lone512_slots.jsonl)")
     ap.add_argument("--gather", default="p2p", choices=["p2p", "nccl"],
                     help="N>1 result exchange: p2p = our fused pack+store kernel over NVLink peer memory (u3d_gather_*), nccl = library all-gather")
     ap.add_argument("--cpu-sample", type=int, default=2048, help="views of the workload timed on the host cores")
@@ -192,7 +195,7 @@ def run_reference_arm(args, rank, world):
     value = nviews / total
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32",
-            "data": "synthetic", "config": config_dict(args, 1), "occluder_mtri_per_s": tris / total / 1e6,
+            "data": "synthetic", "config": config_dict(args, world), "occluder_mtri_per_s": tris / total / 1e6,
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     cpu.close()
@@ -287,6 +290,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.inflight <= 0:
+        args.inflight = 8 if (args.views + world - 1) // world > 1024 else 12
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
         return
