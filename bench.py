@@ -70,7 +70,8 @@ def config_dict(args, world):
             "views": args.views, "drawables": args.drawables, "occluders": args.occluders, "buffer": [WIDTH, HEIGHT],
             "sharding": ("views interleaved over %d rank(s)" % world if world == 1 or args.shard == "interleaved" else
                          "views cost-balanced over %d ranks: equal view counts, assignment derived from the per-view statistics (submitted / set-up "
-                         "triangles, query size, visible count) of one untimed pass, as an engine would use the previous frame's" % world),
+                         "triangles, query size, visible count) of one untimed pass, as an engine would use the previous frame's; costly views "
+                         "first within a shard" % world),
             "exchange": ("none (1 rank)" if world == 1 else "fused pack + NVLink peer-memory stores + flags (u3d_batch_push_results), every step"
                          if args.gather == "p2p" else "NCCL all_gather_into_tensor of counts and packed ids, every step"),
             "pipelining": "%d batch slots on separate streams; step k runs in slot k %% %d" % (max(1, args.inflight), max(1, args.inflight)),
@@ -274,6 +275,10 @@ def balanced_shards(batch, stream, my_ids, n_views, rank, world, device):
     local = torch.from_numpy(np.ascontiguousarray(np.concatenate([t_probe[:, [0, 2]], c_probe], axis=1))).to(device)
     view_stats = sharding.gather_view_stats(local, my_ids, n_views, world).cpu().numpy()
     assignment = sharding.balance_views(view_stats, world)
+    # within a shard: costly views first.  CTAs are handed out in view order, and with only a wave or two of CTAs per launch a costly view that
+    # starts last is what the launch (and every launch queued behind it on the stream) waits for.
+    weight = (view_stats / np.maximum(view_stats.sum(axis=0), 1)).sum(axis=1)
+    assignment = [a[np.lexsort((a, -weight[a]))] for a in assignment]
 
     def worst(parts):
         return [round(float(max(view_stats[p, c].sum() for p in parts) / max(view_stats[:, c].sum() / world, 1.0)), 4)

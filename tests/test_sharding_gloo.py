@@ -182,6 +182,12 @@ def test_bench_rebalancing_step_under_gloo():
     assert got[0][1] == got[1][1], "both ranks must derive the same assignment"
     parts = got[0][1]
     assert sorted(parts[0] + parts[1]) == list(range(n_views)) and len(parts[0]) == len(parts[1]) == n_views // 2
+    # costly views first within a shard (same statistics as the worker's)
+    stats = (np.random.default_rng(11).gamma(1.0, 1.0, (n_views, 4)) * np.array([6000.0, 3000.0, 10000.0, 2000.0])).astype(np.int64)
+    stats = np.stack([stats[:, 0], stats[:, 1], stats[:, 2], stats[:, 3]], axis=1)
+    weight = (stats / stats.sum(axis=0)).sum(axis=1)
+    for part in parts:
+        assert np.all(np.diff(weight[part]) <= 1e-15)
     summary = got[0][2]
     assert max(summary["max_over_mean_balanced"]) < 1.01 < max(summary["max_over_mean_interleaved"])
     import json
