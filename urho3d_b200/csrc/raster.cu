@@ -1423,6 +1423,10 @@ __device__ __forceinline__ TriSetup bcast_tri(const TriSetup& t, int src)
     return r;
 }
 
+#ifndef U3D_FILL_BULK_STORE
+#define U3D_FILL_BULK_STORE 0
+#endif
+
 __device__ __forceinline__ void tile_min(int* tile, int idx, int z)
 {
     if (z < tile[idx])
@@ -1586,9 +1590,32 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             }
         }
     }
+#if U3D_FILL_BULK_STORE
+    // EXPERIMENT, compiled out by default and not yet run on a GPU: when the tile spans whole buffer rows (w <= 256, the benchmark's shape) its
+    // rows are contiguous in HBM too, so the finished tile can leave shared memory as ONE bulk asynchronous copy (TMA, UBLKCP.G.S) issued by
+    // one thread while all threads go on to reduce the hierarchy from the same shared memory.  The writers' generic-proxy stores are fenced
+    // towards the async proxy before the barrier; the copy's read of shared memory is waited for before level 0 overwrites the tile in place.
+    const bool bulkStore = tw == g.w;
+    if (bulkStore)
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+#else
+    constexpr bool bulkStore = false;
+#endif
     __syncthreads();
 
     // ---- write the tile's depth to HBM ----
+#if U3D_FILL_BULK_STORE
+    if (bulkStore)
+    {
+        if (tid == 0)
+        {
+            const uint32_t src = (uint32_t)__cvta_generic_to_shared(tile);
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(depth + (size_t)ty0 * g.w), "r"(src), "r"(rows * tw * 4) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+    }
+    else
+#endif
     {
         const int tw4 = tw >> 2;
         const int n4 = tw4 * rows;
@@ -1600,7 +1627,13 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         }
     }
     if (!tg.fused || !rd.writeMips)
+    {
+#if U3D_FILL_BULK_STORE
+        if (bulkStore && tid == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // shared memory must outlive the copy's read
+#endif
         return;
+    }
 
     // ---- fused depth hierarchy ----
     // Level 0 is computed in place: every thread first pulls its inputs into registers, then (after a barrier) the (min,max) pairs
@@ -1631,6 +1664,10 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
                 acc[j] = make_int2(mn, mx);
             }
         }
+#if U3D_FILL_BULK_STORE
+        if (bulkStore && tid == 0)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); // the tile is overwritten in place below
+#endif
         __syncthreads();
 #pragma unroll
         for (int j = 0; j < kPerThread; ++j)
