@@ -526,5 +526,96 @@ private:
     u3d_gather* gather_{};
 };
 
+#ifdef URHO3D_API
+// ---------------------------------------------------------------------------------------------------------------------------------
+// In-engine helpers (compiled only inside the engine, i.e. after the reference's own headers: Camera.h, Frustum.h, BoundingBox.h).
+// They turn the engine objects the call sites of View.cpp hold into the plain arrays the classes above take, so that the edited call
+// sites of INTEGRATION.md read like the originals.  Compiled and run against the reference's headers by tests/test_engine_types.py.
+// ---------------------------------------------------------------------------------------------------------------------------------
+
+/// Frustum::planes_ (Frustum.h:37-45, 196) as 6 x (normal.xyz, d) in the reference's plane order.
+inline void PlanesOf(const Frustum& frustum, float* planes6x4)
+{
+    for (unsigned i = 0; i < NUM_FRUSTUM_PLANES; ++i)
+    {
+        const Plane& p = frustum.planes_[i];
+        planes6x4[4 * i + 0] = p.normal_.x_;
+        planes6x4[4 * i + 1] = p.normal_.y_;
+        planes6x4[4 * i + 2] = p.normal_.z_;
+        planes6x4[4 * i + 3] = p.d_;
+    }
+}
+
+/// BoundingBox as (min.xyz, max.xyz).
+inline void BoxOf(const BoundingBox& box, float* minMax6)
+{
+    minMax6[0] = box.min_.x_; minMax6[1] = box.min_.y_; minMax6[2] = box.min_.z_;
+    minMax6[3] = box.max_.x_; minMax6[4] = box.max_.y_; minMax6[5] = box.max_.z_;
+}
+
+/// One view of the batched entry point from the Camera a View culls with: what OcclusionBuffer::SetView (OcclusionBuffer.cpp:115-127) and
+/// the octree query of View::GetDrawables (View.cpp:868-878) read from it.
+inline u3d_view MakeView(Camera* camera, unsigned char drawableFlags, unsigned viewMask, int queryMode = U3D_QUERY_OCCLUDED, bool useOcclusion = true)
+{
+    u3d_view v;
+    std::memset(&v, 0, sizeof(v));
+    std::memcpy(v.view, camera->GetView().Data(), sizeof(v.view));
+    const Matrix4 projection = camera->GetProjection();
+    std::memcpy(v.projection, projection.Data(), sizeof(v.projection));
+    PlanesOf(camera->GetFrustum(), v.planes);
+    v.near_clip = camera->GetNearClip();
+    v.far_clip = camera->GetFarClip();
+    v.drawable_flags = drawableFlags;
+    v.view_mask = viewMask;
+    v.reverse_culling = camera->GetReverseCulling() ? 1 : 0;
+    v.query_mode = queryMode;
+    v.use_occlusion = useOcclusion ? 1 : 0;
+    v.orthographic = camera->IsOrthographic() ? 1 : 0;
+    const Vector3 position = camera->GetNode() ? camera->GetNode()->GetWorldPosition() : Vector3::ZERO;
+    v.camera_position[0] = position.x_; v.camera_position[1] = position.y_; v.camera_position[2] = position.z_;
+    return v;
+}
+
+/// The reference's constructor signatures: FrustumOctreeQuery(result, frustum, drawableFlags, viewMask) (OctreeQuery.h:144-149),
+/// OccludedFrustumOctreeQuery(result, frustum, buffer, drawableFlags, viewMask) (View.cpp:120-125), ShadowCasterOctreeQuery (View.cpp:63-67),
+/// ZoneOccluderOctreeQuery (View.cpp:91-95).  result receives drawable ids of the mirror instead of Drawable pointers.
+struct FrustumPlanes
+{
+    explicit FrustumPlanes(const Frustum& frustum) { PlanesOf(frustum, data); }
+    float data[24];
+};
+inline GpuFrustumOctreeQuery MakeFrustumQuery(std::vector<unsigned>& result, const Frustum& frustum, unsigned char drawableFlags = DRAWABLE_ANY,
+    unsigned viewMask = DEFAULT_VIEWMASK)
+{
+    return GpuFrustumOctreeQuery(result, FrustumPlanes(frustum).data, drawableFlags, viewMask);
+}
+inline GpuOccludedFrustumOctreeQuery MakeOccludedFrustumQuery(std::vector<unsigned>& result, const Frustum& frustum, GpuOcclusionBuffer* buffer,
+    unsigned char drawableFlags = DRAWABLE_ANY, unsigned viewMask = DEFAULT_VIEWMASK)
+{
+    return GpuOccludedFrustumOctreeQuery(result, FrustumPlanes(frustum).data, buffer, drawableFlags, viewMask);
+}
+inline GpuShadowCasterOctreeQuery MakeShadowCasterQuery(std::vector<unsigned>& result, const Frustum& frustum, unsigned char drawableFlags = DRAWABLE_ANY,
+    unsigned viewMask = DEFAULT_VIEWMASK)
+{
+    return GpuShadowCasterOctreeQuery(result, FrustumPlanes(frustum).data, drawableFlags, viewMask);
+}
+inline GpuZoneOccluderOctreeQuery MakeZoneOccluderQuery(std::vector<unsigned>& result, const Frustum& frustum, unsigned char drawableFlags = DRAWABLE_ANY,
+    unsigned viewMask = DEFAULT_VIEWMASK)
+{
+    return GpuZoneOccluderOctreeQuery(result, FrustumPlanes(frustum).data, drawableFlags, viewMask);
+}
+
+/// Octree::InsertDrawable for a real Drawable: its world box, flags, view mask, occludee / cast-shadows / occluder state.
+inline unsigned InsertDrawable(GpuOctree& octree, Drawable* drawable)
+{
+    float box[6];
+    BoxOf(drawable->GetWorldBoundingBox(), box);
+    const unsigned id = octree.InsertDrawable(box, drawable->GetDrawableFlags(), drawable->GetViewMask(), drawable->IsOccludee(), drawable->GetCastShadows());
+    if (drawable->IsOccluder())
+        octree.SetOccluder(id, true);
+    return id;
+}
+#endif // URHO3D_API
+
 } // namespace GPUCompute
 } // namespace Urho3D

@@ -20,7 +20,7 @@ constexpr int kCullBigRing = 16384;      // queue entries of the one-CTA-per-SM 
 constexpr int kWStackEntries = U3D_WSTACK; // per-warp texel stack of the cooperative range test
 constexpr int kChunkWords = 256;         // chunk bitmaps: up to 256 * 32 chunks of >= 512 octants = 4M octants
 constexpr int kHeavyExtentDefault = 96;
-__device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)        // rects larger than this (pixels) are tested by a whole warp
+__device__ int g_heavyExtent = kHeavyExtentDefault; // rect extent (pixels) from which a box is walked by a whole warp (tuning hook)
 static int g_cullRingHost = 4096;       // queue entries of the three-CTAs-per-SM shape (2048 / 4096 / 8192)
 #ifndef U3D_WALK_POOL
 #define U3D_WALK_POOL 0
@@ -29,7 +29,9 @@ static int g_cullRingHost = 4096;       // queue entries of the three-CTAs-per-S
 #define U3D_HEAVYCAP 512
 #endif
 constexpr int kHeavyCap = U3D_HEAVYCAP;          // large-rect boxes parked per evaluation pass; each is then taken by one warp
-__device__ int g_walkPool = 0;          // off by default (measured slower: 8.1 vs 6.4 ms, the pass is latency- not issue-bound); 1: the boxes of a warp share one texel stack (range_visible_pool); 0: one walk per lane (tuning hook)
+// Tuning hook, off by default (measured slower: 8.1 vs 6.4 ms, the pass is latency- not issue-bound).  1: the boxes of a warp share one texel
+// stack (range_visible_pool); 0: one walk per lane.  Only read when built with -DU3D_WALK_POOL=1.
+__device__ int g_walkPool = 0;
 
 /// T = threads per CTA, R = work-queue entries held in shared memory between evaluation passes.
 template <int T, int R> struct CullShared
