@@ -1,0 +1,110 @@
+"""Device counterparts of the CPU suite's wild-input pins (tests/test_oracle_vs_reference.py: test_wild_boxes_*, test_queries_over_wild_*,
+test_triangle_soup_fuzz_*; tests/test_host_octree.py: test_wild_drawable_boxes_*).  The oracle equals the compiled reference on all of
+these inputs; here the CUDA path must equal the oracle.  See conftest.py for why this directory is opt-in."""
+import numpy as np
+import pytest
+
+import helpers
+from oracle import oraclebind
+from test_oracle_vs_reference import _soup, _wild_boxes, shape_cases
+from urho3d_b200 import camera, capi, scenes
+
+pytestmark = pytest.mark.gpu
+
+
+def test_wild_boxes_is_visible(gpu_ctx):
+    rs = np.random.RandomState(77)
+    for w, h, fov, pos, yaw, pitch in ((128, 64, 60.0, [0.0, 2.0, 0.0], 30.0, 0.0), (256, 160, 45.0, [10.0, 1.0, -20.0], 200.0, -20.0),
+                                       (64, 30, 100.0, [-30.0, 8.0, 5.0], 90.0, 35.0)):
+        sc = helpers.small_scene(n=200, k=64, extent=40.0, seed=5 + w)
+        v = camera.make_view(pos, yaw, pitch, fov, w / h, 0.1, 200.0)
+        gob = capi.OcclusionBuffer(gpu_ctx)
+        gob.SetSize(w, h)
+        ob = oraclebind.OracleOB()
+        ob.set_size(w, h)
+        gob.SetView(v)
+        ob.set_view(v)
+        gob.SetMaxTriangles(1 << 30)
+        ob.set_max_triangles(1 << 30)
+        gob.Clear()
+        ob.clear()
+        for i in range(sc.k):
+            gob.SetCullMode(sc.cull_mode)
+            ob.set_cull_mode(sc.cull_mode)
+            gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+            ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+        gob.DrawTriangles()
+        boxes = _wild_boxes(rs, 2000, 45.0)
+        assert np.array_equal(gob.IsVisibleMany(boxes), ob.is_visible_many(boxes))      # dirty hierarchy: pixel scan
+        gob.BuildDepthHierarchy()
+        ob.build_hierarchy()
+        assert np.array_equal(gob.IsVisibleMany(boxes), ob.is_visible_many(boxes))      # clean: mip walk
+        gob.close()
+        ob.close()
+
+
+def test_queries_over_wild_drawables(gpu_ctx):
+    rs = np.random.RandomState(12)
+    n = 4000
+    sc = helpers.small_scene(n=n, k=96, extent=80.0, seed=17)
+    sc.aabb[:n // 2] = np.where(rs.uniform(size=(n // 2, 1)) < 0.3, _wild_boxes(rs, n // 2, 85.0), sc.aabb[:n // 2])
+    w, h = 128, 80
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = helpers.stress_views(80.0, w, h, 6, seed=5) + scenes.agent_cameras(4, 80.0, w, h, seed=6)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    for i, v in enumerate(views):
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(batch.depth(i), ob.depth())
+        cand = otree.query(1, v.planes, ob, as_ids=False)
+        vis = otree.order[otree.check_visibility(ob, cand)]
+        assert counts[i, 0] == len(cand) and np.array_equal(ids[offsets[i]:offsets[i + 1]], vis)
+        for mode in (0, 2):
+            got, qc = gs.query(v.planes, None, 0xFF, 0xFFFFFFFF, mode, capi.STAGE_QUERY)
+            assert np.array_equal(got, otree.query(mode, v.planes, None))
+    for shape, params in shape_cases(rs, 80.0):
+        got, qc = gs.query(params, None, mode=shape)
+        assert np.array_equal(got, otree.query(shape, params, None)), (shape, params)
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+@pytest.mark.parametrize("kind", ["tame", "clip", "sliver", "huge", "nonfinite"])
+def test_triangle_soups(gpu_ctx, kind):
+    model = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32)
+    for case in range(12 if kind != "nonfinite" else 5):
+        rs = np.random.RandomState(100 * case + len(kind))
+        w, h = [(64, 64), (128, 80), (256, 36)][case % 3]
+        v = camera.make_view([0, 0, 0], 0, 0, [45.0, 90.0][case % 2], float(w) / h, 0.1, 100.0)
+        vtx = np.ascontiguousarray(_soup(kind, rs, 80))
+        cull = case % 3
+        ob = oraclebind.OracleOB()
+        ob.set_size(w, h)
+        ob.set_view(v)
+        ob.set_max_triangles(1 << 30)
+        ob.clear()
+        ob.set_cull_mode(cull)
+        ob.draw_batch(model, vtx, 12, None, 0, vtx.shape[0])
+        ob.build_hierarchy()
+        gob = capi.OcclusionBuffer(gpu_ctx)
+        gob.SetSize(w, h)
+        gob.SetView(v)
+        gob.SetMaxTriangles(1 << 30)
+        gob.Clear()
+        gob.SetCullMode(cull)
+        gob.AddTriangles(model, vtx, 12, None, 0, vtx.shape[0])
+        gob.DrawTriangles()
+        gob.BuildDepthHierarchy()
+        assert np.array_equal(gob.GetBuffer(), ob.depth()), (kind, case)
+        for a, b in zip(gob.GetMips(), ob.mips()):
+            assert np.array_equal(a, b), (kind, case)
+        assert gob.GetNumTriangles() == ob.num_triangles(), (kind, case)
+        gob.close()
+        ob.close()

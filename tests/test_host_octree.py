@@ -97,3 +97,29 @@ def test_host_sort_follows_the_reference_sort():
             gk, gv = capi.sort_by_key(keys, vals.astype(np.uint32))
             assert np.array_equal(rk, gk) and np.array_equal(rv.astype(np.uint32), gv), (n, distinct)
     ref.close()
+
+
+def test_wild_drawable_boxes_keep_the_reference_structure():
+    """Drawables whose boxes are inverted, flat, points, enormous, infinite or NaN: the mirror's insertion rule (CheckDrawableFit, Octree.cpp:
+    134-190) must put every one of them where the reference's Octree does, and the flattened arrays must stay bit-equal."""
+    rs = np.random.RandomState(8)
+    n = 3000
+    sc = scenes.Scene(n, 4, 200.0, seed=31)
+    b = sc.aabb
+    k = n // 12
+    b[0 * k:1 * k] = b[0 * k:1 * k][:, [3, 4, 5, 0, 1, 2]]        # inverted (undefined BoundingBox)
+    b[1 * k:2 * k, 3:] = b[1 * k:2 * k, :3]                        # points
+    b[2 * k:3 * k, 4] = b[2 * k:3 * k, 1]                          # flat
+    b[3 * k:4 * k, :3] -= rs.uniform(0, 3000, size=(k, 3)).astype(np.float32)   # from a little to far larger than the octree
+    b[3 * k:4 * k, 3:] += rs.uniform(0, 3000, size=(k, 3)).astype(np.float32)
+    b[4 * k:5 * k] += np.float32(990.0)                            # straddling / outside the octree bounds (+-1000)
+    b[5 * k:6 * k, 3] = np.inf
+    b[6 * k:7 * k, 2] = -np.inf
+    b[7 * k:8 * k, 0] = np.nan
+    b[8 * k:9 * k, 5] = np.nan
+    b[9 * k:10 * k] = np.float32(1e30)
+    ref = helpers.make_ref(sc, 64, 64)
+    t, flat = helpers.host_flatten(sc)
+    assert_same_flat(flat, ref.flatten())
+    t.close()
+    ref.close()

@@ -450,3 +450,98 @@ def test_triangle_soup_fuzz_matches_reference(kind):
     # now and then the reference also dies on enormous finite coordinates (spans far outside the buffer's padding): whatever it survives must
     # match; the ordinary classes it must survive entirely
     assert compared >= {"nonfinite": 0, "huge": 8}.get(kind, 12)
+
+
+def _wild_boxes(rs, n, extent):
+    """Boxes that provoke IsVisible's and the frustum tests' edge cases: behind / around the camera, enormous, flat, inverted (min > max, an
+    undefined BoundingBox), far beyond the far plane, with infinite or NaN bounds."""
+    c = rs.uniform(-extent, extent, size=(n, 3)).astype(np.float32)
+    e = rs.uniform(0.01, 5.0, size=(n, 3)).astype(np.float32)
+    b = np.concatenate([c - e, c + e], axis=1).astype(np.float32)
+    k = n // 10
+    b[0 * k:1 * k, :3] -= np.float32(1e4)                    # enormous boxes containing the camera
+    b[0 * k:1 * k, 3:] += np.float32(1e4)
+    b[1 * k:2 * k, 4] = b[1 * k:2 * k, 1]                    # flat in y
+    b[2 * k:3 * k] = b[2 * k:3 * k][:, [3, 4, 5, 0, 1, 2]]   # inverted
+    b[3 * k:4 * k] *= np.float32(1e3)                        # far away
+    b[4 * k:5 * k, 3:] = b[4 * k:5 * k, :3]                  # points
+    b[5 * k:6 * k, 3] = np.inf
+    b[6 * k:7 * k, 1] = -np.inf
+    b[7 * k:7 * k + k // 2, 2] = np.nan
+    b[7 * k + k // 2:8 * k] = np.float32(1e30) * np.sign(b[7 * k + k // 2:8 * k])
+    return b
+
+
+def test_wild_boxes_is_visible_and_frustum_tests_match_reference():
+    """IsVisible (dirty and clean hierarchy) and Frustum::IsInside / IsInsideFast on boxes far outside what a scene normally holds.  Both are
+    read-only in the reference, so every answer is defined and must be equal, also for NaN and infinite bounds."""
+    from urho3d_b200 import camera
+    rs = np.random.RandomState(77)
+    for w, h, fov, pos, yaw, pitch in ((128, 64, 60.0, [0.0, 2.0, 0.0], 30.0, 0.0), (256, 160, 45.0, [10.0, 1.0, -20.0], 200.0, -20.0),
+                                       (64, 30, 100.0, [-30.0, 8.0, 5.0], 90.0, 35.0)):
+        sc = helpers.small_scene(n=200, k=64, extent=40.0, seed=5 + w)
+        ref = helpers.make_ref(sc, w, h)
+        _, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+        v = camera.make_view(pos, yaw, pitch, fov, w / h, 0.1, 200.0)
+        ref.set_view_raw(v)
+        ref.ob_set_max_triangles(1 << 30)
+        ref.ob_clear()
+        ob.set_view(v)
+        ob.set_max_triangles(1 << 30)
+        ob.clear()
+        for i in range(sc.k):
+            ref.ob_set_cull_mode(sc.cull_mode)
+            ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+            ob.set_cull_mode(sc.cull_mode)
+            ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx, 0, 36)
+        ref.ob_draw()
+        boxes = _wild_boxes(rs, 2000, 45.0)
+        dirty = ref.ob_is_visible_many(boxes)
+        assert np.array_equal(ob.is_visible_many(boxes), dirty)
+        ref.ob_build_hierarchy()
+        ob.build_hierarchy()
+        clean = ref.ob_is_visible_many(boxes)
+        assert np.array_equal(ob.is_visible_many(boxes), clean)
+        assert 0 < clean.sum() < len(boxes)
+        for fast in (False, True):
+            want = np.array([ref.frustum_is_inside(b, fast=fast) for b in boxes[::4]])
+            got = np.array([oraclebind.frustum_test(v.planes, b, fast=fast) for b in boxes[::4]])
+            assert np.array_equal(got, want), fast
+        ref.close()
+        ob.close()
+
+
+def test_queries_over_wild_drawables_match_reference():
+    """Every query class over a scene whose drawables include inverted, flat, point-sized, enormous, infinite and NaN boxes (the octree keeps
+    most of those in its root): frustum / occluded / shadow-caster queries with the visibility predicate, sphere / box / point queries and
+    ray casts must give the reference's result sequences."""
+    rs = np.random.RandomState(12)
+    n = 4000
+    sc = helpers.small_scene(n=n, k=96, extent=80.0, seed=17)
+    sc.aabb[:n // 2] = np.where(rs.uniform(size=(n // 2, 1)) < 0.3, _wild_boxes(rs, n // 2, 85.0), sc.aabb[:n // 2])
+    w, h = 128, 80
+    ref = helpers.make_ref(sc, w, h)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    for v in helpers.stress_views(80.0, w, h, 6, seed=5) + scenes.agent_cameras(4, 80.0, w, h, seed=6):
+        vis, counts = helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(ob.depth(), ref.ob_depth())
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+        assert np.array_equal(tree.query(0, v.planes, None), ref.query(0))
+        assert np.array_equal(tree.query(2, v.planes, None), ref.query(2))
+    for shape, params in shape_cases(rs, 80.0):
+        assert np.array_equal(tree.query(shape, params, None, 0xFF), ref.query_shape(shape, params, 0xFF)), (shape, params)
+    hits = 0
+    for o, d, maxd in helpers.random_rays(80.0, 40, seed=2):
+        for single in (False, True):
+            rid, rdist, _ = ref.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
+            oid, odist = tree.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
+            assert np.array_equal(rid, oid), (o, d, maxd, single)
+            assert np.array_equal(rdist.view(np.uint32), odist.view(np.uint32))
+            hits += len(rid)
+    assert hits > 0
+    ref.close()
+    ob.close()
