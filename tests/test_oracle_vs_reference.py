@@ -545,3 +545,56 @@ def test_queries_over_wild_drawables_match_reference():
     assert hits > 0
     ref.close()
     ob.close()
+
+
+def test_wild_boxes_through_in_view_shadow_and_selection_stages():
+    """The later stages over wild boxes: CheckVisibilityWork's draw-distance / Z-range part, ProcessShadowCasters' light-space tests and
+    UpdateOccluders' size / density keys (NaN keys included) must follow the reference there as well."""
+    from urho3d_b200 import camera
+    rs = np.random.RandomState(21)
+    n = 4000
+    w, h = 128, 80
+    sc = helpers.small_scene(n=n, k=200, extent=80.0, seed=19)
+    sc.aabb[:n // 2] = np.where(rs.uniform(size=(n // 2, 1)) < 0.3, _wild_boxes(rs, n // 2, 85.0), sc.aabb[:n // 2])
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.5, rs.uniform(5.0, 120.0, size=sc.n), 0.0).astype(np.float32)
+    ref = helpers.make_ref(sc, w, h)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    # (1) in-view stage
+    for ortho in (False, True):
+        for i in range(4):
+            pos = [rs.uniform(-60, 60), rs.uniform(1, 30) if ortho else 2.0, rs.uniform(-60, 60)]
+            v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), 45.0, w / h, 0.1, 300.0,
+                                 ortho=ortho, ortho_size=rs.uniform(20, 100))
+            helpers.ref_draw_view(ref, sc, v)
+            ob.draw_scene_view(sc, v)
+            cand = tree.query(1, v.planes, ob, as_ids=False)
+            assert np.array_equal(tree.order[cand], ref.query(1))
+            want_ids, want_mm = ref.check_in_view(v.view, v.position, ortho, draw_dist)
+            got_pos, got_mm = tree.check_in_view(ob, cand, v.view, v.position, ortho, draw_dist)
+            assert np.array_equal(tree.order[got_pos], want_ids)
+            assert np.array_equal(got_mm.view(np.uint32), want_mm.view(np.uint32)), (got_mm, want_mm)
+    # (2) shadow casters
+    shadow_mask = np.full(sc.n, 0xFFFFFFFF, np.uint32)
+    shadow_dist = np.where(rs.uniform(size=sc.n) < 0.3, rs.uniform(10.0, 80.0, size=sc.n), 0.0).astype(np.float32)
+    in_view = (rs.uniform(size=sc.n) < 0.3).astype(np.uint8)
+    ids_all = np.arange(sc.n, dtype=np.int32)
+    for s in helpers.shadow_scenarios(ref, 80.0, 12):
+        want = ref.process_shadow_casters(ids_all, s["split"], s["light_type"], 0xFFFFFFFF, shadow_mask, shadow_dist, draw_dist, in_view,
+                                          s["main_view"], s["main_pos"])
+        got = oraclebind.process_shadow_casters(ids_all, sc.aabb, sc.cast_shadows, s["split"], s["light_type"], 0xFFFFFFFF, shadow_mask,
+                                                shadow_dist, draw_dist, in_view, s["main_view"], s["main_pos"])
+        assert np.array_equal(want, got), s["light_type"]
+    # (3) occluder selection keys over wild occluder boxes
+    wild = rs.uniform(size=sc.k) < 0.25
+    sc.occ_aabb[wild] = _wild_boxes(rs, sc.k, 85.0)[wild]
+    occ_dist = np.where(rs.uniform(size=sc.k) < 0.3, rs.uniform(20.0, 120.0, size=sc.k), 0.0).astype(np.float32)
+    for i in range(10):
+        v = camera.make_view([rs.uniform(-80, 80), rs.uniform(1.0, 30.0), rs.uniform(-80, 80)], rs.uniform(0, 360), rs.uniform(-30, 10), 45.0,
+                             1.0, 0.1, 300.0, ortho=bool(i % 2), ortho_size=40.0)
+        ref.set_view_raw(v)
+        for thr in (0.025, 0.0):
+            ridx, rkeys = ref.select_occluders(sc, v, thr, occ_dist)
+            oidx, okeys, _ = oraclebind.select_occluders(sc, v, thr, 1 << 30, occ_dist)
+            assert np.array_equal(ridx, oidx) and np.array_equal(rkeys.view(np.uint32), okeys.view(np.uint32)), (i, thr)
+    ref.close()
+    ob.close()
