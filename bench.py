@@ -639,8 +639,15 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
             cpu.step()  # warm-up pass (page faults of the forked workers, caches), as the --impl reference arm does
-            dt, n, nvis_cpu, _ = cpu.step()
+            dt, n, nvis_cpu, tris_cpu = cpu.step()
             line["cpu_baseline"] = {"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()}
+            # parity gate on the real workload: the sample's views through the CPU arm and through the CUDA path must agree on the
+            # totals of visible drawables and submitted occluder triangles (the per-view sequences are compared in tests/, at sizes the oracle allows)
+            n_cmp = len(cpu.views)
+            line["parity_check"] = {"views": n_cmp, "against": cpu.kind,
+                                    "visible": [int(nvis_cpu), int(counts[:n_cmp, 1].sum())],
+                                    "submitted_tris": [int(tris_cpu), int(stats[:n_cmp, 0].sum())],
+                                    "equal": bool(int(nvis_cpu) == int(counts[:n_cmp, 1].sum()) and int(tris_cpu) == int(stats[:n_cmp, 0].sum()))}
             cpu.close()
         print(json.dumps(line))
     if world > 1:
