@@ -108,3 +108,40 @@ def test_triangle_soups(gpu_ctx, kind):
         assert gob.GetNumTriangles() == ob.num_triangles(), (kind, case)
         gob.close()
         ob.close()
+
+
+@pytest.mark.parametrize("ortho", [False, True])
+def test_in_view_stage_over_wild_drawables(gpu_ctx, ortho):
+    """U3D_STAGE_INVIEW (draw distance + Z range) with inverted / enormous / infinite / NaN drawable boxes in the scene."""
+    rs = np.random.RandomState(21)
+    n = 4000
+    w, h = 128, 80
+    sc = helpers.small_scene(n=n, k=96, extent=80.0, seed=19)
+    sc.aabb[:n // 2] = np.where(rs.uniform(size=(n // 2, 1)) < 0.3, _wild_boxes(rs, n // 2, 85.0), sc.aabb[:n // 2])
+    draw_dist = np.where(rs.uniform(size=sc.n) < 0.5, rs.uniform(5.0, 120.0, size=sc.n), 0.0).astype(np.float32)
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    tree.set_draw_distances(draw_dist)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = []
+    for i in range(6):
+        pos = [rs.uniform(-60, 60), rs.uniform(1, 30) if ortho else 2.0, rs.uniform(-60, 60)]
+        views.append(camera.make_view(pos, rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), 45.0, w / h, 0.1, 300.0,
+                                      ortho=ortho, ortho_size=rs.uniform(20, 100)))
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_INVIEW)
+    zr = batch.z_ranges()
+    for i, v in enumerate(views):
+        ob.draw_scene_view(sc, v)
+        cand = otree.query(1, v.planes, ob, as_ids=False)
+        pos_in, mm = otree.check_in_view(ob, cand, v.view, v.position, ortho, draw_dist)
+        assert counts[i, 0] == len(cand)
+        assert np.array_equal(ids[offsets[i]:offsets[i + 1]], otree.order[pos_in]), "view %d" % i
+        assert np.array_equal(zr[i].view(np.uint32), mm.view(np.uint32)), (i, zr[i], mm)
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
