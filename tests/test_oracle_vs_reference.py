@@ -598,3 +598,33 @@ def test_wild_boxes_through_in_view_shadow_and_selection_stages():
             assert np.array_equal(ridx, oidx) and np.array_equal(rkeys.view(np.uint32), okeys.view(np.uint32)), (i, thr)
     ref.close()
     ob.close()
+
+
+def test_reference_threaded_mode_gives_the_same_buffer_and_sets():
+    """SURVEY 8a row a10 and hard part 7: with worker threads the reference rasterises batches into per-thread buffers and min-merges them
+    (DrawBatch on workers + MergeBuffers, OB.cpp:200-232, 1004-1026), and splits CheckVisibilityWork over the WorkQueue (View.cpp:897-920).
+    Min-compositing is order-independent, so depth plane, mips and numTriangles_ must equal the single-threaded run and the oracle bit for
+    bit -- which is why the CUDA path needs no MergeBuffers step; the visible list may come out in another order, so it is compared as a set
+    (the query result itself is produced on one thread and keeps its sequence)."""
+    w, h = 256, 160
+    sc = helpers.small_scene(n=5000, k=160, extent=90.0, seed=33)
+    ref = refbind.Ref(3)
+    assert ref.num_threads() == 3
+    ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
+    ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    ref.ob_set_size(w, h, threaded=True)
+    flat = ref.flatten()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    for v in scenes.agent_cameras(6, 90.0, w, h, seed=12) + helpers.stress_views(90.0, w, h, 6, seed=13):
+        vis, counts = helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(ob.depth(), ref.ob_depth())
+        for a, b in zip(ob.mips(), ref.ob_mips()):
+            assert np.array_equal(a, b)
+        assert ob.num_triangles() == ref.ob_num_triangles()
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        mine = tree.order[tree.check_visibility(ob, cand)]
+        assert len(mine) == len(vis) and np.array_equal(np.sort(mine), np.sort(vis))
+    ref.close()
+    ob.close()
