@@ -178,6 +178,51 @@ class CpuReference:
                    len(self.views), self.cores, "compiled reference classes (oracle/_ref)" if self.kind == "reference" else "C oracle port")
 
 
+def _engine_threads_child(conn, sc, views, threads):
+    from oracle import refbind
+    ref = refbind.Ref(threads)
+    ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
+    ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    ref.ob_set_size(WIDTH, HEIGHT, threaded=True)
+    best = None
+    for _ in range(2):  # first pass warms caches and the worker threads
+        t0 = time.perf_counter()
+        for v in views:
+            ref.set_view_raw(v)
+            ref.run_view(sc)
+        best = time.perf_counter() - t0
+    conn.send((best, ref.num_threads()))
+    conn.close()
+    os._exit(0)
+
+
+def engine_threaded_rate(sc, views, sample=128):
+    """The reference the way the engine itself runs it: one process, views one after another (Renderer.cpp:673-686), each view's
+    occluder batches rasterised into per-thread buffers and its visibility tests split over WorkQueue worker threads (cores - 1 of them, as
+    Engine.cpp:210 creates).  A forked child, so that the worker threads never live in this process.  Returns a dict or None."""
+    import multiprocessing as mp
+    from oracle import refbind
+    if not refbind.available():
+        return None
+    threads = max(1, min(os.cpu_count() or 1, 64) - 1)
+    ctx = mp.get_context("fork")
+    parent, child = ctx.Pipe(False)
+    p = ctx.Process(target=_engine_threads_child, args=(child, sc, views[:sample], threads), daemon=True)
+    p.start()
+    child.close()
+    try:
+        got = parent.recv() if parent.poll(180) else None
+    except EOFError:
+        got = None
+    if p.is_alive():
+        p.kill()
+    p.join(10)
+    if not got:
+        return None
+    return {"value": len(views[:sample]) / got[0], "unit": "views/s", "worker_threads": got[1], "views": len(views[:sample]),
+            "how": "one process, views in sequence, threaded OcclusionBuffer + WorkQueue split of the visibility tests (the engine's own mode)"}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -200,6 +245,9 @@ def run_reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     cpu.close()
+    eng = engine_threaded_rate(sc, views)
+    if eng:
+        line["cpu_baseline"]["engine_threads"] = eng
     print(json.dumps(line))
 
 
@@ -649,6 +697,9 @@ def main():
                                     "submitted_tris": [int(tris_cpu), int(stats[:n_cmp, 0].sum())],
                                     "equal": bool(int(nvis_cpu) == int(counts[:n_cmp, 1].sum()) and int(tris_cpu) == int(stats[:n_cmp, 0].sum()))}
             cpu.close()
+            eng = engine_threaded_rate(sc, views)
+            if eng:
+                line["cpu_baseline"]["engine_threads"] = eng
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
