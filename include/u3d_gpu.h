@@ -335,6 +335,12 @@ U3D_API int u3d_batch_set_pipelined(u3d_batch* b, int on);
  * With interleaved sharding (view v on rank v % world, slot v / world) view v is found at counts[v % world][v / world]. */
 typedef struct u3d_gather u3d_gather;
 #define U3D_IPC_HANDLE_BYTES 64
+/* Which rank culls which view.  The interleaved rule (view v on rank v % world) leaves the ranks several per cent apart when views differ
+ * widely in cost; this gives every rank the same number of views as that rule but equal shares of every cost column at once.
+ * costs: n_views x n_costs doubles, row-major -- per-view cost proxies, normally the previous frame's statistics (u3d_batch_read_tri_stats,
+ * u3d_batch_read_counts); non-finite or non-positive entries count as 0.  owner_out[v] = rank of view v.  Deterministic, so every rank
+ * derives the same answer from the same statistics.  Host code, no GPU needed. */
+U3D_API int u3d_balance_views(uint32_t n_views, uint32_t n_costs, const double* costs, uint32_t world, uint32_t* owner_out);
 U3D_API int u3d_gather_create(u3d_ctx* ctx, int world, int rank, uint32_t views_per_rank, uint64_t ids_capacity_per_rank, u3d_gather** out);
 U3D_API void u3d_gather_destroy(u3d_gather* g);
 /* Inter-process set-up: every rank exports a 64-byte handle of its block, the host exchanges them by any means (the Python host uses

@@ -126,6 +126,21 @@ int main()
     REQUIRE(GPUCompute::MakeZoneOccluderQuery(ids, frustum).Mode() == U3D_QUERY_ZONE_OCCLUDER);
     REQUIRE(GPUCompute::MakeOccludedFrustumQuery(ids, frustum, nullptr).Mode() == U3D_QUERY_OCCLUDED);
 
+    // multi-GPU host logic is host code as well: 10 views of very different cost over 2 ranks
+    {
+        const std::vector<double> costs = {100.0, 1.0, 1.0, 1.0, 1.0, 96.0, 1.0, 1.0, 1.0, 1.0};
+        const std::vector<unsigned> owner = GPUCompute::BalanceViews(costs, 10, 1, 2);
+        unsigned held[2] = {0, 0};
+        double load[2] = {0.0, 0.0};
+        for (unsigned i = 0; i < 10; ++i)
+        {
+            REQUIRE(owner[i] < 2);
+            ++held[owner[i]];
+            load[owner[i]] += costs[i];
+        }
+        REQUIRE(held[0] == 5 && held[1] == 5 && owner[0] != owner[5] && load[0] + load[1] == 204.0 && load[0] >= 100.0 && load[1] >= 100.0);
+    }
+
     // ---- the call-site code on the reference class ----
     const unsigned numOccluders = 24;
     std::vector<Matrix3x4> transforms;

@@ -192,3 +192,35 @@ def test_bench_rebalancing_step_under_gloo():
     assert max(summary["max_over_mean_balanced"]) < 1.01 < max(summary["max_over_mean_interleaved"])
     import json
     json.dumps(summary)
+
+
+def test_c_abi_balance_views_matches_the_python_helper():
+    """u3d_balance_views (host code in libu3dgpu.so, what a C++ engine calls) against sharding.balance_views: same quotas, every cost column
+    within 0.5 % of the mean, and -- being the same procedure -- the same assignment."""
+    from urho3d_b200 import capi
+    rng = np.random.default_rng(5)
+    n = 4096
+    base = rng.gamma(1.0, 1.0, n)
+    costs = np.stack([base * rng.uniform(0.5, 1.5, n) * 6000, rng.gamma(0.8, 12000.0, n), base * rng.uniform(0.2, 1.8, n) * 2000], axis=1)
+    costs[::97, 1] = np.nan      # garbage counts as zero on both sides
+    costs[5::131, 0] = -3.0
+    for world in (2, 3, 4, 8):
+        owner = capi.balance_views(costs, world)
+        assert owner.shape == (n,) and owner.max() == world - 1
+        assert [int((owner == r).sum()) for r in range(world)] == [len(sharding.shard_views(n, r, world)) for r in range(world)]
+        clean = np.where(np.isfinite(costs) & (costs > 0), costs, 0.0)
+        for col in range(3):
+            loads = np.array([clean[owner == r, col].sum() for r in range(world)])
+            assert loads.max() / loads.mean() < 1.005, (world, col)
+        parts = sharding.balance_views(costs, world)
+        same = all(np.array_equal(np.flatnonzero(owner == r), parts[r]) for r in range(world))
+        if not same:  # summation order may differ in the last bit; the quality may not
+            py = max(max(clean[p, col].sum() for p in parts) / (clean[:, col].sum() / world) for col in range(3))
+            c = max(max(clean[owner == r, col].sum() for r in range(world)) / (clean[:, col].sum() / world) for col in range(3))
+            assert abs(py - c) < 2e-3
+    # edge cases: no views, no information, more ranks than views, one column
+    assert capi.balance_views(np.zeros((0, 2)), 4).shape == (0,)
+    assert capi.balance_views(np.zeros((7, 2)), 2).tolist() == [0, 1, 0, 1, 0, 1, 0]
+    assert sorted(capi.balance_views(np.arange(3.0), 8).tolist()) == [0, 1, 2]
+    one = capi.balance_views(np.array([5.0, 1.0, 1.0, 1.0, 1.0, 1.0]), 2)
+    assert int((one == 0).sum()) == 3 and int((one == 1).sum()) == 3

@@ -526,6 +526,17 @@ private:
     u3d_gather* gather_{};
 };
 
+/// Which rank (GPU) culls which view: equal view counts, every per-view cost column (previous frame's submitted triangles, query sizes,
+/// visible counts ...) shared out evenly (u3d_balance_views).  costs is numViews x numCosts, row-major.  Returns the owner rank per view.
+inline std::vector<unsigned> BalanceViews(const std::vector<double>& costs, unsigned numViews, unsigned numCosts, unsigned world)
+{
+    std::vector<unsigned> owner(numViews);
+    if (costs.size() < (size_t)numViews * numCosts)
+        throw GpuError("BalanceViews: costs array too small");
+    Check(u3d_balance_views(numViews, numCosts, costs.data(), world, owner.data()), "u3d_balance_views");
+    return owner;
+}
+
 #ifdef URHO3D_API
 // ---------------------------------------------------------------------------------------------------------------------------------
 // In-engine helpers (compiled only inside the engine, i.e. after the reference's own headers: Camera.h, Frustum.h, BoundingBox.h).

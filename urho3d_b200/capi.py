@@ -120,6 +120,7 @@ SIGNATURES = {
     "u3d_batch_process_shadow_casters": (C.c_int, [_vp, _vp, C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int, C.POINTER(C.c_uint8), C.c_uint32, _vp]),
     "u3d_scene_raycast": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.POINTER(C.c_uint32), _vp, _vp]),
     "u3d_sort_by_key": (C.c_int, [C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint32)]),
+    "u3d_balance_views": (C.c_int, [C.c_uint32, C.c_uint32, C.POINTER(C.c_double), C.c_uint32, C.POINTER(C.c_uint32)]),
     "u3d_batch_set_occluder_policy": (C.c_int, [_vp, C.c_int, C.c_float, C.c_uint32, C.POINTER(C.c_float), _vp]),
     "u3d_occluders_set_draw_distances": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
     "u3d_batch_read_active_occluders": (C.c_int, [_vp, C.POINTER(C.c_uint32), _vp]),
@@ -168,6 +169,16 @@ def sort_by_key(keys, values):
     v = np.ascontiguousarray(values, np.uint32).copy()
     _chk(lib().u3d_sort_by_key(len(k), _p(k, _f), _p(v, _u32)))
     return k, v
+
+
+def balance_views(costs, world):
+    """u3d_balance_views: per-view cost columns [n] or [n, D] -> owner rank of every view (uint32 [n]); host code."""
+    c = np.ascontiguousarray(costs, np.float64)
+    if c.ndim == 1:
+        c = c[:, None]
+    owner = np.zeros(c.shape[0], np.uint32)
+    _chk(lib().u3d_balance_views(c.shape[0], c.shape[1], c.ctypes.data_as(C.POINTER(C.c_double)), world, _p(owner, _u32)))
+    return owner
 
 
 def debug_set_option(name, value):

@@ -1560,6 +1560,121 @@ int u3d_sort_by_key(uint32_t n, float* keys, uint32_t* values)
     return U3D_OK;
 }
 
+// Multi-GPU host logic: cost-balanced assignment of views to ranks.  Same procedure as urho3d_b200/sharding.py:balance_views:
+// columns normalised to sum 1, views taken in decreasing order of their normalised total and given to the rank whose worst column stays
+// lowest among the ranks with room left (every rank keeps the view count of the interleaved rule), then a few swaps between the rank holding
+// the worst column and the rank lightest in that column.
+int u3d_balance_views(uint32_t n_views, uint32_t n_costs, const double* costs, uint32_t world, uint32_t* owner_out)
+{
+    if (!world || (n_views && (!owner_out || (n_costs && !costs))))
+        return fail(U3D_ERR_INVALID, "u3d_balance_views: NULL argument or zero ranks");
+    const size_t n = n_views, D0 = n_costs, W = world;
+    std::vector<double> tot(D0, 0.0);
+    auto sane = [](double v) { return std::isfinite(v) && v > 0.0 ? v : 0.0; };
+    for (size_t v = 0; v < n; ++v)
+        for (size_t c = 0; c < D0; ++c)
+            tot[c] += sane(costs[v * D0 + c]);
+    std::vector<size_t> cols;
+    for (size_t c = 0; c < D0; ++c)
+        if (tot[c] > 0.0)
+            cols.push_back(c);
+    const size_t D = cols.size();
+    if (!D)
+    {
+        for (size_t v = 0; v < n; ++v)
+            owner_out[v] = (uint32_t)(v % W); // no information: the interleaved rule
+        return U3D_OK;
+    }
+    std::vector<double> c(n * D), key(n, 0.0);
+    for (size_t v = 0; v < n; ++v)
+        for (size_t k = 0; k < D; ++k)
+        {
+            c[v * D + k] = sane(costs[v * D0 + cols[k]]) / tot[cols[k]];
+            key[v] += c[v * D + k];
+        }
+    std::vector<uint32_t> order(n);
+    for (size_t v = 0; v < n; ++v)
+        order[v] = (uint32_t)v;
+    std::stable_sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) { return key[a] > key[b]; });
+    std::vector<size_t> quota(W), held(W, 0);
+    for (size_t r = 0; r < W; ++r)
+        quota[r] = n / W + (r < n % W ? 1 : 0); // len(range(r, n, W))
+    std::vector<double> load(W * D, 0.0);
+    auto worst_of = [&](size_t r) { return *std::max_element(load.begin() + r * D, load.begin() + (r + 1) * D); };
+    for (uint32_t v : order)
+    {
+        size_t best = W;
+        double bestWorst = 0.0;
+        for (size_t r = 0; r < W; ++r)
+        {
+            if (held[r] >= quota[r])
+                continue;
+            double w = 0.0;
+            for (size_t k = 0; k < D; ++k)
+                w = std::max(w, load[r * D + k] + c[(size_t)v * D + k]);
+            if (best == W || w < bestWorst)
+            {
+                best = r;
+                bestWorst = w;
+            }
+        }
+        owner_out[v] = (uint32_t)best;
+        ++held[best];
+        for (size_t k = 0; k < D; ++k)
+            load[best * D + k] += c[(size_t)v * D + k];
+    }
+    for (size_t it = 0; it < 4 * W; ++it)
+    {
+        const size_t top = (size_t)(std::max_element(load.begin(), load.end()) - load.begin());
+        const size_t a = top / D, d = top % D;
+        size_t b = 0;
+        for (size_t r = 1; r < W; ++r)
+            if (load[r * D + d] < load[b * D + d])
+                b = r;
+        if (a == b)
+            break;
+        std::vector<uint32_t> ia, ib;
+        for (size_t v = 0; v < n; ++v)
+            if (owner_out[v] == a)
+                ia.push_back((uint32_t)v);
+            else if (owner_out[v] == b)
+                ib.push_back((uint32_t)v);
+        if (ia.empty() || ib.empty())
+            break;
+        const size_t sa = std::max<size_t>(1, ia.size() / 512), sb = std::max<size_t>(1, ib.size() / 512); // a bounded number of candidate pairs
+        const double before = std::max(worst_of(a), worst_of(b));
+        double bestAfter = before;
+        long bi = -1, bj = -1;
+        for (size_t i = 0; i < ia.size(); i += sa)
+            for (size_t j = 0; j < ib.size(); j += sb)
+            {
+                double after = 0.0;
+                for (size_t k = 0; k < D; ++k)
+                {
+                    const double delta = c[(size_t)ib[j] * D + k] - c[(size_t)ia[i] * D + k]; // what rank a gains by trading view i for view j
+                    after = std::max(after, std::max(load[a * D + k] + delta, load[b * D + k] - delta));
+                }
+                if (after < bestAfter)
+                {
+                    bestAfter = after;
+                    bi = (long)i;
+                    bj = (long)j;
+                }
+            }
+        if (bi < 0 || bestAfter >= before * (1.0 - 1e-12))
+            break;
+        for (size_t k = 0; k < D; ++k)
+        {
+            const double delta = c[(size_t)ib[bj] * D + k] - c[(size_t)ia[bi] * D + k];
+            load[a * D + k] += delta;
+            load[b * D + k] -= delta;
+        }
+        owner_out[ia[bi]] = (uint32_t)b;
+        owner_out[ib[bj]] = (uint32_t)a;
+    }
+    return U3D_OK;
+}
+
 int u3d_scene_raycast(u3d_scene* s, uint32_t n_rays, const float* rays7, uint32_t drawable_flags, uint32_t view_mask, int single, uint32_t capacity,
     uint32_t* counts, u3d_ray_hit* hits, void* stream)
 {
