@@ -223,6 +223,20 @@ def engine_threaded_rate(sc, views, sample=128):
             "how": "one process, views in sequence, threaded OcclusionBuffer + WorkQueue split of the visibility tests (the engine's own mode)"}
 
 
+def host_description():
+    """nproc and CPU model of the box the CPU arm runs on (SURVEY 8d asks for both next to the reference's number)."""
+    model = "unknown"
+    try:
+        with open("/proc/cpuinfo") as f:
+            for ln in f:
+                if ln.lower().startswith("model name"):
+                    model = ln.split(":", 1)[1].strip()
+                    break
+    except OSError:
+        pass
+    return {"nproc": os.cpu_count(), "cpu_model": model}
+
+
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
@@ -242,7 +256,7 @@ def run_reference_arm(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": "views/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32",
             "data": "synthetic", "config": config_dict(args, world), "occluder_mtri_per_s": tris / total / 1e6,
-            "cpu_baseline": {"value": value, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
+            "cpu_baseline": dict({"value": value, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()}, **host_description()),
             "e2e": {"value": value, "unit": "views/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     cpu.close()
     eng = engine_threaded_rate(sc, views)
@@ -668,6 +682,9 @@ def main():
                 "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32+i32",
                 "data": "synthetic", "config": config_dict(args, world),
                 "occluder_mtri_per_s": sub_tris * args.steps / (total_ms * 1e-3) / 1e6,
+                # SURVEY 8d's definition: submitted triangles / time of the draw + hierarchy phases alone (rank 0's shard, phase timers)
+                "occluder_mtri_per_s_raster_phases": float(stats[:, 0].sum()) / max(1e-9, 1e-3 * sum(
+                    phase_ms.get(k, 0.0) for k in ("clear", "select", "scan", "setup", "fill", "hierarchy"))) / 1e6,
                 "per_view": {"submitted_tris": tri_per_view, "query_result": n_cand / args.views, "visible": vis_per_view, "octants": M},
                 "e2e": {"value": args.views * args.steps / e2e_s, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": launches,
@@ -688,7 +705,8 @@ def main():
             cpu = CpuReference(sc, views, min(args.cpu_sample, args.views))
             cpu.step()  # warm-up pass (page faults of the forked workers, caches), as the --impl reference arm does
             dt, n, nvis_cpu, tris_cpu = cpu.step()
-            line["cpu_baseline"] = {"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()}
+            line["cpu_baseline"] = dict({"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
+                                        **host_description())
             # parity gate on the real workload: the sample's views through the CPU arm and through the CUDA path must agree on the
             # totals of visible drawables and submitted occluder triangles (the per-view sequences are compared in tests/, at sizes the oracle allows)
             n_cmp = len(cpu.views)
