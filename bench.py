@@ -211,7 +211,7 @@ def engine_threaded_rate(sc, views, sample=128):
     p.start()
     child.close()
     try:
-        got = parent.recv() if parent.poll(180) else None
+        got = parent.recv() if parent.poll(60) else None
     except EOFError:
         got = None
     if p.is_alive():
