@@ -19,6 +19,7 @@
 #include <Urho3D/Scene/Scene.h>
 
 #include "../../urho3d_b200/GPUCompute/GPUCompute.h"
+#include "../../urho3d_b200/GPUCompute/GpuOcclusionBufferObject.h"
 
 #include <cstdio>
 #include <cstdlib>
@@ -73,10 +74,43 @@ template <class Buffer> void Answers(Buffer* buffer, const BoundingBox* boxes, u
         out[i] = buffer->IsVisible(boxes[i]) ? 1 : 0;
 }
 
+// Compile-time proof that GpuOcclusionBufferObject has OcclusionBuffer's public member signatures (OcclusionBuffer.h:101-158): taking the address
+// of an (overloaded) member with a static_cast to the exact pointer-to-member type only compiles when such a member exists.
+#define SAME_MEMBER(ret, name, args, cv)                                                            \
+    (void)static_cast<ret(OcclusionBuffer::*) args cv>(&OcclusionBuffer::name);                     \
+    (void)static_cast<ret(GpuOcclusionBufferObject::*) args cv>(&GpuOcclusionBufferObject::name)
+
+void SignatureParity()
+{
+    SAME_MEMBER(bool, SetSize, (int, int, bool), );
+    SAME_MEMBER(void, SetView, (Camera*), );
+    SAME_MEMBER(void, SetMaxTriangles, (unsigned), );
+    SAME_MEMBER(void, SetCullMode, (CullMode), );
+    SAME_MEMBER(void, Reset, (), );
+    SAME_MEMBER(void, Clear, (), );
+    SAME_MEMBER(bool, AddTriangles, (const Matrix3x4&, const void*, unsigned, unsigned, unsigned), );
+    SAME_MEMBER(bool, AddTriangles, (const Matrix3x4&, const void*, unsigned, const void*, unsigned, unsigned, unsigned), );
+    SAME_MEMBER(void, DrawTriangles, (), );
+    SAME_MEMBER(void, BuildDepthHierarchy, (), );
+    SAME_MEMBER(void, ResetUseTimer, (), );
+    SAME_MEMBER(int*, GetBuffer, (), const);
+    SAME_MEMBER(const Matrix3x4&, GetView, (), const);
+    SAME_MEMBER(const Matrix4&, GetProjection, (), const);
+    SAME_MEMBER(int, GetWidth, (), const);
+    SAME_MEMBER(int, GetHeight, (), const);
+    SAME_MEMBER(unsigned, GetNumTriangles, (), const);
+    SAME_MEMBER(unsigned, GetMaxTriangles, (), const);
+    SAME_MEMBER(CullMode, GetCullMode, (), const);
+    SAME_MEMBER(bool, IsThreaded, (), const);
+    SAME_MEMBER(bool, IsVisible, (const BoundingBox&), const);
+    SAME_MEMBER(unsigned, GetUseTimer, (), );
+}
+
 } // namespace
 
 int main()
 {
+    SignatureParity();
     SharedPtr<Context> context(new Context());
     context->RegisterSubsystem(new WorkQueue(context));
     RegisterSceneLibrary(context);
@@ -179,6 +213,15 @@ int main()
         REQUIRE(gpuDepth && std::memcmp(gpuDepth, reference->GetBuffer(), sizeof(int) * (size_t)reference->GetWidth() * reference->GetHeight()) == 0);
         std::vector<unsigned char> gpuAnswers;
         Answers(&buffer, boxes.data(), (unsigned)boxes.size(), gpuAnswers);
+        REQUIRE(gpuAnswers == referenceAnswers);
+        // the Object wrapper Renderer's pool would hold: same template, same answers
+        SharedPtr<GpuOcclusionBufferObject> pooled(new GpuOcclusionBufferObject(context, gpu));
+        REQUIRE(pooled->SetSize(256, 160, true) && pooled->IsThreaded());
+        REQUIRE(DrawOccluders(pooled.Get(), camera, transforms.data(), numOccluders, 250) == referenceBudget);
+        REQUIRE(pooled->GetNumTriangles() == reference->GetNumTriangles() && pooled->GetMaxTriangles() == 250 && pooled->GetCullMode() == CULL_NONE);
+        REQUIRE(pooled->GetView().Equals(reference->GetView()) && pooled->GetProjection().Equals(reference->GetProjection()));
+        REQUIRE(std::memcmp(pooled->GetBuffer(), reference->GetBuffer(), sizeof(int) * (size_t)reference->GetWidth() * reference->GetHeight()) == 0);
+        Answers(pooled.Get(), boxes.data(), (unsigned)boxes.size(), gpuAnswers);
         REQUIRE(gpuAnswers == referenceAnswers);
         std::printf("device path compared with the reference OcclusionBuffer in-process: %u triangles, %u of %u boxes visible\n",
             buffer.GetNumTriangles(), visible, (unsigned)boxes.size());
