@@ -20,6 +20,8 @@
 
 #include "../../urho3d_b200/GPUCompute/GPUCompute.h"
 #include "../../urho3d_b200/GPUCompute/GpuOcclusionBufferObject.h"
+#include "../../urho3d_b200/GPUCompute/GpuOctreeMirror.h"
+#include <Urho3D/Graphics/Octree.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -44,6 +46,72 @@ namespace
 const float kBoxVertices[8 * 3] = {-0.5f, -0.5f, -0.5f, 0.5f, -0.5f, -0.5f, 0.5f, 0.5f, -0.5f, -0.5f, 0.5f, -0.5f,
     -0.5f, -0.5f, 0.5f, 0.5f, -0.5f, 0.5f, 0.5f, 0.5f, 0.5f, -0.5f, 0.5f, 0.5f};
 const unsigned short kBoxIndices[36] = {0, 2, 1, 0, 3, 2, 4, 5, 6, 4, 6, 7, 0, 1, 5, 0, 5, 4, 3, 6, 2, 3, 7, 6, 0, 4, 7, 0, 7, 3, 1, 2, 6, 1, 6, 5};
+
+/// A Drawable whose world box is handed in (no Model / GL needed); inserted into the real Octree by Node::AddComponent -> AddToOctree.
+class BoxDrawable : public Drawable
+{
+    URHO3D_OBJECT(BoxDrawable, Drawable);
+
+public:
+    explicit BoxDrawable(Context* context) : Drawable(context, DRAWABLE_GEOMETRY) {}
+    void Setup(const BoundingBox& worldBox, unsigned char flags, unsigned viewMask, bool occludee, bool castShadows)
+    {
+        fixedWorldBox_ = worldBox;
+        drawableFlags_ = flags;
+        viewMask_ = viewMask;
+        occludee_ = occludee;
+        castShadows_ = castShadows;
+        worldBoundingBoxDirty_ = true;
+    }
+    void OnWorldBoundingBoxUpdate() override { worldBoundingBox_ = fixedWorldBox_; }
+    BoundingBox fixedWorldBox_;
+};
+
+/// OccludedFrustumOctreeQuery and ShadowCasterOctreeQuery are file-local in View.cpp (116-158, 59-84): restated on the real base class so that
+/// the real Octree can run them.
+class OccludedQuery : public FrustumOctreeQuery
+{
+public:
+    OccludedQuery(PODVector<Drawable*>& result, const Frustum& frustum, OcclusionBuffer* buffer, unsigned char flags, unsigned mask) :
+        FrustumOctreeQuery(result, frustum, flags, mask), buffer_(buffer) {}
+    Intersection TestOctant(const BoundingBox& box, bool inside) override
+    {
+        if (inside)
+            return buffer_->IsVisible(box) ? INSIDE : OUTSIDE;
+        Intersection result = frustum_.IsInside(box);
+        if (result != OUTSIDE && !buffer_->IsVisible(box))
+            result = OUTSIDE;
+        return result;
+    }
+    OcclusionBuffer* buffer_;
+};
+
+class ShadowCasterQuery : public FrustumOctreeQuery
+{
+public:
+    ShadowCasterQuery(PODVector<Drawable*>& result, const Frustum& frustum, unsigned char flags, unsigned mask) :
+        FrustumOctreeQuery(result, frustum, flags, mask) {}
+    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
+    {
+        while (start != end)
+        {
+            Drawable* drawable = *start++;
+            if (drawable->GetCastShadows() && (drawable->GetDrawableFlags() & drawableFlags_) && (drawable->GetViewMask() & viewMask_) &&
+                (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox())))
+                result_.Push(drawable);
+        }
+    }
+};
+
+bool SameSequence(const PODVector<Drawable*>& a, const PODVector<Drawable*>& b)
+{
+    if (a.Size() != b.Size())
+        return false;
+    for (unsigned i = 0; i < a.Size(); ++i)
+        if (a[i] != b[i])
+            return false;
+    return true;
+}
 
 /// The call-site code, generic in the buffer class: what View::DrawOccluders (threaded branch) and the occluders' DrawOcclusion do.
 template <class Buffer> bool DrawOccluders(Buffer* buffer, Camera* camera, const Matrix3x4* worldTransforms, unsigned numOccluders, unsigned maxTriangles)
@@ -197,6 +265,42 @@ int main()
     std::printf("reference: %u triangles, %u of %u boxes visible\n", reference->GetNumTriangles(), visible, (unsigned)boxes.size());
     REQUIRE(visible > 10 && visible < boxes.size() - 10); // the scene exercises both answers
 
+    // ---- the real Octree with real Drawables: the lists Octree::GetDrawables gives for the query classes of View.cpp ----
+    Octree::RegisterObject(context);
+    SharedPtr<Scene> scene(new Scene(context));
+    Octree* octree = scene->CreateComponent<Octree>();
+    PODVector<Drawable*> sceneDrawables;
+    unsigned seed = 12345u;
+    auto rnd = [&seed]() { seed = seed * 1664525u + 1013904223u; return (float)(seed >> 8) / 16777216.0f; };
+    for (unsigned i = 0; i < 1500; ++i)
+    {
+        const Vector3 c(-70.0f + 140.0f * rnd(), 0.5f + 3.0f * rnd(), -30.0f + 140.0f * rnd());
+        const Vector3 e(0.3f + 1.5f * rnd(), 0.3f + 1.5f * rnd(), 0.3f + 1.5f * rnd());
+        BoxDrawable* d = new BoxDrawable(context);
+        d->Setup(BoundingBox(c - e, c + e), i % 11 == 0 ? DRAWABLE_LIGHT : DRAWABLE_GEOMETRY, i % 7 == 0 ? 0x2u : DEFAULT_VIEWMASK, i % 50 != 0, i % 2 == 0);
+        scene->CreateChild(String::EMPTY, LOCAL)->AddComponent(d, 0, LOCAL); // -> Octree::InsertDrawable
+        sceneDrawables.Push(d);
+    }
+    PODVector<Drawable*> wantFrustum[2], wantShadow[2], wantOccluded[2], wantVisible[2];
+    for (unsigned pass = 0; pass < 2; ++pass)
+    {
+        const unsigned char flags = pass ? (unsigned char)DRAWABLE_GEOMETRY : (unsigned char)DRAWABLE_ANY;
+        const unsigned mask = pass ? 0x1u : DEFAULT_VIEWMASK;
+        FrustumOctreeQuery frustumQuery(wantFrustum[pass], frustum, flags, mask);
+        octree->GetDrawables(frustumQuery);
+        ShadowCasterQuery shadowQuery(wantShadow[pass], frustum, flags, mask);
+        octree->GetDrawables(shadowQuery);
+        OccludedQuery occludedQuery(wantOccluded[pass], frustum, reference.Get(), flags, mask);
+        octree->GetDrawables(occludedQuery);
+        for (unsigned i = 0; i < wantOccluded[pass].Size(); ++i) // CheckVisibilityWork's predicate over the query result (View.cpp:177)
+            if (!wantOccluded[pass][i]->IsOccludee() || reference->IsVisible(wantOccluded[pass][i]->GetWorldBoundingBox()))
+                wantVisible[pass].Push(wantOccluded[pass][i]);
+        std::printf("real Octree, pass %u: frustum %u, shadow casters %u, occluded query %u, visible %u\n", pass, wantFrustum[pass].Size(),
+            wantShadow[pass].Size(), wantOccluded[pass].Size(), wantVisible[pass].Size());
+        REQUIRE(wantFrustum[pass].Size() > 20 && wantShadow[pass].Size() > 10 && wantOccluded[pass].Size() > 10);
+        REQUIRE(wantOccluded[pass].Size() < wantFrustum[pass].Size() && wantVisible[pass].Size() < wantOccluded[pass].Size());
+    }
+
     // ---- the GPU class: loud failure without a device, bit parity with one ----
     try
     {
@@ -223,6 +327,27 @@ int main()
         REQUIRE(std::memcmp(pooled->GetBuffer(), reference->GetBuffer(), sizeof(int) * (size_t)reference->GetWidth() * reference->GetHeight()) == 0);
         Answers(pooled.Get(), boxes.data(), (unsigned)boxes.size(), gpuAnswers);
         REQUIRE(gpuAnswers == referenceAnswers);
+        // ---- Octree::GetDrawables: the mirror against the lists the real Octree gave above, as PODVector<Drawable*> in sequence ----
+        GpuOctreeMirror mirror(gpu, BoundingBox(-1000.0f, 1000.0f), 8); // Octree's defaults, Octree.cpp:46-47
+        for (unsigned i = 0; i < sceneDrawables.Size(); ++i)
+            mirror.InsertDrawable(sceneDrawables[i]);
+        PODVector<Drawable*> got;
+        unsigned compared = 0;
+        for (unsigned pass = 0; pass < 2; ++pass)
+        {
+            const unsigned char flags = pass ? (unsigned char)DRAWABLE_GEOMETRY : (unsigned char)DRAWABLE_ANY;
+            const unsigned mask = pass ? 0x1u : DEFAULT_VIEWMASK;
+            mirror.GetDrawables(got, frustum, flags, mask);
+            REQUIRE(SameSequence(wantFrustum[pass], got));
+            mirror.GetShadowCasters(got, frustum, flags, mask);
+            REQUIRE(SameSequence(wantShadow[pass], got));
+            mirror.GetDrawables(got, frustum, pooled.Get(), flags, mask);
+            REQUIRE(SameSequence(wantOccluded[pass], got));
+            mirror.GetVisibleDrawables(got, frustum, pooled.Get(), flags, mask);
+            REQUIRE(SameSequence(wantVisible[pass], got));
+            compared += wantFrustum[pass].Size() + wantShadow[pass].Size() + wantOccluded[pass].Size() + wantVisible[pass].Size();
+        }
+        std::printf("Octree::GetDrawables compared with the GPU mirror in-process: %u drawables over the query classes\n", compared);
         std::printf("device path compared with the reference OcclusionBuffer in-process: %u triangles, %u of %u boxes visible\n",
             buffer.GetNumTriangles(), visible, (unsigned)boxes.size());
     }

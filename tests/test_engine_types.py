@@ -21,7 +21,8 @@ def build():
     subprocess.check_call(["bash", os.path.join(ROOT, "oracle", "build_ref.sh")])
     if os.path.exists(EXE) and os.path.getmtime(EXE) >= max(os.path.getmtime(p) for p in (
             SRC, os.path.join(ROOT, "urho3d_b200", "GPUCompute", "GPUCompute.h"),
-            os.path.join(ROOT, "urho3d_b200", "GPUCompute", "GpuOcclusionBufferObject.h"), os.path.join(ROOT, "include", "u3d_gpu.h"),
+            os.path.join(ROOT, "urho3d_b200", "GPUCompute", "GpuOcclusionBufferObject.h"),
+            os.path.join(ROOT, "urho3d_b200", "GPUCompute", "GpuOctreeMirror.h"), os.path.join(ROOT, "include", "u3d_gpu.h"),
             os.path.join(REFLIB, "libu3dref.so"))):
         return True
     src, tp, stub = os.path.join(REF, "Source", "Urho3D"), os.path.join(REF, "Source", "ThirdParty"), os.path.join(ROOT, "oracle", "ref_stub")
