@@ -39,7 +39,7 @@ def run(expect_device):
     env = dict(os.environ)
     if expect_device:
         env["U3D_EXPECT_DEVICE"] = "1"
-    out = subprocess.run([EXE], capture_output=True, text=True, timeout=300, env=env)
+    out = subprocess.run([EXE], capture_output=True, text=True, timeout=120, env=env)
     print(out.stdout[-2000:], out.stderr[-2000:])
     return out
 
