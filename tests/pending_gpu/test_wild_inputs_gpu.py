@@ -145,3 +145,39 @@ def test_in_view_stage_over_wild_drawables(gpu_ctx, ortho):
     for o in (batch, occ, mesh, gs, tree):
         o.close()
     ob.close()
+
+
+def test_huge_object_count_sample_layout(gpu_ctx):
+    """Sample 20_HugeObjectCount's scene shape (62.5k boxes on a 0.3-unit grid: hundreds of drawables per leaf octant), batched path."""
+    g = np.arange(-125, 125, dtype=np.float32) * np.float32(0.3)
+    cx, cz = np.meshgrid(g, g, indexing="xy")
+    c = np.stack([cx.ravel(), np.zeros(cx.size, np.float32), cz.ravel()], axis=1).astype(np.float32)
+    half = np.float32(0.125)
+    sc = helpers.small_scene(n=c.shape[0], k=48, extent=30.0, seed=3)
+    sc.aabb[:] = np.concatenate([c - half, c + half], axis=1)
+    w, h = 256, 160
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = [camera.make_view([0.0, 10.0, -100.0], 0.0, 5.0, 45.0, w / h, 0.1, 300.0),
+             camera.make_view([0.0, 1.0, 0.0], 30.0, 0.0, 45.0, w / h, 0.1, 300.0),
+             camera.make_view([-30.0, 40.0, -30.0], 45.0, 50.0, 60.0, w / h, 0.1, 300.0),
+             camera.make_view([36.0, 0.2, 36.0], 225.0, 0.0, 45.0, w / h, 0.1, 80.0)] + helpers.stress_views(30.0, w, h, 3, seed=9)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    counts, offsets, ids = batch.cull_views(capi.pack_views(views), capi.STAGE_VISIBLE)
+    for i, v in enumerate(views):
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(batch.depth(i), ob.depth())
+        cand = otree.query(1, v.planes, ob, as_ids=False)
+        vis = otree.order[otree.check_visibility(ob, cand)]
+        assert counts[i, 0] == len(cand) and np.array_equal(ids[offsets[i]:offsets[i + 1]], vis)
+        for mode in (0, 2):
+            got, qc = gs.query(v.planes, None, 0xFF, 0xFFFFFFFF, mode, capi.STAGE_QUERY)
+            assert np.array_equal(got, otree.query(mode, v.planes, None))
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()

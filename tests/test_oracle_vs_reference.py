@@ -633,3 +633,44 @@ def test_reference_threaded_mode_gives_the_same_buffer_and_sets():
         assert len(mine) == len(vis) and np.array_equal(np.sort(mine), np.sort(vis))
     ref.close()
     ob.close()
+
+
+def test_huge_object_count_sample_layout():
+    """The scene shape of the reference's sample 20_HugeObjectCount (Source/Samples/20_HugeObjectCount/HugeObjectCount.cpp: 250 x 250 boxes of
+    0.25 units on a 0.3-unit grid, the one place the reference itself stresses a 62.5k-drawable octree): hundreds of drawables per
+    leaf octant instead of the benchmark's ~60.  Octree structure, all query classes and the visibility predicate, oracle vs reference."""
+    from urho3d_b200 import camera
+    g = np.arange(-125, 125, dtype=np.float32) * np.float32(0.3)
+    cx, cz = np.meshgrid(g, g, indexing="xy")
+    c = np.stack([cx.ravel(), np.zeros(cx.size, np.float32), cz.ravel()], axis=1).astype(np.float32)
+    half = np.float32(0.125)
+    sc = helpers.small_scene(n=c.shape[0], k=48, extent=30.0, seed=3)
+    sc.aabb[:] = np.concatenate([c - half, c + half], axis=1)
+    assert sc.n == 62500
+    w, h = 256, 160
+    ref = helpers.make_ref(sc, w, h)
+    flat = ref.flatten()
+    t, mine = helpers.host_flatten(sc)
+    for key in ("parent", "level", "first", "count", "order", "box"):
+        assert np.array_equal(mine[key], flat[key]), key
+    assert flat["count"].max() > 300                      # many drawables per octant
+    t.close()
+    tree, ob = helpers.make_oracle(sc, flat, w, h)
+    views = [camera.make_view([0.0, 10.0, -100.0], 0.0, 5.0, 45.0, w / h, 0.1, 300.0),     # the sample's start camera, roughly
+             camera.make_view([0.0, 1.0, 0.0], 30.0, 0.0, 45.0, w / h, 0.1, 300.0),        # inside the field
+             camera.make_view([-30.0, 40.0, -30.0], 45.0, 50.0, 60.0, w / h, 0.1, 300.0),  # looking down on it
+             camera.make_view([36.0, 0.2, 36.0], 225.0, 0.0, 45.0, w / h, 0.1, 80.0)] + helpers.stress_views(30.0, w, h, 3, seed=9)
+    total = 0
+    for v in views:
+        vis, counts = helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(ob.depth(), ref.ob_depth())
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+        assert np.array_equal(tree.query(0, v.planes, None), ref.query(0))
+        assert np.array_equal(tree.query(2, v.planes, None), ref.query(2))
+        total += len(vis)
+    assert total > 20000
+    ref.close()
+    ob.close()
