@@ -605,33 +605,66 @@ def test_wild_boxes_through_in_view_shadow_and_selection_stages():
     ob.close()
 
 
-def test_reference_threaded_mode_gives_the_same_buffer_and_sets():
-    """SURVEY 8a row a10 and hard part 7: with worker threads the reference rasterises batches into per-thread buffers and min-merges them
-    (DrawBatch on workers + MergeBuffers, OB.cpp:200-232, 1004-1026), and splits CheckVisibilityWork over the WorkQueue (View.cpp:897-920).
-    Min-compositing is order-independent, so depth plane, mips and numTriangles_ must equal the single-threaded run and the oracle bit for
-    bit -- which is why the CUDA path needs no MergeBuffers step; the visible list may come out in another order, so it is compared as a set
-    (the query result itself is produced on one thread and keeps its sequence)."""
-    w, h = 256, 160
-    sc = helpers.small_scene(n=5000, k=160, extent=90.0, seed=33)
+def _threaded_reference_child(conn, sc, views, w, h):
+    import faulthandler
+    import os
+    faulthandler.disable()
     ref = refbind.Ref(3)
-    assert ref.num_threads() == 3
     ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
     ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
     ref.ob_set_size(w, h, threaded=True)
-    flat = ref.flatten()
-    tree, ob = helpers.make_oracle(sc, flat, w, h)
-    for v in scenes.agent_cameras(6, 90.0, w, h, seed=12) + helpers.stress_views(90.0, w, h, 6, seed=13):
+    out = [ref.num_threads(), ref.flatten()]
+    for v in views:
         vis, counts = helpers.ref_draw_view(ref, sc, v)
+        out.append((ref.ob_depth(), ref.ob_mips(), ref.ob_num_triangles(), ref.query(1), vis))
+    conn.send(out)
+    conn.close()
+    os._exit(0)   # no teardown of the worker threads in a forked child
+
+
+def test_reference_threaded_mode_gives_the_same_buffer_and_sets():
+    """SURVEY 8a row a10 and hard part 7: with worker threads the reference rasterises batches into per-thread buffers and min-merges them
+    (DrawBatch on workers + MergeBuffers, OB.cpp:200-232, 1004-1026), and splits CheckVisibilityWork over the WorkQueue (View.cpp:897-920).
+    Min-compositing is order-independent, so depth plane and mips must equal the single-threaded run and the oracle bit for bit -- which is
+    why the CUDA path needs no MergeBuffers step; the visible list may come out in another order, so it is compared as a set (the query
+    result itself is produced on one thread and keeps its sequence).  numTriangles_ is NOT compared for equality: the workers increment it
+    without synchronisation (`++numTriangles_` in DrawTriangle, OB.cpp:681-682, reached from DrawBatch on every worker), so the threaded
+    reference loses updates under load (observed: 1333 and 1343 against the true 1368); it can only fall short.
+    The threaded reference runs in a forked child so that its worker threads never live in the test process."""
+    import multiprocessing as mp
+    w, h = 256, 160
+    sc = helpers.small_scene(n=5000, k=160, extent=90.0, seed=33)
+    views = scenes.agent_cameras(6, 90.0, w, h, seed=12) + helpers.stress_views(90.0, w, h, 6, seed=13)
+    ctx = mp.get_context("fork")
+    got = None
+    for attempt in range(2):
+        parent, child = ctx.Pipe(False)
+        p = ctx.Process(target=_threaded_reference_child, args=(child, sc, views, w, h), daemon=True)
+        p.start()
+        child.close()
+        try:
+            got = parent.recv() if parent.poll(60) else None
+        except EOFError:
+            got = None
+        if p.is_alive():
+            p.kill()
+        p.join(10)
+        if got is not None:
+            break
+    if got is None:
+        pytest.skip("the reference in threaded mode did not answer twice (its worker threads are forked into a busy test process)")
+    assert got[0] == 3
+    tree, ob = helpers.make_oracle(sc, got[1], w, h)
+    for v, (depth, mips, ntris, query, vis) in zip(views, got[2:]):
         ob.draw_scene_view(sc, v)
-        assert np.array_equal(ob.depth(), ref.ob_depth())
-        for a, b in zip(ob.mips(), ref.ob_mips()):
+        assert np.array_equal(ob.depth(), depth)
+        for a, b in zip(ob.mips(), mips):
             assert np.array_equal(a, b)
-        assert ob.num_triangles() == ref.ob_num_triangles()
+        assert ntris <= ob.num_triangles(), (ntris, ob.num_triangles())
         cand = tree.query(1, v.planes, ob, as_ids=False)
-        assert np.array_equal(tree.order[cand], ref.query(1))
+        assert np.array_equal(tree.order[cand], query)
         mine = tree.order[tree.check_visibility(ob, cand)]
         assert len(mine) == len(vis) and np.array_equal(np.sort(mine), np.sort(vis))
-    ref.close()
     ob.close()
 
 
