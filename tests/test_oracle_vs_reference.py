@@ -707,3 +707,62 @@ def test_huge_object_count_sample_layout():
     assert total > 20000
     ref.close()
     ob.close()
+
+
+def test_config5_and_config2_shapes_match_reference():
+    """BASELINE config 5 (one 250k-triangle u32-indexed city mesh, 12-byte stride, 2048x2048 buffer, 8 hierarchy levels) and config 2
+    (1024x576, 7 levels, 4k box occluders) at the oracle level: depth plane, every mip, numTriangles_, occluded query and visible set
+    against the compiled reference -- the sizes the GPU suite checks against the oracle (test_config5_city_mesh_2048, test_batched_views)."""
+    from urho3d_b200 import camera
+    # config 5
+    w = h = 2048
+    vtx, idx = scenes.city_mesh(250_000, 500.0)
+    sc = scenes.Scene(100_000, 4, 500.0, seed=55)
+    ref = helpers.make_ref(sc, w, h)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    v = camera.make_view([20.0, 30.0, -480.0], 10.0, 12.0, 50.0, 1.0, 0.5, 1200.0)
+    ref.set_view_raw(v)
+    ref.ob_set_max_triangles(1 << 30)
+    ref.ob_clear()
+    ref.ob_set_cull_mode(1)
+    ref.ob_add_triangles(ident, vtx, 12, idx, 0, idx.shape[0])
+    ref.ob_draw()
+    ref.ob_build_hierarchy()
+    ob.set_view(v)
+    ob.set_max_triangles(1 << 30)
+    ob.clear()
+    ob.set_cull_mode(1)
+    ob.draw_batch(ident, vtx, 12, idx, 0, idx.shape[0])
+    ob.build_hierarchy()
+    assert np.array_equal(ob.depth(), ref.ob_depth())
+    rm, om = ref.ob_mips(), ob.mips()
+    assert len(rm) == len(om) == 8
+    for a, b in zip(om, rm):
+        assert np.array_equal(a, b)
+    assert ob.num_triangles() == ref.ob_num_triangles() > 250_000
+    cand = tree.query(1, v.planes, ob, as_ids=False)
+    assert np.array_equal(tree.order[cand], ref.query(1))
+    vis = tree.order[tree.check_visibility(ob, cand)]
+    assert np.array_equal(vis, ref.check_visibility())
+    assert 0 < len(vis) <= len(cand) < sc.n
+    ref.close()
+    ob.close()
+    # config 2
+    w, h = 1024, 576
+    sc = scenes.Scene(100_000, 4000, 500.0)
+    ref = helpers.make_ref(sc, w, h)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    for v in scenes.agent_cameras(2, 500.0, w, h):
+        vis, counts = helpers.ref_draw_view(ref, sc, v)
+        ob.draw_scene_view(sc, v)
+        assert np.array_equal(ob.depth(), ref.ob_depth())
+        rm, om = ref.ob_mips(), ob.mips()
+        assert len(rm) == len(om) == 7
+        for a, b in zip(om, rm):
+            assert np.array_equal(a, b)
+        cand = tree.query(1, v.planes, ob, as_ids=False)
+        assert np.array_equal(tree.order[cand], ref.query(1))
+        assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
+    ref.close()
+    ob.close()
