@@ -43,6 +43,8 @@ def lib():
             getattr(L, n).argtypes = [C.c_void_p]
         L.orc_ob_num_triangles.argtypes = [C.c_void_p]
         L.orc_ob_num_triangles.restype = C.c_uint
+        L.orc_ob_ref_undefined.argtypes = [C.c_void_p]
+        L.orc_ob_ref_undefined.restype = C.c_ulonglong
         L.orc_ob_set_view.argtypes = [C.c_void_p, _f, _f, C.c_int]
         L.orc_ob_get_viewproj.argtypes = [C.c_void_p, _f]
         L.orc_ob_set_max_triangles.argtypes = [C.c_void_p, C.c_uint]
@@ -115,6 +117,10 @@ class OracleOB:
 
     def num_triangles(self):
         return self.L.orc_ob_num_triangles(self.h)
+
+    def ref_undefined(self):
+        """How often the geometry drawn so far (since creation) would have made the reference write outside its padded allocation."""
+        return int(self.L.orc_ob_ref_undefined(self.h))
 
     def is_visible(self, aabb6):
         b = np.ascontiguousarray(aabb6, dtype=np.float32)

@@ -41,6 +41,7 @@ typedef struct OrcOB
     unsigned num_tris, max_tris;
     int dirty;
     unsigned long long px_tested, px_written; /* statistics only */
+    unsigned long long ref_undefined;         /* writes the reference would have made outside its padded allocation (undefined behaviour there) */
 } OrcOB;
 
 /* x86 cvttss2si/cvttsd2si semantics made explicit: out-of-range and NaN give INT_MIN (SURVEY hard part 2). */
@@ -123,6 +124,10 @@ int orc_ob_num_levels(const OrcOB* ob) { return ob->nlev; }
 unsigned orc_ob_num_triangles(const OrcOB* ob) { return ob->num_tris; }
 int orc_ob_cull_mode(const OrcOB* ob) { return ob->cull; }
 void orc_ob_pixel_stats(const OrcOB* ob, unsigned long long* tested, unsigned long long* written) { *tested = ob->px_tested; *written = ob->px_written; }
+/* Since creation: how often the geometry drawn so far would have made the reference write outside its allocation (one row + one int of
+ * padding each side of the plane, OB.cpp:87-90) -- counted pixel by pixel for the rows walked here, once per half-triangle whose row range
+ * had to be cut short.  Non-zero = the reference's own result for that geometry is undefined (it usually corrupts its heap). */
+unsigned long long orc_ob_ref_undefined(const OrcOB* ob) { return ob->ref_undefined; }
 
 /* Matrix4 * Matrix3x4, Matrix4.cpp:43-63 (a = 4x4 row-major, b = 3x4 row-major). */
 static void mul44_34(const float* a, const float* b, float* o)
@@ -211,7 +216,11 @@ static V4 clip_lerp(V4 a, V4 b, float da, float db) /* ClipEdge, OB.cpp:563-567 
 static void depth_min(OrcOB* ob, int64_t off, int z)
 {
     if (off < 0 || off >= (int64_t)ob->w * ob->h)
+    {
+        if (off < -((int64_t)ob->w + 1) || off >= (int64_t)ob->w * ob->h + ob->w + 1)
+            ++ob->ref_undefined;
         return;
+    }
     ++ob->px_tested;
     if (z < ob->depth[off])
     {
@@ -261,6 +270,8 @@ static void fill_half(OrcOB* ob, int y0, int y1, EdgeI* left, EdgeI* right, int 
         hi = lo = (y1 < lo ? y1 : lo);
     if (lo > y1)
         lo = hi = y1;
+    if (lo != y0 || hi != y1)
+        ++ob->ref_undefined; /* rows far outside the plane: the reference walks (and, unless their spans are empty, writes) them */
     edge_skip(left, lo - y0);
     edge_skip(right, lo - y0);
     for (int64_t y = lo; y < hi; ++y)

@@ -76,7 +76,7 @@ def test_queries_over_wild_drawables(gpu_ctx):
     ob.close()
 
 
-@pytest.mark.parametrize("kind", ["tame", "clip", "sliver", "huge", "nonfinite"])
+@pytest.mark.parametrize("kind", ["tame", "clip", "sliver", "large", "huge", "nonfinite"])
 def test_triangle_soups(gpu_ctx, kind):
     model = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32)
     for case in range(12 if kind != "nonfinite" else 5):
