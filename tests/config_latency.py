@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """Per-phase device time of BASELINE configs C1, C2, C4, C5 (the single-view / frustum-only shapes that are parity cases, not bench
 lines), with the compiled reference (oracle/_ref, one host thread) timed beside them.  Diagnostic: prints one JSON line per config.
+Lives under tests/ because it executes the checker (oracle/_ref), which only tests/, smoke() and bench.py may do.
 
-    python scripts/config_latency.py [C1 C2 C4 C5] [--no-cpu]
+    python tests/config_latency.py [C1 C2 C4 C5] [--no-cpu]
 """
 import json
 import os
