@@ -777,3 +777,52 @@ def test_config5_and_config2_shapes_match_reference():
         assert np.array_equal(tree.order[tree.check_visibility(ob, cand)], vis)
     ref.close()
     ob.close()
+
+
+def test_wild_rays_match_reference():
+    """Octree::Raycast / RaycastSingle with rays a caller should not send but can: zero, non-normalised, denormal, infinite and NaN direction
+    components, origins far outside the octree or non-finite, zero and negative maxDistance.  Ids and bit patterns of the distances must follow
+    the reference (Ray::HitDistance, Math/Ray.cpp:71-148, divides by the direction's components)."""
+    sc = helpers.small_scene(n=3000, k=8, extent=60.0, seed=23)
+    ref = helpers.make_ref(sc, 64, 64)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), 64, 64)
+    rs = np.random.RandomState(6)
+    rays = []
+    for i in range(60):
+        o = np.array([rs.uniform(-60, 60), rs.uniform(0.2, 6.0), rs.uniform(-60, 60)], np.float32)
+        d = rs.normal(size=3).astype(np.float32)
+        kind = i % 12
+        if kind == 0:
+            d[:] = 0.0
+        elif kind == 1:
+            d *= np.float32(1e-30)
+        elif kind == 2:
+            d *= np.float32(1e20)
+        elif kind == 3:
+            d[rs.randint(3)] = np.inf
+        elif kind == 4:
+            d[rs.randint(3)] = np.nan
+        elif kind == 5:
+            d[rs.randint(3)] = 0.0
+            d[rs.randint(3)] = -0.0
+        elif kind == 6:
+            o[rs.randint(3)] = np.float32(1e9)
+        elif kind == 7:
+            o[rs.randint(3)] = np.nan
+        elif kind == 8:
+            o[rs.randint(3)] = -np.inf
+        elif kind == 9:
+            d[:] = [1e-45, 0.0, 1.0]
+        maxd = np.float32([np.inf, 0.0, -1.0, 25.0, np.nan][i % 5])
+        rays.append((o, d, maxd))
+    hits = 0
+    for o, d, maxd in rays:
+        for single in (False, True):
+            rid, rdist, _ = ref.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
+            oid, odist = tree.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
+            assert np.array_equal(rid, oid), (o, d, maxd, single)
+            assert np.array_equal(rdist.view(np.uint32), odist.view(np.uint32)), (o, d, maxd, single)
+            hits += len(rid)
+    assert hits > 0
+    ref.close()
+    ob.close()
