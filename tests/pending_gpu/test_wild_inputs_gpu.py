@@ -6,7 +6,7 @@ import pytest
 
 import helpers
 from oracle import oraclebind
-from test_oracle_vs_reference import _soup, _wild_boxes, shape_cases
+from test_oracle_vs_reference import _soup, _wild_boxes, shape_cases, wild_rays
 from urho3d_b200 import camera, capi, scenes
 
 pytestmark = pytest.mark.gpu
@@ -179,5 +179,26 @@ def test_huge_object_count_sample_layout(gpu_ctx):
             got, qc = gs.query(v.planes, None, 0xFF, 0xFFFFFFFF, mode, capi.STAGE_QUERY)
             assert np.array_equal(got, otree.query(mode, v.planes, None))
     for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+def test_wild_rays(gpu_ctx):
+    """u3d_scene_raycast with zero / denormal / infinite / NaN directions and origins: ids and distance bit patterns equal the oracle's."""
+    sc = helpers.small_scene(n=3000, k=8, extent=60.0, seed=23)
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    tree.add(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    flat = tree.flatten()
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    otree, ob = helpers.make_oracle(sc, flat, 8, 8)
+    rays = wild_rays(np.random.RandomState(6))
+    rays7 = np.array([list(o) + list(d) + [m] for o, d, m in rays], np.float32)
+    for single in (False, True):
+        got = gs.raycast(rays7, 0xFF, 0xFFFFFFFF, single, capacity=8192)
+        for i, (o, d, m) in enumerate(rays):
+            wid, wdist = otree.raycast(o, d, m, 0xFF, 0xFFFFFFFF, single)
+            assert np.array_equal(got[i]["drawable"], wid.astype(np.uint32)), "ray %d single %d" % (i, single)
+            assert np.array_equal(got[i]["distance"].view(np.uint32), wdist.view(np.uint32))
+    for o in (gs, tree):
         o.close()
     ob.close()

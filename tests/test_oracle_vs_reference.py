@@ -779,17 +779,12 @@ def test_config5_and_config2_shapes_match_reference():
     ob.close()
 
 
-def test_wild_rays_match_reference():
-    """Octree::Raycast / RaycastSingle with rays a caller should not send but can: zero, non-normalised, denormal, infinite and NaN direction
-    components, origins far outside the octree or non-finite, zero and negative maxDistance.  Ids and bit patterns of the distances must follow
-    the reference (Ray::HitDistance, Math/Ray.cpp:71-148, divides by the direction's components)."""
-    sc = helpers.small_scene(n=3000, k=8, extent=60.0, seed=23)
-    ref = helpers.make_ref(sc, 64, 64)
-    tree, ob = helpers.make_oracle(sc, ref.flatten(), 64, 64)
-    rs = np.random.RandomState(6)
+def wild_rays(rs, count=60, extent=60.0):
+    """Rays a caller should not send but can: zero, non-normalised, denormal, infinite and NaN direction components, origins far outside the
+    octree or non-finite, zero / negative / NaN maxDistance."""
     rays = []
-    for i in range(60):
-        o = np.array([rs.uniform(-60, 60), rs.uniform(0.2, 6.0), rs.uniform(-60, 60)], np.float32)
+    for i in range(count):
+        o = np.array([rs.uniform(-extent, extent), rs.uniform(0.2, 6.0), rs.uniform(-extent, extent)], np.float32)
         d = rs.normal(size=3).astype(np.float32)
         kind = i % 12
         if kind == 0:
@@ -815,8 +810,17 @@ def test_wild_rays_match_reference():
             d[:] = [1e-45, 0.0, 1.0]
         maxd = np.float32([np.inf, 0.0, -1.0, 25.0, np.nan][i % 5])
         rays.append((o, d, maxd))
+    return rays
+
+
+def test_wild_rays_match_reference():
+    """Octree::Raycast / RaycastSingle with the rays of wild_rays().  Ids and bit patterns of the distances must follow the reference
+    (Ray::HitDistance, Math/Ray.cpp:71-148, divides by the direction's components)."""
+    sc = helpers.small_scene(n=3000, k=8, extent=60.0, seed=23)
+    ref = helpers.make_ref(sc, 64, 64)
+    tree, ob = helpers.make_oracle(sc, ref.flatten(), 64, 64)
     hits = 0
-    for o, d, maxd in rays:
+    for o, d, maxd in wild_rays(np.random.RandomState(6)):
         for single in (False, True):
             rid, rdist, _ = ref.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
             oid, odist = tree.raycast(o, d, maxd, 0xFF, 0xFFFFFFFF, single)
