@@ -52,8 +52,6 @@ def test_engine_overloads_compile_link_and_run_against_the_reference_headers():
 
 
 @pytest.mark.gpu
-@pytest.mark.xfail(strict=False, reason="first run on a device pending: written after round 1's GPU budget was spent.  Non-strict so that it "
-                                        "cannot block the suite; an XPASS in the log is the verification, after which the marker goes away")
 def test_gpu_class_matches_the_reference_class_in_one_process():
     if not build():
         pytest.skip("no prebuilt binary travelled")

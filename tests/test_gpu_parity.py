@@ -130,6 +130,51 @@ def test_budget_cullmodes_nonindexed_u32(gpu_ctx):
     ob.close()
 
 
+def test_reset(gpu_ctx):
+    """OcclusionBuffer::Reset (OB.cpp:146-150) through u3d_ob_reset: queued batches are dropped undrawn, what was drawn stays, numTriangles_
+    and with it the budget start again (CPU pin of the same sequence: test_reset_drops_queued_batches_and_the_triangle_count)."""
+    w, h = 64, 64
+    sc = helpers.small_scene(n=10, k=8, extent=10.0, seed=9)
+    v = helpers.stress_views(10.0, w, h, 1, seed=4)[0]
+    gob = capi.OcclusionBuffer(gpu_ctx)
+    gob.SetSize(w, h)
+    ob = oraclebind.OracleOB()
+    ob.set_size(w, h)
+    gob.SetView(v)
+    ob.set_view(v)
+    gob.SetMaxTriangles(30)
+    ob.set_max_triangles(30)
+    gob.Clear()
+    ob.clear()
+    gob.SetCullMode(sc.cull_mode)
+    ob.set_cull_mode(sc.cull_mode)
+    assert gob.AddTriangles(sc.occ_model[0], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36) == ob.draw_batch(sc.occ_model[0], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+    gob.DrawTriangles()
+    gob.Reset()
+    ob.reset()
+    assert gob.GetNumTriangles() == 0 == ob.num_triangles()
+    assert np.array_equal(gob.GetBuffer(), ob.depth())
+    for i in (1, 2, 3):
+        gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+    gob.Reset()
+    gob.DrawTriangles()
+    assert gob.GetNumTriangles() == 0
+    assert np.array_equal(gob.GetBuffer(), ob.depth())
+    rets = []
+    for i in (4, 5, 6, 7):
+        rets.append((gob.AddTriangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36), ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)))
+    gob.DrawTriangles()
+    assert all(a == b for a, b in rets) and rets[0][0] and not rets[-1][0]
+    assert np.array_equal(gob.GetBuffer(), ob.depth())
+    assert gob.GetNumTriangles() == ob.num_triangles()
+    gob.BuildDepthHierarchy()
+    ob.build_hierarchy()
+    for a, b in zip(gob.GetMips(), ob.mips()):
+        assert np.array_equal(a, b)
+    gob.close()
+    ob.close()
+
+
 @pytest.mark.parametrize("mode", [capi.QUERY_FRUSTUM, capi.QUERY_OCCLUDED, capi.QUERY_SHADOWCASTER])
 def test_octree_queries(gpu_ctx, mode):
     """Octree::GetDrawables(query) result_ sequence for the three frustum query classes, with flag/mask filtering."""

@@ -1,6 +1,7 @@
 """Device counterparts of the CPU suite's wild-input pins (tests/test_oracle_vs_reference.py: test_wild_boxes_*, test_queries_over_wild_*,
 test_triangle_soup_fuzz_*; tests/test_host_octree.py: test_wild_drawable_boxes_*).  The oracle equals the compiled reference on all of
-these inputs; here the CUDA path must equal the oracle.  See conftest.py for why this directory is opt-in."""
+these inputs; here the CUDA path must equal the oracle.  (First run on a device at the start of round 2: 11 of 12 passed; the ray test found
+that a NaN maxDistance must reject every drawable while still walking every octant, fixed in shape_test.)"""
 import numpy as np
 import pytest
 

@@ -109,6 +109,46 @@ def test_non_indexed_and_u32_indices_and_cull_modes():
     v.reverse_culling = False
 
 
+def test_reset_drops_queued_batches_and_the_triangle_count():
+    """OcclusionBuffer::Reset (OB.cpp:146-150): numTriangles_ = 0 and batches_.Clear() -- queued geometry is never drawn, what was drawn
+    before stays in the plane, and the budget starts again."""
+    w, h = 64, 64
+    sc = helpers.small_scene(n=10, k=8, extent=10.0, seed=9)
+    ref = helpers.make_ref(sc, w, h)
+    _, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
+    v = helpers.stress_views(10.0, w, h, 1, seed=4)[0]
+    ref.set_view_raw(v)
+    ob.set_view(v)
+    ref.ob_set_max_triangles(30)
+    ob.set_max_triangles(30)
+    ref.ob_clear()
+    ob.clear()
+    ref.ob_set_cull_mode(sc.cull_mode)
+    ob.set_cull_mode(sc.cull_mode)
+    # drawn, then reset: the plane keeps it, the count does not
+    assert ref.ob_add_triangles(sc.occ_model[0], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36) == ob.draw_batch(sc.occ_model[0], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+    ref.ob_draw()
+    ref.ob_reset()
+    ob.reset()
+    assert ref.ob_num_triangles() == 0 == ob.num_triangles()
+    assert np.array_equal(ob.depth(), ref.ob_depth())
+    # queued, then reset: never drawn (the oracle draws at once, so it simply does not get these)
+    for i in (1, 2, 3):
+        ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)
+    ref.ob_reset()
+    ref.ob_draw()
+    assert ref.ob_num_triangles() == 0
+    assert np.array_equal(ob.depth(), ref.ob_depth())
+    # the budget starts again after Reset
+    rets = []
+    for i in (4, 5, 6, 7):
+        rets.append((ref.ob_add_triangles(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36), ob.draw_batch(sc.occ_model[i], sc.mesh_vtx, 52, sc.mesh_idx, 0, 36)))
+    ref.ob_draw()
+    assert all(a == b for a, b in rets) and rets[0][0] and not rets[-1][0]
+    assert np.array_equal(ob.depth(), ref.ob_depth())
+    assert ob.num_triangles() == ref.ob_num_triangles()
+
+
 @pytest.mark.parametrize("ortho", [False, True])
 def test_in_view_stage_matches_reference(ortho):
     """Rest of CheckVisibilityWork (View.cpp:177-211): draw distance + view-space Z range, oracle vs the reference's own math types."""

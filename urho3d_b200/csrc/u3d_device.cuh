@@ -313,7 +313,9 @@ template <bool FAST> __device__ __forceinline__ int shape_test(int mode, const f
         if (FAST && mode == QUERY_RAY_CANDIDATES)
             return INSIDE;
         const float d = ray_hit_distance(p, mnx, mny, mnz, mxx, mxy, mxz);
-        if (d >= p[6])
+        // octants: `if (octantDist >= maxDistance_) return;` (Octree.cpp:259-261); drawables: `if (distance < maxDistance_)` (Drawable.cpp:120-121).
+        // The two differ when maxDistance is NaN: every octant is walked and no drawable is a hit.
+        if (FAST ? !(d < p[6]) : d >= p[6])
             return OUTSIDE;
         return FAST ? INSIDE : INTERSECTS;
     }
