@@ -82,8 +82,22 @@ def config_dict(args, world):
 # ------------------------------------------------------------------------------------------------------------------------------
 # CPU reference arm (oracle/_ref = the UNMODIFIED reference compiled from /root/reference; falls back to the C oracle port)
 # ------------------------------------------------------------------------------------------------------------------------------
+_HASH_P = np.uint64(0x9E3779B97F4A7C15)
+
+
+def seq_hash(ids):
+    """Order-sensitive 64-bit hash of an id sequence: sum_i (id_i + 1) * P^(i+1) + n * P, in wrapping uint64 arithmetic.  Computed the same
+    way from the CPU arm's result_ sequences and from the CUDA path's packed output; swapping two ids or dropping one changes it."""
+    ids = np.asarray(ids).astype(np.uint64)
+    n = ids.shape[0]
+    with np.errstate(over="ignore"):
+        w = np.cumprod(np.full(n, _HASH_P, np.uint64), dtype=np.uint64) if n else np.zeros(0, np.uint64)
+        return int(((ids + np.uint64(1)) * w).sum(dtype=np.uint64) + np.uint64(n) * _HASH_P)
+
+
 def _ref_worker(ref, sc, views, conn):
-    """Persistent worker: waits for (lo, hi) ranges, runs the reference over those views, answers (seconds, visible, triangles)."""
+    """Persistent worker: waits for (lo, hi) ranges, runs the reference over those views, answers (seconds, visible, triangles, per-view
+    hashes of the visible-id sequences)."""
     while True:
         msg = conn.recv()
         if msg is None:
@@ -92,12 +106,15 @@ def _ref_worker(ref, sc, views, conn):
         t0 = time.perf_counter()
         nvis = 0
         tris = 0
+        seqs = []
         for i in range(lo, hi):
             ref.set_view_raw(views[i])
             vis, counts, _ = ref.run_view(sc)
             nvis += len(vis)
             tris += int(counts[0])
-        conn.send((time.perf_counter() - t0, nvis, tris))
+            seqs.append(vis)
+        dt = time.perf_counter() - t0  # hashing is the checker's work, not the reference's: outside the timed part
+        conn.send((dt, nvis, tris, [seq_hash(x) for x in seqs]))
 
 
 class CpuReference:
@@ -145,11 +162,15 @@ class CpuReference:
         for w, (_, conn) in enumerate(self.workers):
             conn.send((n * w // self.cores, n * (w + 1) // self.cores))
         nvis = tris = 0
+        self.hashes = []
+        dt = None
         for _, conn in self.workers:
-            _, a, b = conn.recv()
+            _, a, b, hs = conn.recv()
+            dt = time.perf_counter() - t0  # wall clock until the last worker's answer arrived (hashing happens after each worker's timed loop)
             nvis += a
             tris += b
-        return time.perf_counter() - t0, n, nvis, tris
+            self.hashes += hs
+        return dt, n, nvis, tris
 
     def _step_port(self):
         from oracle import oraclebind
@@ -166,11 +187,16 @@ class CpuReference:
         tree, ob = self._port
         t0 = time.perf_counter()
         nvis = tris = 0
+        seqs = []
         for v in self.views:
             tris += ob.draw_scene_view(self.sc, v)
             cand = tree.query(1, v.planes, ob, as_ids=False)
-            nvis += len(tree.check_visibility(ob, cand))
-        return time.perf_counter() - t0, len(self.views), nvis, tris
+            vis = tree.order[tree.check_visibility(ob, cand)]
+            nvis += len(vis)
+            seqs.append(vis)
+        dt = time.perf_counter() - t0
+        self.hashes = [seq_hash(x) for x in seqs]
+        return dt, len(self.views), nvis, tris
 
     def describe(self):
         return "%d of the workload's views, split over %d single-threaded processes, each running the %s per view: Clear, AddTriangles for " \
@@ -707,13 +733,20 @@ def main():
             dt, n, nvis_cpu, tris_cpu = cpu.step()
             line["cpu_baseline"] = dict({"value": n / dt, "unit": "views/s", "cores": cpu.cores, "kind": cpu.kind, "sample": cpu.describe()},
                                         **host_description())
-            # parity gate on the real workload: the sample's views through the CPU arm and through the CUDA path must agree on the
-            # totals of visible drawables and submitted occluder triangles (the per-view sequences are compared in tests/, at sizes the oracle allows)
+            # parity gate on the real workload: every view of the sample through the CPU arm and through the CUDA path (the e2e leg's
+            # host output) must give the same visible-id SEQUENCE (order-sensitive 64-bit hash per view, Octree.cpp:243-254's result_ order), and
+            # the same totals of visible drawables and submitted occluder triangles
             n_cmp = len(cpu.views)
+            h_ids = slots[0]["h_ids"]
+            gpu_hashes = [seq_hash(h_ids[int(h_offsets[i]):int(h_offsets[i + 1])]) for i in range(n_cmp)]
+            n_equal = sum(1 for a, b in zip(cpu.hashes, gpu_hashes) if a == b)
             line["parity_check"] = {"views": n_cmp, "against": cpu.kind,
+                                    "views_equal": "%d/%d" % (n_equal, n_cmp),
+                                    "how": "order-sensitive 64-bit hash of each view's visible drawable id sequence, CPU arm vs the e2e leg's host output",
                                     "visible": [int(nvis_cpu), int(counts[:n_cmp, 1].sum())],
                                     "submitted_tris": [int(tris_cpu), int(stats[:n_cmp, 0].sum())],
-                                    "equal": bool(int(nvis_cpu) == int(counts[:n_cmp, 1].sum()) and int(tris_cpu) == int(stats[:n_cmp, 0].sum()))}
+                                    "equal": bool(n_equal == n_cmp and len(cpu.hashes) == n_cmp and int(nvis_cpu) == int(counts[:n_cmp, 1].sum())
+                                                  and int(tris_cpu) == int(stats[:n_cmp, 0].sum()))}
             cpu.close()
             eng = engine_threaded_rate(sc, views)
             if eng:

@@ -33,3 +33,13 @@ def gpu_ctx():
     ctx = capi.Context(0)
     yield ctx
     ctx.close()
+
+
+@pytest.fixture(params=["per_view", "dense"])
+def cull_path(request):
+    """Runs a GPU test once per cull path of the batched entry point: the one-CTA-per-view kernel (cull.cu) and the batch-wide dense
+    launches (cull_dense.cu), which by default only takes batches of 16 views and more."""
+    from urho3d_b200 import capi
+    capi.debug_set_option("cull_dense", 0 if request.param == "per_view" else 2)
+    yield request.param
+    capi.debug_set_option("cull_dense", 1)

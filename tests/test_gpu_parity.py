@@ -10,7 +10,7 @@ import helpers
 from oracle import oraclebind
 from urho3d_b200 import camera, capi, scenes
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cull_path")]
 
 GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
 
@@ -245,6 +245,36 @@ def test_batched_views(gpu_ctx, w, h, nviews, stress):
         sub, cand, vis = oracle_view(sc, otree, ob, v)
         assert np.array_equal(qids[off[i]:off[i + 1]], cand)
     for o in (batch, occ, mesh, gs, tree):
+        o.close()
+    ob.close()
+
+
+@pytest.mark.parametrize("opt", ["dense_queue_cap", "dense_pool_cap"])
+def test_dense_path_overflow_is_answered_on_the_device(gpu_ctx, opt):
+    """The batch-wide cull path works out of bounded scratch (a queue of (view, octant) pairs, a pool of result words).  When either is
+    too small the sequence raises a device flag and the one-CTA-per-view kernel queued behind it produces the result: same sequences,
+    no error, no host round trip."""
+    w, h, nviews = 128, 128, 24
+    sc = helpers.small_scene(n=8000, k=96, extent=100.0, seed=77)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    otree, ob = helpers.make_oracle(sc, flat, w, h)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = scenes.agent_cameras(nviews, 100.0, w, h, seed=3)
+    capi.debug_set_option("cull_dense", 2)
+    capi.debug_set_option(opt, 64)
+    try:
+        batch = capi.Batch(gpu_ctx, gs, occ, w, h, nviews, sc.n)
+        for stage in (capi.STAGE_VISIBLE, capi.STAGE_QUERY):
+            counts, offsets, ids = batch.cull_views(capi.pack_views(views), stage)
+            for i, v in enumerate(views):
+                sub, cand, vis = oracle_view(sc, otree, ob, v)
+                want = vis if stage == capi.STAGE_VISIBLE else cand
+                assert counts[i, 0] == len(cand) and np.array_equal(ids[offsets[i]:offsets[i + 1]], want)
+        batch.close()
+    finally:
+        capi.debug_set_option(opt, 0)
+    for o in (occ, mesh, gs, tree):
         o.close()
     ob.close()
 

@@ -10,7 +10,7 @@ from oracle import oraclebind
 from test_oracle_vs_reference import _soup, _wild_boxes, shape_cases, wild_rays
 from urho3d_b200 import camera, capi, scenes
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu, pytest.mark.usefixtures("cull_path")]
 
 
 def test_wild_boxes_is_visible(gpu_ctx):

@@ -18,6 +18,11 @@ using namespace u3d;
 static thread_local std::string g_err;
 static int g_forceIrregular = 0; // u3d_debug_set_option("force_irregular")
 static int g_laneAreaMax = kLaneAreaMax, g_warpAreaMax = kWarpAreaMax; // tuning hooks "lane_area_max" / "warp_area_max"
+// Which cull path a batch takes ("cull_dense"): 0 = one CTA per view always, 1 = the batch-wide dense path from kDenseMinViews views on,
+// 2 = the dense path always.  "dense_queue_cap" / "dense_pool_cap" shrink its scratch (test hook for the on-device fallback).
+static int g_cullDense = 1;
+static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
+constexpr int kDenseMinViews = 16;
 
 static int fail(int code, const std::string& msg)
 {
@@ -323,6 +328,59 @@ struct u3d_ob
     DevBuf<uint32_t> outIdx, outCounts;
 };
 
+/// Scratch of the batch-wide cull path (cull_dense.cu); sized from the scene and the batch's view capacity, grow-only.
+struct DenseScratch
+{
+    DevBuf<uint2> queue, groupList;
+    DevBuf<uint32_t> ctr, groupCount, groupOff, wordBase, viewWords, visWord, wordSlot, wordMeta, testMask;
+    DenseDev dev{};
+    int ensure(uint32_t maxViews, const SceneDev& sc, uint32_t queueCapOverride, uint32_t poolCapOverride)
+    {
+        const uint64_t V = maxViews, M = (uint64_t)sc.numOctants, N = (uint64_t)sc.numDrawables;
+        const int groups = (int)((M + 31) / 32), aliveWords = (int)((M + 1023) / 1024);
+        // worst cases: every octant of every view queued once; every drawable of every view in a word of its own octant.
+        // The defaults hold a good part of that; an overflow is caught on the device and answered by the one-CTA-per-view kernel.
+        const uint64_t queueWorst = V * M, poolWorst = V * ((N + 31) / 32 + std::min(M, N));
+        uint64_t queueCap = std::min<uint64_t>(queueWorst, std::max<uint64_t>(1u << 20, queueWorst / 2));
+        uint64_t poolCap = std::min<uint64_t>(poolWorst, std::max<uint64_t>(1u << 20, poolWorst / 4));
+        queueCap = std::min<uint64_t>(queueCap, 0x7FFFFFFFu);
+        poolCap = std::min<uint64_t>(poolCap, 0x7FFFFFFFu);
+        if (queueCapOverride)
+            queueCap = queueCapOverride;
+        if (poolCapOverride)
+            poolCap = poolCapOverride;
+        CU_CHECK(queue.ensure(queueCap));
+        CU_CHECK(ctr.ensure(dense_counter_bytes((int)V, (int)M) / 4));
+        CU_CHECK(groupCount.ensure(V * groups));
+        CU_CHECK(groupOff.ensure(V * groups));
+        CU_CHECK(groupList.ensure(V * groups));
+        CU_CHECK(wordBase.ensure(V));
+        CU_CHECK(viewWords.ensure(V));
+        CU_CHECK(visWord.ensure(poolCap));
+        CU_CHECK(wordSlot.ensure(poolCap));
+        CU_CHECK(wordMeta.ensure(poolCap));
+        CU_CHECK(testMask.ensure(poolCap));
+        dev.queue = queue.p;
+        dev.queueCap = (uint32_t)queueCap;
+        dev.ctr = ctr.p;
+        dev.aliveBits = ctr.p + 64;
+        dev.aliveWords = aliveWords;
+        dev.groupCount = groupCount.p;
+        dev.groupOff = groupOff.p;
+        dev.groupsPerView = groups;
+        dev.groupList = groupList.p;
+        dev.wordBase = wordBase.p;
+        dev.viewWords = viewWords.p;
+        dev.visWord = visWord.p;
+        dev.wordSlot = wordSlot.p;
+        dev.wordMeta = wordMeta.p;
+        dev.testMask = testMask.p;
+        dev.poolCap = (uint32_t)poolCap;
+        dev.stateStride = groups * 32;
+        return 0;
+    }
+};
+
 struct u3d_batch
 {
     u3d_ctx* ctx{};
@@ -333,6 +391,7 @@ struct u3d_batch
     uint32_t outCap{};
     uint64_t poolTris{};
     DevBuf<unsigned char> octState;
+    DenseScratch dense;
     DevBuf<uint32_t> outIdx, outCounts, packOffsets, packed;
     DevBuf<float> zRange; // per view (minZ, maxZ)
     PinnedBuf<ViewConst> hostViews;
@@ -389,6 +448,26 @@ int u3d_debug_set_option(const char* name, int value)
         cull_set_heavy_extent(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "cull_dense") == 0)
+    {
+        g_cullDense = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_heavy") == 0)
+    {
+        dense_set_heavy_extent(value);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_queue_cap") == 0)
+    {
+        g_denseQueueCap = (uint32_t)value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_pool_cap") == 0)
+    {
+        g_densePoolCap = (uint32_t)value;
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "cull_ring") == 0)
     {
         cull_set_ring(value);
@@ -436,6 +515,8 @@ int u3d_ctx_create(int device, u3d_ctx** out)
         return fail(U3D_ERR_NOMEM, "out of host memory");
     c->device = device;
     e = init_tile_kernel();
+    if (e == cudaSuccess)
+        e = init_cull_kernels();
     if (e == cudaSuccess)
         e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess)
@@ -1373,6 +1454,8 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
     // scratch lives in the ob when there is one, else in a temporary
     u3d_ob tmp;
     u3d_ob* holder = ob ? ob : &tmp;
+    if (ob && ob->ctx != ctx)
+        return fail(U3D_ERR_INVALID, "u3d_octree_query: the occlusion buffer belongs to another context than the scene");
     holder->ctx = ctx;
     ViewConst vc{};
     if (useOb)
@@ -1392,7 +1475,8 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
     CU_CHECK(cudaMemcpyAsync(holder->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(holder->vs.flags.p, 0, 4, st));
     launch_cull(scene->dev, g, holder->vs.views.p, 1, useOb ? ob->vs.depth.p : nullptr, useOb ? ob->vs.mips.p : nullptr,
-        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr, holder->vs.flags.p, false, st);
+        useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, scene->dev.numOctants, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr,
+        holder->vs.flags.p, false, nullptr, st);
     CU_CHECK(cudaGetLastError());
     uint32_t counts[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(counts, holder->outCounts.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1710,8 +1794,8 @@ int u3d_scene_raycast(u3d_scene* s, uint32_t n_rays, const float* rays7, uint32_
     CU_CHECK(cudaMemcpyAsync(s->rayViews.p, s->rayHost.data(), (size_t)n_rays * sizeof(ViewConst), cudaMemcpyHostToDevice, st));
     CU_CHECK(cudaMemsetAsync(s->rayFlags.p, 0, 4, st));
     const BufGeom g = make_geom(2, 2);
-    launch_cull(s->dev, g, s->rayViews.p, (int)n_rays, nullptr, nullptr, 0, s->rayOctState.p, STAGE_QUERY, s->rayIdx.p, devCap, s->rayCounts.p, nullptr,
-        s->rayFlags.p, false, st);
+    launch_cull(s->dev, g, s->rayViews.p, (int)n_rays, nullptr, nullptr, 0, s->rayOctState.p, s->dev.numOctants, STAGE_QUERY, s->rayIdx.p, devCap,
+        s->rayCounts.p, nullptr, s->rayFlags.p, false, nullptr, st);
     launch_ray_distances(s->dev, s->rayViews.p, (int)n_rays, s->slotOfIdDev.p, s->rayIdx.p, devCap, s->rayCounts.p, s->rayDist.p, st);
     CU_CHECK(cudaGetLastError());
     s->rayHostCounts.resize((size_t)n_rays * 2);
@@ -1805,7 +1889,7 @@ int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, i
     if (rc >= 0)
     {
         // ViewSet::alloc sized views for `nviews`; frustum-only batches still need max_views view constants
-        if ((e = b->vs.views.ensure(max_views)) || (e = b->octState.ensure((size_t)max_views * scene->dev.numOctants)) ||
+        if ((e = b->vs.views.ensure(max_views)) || (e = b->octState.ensure((size_t)max_views * ((scene->dev.numOctants + 31) / 32 * 32))) ||
             (e = b->outIdx.ensure((size_t)max_views * std::max<uint32_t>(out_capacity, 1))) || (e = b->outCounts.ensure((size_t)max_views * 2)) ||
             (e = b->packOffsets.ensure((size_t)max_views + 1)) || (e = b->zRange.ensure((size_t)max_views * 2)) || (e = b->hostViews.ensure(max_views)) || (e = b->hostCounts.ensure((size_t)max_views * 2 + 2)))
             rc = fail(U3D_ERR_CUDA, std::string("u3d_batch_create: ") + cudaGetErrorString(e));
@@ -1971,8 +2055,28 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
     CU_CHECK(mark(6));
     if (part != 1)
     {
-        launch_cull(b->scene->dev, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p, vs.flags.p, b->pipelined, st);
-        b->lastLaunches += 1;
+        const SceneDev& sc = b->scene->dev;
+        const int stateStride = (sc.numOctants + 31) / 32 * 32;
+        CU_CHECK(b->octState.ensure((size_t)vs.maxViews * stateStride));
+        const bool dense = (g_cullDense == 2 || (g_cullDense == 1 && V >= kDenseMinViews)) && sc.numLevels <= 30;
+        if (dense)
+        {
+            int rc = b->dense.ensure(vs.maxViews, sc, g_denseQueueCap, g_densePoolCap);
+            if (rc < 0)
+                return rc;
+            launch_cull_dense(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p,
+                vs.flags.p, b->dense.dev, st);
+            // answered on the device if the dense path's scratch overflowed (returns at once otherwise)
+            launch_cull(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stateStride, stage, b->outIdx.p, b->outCap, b->outCounts.p,
+                b->zRange.p, vs.flags.p, b->pipelined, b->dense.dev.ctr + 34, st);
+            b->lastLaunches += (uint32_t)dense_launch_count(sc) + 1;
+        }
+        else
+        {
+            launch_cull(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stateStride, stage, b->outIdx.p, b->outCap, b->outCounts.p,
+                b->zRange.p, vs.flags.p, b->pipelined, nullptr, st);
+            b->lastLaunches += 1;
+        }
         CU_CHECK(cudaGetLastError());
     }
     CU_CHECK(mark(7));

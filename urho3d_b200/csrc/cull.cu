@@ -222,10 +222,13 @@ __device__ int g_cullProfOn;
     } while (0)
 
 template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_cull_views(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
-    const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stage,
-    uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags)
+    const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ octStateAll, int stateStride, int stage,
+    uint32_t* __restrict__ outIdx, uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags,
+    const uint32_t* __restrict__ onlyIf)
 {
     static_assert(R / 32 <= T && R % T == 0, "queue size must be a multiple of the block size and at most 32 entries per thread");
+    if (onlyIf && !*onlyIf)
+        return; // fallback launch behind the dense path: nothing overflowed
     extern __shared__ __align__(16) unsigned char cullSmem[];
     CullShared<T, R>& sh = *reinterpret_cast<CullShared<T, R>*>(cullSmem);
     const int v = blockIdx.x;
@@ -256,7 +259,7 @@ template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_c
     const bool useMips = mipsValid != 0;
     const int* depth = depthAll + (size_t)v * g.w * g.h;
     const int2* mips = mipAll + (size_t)v * g.mipTexels;
-    unsigned char* state = octStateAll + (size_t)v * sc.numOctants;
+    unsigned char* state = octStateAll + (size_t)v * stateStride;
     uint32_t* out = outIdx + (size_t)v * outCap;
 
     CULL_PROF_MARK(0);
@@ -348,7 +351,7 @@ template <int T, int MINB, int R> __global__ void __launch_bounds__(T, MINB) k_c
     {
         // the root is never tested by OctreeQuery walks (Octree.cpp:231); the ray walk tests every octant (Octree.cpp:257-261)
         bool rootAlive = true;
-        if (vc.queryMode >= QUERY_RAY)
+        if (vc.queryMode == QUERY_RAY || vc.queryMode == QUERY_RAY_CANDIDATES)
         {
             const float4 mn = sc.octMin[0], mx = sc.octMax[0];
             rootAlive = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
@@ -673,12 +676,26 @@ __global__ void k_is_visible(BufGeom g, const ViewConst* __restrict__ view, cons
     out[i] = ob_is_visible(g, view->vp, depth, mips, mipsValid != 0, b[0], b[1], b[2], b[3], b[4], b[5]) ? 1 : 0;
 }
 
+/// Dynamic shared memory sizes of the cull kernel's instantiations; the attribute belongs to the current device's context, so this runs
+/// once per u3d_ctx_create (not per launch).
+cudaError_t init_cull_kernels()
+{
+    cudaError_t e = cudaFuncSetAttribute(k_cull_views<512, 3, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 8192>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_cull_views<512, 3, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 4096>));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(k_cull_views<1024, 1, kCullBigRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<1024, kCullBigRing>));
+    return e;
+}
+
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
-    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, bool pipelined, cudaStream_t s)
+    unsigned char* octState, int stateStride, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags,
+    bool pipelined, const uint32_t* onlyIf, cudaStream_t s)
 {
     if (!numViews)
         return;
-    cudaMemsetAsync(octState, 0, (size_t)numViews * sc.numOctants, s); // octants the sweeps skip must read as culled
+    if (!onlyIf)
+        cudaMemsetAsync(octState, 0, (size_t)numViews * stateStride, s); // octants the sweeps skip must read as culled
     // Large batches: 512-thread CTAs, three per SM (best throughput).  Batches of a few views per SM: one 1024-thread CTA per SM, which
     // halves the latency of a view and avoids a nearly empty second wave (measured: 512 views 2.0 ms -> 1.46 ms; 4096 views 6.4 ms vs 9.2 ms).
     // When the caller keeps several batches in flight (`pipelined`) other launches fill that wave, and the first shape wins again
@@ -688,27 +705,23 @@ void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, i
         // queue entries per CTA (tuning hook "cull_ring"): a larger queue means fewer evaluation passes (each ends in block-wide barriers)
         if (g_cullRingHost == 8192)
         {
-            cudaFuncSetAttribute(k_cull_views<512, 3, 8192>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 8192>));
-            k_cull_views<512, 3, 8192><<<numViews, 512, sizeof(CullShared<512, 8192>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
-                outCap, outCounts, zRange, flags);
+            k_cull_views<512, 3, 8192><<<numViews, 512, sizeof(CullShared<512, 8192>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stateStride, stage, outIdx,
+                outCap, outCounts, zRange, flags, onlyIf);
         }
         else if (g_cullRingHost == 4096)
         {
-            // set per launch (~1 us): the attribute belongs to the current device's context, and one process may drive several devices
-            cudaFuncSetAttribute(k_cull_views<512, 3, 4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<512, 4096>));
-            k_cull_views<512, 3, 4096><<<numViews, 512, sizeof(CullShared<512, 4096>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
-                outCap, outCounts, zRange, flags);
+            k_cull_views<512, 3, 4096><<<numViews, 512, sizeof(CullShared<512, 4096>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stateStride, stage, outIdx,
+                outCap, outCounts, zRange, flags, onlyIf);
         }
         else
-            k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stage, outIdx,
-                outCap, outCounts, zRange, flags);
+            k_cull_views<512, 3, 2048><<<numViews, 512, sizeof(CullShared<512, 2048>), s>>>(sc, g, views, depth, mips, mipsValid, octState, stateStride, stage, outIdx,
+                outCap, outCounts, zRange, flags, onlyIf);
     }
     else
     {
         // one CTA per SM has the whole shared memory: a 16K-entry queue means one evaluation pass per ~16K survivors instead of one per 1-2K
-        cudaFuncSetAttribute(k_cull_views<1024, 1, kCullBigRing>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(CullShared<1024, kCullBigRing>));
         k_cull_views<1024, 1, kCullBigRing><<<numViews, 1024, sizeof(CullShared<1024, kCullBigRing>), s>>>(sc, g, views, depth, mips, mipsValid, octState,
-            stage, outIdx, outCap, outCounts, zRange, flags);
+            stateStride, stage, outIdx, outCap, outCounts, zRange, flags, onlyIf);
     }
 }
 

@@ -1,0 +1,666 @@
+// Octree query + occlusion culling for a whole batch of views as dense, barrier-free launches.  Same results as cull.cu's
+// one-CTA-per-view kernel (which stays for single views and as the on-device fallback when this path's scratch overflows):
+//   Octree::GetDrawables(OctreeQuery&) -> Octant::GetDrawablesInternal        (Octree.cpp:495-499, 229-255)
+//   FrustumOctreeQuery / OccludedFrustumOctreeQuery / ShadowCasterOctreeQuery (OctreeQuery.cpp:98-118, View.cpp:116-158, 59-84)
+//   CheckVisibilityWork's occlusion predicate + the in-view stage             (View.cpp:177-211)
+//
+// The work of ALL views is pooled, so no launch depends on how much one view has to do:
+//   k_dense_seed      one thread per view: the root (never tested by OctreeQuery walks, Octree.cpp:231) and its children
+//   k_dense_level     per octree level: a global queue of (view, octant, inside) pairs, 32 per warp, TestOctant on dense warps;
+//                     survivors record their state and append their children to the next level's part of the queue
+//   k_dense_groups    per view and group of 32 octants (DFS order): result words (32 drawables each) the group's surviving octants need
+//   k_dense_scan      per view: exclusive scan of those -> every octant's drawables own a run of words in DFS order
+//   k_dense_words     one warp per surviving group: describes every word (first DFS slot, view, valid drawables, inside flag)
+//   k_dense_frustum   flat over the words: TestDrawables, 32 drawables per warp step (two coalesced float4 loads each)
+//   k_dense_occlusion flat over the words: the drawables that still need the occlusion predicate, handed out 32 at a time
+//   k_dense_emit      per view: scan of the words' popcounts -> ids in result_ order (= ascending DFS slot)
+// No block-wide barrier anywhere except the emit kernel's scan; boxes with large screen rects are walked by the whole warp.
+#include "u3d_device.cuh"
+#include "u3d_kernels.h"
+
+namespace u3d
+{
+
+constexpr int kDenseThreads = 256;
+constexpr int kDenseWarps = kDenseThreads / 32;
+constexpr int kDenseWStack = 128;  // per-warp texel stack of the cooperative range test
+
+__device__ int g_denseHeavyExtent = 64; // rect extent (pixels) from which a box is walked by the whole warp (tuning hook "dense_heavy")
+
+enum : int { CTR_LEVEL0 = 0, CTR_GROUPS = 32, CTR_POOL = 33, CTR_FALLBACK = 34 };
+
+/// OcclusionBuffer::IsVisible for one box per lane, each lane with its own view.  Small rects are walked by their lane, large ones
+/// by the whole warp one after another.  Every lane of the warp must call.
+__device__ __forceinline__ bool dense_is_visible(const BufGeom& g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+    const int2* __restrict__ mipAll, bool useMips, bool need, int v, const float4& mn, const float4& mx, uint32_t* wstack)
+{
+    const int lane = threadIdx.x & 31;
+    BoxRect r;
+    r.left = r.top = r.right = r.bottom = r.z = 0;
+    bool vis = false, heavy = false;
+    if (need)
+    {
+        const int* depth = depthAll + (size_t)v * g.w * g.h;
+        const int2* mips = mipAll + (size_t)v * g.mipTexels;
+        if (ob_project(g, views[v].vp, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z, r))
+            vis = true;
+        else if (useMips && max(r.right - r.left, r.bottom - r.top) >= g_denseHeavyExtent)
+            heavy = true;
+        else
+            vis = range_visible_thread(g, depth, mips, useMips, r);
+    }
+    uint32_t todo = __ballot_sync(0xffffffffu, heavy);
+    while (todo)
+    {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        BoxRect rr;
+        rr.left = __shfl_sync(0xffffffffu, r.left, src);
+        rr.top = __shfl_sync(0xffffffffu, r.top, src);
+        rr.right = __shfl_sync(0xffffffffu, r.right, src);
+        rr.bottom = __shfl_sync(0xffffffffu, r.bottom, src);
+        rr.z = __shfl_sync(0xffffffffu, r.z, src);
+        const int vv = __shfl_sync(0xffffffffu, v, src);
+        const bool rv = range_visible_warp(g, depthAll + (size_t)vv * g.w * g.h, mipAll + (size_t)vv * g.mipTexels, rr, wstack, kDenseWStack);
+        if (lane == src)
+            vis = rv;
+    }
+    return vis;
+}
+
+__device__ __forceinline__ void dense_mark_alive(const SceneDev& sc, const DenseDev& dd, int v, int o, unsigned char st, unsigned char* __restrict__ stateAll)
+{
+    stateAll[(size_t)v * dd.stateStride + o] = st;
+    if (sc.octCount[o] > 0)
+        atomicOr(&dd.aliveBits[(size_t)v * dd.aliveWords + (o >> 10)], 1u << ((o >> 5) & 31));
+}
+
+__global__ void __launch_bounds__(kDenseThreads) k_dense_seed(SceneDev sc, const ViewConst* __restrict__ views, int numViews, unsigned char* __restrict__ stateAll,
+    DenseDev dd)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= numViews)
+        return;
+    const ViewConst& vc = views[v];
+    // the root is never tested by OctreeQuery walks (Octree.cpp:231); the ray walk tests every octant (Octree.cpp:257-261)
+    bool rootAlive = true;
+    if (vc.queryMode == QUERY_RAY || vc.queryMode == QUERY_RAY_CANDIDATES)
+    {
+        const float4 mn = sc.octMin[0], mx = sc.octMax[0];
+        rootAlive = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+    }
+    if (!rootAlive)
+        return;
+    dense_mark_alive(sc, dd, v, 0, 1, stateAll);
+    const int2 ch = sc.octChild[0];
+    if (ch.y)
+    {
+        const uint32_t pos = atomicAdd(&dd.ctr[CTR_LEVEL0 + 1], (uint32_t)ch.y);
+        if (pos + (uint32_t)ch.y > dd.queueCap)
+        {
+            dd.ctr[CTR_FALLBACK] = 1;
+            return;
+        }
+        for (int j = 0; j < ch.y; ++j)
+            dd.queue[pos + j] = make_uint2((uint32_t)v, (uint32_t)sc.bfs[ch.x + j]);
+    }
+}
+
+/// TestOctant for every queued (view, octant) pair of one level; the pairs of level `level` sit behind those of the levels before it.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_level(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+    const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ stateAll, DenseDev dd, int level)
+{
+    __shared__ uint32_t wstack[kDenseWarps][kDenseWStack];
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    uint32_t base = 0;
+    for (int l = 1; l < level; ++l)
+        base += dd.ctr[CTR_LEVEL0 + l];
+    const uint32_t n = dd.ctr[CTR_LEVEL0 + level];
+    const uint32_t nextBase = base + n;
+    const bool useMips = mipsValid != 0;
+    const uint32_t totalWarps = gridDim.x * kDenseWarps;
+    // Upper levels hold few pairs, and their boxes have large screen rects that a warp walks one after another: spread them over all
+    // warps of the grid instead of filling a few warps with 32 each.
+    const uint32_t per = n >= totalWarps * 32u ? 32u : max(1u, (n + totalWarps - 1u) / totalWarps);
+    for (uint32_t it = blockIdx.x * kDenseWarps + wid; it * per < n; it += totalWarps)
+    {
+        const uint32_t idx = it * per + lane;
+        int v = 0, o = 0, res = OUTSIDE;
+        bool occluded = false;
+        float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
+        if ((uint32_t)lane < per && idx < n)
+        {
+            const uint2 e = dd.queue[base + idx];
+            v = (int)e.x;
+            o = (int)(e.y & 0x7FFFFFFFu);
+            const ViewConst& vc = views[v];
+            mn = sc.octMin[o];
+            mx = sc.octMax[o];
+            if (e.y >> 31)
+                res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
+            else
+                res = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+            occluded = vc.useOcclusion != 0 && vc.queryMode == QUERY_OCCLUDED;
+        }
+        // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
+        if (__any_sync(0xffffffffu, occluded && res != OUTSIDE))
+        {
+            const bool need = occluded && res != OUTSIDE;
+            const bool vis = dense_is_visible(g, views, depthAll, mipAll, useMips, need, v, mn, mx, wstack[wid]);
+            if (need && !vis)
+                res = OUTSIDE;
+        }
+        const bool alive = res != OUTSIDE;
+        int2 ch = make_int2(0, 0);
+        if (alive)
+        {
+            dense_mark_alive(sc, dd, v, o, res == INSIDE ? 2 : 1, stateAll);
+            ch = sc.octChild[o];
+        }
+        // children join the next level's part of the queue: one atomic per warp
+        int off = ch.y;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const int t = __shfl_up_sync(0xffffffffu, off, s);
+            if (lane >= s)
+                off += t;
+        }
+        const int total = __shfl_sync(0xffffffffu, off, 31);
+        if (total)
+        {
+            off -= ch.y;
+            uint32_t pos = 0;
+            if (lane == 0)
+                pos = atomicAdd(&dd.ctr[CTR_LEVEL0 + level + 1], (uint32_t)total);
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if ((uint64_t)nextBase + pos + (uint32_t)total > dd.queueCap)
+            {
+                if (lane == 0)
+                    dd.ctr[CTR_FALLBACK] = 1;
+            }
+            else
+            {
+                const uint32_t ins = res == INSIDE ? 0x80000000u : 0u;
+                for (int j = 0; j < ch.y; ++j)
+                    dd.queue[nextBase + pos + off + j] = make_uint2((uint32_t)v, (uint32_t)sc.bfs[ch.x + j] | ins);
+            }
+        }
+    }
+}
+
+/// One warp per (view, block of 1024 octants), one lane per group of 32 octants: result words the group's surviving octants need.
+/// Groups with work are appended to the group list.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_groups(SceneDev sc, int numViews, const unsigned char* __restrict__ stateAll, DenseDev dd)
+{
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t totalWarps = gridDim.x * kDenseWarps;
+    const uint32_t items = (uint32_t)numViews * dd.aliveWords;
+    for (uint32_t it = blockIdx.x * kDenseWarps + wid; it < items; it += totalWarps)
+    {
+        const int v = (int)(it / dd.aliveWords), blk = (int)(it % dd.aliveWords);
+        const uint32_t bits = dd.aliveBits[(size_t)v * dd.aliveWords + blk];
+        const int grp = blk * 32 + lane;
+        uint32_t words = 0;
+        if ((bits >> lane) & 1u)
+        {
+            const unsigned char* st = stateAll + (size_t)v * dd.stateStride + grp * 32;
+            const uint4 s0 = *reinterpret_cast<const uint4*>(st), s1 = *reinterpret_cast<const uint4*>(st + 16);
+            const uint32_t sw[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if ((sw[j >> 2] >> ((j & 3) * 8)) & 0xFFu)
+                    words += ((uint32_t)sc.octCount[grp * 32 + j] + 31u) >> 5;
+        }
+        if (grp < dd.groupsPerView)
+            dd.groupCount[(size_t)v * dd.groupsPerView + grp] = words;
+        const uint32_t bal = __ballot_sync(0xffffffffu, words != 0);
+        if (bal)
+        {
+            uint32_t pos = 0;
+            if (lane == 0)
+                pos = atomicAdd(&dd.ctr[CTR_GROUPS], (uint32_t)__popc(bal));
+            pos = __shfl_sync(0xffffffffu, pos, 0);
+            if (words)
+                dd.groupList[pos + __popc(bal & ((1u << lane) - 1u))] = make_uint2((uint32_t)v, (uint32_t)grp);
+        }
+    }
+}
+
+/// One warp per view: exclusive scan of the groups' word counts; the view's words get a region of the pool.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_scan(int numViews, DenseDev dd)
+{
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31;
+    const int v = (blockIdx.x * kDenseThreads + threadIdx.x) >> 5;
+    if (v >= numViews)
+        return;
+    const uint32_t* cnt = dd.groupCount + (size_t)v * dd.groupsPerView;
+    uint32_t* offs = dd.groupOff + (size_t)v * dd.groupsPerView;
+    uint32_t carry = 0;
+    for (int b = 0; b < dd.groupsPerView; b += 32)
+    {
+        const uint32_t c = b + lane < dd.groupsPerView ? cnt[b + lane] : 0u;
+        uint32_t x = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, x, s);
+            if (lane >= s)
+                x += t;
+        }
+        if (b + lane < dd.groupsPerView)
+            offs[b + lane] = carry + x - c;
+        carry += __shfl_sync(0xffffffffu, x, 31);
+    }
+    if (lane == 0)
+    {
+        const uint32_t pos = atomicAdd(&dd.ctr[CTR_POOL], carry);
+        dd.wordBase[v] = pos;
+        dd.viewWords[v] = carry;
+        if ((uint64_t)pos + carry > dd.poolCap)
+            dd.ctr[CTR_FALLBACK] = 1;
+    }
+}
+
+/// One warp per group with work: every surviving octant of the group describes its result words (first DFS slot, view, number of valid
+/// drawables, inside flag), so that the drawable tests can run flat over the pool.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_words(SceneDev sc, const unsigned char* __restrict__ stateAll, DenseDev dd)
+{
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t nGroups = dd.ctr[CTR_GROUPS];
+    const uint32_t totalWarps = gridDim.x * kDenseWarps;
+    for (uint32_t it = blockIdx.x * kDenseWarps + wid; it < nGroups; it += totalWarps)
+    {
+        const uint2 item = dd.groupList[it];
+        const int v = (int)item.x, grp = (int)item.y;
+        const uint32_t wordBase = dd.wordBase[v] + dd.groupOff[(size_t)v * dd.groupsPerView + grp];
+        const int o = grp * 32 + lane;
+        uint32_t cnt = 0, first = 0, ins = 0;
+        if (o < sc.numOctants)
+        {
+            const unsigned char st = stateAll[(size_t)v * dd.stateStride + o];
+            if (st)
+            {
+                cnt = (uint32_t)sc.octCount[o];
+                first = (uint32_t)__float_as_int(sc.octMax[o].w);
+                ins = st == 2 ? 1u : 0u;
+            }
+        }
+        uint32_t woff = (cnt + 31u) >> 5;
+        {
+            const uint32_t mine = woff;
+#pragma unroll
+            for (int s = 1; s < 32; s <<= 1)
+            {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, woff, s);
+                if (lane >= s)
+                    woff += t;
+            }
+            woff -= mine;
+        }
+        const uint32_t common = (uint32_t)v | (ins << 21);
+        if (cnt && cnt <= 256)
+            for (uint32_t k = 0; k < cnt; k += 32)
+            {
+                const uint32_t w = wordBase + woff + (k >> 5);
+                dd.wordSlot[w] = first + k;
+                dd.wordMeta[w] = common | ((min(cnt - k, 32u) - 1u) << 16);
+            }
+        // octants with many drawables: the whole warp writes their descriptors
+        uint32_t big = __ballot_sync(0xffffffffu, cnt > 256);
+        while (big)
+        {
+            const int j = __ffs(big) - 1;
+            big &= big - 1;
+            const uint32_t bCnt = __shfl_sync(0xffffffffu, cnt, j), bFirst = __shfl_sync(0xffffffffu, first, j);
+            const uint32_t bWord = wordBase + __shfl_sync(0xffffffffu, woff, j), bCommon = __shfl_sync(0xffffffffu, common, j);
+            for (uint32_t k = lane * 32u; k < bCnt; k += 1024u)
+            {
+                dd.wordSlot[bWord + (k >> 5)] = bFirst + k;
+                dd.wordMeta[bWord + (k >> 5)] = bCommon | ((min(bCnt - k, 32u) - 1u) << 16);
+            }
+        }
+    }
+}
+
+/// FrustumOctreeQuery::TestDrawables (OctreeQuery.cpp:106-118) / ShadowCasterOctreeQuery (View.cpp:70-82) / ZoneOccluderOctreeQuery
+/// (View.cpp:99-112) flat over the pool: one word = 32 consecutive drawables of one surviving octant of one view per warp step, two coalesced
+/// float4 loads per drawable.  Writes, per word, the drawables that are in the result without a buffer test and those that still need
+/// CheckVisibilityWork's occlusion predicate (k_dense_occlusion); the in-view stage's draw-distance test (View.cpp:179-186) is applied here.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_frustum(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outCounts,
+    DenseDev dd)
+{
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const uint32_t total = dd.ctr[CTR_POOL];
+    const uint32_t totalWarps = gridDim.x * kDenseWarps;
+    const bool inViewStage = stage == STAGE_INVIEW;
+    for (uint32_t it = blockIdx.x * kDenseWarps + wid; it * 32u < total; it += totalWarps)
+    {
+        const uint32_t w0 = it * 32u, myW = w0 + lane;
+        uint32_t meta = 0, slot0 = 0;
+        if (myW < total)
+        {
+            meta = dd.wordMeta[myW];
+            slot0 = dd.wordSlot[myW];
+        }
+        const int nW = (int)min(32u, total - w0);
+        uint32_t myVis = 0, myTest = 0, myQuery = 0;
+        for (int j = 0; j < nW; ++j)
+        {
+            const uint32_t m = __shfl_sync(0xffffffffu, meta, j), s0 = __shfl_sync(0xffffffffu, slot0, j);
+            const ViewConst& vc = views[m & 0xFFFFu];
+            const int queryMode = vc.queryMode;
+            const bool sInside = (m >> 21) & 1u;
+            const uint32_t d = s0 + lane;
+            bool pass = false, test = false, vis0 = false;
+            if ((uint32_t)lane <= ((m >> 16) & 31u))
+            {
+                const float4 mn = sc.drwMin[d];
+                const float4 mx = sc.drwMax[d];
+                const uint32_t dm = __float_as_uint(mn.w);
+                const bool flagsOk = queryMode != QUERY_ZONE_OCCLUDER ? (dm & 0xFFu & vc.drawableFlags) != 0
+                                                                      : ((dm & 0xFFu) == 4u || ((dm & 0xFFu) == 1u && (dm & kMetaOccluder)));
+                if (flagsOk && (__float_as_uint(mx.w) & vc.viewMask) && (queryMode != QUERY_SHADOWCASTER || (dm & kMetaCastShadows)))
+                    pass = sInside || shape_test<true>(queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) != OUTSIDE;
+                if (pass)
+                {
+                    // !buffer || !drawable->IsOccludee() || buffer->IsVisible(box), View.cpp:177: the last term is k_dense_occlusion's
+                    if (stage >= STAGE_VISIBLE && vc.useOcclusion != 0 && (dm & kMetaOccludee))
+                        test = true;
+                    else
+                        vis0 = true;
+                    if (inViewStage)
+                    {
+                        // Drawable::UpdateBatches distance (Drawable.cpp:134-137) and the draw-distance test (View.cpp:179-186)
+                        const float maxDistance = sc.drwDrawDist[d];
+                        if (maxDistance > 0.0f)
+                        {
+                            const float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f; // BoundingBox::Center
+                            float dist;
+                            if (!vc.ortho)
+                            {
+                                const float dx = cx - vc.camPos[0], dy = cy - vc.camPos[1], dz = cz - vc.camPos[2];
+                                dist = sqrtf(dx * dx + dy * dy + dz * dz); // (worldPos - cameraPos).Length(), Camera.cpp:487-493
+                            }
+                            else
+                                // Abs((GetView() * worldPos).z_), Camera.cpp:495, in the operation order of the reference's default (URHO3D_SSE)
+                                // build of Matrix3x4 * Vector3 (Matrix3x4.h:256-274): (m20*x + m22*z) + (m21*y + m23)
+                                dist = fabsf((vc.viewZ[0] * cx + vc.viewZ[2] * cz) + (vc.viewZ[1] * cy + vc.viewZ[3]));
+                            if (dist > maxDistance)
+                            {
+                                vis0 = false;
+                                test = false;
+                            }
+                        }
+                    }
+                }
+            }
+            const uint32_t q = __ballot_sync(0xffffffffu, pass);
+            const uint32_t v0 = __ballot_sync(0xffffffffu, vis0);
+            const uint32_t tb = __ballot_sync(0xffffffffu, test);
+            if (lane == j)
+            {
+                myVis = v0;
+                myTest = tb;
+                myQuery = (uint32_t)__popc(q);
+            }
+        }
+        if (myW < total)
+        {
+            dd.visWord[myW] = myVis;
+            dd.testMask[myW] = myTest;
+        }
+        // query result size per view (counts[v][0]): the words of a step nearly always belong to one view
+        const uint32_t myView = meta & 0xFFFFu;
+        const uint32_t firstView = __shfl_sync(0xffffffffu, myView, 0);
+        if (__all_sync(0xffffffffu, myW >= total || myView == firstView))
+        {
+            const uint32_t sum = __reduce_add_sync(0xffffffffu, myQuery);
+            if (lane == 0 && sum)
+                atomicAdd(&outCounts[2 * firstView], sum);
+        }
+        else if (myQuery)
+            atomicAdd(&outCounts[2 * myView], myQuery);
+    }
+}
+
+/// CheckVisibilityWork's occlusion predicate (View.cpp:177) over the drawables k_dense_frustum left to it.  A warp step takes 32 words,
+/// and hands their marked drawables out 32 at a time (candidate c belongs to the word whose running count covers c), so that
+/// OcclusionBuffer::IsVisible always runs on full warps.
+__global__ void __launch_bounds__(kDenseThreads) k_dense_occlusion(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+    const int2* __restrict__ mipAll, int mipsValid, DenseDev dd)
+{
+    __shared__ uint32_t wstack[kDenseWarps][kDenseWStack];
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool useMips = mipsValid != 0;
+    const uint32_t total = dd.ctr[CTR_POOL];
+    const uint32_t totalWarps = gridDim.x * kDenseWarps;
+    for (uint32_t it = blockIdx.x * kDenseWarps + wid; it * 32u < total; it += totalWarps)
+    {
+        const uint32_t myW = it * 32u + lane;
+        uint32_t mask = 0, view = 0, slot0 = 0;
+        if (myW < total)
+            mask = dd.testMask[myW];
+        if (!__any_sync(0xffffffffu, mask != 0))
+            continue;
+        if (mask)
+        {
+            view = dd.wordMeta[myW] & 0xFFFFu;
+            slot0 = dd.wordSlot[myW];
+        }
+        const uint32_t cnt = (uint32_t)__popc(mask);
+        uint32_t excl = cnt;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, excl, s);
+            if (lane >= s)
+                excl += t;
+        }
+        const uint32_t tot = __shfl_sync(0xffffffffu, excl, 31);
+        excl -= cnt;
+        for (uint32_t c0 = 0; c0 < tot; c0 += 32)
+        {
+            const uint32_t c = min(c0 + lane, tot - 1);
+            const bool have = c0 + lane < tot;
+            // owner = the last lane whose running count is <= c (it has drawables left: the next lane's count is beyond c)
+            int owner = 0;
+#pragma unroll
+            for (int step = 16; step; step >>= 1)
+            {
+                const uint32_t e = __shfl_sync(0xffffffffu, excl, (owner + step) & 31);
+                if (owner + step < 32 && e <= c)
+                    owner += step;
+            }
+            const uint32_t oMask = __shfl_sync(0xffffffffu, mask, owner), oExcl = __shfl_sync(0xffffffffu, excl, owner);
+            const uint32_t oSlot = __shfl_sync(0xffffffffu, slot0, owner), oView = __shfl_sync(0xffffffffu, view, owner);
+            const uint32_t bit = __fns(oMask, 0, (int)(c - oExcl) + 1);
+            float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
+            if (have)
+            {
+                mn = sc.drwMin[oSlot + bit];
+                mx = sc.drwMax[oSlot + bit];
+            }
+            const bool vis = dense_is_visible(g, views, depthAll, mipAll, useMips, have, (int)oView, mn, mx, wstack[wid]);
+            if (have && vis)
+                atomicOr(&dd.visWord[it * 32u + owner], 1u << bit);
+        }
+    }
+}
+
+/// Per view: ids of the set bits of the view's words in order (= the reference's result_ order), counts, and for the in-view stage the
+/// view-space Z range of the geometries (View.cpp:198-211, merged as View.cpp:926-951).
+__global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outIdx,
+    uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags, DenseDev dd)
+{
+    __shared__ uint32_t warpTot[kDenseWarps];
+    __shared__ float red[2 * kDenseWarps];
+    if (dd.ctr[CTR_FALLBACK])
+        return;
+    const int v = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const ViewConst& vc = views[v];
+    const bool inViewStage = stage == STAGE_INVIEW;
+    const uint32_t nWords = dd.viewWords[v];
+    const uint32_t* words = dd.visWord + dd.wordBase[v];
+    const uint32_t* slots = dd.wordSlot + dd.wordBase[v];
+    uint32_t* out = outIdx + (size_t)v * outCap;
+    uint32_t cursor = 0;
+    float zMin = __int_as_float(0x7f800000), zMax = 0.0f; // PerThreadSceneResult::minZ_/maxZ_ start values, View.cpp:893-894
+    for (uint32_t base = 0; base < nWords; base += kDenseThreads)
+    {
+        const uint32_t i = base + tid;
+        uint32_t word = i < nWords ? words[i] : 0u;
+        const uint32_t c = (uint32_t)__popc(word);
+        // block-wide exclusive scan
+        uint32_t x = c;
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, x, s);
+            if (lane >= s)
+                x += t;
+        }
+        __syncthreads(); // warpTot of the previous round has been read
+        if (lane == 31)
+            warpTot[wid] = x;
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+#pragma unroll
+        for (int w = 0; w < kDenseWarps; ++w)
+        {
+            const uint32_t t = warpTot[w];
+            if (w < wid)
+                pre += t;
+            tot += t;
+        }
+        uint32_t pos = cursor + pre + x - c;
+        if (word)
+        {
+            const uint32_t s0 = slots[i];
+            while (word)
+            {
+                const int b = __ffs(word) - 1;
+                word &= word - 1;
+                const uint32_t d = s0 + (uint32_t)b;
+                if (pos < outCap)
+                    out[pos] = sc.drwId[d];
+                ++pos;
+                if (inViewStage)
+                {
+                    const float4 mn = sc.drwMin[d];
+                    if (__float_as_uint(mn.w) & 1u) // DRAWABLE_GEOMETRY
+                    {
+                        const float4 mx = sc.drwMax[d];
+                        const float cx = (mx.x + mn.x) * 0.5f, cy = (mx.y + mn.y) * 0.5f, cz = (mx.z + mn.z) * 0.5f;
+                        const float ex = (mx.x - mn.x) * 0.5f, ey = (mx.y - mn.y) * 0.5f, ez = (mx.z - mn.z) * 0.5f;
+                        if (ex * ex + ey * ey + ez * ez < 100000000.0f * 100000000.0f) // M_LARGE_VALUE, MathDefs.h:55
+                        {
+                            const float viewCenterZ = vc.viewZ[0] * cx + vc.viewZ[1] * cy + vc.viewZ[2] * cz + vc.viewZ[3];
+                            const float viewEdgeZ = fabsf(vc.viewZ[0]) * ex + fabsf(vc.viewZ[1]) * ey + fabsf(vc.viewZ[2]) * ez;
+                            const float lo = viewCenterZ - viewEdgeZ, hi = viewCenterZ + viewEdgeZ;
+                            zMin = lo < zMin ? lo : zMin;
+                            zMax = hi > zMax ? hi : zMax;
+                        }
+                    }
+                }
+            }
+        }
+        cursor += tot;
+    }
+    if (inViewStage && zRangeAll)
+    {
+        for (int s = 16; s; s >>= 1)
+        {
+            const float a = __shfl_xor_sync(0xffffffffu, zMin, s), b = __shfl_xor_sync(0xffffffffu, zMax, s);
+            zMin = a < zMin ? a : zMin;
+            zMax = b > zMax ? b : zMax;
+        }
+        if (lane == 0)
+        {
+            red[2 * wid] = zMin;
+            red[2 * wid + 1] = zMax;
+        }
+        __syncthreads();
+        if (tid == 0)
+        {
+            for (int w = 1; w < kDenseWarps; ++w)
+            {
+                zMin = red[2 * w] < zMin ? red[2 * w] : zMin;
+                zMax = red[2 * w + 1] > zMax ? red[2 * w + 1] : zMax;
+            }
+            if (zMin == __int_as_float(0x7f800000))
+                zMin = 0.0f; // View.cpp:950-951
+            zRangeAll[2 * v] = zMin;
+            zRangeAll[2 * v + 1] = zMax;
+        }
+    }
+    if (tid == 0)
+    {
+        outCounts[2 * v + 1] = cursor;
+        if (cursor > outCap)
+            atomicOr(flags, kFlagOutOverflow);
+    }
+}
+
+size_t dense_counter_bytes(int numViews, int numOctants)
+{
+    const int aliveWords = (numOctants + 1023) / 1024;
+    return ((size_t)64 + (size_t)numViews * aliveWords) * 4;
+}
+
+static int g_denseGrid = 0;
+
+void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, const DenseDev& dd,
+    cudaStream_t s)
+{
+    if (!numViews)
+        return;
+    if (!g_denseGrid)
+    {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        g_denseGrid = sms * 6;
+    }
+    const int grid = g_denseGrid;
+    // octants the walk never reaches must read as culled; counters, alive bits and the views' query counts start at zero
+    cudaMemsetAsync(octState, 0, (size_t)numViews * dd.stateStride, s);
+    cudaMemsetAsync(dd.ctr, 0, dense_counter_bytes(numViews, sc.numOctants), s);
+    cudaMemsetAsync(outCounts, 0, (size_t)numViews * 8, s);
+    k_dense_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, dd);
+    for (int lv = 1; lv < sc.numLevels; ++lv)
+        k_dense_level<<<grid, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, lv);
+    k_dense_groups<<<grid, kDenseThreads, 0, s>>>(sc, numViews, octState, dd);
+    k_dense_scan<<<(numViews * 32 + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(numViews, dd);
+    k_dense_words<<<grid, kDenseThreads, 0, s>>>(sc, octState, dd);
+    k_dense_frustum<<<grid, kDenseThreads, 0, s>>>(sc, views, stage, outCounts, dd);
+    if (stage >= STAGE_VISIBLE && depth)
+        k_dense_occlusion<<<grid, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, dd);
+    k_dense_emit<<<numViews, kDenseThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd);
+}
+
+int dense_launch_count(const SceneDev& sc)
+{
+    return 7 + (sc.numLevels > 1 ? sc.numLevels - 1 : 0);
+}
+
+void dense_set_heavy_extent(int px)
+{
+    cudaMemcpyToSymbol(g_denseHeavyExtent, &px, sizeof(int));
+}
+
+} // namespace u3d

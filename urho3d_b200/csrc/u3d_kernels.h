@@ -105,11 +105,46 @@ cudaError_t init_tile_kernel();
 void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* depth, int2* mips, const RasterDev& rd, cudaStream_t s);
 void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s);
 
-/// Octree query (+ optional CheckVisibility predicate) for every view.  octState: numViews x numOctants bytes of scratch.
+cudaError_t init_cull_kernels();
+/// Octree query (+ optional CheckVisibility predicate) for every view, one CTA per view.  octState: numViews x stateStride bytes of scratch.
+/// onlyIf != nullptr: the kernel runs only when *onlyIf is non-zero on the device (fallback behind launch_cull_dense); octState is then
+/// not cleared here (what the dense path left in it is what this kernel would write itself).
 void launch_cull(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
-    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
+    unsigned char* octState, int stateStride, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts /* [V][2]: query result size, emitted */,
     float* zRange /* [V][2] minZ, maxZ (STAGE_INVIEW; may be null) */, uint32_t* flags,
-    bool pipelined /* other launches share the GPU: prefer the shape with the best aggregate throughput */, cudaStream_t s);
+    bool pipelined /* other launches share the GPU: prefer the shape with the best aggregate throughput */, const uint32_t* onlyIf, cudaStream_t s);
+
+/// Scratch of the batch-wide cull path (cull_dense.cu).  ctr = counter block: [0..31] queued (view, octant) pairs per octree level,
+/// [32] groups with work, [33] words handed out, [34] overflow -> fall back to launch_cull; the per-view alive bits follow it.
+struct DenseDev
+{
+    uint2* queue;            // (view, octant | inside << 31), level after level
+    uint32_t queueCap;
+    uint32_t* ctr;
+    uint32_t* aliveBits;     // per view: one bit per group of 32 octants that holds a surviving octant with drawables
+    int aliveWords;          // words per view = ceil(numOctants / 1024)
+    uint32_t* groupCount;    // per view and group: result words (32 drawables each) its surviving octants need
+    uint32_t* groupOff;      // exclusive scan of groupCount within the view
+    int groupsPerView;       // ceil(numOctants / 32)
+    uint2* groupList;        // (view, group) of every group with work
+    uint32_t* wordBase;      // per view: first word of its region in the pool
+    uint32_t* viewWords;     // per view: words in use
+    uint32_t* visWord;       // pool: one bit per drawable that is in the result
+    uint32_t* wordSlot;      // pool: DFS slot of a word's bit 0
+    uint32_t* wordMeta;      // pool: view | (valid drawables - 1) << 16 | inside << 21
+    uint32_t* testMask;      // pool: drawables that passed the query and still need the occlusion predicate
+    uint32_t poolCap;
+    int stateStride;         // bytes of octant state per view (groupsPerView * 32)
+};
+size_t dense_counter_bytes(int numViews, int numOctants);
+int dense_launch_count(const SceneDev& sc);
+void dense_set_heavy_extent(int px);
+/// Same results as launch_cull, all views pooled into dense launches (no per-view CTA, no block barriers).  Needs numLevels <= 30.
+/// If a queue or the word pool overflows, ctr[34] is raised on the device and every later kernel of the sequence returns at once:
+/// the caller queues launch_cull(..., onlyIf = ctr + 34) behind it.
+void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
+    unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, const DenseDev& dd,
+    cudaStream_t s);
 
 /// Ray::HitDistance of every drawable a QUERY_RAY / QUERY_RAY_CANDIDATES run emitted (slotOfId: drawable id -> DFS slot).
 void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
