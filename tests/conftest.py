@@ -31,6 +31,9 @@ def gpu_ctx():
     """One device context for the whole GPU test session.  Fails (does not skip) when the CUDA library cannot run."""
     from urho3d_b200 import capi
     ctx = capi.Context(0)
+    for kv in filter(None, os.environ.get("U3D_DEBUG_OPTS", "").split(",")):  # run the suite under a tuning option, e.g. "dense_pool=1"
+        name, val = kv.split("=")
+        capi.debug_set_option(name, int(val))
     yield ctx
     ctx.close()
 

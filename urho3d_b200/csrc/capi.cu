@@ -22,6 +22,7 @@ static int g_laneAreaMax = kLaneAreaMax, g_warpAreaMax = kWarpAreaMax; // tuning
 // 2 = the dense path always.  "dense_queue_cap" / "dense_pool_cap" shrink its scratch (test hook for the on-device fallback).
 static int g_cullDense = 1;
 static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
+static int g_readDenseProf = 0; // "read_dense_prof": u3d_debug_read_cull_prof returns the dense path's timers
 constexpr int kDenseMinViews = 16;
 
 static int fail(int code, const std::string& msg)
@@ -363,7 +364,7 @@ struct DenseScratch
         dev.queue = queue.p;
         dev.queueCap = (uint32_t)queueCap;
         dev.ctr = ctr.p;
-        dev.aliveBits = ctr.p + 64;
+        dev.aliveBits = ctr.p + 128;
         dev.aliveWords = aliveWords;
         dev.groupCount = groupCount.p;
         dev.groupOff = groupOff.p;
@@ -458,6 +459,16 @@ int u3d_debug_set_option(const char* name, int value)
         dense_set_heavy_extent(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "dense_walker") == 0)
+    {
+        dense_set_walker(value);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_pool") == 0)
+    {
+        dense_set_walk_pool(value);
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "dense_queue_cap") == 0)
     {
         g_denseQueueCap = (uint32_t)value;
@@ -483,6 +494,16 @@ int u3d_debug_set_option(const char* name, int value)
         cull_prof_enable(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "read_dense_prof") == 0)
+    {
+        g_readDenseProf = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_prof") == 0)
+    {
+        dense_prof_enable(value);
+        return U3D_OK;
+    }
     return fail(U3D_ERR_INVALID, "u3d_debug_set_option: unknown option");
 }
 
@@ -490,7 +511,10 @@ int u3d_debug_read_cull_prof(unsigned long long* out8)
 {
     if (!out8)
         return fail(U3D_ERR_INVALID, "NULL argument");
-    cull_prof_read(out8);
+    if (g_readDenseProf)
+        dense_prof_read(out8);
+    else
+        cull_prof_read(out8);
     return U3D_OK;
 }
 

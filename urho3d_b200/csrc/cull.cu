@@ -139,7 +139,7 @@ template <int T, int R> __device__ __forceinline__ bool visible_stage_a(const Bu
 #if U3D_WALK_POOL
     if (pool)
     {
-        const bool pv = range_visible_pool(g, depth, mips, r, pooled, sh.wstack[threadIdx.x >> 5], (int)(sizeof(sh.wstack[0]) / sizeof(uint32_t)));
+        const bool pv = range_visible_pool(g, depth, mips, 0, r, pooled, sh.wstack[threadIdx.x >> 5], (int)(sizeof(sh.wstack[0]) / sizeof(uint32_t)));
         if (pooled)
             vis = pv;
     }

@@ -599,9 +599,12 @@ __device__ __forceinline__ uint32_t pack_pool(int box, int lv, int x, int y)
 /// kinds run on dense warps, whereas one walk per lane leaves ~3/4 of the lanes idle.  Entries of boxes that were decided in the
 /// meantime are dropped when popped.  Children that do not fit on the stack are walked by their lane alone.
 /// Requires level < 8 and mip dimensions < 4096 (buffers up to 8192 x 8192).  Must be called by all 32 lanes.
-__device__ __forceinline__ bool range_visible_pool(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r,
+/// Every lane may look into another view's buffer: depthAll / mipAll are the batch's planes, `view` this lane's view index.
+__device__ __forceinline__ bool range_visible_pool(const BufGeom& g, const int* __restrict__ depthAll, const int2* __restrict__ mipAll, int view, const BoxRect& r,
     bool need, uint32_t* wstack, int cap)
 {
+    const int* depth = depthAll + (size_t)view * g.w * g.h;
+    const int2* mips = mipAll + (size_t)view * g.mipTexels;
     const int lane = threadIdx.x & 31;
     const uint32_t lt = (1u << lane) - 1u;
     uint32_t visMask = 0;
@@ -660,13 +663,16 @@ __device__ __forceinline__ bool range_visible_pool(const BufGeom& g, const int* 
         rb.right = __shfl_sync(0xffffffffu, r.right, b);
         rb.bottom = __shfl_sync(0xffffffffu, r.bottom, b);
         rb.z = __shfl_sync(0xffffffffu, r.z, b);
+        const int vb = __shfl_sync(0xffffffffu, view, b);
+        const int* depthB = depthAll + (size_t)vb * g.w * g.h;
+        const int2* mipsB = mipAll + (size_t)vb * g.mipTexels;
         const int lv = (int)((e >> 24) & 7u), x = (int)((e >> 12) & 0xFFFu), y = (int)(e & 0xFFFu);
         int c = 0;
         if (lane < take && !((visMask >> b) & 1u))
         {
-            c = classify_texel(g, mips, rb, lv, x, y);
+            c = classify_texel(g, mipsB, rb, lv, x, y);
             if (c == 2 && lv == 0)
-                c = texel_pixels_visible(g, depth, rb, x, y) ? 1 : 0;
+                c = texel_pixels_visible(g, depthB, rb, x, y) ? 1 : 0;
         }
         visMask |= __reduce_or_sync(0xffffffffu, c == 1 ? (1u << b) : 0u);
         if ((visMask & needMask) == needMask)
@@ -724,7 +730,7 @@ __device__ __forceinline__ bool range_visible_pool(const BufGeom& g, const int* 
                 sub.top = max(rb.top, y << s);
                 sub.right = min(rb.right, ((x + 1) << s) - 1);
                 sub.bottom = min(rb.bottom, ((y + 1) << s) - 1);
-                lonely = range_visible_thread(g, depth, mips, true, sub);
+                lonely = range_visible_thread(g, depthB, mipsB, true, sub);
             }
             visMask |= __reduce_or_sync(0xffffffffu, lonely ? (1u << b) : 0u);
             n += keptEnd;
