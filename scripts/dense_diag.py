@@ -34,8 +34,16 @@ capi.debug_set_option("read_dense_prof", 1)
 capi.debug_set_option("dense_prof", 1)
 b.run(capi.STAGE_VISIBLE, s, part=2); torch.cuda.synchronize()
 p = capi.read_cull_prof().astype(np.float64)
-capi.debug_set_option("dense_prof", 0)
 for k, name in ((0, "level kernels (all levels together)"), (1, "occlusion kernel")):
     t0, t1, busy, n = p[4 * k:4 * k + 4]
     if n:
         print("%-36s span %.3f ms, warps %d, mean busy %.3f ms = %.1f%% of the span" % (name, (t1 - t0) * 1e-6, n, busy / n * 1e-6, 100.0 * busy / n / (t1 - t0)))
+t_first = None
+for lv in range(1, 10):
+    capi.debug_set_option("read_dense_prof", 2 + lv)  # that level's four numbers
+    q = capi.read_cull_prof().astype(np.float64)
+    t0, t1, busy, n = q[:4]
+    if n:
+        t_first = t0 if t_first is None else t_first
+        print("  level %d: starts at %.3f ms, span %.3f ms, warps %d, mean busy %.3f ms (%.0f%%)" % (lv, (t0 - t_first) * 1e-6, (t1 - t0) * 1e-6, n, busy / n * 1e-6, 100.0 * busy / n / (t1 - t0)))
+capi.debug_set_option("dense_prof", 0)

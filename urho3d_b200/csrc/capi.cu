@@ -459,6 +459,16 @@ int u3d_debug_set_option(const char* name, int value)
         dense_set_heavy_extent(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "walk_budget_busy") == 0)
+    {
+        dense_set_walk_budget(value, -1);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "walk_budget_idle") == 0)
+    {
+        dense_set_walk_budget(-1, value);
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "dense_walker") == 0)
     {
         dense_set_walker(value);
@@ -511,7 +521,14 @@ int u3d_debug_read_cull_prof(unsigned long long* out8)
 {
     if (!out8)
         return fail(U3D_ERR_INVALID, "NULL argument");
-    if (g_readDenseProf)
+    if (g_readDenseProf >= 2 && g_readDenseProf < 34)
+    {
+        unsigned long long all[128];
+        dense_prof_read_levels(all); // "read_dense_prof" = 2 + level: that level's four numbers
+        for (int i = 0; i < 8; ++i)
+            out8[i] = i < 4 ? all[4 * (g_readDenseProf - 2) + i] : 0ull;
+    }
+    else if (g_readDenseProf)
         dense_prof_read(out8);
     else
         cull_prof_read(out8);

@@ -33,7 +33,7 @@ __device__ int g_denseWalkPool = 0;     // 1: the boxes of a warp share one texe
 
 // Diagnostic ("cull_prof" option): per kernel family k (0 = levels, 1 = occlusion) [4k] earliest warp start, [4k+1] latest warp end (ns,
 // globaltimer), [4k+2] sum of the warps' busy times, [4k+3] warps.  sum / (warps * (end - start)) = how evenly the warps finish.
-__device__ unsigned long long g_denseProf[8];
+__device__ unsigned long long g_denseProf[8 + 4 * 32]; // [8 + 4 * level ...]: the same four numbers per octree level
 __device__ int g_denseProfOn;
 __device__ __forceinline__ unsigned long long dense_now()
 {
@@ -494,6 +494,7 @@ constexpr int kWalkStack = 64;    // texels per lane: <= 9 to start with, + 3 pe
 struct WalkShared
 {
     uint32_t lt[kDenseWarps][kWalkBuf], rb[kDenseWarps][kWalkBuf], z[kDenseWarps][kWalkBuf], meta[kDenseWarps][kWalkBuf], tag[kDenseWarps][kWalkBuf];
+    uint32_t wstack[kDenseWarps][kDenseWStack];
 };
 
 /// Level of the first grid: one below the level whose texels match the rect's size (so the grid is at most 3 x 3), or the coarsest level
@@ -566,13 +567,16 @@ __device__ __forceinline__ int walk_top(const BufGeom& g, const int2* __restrict
     return mask ? 2 : 0;
 }
 
-/// Tier 2 for one rect: depth-first refinement of the texels in `mask`.
-__device__ __forceinline__ bool walk_deep(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r, uint32_t mask)
+/// Tier 2 for one rect, one lane: depth-first refinement of the texels in `mask`, at most `budget` steps.  Returns 1 = visible,
+/// 0 = nothing visible, 2 = budget spent with `sp` texels left on `stack` (the warp finishes those together, walk_drain).
+__device__ int g_walkBudgetBusy = 96;  // steps a lane walks alone while the launch has plenty of other work ("walk_budget_busy")
+__device__ int g_walkBudgetIdle = 8;   // ... and in launches with little work, where a long walk is what everybody waits for ("walk_budget_idle")
+__device__ __forceinline__ int walk_deep(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r, uint32_t mask,
+    uint32_t* stack, int& sp, int budget)
 {
-    uint32_t stack[kWalkStack];
     const int lv0 = walk_top_level(g, r), s0 = lv0 + 1;
     const int rx0 = r.left >> s0, ry0 = r.top >> s0;
-    int sp = 0;
+    sp = 0;
     if (mask & kWalkBigGrid)
     {
         // the border texels of the first grid (<= 28 of 8 x 8); they are classified again when popped
@@ -584,6 +588,8 @@ __device__ __forceinline__ bool walk_deep(const BufGeom& g, const int* __restric
                 if (!(rIn && ((rx0 + i) << s0) >= r.left && min(((rx0 + i + 1) << s0) - 1, g.w - 1) <= r.right))
                     stack[sp++] = pack_texel(lv0, rx0 + i, ry0 + j);
         }
+        if (sp > budget)
+            return 2; // a long border: straight to the warp
     }
     else
     {
@@ -594,19 +600,21 @@ __device__ __forceinline__ bool walk_deep(const BufGeom& g, const int* __restric
                 if ((mask >> (j * 3 + i)) & 1u)
                     stack[sp++] = pack_texel(lv0, rx0 + i, ry0 + j) | 0x80000000u; // bit 31: known to be mixed and cut by the rect's border
     }
-    while (sp)
+    for (int step = 0; sp; ++step)
     {
+        if (step == budget)
+            return 2;
         const uint32_t e = stack[--sp];
         const int lv = (int)((e >> 27) & 15u), x = (int)((e >> 14) & 0x1FFF), y = (int)(e & 0x3FFF);
         const int c = (e >> 31) ? 2 : classify_texel(g, mips, r, lv, x, y);
         if (c == 1)
-            return true;
+            return 1;
         if (c == 0)
             continue;
         if (lv == 0)
         {
             if (texel_pixels_visible(g, depth, r, x, y))
-                return true;
+                return 1;
         }
         else
         {
@@ -618,7 +626,7 @@ __device__ __forceinline__ bool walk_deep(const BufGeom& g, const int* __restric
                     stack[sp++] = pack_texel(cl, cx, cy);
         }
     }
-    return false;
+    return 0;
 }
 
 /// Tier 1 for one box per lane with `need`: returns the lane's state 0 / 1 (decided) or 2 (undecided, `r` and `mask` valid).
@@ -658,7 +666,7 @@ __device__ __forceinline__ void walk_push(WalkShared& sh, int wid, int& buffered
 /// Tier 2 for up to 32 buffered boxes, one per lane.  Returns true on lanes that held a box (`meta`, `tag` = what walk_push stored), and
 /// the answer in `vis`.
 __device__ __forceinline__ bool walk_drain(const BufGeom& g, const int* __restrict__ depthAll, const int2* __restrict__ mipAll, WalkShared& sh, int wid,
-    int& buffered, uint32_t& meta, uint32_t& tag, bool& vis)
+    int& buffered, uint32_t& meta, uint32_t& tag, bool& vis, int budget)
 {
     const int lane = threadIdx.x & 31;
     const int take = min(buffered, 32);
@@ -666,11 +674,14 @@ __device__ __forceinline__ bool walk_drain(const BufGeom& g, const int* __restri
     const bool had = lane < take;
     vis = false;
     meta = tag = 0;
+    BoxRect r;
+    r.left = r.top = r.right = r.bottom = r.z = 0;
+    uint32_t stack[kWalkStack];
+    int sp = 0, state = 0;
     if (had)
     {
         const int p = buffered + lane;
         const uint32_t a = sh.lt[wid][p], b = sh.rb[wid][p];
-        BoxRect r;
         r.left = (int)(a & 0xFFFFu);
         r.top = (int)(a >> 16);
         r.right = (int)(b & 0xFFFFu);
@@ -679,7 +690,31 @@ __device__ __forceinline__ bool walk_drain(const BufGeom& g, const int* __restri
         meta = sh.meta[wid][p];
         tag = sh.tag[wid][p];
         const uint32_t vv = meta & 0xFFFFu;
-        vis = walk_deep(g, depthAll + (size_t)vv * g.w * g.h, mipAll + (size_t)vv * g.mipTexels, r, (meta >> 16) & 0x3FFu);
+        state = walk_deep(g, depthAll + (size_t)vv * g.w * g.h, mipAll + (size_t)vv * g.mipTexels, r, (meta >> 16) & 0x3FFu, stack, sp, budget);
+        vis = state == 1;
+    }
+    // walks that ran out of their budget (long borders): the warp finishes them one after another, 32 texels per step
+    uint32_t todo = __ballot_sync(0xffffffffu, state == 2);
+    while (todo)
+    {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        __syncwarp();
+        if (lane == src)
+            for (int k = 0; k < sp; ++k)
+                sh.wstack[wid][k] = stack[k];
+        __syncwarp();
+        BoxRect rr;
+        rr.left = __shfl_sync(0xffffffffu, r.left, src);
+        rr.top = __shfl_sync(0xffffffffu, r.top, src);
+        rr.right = __shfl_sync(0xffffffffu, r.right, src);
+        rr.bottom = __shfl_sync(0xffffffffu, r.bottom, src);
+        rr.z = __shfl_sync(0xffffffffu, r.z, src);
+        const uint32_t vv = __shfl_sync(0xffffffffu, meta, src) & 0xFFFFu;
+        const int n = __shfl_sync(0xffffffffu, sp, src);
+        const bool rv = range_visible_warp_from(g, depthAll + (size_t)vv * g.w * g.h, mipAll + (size_t)vv * g.mipTexels, rr, sh.wstack[wid], n, kDenseWStack);
+        if (lane == src)
+            vis = rv;
     }
     __syncwarp();
     return had;
@@ -740,20 +775,21 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_dense_level(SceneDev sc, B
     const bool useMips = mipsValid != 0;
     const uint32_t totalWarps = gridDim.x * kDenseWarps;
     const unsigned long long profT0 = g_denseProfOn ? dense_now() : 0ull;
-    int buffered = 0;
-    // octants whose visibility needs the deeper walk: meta = view | mask << 16 | inside << 26, tag = octant
-    auto drain = [&]() {
-        uint32_t meta, tag;
-        bool vis;
-        const bool had = walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis);
-        level_finalize(sc, dd, stateAll, level, nextBase, had && vis, (int)(meta & 0xFFFFu), (int)tag, (meta >> 26) & 1u);
-    };
     // Upper levels hold few pairs, and their boxes have large screen rects that a warp walks one after another: spread them over all
     // warps of the grid instead of filling a few warps with 32 each.
     const uint32_t per = n >= totalWarps * 32u ? 32u : max(1u, (n + totalWarps - 1u) / totalWarps);
     const uint32_t nSteps = (n + per - 1u) / per;
     // dynamic chunks of 4 steps once there are enough of them; small levels go one step per warp
     const uint32_t kChunk = nSteps >= totalWarps * 8u ? 4u : 1u;
+    const int budget = nSteps >= totalWarps * 4u ? g_walkBudgetBusy : g_walkBudgetIdle;
+    int buffered = 0;
+    // octants whose visibility needs the deeper walk: meta = view | mask << 16 | inside << 26, tag = octant
+    auto drain = [&]() {
+        uint32_t meta, tag;
+        bool vis;
+        const bool had = walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis, budget);
+        level_finalize(sc, dd, stateAll, level, nextBase, had && vis, (int)(meta & 0xFFFFu), (int)tag, (meta >> 26) & 1u);
+    };
     uint32_t* ticket = &dd.ctr[CTR_TICKET_LEVEL0 + level];
     for (uint32_t chunk = next_chunk(ticket); chunk * kChunk < nSteps; chunk = next_chunk(ticket))
     for (uint32_t it = chunk * kChunk; it < min((chunk + 1u) * kChunk, nSteps); ++it)
@@ -805,6 +841,7 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_dense_level(SceneDev sc, B
     if (buffered)
         drain();
     dense_prof_end(0, profT0);
+    dense_prof_end(2 + level, profT0);
 }
 
 /// CheckVisibilityWork's occlusion predicate (View.cpp:177) over the drawables k_dense_frustum left to it.
@@ -821,11 +858,12 @@ __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion
     const uint32_t total = dd.ctr[CTR_POOL];
     const uint32_t totalWarps = gridDim.x * kDenseWarps;
     const unsigned long long profT0 = g_denseProfOn ? dense_now() : 0ull;
+    const int budget = g_walkBudgetBusy;
     int buffered = 0;
     auto drain = [&]() {
         uint32_t meta, tag;
         bool vis;
-        if (walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis) && vis)
+        if (walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis, budget) && vis)
             atomicOr(&dd.visWord[tag], 1u << (meta >> 26));
     };
     constexpr uint32_t kChunk = 1; // blocks of 32 words per ticket
@@ -1078,13 +1116,28 @@ void dense_set_walk_pool(int on)
 void dense_prof_enable(int on)
 {
     cudaMemcpyToSymbol(g_denseProfOn, &on, sizeof(int));
-    unsigned long long init[8] = {~0ull, 0, 0, 0, ~0ull, 0, 0, 0};
+    unsigned long long init[8 + 4 * 32];
+    for (int i = 0; i < 8 + 4 * 32; ++i)
+        init[i] = (i & 3) == 0 ? ~0ull : 0ull;
     cudaMemcpyToSymbol(g_denseProf, init, sizeof(init));
 }
 
 void dense_prof_read(unsigned long long* out8)
 {
     cudaMemcpyFromSymbol(out8, g_denseProf, 8 * sizeof(unsigned long long));
+}
+
+void dense_prof_read_levels(unsigned long long* out128)
+{
+    cudaMemcpyFromSymbol(out128, g_denseProf, 4 * 32 * sizeof(unsigned long long), 8 * sizeof(unsigned long long));
+}
+
+void dense_set_walk_budget(int busy, int idle)
+{
+    if (busy >= 0)
+        cudaMemcpyToSymbol(g_walkBudgetBusy, &busy, sizeof(int));
+    if (idle >= 0)
+        cudaMemcpyToSymbol(g_walkBudgetIdle, &idle, sizeof(int));
 }
 
 void dense_set_walker(int on)

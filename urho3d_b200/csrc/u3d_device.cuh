@@ -468,6 +468,9 @@ __device__ __forceinline__ bool range_visible_thread(const BufGeom& g, const int
     return false;
 }
 
+__device__ __forceinline__ bool range_visible_warp_from(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r,
+    uint32_t* wstack, int n, int cap);
+
 /// Same predicate evaluated by a whole warp for ONE rect (all lanes pass the same r): the pending texels sit on a per-warp stack in
 /// shared memory and are classified 32 at a time, so a box whose border cuts hundreds of mixed texels costs tens of steps instead
 /// of hundreds of dependent loads on one lane.  `wstack` has `cap` entries; if it would overflow, the surplus subtrees are walked
@@ -480,11 +483,20 @@ __device__ __forceinline__ bool range_visible_warp(const BufGeom& g, const int* 
     const int sh0 = top_lv + 1;
     const int rx0 = r.left >> sh0, ry0 = r.top >> sh0;
     const int nx = (r.right >> sh0) - rx0 + 1, ny = (r.bottom >> sh0) - ry0 + 1;
-    int n = nx * ny; // <= 64: the coarsest level is at most 8 x 8 texels, finer start levels give at most 2 x 2
+    const int n = nx * ny; // <= 64: the coarsest level is at most 8 x 8 texels, finer start levels give at most 2 x 2
     __syncwarp();
     for (int i = lane; i < n; i += 32)
         wstack[i] = pack_texel(top_lv, rx0 + i % nx, ry0 + i / nx);
     __syncwarp();
+    return range_visible_warp_from(g, depth, mips, r, wstack, n, cap);
+}
+
+/// The cooperative walk from `n` pending texels already on the warp's stack (an entry with bit 31 set is known to be mixed and cut by
+/// the rect's border: it is refined without being classified again).  Must be called by all 32 lanes with the same arguments.
+__device__ __forceinline__ bool range_visible_warp_from(const BufGeom& g, const int* __restrict__ depth, const int2* __restrict__ mips, const BoxRect& r,
+    uint32_t* wstack, int n, int cap)
+{
+    const int lane = threadIdx.x & 31;
     while (n > 0)
     {
         const int take = min(n, 32);
@@ -494,10 +506,10 @@ __device__ __forceinline__ bool range_visible_warp(const BufGeom& g, const int* 
         if (lane < take)
         {
             e = wstack[n + lane];
-            lv = (int)(e >> 27);
+            lv = (int)((e >> 27) & 15u);
             x = (int)((e >> 14) & 0x1FFF);
             y = (int)(e & 0x3FFF);
-            c = classify_texel(g, mips, r, lv, x, y);
+            c = (e >> 31) ? 2 : classify_texel(g, mips, r, lv, x, y);
             if (c == 2 && lv == 0)
                 c = texel_pixels_visible(g, depth, r, x, y) ? 1 : 0;
         }

@@ -141,8 +141,10 @@ int dense_launch_count(const SceneDev& sc);
 void dense_set_heavy_extent(int px);
 void dense_set_walk_pool(int on);
 void dense_set_walker(int on);
+void dense_set_walk_budget(int busy, int idle);
 void dense_prof_enable(int on);
 void dense_prof_read(unsigned long long* out8);
+void dense_prof_read_levels(unsigned long long* out128);
 /// Same results as launch_cull, all views pooled into dense launches (no per-view CTA, no block barriers).  Needs numLevels <= 30.
 /// If a queue or the word pool overflows, ctr[34] is raised on the device and every later kernel of the sequence returns at once:
 /// the caller queues launch_cull(..., onlyIf = ctr + 34) behind it.
