@@ -228,6 +228,10 @@ U3D_API int u3d_sort_by_key(uint32_t n, float* keys, uint32_t* values);
 U3D_API int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, int width, int height, uint32_t max_views,
     uint32_t out_capacity, uint64_t tri_pool, u3d_batch** out);
 U3D_API void u3d_batch_destroy(u3d_batch* b);
+/* Re-points the batch at another scene of the same context (the scene object is replaced whenever the flattened octree changes:
+ * Octree::InsertDrawable / RemoveDrawable / a move across octants, Octree.cpp:134-190, 440-472).  The batch keeps no pointer into the old
+ * scene afterwards, so that one may be destroyed.  Call before u3d_batch_run; per-view buffers and occluders are kept. */
+U3D_API int u3d_batch_set_scene(u3d_batch* b, u3d_scene* scene);
 /* Host -> device copy of n views (asynchronous on `stream`; the host array is consumed before the call returns). */
 U3D_API int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* stream);
 /* The whole per-view pipeline for the views last set, all on `stream`, no host synchronisation:

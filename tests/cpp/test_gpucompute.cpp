@@ -4,9 +4,11 @@
 // (oracle/u3d_oracle.c, linked as the checker only).  Built and run by tests/test_gpu_cpp_host.py.
 #include "../../urho3d_b200/GPUCompute/GPUCompute.h"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 
 extern "C"
@@ -228,6 +230,51 @@ int main()
     GpuFrustumOctreeQuery everything(result, all);
     octree.GetDrawables(everything);
     EXPECT((int)result.size() == N);
+    // The batched entry point across structural changes of the octree (u3d_batch_set_scene through GpuViewBatch): GpuOctree::Sync replaces
+    // the device scene after an insert / a removal / a move across octants; the batch must follow it.
+    {
+        GpuViewBatch batch(ctx, octree, nullptr, 2, 2, 4, N + 64);
+        u3d_view views[2];
+        std::memset(views, 0, sizeof(views));
+        for (int k = 0; k < 2; ++k)
+        {
+            views[k].view[0] = views[k].view[5] = views[k].view[10] = 1.0f;
+            views[k].projection[0] = views[k].projection[5] = views[k].projection[10] = views[k].projection[15] = 1.0f;
+            std::memcpy(views[k].planes, all, sizeof(all));
+            views[k].drawable_flags = 0xFF;
+            views[k].view_mask = 0xFFFFFFFFu;
+            views[k].query_mode = U3D_QUERY_FRUSTUM;
+        }
+        views[1].planes[3] = -40.0f; // near plane z >= 40: a part of the scene only
+        std::vector<unsigned> ids;
+        EXPECT(batch.CullViews(views, 2, ids, false));
+        EXPECT(batch.Offsets()[1] == (unsigned)N);
+        const unsigned partBefore = batch.Offsets()[2] - batch.Offsets()[1];
+        // insert, move across octants (twice: the last box wins), remove
+        float extra[6] = {10, 0, 60, 11, 1, 61};
+        const unsigned newId = octree.InsertDrawable(extra, 1, 0xFFFFFFFFu, true, false);
+        float far1[6] = {-70, 0, -70, -69, 1, -69}, far2[6] = {70, 0, 70, 71, 1, 71};
+        octree.UpdateDrawable(5, far1);
+        octree.UpdateDrawable(5, far2);
+        octree.RemoveDrawable(7);
+        EXPECT(batch.CullViews(views, 2, ids, false));
+        EXPECT(batch.Offsets()[1] == (unsigned)N); // + 1 inserted - 1 removed
+        std::vector<unsigned> single;
+        GpuFrustumOctreeQuery q0(single, views[0].planes), q1(single, views[1].planes);
+        octree.GetDrawables(q0);
+        EXPECT(single.size() == batch.Offsets()[1] && std::equal(single.begin(), single.end(), ids.begin()));
+        octree.GetDrawables(q1);
+        EXPECT(single.size() == batch.Offsets()[2] - batch.Offsets()[1] && std::equal(single.begin(), single.end(), ids.begin() + batch.Offsets()[1]));
+        bool sawNew = false, saw5 = false, saw7 = false;
+        for (unsigned i = batch.Offsets()[1]; i < batch.Offsets()[2]; ++i)
+        {
+            sawNew |= ids[i] == newId;
+            saw5 |= ids[i] == 5;
+            saw7 |= ids[i] == 7;
+        }
+        EXPECT(sawNew && saw5 && !saw7);
+        std::printf("batch across structural changes: %u -> %u drawables behind z = 40\n", partBefore, batch.Offsets()[2] - batch.Offsets()[1]);
+    }
     orc_ob_destroy(ob);
     std::printf("OK\n");
     return 0;

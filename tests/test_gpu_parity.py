@@ -574,6 +574,73 @@ def test_incremental_box_updates(gpu_ctx):
         o.close()
 
 
+def test_update_boxes_with_duplicate_ids_keeps_the_last_box(gpu_ctx):
+    """A drawable that moved twice before the upload appears twice in u3d_scene_update_boxes: the last box must win (as in the host
+    tree), whatever order the device threads run in."""
+    sc = helpers.small_scene(n=4000, k=4, extent=100.0, seed=43)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    rs = np.random.RandomState(4)
+    boxes = sc.aabb.copy()
+    ids, staged = [], []
+    for i in rs.choice(sc.n, size=600, replace=False):
+        first = boxes[i] + np.tile(rs.uniform(-0.2, 0.2, 3), 2).astype(np.float32)
+        second = boxes[i] + np.tile(rs.uniform(-0.2, 0.2, 3), 2).astype(np.float32)
+        if tree.update(int(i), first) and tree.update(int(i), second):
+            ids += [int(i), int(i)]
+            staged += [first, second]
+            boxes[i] = second
+        else:
+            tree.update(int(i), boxes[i])
+    flat2 = tree.flatten()
+    if not all(np.array_equal(flat[k], flat2[k]) for k in ("parent", "first", "count", "order")):
+        pytest.skip("layout changed while restoring a moved drawable")
+    assert len(ids) > 600
+    # interleave so that the two entries of a drawable are far apart in the launch
+    perm = np.concatenate([np.arange(0, len(ids), 2), np.arange(1, len(ids), 2)])
+    gs.update_boxes(np.array(ids)[perm], np.array(staged, np.float32)[perm])
+    otree, _ = helpers.make_oracle(scenes_with_boxes(sc, boxes), flat2, 8, 8)
+    for v in scenes.agent_cameras(6, 100.0, 256, 160, seed=5):
+        a, _ = gs.query(v.planes, None, mode=capi.QUERY_FRUSTUM)
+        assert np.array_equal(a, otree.query(0, v.planes, None))
+    for o in (gs, tree):
+        o.close()
+
+
+def test_batch_follows_the_scene_after_structural_changes(gpu_ctx):
+    """u3d_batch_set_scene: after inserts / removals / moves across octants the flattened scene is a new object (more octants, other
+    order); a batch created before must run against it, not against the destroyed one."""
+    sc = helpers.small_scene(n=3000, k=4, extent=60.0, seed=45)
+    tree = capi.Octree(sc.octree_min, sc.octree_max, sc.octree_levels)
+    half = sc.n // 2
+    tree.add(sc.aabb[:half], sc.flags[:half], sc.view_mask[:half], sc.occludee[:half], sc.cast_shadows[:half])
+    gs = capi.GpuScene(gpu_ctx, octree=tree)
+    views = scenes.agent_cameras(20, 60.0, 256, 160, seed=6)
+    packed = capi.pack_views(views, query_mode=capi.QUERY_FRUSTUM)
+    batch = capi.Batch(gpu_ctx, gs, None, 2, 2, len(views), sc.n)
+    c0, o0, i0 = batch.cull_views(packed, capi.STAGE_QUERY)
+    # structural change: the other half arrives, some drawables leave, some jump across the world
+    tree.add(sc.aabb[half:], sc.flags[half:], sc.view_mask[half:], sc.occludee[half:], sc.cast_shadows[half:])
+    boxes = sc.aabb.copy()
+    for i in range(0, half, 7):
+        tree.remove(i)
+    for i in range(3, half, 11):
+        if i % 7:
+            boxes[i] = boxes[i] + np.tile(np.float32([35.0, 0.0, -28.0]), 2)
+            tree.update(i, boxes[i])
+    flat = tree.flatten()
+    gs2 = capi.GpuScene(gpu_ctx, octree=tree)
+    gs.close()  # the old scene is gone, as after GpuOctree::Sync
+    batch.set_scene(gs2)
+    c1, o1, i1 = batch.cull_views(packed, capi.STAGE_QUERY)
+    otree, _ = helpers.make_oracle(scenes_with_boxes(sc, boxes), flat, 8, 8)
+    for k, v in enumerate(views):
+        want = otree.query(0, v.planes, None)
+        assert np.array_equal(i1[o1[k]:o1[k + 1]], want), "view %d" % k
+    assert not np.array_equal(c0, c1)
+    for o in (batch, gs2, tree):
+        o.close()
+
+
 def scenes_with_boxes(sc, boxes):
     import copy
     c = copy.copy(sc)

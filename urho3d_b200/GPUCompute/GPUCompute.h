@@ -316,7 +316,8 @@ public:
     {
         if (u3d_octree_update(tree_, id, worldBoxMinMax6) == 1 && !dirty_)
         {
-            // stayed in its octant: only its box has to be refreshed in HBM
+            // stayed in its octant: only its box has to be refreshed in HBM (several moves of one drawable before the next Sync: the
+            // last box wins -- u3d_scene_update_boxes folds duplicate ids in call order)
             pendingIds_.push_back(id);
             pendingBoxes_.insert(pendingBoxes_.end(), worldBoxMinMax6, worldBoxMinMax6 + 6);
         }
@@ -349,6 +350,7 @@ public:
         Check(u3d_scene_create(ctx_.Handle(), tree_, &scene_), "u3d_scene_create");
         u3d_scene_counts(scene_, &numOctants_, &numDrawables_);
         dirty_ = false;
+        ++generation_; // every holder of the old u3d_scene* (GpuViewBatch) must rebind: that object is gone
     }
     /// Octree::GetDrawables(OctreeQuery&) (Octree.cpp:495-499): clears query.result_, then fills it in pre-order DFS order.
     void GetDrawables(GpuOctreeQuery& query)
@@ -388,6 +390,8 @@ public:
         return scene_;
     }
     u3d_octree* Tree() const { return tree_; }
+    /// Bumped whenever Sync() replaced the device scene (structural change of the octree).
+    unsigned long long Generation() const { return generation_; }
 
 private:
     void RaycastImpl(GpuRayOctreeQuery& query, bool single)
@@ -408,6 +412,7 @@ private:
     u3d_scene* scene_{};
     uint32_t numOctants_{}, numDrawables_{};
     bool dirty_{true};
+    unsigned long long generation_{0};
     std::vector<uint32_t> pendingIds_;
     std::vector<float> pendingBoxes_;
 };
@@ -418,8 +423,10 @@ class GpuViewBatch
 public:
     GpuViewBatch(GpuContext& ctx, GpuOctree& octree, u3d_occluders* occluders, int width, int height, unsigned maxViews, unsigned outCapacity,
         unsigned long long triPool = 0)
+        : octree_(octree)
     {
         Check(u3d_batch_create(ctx.Handle(), octree.Scene(), occluders, width, height, maxViews, outCapacity, triPool, &batch_), "u3d_batch_create");
+        generation_ = octree.Generation();
         counts_.resize((size_t)maxViews * 2);
         offsets_.resize((size_t)maxViews + 1);
     }
@@ -431,6 +438,8 @@ public:
     bool CullViews(const u3d_view* views, unsigned count, std::vector<unsigned>& ids, bool visibilityPredicate = true)
     {
         const int stage = visibilityPredicate ? U3D_STAGE_VISIBLE : U3D_STAGE_QUERY;
+        if (!Rebind())
+            return false;
         if (u3d_batch_set_views(batch_, views, count, nullptr) < 0)
             return false;
         if (policy_ && camera3_.size() < 3 * (size_t)count)
@@ -465,6 +474,8 @@ public:
     bool ProcessShadowCasters(const u3d_shadow_split* splits, const float* mainView12, const float* mainCameraPos3, bool mainOrthographic,
         const unsigned char* inView, unsigned numInView, unsigned count, std::vector<unsigned>& ids)
     {
+        if (!Rebind())
+            return false;
         if (u3d_batch_process_shadow_casters(batch_, splits, mainView12, mainCameraPos3, mainOrthographic ? 1 : 0, inView, numInView, nullptr) < 0 ||
             u3d_batch_read_counts(batch_, counts_.data(), nullptr) < 0)
             return false;
@@ -482,6 +493,22 @@ public:
     u3d_batch* Handle() const { return batch_; }
 
 private:
+    /// GpuOctree::Sync() replaces its u3d_scene after every structural change (insert / remove / a move across octants); the batch is then
+    /// re-pointed at the new one before it runs, instead of launching kernels on the freed scene.
+    bool Rebind()
+    {
+        u3d_scene* scene = octree_.Scene(); // syncs
+        if (generation_ != octree_.Generation())
+        {
+            if (u3d_batch_set_scene(batch_, scene) < 0)
+                return false;
+            generation_ = octree_.Generation();
+        }
+        return true;
+    }
+
+    GpuOctree& octree_;
+    unsigned long long generation_{};
     u3d_batch* batch_{};
     std::vector<unsigned> counts_, offsets_;
     bool policy_{};

@@ -97,6 +97,7 @@ SIGNATURES = {
     "u3d_octree_query": (C.c_int, [_vp, _vp, _f, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _u32, C.c_uint32, _u32, _u32]),
     "u3d_batch_create": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_uint64, C.POINTER(_vp)]),
     "u3d_batch_destroy": (None, [_vp]),
+    "u3d_batch_set_scene": (C.c_int, [_vp, _vp]),
     "u3d_batch_set_views": (C.c_int, [_vp, _vp, C.c_uint32, _vp]),
     "u3d_batch_run": (C.c_int, [_vp, C.c_int, _vp]),
     "u3d_batch_run_part": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
@@ -509,6 +510,10 @@ class Batch:
         self.max_views = max_views
         self.out_capacity = out_capacity
         self.n = 0
+
+    def set_scene(self, scene):
+        """Re-point the batch at another GpuScene (after the octree's flattened layout changed)."""
+        _chk(lib().u3d_batch_set_scene(self.h, scene.h))
 
     def set_views(self, packed, stream=None):
         packed = np.ascontiguousarray(packed)

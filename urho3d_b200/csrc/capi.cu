@@ -218,7 +218,16 @@ struct ViewSet
     DevBuf<ViewConst> views;
     DevBuf<int> depth;
     DevBuf<int2> mips;
-    DevBuf<uint32_t> itemCount, submitted, triCap, triCount, drawnSources, flags;
+    // Counters that start every run at zero live in ONE block (one cudaMemsetAsync per run instead of a dozen): the members below point into it.
+    struct Sub
+    {
+        uint32_t* p{};
+        size_t n{};
+    };
+    DevBuf<uint32_t> zeroBlock;
+    size_t zeroWords{};
+    Sub itemCount, submitted, triCount, drawnSources, flags, binCount, irrTotal, irrOfView, clipCount;
+    DevBuf<uint32_t> triCap;
     DevBuf<uint64_t> triBase;
     DevBuf<TriSetup> pool;
     DevBuf<DrawItem> items;
@@ -226,12 +235,12 @@ struct ViewSet
     // tile path
     TileGeom tg{};
     bool useTiles{};
-    DevBuf<uint32_t> binIdx, binCount, irrTotal, irrOfView;
+    DevBuf<uint32_t> binIdx;
     DevBuf<unsigned long long> irrList;
     uint32_t irrCap{};
     DevBuf<float> clipQueue;
-    DevBuf<uint32_t> clipCount;
     uint32_t clipCap{};
+    cudaError_t clear_counters(cudaStream_t st) { return cudaMemsetAsync(zeroBlock.p, 0, zeroWords * 4, st); }
     RasterDev raster_dev(bool tiles, int writeMips)
     {
         RasterDev rd{};
@@ -268,27 +277,34 @@ struct ViewSet
         {
             irrCap = 1u << 20;
             CU_CHECK(binIdx.ensure(std::max<uint64_t>(poolTris, 1) * tg.numTiles * kNumCls));
-            CU_CHECK(binCount.ensure((size_t)nviews * tg.numTiles * kNumCls));
             CU_CHECK(irrList.ensure(irrCap));
-            CU_CHECK(irrTotal.ensure(1));
-            CU_CHECK(irrOfView.ensure(nviews));
+        }
+        {
+            const size_t nBins = useTiles ? (size_t)nviews * tg.numTiles * kNumCls : 0;
+            zeroWords = 4 + 5 * (size_t)nviews + nBins;
+            CU_CHECK(zeroBlock.ensure(zeroWords));
+            uint32_t* q = zeroBlock.p;
+            flags = Sub{q, 1};
+            clipCount = Sub{q + 1, 1};
+            irrTotal = Sub{q + 2, 1};
+            q += 4;
+            itemCount = Sub{q, nviews};
+            submitted = Sub{q + nviews, nviews};
+            triCount = Sub{q + 2 * (size_t)nviews, nviews};
+            drawnSources = Sub{q + 3 * (size_t)nviews, nviews};
+            irrOfView = Sub{q + 4 * (size_t)nviews, nviews};
+            binCount = Sub{q + 5 * (size_t)nviews, nBins};
         }
         CU_CHECK(views.ensure(nviews));
         CU_CHECK(depth.ensure((size_t)nviews * w * h));
         CU_CHECK(mips.ensure((size_t)nviews * g.mipTexels));
-        CU_CHECK(itemCount.ensure(nviews));
-        CU_CHECK(submitted.ensure(nviews));
         CU_CHECK(triCap.ensure(nviews));
-        CU_CHECK(triCount.ensure(nviews));
-        CU_CHECK(drawnSources.ensure(nviews));
         CU_CHECK(triBase.ensure(nviews));
-        CU_CHECK(flags.ensure(1));
         CU_CHECK(items.ensure((size_t)nviews * std::max<uint32_t>(itemCap, 1)));
         CU_CHECK(pool.ensure(std::max<uint64_t>(poolTris, 1)));
         // triangles that cross a clip plane are a fraction of the submitted ones; an overflow is reported, not dropped silently
         clipCap = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(poolTris / 4, 4096), 0x7FFFFFFFu);
         CU_CHECK(clipQueue.ensure((size_t)clipCap * kClipEntryFloats));
-        CU_CHECK(clipCount.ensure(1));
         return 0;
     }
 };
@@ -326,7 +342,7 @@ struct u3d_ob
     DevBuf<unsigned char> visOut;
     // query scratch
     DevBuf<unsigned char> octState;
-    DevBuf<uint32_t> outIdx, outCounts;
+    DevBuf<uint32_t> outIdx, outCounts, queryFlags;
 };
 
 /// Scratch of the batch-wide cull path (cull_dense.cu); sized from the scene and the batch's view capacity, grow-only.
@@ -397,6 +413,13 @@ struct u3d_batch
     DevBuf<float> zRange; // per view (minZ, maxZ)
     PinnedBuf<ViewConst> hostViews;
     PinnedBuf<uint32_t> hostCounts;
+    cudaEvent_t viewsCopied{};        // the last host -> device copy out of hostViews (whatever stream it ran on)
+    bool haveViewsEvent{};
+    // u3d_batch_cull_views: flags | counts | packed offsets leave the device as ONE block, and the packed ids are copied in the same
+    // breath up to the size the previous call needed (+ 1/8), so that the call has a single synchronisation in the steady state
+    DevBuf<uint32_t> hdr;
+    PinnedBuf<uint32_t> hostHdr;
+    uint64_t idsGuess{};
     uint32_t lastLaunches{};
     bool hasBuffers{};
     cudaEvent_t ev[U3D_NUM_PHASES + 1]{};
@@ -417,6 +440,8 @@ struct u3d_batch
         if (haveEvents)
             for (auto& e : ev)
                 cudaEventDestroy(e);
+        if (haveViewsEvent)
+            cudaEventDestroy(viewsCopied);
     }
 };
 
@@ -839,7 +864,11 @@ int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
     {
         rc = u3d_scene_set_draw_distances(*out, (uint32_t)n, dd.data());
         if (rc < 0)
+        {
+            u3d_scene_destroy(*out); // never hand out a half-initialised scene
+            *out = nullptr;
             return rc;
+        }
     }
     std::vector<uint8_t> occl(std::max<size_t>(n, 1), 0);
     any = false;
@@ -848,7 +877,13 @@ int u3d_scene_create(u3d_ctx* ctx, const u3d_octree* t, u3d_scene** out)
         occl[i] = dr[i].occluder;
         any |= dr[i].occluder;
     }
-    return any ? u3d_scene_set_occluder_flags(*out, (uint32_t)n, occl.data()) : U3D_OK;
+    rc = any ? u3d_scene_set_occluder_flags(*out, (uint32_t)n, occl.data()) : U3D_OK;
+    if (rc < 0)
+    {
+        u3d_scene_destroy(*out);
+        *out = nullptr;
+    }
+    return rc;
 }
 
 int u3d_scene_set_occluder_flags(u3d_scene* s, uint32_t n, const uint8_t* is_occluder)
@@ -892,17 +927,33 @@ int u3d_scene_update_boxes(u3d_scene* s, uint32_t n, const uint32_t* ids, const 
         return U3D_OK;
     CU_CHECK(cudaSetDevice(s->ctx->device));
     cudaStream_t st = s->ctx->pick(stream);
-    std::vector<uint32_t> slots(n);
+    // A drawable may appear several times (it moved more than once since the last upload): the LAST box wins, as in the host tree.  The
+    // kernel writes one slot per thread without ordering, so duplicates are folded here.
+    std::vector<uint32_t> slots;
+    std::vector<float> boxes;
+    slots.reserve(n);
+    boxes.reserve((size_t)n * 6);
+    std::map<uint32_t, uint32_t> where; // slot -> position in `slots`
     for (uint32_t i = 0; i < n; ++i)
     {
         if (ids[i] >= s->slotOfId.size() || s->slotOfId[ids[i]] == 0xFFFFFFFFu)
             return fail(U3D_ERR_INVALID, "u3d_scene_update_boxes: drawable id is not in the scene");
-        slots[i] = s->slotOfId[ids[i]];
+        const uint32_t slot = s->slotOfId[ids[i]];
+        auto it = where.find(slot);
+        if (it == where.end())
+        {
+            where.emplace(slot, (uint32_t)slots.size());
+            slots.push_back(slot);
+            boxes.insert(boxes.end(), aabb6 + 6 * (size_t)i, aabb6 + 6 * (size_t)i + 6);
+        }
+        else
+            std::memcpy(&boxes[6 * (size_t)it->second], aabb6 + 6 * (size_t)i, 24);
     }
+    n = (uint32_t)slots.size();
     CU_CHECK(s->updSlots.ensure(n));
     CU_CHECK(s->updBoxes.ensure((size_t)n * 6));
     CU_CHECK(cudaMemcpyAsync(s->updSlots.p, slots.data(), (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemcpyAsync(s->updBoxes.p, aabb6, (size_t)n * 24, cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaMemcpyAsync(s->updBoxes.p, boxes.data(), (size_t)n * 24, cudaMemcpyHostToDevice, st));
     launch_update_boxes(s->drwMin.p, s->drwMax.p, s->updSlots.p, s->updBoxes.p, n, st);
     CU_CHECK(cudaGetLastError());
     CU_CHECK(cudaStreamSynchronize(st)); // host staging vectors go out of scope
@@ -1354,13 +1405,10 @@ int u3d_ob_draw_triangles(u3d_ob* ob)
         const uint32_t nItems = (uint32_t)items.size();
         const uint32_t cap = (uint32_t)std::min<uint64_t>(poolTris, 0xFFFFFFFFu);
         const uint64_t zero64 = 0;
+        CU_CHECK(vs.clear_counters(st));
         CU_CHECK(cudaMemcpyAsync(vs.itemCount.p, &nItems, 4, cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaMemcpyAsync(vs.triCap.p, &cap, 4, cudaMemcpyHostToDevice, st));
         CU_CHECK(cudaMemcpyAsync(vs.triBase.p, &zero64, 8, cudaMemcpyHostToDevice, st));
-        CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.clipCount.p, 0, 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
         int rc = ob_upload_view(ob); // cullMode_ is read at draw time (OB.cpp:634)
         if (rc < 0)
             return rc;
@@ -1509,15 +1557,15 @@ int u3d_octree_query(u3d_scene* scene, u3d_ob* ob, const float planes24[24], uin
     vc.useOcclusion = useOb ? 1 : 0;
     BufGeom g = useOb ? ob->vs.g : make_geom(2, 2);
     CU_CHECK(holder->vs.views.ensure(1));
-    CU_CHECK(holder->vs.flags.ensure(1));
+    CU_CHECK(holder->queryFlags.ensure(1));
     CU_CHECK(holder->octState.ensure((size_t)scene->dev.numOctants));
     CU_CHECK(holder->outIdx.ensure(std::max<uint32_t>(capacity, 1)));
     CU_CHECK(holder->outCounts.ensure(2));
     CU_CHECK(cudaMemcpyAsync(holder->vs.views.p, &vc, sizeof(vc), cudaMemcpyHostToDevice, st));
-    CU_CHECK(cudaMemsetAsync(holder->vs.flags.p, 0, 4, st));
+    CU_CHECK(cudaMemsetAsync(holder->queryFlags.p, 0, 4, st));
     launch_cull(scene->dev, g, holder->vs.views.p, 1, useOb ? ob->vs.depth.p : nullptr, useOb ? ob->vs.mips.p : nullptr,
         useOb && !ob->hierarchyDirty ? 1 : 0, holder->octState.p, scene->dev.numOctants, stage, holder->outIdx.p, capacity, holder->outCounts.p, nullptr,
-        holder->vs.flags.p, false, nullptr, st);
+        holder->queryFlags.p, false, nullptr, st);
     CU_CHECK(cudaGetLastError());
     uint32_t counts[2] = {0, 0};
     CU_CHECK(cudaMemcpyAsync(counts, holder->outCounts.p, 8, cudaMemcpyDeviceToHost, st));
@@ -1945,6 +1993,19 @@ int u3d_batch_create(u3d_ctx* ctx, u3d_scene* scene, u3d_occluders* occluders, i
     return U3D_OK;
 }
 
+int u3d_batch_set_scene(u3d_batch* b, u3d_scene* scene)
+{
+    if (!b || !scene)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_scene: NULL argument");
+    if (scene->ctx != b->ctx)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_scene: the scene belongs to another context");
+    CU_CHECK(cudaSetDevice(b->ctx->device));
+    b->scene = scene;
+    // the per-view octant states (and, at the next run, the dense path's scratch) follow the new scene's octant count
+    CU_CHECK(b->octState.ensure((size_t)b->vs.maxViews * ((scene->dev.numOctants + 31) / 32 * 32)));
+    return U3D_OK;
+}
+
 void u3d_batch_destroy(u3d_batch* b)
 {
     if (!b)
@@ -1961,8 +2022,14 @@ int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* s
         return fail(U3D_ERR_CAPACITY, "u3d_batch_set_views: more views than max_views");
     CU_CHECK(cudaSetDevice(b->ctx->device));
     cudaStream_t st = b->ctx->pick(stream);
-    // the pinned staging array may still be in flight from the previous call on this stream
-    CU_CHECK(cudaStreamSynchronize(st));
+    // the pinned staging array may still be in flight from the previous call (on this or another stream)
+    if (!b->haveViewsEvent)
+    {
+        CU_CHECK(cudaEventCreateWithFlags(&b->viewsCopied, cudaEventDisableTiming));
+        b->haveViewsEvent = true;
+    }
+    else
+        CU_CHECK(cudaEventSynchronize(b->viewsCopied));
     for (uint32_t i = 0; i < n; ++i)
     {
         const u3d_view& v = views[i];
@@ -1989,6 +2056,7 @@ int u3d_batch_set_views(u3d_batch* b, const u3d_view* views, uint32_t n, void* s
     b->numViews = n;
     if (n)
         CU_CHECK(cudaMemcpyAsync(b->vs.views.p, b->hostViews.p, (size_t)n * sizeof(ViewConst), cudaMemcpyHostToDevice, st));
+    CU_CHECK(cudaEventRecord(b->viewsCopied, st));
     return U3D_OK;
 }
 
@@ -2008,22 +2076,11 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
     auto mark = [&](int phase) -> cudaError_t { return timed ? cudaEventRecord(b->ev[phase], st) : cudaSuccess; };
     CU_CHECK(mark(0));
     if (part != 2)
-        CU_CHECK(cudaMemsetAsync(vs.flags.p, 0, 4, st));
+        CU_CHECK(vs.clear_counters(st)); // flags, per-view triangle / item counters, tile bins: one block, one memset
     if (b->hasBuffers && part != 2)
     {
         const u3d_occluders* oc = b->occ;
-        CU_CHECK(cudaMemsetAsync(vs.itemCount.p, 0, (size_t)V * 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.submitted.p, 0, (size_t)V * 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.triCount.p, 0, (size_t)V * 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.drawnSources.p, 0, (size_t)V * 4, st));
-        CU_CHECK(cudaMemsetAsync(vs.clipCount.p, 0, 4, st));
-        if (vs.useTiles)
-        {
-            CU_CHECK(cudaMemsetAsync(vs.binCount.p, 0, (size_t)V * vs.tg.numTiles * kNumCls * 4, st));
-            CU_CHECK(cudaMemsetAsync(vs.irrTotal.p, 0, 4, st));
-            CU_CHECK(cudaMemsetAsync(vs.irrOfView.p, 0, (size_t)V * 4, st));
-        }
-        else
+        if (!vs.useTiles)
         {
             launch_clear(vs.depth.p, (size_t)V * vs.g.w * vs.g.h, st);
             b->lastLaunches += 1;
@@ -2147,22 +2204,14 @@ int u3d_batch_run_timed(u3d_batch* b, int stage, void* stream, float* phase_ms)
 
 int u3d_batch_run(u3d_batch* b, int stage, void* stream) { return u3d_batch_run_part(b, 0, stage, stream); }
 
+static int flags_to_error(uint32_t flags);
+
 static int batch_check_flags(u3d_batch* b, cudaStream_t st)
 {
     uint32_t flags = 0;
     CU_CHECK(cudaMemcpyAsync(&flags, b->vs.flags.p, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
-    if (flags & kFlagClipOverflow)
-        return fail(U3D_ERR_CAPACITY, "clipper queue too small for this batch: recreate the batch with a larger tri_pool");
-    if (flags & kFlagIrrOverflow)
-        return fail(U3D_ERR_CAPACITY, "more than 2^20 irregular triangles in one batch (degenerate input)");
-    if (flags & (kFlagTriOverflow | kFlagPoolOverflow))
-        return fail(U3D_ERR_CAPACITY, "triangle pool too small for this batch: recreate the batch with a larger tri_pool");
-    if (flags & kFlagOutOverflow)
-        return fail(U3D_ERR_CAPACITY, "a view produced more results than out_capacity");
-    if (flags & kFlagRankOverflow)
-        return fail(U3D_ERR_CAPACITY, "a view has more than 4096 occluder candidates after the size threshold (ranked selection)");
-    return U3D_OK;
+    return flags_to_error(flags);
 }
 
 int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream)
@@ -2219,6 +2268,67 @@ __global__ void k_pack_offsets(int numViews, const uint32_t* __restrict__ counts
     }
     if (threadIdx.x == 0)
         offsets[numViews] = carry;
+}
+
+/// k_pack_offsets + a copy of everything the host wants to see first, as one block: hdr = flags | counts[V][2] | offsets[V + 1].
+__global__ void k_pack_header(int numViews, const uint32_t* __restrict__ counts, uint32_t cap, uint32_t* __restrict__ offsets, const uint32_t* __restrict__ flags,
+    uint32_t* __restrict__ hdr)
+{
+    __shared__ uint32_t carry;
+    __shared__ uint32_t warpSum[32];
+    if (threadIdx.x == 0)
+    {
+        carry = 0;
+        hdr[0] = *flags;
+    }
+    __syncthreads();
+    uint32_t* hCounts = hdr + 1;
+    uint32_t* hOffsets = hdr + 1 + 2 * (size_t)numViews;
+    for (int base = 0; base < numViews; base += blockDim.x)
+    {
+        const int v = base + threadIdx.x;
+        uint32_t c = 0;
+        if (v < numViews)
+        {
+            const uint32_t q = counts[2 * v], e = counts[2 * v + 1];
+            hCounts[2 * v] = q;
+            hCounts[2 * v + 1] = e;
+            c = min(e, cap);
+        }
+        uint32_t x = c;
+        const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o)
+                x += y;
+        }
+        if (lane == 31)
+            warpSum[wid] = x;
+        __syncthreads();
+        uint32_t pre = 0, tot = 0;
+        for (int i = 0; i < (int)(blockDim.x >> 5); ++i)
+        {
+            if (i < wid)
+                pre += warpSum[i];
+            tot += warpSum[i];
+        }
+        if (v < numViews)
+        {
+            const uint32_t off = carry + pre + x - c;
+            offsets[v] = off;
+            hOffsets[v] = off;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0)
+            carry += tot;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0)
+    {
+        offsets[numViews] = carry;
+        hOffsets[numViews] = carry;
+    }
 }
 
 __global__ void k_pack_ids(const uint32_t* __restrict__ counts, uint32_t cap, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ids,
@@ -2459,10 +2569,18 @@ int u3d_gather_create(u3d_ctx* ctx, int world, int rank, uint32_t views_per_rank
     g->lay.cap = std::max<uint64_t>(ids_capacity_per_rank, 1);
     g->lay.world = world;
     CU_CHECK(cudaMalloc((void**)&g->block, g->lay.bytes()));
-    CU_CHECK(cudaMemset(g->block, 0, g->lay.idsOff()));
-    CU_CHECK(g->doneCounter.ensure(1));
-    CU_CHECK(cudaMemset(g->doneCounter.p, 0, 4));
-    CU_CHECK(cudaDeviceSynchronize());
+    cudaError_t ge = cudaMemset(g->block, 0, g->lay.idsOff());
+    if (ge == cudaSuccess)
+        ge = g->doneCounter.ensure(1);
+    if (ge == cudaSuccess)
+        ge = cudaMemset(g->doneCounter.p, 0, 4);
+    if (ge == cudaSuccess)
+        ge = cudaDeviceSynchronize();
+    if (ge != cudaSuccess)
+    {
+        cudaFree(g->block); // u3d_gather has no destructor of its own
+        return fail(U3D_ERR_CUDA, std::string("u3d_gather_create: ") + cudaGetErrorString(ge));
+    }
     g->peers.block[rank] = g->block;
     *out = g.release();
     return U3D_OK;
@@ -2651,10 +2769,10 @@ int u3d_batch_set_occluder_policy(u3d_batch* b, int enable, float size_threshold
 {
     if (!b || (enable && !camera3 && b->numViews))
         return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: NULL argument");
-    if (!b->hasBuffers)
-        return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: the batch has no occluders");
     if (enable < 0 || enable > 2)
         return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: enable must be 0, 1 or 2");
+    if (enable && !b->hasBuffers)
+        return fail(U3D_ERR_INVALID, "u3d_batch_set_occluder_policy: the batch has no occluders");
     b->rankOccluders = enable != 0;
     b->serialOccluders = enable == 2;
     if (!enable)
@@ -2836,6 +2954,21 @@ int u3d_batch_read_setup_records(u3d_batch* b, uint32_t view, int32_t* out16, ui
     return U3D_OK;
 }
 
+static int flags_to_error(uint32_t flags)
+{
+    if (flags & kFlagClipOverflow)
+        return fail(U3D_ERR_CAPACITY, "clipper queue too small for this batch: recreate the batch with a larger tri_pool");
+    if (flags & kFlagIrrOverflow)
+        return fail(U3D_ERR_CAPACITY, "more than 2^20 irregular triangles in one batch (degenerate input)");
+    if (flags & (kFlagTriOverflow | kFlagPoolOverflow))
+        return fail(U3D_ERR_CAPACITY, "triangle pool too small for this batch: recreate the batch with a larger tri_pool");
+    if (flags & kFlagOutOverflow)
+        return fail(U3D_ERR_CAPACITY, "a view produced more results than out_capacity");
+    if (flags & kFlagRankOverflow)
+        return fail(U3D_ERR_CAPACITY, "a view has more than 4096 occluder candidates after the size threshold (ranked selection)");
+    return U3D_OK;
+}
+
 int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int stage, uint32_t* counts, uint32_t* offsets, uint32_t* ids, uint64_t capacity,
     void* stream)
 {
@@ -2845,15 +2978,53 @@ int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int st
     rc = u3d_batch_run(b, stage, stream);
     if (rc < 0)
         return rc;
-    if (counts)
+    if (!counts && !offsets)
+        return U3D_OK;
+    cudaStream_t st = b->ctx->pick(stream);
+    const int V = (int)n;
+    if (!V)
     {
-        rc = u3d_batch_read_counts(b, counts, stream);
-        if (rc < 0)
-            return rc;
+        if (offsets)
+            offsets[0] = 0;
+        return U3D_OK;
     }
+    // One synchronisation: the header (flags | counts | packed offsets) and the packed ids leave in the same breath, the ids up to what
+    // the previous call needed plus 1/8 (frames are coherent); only a batch that outgrew that pays a second copy.
+    const size_t hdrWords = 1 + 2 * (size_t)V + (size_t)V + 1;
+    CU_CHECK(b->hdr.ensure(1 + 3 * (size_t)b->vs.maxViews + 1));
+    CU_CHECK(b->hostHdr.ensure(1 + 3 * (size_t)b->vs.maxViews + 1));
+    CU_CHECK(b->packed.ensure((size_t)b->vs.maxViews * std::max<uint32_t>(b->outCap, 1)));
+    k_pack_header<<<1, 1024, 0, st>>>(V, b->outCounts.p, b->outCap, b->packOffsets.p, b->vs.flags.p, b->hdr.p);
+    const bool wantIds = offsets && ids && capacity;
+    if (wantIds)
+        k_pack_ids<<<V, 256, 0, st>>>(b->outCounts.p, b->outCap, b->packOffsets.p, b->outIdx.p, b->packed.p);
+    CU_CHECK(cudaGetLastError());
+    b->lastLaunches += wantIds ? 2 : 1;
+    CU_CHECK(cudaMemcpyAsync(b->hostHdr.p, b->hdr.p, hdrWords * 4, cudaMemcpyDeviceToHost, st));
+    const uint64_t packedCap = (uint64_t)V * std::max<uint32_t>(b->outCap, 1);
+    const uint64_t first = wantIds ? std::min<uint64_t>(std::min<uint64_t>(capacity, packedCap), b->idsGuess) : 0;
+    if (first)
+        CU_CHECK(cudaMemcpyAsync(ids, b->packed.p, first * 4, cudaMemcpyDeviceToHost, st));
+    CU_CHECK(cudaStreamSynchronize(st));
+    rc = flags_to_error(b->hostHdr.p[0]);
+    if (rc < 0)
+        return rc;
+    if (counts)
+        std::memcpy(counts, b->hostHdr.p + 1, (size_t)V * 8);
     if (offsets)
-        rc = u3d_batch_read_packed(b, offsets, ids, capacity, stream);
-    return rc;
+    {
+        std::memcpy(offsets, b->hostHdr.p + 1 + 2 * (size_t)V, ((size_t)V + 1) * 4);
+        const uint64_t total = offsets[V];
+        if (total > capacity)
+            return fail(U3D_ERR_CAPACITY, "u3d_batch_cull_views: ids capacity too small");
+        if (wantIds && total > first)
+        {
+            CU_CHECK(cudaMemcpyAsync(ids + first, b->packed.p + first, (total - first) * 4, cudaMemcpyDeviceToHost, st));
+            CU_CHECK(cudaStreamSynchronize(st));
+        }
+        b->idsGuess = total + total / 8 + 1024;
+    }
+    return U3D_OK;
 }
 
 int u3d_batch_device_results(u3d_batch* b, void** counts_dev, void** ids_dev, uint32_t* out_capacity)

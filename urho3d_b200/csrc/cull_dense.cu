@@ -140,11 +140,13 @@ __device__ __forceinline__ void dense_mark_alive(const SceneDev& sc, const Dense
 }
 
 __global__ void __launch_bounds__(kDenseThreads) k_dense_seed(SceneDev sc, const ViewConst* __restrict__ views, int numViews, unsigned char* __restrict__ stateAll,
-    DenseDev dd)
+    uint32_t* __restrict__ outCounts, DenseDev dd)
 {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= numViews)
         return;
+    outCounts[2 * v] = 0; // k_dense_frustum adds the query result size up with atomics
+    outCounts[2 * v + 1] = 0;
     const ViewConst& vc = views[v];
     // the root is never tested by OctreeQuery walks (Octree.cpp:231); the ray walk tests every octant (Octree.cpp:257-261)
     bool rootAlive = true;
@@ -1082,11 +1084,10 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         g_denseGrid = sms * 6;
     }
     const int grid = gridLight;
-    // octants the walk never reaches must read as culled; counters, alive bits and the views' query counts start at zero
+    // octants the walk never reaches must read as culled; counters and alive bits start at zero (the views' counts: k_dense_seed)
     cudaMemsetAsync(octState, 0, (size_t)numViews * dd.stateStride, s);
     cudaMemsetAsync(dd.ctr, 0, dense_counter_bytes(numViews, sc.numOctants), s);
-    cudaMemsetAsync(outCounts, 0, (size_t)numViews * 8, s);
-    k_dense_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, dd);
+    k_dense_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, outCounts, dd);
     for (int lv = 1; lv < sc.numLevels; ++lv)
         k_dense_level<<<gridLevel, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, lv);
     k_dense_groups<<<grid, kDenseThreads, 0, s>>>(sc, numViews, octState, dd);
