@@ -529,7 +529,7 @@ def main():
                 g.release(comm.cuda_stream)
                 sl["done"] = torch.cuda.Event()
                 sl["done"].record(comm)
-                extra = 5
+                extra = 3  # k_push_results, k_gather_wait, k_gather_signal
             elif do_gather:
                 # library baseline: every rank's per-view counts and packed visible sets, all-gathered over NCCL
                 sl["batch"].pack_device(sl["stream"])

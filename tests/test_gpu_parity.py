@@ -769,6 +769,30 @@ def test_peer_memory_result_exchange(gpu_ctx, world):
             assert offsets[0, len(shards[0])] == sum(len(want[v]) for v in shards[0])
         for r in range(world):
             gathers[r].release(streams[r].cuda_stream)
+    # a rank that pushes fewer views than before (uneven shards, a last partial batch): its unused slots read as empty everywhere,
+    # not as the previous epoch's counts; then full again
+    short = min(2, len(shards[0]))
+    for nfirst in (short, len(shards[0])):
+        batches[0].set_views(capi.pack_views([views[i] for i in shards[0][:nfirst]]))
+        for r in range(world):
+            batches[r].run(capi.STAGE_VISIBLE, streams[r].cuda_stream)
+            gathers[r].push(batches[r], streams[r].cuda_stream)
+        for r in range(world):
+            gathers[r].wait(streams[r].cuda_stream)
+        for r in range(world):
+            counts, offsets, ids = gathers[r].read(streams[r].cuda_stream)
+            tot0 = sum(len(want[v]) for v in shards[0][:nfirst])
+            assert np.all(counts[0, nfirst:] == 0), "stale counts in unused slots"
+            assert np.all(offsets[0, nfirst:] == tot0)
+            for slot, v in enumerate(shards[0][:nfirst]):
+                o = offsets[0, slot]
+                assert counts[0, slot, 1] == len(want[v]) and np.array_equal(ids[0, o:o + len(want[v])], want[v])
+            for src in range(1, world):
+                for slot, v in enumerate(shards[src]):
+                    o = offsets[src, slot]
+                    assert np.array_equal(ids[src, o:o + len(want[v])], want[v])
+        for r in range(world):
+            gathers[r].release(streams[r].cuda_stream)
     # capacity: a region that cannot hold a rank's ids is reported, not silently truncated
     small = [capi.Gather(gpu_ctx, world, r, per, 8) for r in range(world)]
     for g in small:
@@ -780,6 +804,7 @@ def test_peer_memory_result_exchange(gpu_ctx, world):
     with pytest.raises(capi.U3DError) as e:
         small[0].status(streams[0].cuda_stream)
     assert e.value.code == 4
+    small[0].status(streams[0].cuda_stream)  # reported once, then cleared: a later status of the same object is clean
     for o in (*small, *gathers, *batches, occ, mesh, gs, tree):
         o.close()
     ob.close()

@@ -2480,59 +2480,129 @@ __global__ void k_gather_signal(PeerTable peers, int world, int myRank, size_t f
     st_release_sys(reinterpret_cast<uint32_t*>(peers.block[r] + flagOff) + myRank, epoch);
 }
 
-/// Fused pack + all-gather: block v copies the emitted ids of view v to offset offsets[v] of region [myRank] in EVERY rank's block
-/// (coalesced 4-byte stores, 128 B per warp and destination), writes the view's counts and packed offset beside them, and the last
-/// block to finish raises the arrival flags.
+/// The whole producer side of the exchange in ONE launch, one block per view slot of this rank (all `per` of them, so that the
+/// slots this batch does not use read as empty on every rank):
+///   1. wait until every consumer has released the previous epoch's contents of this rank's regions (ack flags of the own block);
+///   2. packed offset of the view = sum of the emitted counts of the views before it (every block sums for itself: a few KB of L2 reads
+///      instead of a scan kernel in front);
+///   3. copy the view's emitted ids into region [myRank] of EVERY rank's block: each element is loaded once and stored with 16-byte
+///      peer stores (NVLink packets of 4 ids; the destination is aligned by a scalar head, the source is read as 4 scalars);
+///   4. counts and offsets beside them; the last block to finish raises this rank's arrival flag in every block.
 __global__ void __launch_bounds__(256) k_push_results(PeerTable peers, GatherLayout lay, int myRank, int numViews, const uint32_t* __restrict__ counts,
-    uint32_t outCap, const uint32_t* __restrict__ offsets, const uint32_t* __restrict__ ids, uint32_t epoch, uint32_t* __restrict__ doneCounter)
+    uint32_t outCap, const uint32_t* __restrict__ ids, uint32_t epoch, uint32_t* __restrict__ doneCounter, unsigned long long timeoutNs)
 {
+    __shared__ uint32_t red[2][8];
+    __shared__ bool last;
     const int v = blockIdx.x;
     const int world = lay.world;
-    const uint32_t n = min(counts[2 * v + 1], outCap);
-    const uint32_t off = offsets[v];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    uint32_t* ownStatus = reinterpret_cast<uint32_t*>(peers.block[myRank]) + 2 * kMaxRanks;
+    // 1. acknowledgements of the previous epoch
+    if (epoch > 1 && tid < world)
+    {
+        const uint32_t* ack = reinterpret_cast<const uint32_t*>(peers.block[myRank]) + kMaxRanks + tid;
+        const unsigned long long t0 = global_timer_ns();
+        while ((int)(ld_acquire_sys(ack) - (epoch - 1)) < 0)
+        {
+            __nanosleep(200);
+            if (global_timer_ns() - t0 > timeoutNs)
+            {
+                atomicOr(ownStatus, kGatherTimeout);
+                break;
+            }
+        }
+    }
+    // 2. offsets
+    uint32_t before = 0, total = 0;
+    for (int u = tid; u < numViews; u += 256)
+    {
+        const uint32_t c = min(counts[2 * u + 1], outCap);
+        total += c;
+        if (u < v)
+            before += c;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1)
+    {
+        before += __shfl_xor_sync(0xffffffffu, before, o);
+        total += __shfl_xor_sync(0xffffffffu, total, o);
+    }
+    if (lane == 0)
+    {
+        red[0][wid] = before;
+        red[1][wid] = total;
+    }
+    __syncthreads(); // also orders the acknowledgement wait before any store below
+    before = total = 0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w)
+    {
+        before += red[0][w];
+        total += red[1][w];
+    }
+    const bool used = v < numViews;
+    const uint32_t off = used ? before : total;
+    const uint32_t n = used ? min(counts[2 * v + 1], outCap) : 0u;
+    // 3. ids
     uint32_t m = n;
     if ((uint64_t)off + n > lay.cap)
     {
         m = off < lay.cap ? (uint32_t)(lay.cap - off) : 0u;
-        if (threadIdx.x < world) // every consumer must learn that this rank's region is truncated
-            atomicOr(reinterpret_cast<uint32_t*>(peers.block[threadIdx.x]) + 2 * kMaxRanks, kGatherOverflow);
+        if (tid < world) // every consumer must learn that this rank's region is truncated
+            atomicOr(reinterpret_cast<uint32_t*>(peers.block[tid]) + 2 * kMaxRanks, kGatherOverflow);
     }
-    const uint32_t* src = ids + (size_t)v * outCap;
-    // each element is loaded once and stored to every destination
-    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x)
+    if (m)
     {
-        const uint32_t x = src[i];
-        for (int r = 0; r < world; ++r)
+        const uint32_t* src = ids + (size_t)v * outCap;
+        const size_t d0 = (size_t)myRank * lay.cap + off;          // first destination element inside the ids region
+        const uint32_t head = min(m, (uint32_t)((4 - (d0 & 3)) & 3)); // scalar elements until the destination is 16-byte aligned
+        const uint32_t nBody = (m - head) >> 2, tail = head + (nBody << 2);
+        for (uint32_t k = tid; k < nBody; k += 256)
         {
-            const int dst = (myRank + r) % world; // start with the own block, spread the ranks over the links
-            reinterpret_cast<uint32_t*>(peers.block[dst] + lay.idsOff())[(size_t)myRank * lay.cap + off + i] = x;
+            const uint32_t* p = src + head + (k << 2);
+            const uint4 x = make_uint4(p[0], p[1], p[2], p[3]);
+            for (int r = 0; r < world; ++r)
+            {
+                const int dst = (myRank + r) % world; // start with the own block, spread the ranks over the links
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint32_t*>(peers.block[dst] + lay.idsOff()) + d0 + head + (k << 2)) = x;
+            }
+        }
+        for (uint32_t i = tid; i < head + (m - tail); i += 256)
+        {
+            const uint32_t e = i < head ? i : tail + (i - head);
+            const uint32_t x = src[e];
+            for (int r = 0; r < world; ++r)
+            {
+                const int dst = (myRank + r) % world;
+                reinterpret_cast<uint32_t*>(peers.block[dst] + lay.idsOff())[d0 + e] = x;
+            }
         }
     }
-    if (threadIdx.x < world)
+    // 4. counts, offsets, arrival
+    if (tid < world)
     {
-        const int dst = threadIdx.x;
+        const int dst = tid;
         uint32_t* c = reinterpret_cast<uint32_t*>(peers.block[dst] + lay.countsOff()) + ((size_t)myRank * lay.per + v) * 2;
-        c[0] = counts[2 * v];
-        c[1] = counts[2 * v + 1];
+        c[0] = used ? counts[2 * v] : 0u;
+        c[1] = used ? counts[2 * v + 1] : 0u;
         uint32_t* o = reinterpret_cast<uint32_t*>(peers.block[dst] + lay.offsetsOff()) + (size_t)myRank * (lay.per + 1);
         o[v] = off;
-        if (v == numViews - 1)
-            o[numViews] = offsets[numViews];
+        if (v == (int)lay.per - 1)
+            o[lay.per] = total;
     }
     __threadfence_system();
     __syncthreads();
-    __shared__ bool last;
-    if (threadIdx.x == 0)
-        last = atomicAdd(doneCounter, 1u) == (uint32_t)numViews - 1u;
+    if (tid == 0)
+        last = atomicAdd(doneCounter, 1u) == gridDim.x - 1u;
     __syncthreads();
     if (last)
     {
-        if (threadIdx.x == 0)
+        if (tid == 0)
             *doneCounter = 0;
-        if (threadIdx.x < world)
+        if (tid < world)
         {
             __threadfence_system();
-            st_release_sys(reinterpret_cast<uint32_t*>(peers.block[threadIdx.x]) + myRank, epoch);
+            st_release_sys(reinterpret_cast<uint32_t*>(peers.block[tid]) + myRank, epoch);
         }
     }
 }
@@ -2669,17 +2739,8 @@ int u3d_batch_push_results(u3d_batch* b, u3d_gather* g, void* stream)
     cudaStream_t st = b->ctx->pick(stream);
     const int V = (int)b->numViews;
     const uint32_t epoch = ++g->epoch;
-    // every consumer has released the previous contents of this rank's regions (ack[] of the own block)
-    if (epoch > 1)
-        k_gather_wait<<<1, kMaxRanks, 0, st>>>(reinterpret_cast<uint32_t*>(g->block) + kMaxRanks, g->world, epoch - 1, reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks,
-            g->timeoutNs);
-    if (V)
-    {
-        k_pack_offsets<<<1, 1024, 0, st>>>(V, b->outCounts.p, b->outCap, b->packOffsets.p);
-        k_push_results<<<V, 256, 0, st>>>(g->peers, g->lay, g->rank, V, b->outCounts.p, b->outCap, b->packOffsets.p, b->outIdx.p, epoch, g->doneCounter.p);
-    }
-    else
-        k_gather_signal<<<1, kMaxRanks, 0, st>>>(g->peers, g->world, g->rank, 0, epoch);
+    // one launch: acknowledgement wait + packed offsets + peer stores + arrival flags (k_push_results)
+    k_push_results<<<g->lay.per, 256, 0, st>>>(g->peers, g->lay, g->rank, V, b->outCounts.p, b->outCap, b->outIdx.p, epoch, g->doneCounter.p, g->timeoutNs);
     CU_CHECK(cudaGetLastError());
     return U3D_OK;
 }
@@ -2748,6 +2809,12 @@ int u3d_gather_status(u3d_gather* g, void* stream)
     uint32_t status = 0;
     CU_CHECK(cudaMemcpyAsync(&status, reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks, 4, cudaMemcpyDeviceToHost, st));
     CU_CHECK(cudaStreamSynchronize(st));
+    if (status)
+    {
+        // reported once: the word is cleared so that one bad epoch does not fail every later read of this object
+        CU_CHECK(cudaMemsetAsync(reinterpret_cast<uint32_t*>(g->block) + 2 * kMaxRanks, 0, 4, st));
+        CU_CHECK(cudaStreamSynchronize(st));
+    }
     if (status & kGatherTimeout)
         return fail(U3D_ERR_CUDA, "result exchange timed out waiting for a peer rank");
     if (status & kGatherOverflow)
