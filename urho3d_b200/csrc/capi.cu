@@ -22,6 +22,10 @@ static int g_laneAreaMax = kLaneAreaMax, g_warpAreaMax = kWarpAreaMax; // tuning
 // 2 = the dense path always.  "dense_queue_cap" / "dense_pool_cap" shrink its scratch (test hook for the on-device fallback).
 static int g_cullDense = 1;
 static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
+// "two_phase": 1 = the batched path draws a view's nearest occluders first and the others only if their box shows in that buffer
+// (launch_items_near_far / launch_items_far_test), 0 = every selected occluder is set up and filled.  "two_phase_min" / "two_phase_shift":
+// the near set holds at least that many draw items, or 1 / 2^shift of the view's items.
+static int g_twoPhase = 1, g_twoPhaseMin = 32, g_twoPhaseShift = 3;
 static int g_readDenseProf = 0; // "read_dense_prof": u3d_debug_read_cull_prof returns the dense path's timers
 constexpr int kDenseMinViews = 16;
 
@@ -225,7 +229,7 @@ struct ViewSet
         size_t n{};
     };
     DevBuf<uint32_t> zeroBlock;
-    size_t zeroWords{};
+    size_t zeroWords{}, passLocalOffset{};
     Sub itemCount, submitted, triCount, drawnSources, flags, binCount, irrTotal, irrOfView, clipCount;
     DevBuf<uint32_t> triCap;
     DevBuf<uint64_t> triBase;
@@ -241,6 +245,7 @@ struct ViewSet
     DevBuf<float> clipQueue;
     uint32_t clipCap{};
     cudaError_t clear_counters(cudaStream_t st) { return cudaMemsetAsync(zeroBlock.p, 0, zeroWords * 4, st); }
+    cudaError_t clear_pass_counters(cudaStream_t st) { return cudaMemsetAsync(zeroBlock.p + passLocalOffset, 0, (zeroWords - passLocalOffset) * 4, st); }
     RasterDev raster_dev(bool tiles, int writeMips)
     {
         RasterDev rd{};
@@ -280,20 +285,25 @@ struct ViewSet
             CU_CHECK(irrList.ensure(irrCap));
         }
         {
+            // [flags, pad x3 | itemCount | submitted | triCount | drawnSources || clipCount, irrTotal, pad x2 | irrOfView | binCount]: the part
+            // behind || belongs to one set-up + fill pass and is cleared again between the two passes of the two-phase occluder drawing
             const size_t nBins = useTiles ? (size_t)nviews * tg.numTiles * kNumCls : 0;
-            zeroWords = 4 + 5 * (size_t)nviews + nBins;
+            passLocalOffset = 4 + 4 * (size_t)nviews;
+            zeroWords = passLocalOffset + 4 + (size_t)nviews + nBins;
             CU_CHECK(zeroBlock.ensure(zeroWords));
             uint32_t* q = zeroBlock.p;
             flags = Sub{q, 1};
-            clipCount = Sub{q + 1, 1};
-            irrTotal = Sub{q + 2, 1};
             q += 4;
             itemCount = Sub{q, nviews};
             submitted = Sub{q + nviews, nviews};
             triCount = Sub{q + 2 * (size_t)nviews, nviews};
             drawnSources = Sub{q + 3 * (size_t)nviews, nviews};
-            irrOfView = Sub{q + 4 * (size_t)nviews, nviews};
-            binCount = Sub{q + 5 * (size_t)nviews, nBins};
+            q = zeroBlock.p + passLocalOffset;
+            clipCount = Sub{q, 1};
+            irrTotal = Sub{q + 1, 1};
+            q += 4;
+            irrOfView = Sub{q, nviews};
+            binCount = Sub{q + nviews, nBins};
         }
         CU_CHECK(views.ensure(nviews));
         CU_CHECK(depth.ensure((size_t)nviews * w * h));
@@ -351,6 +361,18 @@ struct DenseScratch
     DevBuf<uint2> queue, groupList;
     DevBuf<uint32_t> ctr, groupCount, groupOff, wordBase, viewWords, visWord, wordSlot, wordMeta, testMask;
     DenseDev dev{};
+    uint32_t epochCounter{};
+    /// Epoch of the next run's queue entries; the queue is wiped whenever the 16-bit tag starts over (and before its first use), so an
+    /// entry left by an earlier run can never carry the current tag.
+    cudaError_t next_epoch(cudaStream_t st)
+    {
+        cudaError_t e = cudaSuccess;
+        if (epochCounter % 65535u == 0)
+            e = cudaMemsetAsync(queue.p, 0, queue.n * sizeof(uint2), st);
+        dev.epoch = epochCounter % 65535u + 1u;
+        ++epochCounter;
+        return e;
+    }
     int ensure(uint32_t maxViews, const SceneDev& sc, uint32_t queueCapOverride, uint32_t poolCapOverride)
     {
         const uint64_t V = maxViews, M = (uint64_t)sc.numOctants, N = (uint64_t)sc.numDrawables;
@@ -366,7 +388,10 @@ struct DenseScratch
             queueCap = queueCapOverride;
         if (poolCapOverride)
             poolCap = poolCapOverride;
+        const uint2* oldQueue = queue.p;
         CU_CHECK(queue.ensure(queueCap));
+        if (queue.p != oldQueue)
+            epochCounter = 0; // fresh memory: wiped below before its first use
         CU_CHECK(ctr.ensure(dense_counter_bytes((int)V, (int)M) / 4));
         CU_CHECK(groupCount.ensure(V * groups));
         CU_CHECK(groupOff.ensure(V * groups));
@@ -408,6 +433,8 @@ struct u3d_batch
     uint32_t outCap{};
     uint64_t poolTris{};
     DevBuf<unsigned char> octState;
+    DevBuf<unsigned char> itemPass;   // two-phase occluder drawing: per (view, item) kPassNear / kPassFarVisible / kPassFarHidden
+    bool countPending{};              // numTriangles_ of the occluders the second pass skipped is still to be counted (u3d_batch_read_tri_stats)
     DenseScratch dense;
     DevBuf<uint32_t> outIdx, outCounts, packOffsets, packed;
     DevBuf<float> zRange; // per view (minZ, maxZ)
@@ -474,6 +501,21 @@ int u3d_debug_set_option(const char* name, int value)
         cull_set_heavy_extent(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "two_phase") == 0)
+    {
+        g_twoPhase = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "two_phase_min") == 0)
+    {
+        g_twoPhaseMin = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "two_phase_shift") == 0)
+    {
+        g_twoPhaseShift = value;
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "cull_dense") == 0)
     {
         g_cullDense = value;
@@ -492,6 +534,16 @@ int u3d_debug_set_option(const char* name, int value)
     if (name && std::strcmp(name, "walk_budget_idle") == 0)
     {
         dense_set_walk_budget(-1, value);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_tree_blocks") == 0)
+    {
+        dense_set_tree_blocks(value);
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "dense_tree") == 0)
+    {
+        dense_set_tree(value);
         return U3D_OK;
     }
     if (name && std::strcmp(name, "dense_walker") == 0)
@@ -2123,14 +2175,24 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             launch_select(vs.views.p, V, (int)oc->n, oc->aabb6.p, oc->mesh.p, oc->start.p, oc->count.p, vs.items.p, vs.itemCap, vs.itemCount.p, vs.submitted.p, st);
         CU_CHECK(mark(2));
         launch_scan_regions(V, vs.submitted.p, 64, b->poolTris, vs.triBase.p, vs.triCap.p, vs.flags.p, st);
+        const bool twoPhase = g_twoPhase && vs.useTiles;
+        b->countPending = false;
+        RasterDev rd = vs.raster_dev(vs.useTiles, 1);
+        if (twoPhase)
+        {
+            CU_CHECK(b->itemPass.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
+            launch_items_near_far(vs.views.p, V, vs.items.p, vs.itemCap, vs.itemCount.p, oc->aabb6.p, b->itemPass.p, (uint32_t)g_twoPhaseMin, g_twoPhaseShift, st);
+            rd.itemPass = b->itemPass.p;
+            rd.pass = kPassNear;
+            b->lastLaunches += 1;
+        }
         CU_CHECK(mark(3));
-        launch_setup(vs.g, vs.tg, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p,
-            vs.raster_dev(vs.useTiles, 1), st);
+        launch_setup(vs.g, vs.tg, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, rd, st);
         CU_CHECK(mark(4));
         int firstLevel = 0;
         if (vs.useTiles)
         {
-            launch_fill_tiles(vs.g, vs.tg, V, vs.depth.p, vs.mips.p, vs.raster_dev(true, 1), st);
+            launch_fill_tiles(vs.g, vs.tg, V, vs.depth.p, vs.mips.p, rd, st);
             firstLevel = vs.tg.fused;
             b->lastLaunches += 3;
         }
@@ -2142,6 +2204,20 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         CU_CHECK(mark(5));
         launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, firstLevel, st);
         b->lastLaunches += 4 + (uint32_t)(vs.g.nlev - firstLevel); // select, region scan, set-up, clipper + one launch per unfused level
+        if (twoPhase)
+        {
+            // second pass: the occluders that were left out, as far as their boxes show in the first pass's buffer (and hierarchy)
+            launch_items_far_test(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->aabb6.p, vs.depth.p, vs.mips.p,
+                b->itemPass.p, st);
+            CU_CHECK(vs.clear_pass_counters(st));
+            rd.pass = kPassFarVisible;
+            rd.secondPass = 1;
+            launch_setup(vs.g, vs.tg, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, rd, st);
+            launch_fill_tiles(vs.g, vs.tg, V, vs.depth.p, vs.mips.p, rd, st);
+            launch_hierarchy(vs.g, V, vs.depth.p, vs.mips.p, firstLevel, st);
+            b->lastLaunches += 5 + (uint32_t)(vs.g.nlev - firstLevel);
+            b->countPending = true;
+        }
         CU_CHECK(cudaGetLastError());
         }
     }
@@ -2162,6 +2238,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             int rc = b->dense.ensure(vs.maxViews, sc, g_denseQueueCap, g_densePoolCap);
             if (rc < 0)
                 return rc;
+            CU_CHECK(b->dense.next_epoch(st));
             launch_cull_dense(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p,
                 vs.flags.p, b->dense.dev, st);
             // answered on the device if the dense path's scratch overflowed (returns at once otherwise)
@@ -2982,6 +3059,22 @@ int u3d_batch_read_tri_stats(u3d_batch* b, uint32_t* stats3, void* stream)
     {
         std::memset(stats3, 0, (size_t)V * 12);
         return U3D_OK;
+    }
+    if (b->countPending && V)
+    {
+        // numTriangles_ counts every source triangle that passes clipping and culling, drawn into a visible place or not (OB.cpp:681-682).
+        // The occluders the second pass left out never went through set-up; their triangles are counted here, on demand, by the same
+        // kernels in count-only mode (the count is a statistic of the batched path: its budget is checked on submitted triangles).
+        ViewSet& vs = b->vs;
+        const u3d_occluders* oc = b->occ;
+        RasterDev rd = vs.raster_dev(true, 1);
+        rd.itemPass = b->itemPass.p;
+        rd.pass = kPassFarHidden;
+        rd.countOnly = 1;
+        CU_CHECK(cudaMemsetAsync(vs.clipCount.p, 0, 4, st));
+        launch_setup(vs.g, vs.tg, vs.views.p, (int)V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, rd, st);
+        CU_CHECK(cudaGetLastError());
+        b->countPending = false;
     }
     std::vector<uint32_t> sub(V), drawn(V), setup(V);
     CU_CHECK(cudaMemcpyAsync(sub.data(), b->vs.submitted.p, (size_t)V * 4, cudaMemcpyDeviceToHost, st));

@@ -846,6 +846,221 @@ __global__ void __launch_bounds__(kDenseThreads, 3) k_dense_level(SceneDev sc, B
     dense_prof_end(2 + level, profT0);
 }
 
+// -----------------------------------------------------------------------------------------------------------------------------
+// All octree levels in ONE persistent launch.  A child octant can be tested as soon as its parent has survived -- nothing needs a
+// whole level to finish first -- so the (view, octant) pairs of every level go through one global work queue: warps claim 32 slots
+// at a time, test what has been published in them, and append the survivors' children behind the queue's tail.  There is one ramp-up
+// and one tail for the whole tree instead of one per level, and no launch in between.
+//   entry  = (view | epoch << 16, octant | inside << 31): one aligned 8-byte store, so a consumer that sees the epoch sees the
+//            payload; the epoch changes every run, stale entries of earlier runs never match (the queue is wiped when it wraps)
+//   head   = next slot to claim, tail = next slot to reserve, work = pairs published and not finished yet (children are added
+//            before their parent is subtracted): 0 means the walk is complete
+// -----------------------------------------------------------------------------------------------------------------------------
+enum : int { CTR_QHEAD = 40, CTR_QTAIL = 41, CTR_QWORK = 42 };
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p)
+{
+    uint2 v;
+    asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+/// Warp-wide: lanes with `alive` record their octant's state and publish its children behind the queue's tail.
+__device__ __forceinline__ void tree_finalize(const SceneDev& sc, const DenseDev& dd, unsigned char* __restrict__ stateAll, uint32_t epochTag, bool alive,
+    int v, int o, bool inside)
+{
+    const int lane = threadIdx.x & 31;
+    int2 ch = make_int2(0, 0);
+    if (alive)
+    {
+        dense_mark_alive(sc, dd, v, o, inside ? 2 : 1, stateAll);
+        ch = sc.octChild[o];
+    }
+    int off = ch.y;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1)
+    {
+        const int t = __shfl_up_sync(0xffffffffu, off, s);
+        if (lane >= s)
+            off += t;
+    }
+    const int total = __shfl_sync(0xffffffffu, off, 31);
+    if (!total)
+        return;
+    off -= ch.y;
+    uint32_t pos = 0;
+    if (lane == 0)
+    {
+        atomicAdd(&dd.ctr[CTR_QWORK], (uint32_t)total); // before this warp reports the parents as finished
+        pos = atomicAdd(&dd.ctr[CTR_QTAIL], (uint32_t)total);
+    }
+    pos = __shfl_sync(0xffffffffu, pos, 0);
+    if ((uint64_t)pos + (uint32_t)total > dd.queueCap)
+    {
+        if (lane == 0)
+            dd.ctr[CTR_FALLBACK] = 1;
+        return;
+    }
+    const uint32_t ins = inside ? 0x80000000u : 0u;
+    for (int j = 0; j < ch.y; ++j)
+        dd.queue[pos + off + j] = make_uint2((uint32_t)v | epochTag, (uint32_t)sc.bfs[ch.x + j] | ins);
+}
+
+__global__ void __launch_bounds__(kDenseThreads) k_dense_tree_seed(SceneDev sc, const ViewConst* __restrict__ views, int numViews,
+    unsigned char* __restrict__ stateAll, uint32_t* __restrict__ outCounts, DenseDev dd, uint32_t epochTag)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= numViews)
+        return;
+    outCounts[2 * v] = 0; // k_dense_frustum adds the query result size up with atomics
+    outCounts[2 * v + 1] = 0;
+    const ViewConst& vc = views[v];
+    // the root is never tested by OctreeQuery walks (Octree.cpp:231); the ray walk tests every octant (Octree.cpp:257-261)
+    if (vc.queryMode == QUERY_RAY || vc.queryMode == QUERY_RAY_CANDIDATES)
+    {
+        const float4 mn = sc.octMin[0], mx = sc.octMax[0];
+        if (shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z) == OUTSIDE)
+            return;
+    }
+    dense_mark_alive(sc, dd, v, 0, 1, stateAll);
+    const int2 ch = sc.octChild[0];
+    if (ch.y)
+    {
+        atomicAdd(&dd.ctr[CTR_QWORK], (uint32_t)ch.y);
+        const uint32_t pos = atomicAdd(&dd.ctr[CTR_QTAIL], (uint32_t)ch.y);
+        if (pos + (uint32_t)ch.y > dd.queueCap)
+        {
+            dd.ctr[CTR_FALLBACK] = 1;
+            return;
+        }
+        for (int j = 0; j < ch.y; ++j)
+            dd.queue[pos + j] = make_uint2((uint32_t)v | epochTag, (uint32_t)sc.bfs[ch.x + j]);
+    }
+}
+
+__global__ void __launch_bounds__(kDenseThreads, 3) k_dense_tree(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+    const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ stateAll, DenseDev dd, uint32_t epochTag)
+{
+    __shared__ WalkShared sh;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const bool useMips = mipsValid != 0;
+    const uint32_t totalLanes = gridDim.x * kDenseThreads;
+    const unsigned long long profT0 = g_denseProfOn ? dense_now() : 0ull;
+    const int budgetBusy = g_walkBudgetBusy, budgetIdle = g_walkBudgetIdle;
+    int budget = budgetIdle;
+    int buffered = 0;
+    uint32_t finished = 0;   // pairs this warp has finished and not yet subtracted from the work counter (warp-uniform)
+    uint32_t claimBase = 0, claimMask = 0;
+    auto report = [&]() {
+        if (finished && lane == 0)
+            atomicSub(&dd.ctr[CTR_QWORK], finished);
+        finished = 0;
+    };
+    // octants whose visibility needs the deeper walk: meta = view | mask << 16 | inside << 26, tag = octant
+    auto drain = [&]() {
+        uint32_t meta, tag;
+        bool vis;
+        const bool had = walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis, budget);
+        tree_finalize(sc, dd, stateAll, epochTag, had && vis, (int)(meta & 0xFFFFu), (int)tag, (meta >> 26) & 1u);
+        finished += (uint32_t)__popc(__ballot_sync(0xffffffffu, had));
+    };
+    for (;;)
+    {
+        if (!claimMask)
+        {
+            uint32_t tail = 0;
+            if (lane == 0)
+            {
+                claimBase = atomicAdd(&dd.ctr[CTR_QHEAD], 32u);
+                tail = ld_volatile_u32(&dd.ctr[CTR_QTAIL]);
+            }
+            claimBase = __shfl_sync(0xffffffffu, claimBase, 0);
+            tail = __shfl_sync(0xffffffffu, tail, 0);
+            claimMask = 0xffffffffu;
+            // with a backlog, a lane may walk long borders alone; when the queue runs dry, a long walk is what everybody waits for
+            budget = (tail > claimBase && tail - claimBase > totalLanes) ? budgetBusy : budgetIdle;
+        }
+        const uint32_t slot = claimBase + lane;
+        uint2 e = make_uint2(0u, 0u);
+        bool ready = false;
+        if (((claimMask >> lane) & 1u) && slot < dd.queueCap)
+        {
+            e = ld_volatile_u2(dd.queue + slot);
+            ready = (e.x & 0xFFFF0000u) == epochTag;
+        }
+        const uint32_t readyMask = __ballot_sync(0xffffffffu, ready);
+        if (!readyMask)
+        {
+            if (buffered)
+            {
+                drain();
+                continue;
+            }
+            report();
+            uint32_t stop = 0;
+            if (lane == 0)
+                stop = (ld_volatile_u32(&dd.ctr[CTR_QWORK]) == 0u || ld_volatile_u32(&dd.ctr[CTR_FALLBACK]) != 0u) ? 1u : 0u;
+            if (__shfl_sync(0xffffffffu, stop, 0))
+                break;
+            __nanosleep(100);
+            continue;
+        }
+        claimMask &= ~readyMask;
+        int v = 0, o = 0, res = OUTSIDE;
+        bool occluded = false;
+        float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
+        if (ready)
+        {
+            v = (int)(e.x & 0xFFFFu);
+            o = (int)(e.y & 0x7FFFFFFFu);
+            const ViewConst& vc = views[v];
+            mn = sc.octMin[o];
+            mx = sc.octMax[o];
+            if (e.y >> 31)
+                res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
+            else
+                res = shape_test<false>(vc.queryMode, vc.planes, mn.x, mn.y, mn.z, mx.x, mx.y, mx.z);
+            occluded = vc.useOcclusion != 0 && vc.queryMode == QUERY_OCCLUDED;
+        }
+        // OccludedFrustumOctreeQuery::TestOctant, View.cpp:128-139
+        bool undecided = false;
+        if (__any_sync(0xffffffffu, occluded && res != OUTSIDE))
+        {
+            const bool need = occluded && res != OUTSIDE;
+            if (useMips)
+            {
+                BoxRect r;
+                uint32_t topMask;
+                const int state = walk_project(g, views, mipAll, need, (uint32_t)v, mn, mx, r, topMask);
+                if (need && state == 0)
+                    res = OUTSIDE;
+                undecided = need && state == 2;
+                walk_push(sh, wid, buffered, undecided, r, (uint32_t)v | (topMask << 16) | (res == INSIDE ? 1u << 26 : 0u), (uint32_t)o);
+            }
+            else
+            {
+                const bool vis = dense_is_visible(g, views, depthAll, mipAll, false, need, v, mn, mx, nullptr);
+                if (need && !vis)
+                    res = OUTSIDE;
+            }
+        }
+        tree_finalize(sc, dd, stateAll, epochTag, ready && res != OUTSIDE && !undecided, v, o, res == INSIDE);
+        finished += (uint32_t)__popc(__ballot_sync(0xffffffffu, ready && !undecided));
+        if (buffered >= 32)
+            drain();
+        if (finished >= 1024u)
+            report();
+    }
+    dense_prof_end(0, profT0);
+}
+
 /// CheckVisibilityWork's occlusion predicate (View.cpp:177) over the drawables k_dense_frustum left to it.
 #ifndef U3D_OCC_MINB
 #define U3D_OCC_MINB 1
@@ -1049,6 +1264,125 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const
     }
 }
 
+// -----------------------------------------------------------------------------------------------------------------------------
+// Two-phase occluder drawing (see u3d_kernels.h): near / far split of a view's draw items and the visibility test of the far ones.
+// -----------------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t item_depth_bin(const float* vp, const float* b)
+{
+    // clip-space w of the box centre = its distance along the view direction (perspective) -- any monotone key will do, the split only
+    // decides what is drawn first.  Positive floats order like their bit patterns: exponent + 2 mantissa bits = 1024 bins.
+    const float cx = (b[0] + b[3]) * 0.5f, cy = (b[1] + b[4]) * 0.5f, cz = (b[2] + b[5]) * 0.5f;
+    const float w = vp[12] * cx + vp[13] * cy + vp[14] * cz + vp[15];
+    return w > 0.0f ? min(__float_as_uint(w) >> 21, 1023u) : 0u;
+}
+
+__global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
+    const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, unsigned char* __restrict__ itemPass, uint32_t minNear, int shift)
+{
+    __shared__ uint32_t hist[1024];
+    __shared__ uint32_t sCut;
+    const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    const uint32_t n = min(itemCount[v], itemCap);
+    const uint32_t target = max(minNear, n >> shift);
+    const DrawItem* mine = items + (size_t)v * itemCap;
+    unsigned char* pass = itemPass + (size_t)v * itemCap;
+    if (n <= target || !views[v].useOcclusion)
+    {
+        for (uint32_t i = tid; i < n; i += 256)
+            pass[i] = kPassNear;
+        return;
+    }
+    for (int i = tid; i < 1024; i += 256)
+        hist[i] = 0;
+    __syncthreads();
+    const float* vp = views[v].vp;
+    for (uint32_t i = tid; i < n; i += 256)
+        atomicAdd(&hist[item_depth_bin(vp, occAabb6 + 6 * (size_t)mine[i].model)], 1u);
+    __syncthreads();
+    if (tid < 32)
+    {
+        // the first bin at which the running count reaches the target: lanes own 32 bins each
+        uint32_t sum = 0;
+        for (int k = 0; k < 32; ++k)
+            sum += hist[lane * 32 + k];
+        uint32_t incl = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o)
+                incl += t;
+        }
+        const uint32_t reached = __ballot_sync(0xffffffffu, incl >= target);
+        const int owner = reached ? __ffs(reached) - 1 : 31;
+        if (lane == owner)
+        {
+            uint32_t run = incl - sum;
+            int k = 0;
+            for (; k < 31; ++k)
+            {
+                run += hist[lane * 32 + k];
+                if (run >= target)
+                    break;
+            }
+            sCut = (uint32_t)(lane * 32 + k);
+        }
+    }
+    __syncthreads();
+    const uint32_t cut = sCut;
+    for (uint32_t i = tid; i < n; i += 256)
+        pass[i] = item_depth_bin(vp, occAabb6 + 6 * (size_t)mine[i].model) <= cut ? kPassNear : kPassFarHidden;
+}
+
+__global__ void __launch_bounds__(256) k_items_far_test(BufGeom g, const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
+    const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, const int* __restrict__ depthAll, const int2* __restrict__ mipAll,
+    unsigned char* __restrict__ itemPass)
+{
+    const int v = blockIdx.y;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= min(itemCount[v], itemCap))
+        return;
+    unsigned char* pass = itemPass + (size_t)v * itemCap + i;
+    if (*pass != kPassFarHidden)
+        return;
+    const float* b = occAabb6 + 6 * (size_t)items[(size_t)v * itemCap + i].model;
+    BoxRect r;
+    bool visible = ob_project(g, views[v].vp, b[0], b[1], b[2], b[3], b[4], b[5], r);
+    if (!visible)
+    {
+        const int* depth = depthAll + (size_t)v * g.w * g.h;
+        const int2* mips = mipAll + (size_t)v * g.mipTexels;
+        uint32_t mask;
+        const int state = walk_top(g, mips, r, mask);
+        visible = state == 1;
+        if (state == 2)
+        {
+            uint32_t stack[kWalkStack];
+            int sp;
+            // an unfinished walk counts as visible: drawing an occluder that would not have shown is only wasted work
+            visible = walk_deep(g, depth, mips, r, mask, stack, sp, 64) != 0;
+        }
+    }
+    if (visible)
+        *pass = kPassFarVisible;
+}
+
+void launch_items_near_far(const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, const uint32_t* itemCount, const float* occAabb6,
+    unsigned char* itemPass, uint32_t minNear, int shift, cudaStream_t s)
+{
+    if (numViews)
+        k_items_near_far<<<numViews, 256, 0, s>>>(views, items, itemCap, itemCount, occAabb6, itemPass, minNear, shift);
+}
+
+void launch_items_far_test(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
+    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, cudaStream_t s)
+{
+    if (!numViews || !maxItems)
+        return;
+    dim3 grid((maxItems + 255) / 256, numViews);
+    k_items_far_test<<<grid, 256, 0, s>>>(g, views, items, itemCap, itemCount, occAabb6, depth, mips, itemPass);
+}
+
 size_t dense_counter_bytes(int numViews, int numOctants)
 {
     const int aliveWords = (numOctants + 1023) / 1024;
@@ -1056,6 +1390,9 @@ size_t dense_counter_bytes(int numViews, int numOctants)
 }
 
 static int g_denseGrid = 0;
+static int g_denseTreeBlocks = 0; // "dense_tree_blocks": blocks per SM of the persistent tree kernel (0 = as many as fit)
+static int gridSms = 148;
+static int g_denseTree = 1;   // "dense_tree": 1 = all octree levels in one persistent launch (k_dense_tree), 0 = one launch per level
 static int g_denseWalker = 1; // "dense_walker": 1 = occlusion predicate with the warp walker, 0 = one walk per lane
 
 void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
@@ -1064,12 +1401,13 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
 {
     if (!numViews)
         return;
-    static int gridLevel = 0, gridOcc = 0, gridOccWalk = 0, gridFrustum = 0, gridLight = 0;
+    static int gridLevel = 0, gridTree = 0, gridOcc = 0, gridOccWalk = 0, gridFrustum = 0, gridLight = 0;
     if (!g_denseGrid)
     {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        gridSms = sms;
         // persistent grids: exactly the blocks that are resident at once (a second, partial wave would leave SMs idle at the end)
         auto fit = [&](auto kernel) {
             int perSm = 1;
@@ -1077,6 +1415,7 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
             return sms * std::max(perSm, 1);
         };
         gridLevel = fit(k_dense_level);
+        gridTree = fit(k_dense_tree);
         gridOcc = fit(k_dense_occlusion);
         gridOccWalk = fit(k_dense_occlusion_walk);
         gridFrustum = fit(k_dense_frustum);
@@ -1087,9 +1426,19 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
     // octants the walk never reaches must read as culled; counters and alive bits start at zero (the views' counts: k_dense_seed)
     cudaMemsetAsync(octState, 0, (size_t)numViews * dd.stateStride, s);
     cudaMemsetAsync(dd.ctr, 0, dense_counter_bytes(numViews, sc.numOctants), s);
-    k_dense_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, outCounts, dd);
-    for (int lv = 1; lv < sc.numLevels; ++lv)
-        k_dense_level<<<gridLevel, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, lv);
+    if (g_denseTree && numViews <= 65535)
+    {
+        const uint32_t epochTag = dd.epoch << 16; // 1..65535, new every run (capi.cu wipes the queue when it wraps)
+        k_dense_tree_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, outCounts, dd, epochTag);
+        const int blocks = g_denseTreeBlocks > 0 ? std::min(gridTree, gridSms * g_denseTreeBlocks) : gridTree;
+        k_dense_tree<<<blocks, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, epochTag);
+    }
+    else
+    {
+        k_dense_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, outCounts, dd);
+        for (int lv = 1; lv < sc.numLevels; ++lv)
+            k_dense_level<<<gridLevel, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, lv);
+    }
     k_dense_groups<<<grid, kDenseThreads, 0, s>>>(sc, numViews, octState, dd);
     k_dense_scan<<<(numViews * 32 + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(numViews, dd);
     k_dense_words<<<grid, kDenseThreads, 0, s>>>(sc, octState, dd);
@@ -1106,7 +1455,7 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
 
 int dense_launch_count(const SceneDev& sc)
 {
-    return 7 + (sc.numLevels > 1 ? sc.numLevels - 1 : 0);
+    return g_denseTree ? 9 : 7 + (sc.numLevels > 1 ? sc.numLevels - 1 : 0);
 }
 
 void dense_set_walk_pool(int on)
@@ -1139,6 +1488,16 @@ void dense_set_walk_budget(int busy, int idle)
         cudaMemcpyToSymbol(g_walkBudgetBusy, &busy, sizeof(int));
     if (idle >= 0)
         cudaMemcpyToSymbol(g_walkBudgetIdle, &idle, sizeof(int));
+}
+
+void dense_set_tree(int on)
+{
+    g_denseTree = on;
+}
+
+void dense_set_tree_blocks(int perSm)
+{
+    g_denseTreeBlocks = perSm;
 }
 
 void dense_set_walker(int on)

@@ -561,6 +561,7 @@ struct EmitCtx
     int w, h, tileW, tilesX, tilesY;
     int forceIrregular;
     int laneAreaMax, warpAreaMax;
+    int countOnly;           // decide drawOk only: nothing is emitted
 };
 
 /// Append one record to the view's region; on the tile path also classify it and bin it.
@@ -726,7 +727,8 @@ __device__ __forceinline__ bool setup_triangle(const BufGeom& g, int cullMode, c
     bool clockwise;
     if (!project_and_cull(g, cullMode, c0, c1, c2, p0, p1, p2, clockwise))
         return false;
-    raster_setup(p0, p1, p2, clockwise, ec);
+    if (!ec.countOnly)
+        raster_setup(p0, p1, p2, clockwise, ec);
     return true;
 }
 
@@ -848,6 +850,7 @@ __device__ __forceinline__ EmitCtx make_emit_ctx(const BufGeom& g, const TileGeo
     ec.forceIrregular = rd.forceIrregular;
     ec.laneAreaMax = rd.laneAreaMax;
     ec.warpAreaMax = rd.warpAreaMax;
+    ec.countOnly = rd.countOnly;
     return ec;
 }
 
@@ -927,12 +930,19 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
         const uint32_t nLocal = min((uint32_t)kSetupItems, nItems - itemBase);
         __syncthreads(); // previous slice fully consumed
         if (threadIdx.x < nLocal)
-            sItem[threadIdx.x] = items[(size_t)v * itemCap + itemBase + threadIdx.x];
+        {
+            DrawItem it = items[(size_t)v * itemCap + itemBase + threadIdx.x];
+            if (rd.itemPass && rd.itemPass[(size_t)v * itemCap + itemBase + threadIdx.x] != rd.pass)
+                it.count = 0; // another pass's item (two-phase occluder drawing)
+            sItem[threadIdx.x] = it;
+        }
         __syncthreads();
         // modelViewProj = viewProj_ * model  (Matrix4 * Matrix3x4, Matrix4.cpp:43-63)
         for (uint32_t e = threadIdx.x; e < nLocal * 16; e += blockDim.x)
         {
             const uint32_t it = e >> 4, r = (e >> 2) & 3, c = e & 3;
+            if (!sItem[it].count)
+                continue;
             const float* a = vc.vp + 4 * r;
             const float* b = models + 12 * (size_t)sItem[it].model;
             float val;
@@ -1024,6 +1034,11 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
                         kind = 2;
                     else if (project_and_cull(g, cullMode, c0, c1, c2, p0, p1, p2, clockwise))
                         kind = 1;
+                }
+                if (kind == 1 && rd.countOnly)
+                {
+                    ++drawn; // DrawTriangle2D would run: drawOk
+                    kind = 0;
                 }
             }
             {
@@ -1445,11 +1460,15 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
     const int rows = min(kTileH, g.h - ty0); // valid rows of this tile
     const int tid = threadIdx.x, lane = tid & 31;
     int* depth = depthAll + (size_t)v * g.w * g.h;
-    const bool fromGlobal = rd.irrOfView[v] != 0;
+    // second pass of the two-phase occluder drawing: composite on top of what the first pass left in HBM; tiles without new triangles
+    // keep their depth and their hierarchy texels
+    const bool fromGlobal = rd.secondPass || rd.irrOfView[v] != 0;
 
     // ---- tiles nothing was binned to: constant depth and constant mips, no shared-memory round trip ----
     {
         const uint32_t* bc = rd.binCount + ((size_t)v * tg.numTiles + tIdx) * kNumCls;
+        if (rd.secondPass && rd.irrOfView[v] == 0 && (bc[0] | bc[1] | bc[2]) == 0)
+            return;
         if (!fromGlobal && (bc[0] | bc[1] | bc[2]) == 0)
         {
             const int tw4 = tw >> 2;
@@ -1864,7 +1883,8 @@ void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* 
 {
     if (!numViews)
         return;
-    k_irregular_clear<<<dim3(4, numViews), 256, 0, s>>>(g, depth, rd.irrOfView);
+    if (!rd.secondPass)
+        k_irregular_clear<<<dim3(4, numViews), 256, 0, s>>>(g, depth, rd.irrOfView);
     k_irregular_fill<<<148, 256, 0, s>>>(g, depth, rd.pool, rd.triBase, rd.irrList, rd.irrCap, rd.irrTotal);
     k_fill_tiles<<<dim3(tg.numTiles, numViews), kTileThreads, (size_t)tg.tileW * kTileH * 4, s>>>(g, tg, depth, mips, rd);
 }
