@@ -17,7 +17,16 @@ ln -sfn "$SRC" "$OUT/inc/Urho3D"
 ln -sfn "$TP/SDL/include" "$OUT/inc/SDL"
 ln -sfn "$TP/PugiXml/src" "$OUT/inc/PugiXml"
 CXXFLAGS="-std=c++11 -O3 -DNDEBUG -msse3 -ffp-contract=off -fPIC -w -DGLEW_NO_GLU -DGLEW_STATIC -DURHO3D_STATIC_DEFINE -DURHO3D_THREADING -DURHO3D_LOGGING -DURHO3D_OPENGL -DURHO3D_SSE \
- -I$HERE/ref_stub -I$HERE/ref_stub/Urho3D -I$HERE/ref_stub/sdlcfg -I$OUT/inc -I$SRC -I$REF/Source -I$TP -I$TP/SDL/include -I$TP/rapidjson/include -I$TP/WebP/src"
+ -I$OUT -I$HERE/ref_stub -I$HERE/ref_stub/Urho3D -I$HERE/ref_stub/sdlcfg -I$OUT/inc -I$SRC -I$REF/Source -I$TP -I$TP/SDL/include -I$TP/rapidjson/include -I$TP/WebP/src"
+# The three OctreeQuery subclasses that are file-local in View.cpp (ShadowCasterOctreeQuery, ZoneOccluderOctreeQuery,
+# OccludedFrustumOctreeQuery, View.cpp:58-157) are compiled from the reference's own text: the lines between the first class comment and
+# CheckVisibilityWork are extracted into a generated include (git-ignored, under oracle/_ref/) that ref_harness.cpp pulls into namespace
+# Urho3D.  View.cpp itself needs the GL back-end and cannot be compiled here.
+VIEWCPP="$SRC/Graphics/View.cpp"
+awk '/^\/\/\/ %Frustum octree query for shadowcasters\./{on=1} /^void CheckVisibilityWork\(/{on=0} on' "$VIEWCPP" > "$OUT/view_queries.inc"
+for c in "class ShadowCasterOctreeQuery" "class ZoneOccluderOctreeQuery" "class OccludedFrustumOctreeQuery"; do
+  grep -q "$c" "$OUT/view_queries.inc" || { echo "could not extract '$c' from $VIEWCPP"; exit 1; }
+done
 FILES=""
 for d in Container Math Core IO Resource Scene; do FILES="$FILES $(ls $SRC/$d/*.cpp)"; done
 for f in OcclusionBuffer Octree OctreeQuery Camera Drawable GraphicsDefs; do FILES="$FILES $SRC/Graphics/$f.cpp"; done

@@ -7,8 +7,8 @@
 //     world AABBs are supplied directly (a test Drawable subclass),
 //   * the reference Camera (Camera.cpp:284-308 frustum, :585-595 view, :648-691 projection),
 //   * the reference OcclusionBuffer (OcclusionBuffer.h:101-158),
-//   * a verbatim-behaviour restatement of the ~45-line OccludedFrustumOctreeQuery /
-//     ShadowCasterOctreeQuery classes, which are private to View.cpp:59-158 and so cannot be linked,
+//   * the reference's OWN text of ShadowCasterOctreeQuery / ZoneOccluderOctreeQuery / OccludedFrustumOctreeQuery (file-local classes of
+//     View.cpp:58-157), extracted by the build recipe into a generated include and compiled here,
 //   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
 //     View.cpp:897-920 does when worker threads exist.
 //
@@ -37,10 +37,20 @@
 #include <Urho3D/Math/Ray.h>
 #include <Urho3D/Container/Sort.h>
 
+// The reference's own text of View.cpp:58-157 (ShadowCasterOctreeQuery, ZoneOccluderOctreeQuery, OccludedFrustumOctreeQuery), extracted at
+// build time by oracle/build_ref.sh into oracle/_ref/view_queries.inc: the classes are file-local in View.cpp, which cannot be compiled here.
+namespace Urho3D
+{
+#include "view_queries.inc"
+}
+
 using namespace Urho3D;
 
 namespace
 {
+using ZoneOccluderQuery = ZoneOccluderOctreeQuery;
+using OccludedQuery = OccludedFrustumOctreeQuery;
+using ShadowCasterQuery = ShadowCasterOctreeQuery;
 
 /// Drawable whose world AABB is handed in by the test, and whose DrawOcclusion does what
 /// StaticModel::DrawOcclusion does (StaticModel.cpp:189-228): SetCullMode + indexed AddTriangles.
@@ -66,82 +76,6 @@ public:
 
     BoundingBox fixedWorldBox_;
     int id_{};
-};
-
-/// Behavioural restatement of View.cpp:87-113 (class is file-local there): zones and occluders inside a frustum.
-class ZoneOccluderQuery : public FrustumOctreeQuery
-{
-public:
-    ZoneOccluderQuery(PODVector<Drawable*>& result, const Frustum& frustum, unsigned char flags, unsigned mask) :
-        FrustumOctreeQuery(result, frustum, flags, mask) {}
-
-    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
-    {
-        while (start != end)
-        {
-            Drawable* drawable = *start++;
-            unsigned char flags = drawable->GetDrawableFlags();
-            if ((flags == DRAWABLE_ZONE || (flags == DRAWABLE_GEOMETRY && drawable->IsOccluder())) && (drawable->GetViewMask() & viewMask_))
-            {
-                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
-                    result_.Push(drawable);
-            }
-        }
-    }
-};
-
-/// Behavioural restatement of View.cpp:116-158 (class is file-local there).
-class OccludedQuery : public FrustumOctreeQuery
-{
-public:
-    OccludedQuery(PODVector<Drawable*>& result, const Frustum& frustum, OcclusionBuffer* buffer, unsigned char flags, unsigned mask) :
-        FrustumOctreeQuery(result, frustum, flags, mask), buffer_(buffer) {}
-
-    Intersection TestOctant(const BoundingBox& box, bool inside) override
-    {
-        if (inside)
-            return buffer_->IsVisible(box) ? INSIDE : OUTSIDE;
-        Intersection result = frustum_.IsInside(box);
-        if (result != OUTSIDE && !buffer_->IsVisible(box))
-            result = OUTSIDE;
-        return result;
-    }
-
-    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
-    {
-        while (start != end)
-        {
-            Drawable* drawable = *start++;
-            if ((drawable->GetDrawableFlags() & drawableFlags_) && (drawable->GetViewMask() & viewMask_))
-            {
-                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
-                    result_.Push(drawable);
-            }
-        }
-    }
-
-    OcclusionBuffer* buffer_;
-};
-
-/// Behavioural restatement of View.cpp:59-84.
-class ShadowCasterQuery : public FrustumOctreeQuery
-{
-public:
-    ShadowCasterQuery(PODVector<Drawable*>& result, const Frustum& frustum, unsigned char flags, unsigned mask) :
-        FrustumOctreeQuery(result, frustum, flags, mask) {}
-
-    void TestDrawables(Drawable** start, Drawable** end, bool inside) override
-    {
-        while (start != end)
-        {
-            Drawable* drawable = *start++;
-            if (drawable->GetCastShadows() && (drawable->GetDrawableFlags() & drawableFlags_) && (drawable->GetViewMask() & viewMask_))
-            {
-                if (inside || frustum_.IsInsideFast(drawable->GetWorldBoundingBox()))
-                    result_.Push(drawable);
-            }
-        }
-    }
 };
 
 struct Ref
