@@ -241,8 +241,11 @@ U3D_API int u3d_batch_run(u3d_batch* b, int stage, void* stream);
 /* Parts of the pipeline, for measurement: 1 = raster+hierarchy only, 2 = cull only (buffers from a previous run). */
 U3D_API int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream);
 /* u3d_batch_run with a CUDA event after each phase; synchronises and returns the device time of each phase in milliseconds:
- * 0 clear, 1 occluder select, 2 region scan, 3 triangle set-up, 4 depth fill, 5 depth hierarchy, 6 octree query + visibility. */
-#define U3D_NUM_PHASES 7
+ * 0 clear, 1 occluder select (+ near / far split), 2 region scan, 3 triangle set-up (first pass), 4 depth fill + fused hierarchy (first
+ * pass), 5 remaining hierarchy levels + the second pass of the two-phase occluder drawing (box test, set-up, fill),
+ * 6 octree walk (octant tests), 7 drawable query tests, 8 occlusion predicate over the query's survivors, 9 ordered result emission.
+ * The one-CTA-per-view cull kernel (small batches) reports its whole time under 6. */
+#define U3D_NUM_PHASES 10
 U3D_API int u3d_batch_run_timed(u3d_batch* b, int stage, void* stream, float* phase_ms);
 /* Results.  counts = n x 2 uint32: (query result size, emitted count).  Synchronises `stream`; reports pool/output overflow. */
 U3D_API int u3d_batch_read_counts(u3d_batch* b, uint32_t* counts, void* stream);

@@ -50,6 +50,68 @@ def cpu_view(sc, views, w, h, mesh=None):
     return round(dt * 1e3, 3)
 
 
+def cpu_shadow_views(sc, views, budget_s=20.0):
+    """C4 on the host: the reference's ShadowCasterOctreeQuery (its own text, View.cpp:59-84) per shadow view, one thread, as many of the
+    388 views as fit into the time budget (the four cascades first: they dominate)."""
+    from oracle import refbind
+    if not refbind.available():
+        return {}
+    ref = refbind.Ref(0)
+    ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
+    ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    t0 = time.perf_counter()
+    per = []
+    for v in views:
+        t1 = time.perf_counter()
+        ref.set_view_raw(v)
+        ref.query(2)
+        per.append(time.perf_counter() - t1)
+        if time.perf_counter() - t0 > budget_s:
+            break
+    ref.close()
+    n = len(per)
+    # cascades are views 0-3; the cube faces are alike, so the unmeasured ones are taken at the measured faces' mean
+    faces = per[4:] or per
+    est = sum(per) + (len(views) - n) * (sum(faces) / len(faces))
+    return {"cpu_ref_views_timed": n, "cpu_ref_ms_timed": round(sum(per) * 1e3, 2), "cpu_ref_ms_all_views_1thread": round(est * 1e3, 2),
+            "cpu_ref_note": "ShadowCasterOctreeQuery per view with the compiled reference, one thread; views beyond the time budget extrapolated from the "
+                            "measured cube faces"}
+
+
+def cpu_city_view(sc, view, w, h, vtx, idx):
+    """C5 on the host: the 250k-triangle mesh through the reference's AddTriangles / DrawTriangles / BuildDepthHierarchy, its occluded query and
+    the visibility predicate over the query's survivors, one thread."""
+    from oracle import refbind
+    if not refbind.available():
+        return {}
+    ref = refbind.Ref(0)
+    ref.octree_set_size(sc.octree_min, sc.octree_max, sc.octree_levels)
+    ref.add_drawables(sc.aabb, sc.flags, sc.view_mask, sc.occludee, sc.cast_shadows)
+    ref.ob_set_size(w, h)
+    ident = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    best = None
+    for _ in range(2):
+        ref.set_view_raw(view)
+        t0 = time.perf_counter()
+        ref.ob_set_max_triangles(1 << 30)
+        ref.ob_clear()
+        ref.ob_set_cull_mode(capi.CULL_CCW)
+        ref.ob_add_triangles(ident, vtx, 12, idx, 0, idx.shape[0])
+        ref.ob_draw()
+        t1 = time.perf_counter()
+        ref.ob_build_hierarchy()
+        t2 = time.perf_counter()
+        q = ref.query(1)
+        t3 = time.perf_counter()
+        vis = ref.check_visibility(True)
+        t4 = time.perf_counter()
+        cur = {"raster": t1 - t0, "hierarchy": t2 - t1, "query": t3 - t2, "visibility": t4 - t3, "total": t4 - t0}
+        if best is None or cur["total"] < best["total"]:
+            best = cur
+    ref.close()
+    return {"cpu_ref_ms_1thread": {k: round(v * 1e3, 3) for k, v in best.items()}, "cpu_ref_query_result": int(len(q)), "cpu_ref_visible": int(len(vis))}
+
+
 def run(name, cpu):
     cfg = scenes.CONFIGS[name]
     ctx = capi.Context(0)
@@ -99,7 +161,11 @@ def run(name, cpu):
         batch.cull_views(packed, capi.STAGE_VISIBLE)
         t.append(time.perf_counter() - t0)
     out["call_ms"] = round(statistics.median(t) * 1e3, 3)
-    if cpu and name not in ("C4", "C5"):
+    if cpu and name == "C4":
+        out.update(cpu_shadow_views(sc, views))
+    elif cpu and name == "C5":
+        out.update(cpu_city_view(sc, views[0], w, h, vtx, idx))
+    elif cpu:
         out["cpu_ref_ms_per_view_1thread"] = cpu_view(sc, views, w, h)
     print(json.dumps(out), flush=True)
     for o in (batch, occ, mesh, gs, tree, ctx):

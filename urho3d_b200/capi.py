@@ -524,7 +524,7 @@ class Batch:
     def run(self, stage=STAGE_VISIBLE, stream=None, part=0):
         _chk(lib().u3d_batch_run_part(self.h, part, stage, stream))
 
-    PHASES = ("clear", "select", "scan", "setup", "fill", "hierarchy", "cull")
+    PHASES = ("clear", "select", "scan", "setup", "fill", "second_pass", "tree", "frustum", "occlusion", "emit")
 
     def run_timed(self, stage=STAGE_VISIBLE, stream=None):
         """Run with a CUDA event after each phase; returns dict phase -> device milliseconds (synchronises)."""

@@ -25,7 +25,7 @@ static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
 // "two_phase": 1 = the batched path draws a view's nearest occluders first and the others only if their box shows in that buffer
 // (launch_items_near_far / launch_items_far_test), 0 = every selected occluder is set up and filled.  "two_phase_min" / "two_phase_shift":
 // the near set holds at least that many draw items, or 1 / 2^shift of the view's items.
-static int g_twoPhase = 1, g_twoPhaseMin = 32, g_twoPhaseShift = 3;
+static int g_twoPhase = 1, g_twoPhaseMin = 32, g_twoPhaseShift = 4;
 static int g_readDenseProf = 0; // "read_dense_prof": u3d_debug_read_cull_prof returns the dense path's timers
 constexpr int kDenseMinViews = 16;
 
@@ -2240,7 +2240,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
                 return rc;
             CU_CHECK(b->dense.next_epoch(st));
             launch_cull_dense(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p,
-                vs.flags.p, b->dense.dev, st);
+                vs.flags.p, b->dense.dev, st, timed ? b->ev + 7 : nullptr);
             // answered on the device if the dense path's scratch overflowed (returns at once otherwise)
             launch_cull(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stateStride, stage, b->outIdx.p, b->outCap, b->outCounts.p,
                 b->zRange.p, vs.flags.p, b->pipelined, b->dense.dev.ctr + 34, st);
@@ -2251,10 +2251,17 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             launch_cull(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stateStride, stage, b->outIdx.p, b->outCap, b->outCounts.p,
                 b->zRange.p, vs.flags.p, b->pipelined, nullptr, st);
             b->lastLaunches += 1;
+            for (int p = 7; p <= 9; ++p)
+                CU_CHECK(mark(p));
         }
         CU_CHECK(cudaGetLastError());
     }
-    CU_CHECK(mark(7));
+    else
+    {
+        for (int p = 7; p <= 9; ++p)
+            CU_CHECK(mark(p));
+    }
+    CU_CHECK(mark(10));
     return U3D_OK;
 }
 

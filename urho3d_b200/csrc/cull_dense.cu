@@ -1397,7 +1397,7 @@ static int g_denseWalker = 1; // "dense_walker": 1 = occlusion predicate with th
 
 void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, const DenseDev& dd,
-    cudaStream_t s)
+    cudaStream_t s, cudaEvent_t* phaseEvents)
 {
     if (!numViews)
         return;
@@ -1439,10 +1439,14 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         for (int lv = 1; lv < sc.numLevels; ++lv)
             k_dense_level<<<gridLevel, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, lv);
     }
+    if (phaseEvents)
+        cudaEventRecord(phaseEvents[0], s);
     k_dense_groups<<<grid, kDenseThreads, 0, s>>>(sc, numViews, octState, dd);
     k_dense_scan<<<(numViews * 32 + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(numViews, dd);
     k_dense_words<<<grid, kDenseThreads, 0, s>>>(sc, octState, dd);
     k_dense_frustum<<<gridFrustum, kDenseThreads, 0, s>>>(sc, views, stage, outCounts, dd);
+    if (phaseEvents)
+        cudaEventRecord(phaseEvents[1], s);
     if (stage >= STAGE_VISIBLE && depth)
     {
         if (g_denseWalker && mipsValid && g.nlev <= 16)
@@ -1450,6 +1454,8 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         else
             k_dense_occlusion<<<gridOcc, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, dd);
     }
+    if (phaseEvents)
+        cudaEventRecord(phaseEvents[2], s);
     k_dense_emit<<<numViews, kDenseThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd);
 }
 

@@ -1452,6 +1452,8 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
 {
     extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
     __shared__ uint32_t sNext[2];
+    constexpr int kCtaStage = kTileThreads / 4; // CTA-class records staged per batch: one int4 per thread
+    __shared__ int4 sCtaTri[kCtaStage][4];
 
     const int v = blockIdx.y;
     const int tIdx = blockIdx.x;
@@ -1521,7 +1523,69 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
     const int ty1 = ty0 + rows, tx1 = tx0 + tw;
     const uint32_t nLane = min(binCount[kClsLane], cap), nWarp = min(binCount[kClsWarp], cap), nCta = min(binCount[kClsCta], cap);
 
-    // (1) small triangles (bbox area <= 64; 86 % of the triangles of the benchmark scene): one per lane, groups of 32 handed out
+    // (1) large triangles first: the whole CTA, and nothing else touches the tile meanwhile.  Row y of the tile belongs to warp y mod 16 for
+    //     EVERY triangle of this class, so a warp is the only writer of its rows: plain read-modify-write, no atomics, and each lane takes
+    //     4 neighbouring pixels with one 16-byte load and one 16-byte store (the tile's rows are 16-byte aligned, tw is a multiple of 4).
+    {
+        const uint32_t* bin = binBase + (size_t)kClsCta * cap;
+        const int wid = tid >> 5;
+        constexpr int kWarps = kTileThreads / 32;
+        // The records are staged in shared memory 128 at a time by all threads (one coalesced 16-byte load each): every warp walks every
+        // record of this class, and a 64-byte L2 round trip per record and warp is what the tile would otherwise wait for.
+        for (uint32_t base = 0; base < nCta; base += kCtaStage)
+        {
+            const uint32_t nStage = min((uint32_t)kCtaStage, nCta - base);
+            __syncthreads(); // the previous batch has been walked by every warp
+            if ((uint32_t)(tid >> 2) < nStage)
+                sCtaTri[tid >> 2][tid & 3] = reinterpret_cast<const int4*>(region + (bin[base + (tid >> 2)] & 0x1FFFFFFFu))[tid & 3];
+            __syncthreads();
+        for (uint32_t i = 0; i < nStage; ++i)
+        {
+            TriSetup ts;
+            {
+                const int4 a = sCtaTri[i][0], b = sCtaTri[i][1], c = sCtaTri[i][2], d = sCtaTri[i][3];
+                ts.y0 = a.x; ts.y1 = a.y; ts.y2 = a.z; ts.dzdx = a.w;
+                ts.tlx = b.x; ts.tlxs = b.y; ts.tlz = b.z; ts.tlzs = b.w;
+                ts.trx = c.x; ts.trxs = c.y; ts.blx = c.z; ts.blxs = c.w;
+                ts.blz = d.x; ts.blzs = d.y; ts.brx = d.z; ts.brxs = d.w;
+            }
+            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+            // first row >= ya owned by this warp (rows are counted from the tile's first row)
+            const int first = ya + ((wid - (ya - ty0)) & (kWarps - 1));
+            for (int y = first; y < yb; y += kWarps)
+            {
+                const HalfRow r = tri_row(ts, y);
+                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
+                if (xa >= xb)
+                    continue;
+                int* trow = tile + (y - ty0) * tw - tx0;
+                if ((tw & 3) == 0)
+                {
+                    for (int x4 = ((xa - tx0) & ~3) + tx0 + 4 * lane; x4 < xb; x4 += 128)
+                    {
+                        int4 d = *reinterpret_cast<int4*>(trow + x4);
+                        const uint32_t z0 = r.z0 + (uint32_t)(x4 - r.xl) * (uint32_t)ts.dzdx;
+                        const int za = (int)z0, zb = (int)(z0 + (uint32_t)ts.dzdx), zc = (int)(z0 + 2u * (uint32_t)ts.dzdx), zd = (int)(z0 + 3u * (uint32_t)ts.dzdx);
+                        if (x4 >= xa && x4 < xb && za < d.x) d.x = za;
+                        if (x4 + 1 >= xa && x4 + 1 < xb && zb < d.y) d.y = zb;
+                        if (x4 + 2 >= xa && x4 + 2 < xb && zc < d.z) d.z = zc;
+                        if (x4 + 3 >= xa && x4 + 3 < xb && zd < d.w) d.w = zd;
+                        *reinterpret_cast<int4*>(trow + x4) = d;
+                    }
+                }
+                else
+                    for (int x = xa + lane; x < xb; x += 32)
+                    {
+                        const int z = (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx);
+                        if (z < trow[x])
+                            trow[x] = z;
+                    }
+            }
+        }
+        }
+    }
+    __syncthreads(); // the other classes composite with atomics, from any warp
+    // (2) small triangles (bbox area <= 64; 86 % of the triangles of the benchmark scene): one per lane, groups of 32 handed out
     //     dynamically
     {
         const uint32_t* bin = binBase + (size_t)kClsLane * cap;
@@ -1548,7 +1612,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             }
         }
     }
-    // (2) medium triangles: one warp each.  The warp is laid out as (32 / L) rows x L lanes per row, L chosen at set-up so that every
+    // (3) medium triangles: one warp each.  The warp is laid out as (32 / L) rows x L lanes per row, L chosen at set-up so that every
     //     lane walks about 8 pixels of its row; groups of 8 triangles are handed out so that short bins still use all warps.
     {
         const uint32_t* bin = binBase + (size_t)kClsWarp * cap;
@@ -1588,24 +1652,6 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
                             tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
                     }
                 }
-            }
-        }
-    }
-    // (3) large triangles: the whole CTA, rows interleaved over the warps, lanes across the span
-    {
-        const uint32_t* bin = binBase + (size_t)kClsCta * cap;
-        const int wid = tid >> 5;
-        for (uint32_t i = 0; i < nCta; ++i)
-        {
-            const TriSetup ts = load_tri(region + (bin[i] & 0x1FFFFFFFu));
-            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
-            for (int y = ya + wid; y < yb; y += kTileThreads / 32)
-            {
-                const HalfRow r = tri_row(ts, y);
-                const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
-                int* trow = tile + (y - ty0) * tw - tx0;
-                for (int x = xa + lane; x < xb; x += 32)
-                    tile_min(trow, x, (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx));
             }
         }
     }
