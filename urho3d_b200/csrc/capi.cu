@@ -2240,7 +2240,7 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
                 return rc;
             CU_CHECK(b->dense.next_epoch(st));
             launch_cull_dense(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stage, b->outIdx.p, b->outCap, b->outCounts.p, b->zRange.p,
-                vs.flags.p, b->dense.dev, st, timed ? b->ev + 7 : nullptr);
+                vs.flags.p, b->dense.dev, st, timed ? b->ev + 7 : nullptr, b->pipelined);
             // answered on the device if the dense path's scratch overflowed (returns at once otherwise)
             launch_cull(sc, vs.g, vs.views.p, V, vs.depth.p, vs.mips.p, 1, b->octState.p, stateStride, stage, b->outIdx.p, b->outCap, b->outCounts.p,
                 b->zRange.p, vs.flags.p, b->pipelined, b->dense.dev.ctr + 34, st);

@@ -23,8 +23,15 @@
 namespace u3d
 {
 
-constexpr int kDenseThreads = 256;
+// Block size of the persistent / grid-stride kernels.  Small blocks: a block's SM resources are released when its LAST warp is done, and
+// with several batches in flight on their own streams the next launch's blocks move in as soon as they are (measured: see profiles).
+#ifndef U3D_DENSE_THREADS
+#define U3D_DENSE_THREADS 128 // A/B at 4096 views, 8 batches in flight: 622 k views/s with 256, 652 k with 128 or 64
+#endif
+constexpr int kDenseThreads = U3D_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
+constexpr int kDenseMinBlocks = 3 * 256 / kDenseThreads; // the walking kernels: 768 threads (<= 85 registers) per SM
+constexpr int kEmitThreads = 256, kEmitWarps = kEmitThreads / 32; // k_dense_emit: one block per view
 constexpr int kDenseWStack = 128;  // per-warp texel stack of the cooperative range test
 
 __device__ int g_denseHeavyExtent = 64; // rect extent (pixels) from which a box is walked by the whole warp (tuning hook "dense_heavy")
@@ -762,7 +769,7 @@ __device__ __forceinline__ void level_finalize(const SceneDev& sc, const DenseDe
 }
 
 /// TestOctant for every queued (view, octant) pair of one level; the pairs of level `level` sit behind those of the levels before it.
-__global__ void __launch_bounds__(kDenseThreads, 3) k_dense_level(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+__global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_level(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
     const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ stateAll, DenseDev dd, int level)
 {
     __shared__ WalkShared sh;
@@ -945,7 +952,7 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_tree_seed(SceneDev sc, 
     }
 }
 
-__global__ void __launch_bounds__(kDenseThreads, 3) k_dense_tree(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
+__global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_tree(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views, const int* __restrict__ depthAll,
     const int2* __restrict__ mipAll, int mipsValid, unsigned char* __restrict__ stateAll, DenseDev dd, uint32_t epochTag)
 {
     __shared__ WalkShared sh;
@@ -1151,11 +1158,11 @@ __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion
 
 /// Per view: ids of the set bits of the view's words in order (= the reference's result_ order), counts, and for the in-view stage the
 /// view-space Z range of the geometries (View.cpp:198-211, merged as View.cpp:926-951).
-__global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outIdx,
+__global__ void __launch_bounds__(kEmitThreads) k_dense_emit(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outIdx,
     uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags, DenseDev dd)
 {
-    __shared__ uint32_t warpTot[kDenseWarps];
-    __shared__ float red[2 * kDenseWarps];
+    __shared__ uint32_t warpTot[kEmitWarps];
+    __shared__ float red[2 * kEmitWarps];
     if (dd.ctr[CTR_FALLBACK])
         return;
     const int v = blockIdx.x;
@@ -1168,7 +1175,7 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const
     uint32_t* out = outIdx + (size_t)v * outCap;
     uint32_t cursor = 0;
     float zMin = __int_as_float(0x7f800000), zMax = 0.0f; // PerThreadSceneResult::minZ_/maxZ_ start values, View.cpp:893-894
-    for (uint32_t base = 0; base < nWords; base += kDenseThreads)
+    for (uint32_t base = 0; base < nWords; base += kEmitThreads)
     {
         const uint32_t i = base + tid;
         uint32_t word = i < nWords ? words[i] : 0u;
@@ -1188,7 +1195,7 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const
         __syncthreads();
         uint32_t pre = 0, tot = 0;
 #pragma unroll
-        for (int w = 0; w < kDenseWarps; ++w)
+        for (int w = 0; w < kEmitWarps; ++w)
         {
             const uint32_t t = warpTot[w];
             if (w < wid)
@@ -1245,7 +1252,7 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_emit(SceneDev sc, const
         __syncthreads();
         if (tid == 0)
         {
-            for (int w = 1; w < kDenseWarps; ++w)
+            for (int w = 1; w < kEmitWarps; ++w)
             {
                 zMin = red[2 * w] < zMin ? red[2 * w] : zMin;
                 zMax = red[2 * w + 1] > zMax ? red[2 * w + 1] : zMax;
@@ -1390,14 +1397,14 @@ size_t dense_counter_bytes(int numViews, int numOctants)
 }
 
 static int g_denseGrid = 0;
-static int g_denseTreeBlocks = 0; // "dense_tree_blocks": blocks per SM of the persistent tree kernel (0 = as many as fit)
+static int g_denseTreeBlocks = 0; // "dense_tree_blocks": 256-thread units per SM of the persistent tree kernel (0 = as many as fit)
 static int gridSms = 148;
 static int g_denseTree = 1;   // "dense_tree": 1 = all octree levels in one persistent launch (k_dense_tree), 0 = one launch per level
 static int g_denseWalker = 1; // "dense_walker": 1 = occlusion predicate with the warp walker, 0 = one walk per lane
 
 void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, const DenseDev& dd,
-    cudaStream_t s, cudaEvent_t* phaseEvents)
+    cudaStream_t s, cudaEvent_t* phaseEvents, bool pipelined)
 {
     if (!numViews)
         return;
@@ -1419,7 +1426,7 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         gridOcc = fit(k_dense_occlusion);
         gridOccWalk = fit(k_dense_occlusion_walk);
         gridFrustum = fit(k_dense_frustum);
-        gridLight = sms * 8;
+        gridLight = sms * 8 * (256 / kDenseThreads);
         g_denseGrid = sms * 6;
     }
     const int grid = gridLight;
@@ -1430,7 +1437,11 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
     {
         const uint32_t epochTag = dd.epoch << 16; // 1..65535, new every run (capi.cu wipes the queue when it wraps)
         k_dense_tree_seed<<<(numViews + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(sc, views, numViews, octState, outCounts, dd, epochTag);
-        const int blocks = g_denseTreeBlocks > 0 ? std::min(gridTree, gridSms * g_denseTreeBlocks) : gridTree;
+        // With other batches in flight on their own streams the persistent kernel takes one 256-thread unit per SM: it spends much of its
+        // life waiting for the next octree level's pairs, and a full-size grid would keep everybody else off the GPU meanwhile (512 views,
+        // 12 batches in flight: 407 k views/s full size, 483 k with one unit; 4096 views: the same either way).  Alone, it takes every slot.
+        const int units = g_denseTreeBlocks > 0 ? g_denseTreeBlocks : (pipelined ? 1 : 0);
+        const int blocks = units > 0 ? std::min(gridTree, gridSms * units * (256 / kDenseThreads)) : gridTree;
         k_dense_tree<<<blocks, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, epochTag);
     }
     else
@@ -1456,7 +1467,7 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
     }
     if (phaseEvents)
         cudaEventRecord(phaseEvents[2], s);
-    k_dense_emit<<<numViews, kDenseThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd);
+    k_dense_emit<<<numViews, kEmitThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd);
 }
 
 int dense_launch_count(const SceneDev& sc)

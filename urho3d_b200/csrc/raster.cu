@@ -1448,7 +1448,10 @@ __device__ __forceinline__ void tile_min(int* tile, int idx, int z)
         atomicMin(tile + idx, z);
 }
 
-__global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
+#ifndef U3D_TILE_MINB
+#define U3D_TILE_MINB 2
+#endif
+__global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
 {
     extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
     __shared__ uint32_t sNext[2];
@@ -1458,7 +1461,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
     const int v = blockIdx.y;
     const int tIdx = blockIdx.x;
     const int tx0 = (tIdx % tg.tilesX) * tg.tileW, ty0 = (tIdx / tg.tilesX) * kTileH;
-    const int tw = tg.tileW;
+    const int tw = tg.tileW, twLog = tg.tileWLog, tw4Log = twLog - 2;
     const int rows = min(kTileH, g.h - ty0); // valid rows of this tile
     const int tid = threadIdx.x, lane = tid & 31;
     int* depth = depthAll + (size_t)v * g.w * g.h;
@@ -1476,7 +1479,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             const int tw4 = tw >> 2;
             const int4 c4 = make_int4(kClearDepth, kClearDepth, kClearDepth, kClearDepth);
             for (int i = tid; i < tw4 * rows; i += kTileThreads)
-                *reinterpret_cast<int4*>(depth + (size_t)(ty0 + i / tw4) * g.w + tx0 + ((i % tw4) << 2)) = c4;
+                *reinterpret_cast<int4*>(depth + (size_t)(ty0 + (i >> tw4Log)) * g.w + tx0 + ((i & (tw4 - 1)) << 2)) = c4;
             if (tg.fused && rd.writeMips)
             {
                 int2* mips = mipAll + (size_t)v * g.mipTexels;
@@ -1487,7 +1490,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
                     const int gy0 = ty0 >> (lv + 1), gx0 = tx0 >> (lv + 1);
                     const int lrows = min(g.mh[lv] - gy0, kTileH >> (lv + 1));
                     for (int i = tid; i < lw * lrows; i += kTileThreads)
-                        mips[g.moff[lv] + (size_t)(gy0 + i / lw) * g.mw[lv] + gx0 + i % lw] = c2;
+                        mips[g.moff[lv] + (size_t)(gy0 + (i >> (twLog - lv - 1))) * g.mw[lv] + gx0 + (i & (lw - 1))] = c2;
                 }
             }
             return;
@@ -1502,9 +1505,9 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         for (int i = tid; i < n4; i += kTileThreads)
         {
             int4 val = make_int4(kClearDepth, kClearDepth, kClearDepth, kClearDepth);
-            const int r = i / tw4;
+            const int r = i >> tw4Log;
             if (fromGlobal && r < rows)
-                val = *reinterpret_cast<const int4*>(depth + (size_t)(ty0 + r) * g.w + tx0 + ((i % tw4) << 2));
+                val = *reinterpret_cast<const int4*>(depth + (size_t)(ty0 + r) * g.w + tx0 + ((i & (tw4 - 1)) << 2));
             t4[i] = val;
         }
         if (tid == 0)
@@ -1687,7 +1690,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         const int4* t4 = reinterpret_cast<const int4*>(tile);
         for (int i = tid; i < n4; i += kTileThreads)
         {
-            const int r = i / tw4, c4 = i % tw4;
+            const int r = i >> tw4Log, c4 = i & (tw4 - 1);
             *reinterpret_cast<int4*>(depth + (size_t)(ty0 + r) * g.w + tx0 + (c4 << 2)) = t4[i];
         }
     }
@@ -1717,7 +1720,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             const int i = tid + j * kTileThreads;
             if (i < n)
             {
-                const int x = i % lw, y = i / lw;
+                const int x = i & (lw - 1), y = i >> (twLog - 1);
                 const int2 a = *reinterpret_cast<const int2*>(tile + (2 * y) * tw + 2 * x);
                 int mn = min(a.x, a.y), mx = max(a.x, a.y);
                 if (2 * y + 1 < rows) // the buffer's last row pair may be a single row only when h is odd; heights are even, kept for safety
@@ -1740,7 +1743,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
             const int i = tid + j * kTileThreads;
             if (i < n)
             {
-                const int x = i % lw, y = i / lw;
+                const int x = i & (lw - 1), y = i >> (twLog - 1);
                 lv0[i] = acc[j];
                 mips[g.moff[0] + (size_t)((ty0 >> 1) + y) * g.mw[0] + (tx0 >> 1) + x] = acc[j];
             }
@@ -1760,7 +1763,7 @@ __global__ void __launch_bounds__(kTileThreads) k_fill_tiles(BufGeom g, TileGeom
         const int n = lw * lrows;
         for (int i = tid; i < n; i += kTileThreads)
         {
-            const int x = i % lw, y = i / lw;
+            const int x = i & (lw - 1), y = i >> (twLog - lv - 1);
             const int2 a = prev[(2 * y) * prevW + 2 * x], b = prev[(2 * y) * prevW + 2 * x + 1];
             int mn = min(a.x, b.x), mx = max(a.y, b.y);
             if (prevGy0 + 2 * y + 1 < prevGlobalH) // odd previous height: the last row reduces a single row (OB.cpp:297-324)
@@ -1836,6 +1839,9 @@ TileGeom make_tile_geom(const BufGeom& g)
         ++f;
     // the in-place level-0 pass keeps its inputs in registers: needs tileW >= 4 for the int4 paths
     t.fused = t.tileW >= 4 ? f : 0;
+    t.tileWLog = 0;
+    while ((1 << t.tileWLog) < t.tileW)
+        ++t.tileWLog;
     return t;
 }
 

@@ -35,6 +35,7 @@ constexpr int kWarpGroup = 8;         // warp-class triangles handed to a warp a
 struct TileGeom
 {
     int tileW, tilesX, tilesY, numTiles;
+    int tileWLog; // tileW is a power of two (min(width, 256), widths are powers of two): index arithmetic by shifts
     int fused;   // hierarchy levels reduced inside the tile kernel
 };
 
@@ -171,7 +172,8 @@ void dense_prof_read_levels(unsigned long long* out128);
 /// the caller queues launch_cull(..., onlyIf = ctr + 34) behind it.
 void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* views, int numViews, const int* depth, const int2* mips, int mipsValid,
     unsigned char* octState, int stage, uint32_t* outIdx, uint32_t outCap, uint32_t* outCounts, float* zRange, uint32_t* flags, const DenseDev& dd,
-    cudaStream_t s, cudaEvent_t* phaseEvents = nullptr /* 3 events: after the octree walk, after the drawable tests, after the occlusion pass */);
+    cudaStream_t s, cudaEvent_t* phaseEvents = nullptr /* 3 events: after the octree walk, after the drawable tests, after the occlusion pass */,
+    bool pipelined = false /* other batches are in flight on other streams: leave them room */);
 
 /// Ray::HitDistance of every drawable a QUERY_RAY / QUERY_RAY_CANDIDATES run emitted (slotOfId: drawable id -> DFS slot).
 void launch_ray_distances(const SceneDev& sc, const ViewConst* views, int numRays, const uint32_t* slotOfId, const uint32_t* outIdx, uint32_t outCap,
