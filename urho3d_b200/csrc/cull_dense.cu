@@ -30,7 +30,10 @@ namespace u3d
 #endif
 constexpr int kDenseThreads = U3D_DENSE_THREADS;
 constexpr int kDenseWarps = kDenseThreads / 32;
-constexpr int kDenseMinBlocks = 3 * 256 / kDenseThreads; // the walking kernels: 768 threads (<= 85 registers) per SM
+#ifndef U3D_TREE_UNITS
+#define U3D_TREE_UNITS 4 // 64 registers (A/B, 4096 views: 663 k views/s at 85 registers, 698 k at 64)
+#endif
+constexpr int kDenseMinBlocks = U3D_TREE_UNITS * 256 / kDenseThreads; // the octree kernels: 1024 threads (<= 64 registers) per SM
 constexpr int kEmitThreads = 256, kEmitWarps = kEmitThreads / 32; // k_dense_emit: one block per view
 constexpr int kDenseWStack = 128;  // per-warp texel stack of the cooperative range test
 
@@ -1070,7 +1073,8 @@ __global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_tree(S
 
 /// CheckVisibilityWork's occlusion predicate (View.cpp:177) over the drawables k_dense_frustum left to it.
 #ifndef U3D_OCC_MINB
-#define U3D_OCC_MINB 1
+#define U3D_OCC_MINB (1024 / U3D_DENSE_THREADS) // 64 registers: the kernel is bound by the latency of its dependent loads, more warps per SM win
+                                                 // over fewer spills (A/B, 4096 views: 649 k views/s at 80 registers, 673 k at 64, 667 k at 48)
 #endif
 __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion_walk(SceneDev sc, BufGeom g, const ViewConst* __restrict__ views,
     const int* __restrict__ depthAll, const int2* __restrict__ mipAll, DenseDev dd)
