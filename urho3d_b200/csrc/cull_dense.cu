@@ -1163,23 +1163,47 @@ __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion
 /// Per view: ids of the set bits of the view's words in order (= the reference's result_ order), counts, and for the in-view stage the
 /// view-space Z range of the geometries (View.cpp:198-211, merged as View.cpp:926-951).
 __global__ void __launch_bounds__(kEmitThreads) k_dense_emit(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outIdx,
-    uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags, DenseDev dd)
+    uint32_t outCap, uint32_t* __restrict__ outCounts, float* __restrict__ zRangeAll, uint32_t* __restrict__ flags, DenseDev dd, uint32_t chunkWords)
 {
     __shared__ uint32_t warpTot[kEmitWarps];
     __shared__ float red[2 * kEmitWarps];
     if (dd.ctr[CTR_FALLBACK])
         return;
-    const int v = blockIdx.x;
+    // grid (chunks, views): a view with a very long result (a shadow cascade over most of the scene) is emitted by several blocks, each
+    // over `chunkWords` of the view's words; a block finds its first output position by counting the bits of the words before its chunk
+    const int v = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const ViewConst& vc = views[v];
     const bool inViewStage = stage == STAGE_INVIEW;
-    const uint32_t nWords = dd.viewWords[v];
+    const uint32_t allWords = dd.viewWords[v];
+    // equal shares of the view's words (in units of 256), whatever their number
+    const uint32_t share = gridDim.x > 1 ? max(256u, ((allWords + gridDim.x - 1) / gridDim.x + 255u) / 256u * 256u) : chunkWords;
+    const uint32_t first = blockIdx.x * share;
+    if (first >= allWords && blockIdx.x != 0)
+        return;
+    const bool lastChunk = first + share >= allWords;
+    const uint32_t nWords = min(allWords, first + share);
     const uint32_t* words = dd.visWord + dd.wordBase[v];
     const uint32_t* slots = dd.wordSlot + dd.wordBase[v];
     uint32_t* out = outIdx + (size_t)v * outCap;
     uint32_t cursor = 0;
+    if (first)
+    {
+        uint32_t sum = 0;
+        for (uint32_t i = tid; i < first; i += kEmitThreads)
+            sum += (uint32_t)__popc(words[i]);
+#pragma unroll
+        for (int s = 16; s; s >>= 1)
+            sum += __shfl_xor_sync(0xffffffffu, sum, s);
+        if (lane == 0)
+            warpTot[wid] = sum;
+        __syncthreads();
+        for (int w = 0; w < kEmitWarps; ++w)
+            cursor += warpTot[w];
+        __syncthreads();
+    }
     float zMin = __int_as_float(0x7f800000), zMax = 0.0f; // PerThreadSceneResult::minZ_/maxZ_ start values, View.cpp:893-894
-    for (uint32_t base = 0; base < nWords; base += kEmitThreads)
+    for (uint32_t base = first; base < nWords; base += kEmitThreads)
     {
         const uint32_t i = base + tid;
         uint32_t word = i < nWords ? words[i] : 0u;
@@ -1267,7 +1291,7 @@ __global__ void __launch_bounds__(kEmitThreads) k_dense_emit(SceneDev sc, const 
             zRangeAll[2 * v + 1] = zMax;
         }
     }
-    if (tid == 0)
+    if (tid == 0 && lastChunk)
     {
         outCounts[2 * v + 1] = cursor;
         if (cursor > outCap)
@@ -1471,7 +1495,12 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
     }
     if (phaseEvents)
         cudaEventRecord(phaseEvents[2], s);
-    k_dense_emit<<<numViews, kEmitThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd);
+    {
+        // few views: several blocks per view (the in-view stage reduces a Z range per view in one block)
+        const uint32_t chunks = stage == STAGE_INVIEW ? 1u : std::min<uint32_t>(16u, std::max<uint32_t>(1u, (2048u + numViews - 1) / numViews));
+        const uint32_t chunkWords = 0x7FFFFFFFu;
+        k_dense_emit<<<dim3(chunks, numViews), kEmitThreads, 0, s>>>(sc, views, stage, outIdx, outCap, outCounts, zRange, flags, dd, chunkWords);
+    }
 }
 
 int dense_launch_count(const SceneDev& sc)

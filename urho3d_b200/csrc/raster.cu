@@ -7,6 +7,8 @@
 #include "u3d_device.cuh"
 #include "u3d_kernels.h"
 
+#include <algorithm>
+
 namespace u3d
 {
 
@@ -875,7 +877,7 @@ __global__ void __launch_bounds__(128) k_clip_triangles(BufGeom g, TileGeom tg, 
 /// space of those items.  DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
 __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
     const DrawItem* __restrict__ items, uint32_t itemCap, const uint32_t* __restrict__ itemCount, const float* __restrict__ models,
-    const MeshDev* __restrict__ meshes, RasterDev rd)
+    const MeshDev* __restrict__ meshes, RasterDev rd, uint32_t sliceItems /* <= kSetupItems: items a block takes at a time */)
 {
     const int v = blockIdx.y;
     const uint32_t nItems = itemCount[v];
@@ -925,9 +927,9 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
             sCount[0] = total - n;
         __syncthreads();
     };
-    for (uint32_t itemBase = blockIdx.x * kSetupItems; itemBase < nItems; itemBase += gridDim.x * kSetupItems)
+    for (uint32_t itemBase = blockIdx.x * sliceItems; itemBase < nItems; itemBase += gridDim.x * sliceItems)
     {
-        const uint32_t nLocal = min((uint32_t)kSetupItems, nItems - itemBase);
+        const uint32_t nLocal = min(sliceItems, nItems - itemBase);
         __syncthreads(); // previous slice fully consumed
         if (threadIdx.x < nLocal)
         {
@@ -1906,11 +1908,15 @@ void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, 
 {
     if (!maxItems || !numViews)
         return;
-    uint32_t slices = (maxItems + kSetupItems - 1) / kSetupItems;
-    // a few blocks per view sweep its item slices; single views get as many blocks as they have slices
-    const uint32_t perView = numViews >= 148 ? 8u : 1024u;
-    dim3 grid(slices < perView ? slices : perView, numViews);
-    k_setup_triangles<<<grid, kSetupThreads, kSetupQueueBytes, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd);
+    // A few blocks per view sweep its items in slices.  Many views: slices of kSetupItems (64 boxes = 768 triangles = 3 full sweeps of the
+    // block).  Few views (one 250k-triangle mesh = 977 items of 256 triangles): smaller slices, so that the launch still has a few blocks per SM.
+    const uint32_t wantBlocks = numViews >= 148 ? 8u : std::max<uint32_t>(8u, (148u * 4u + numViews - 1) / numViews);
+    uint32_t sliceItems = kSetupItems;
+    while (sliceItems > 1 && (maxItems + sliceItems - 1) / sliceItems < wantBlocks)
+        sliceItems >>= 1;
+    const uint32_t slices = (maxItems + sliceItems - 1) / sliceItems;
+    dim3 grid(std::min(slices, std::max(wantBlocks, 1u)), numViews);
+    k_setup_triangles<<<grid, kSetupThreads, kSetupQueueBytes, s>>>(g, tg, views, items, itemCap, itemCount, models, meshes, rd, sliceItems);
     k_clip_triangles<<<148 * 8, 128, 0, s>>>(g, tg, views, rd);
 }
 
