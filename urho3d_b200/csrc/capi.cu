@@ -541,6 +541,11 @@ int u3d_debug_set_option(const char* name, int value)
         dense_set_tree_blocks(value);
         return U3D_OK;
     }
+    if (name && std::strcmp(name, "frustum_bulk") == 0)
+    {
+        dense_set_frustum_bulk(value);
+        return U3D_OK;
+    }
     if (name && std::strcmp(name, "dense_tree") == 0)
     {
         dense_set_tree(value);

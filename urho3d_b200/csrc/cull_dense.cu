@@ -326,15 +326,45 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_words(SceneDev sc, cons
 /// (View.cpp:99-112) flat over the pool: one word = 32 consecutive drawables of one surviving octant of one view per warp step, two coalesced
 /// float4 loads per drawable.  Writes, per word, the drawables that are in the result without a buffer test and those that still need
 /// CheckVisibilityWork's occlusion predicate (k_dense_occlusion); the in-view stage's draw-distance test (View.cpp:179-186) is applied here.
-__global__ void __launch_bounds__(kDenseThreads) k_dense_frustum(SceneDev sc, const ViewConst* __restrict__ views, int stage, uint32_t* __restrict__ outCounts,
-    DenseDev dd)
+// BULK = true: the 32 boxes of a word (two runs of <= 512 contiguous bytes, one per array) arrive in shared memory by two bulk
+// asynchronous copies (TMA, cp.async.bulk + mbarrier complete_tx) issued one word ahead by lane 0, double-buffered per warp; the lanes
+// then read their box with two 16-byte shared loads.  BULK = false: two coalesced 16-byte global loads per lane.  A/B: profiles/README.md.
+__device__ __forceinline__ uint32_t smem_addr(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+template <bool BULK> __global__ void __launch_bounds__(kDenseThreads) k_dense_frustum(SceneDev sc, const ViewConst* __restrict__ views, int stage,
+    uint32_t* __restrict__ outCounts, DenseDev dd)
 {
+    __shared__ __align__(16) float4 sBox[BULK ? kDenseWarps : 1][2][2][32]; // [warp][buffer][min / max][lane]
+    __shared__ __align__(8) unsigned long long sBar[BULK ? kDenseWarps : 1][2];
     if (dd.ctr[CTR_FALLBACK])
         return;
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t total = dd.ctr[CTR_POOL];
     const uint32_t totalWarps = gridDim.x * kDenseWarps;
     const bool inViewStage = stage == STAGE_INVIEW;
+    uint32_t phase[2] = {0u, 0u};
+    if (BULK)
+    {
+        if (lane == 0)
+        {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[wid][0])));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_addr(&sBar[wid][1])));
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+    }
+    // lane 0: both copies of one word into buffer `buf`
+    auto fetch = [&](int buf, uint32_t s0, uint32_t nValid) {
+        const uint32_t bytes = nValid * 16u;
+        const uint32_t bar = smem_addr(&sBar[wid][buf]);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2u * bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&sBox[wid][buf][0][0])),
+                     "l"(sc.drwMin + s0), "r"(bytes), "r"(bar)
+                     : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(&sBox[wid][buf][1][0])),
+                     "l"(sc.drwMax + s0), "r"(bytes), "r"(bar)
+                     : "memory");
+    };
     for (uint32_t it = blockIdx.x * kDenseWarps + wid; it * 32u < total; it += totalWarps)
     {
         const uint32_t w0 = it * 32u, myW = w0 + lane;
@@ -346,9 +376,28 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_frustum(SceneDev sc, co
         }
         const int nW = (int)min(32u, total - w0);
         uint32_t myVis = 0, myTest = 0, myQuery = 0;
+        if (BULK)
+        {
+            __syncwarp(); // every lane is done with both buffers
+            const uint32_t m0 = __shfl_sync(0xffffffffu, meta, 0), f0 = __shfl_sync(0xffffffffu, slot0, 0);
+            if (lane == 0)
+                fetch(0, f0, ((m0 >> 16) & 31u) + 1u);
+        }
         for (int j = 0; j < nW; ++j)
         {
             const uint32_t m = __shfl_sync(0xffffffffu, meta, j), s0 = __shfl_sync(0xffffffffu, slot0, j);
+            if (BULK)
+            {
+                const uint32_t mNext = __shfl_sync(0xffffffffu, meta, (j + 1) & 31), sNext = __shfl_sync(0xffffffffu, slot0, (j + 1) & 31);
+                __syncwarp(); // buffer (j + 1) & 1 was read two words ago by every lane
+                if (lane == 0 && j + 1 < nW)
+                    fetch((j + 1) & 1, sNext, ((mNext >> 16) & 31u) + 1u);
+                const uint32_t bar = smem_addr(&sBar[wid][j & 1]);
+                uint32_t done = 0;
+                while (!done)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }" : "=r"(done) : "r"(bar), "r"(phase[j & 1]) : "memory");
+                phase[j & 1] ^= 1u;
+            }
             const ViewConst& vc = views[m & 0xFFFFu];
             const int queryMode = vc.queryMode;
             const bool sInside = (m >> 21) & 1u;
@@ -356,8 +405,8 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_frustum(SceneDev sc, co
             bool pass = false, test = false, vis0 = false;
             if ((uint32_t)lane <= ((m >> 16) & 31u))
             {
-                const float4 mn = sc.drwMin[d];
-                const float4 mx = sc.drwMax[d];
+                const float4 mn = BULK ? sBox[wid][j & 1][0][lane] : sc.drwMin[d];
+                const float4 mx = BULK ? sBox[wid][j & 1][1][lane] : sc.drwMax[d];
                 const uint32_t dm = __float_as_uint(mn.w);
                 const bool flagsOk = queryMode != QUERY_ZONE_OCCLUDER ? (dm & 0xFFu & vc.drawableFlags) != 0
                                                                       : ((dm & 0xFFu) == 4u || ((dm & 0xFFu) == 1u && (dm & kMetaOccluder)));
@@ -1427,6 +1476,7 @@ size_t dense_counter_bytes(int numViews, int numOctants)
 static int g_denseGrid = 0;
 static int g_denseTreeBlocks = 0; // "dense_tree_blocks": 256-thread units per SM of the persistent tree kernel (0 = as many as fit)
 static int gridSms = 148;
+static int g_frustumBulk = 0;  // "frustum_bulk": 1 = the drawable tests read their boxes through bulk asynchronous copies (TMA) into shared memory
 static int g_denseTree = 1;   // "dense_tree": 1 = all octree levels in one persistent launch (k_dense_tree), 0 = one launch per level
 static int g_denseWalker = 1; // "dense_walker": 1 = occlusion predicate with the warp walker, 0 = one walk per lane
 
@@ -1453,7 +1503,7 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         gridTree = fit(k_dense_tree);
         gridOcc = fit(k_dense_occlusion);
         gridOccWalk = fit(k_dense_occlusion_walk);
-        gridFrustum = fit(k_dense_frustum);
+        gridFrustum = std::min(fit(k_dense_frustum<false>), fit(k_dense_frustum<true>));
         gridLight = sms * 8 * (256 / kDenseThreads);
         g_denseGrid = sms * 6;
     }
@@ -1468,7 +1518,8 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         // With other batches in flight on their own streams the persistent kernel takes one 256-thread unit per SM: it spends much of its
         // life waiting for the next octree level's pairs, and a full-size grid would keep everybody else off the GPU meanwhile (512 views,
         // 12 batches in flight: 407 k views/s full size, 483 k with one unit; 4096 views: the same either way).  Alone, it takes every slot.
-        const int units = g_denseTreeBlocks > 0 ? g_denseTreeBlocks : (pipelined ? 1 : 0);
+        // (large batches keep the kernel busy enough either way: full size, which also keeps its share of the step readable in a launch list)
+        const int units = g_denseTreeBlocks > 0 ? g_denseTreeBlocks : (pipelined && numViews <= 1024 ? 1 : 0);
         const int blocks = units > 0 ? std::min(gridTree, gridSms * units * (256 / kDenseThreads)) : gridTree;
         k_dense_tree<<<blocks, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, epochTag);
     }
@@ -1483,7 +1534,10 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
     k_dense_groups<<<grid, kDenseThreads, 0, s>>>(sc, numViews, octState, dd);
     k_dense_scan<<<(numViews * 32 + kDenseThreads - 1) / kDenseThreads, kDenseThreads, 0, s>>>(numViews, dd);
     k_dense_words<<<grid, kDenseThreads, 0, s>>>(sc, octState, dd);
-    k_dense_frustum<<<gridFrustum, kDenseThreads, 0, s>>>(sc, views, stage, outCounts, dd);
+    if (g_frustumBulk)
+        k_dense_frustum<true><<<gridFrustum, kDenseThreads, 0, s>>>(sc, views, stage, outCounts, dd);
+    else
+        k_dense_frustum<false><<<gridFrustum, kDenseThreads, 0, s>>>(sc, views, stage, outCounts, dd);
     if (phaseEvents)
         cudaEventRecord(phaseEvents[1], s);
     if (stage >= STAGE_VISIBLE && depth)
@@ -1538,6 +1592,11 @@ void dense_set_walk_budget(int busy, int idle)
         cudaMemcpyToSymbol(g_walkBudgetBusy, &busy, sizeof(int));
     if (idle >= 0)
         cudaMemcpyToSymbol(g_walkBudgetIdle, &idle, sizeof(int));
+}
+
+void dense_set_frustum_bulk(int on)
+{
+    g_frustumBulk = on;
 }
 
 void dense_set_tree(int on)

@@ -162,6 +162,7 @@ void dense_set_heavy_extent(int px);
 void dense_set_walk_pool(int on);
 void dense_set_walker(int on);
 void dense_set_tree(int on);
+void dense_set_frustum_bulk(int on);
 void dense_set_tree_blocks(int perSm);
 void dense_set_walk_budget(int busy, int idle);
 void dense_prof_enable(int on);
