@@ -1518,8 +1518,9 @@ void launch_cull_dense(const SceneDev& sc, const BufGeom& g, const ViewConst* vi
         // With other batches in flight on their own streams the persistent kernel takes one 256-thread unit per SM: it spends much of its
         // life waiting for the next octree level's pairs, and a full-size grid would keep everybody else off the GPU meanwhile (512 views,
         // 12 batches in flight: 407 k views/s full size, 483 k with one unit; 4096 views: the same either way).  Alone, it takes every slot.
-        // (large batches keep the kernel busy enough either way: full size, which also keeps its share of the step readable in a launch list)
-        const int units = g_denseTreeBlocks > 0 ? g_denseTreeBlocks : (pipelined && numViews <= 1024 ? 1 : 0);
+        // (4096 views, 8 batches in flight: 685 k views/s with one unit, 677 k with two, 666 k with four.  In a serialised launch list -- ncu --
+        // the one-unit kernel runs alone and looks twice as long as it costs in the live, overlapped run.)
+        const int units = g_denseTreeBlocks > 0 ? g_denseTreeBlocks : (pipelined ? 1 : 0);
         const int blocks = units > 0 ? std::min(gridTree, gridSms * units * (256 / kDenseThreads)) : gridTree;
         k_dense_tree<<<blocks, kDenseThreads, 0, s>>>(sc, g, views, depth, mips, mipsValid, octState, dd, epochTag);
     }
