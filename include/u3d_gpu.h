@@ -111,12 +111,12 @@ U3D_API void u3d_octree_destroy(u3d_octree* t);
  * NULL arrays mean DRAWABLE_GEOMETRY / DEFAULT_VIEWMASK / occludee / no shadows.  Ids are assigned consecutively; *first_id = first. */
 U3D_API int u3d_octree_add(u3d_octree* t, uint32_t n, const float* aabb6, const uint8_t* drawable_flags, const uint32_t* view_mask,
     const uint8_t* occludee, const uint8_t* cast_shadows, uint32_t* first_id);
-/* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472).  Returns 1 when the flattened layout did not
- * change (the drawable stayed in its octant: u3d_scene_update_boxes is enough), 0 when it did (re-create the scene). */
 /* Drawable::SetDrawDistance for n drawables starting at first_id (0 = unlimited, the default; used by U3D_STAGE_INVIEW). */
 U3D_API int u3d_octree_set_draw_distances(u3d_octree* t, uint32_t first_id, uint32_t n, const float* draw_distance);
 /* Drawable::SetOccluder for n drawables starting at first_id (default: not an occluder; used by U3D_QUERY_ZONE_OCCLUDER). */
 U3D_API int u3d_octree_set_occluder_flags(u3d_octree* t, uint32_t first_id, uint32_t n, const uint8_t* is_occluder);
+/* A moved/resized drawable: the reinsertion rule of Octree::Update (Octree.cpp:440-472).  Returns 1 when the flattened layout did not
+ * change (the drawable stayed in its octant: u3d_scene_update_boxes is enough), 0 when it did (re-create the scene). */
 U3D_API int u3d_octree_update(u3d_octree* t, uint32_t id, const float aabb6[6]);
 /* Octree::RemoveDrawable path (Octree.h:66-74, DecDrawableCount :123-136). */
 U3D_API int u3d_octree_remove(u3d_octree* t, uint32_t id);
@@ -138,7 +138,8 @@ U3D_API int u3d_scene_set_draw_distances(u3d_scene* s, uint32_t n, const float* 
 /* Drawable::IsOccluder() per drawable id for a scene made with u3d_scene_create_flat (in place: one bit of each record's meta word). */
 U3D_API int u3d_scene_set_occluder_flags(u3d_scene* s, uint32_t n, const uint8_t* is_occluder);
 /* Dirty-range maintenance: new world boxes for n drawables whose octant did not change (u3d_octree_update returned 1); only their
- * 2 x 12 bytes are rewritten in HBM, the layout and the meta words stay. */
+ * 2 x 12 bytes are rewritten in HBM, the layout and the meta words stay.  An id may appear several times (the drawable moved more than
+ * once since the last upload): the LAST box of the call wins, as in the host tree. */
 U3D_API int u3d_scene_update_boxes(u3d_scene* s, uint32_t n, const uint32_t* ids, const float* aabb6, void* stream);
 U3D_API void u3d_scene_destroy(u3d_scene* s);
 U3D_API int u3d_scene_counts(const u3d_scene* s, uint32_t* num_octants, uint32_t* num_drawables);

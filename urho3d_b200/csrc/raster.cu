@@ -1590,7 +1590,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
         }
     }
     __syncthreads(); // the other classes composite with atomics, from any warp
-    // (2) small triangles (bbox area <= 64; 86 % of the triangles of the benchmark scene): one per lane, groups of 32 handed out
+    // (2) small triangles (bbox area <= 256 px^2, kLaneAreaMax; 86 % of the triangles of the benchmark scene have <= 64): one per lane, groups of 32 handed out
     //     dynamically
     {
         const uint32_t* bin = binBase + (size_t)kClsLane * cap;
