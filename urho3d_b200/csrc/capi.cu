@@ -434,6 +434,7 @@ struct u3d_batch
     uint64_t poolTris{};
     DevBuf<unsigned char> octState;
     DevBuf<unsigned char> itemPass;   // two-phase occluder drawing: per (view, item) kPassNear / kPassFarVisible / kPassFarHidden
+    DevBuf<uint32_t> nearList, farVisList, listCounts; // ... and the near / far-visible items' positions, compacted; listCounts = [2][maxViews]
     bool countPending{};              // numTriangles_ of the occluders the second pass skipped is still to be counted (u3d_batch_read_tri_stats)
     DenseScratch dense;
     DevBuf<uint32_t> outIdx, outCounts, packOffsets, packed;
@@ -2186,9 +2187,13 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         if (twoPhase)
         {
             CU_CHECK(b->itemPass.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
-            launch_items_near_far(vs.views.p, V, vs.items.p, vs.itemCap, vs.itemCount.p, oc->aabb6.p, b->itemPass.p, (uint32_t)g_twoPhaseMin, g_twoPhaseShift, st);
-            rd.itemPass = b->itemPass.p;
-            rd.pass = kPassNear;
+            CU_CHECK(b->nearList.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
+            CU_CHECK(b->farVisList.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
+            CU_CHECK(b->listCounts.ensure((size_t)vs.maxViews * 2));
+            launch_items_near_far(vs.views.p, V, vs.items.p, vs.itemCap, vs.itemCount.p, oc->aabb6.p, b->itemPass.p, b->nearList.p, b->listCounts.p,
+                b->listCounts.p + vs.maxViews, (uint32_t)g_twoPhaseMin, g_twoPhaseShift, st);
+            rd.itemList = b->nearList.p;
+            rd.listCount = b->listCounts.p;
             b->lastLaunches += 1;
         }
         CU_CHECK(mark(3));
@@ -2213,9 +2218,10 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         {
             // second pass: the occluders that were left out, as far as their boxes show in the first pass's buffer (and hierarchy)
             launch_items_far_test(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->aabb6.p, vs.depth.p, vs.mips.p,
-                b->itemPass.p, st);
+                b->itemPass.p, b->farVisList.p, b->listCounts.p + vs.maxViews, st);
             CU_CHECK(vs.clear_pass_counters(st));
-            rd.pass = kPassFarVisible;
+            rd.itemList = b->farVisList.p;
+            rd.listCount = b->listCounts.p + vs.maxViews;
             rd.secondPass = 1;
             launch_setup(vs.g, vs.tg, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->model12.p, oc->meshTable.p, rd, st);
             launch_fill_tiles(vs.g, vs.tg, V, vs.depth.p, vs.mips.p, rd, st);

@@ -1361,19 +1361,31 @@ __device__ __forceinline__ uint32_t item_depth_bin(const float* vp, const float*
 }
 
 __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
-    const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, unsigned char* __restrict__ itemPass, uint32_t minNear, int shift)
+    const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, unsigned char* __restrict__ itemPass, uint32_t* __restrict__ nearList,
+    uint32_t* __restrict__ nearCount, uint32_t* __restrict__ farVisCount, uint32_t minNear, int shift)
 {
     __shared__ uint32_t hist[1024];
-    __shared__ uint32_t sCut;
+    __shared__ uint32_t sCut, sNear;
     const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = min(itemCount[v], itemCap);
     const uint32_t target = max(minNear, n >> shift);
     const DrawItem* mine = items + (size_t)v * itemCap;
     unsigned char* pass = itemPass + (size_t)v * itemCap;
+    uint32_t* list = nearList + (size_t)v * itemCap;
+    if (tid == 0)
+    {
+        farVisCount[v] = 0;
+        sNear = 0;
+    }
     if (n <= target || !views[v].useOcclusion)
     {
         for (uint32_t i = tid; i < n; i += 256)
+        {
             pass[i] = kPassNear;
+            list[i] = i;
+        }
+        if (tid == 0)
+            nearCount[v] = n;
         return;
     }
     for (int i = tid; i < 1024; i += 256)
@@ -1414,13 +1426,29 @@ __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restr
     }
     __syncthreads();
     const uint32_t cut = sCut;
-    for (uint32_t i = tid; i < n; i += 256)
-        pass[i] = item_depth_bin(vp, occAabb6 + 6 * (size_t)mine[i].model) <= cut ? kPassNear : kPassFarHidden;
+    for (uint32_t base = 0; base < n; base += 256)
+    {
+        const uint32_t i = base + tid;
+        const bool near = i < n && item_depth_bin(vp, occAabb6 + 6 * (size_t)mine[i].model) <= cut;
+        if (i < n)
+            pass[i] = near ? kPassNear : kPassFarHidden;
+        // the near items' positions, compacted (order is irrelevant: min-compositing)
+        const uint32_t bal = __ballot_sync(0xffffffffu, near);
+        uint32_t pos = 0;
+        if (lane == 0 && bal)
+            pos = atomicAdd(&sNear, (uint32_t)__popc(bal));
+        pos = __shfl_sync(0xffffffffu, pos, 0);
+        if (near)
+            list[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+    }
+    __syncthreads();
+    if (tid == 0)
+        nearCount[v] = sNear;
 }
 
 __global__ void __launch_bounds__(256) k_items_far_test(BufGeom g, const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
     const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, const int* __restrict__ depthAll, const int2* __restrict__ mipAll,
-    unsigned char* __restrict__ itemPass)
+    unsigned char* __restrict__ itemPass, uint32_t* __restrict__ farVisList, uint32_t* __restrict__ farVisCount)
 {
     const int v = blockIdx.y;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1448,23 +1476,27 @@ __global__ void __launch_bounds__(256) k_items_far_test(BufGeom g, const ViewCon
         }
     }
     if (visible)
+    {
         *pass = kPassFarVisible;
+        farVisList[(size_t)v * itemCap + atomicAdd(&farVisCount[v], 1u)] = i;
+    }
 }
 
 void launch_items_near_far(const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, const uint32_t* itemCount, const float* occAabb6,
-    unsigned char* itemPass, uint32_t minNear, int shift, cudaStream_t s)
+    unsigned char* itemPass, uint32_t* nearList, uint32_t* nearCount, uint32_t* farVisCount, uint32_t minNear, int shift, cudaStream_t s)
 {
     if (numViews)
-        k_items_near_far<<<numViews, 256, 0, s>>>(views, items, itemCap, itemCount, occAabb6, itemPass, minNear, shift);
+        k_items_near_far<<<numViews, 256, 0, s>>>(views, items, itemCap, itemCount, occAabb6, itemPass, nearList, nearCount, farVisCount, minNear, shift);
 }
 
 void launch_items_far_test(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
-    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, cudaStream_t s)
+    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, uint32_t* farVisList,
+    uint32_t* farVisCount, cudaStream_t s)
 {
     if (!numViews || !maxItems)
         return;
     dim3 grid((maxItems + 255) / 256, numViews);
-    k_items_far_test<<<grid, 256, 0, s>>>(g, views, items, itemCap, itemCount, occAabb6, depth, mips, itemPass);
+    k_items_far_test<<<grid, 256, 0, s>>>(g, views, items, itemCap, itemCount, occAabb6, depth, mips, itemPass, farVisList, farVisCount);
 }
 
 size_t dense_counter_bytes(int numViews, int numOctants)

@@ -880,7 +880,7 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
     const MeshDev* __restrict__ meshes, RasterDev rd, uint32_t sliceItems /* <= kSetupItems: items a block takes at a time */)
 {
     const int v = blockIdx.y;
-    const uint32_t nItems = itemCount[v];
+    const uint32_t nItems = rd.itemList ? min(rd.listCount[v], itemCap) : itemCount[v];
 
     __shared__ float sMvp[kSetupItems][16];
     __shared__ DrawItem sItem[kSetupItems];
@@ -933,9 +933,15 @@ __global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, Ti
         __syncthreads(); // previous slice fully consumed
         if (threadIdx.x < nLocal)
         {
-            DrawItem it = items[(size_t)v * itemCap + itemBase + threadIdx.x];
-            if (rd.itemPass && rd.itemPass[(size_t)v * itemCap + itemBase + threadIdx.x] != rd.pass)
-                it.count = 0; // another pass's item (two-phase occluder drawing)
+            DrawItem it;
+            if (rd.itemList)
+                it = items[(size_t)v * itemCap + rd.itemList[(size_t)v * itemCap + itemBase + threadIdx.x]];
+            else
+            {
+                it = items[(size_t)v * itemCap + itemBase + threadIdx.x];
+                if (rd.itemPass && rd.itemPass[(size_t)v * itemCap + itemBase + threadIdx.x] != rd.pass)
+                    it.count = 0; // another pass's item (two-phase occluder drawing)
+            }
             sItem[threadIdx.x] = it;
         }
         __syncthreads();

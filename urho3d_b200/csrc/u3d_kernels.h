@@ -64,6 +64,10 @@ struct RasterDev
     // `pass` (itemPass == nullptr: all of them)
     const unsigned char* itemPass; // per (view, item): kPassNear, kPassFarVisible, kPassFarHidden
     int pass;
+    // ... or, when set, exactly the items listed (positions in the view's item array): the near / far-visible lists are short, and a block
+    // that sweeps all items to find a handful is what the set-up launch would otherwise spend its time on
+    const uint32_t* itemList;    // per view: itemCap positions
+    const uint32_t* listCount;   // per view
     int countOnly;               // set-up decides drawOk per source triangle (numTriangles_, OB.cpp:681-682) but emits nothing
     int secondPass;              // the tile kernel composites on top of the plane it finds and leaves untouched tiles alone
 };
@@ -117,9 +121,10 @@ cudaError_t init_tile_kernel();
 /// them) get kPassNear, the rest kPassFarHidden.  far_test: items marked kPassFarHidden whose occluder box is visible in the buffers drawn
 /// so far become kPassFarVisible.
 void launch_items_near_far(const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, const uint32_t* itemCount, const float* occAabb6,
-    unsigned char* itemPass, uint32_t minNear, int shift, cudaStream_t s);
+    unsigned char* itemPass, uint32_t* nearList, uint32_t* nearCount, uint32_t* farVisCount /* zeroed here */, uint32_t minNear, int shift, cudaStream_t s);
 void launch_items_far_test(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
-    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, cudaStream_t s);
+    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, uint32_t* farVisList,
+    uint32_t* farVisCount, cudaStream_t s);
 /// irregular pre-pass (2 launches) + tile kernel (1 launch)
 void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* depth, int2* mips, const RasterDev& rd, cudaStream_t s);
 void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s);
