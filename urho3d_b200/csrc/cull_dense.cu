@@ -1143,15 +1143,15 @@ __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion
         if (walk_drain(g, depthAll, mipAll, sh, wid, buffered, meta, tag, vis, budget) && vis)
             atomicOr(&dd.visWord[tag], 1u << (meta >> 26));
     };
-    constexpr uint32_t kChunk = 1; // blocks of 32 words per ticket
-    const uint32_t nBlocks = (total + 31u) / 32u;
-    (void)totalWarps;
-    for (uint32_t chunk = next_chunk(&dd.ctr[CTR_TICKET_OCC]); chunk * kChunk < nBlocks; chunk = next_chunk(&dd.ctr[CTR_TICKET_OCC]))
-    for (uint32_t it = chunk * kChunk; it < min((chunk + 1u) * kChunk, nBlocks); ++it)
+    // words per ticket: 32 (one per lane) when there is plenty of work; small launches hand out 8 at a time -- a ticket is up to 32
+    // candidates per word, and with few tickets per warp the last ticket is what the launch ends on
+    const uint32_t wpt = total >= totalWarps * 32u * 8u ? 32u : 8u;
+    const uint32_t nBlocks = (total + wpt - 1u) / wpt;
+    for (uint32_t it = next_chunk(&dd.ctr[CTR_TICKET_OCC]); it < nBlocks; it = next_chunk(&dd.ctr[CTR_TICKET_OCC]))
     {
-        const uint32_t myW = it * 32u + lane;
+        const uint32_t myW = it * wpt + lane;
         uint32_t mask = 0, view = 0, slot0 = 0;
-        if (myW < total)
+        if ((uint32_t)lane < wpt && myW < total)
             mask = dd.testMask[myW];
         if (!__any_sync(0xffffffffu, mask != 0))
             continue;
@@ -1187,7 +1187,7 @@ __global__ void __launch_bounds__(kDenseThreads, U3D_OCC_MINB) k_dense_occlusion
             const uint32_t oMask = __shfl_sync(0xffffffffu, mask, owner), oExcl = __shfl_sync(0xffffffffu, excl, owner);
             const uint32_t oSlot = __shfl_sync(0xffffffffu, slot0, owner), oView = __shfl_sync(0xffffffffu, view, owner);
             const uint32_t bit = nth_set_bit(oMask, c - oExcl);
-            const uint32_t word = it * 32u + owner;
+            const uint32_t word = it * wpt + owner;
             float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
             if (cand)
             {
