@@ -170,6 +170,8 @@ struct u3d_scene
     DevBuf<int2> octChild;
     DevBuf<uint32_t> drwId;
     DevBuf<float> drwDrawDist;       // per DFS slot, 0 = unlimited
+    DevBuf<uint4> wordInfo;          // static filter summaries per 32 consecutive drawables of an octant (SceneDev::wordInfo)
+    DevBuf<uint32_t> octWordStart;
     DevBuf<uint32_t> updSlots;       // staging of u3d_scene_update_boxes
     DevBuf<float> updBoxes;
     std::vector<uint32_t> slotOfId;  // drawable id -> DFS slot (for late per-drawable uploads)
@@ -359,7 +361,7 @@ struct u3d_ob
 struct DenseScratch
 {
     DevBuf<uint2> queue, groupList;
-    DevBuf<uint32_t> ctr, groupCount, groupOff, wordBase, viewWords, visWord, wordSlot, wordMeta, testMask;
+    DevBuf<uint32_t> ctr, groupCount, groupOff, wordBase, viewWords, visWord, wordSlot, wordMeta, testMask, wordStatic;
     DenseDev dev{};
     uint32_t epochCounter{};
     /// Epoch of the next run's queue entries; the queue is wiped whenever the 16-bit tag starts over (and before its first use), so an
@@ -402,6 +404,7 @@ struct DenseScratch
         CU_CHECK(wordSlot.ensure(poolCap));
         CU_CHECK(wordMeta.ensure(poolCap));
         CU_CHECK(testMask.ensure(poolCap));
+        CU_CHECK(wordStatic.ensure(poolCap));
         dev.queue = queue.p;
         dev.queueCap = (uint32_t)queueCap;
         dev.ctr = ctr.p;
@@ -417,6 +420,7 @@ struct DenseScratch
         dev.wordSlot = wordSlot.p;
         dev.wordMeta = wordMeta.p;
         dev.testMask = testMask.p;
+        dev.wordStatic = wordStatic.p;
         dev.poolCap = (uint32_t)poolCap;
         dev.stateStride = groups * 32;
         return 0;
@@ -848,9 +852,37 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
         return cudaMemcpy(buf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice);
     };
     std::vector<int> cnt(count, count + M);
+    // static filter summaries (SceneDev::wordInfo)
+    std::vector<uint32_t> wordStart(M + 1, 0);
+    for (uint32_t i = 0; i < M; ++i)
+        wordStart[i + 1] = wordStart[i] + ((uint32_t)count[i] + 31u) / 32u;
+    std::vector<uint4> wordInfo(std::max<uint32_t>(wordStart[M], 1), make_uint4(0xFFFFFFFFu, 0, 0, 0));
+    for (uint32_t i = 0; i < M; ++i)
+        for (uint32_t k = 0; k < (uint32_t)count[i]; k += 32)
+        {
+            const uint32_t s0 = (uint32_t)first[i] + k, nv = std::min<uint32_t>(32u, (uint32_t)count[i] - k);
+            uint32_t meta0, vm0;
+            std::memcpy(&meta0, &dmin[s0].w, 4);
+            std::memcpy(&vm0, &dmax[s0].w, 4);
+            bool uniform = true;
+            uint32_t occ = 0, cast = 0;
+            for (uint32_t j = 0; j < nv; ++j)
+            {
+                uint32_t meta, vm;
+                std::memcpy(&meta, &dmin[s0 + j].w, 4);
+                std::memcpy(&vm, &dmax[s0 + j].w, 4);
+                uniform = uniform && (meta & 0xFFu) == (meta0 & 0xFFu) && vm == vm0;
+                if (meta & kMetaOccludee)
+                    occ |= 1u << j;
+                if (meta & kMetaCastShadows)
+                    cast |= 1u << j;
+            }
+            wordInfo[wordStart[i] + k / 32] = make_uint4(uniform ? (meta0 & 0xFFu) : 0xFFFFFFFFu, vm0, occ, cast);
+        }
     cudaError_t e = cudaSuccess;
     if ((e = up(s->octMin, omin)) || (e = up(s->octMax, omax)) || (e = up(s->octCount, cnt)) || (e = up(s->bfs, bfs)) || (e = up(s->octChild, child)) ||
-        (e = up(s->levelStart, levelStart)) || (e = up(s->drwMin, dmin)) || (e = up(s->drwMax, dmax)) || (e = up(s->drwId, ids)))
+        (e = up(s->levelStart, levelStart)) || (e = up(s->drwMin, dmin)) || (e = up(s->drwMax, dmax)) || (e = up(s->drwId, ids)) ||
+        (e = up(s->wordInfo, wordInfo)) || (e = up(s->octWordStart, wordStart)))
     {
         delete s;
         return fail(U3D_ERR_CUDA, std::string("scene upload: ") + cudaGetErrorString(e));
@@ -867,6 +899,8 @@ int u3d_scene_create_flat(u3d_ctx* ctx, uint32_t M, const int32_t* parent, const
     s->dev.drwMin = s->drwMin.p;
     s->dev.drwMax = s->drwMax.p;
     s->dev.drwId = s->drwId.p;
+    s->dev.wordInfo = s->wordInfo.p;
+    s->dev.octWordStart = s->octWordStart.p;
     {
         cudaError_t e2 = s->drwDrawDist.ensure(std::max<uint32_t>(S, 1));
         if (e2 == cudaSuccess)

@@ -298,12 +298,14 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_words(SceneDev sc, cons
             woff -= mine;
         }
         const uint32_t common = (uint32_t)v | (ins << 21);
+        const uint32_t staticBase = cnt ? sc.octWordStart[o] : 0u;
         if (cnt && cnt <= 256)
             for (uint32_t k = 0; k < cnt; k += 32)
             {
                 const uint32_t w = wordBase + woff + (k >> 5);
                 dd.wordSlot[w] = first + k;
                 dd.wordMeta[w] = common | ((min(cnt - k, 32u) - 1u) << 16);
+                dd.wordStatic[w] = staticBase + (k >> 5);
             }
         // octants with many drawables: the whole warp writes their descriptors
         uint32_t big = __ballot_sync(0xffffffffu, cnt > 256);
@@ -313,10 +315,12 @@ __global__ void __launch_bounds__(kDenseThreads) k_dense_words(SceneDev sc, cons
             big &= big - 1;
             const uint32_t bCnt = __shfl_sync(0xffffffffu, cnt, j), bFirst = __shfl_sync(0xffffffffu, first, j);
             const uint32_t bWord = wordBase + __shfl_sync(0xffffffffu, woff, j), bCommon = __shfl_sync(0xffffffffu, common, j);
+            const uint32_t bStatic = __shfl_sync(0xffffffffu, staticBase, j);
             for (uint32_t k = lane * 32u; k < bCnt; k += 1024u)
             {
                 dd.wordSlot[bWord + (k >> 5)] = bFirst + k;
                 dd.wordMeta[bWord + (k >> 5)] = bCommon | ((min(bCnt - k, 32u) - 1u) << 16);
+                dd.wordStatic[bWord + (k >> 5)] = bStatic + (k >> 5);
             }
         }
     }
@@ -376,6 +380,27 @@ template <bool BULK> __global__ void __launch_bounds__(kDenseThreads) k_dense_fr
         }
         const int nW = (int)min(32u, total - w0);
         uint32_t myVis = 0, myTest = 0, myQuery = 0;
+        // Words of octants that are INSIDE the query volume: every drawable passes the shape test, so the word's result follows from
+        // its static summary (flags / view mask if uniform over the word, occludee and shadow-caster bits) -- one 16-byte load by the
+        // word's own lane instead of 2 x 512 bytes of boxes and a warp step.  (Not for the in-view stage, which needs per-drawable
+        // distances, nor for the zone / occluder query, whose flag test reads the occluder bit.)
+        bool fast = false;
+        if (!BULK && myW < total && !inViewStage && ((meta >> 21) & 1u))
+        {
+            const ViewConst& vcw = views[meta & 0xFFFFu];
+            const uint4 info = sc.wordInfo[dd.wordStatic[myW]];
+            if (info.x != 0xFFFFFFFFu && vcw.queryMode != QUERY_ZONE_OCCLUDER)
+            {
+                const uint32_t nv = ((meta >> 16) & 31u) + 1u;
+                uint32_t q = ((info.x & vcw.drawableFlags) != 0u && (info.y & vcw.viewMask) != 0u) ? (nv == 32u ? 0xFFFFFFFFu : (1u << nv) - 1u) : 0u;
+                if (vcw.queryMode == QUERY_SHADOWCASTER)
+                    q &= info.w;
+                myTest = (stage >= STAGE_VISIBLE && vcw.useOcclusion != 0) ? (q & info.z) : 0u;
+                myVis = q & ~myTest;
+                myQuery = (uint32_t)__popc(q);
+                fast = true;
+            }
+        }
         if (BULK)
         {
             __syncwarp(); // every lane is done with both buffers
@@ -383,8 +408,11 @@ template <bool BULK> __global__ void __launch_bounds__(kDenseThreads) k_dense_fr
             if (lane == 0)
                 fetch(0, f0, ((m0 >> 16) & 31u) + 1u);
         }
+        const uint32_t slow = __ballot_sync(0xffffffffu, myW < total && !fast);
         for (int j = 0; j < nW; ++j)
         {
+            if (!BULK && !((slow >> j) & 1u))
+                continue;
             const uint32_t m = __shfl_sync(0xffffffffu, meta, j), s0 = __shfl_sync(0xffffffffu, slot0, j);
             if (BULK)
             {

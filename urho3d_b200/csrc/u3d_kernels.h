@@ -89,6 +89,11 @@ struct SceneDev
     const float4* drwMax;          // xyz = world AABB max, w = viewMask (uint bits)
     const uint32_t* drwId;         // caller's drawable id for each DFS slot
     const float* drwDrawDist;      // Drawable::GetDrawDistance per DFS slot (0 = unlimited)
+    // Static summaries of the drawables' filter words, per "word" = 32 consecutive drawables of one octant (word k of octant o has index
+    // octWordStart[o] + k): x = drawableFlags if all of the word's drawables have the same flags AND view mask, else 0xFFFFFFFF; y = that view
+    // mask; z = occludee bits; w = castShadows bits.  A word of an octant that is INSIDE the query volume needs nothing else from HBM.
+    const uint4* wordInfo;
+    const uint32_t* octWordStart;  // numOctants + 1
 };
 
 void launch_clear(int* depth, size_t nInts, cudaStream_t s);
@@ -157,6 +162,7 @@ struct DenseDev
     uint32_t* wordSlot;      // pool: DFS slot of a word's bit 0
     uint32_t* wordMeta;      // pool: view | (valid drawables - 1) << 16 | inside << 21
     uint32_t* testMask;      // pool: drawables that passed the query and still need the occlusion predicate
+    uint32_t* wordStatic;    // pool: index of the word's static summary (SceneDev::wordInfo)
     uint32_t poolCap;
     int stateStride;         // bytes of octant state per view (groupsPerView * 32)
     uint32_t epoch;          // 1..65535, tags the queue entries of this run (k_dense_tree)
