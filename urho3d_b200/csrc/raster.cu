@@ -1553,17 +1553,22 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
         for (uint32_t i = 0; i < nStage; ++i)
         {
             TriSetup ts;
+            const int4 a = sCtaTri[i][0];
+            ts.y0 = a.x; ts.y1 = a.y; ts.y2 = a.z; ts.dzdx = a.w;
+            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
+            // first row >= ya owned by this warp (rows are counted from the tile's first row)
+            const int first = ya + ((wid - (ya - ty0)) & (kWarps - 1));
+            if (first >= yb)
+                continue; // none of this warp's rows: the rest of the record is not even read
             {
-                const int4 a = sCtaTri[i][0], b = sCtaTri[i][1], c = sCtaTri[i][2], d = sCtaTri[i][3];
-                ts.y0 = a.x; ts.y1 = a.y; ts.y2 = a.z; ts.dzdx = a.w;
+                const int4 b = sCtaTri[i][1], c = sCtaTri[i][2], d = sCtaTri[i][3];
                 ts.tlx = b.x; ts.tlxs = b.y; ts.tlz = b.z; ts.tlzs = b.w;
                 ts.trx = c.x; ts.trxs = c.y; ts.blx = c.z; ts.blxs = c.w;
                 ts.blz = d.x; ts.blzs = d.y; ts.brx = d.z; ts.brxs = d.w;
             }
-            const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
-            // first row >= ya owned by this warp (rows are counted from the tile's first row)
-            const int first = ya + ((wid - (ya - ty0)) & (kWarps - 1));
-            for (int y = first; y < yb; y += kWarps)
+            // Spans of this class are ~40 pixels on the benchmark scene: each HALF of the warp takes one of the warp's rows (16 lanes x 4
+            // pixels = 64 pixels per step), two rows per iteration.
+            for (int y = first + kWarps * (lane >> 4); y < yb; y += 2 * kWarps)
             {
                 const HalfRow r = tri_row(ts, y);
                 const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
@@ -1572,7 +1577,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
                 int* trow = tile + (y - ty0) * tw - tx0;
                 if ((tw & 3) == 0)
                 {
-                    for (int x4 = ((xa - tx0) & ~3) + tx0 + 4 * lane; x4 < xb; x4 += 128)
+                    for (int x4 = ((xa - tx0) & ~3) + tx0 + 4 * (lane & 15); x4 < xb; x4 += 64)
                     {
                         int4 d = *reinterpret_cast<int4*>(trow + x4);
                         const uint32_t z0 = r.z0 + (uint32_t)(x4 - r.xl) * (uint32_t)ts.dzdx;
@@ -1585,7 +1590,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
                     }
                 }
                 else
-                    for (int x = xa + lane; x < xb; x += 32)
+                    for (int x = xa + (lane & 15); x < xb; x += 16)
                     {
                         const int z = (int)(r.z0 + (uint32_t)(x - r.xl) * (uint32_t)ts.dzdx);
                         if (z < trow[x])
