@@ -629,30 +629,39 @@ __device__ __forceinline__ int walk_top(const BufGeom& g, const int2* __restrict
         mask = cut ? kWalkBigGrid : 0u;
         return cut ? 2 : 0;
     }
-    // a texel's pixels lie inside the rect when its column and its row do (the last column / row is cut by the buffer's edge)
-    bool colIn[3], rowIn[3];
+    // Nine loads (indices clamped into the grid, duplicates hit L1) and nine-bit masks instead of branches: bit j * 3 + i = texel (i, j).
+    //   valid: the texel belongs to the grid (i < nx, j < ny)
+    //   in:    its pixels all lie inside the rect -- its column and its row do (the last column / row is cut by the buffer's edge)
+    //   nearer: z <= min (every pixel under it is at least as far as the box), mixed: min < z <= max
+    // A mixed texel inside the rect proves visibility (the pixel that holds its max lies in the rect); mixed texels cut by the border are
+    // the ones that have to be refined.
+    uint32_t colIn = 0, rowIn = 0;
 #pragma unroll
     for (int i = 0; i < 3; ++i)
     {
-        colIn[i] = ((rx0 + i) << s) >= r.left && min(((rx0 + i + 1) << s) - 1, g.w - 1) <= r.right;
-        rowIn[i] = ((ry0 + i) << s) >= r.top && min(((ry0 + i + 1) << s) - 1, g.h - 1) <= r.bottom;
+        colIn |= (((rx0 + i) << s) >= r.left && min(((rx0 + i + 1) << s) - 1, g.w - 1) <= r.right) ? (1u << i) : 0u;
+        rowIn |= (((ry0 + i) << s) >= r.top && min(((ry0 + i + 1) << s) - 1, g.h - 1) <= r.bottom) ? (1u << i) : 0u;
     }
-    // branch-free: nine loads (indices clamped into the grid, duplicates hit L1), predicates combined with logic ops
+    auto spread = [](uint32_t rows) { return (rows & 1u) | ((rows & 2u) << 2) | ((rows & 4u) << 4); }; // row bit j -> bit 3 j
+    const uint32_t valid = ((1u << nx) - 1u) * spread((1u << ny) - 1u);
+    const uint32_t in = colIn * spread(rowIn);
+    const int c1 = nx > 1 ? 1 : 0, c2 = nx > 2 ? 2 : nx - 1;
+    const int r1 = ny > 1 ? stride : 0, r2 = ny > 2 ? 2 * stride : (ny - 1) * stride;
+    const int colOff[3] = {0, c1, c2}, rowOff[3] = {0, r1, r2};
+    uint32_t nearer = 0, reach = 0; // reach: z <= max
 #pragma unroll
     for (int j = 0; j < 3; ++j)
 #pragma unroll
         for (int i = 0; i < 3; ++i)
         {
-            const int2 t = row[min(j, ny - 1) * stride + min(i, nx - 1)];
-            const bool valid = i < nx && j < ny;
-            const bool nearer = r.z <= t.x;          // every pixel under the texel is at least as far as the box
-            const bool mixed = !nearer && r.z <= t.y;
-            const bool in = colIn[i] && rowIn[j];    // a mixed texel inside the rect: the pixel that holds its max lies in the rect
-            vis |= valid && (nearer || (mixed && in));
-            mask |= (valid && mixed && !in) ? (1u << (j * 3 + i)) : 0u;
+            const int2 t = row[rowOff[j] + colOff[i]];
+            nearer |= r.z <= t.x ? (1u << (j * 3 + i)) : 0u;
+            reach |= r.z <= t.y ? (1u << (j * 3 + i)) : 0u;
         }
-    if (vis)
+    const uint32_t mixed = reach & ~nearer;
+    if (valid & (nearer | (mixed & in)))
         return 1;
+    mask = valid & mixed & ~in;
     return mask ? 2 : 0;
 }
 
