@@ -716,12 +716,16 @@ __device__ __forceinline__ int walk_deep(const BufGeom& g, const int* __restrict
         }
         else
         {
+            // the <= 2 x 2 children that overlap the rect (and exist: the finer level may end one texel earlier), without loops
             const int cl = lv - 1;
-            const int x0 = max(2 * x, r.left >> lv), x1 = min(min(2 * x + 1, r.right >> lv), g.mw[cl] - 1);
-            const int y0 = max(2 * y, r.top >> lv), y1 = min(min(2 * y + 1, r.bottom >> lv), g.mh[cl] - 1);
-            for (int cy = y0; cy <= y1; ++cy)
-                for (int cx = x0; cx <= x1; ++cx)
-                    stack[sp++] = pack_texel(cl, cx, cy);
+            const int xLo = r.left >> lv, xHi = min(r.right >> lv, g.mw[cl] - 1), yLo = r.top >> lv, yHi = min(r.bottom >> lv, g.mh[cl] - 1);
+            const bool xa = 2 * x >= xLo && 2 * x <= xHi, xb = 2 * x + 1 >= xLo && 2 * x + 1 <= xHi;
+            const bool ya = 2 * y >= yLo && 2 * y <= yHi, yb = 2 * y + 1 >= yLo && 2 * y + 1 <= yHi;
+            const uint32_t base = pack_texel(cl, 2 * x, 2 * y);
+            if (xa && ya) stack[sp++] = base;
+            if (xb && ya) stack[sp++] = base + (1u << 14);
+            if (xa && yb) stack[sp++] = base + 1u;
+            if (xb && yb) stack[sp++] = base + (1u << 14) + 1u;
         }
     }
     return 0;
