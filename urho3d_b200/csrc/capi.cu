@@ -2223,9 +2223,9 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
             CU_CHECK(b->itemPass.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
             CU_CHECK(b->nearList.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
             CU_CHECK(b->farVisList.ensure((size_t)vs.maxViews * std::max<uint32_t>(vs.itemCap, 1)));
-            CU_CHECK(b->listCounts.ensure((size_t)vs.maxViews * 2));
+            CU_CHECK(b->listCounts.ensure((size_t)vs.maxViews * 3)); // near, far-visible, far
             launch_items_near_far(vs.views.p, V, vs.items.p, vs.itemCap, vs.itemCount.p, oc->aabb6.p, b->itemPass.p, b->nearList.p, b->listCounts.p,
-                b->listCounts.p + vs.maxViews, (uint32_t)g_twoPhaseMin, g_twoPhaseShift, st);
+                b->listCounts.p + 2 * (size_t)vs.maxViews, b->listCounts.p + vs.maxViews, (uint32_t)g_twoPhaseMin, g_twoPhaseShift, st);
             rd.itemList = b->nearList.p;
             rd.listCount = b->listCounts.p;
             b->lastLaunches += 1;
@@ -2251,8 +2251,8 @@ int u3d_batch_run_part(u3d_batch* b, int part, int stage, void* stream)
         if (twoPhase)
         {
             // second pass: the occluders that were left out, as far as their boxes show in the first pass's buffer (and hierarchy)
-            launch_items_far_test(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, vs.itemCount.p, oc->aabb6.p, vs.depth.p, vs.mips.p,
-                b->itemPass.p, b->farVisList.p, b->listCounts.p + vs.maxViews, st);
+            launch_items_far_test(vs.g, vs.views.p, V, vs.items.p, vs.itemCap, oc->totalItems, b->nearList.p, b->listCounts.p + 2 * (size_t)vs.maxViews,
+                oc->aabb6.p, vs.depth.p, vs.mips.p, b->itemPass.p, b->farVisList.p, b->listCounts.p + vs.maxViews, st);
             CU_CHECK(vs.clear_pass_counters(st));
             rd.itemList = b->farVisList.p;
             rd.listCount = b->listCounts.p + vs.maxViews;

@@ -1403,10 +1403,10 @@ __device__ __forceinline__ uint32_t item_depth_bin(const float* vp, const float*
 
 __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
     const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, unsigned char* __restrict__ itemPass, uint32_t* __restrict__ nearList,
-    uint32_t* __restrict__ nearCount, uint32_t* __restrict__ farVisCount, uint32_t minNear, int shift)
+    uint32_t* __restrict__ nearCount, uint32_t* __restrict__ farCount, uint32_t* __restrict__ farVisCount, uint32_t minNear, int shift)
 {
     __shared__ uint32_t hist[1024];
-    __shared__ uint32_t sCut, sNear;
+    __shared__ uint32_t sCut, sNear, sFar;
     const int v = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     const uint32_t n = min(itemCount[v], itemCap);
     const uint32_t target = max(minNear, n >> shift);
@@ -1417,6 +1417,7 @@ __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restr
     {
         farVisCount[v] = 0;
         sNear = 0;
+        sFar = 0;
     }
     if (n <= target || !views[v].useOcclusion)
     {
@@ -1426,7 +1427,10 @@ __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restr
             list[i] = i;
         }
         if (tid == 0)
+        {
             nearCount[v] = n;
+            farCount[v] = 0;
+        }
         return;
     }
     for (int i = tid; i < 1024; i += 256)
@@ -1481,23 +1485,32 @@ __global__ void __launch_bounds__(256) k_items_near_far(const ViewConst* __restr
         pos = __shfl_sync(0xffffffffu, pos, 0);
         if (near)
             list[pos + __popc(bal & ((1u << lane) - 1u))] = i;
+        // ... and the far ones from the back of the same array (k_items_far_test walks them densely): list[itemCap - 1 - k]
+        const uint32_t fbal = __ballot_sync(0xffffffffu, i < n && !near);
+        uint32_t fpos = 0;
+        if (lane == 0 && fbal)
+            fpos = atomicAdd(&sFar, (uint32_t)__popc(fbal));
+        fpos = __shfl_sync(0xffffffffu, fpos, 0);
+        if (i < n && !near)
+            list[itemCap - 1u - (fpos + __popc(fbal & ((1u << lane) - 1u)))] = i;
     }
     __syncthreads();
     if (tid == 0)
+    {
         nearCount[v] = sNear;
+        farCount[v] = sFar;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_items_far_test(BufGeom g, const ViewConst* __restrict__ views, const DrawItem* __restrict__ items, uint32_t itemCap,
-    const uint32_t* __restrict__ itemCount, const float* __restrict__ occAabb6, const int* __restrict__ depthAll, const int2* __restrict__ mipAll,
-    unsigned char* __restrict__ itemPass, uint32_t* __restrict__ farVisList, uint32_t* __restrict__ farVisCount)
+    const uint32_t* __restrict__ nearList, const uint32_t* __restrict__ farCount, const float* __restrict__ occAabb6, const int* __restrict__ depthAll,
+    const int2* __restrict__ mipAll, unsigned char* __restrict__ itemPass, uint32_t* __restrict__ farVisList, uint32_t* __restrict__ farVisCount)
 {
     const int v = blockIdx.y;
-    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= min(itemCount[v], itemCap))
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= min(farCount[v], itemCap))
         return;
-    unsigned char* pass = itemPass + (size_t)v * itemCap + i;
-    if (*pass != kPassFarHidden)
-        return;
+    const uint32_t i = nearList[(size_t)v * itemCap + (itemCap - 1u - k)]; // the far items sit at the back of the near list's array
     const float* b = occAabb6 + 6 * (size_t)items[(size_t)v * itemCap + i].model;
     BoxRect r;
     bool visible = ob_project(g, views[v].vp, b[0], b[1], b[2], b[3], b[4], b[5], r);
@@ -1518,26 +1531,29 @@ __global__ void __launch_bounds__(256) k_items_far_test(BufGeom g, const ViewCon
     }
     if (visible)
     {
-        *pass = kPassFarVisible;
+        itemPass[(size_t)v * itemCap + i] = kPassFarVisible;
         farVisList[(size_t)v * itemCap + atomicAdd(&farVisCount[v], 1u)] = i;
     }
 }
 
 void launch_items_near_far(const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, const uint32_t* itemCount, const float* occAabb6,
-    unsigned char* itemPass, uint32_t* nearList, uint32_t* nearCount, uint32_t* farVisCount, uint32_t minNear, int shift, cudaStream_t s)
+    unsigned char* itemPass, uint32_t* nearList, uint32_t* nearCount, uint32_t* farCount, uint32_t* farVisCount, uint32_t minNear, int shift,
+    cudaStream_t s)
 {
     if (numViews)
-        k_items_near_far<<<numViews, 256, 0, s>>>(views, items, itemCap, itemCount, occAabb6, itemPass, nearList, nearCount, farVisCount, minNear, shift);
+        k_items_near_far<<<numViews, 256, 0, s>>>(views, items, itemCap, itemCount, occAabb6, itemPass, nearList, nearCount, farCount, farVisCount, minNear,
+            shift);
 }
 
 void launch_items_far_test(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
-    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, uint32_t* farVisList,
-    uint32_t* farVisCount, cudaStream_t s)
+    const uint32_t* nearList, const uint32_t* farCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass,
+    uint32_t* farVisList, uint32_t* farVisCount, cudaStream_t s)
 {
     if (!numViews || !maxItems)
         return;
-    dim3 grid((maxItems + 255) / 256, numViews);
-    k_items_far_test<<<grid, 256, 0, s>>>(g, views, items, itemCap, itemCount, occAabb6, depth, mips, itemPass, farVisList, farVisCount);
+    // 128-thread blocks over each view's compacted far list (a few hundred items of up to maxItems)
+    dim3 grid((maxItems + 127) / 128, numViews);
+    k_items_far_test<<<grid, 128, 0, s>>>(g, views, items, itemCap, nearList, farCount, occAabb6, depth, mips, itemPass, farVisList, farVisCount);
 }
 
 size_t dense_counter_bytes(int numViews, int numOctants)

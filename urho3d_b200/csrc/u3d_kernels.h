@@ -126,10 +126,11 @@ cudaError_t init_tile_kernel();
 /// them) get kPassNear, the rest kPassFarHidden.  far_test: items marked kPassFarHidden whose occluder box is visible in the buffers drawn
 /// so far become kPassFarVisible.
 void launch_items_near_far(const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, const uint32_t* itemCount, const float* occAabb6,
-    unsigned char* itemPass, uint32_t* nearList, uint32_t* nearCount, uint32_t* farVisCount /* zeroed here */, uint32_t minNear, int shift, cudaStream_t s);
+    unsigned char* itemPass, uint32_t* nearList /* near items from the front, far items from the back */, uint32_t* nearCount, uint32_t* farCount,
+    uint32_t* farVisCount /* zeroed here */, uint32_t minNear, int shift, cudaStream_t s);
 void launch_items_far_test(const BufGeom& g, const ViewConst* views, int numViews, const DrawItem* items, uint32_t itemCap, uint32_t maxItems,
-    const uint32_t* itemCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass, uint32_t* farVisList,
-    uint32_t* farVisCount, cudaStream_t s);
+    const uint32_t* nearList, const uint32_t* farCount, const float* occAabb6, const int* depth, const int2* mips, unsigned char* itemPass,
+    uint32_t* farVisList, uint32_t* farVisCount, cudaStream_t s);
 /// irregular pre-pass (2 launches) + tile kernel (1 launch)
 void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* depth, int2* mips, const RasterDev& rd, cudaStream_t s);
 void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s);
