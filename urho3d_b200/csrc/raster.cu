@@ -1603,21 +1603,27 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
     __syncthreads(); // the other classes composite with atomics, from any warp
     // (2) small triangles (bbox area <= 256 px^2, kLaneAreaMax; 86 % of the triangles of the benchmark scene have <= 64): one per lane, groups of 32 handed out
     //     dynamically
+    //     -- and when the bin is short (the first pass of the two-phase drawing leaves ~100 per tile), 2, 4 or 8 neighbouring lanes share a
+    //     triangle's rows so that the bin still spreads over all 16 warps instead of keeping 3 of them busy while 13 wait at the barrier
     {
         const uint32_t* bin = binBase + (size_t)kClsLane * cap;
+        const int shareLog = nLane > 256u ? 0 : nLane > 128u ? 1 : nLane > 64u ? 2 : 3;
+        const uint32_t perClaim = 32u >> shareLog;
+        const int sub = lane & ((1 << shareLog) - 1), step = 1 << shareLog;
         for (;;)
         {
             uint32_t base = 0;
             if (lane == 0)
-                base = atomicAdd(&sNext[0], 32u);
+                base = atomicAdd(&sNext[0], perClaim);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= nLane)
                 break;
-            if (base + lane < nLane)
+            const uint32_t mine = base + (uint32_t)(lane >> shareLog);
+            if (mine < nLane)
             {
-                const TriSetup ts = load_tri(region + (bin[base + lane] & 0x1FFFFFFFu));
+                const TriSetup ts = load_tri(region + (bin[mine] & 0x1FFFFFFFu));
                 const int ya = max(ts.y0, ty0), yb = min(ts.y2, ty1);
-                for (int y = ya; y < yb; ++y)
+                for (int y = ya + sub; y < yb; y += step)
                 {
                     const HalfRow r = tri_row(ts, y);
                     const int xa = max(r.xl, tx0), xb = min(r.xr, tx1);
@@ -1632,15 +1638,16 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
     //     lane walks about 8 pixels of its row; groups of 8 triangles are handed out so that short bins still use all warps.
     {
         const uint32_t* bin = binBase + (size_t)kClsWarp * cap;
+        const uint32_t warpGroup = min((uint32_t)kWarpGroup, max(1u, (nWarp + kTileThreads / 32 - 1) / (kTileThreads / 32))); // short bins: one claim per warp
         for (;;)
         {
             uint32_t base = 0;
             if (lane == 0)
-                base = atomicAdd(&sNext[1], (uint32_t)kWarpGroup);
+                base = atomicAdd(&sNext[1], warpGroup);
             base = __shfl_sync(0xffffffffu, base, 0);
             if (base >= nWarp)
                 break;
-            const uint32_t cnt = min((uint32_t)kWarpGroup, nWarp - base);
+            const uint32_t cnt = min(warpGroup, nWarp - base);
             // lanes 0..cnt-1 fetch one record each (one L2 round trip per group); the warp then walks them from registers
             uint32_t mine = 0;
             TriSetup my;
