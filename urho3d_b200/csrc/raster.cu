@@ -1456,8 +1456,15 @@ __device__ __forceinline__ void tile_min(int* tile, int idx, int z)
         atomicMin(tile + idx, z);
 }
 
+#ifndef U3D_FILL_SHARE_SHIFT
+#define U3D_FILL_SHARE_SHIFT 0 // lanes per lane-class triangle ~ (512 << shift) / triangles in the bin ...
+#define U3D_FILL_SHARE_MAX 3   // ... up to 1 << max
+#endif
+#ifndef U3D_FILL_WARP_DIV
+#define U3D_FILL_WARP_DIV 128  // warp-class claims of a short bin: bin / this many triangles each (A/B, fill: 16 -> 1.29 ms, 32 -> 1.23, 64 -> 1.18, 128 -> 1.16)
+#endif
 #ifndef U3D_TILE_MINB
-#define U3D_TILE_MINB 2
+#define U3D_TILE_MINB 3 // three 72 KB tiles fit an SM's shared memory; 40 registers cost 52 bytes of spills and win (A/B: fill 1.15 -> 1.06 ms)
 #endif
 __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
 {
@@ -1607,7 +1614,8 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
     //     triangle's rows so that the bin still spreads over all 16 warps instead of keeping 3 of them busy while 13 wait at the barrier
     {
         const uint32_t* bin = binBase + (size_t)kClsLane * cap;
-        const int shareLog = nLane > 256u ? 0 : nLane > 128u ? 1 : nLane > 64u ? 2 : 3;
+        const uint32_t nl = nLane >> U3D_FILL_SHARE_SHIFT;
+        const int shareLog = min(U3D_FILL_SHARE_MAX, nl > 256u ? 0 : nl > 128u ? 1 : nl > 64u ? 2 : nl > 32u ? 3 : nl > 16u ? 4 : 5);
         const uint32_t perClaim = 32u >> shareLog;
         const int sub = lane & ((1 << shareLog) - 1), step = 1 << shareLog;
         for (;;)
@@ -1638,7 +1646,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
     //     lane walks about 8 pixels of its row; groups of 8 triangles are handed out so that short bins still use all warps.
     {
         const uint32_t* bin = binBase + (size_t)kClsWarp * cap;
-        const uint32_t warpGroup = min((uint32_t)kWarpGroup, max(1u, (nWarp + kTileThreads / 32 - 1) / (kTileThreads / 32))); // short bins: one claim per warp
+        const uint32_t warpGroup = min((uint32_t)kWarpGroup, max(1u, (nWarp + U3D_FILL_WARP_DIV - 1) / U3D_FILL_WARP_DIV)); // short bins: one claim per warp
         for (;;)
         {
             uint32_t base = 0;

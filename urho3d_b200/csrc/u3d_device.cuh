@@ -336,7 +336,11 @@ struct BoxRect
 /// :386-389); otherwise fills `r`.
 __device__ __forceinline__ bool ob_project(const BufGeom& g, const float* vp, float mnx, float mny, float mnz, float mxx, float mxy, float mxz, BoxRect& r)
 {
+    // The reference's `if (s < min) min = s` chain (OB.cpp:373-380) skips NaN corners and never leaves a NaN first corner: fminf / fmaxf
+    // (one FMNMX each, they return the other operand for a NaN) do the same for every corner but the first, which is put back below.
+    // (They may pick -0 where the chain keeps +0; both become the same integer further down.)
     float minX = 0.f, maxX = 0.f, minY = 0.f, maxY = 0.f, minZ = 0.f;
+    float firstX = 0.f, firstY = 0.f, firstZ = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i)
     {
@@ -347,19 +351,22 @@ __device__ __forceinline__ bool ob_project(const BufGeom& g, const float* vp, fl
         V3 s = viewport_transform(g, v);
         if (i == 0)
         {
-            minX = maxX = s.x;
-            minY = maxY = s.y;
-            minZ = s.z;
+            minX = maxX = firstX = s.x;
+            minY = maxY = firstY = s.y;
+            minZ = firstZ = s.z;
         }
         else
         {
-            if (s.x < minX) minX = s.x;
-            if (s.x > maxX) maxX = s.x;
-            if (s.y < minY) minY = s.y;
-            if (s.y > maxY) maxY = s.y;
-            if (s.z < minZ) minZ = s.z;
+            minX = fminf(minX, s.x);
+            maxX = fmaxf(maxX, s.x);
+            minY = fminf(minY, s.y);
+            maxY = fmaxf(maxY, s.y);
+            minZ = fminf(minZ, s.z);
         }
     }
+    if (firstX != firstX) minX = maxX = firstX;
+    if (firstY != firstY) minY = maxY = firstY;
+    if (firstZ != firstZ) minZ = firstZ;
     int left = trunc_x86(minX - 1.5f), top = trunc_x86(minY - 1.5f), right = round_x86(maxX), bottom = round_x86(maxY);
     if (right < 0 || bottom < 0)
         return true;
