@@ -875,7 +875,11 @@ __global__ void __launch_bounds__(128) k_clip_triangles(BufGeom g, TileGeom tg, 
 
 /// Blocks of a view sweep its draw items in slices of kSetupItems; inside a slice the threads sweep the flat triangle index
 /// space of those items.  DrawBatch + DrawTriangle (OB.cpp:464-541, 589-683).
-__global__ void __launch_bounds__(kSetupThreads) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
+#ifndef U3D_SETUP_MINB
+#define U3D_SETUP_MINB 4 // 64 registers (24 bytes of spills), 4 blocks per SM; A/B on the bench: set-up 0.39 ms at 106 registers / 2 blocks, 0.31 at
+                         // 79 / 3, 0.28 at 64 / 4 (the kernel waits on barriers and dependent loads, more resident warps hide them)
+#endif
+__global__ void __launch_bounds__(kSetupThreads, U3D_SETUP_MINB) k_setup_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views,
     const DrawItem* __restrict__ items, uint32_t itemCap, const uint32_t* __restrict__ itemCount, const float* __restrict__ models,
     const MeshDev* __restrict__ meshes, RasterDev rd, uint32_t sliceItems /* <= kSetupItems: items a block takes at a time */)
 {
