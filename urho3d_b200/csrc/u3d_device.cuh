@@ -146,19 +146,20 @@ template <bool FAST> __device__ __forceinline__ int frustum_test(const float* pl
 {
     float cx = (mxx + mnx) * 0.5f, cy = (mxy + mny) * 0.5f, cz = (mxz + mnz) * 0.5f;
     float ex = cx - mnx, ey = cy - mny, ez = cz - mnz;
-    bool allInside = true;
+    // All six planes, no early return: a warp runs every plane anyway as long as one of its lanes is still inside, and the reference's
+    // answer depends only on whether SOME plane rejects the box / cuts it (the comparisons are the same, NaNs compare false on both sides).
+    bool outside = false, allInside = true;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
     {
         const float nx = planes[4 * i], ny = planes[4 * i + 1], nz = planes[4 * i + 2], d = planes[4 * i + 3];
         float dist = nx * cx + ny * cy + nz * cz + d;
         float absDist = fabsf(nx) * ex + fabsf(ny) * ey + fabsf(nz) * ez;
-        if (dist < -absDist)
-            return OUTSIDE;
-        if (!FAST && dist < absDist)
-            allInside = false;
+        outside |= dist < -absDist;
+        if (!FAST)
+            allInside &= !(dist < absDist);
     }
-    return (FAST || allInside) ? INSIDE : INTERSECTS;
+    return outside ? OUTSIDE : (FAST || allInside) ? INSIDE : INTERSECTS;
 }
 
 /// Ray::HitDistance(const BoundingBox&), Math/Ray.cpp:71-148: 0 when the origin is inside, else the nearest entry through one of the
