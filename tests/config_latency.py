@@ -115,6 +115,9 @@ def cpu_city_view(sc, view, w, h, vtx, idx):
 def run(name, cpu):
     cfg = scenes.CONFIGS[name]
     ctx = capi.Context(0)
+    for kv in filter(None, os.environ.get("U3D_DEBUG_OPTS", "").split(",")):  # tuning sweeps only, e.g. "tile_target=444"
+        opt, val = kv.split("=")
+        capi.debug_set_option(opt, int(val))
     out = {"config": name}
     w, h = cfg["width"], cfg["height"]
     if name == "C5":

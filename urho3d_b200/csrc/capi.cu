@@ -26,6 +26,7 @@ static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
 // (launch_items_near_far / launch_items_far_test), 0 = every selected occluder is set up and filled.  "two_phase_min" / "two_phase_shift":
 // the near set holds at least that many draw items, or 1 / 2^shift of the view's items.
 static int g_twoPhase = 1, g_twoPhaseMin = 32, g_twoPhaseShift = 4;
+static int g_tileTarget = 148 * 3; // tiles a full batch should launch at least (make_tile_geom halves the tile height below it); "tile_target"
 static int g_readDenseProf = 0; // "read_dense_prof": u3d_debug_read_cull_prof returns the dense path's timers
 constexpr int kDenseMinViews = 16;
 
@@ -276,7 +277,7 @@ struct ViewSet
     {
         ctx = c;
         g = make_geom(w, h);
-        tg = make_tile_geom(g);
+        tg = make_tile_geom(g, nviews, (uint32_t)std::max(g_tileTarget, 0));
         useTiles = tiles && g.w >= 4;
         maxViews = nviews;
         itemCap = itemCapPerView;
@@ -514,6 +515,11 @@ int u3d_debug_set_option(const char* name, int value)
     if (name && std::strcmp(name, "two_phase_min") == 0)
     {
         g_twoPhaseMin = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "tile_target") == 0)
+    {
+        g_tileTarget = value; // takes effect for buffers / batches created afterwards
         return U3D_OK;
     }
     if (name && std::strcmp(name, "two_phase_shift") == 0)

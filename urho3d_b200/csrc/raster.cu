@@ -560,11 +560,42 @@ struct EmitCtx
     uint32_t* irrTotal;
     uint32_t* irrOfView;
     uint32_t view;
-    int w, h, tileW, tilesX, tilesY;
+    int w, h, tileW, tilesX, tilesY, tileHLog;
     int forceIrregular;
     int laneAreaMax, warpAreaMax;
     int countOnly;           // decide drawOk only: nothing is emitted
+    // k_clip_triangles: triangles that cover many tiles are not binned by the thread that clipped them but queued here, and the whole
+    // warp bins them afterwards (BinRequest; nullptr elsewhere)
+    struct BinRequest* defer;
+    uint32_t* deferCount;
 };
+
+struct BinRequest { uint32_t view; int txa, tya, nx, n; uint32_t cls, entry, pad; };
+constexpr int kDeferCap = 160; // requests per warp between two drains; beyond it the thread bins alone
+
+/// Tiles first + k * stride (k = 0, 1, ...) of a triangle's n tiles, four at a time: the four atomics are in flight together; a thread that
+/// waits for each position before it asks for the next pays a round trip per tile.
+__device__ __forceinline__ void bin_tiles(uint32_t* binCount, uint32_t* binIdx, uint32_t cap, int tilesX, int txa, int tya, int nx, int n, uint32_t c, uint32_t e,
+    int first, int stride)
+{
+    for (int k0 = first; k0 < n; k0 += 4 * stride)
+    {
+        uint32_t pos[4];
+        int tile[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+        {
+            const int k = k0 + j * stride;
+            // buffers up to 256 wide have one tile per row of tiles: no division
+            tile[j] = k >= n ? -1 : nx == 1 ? (tya + k) * tilesX + txa : (tya + k / nx) * tilesX + txa + k % nx;
+            pos[j] = tile[j] >= 0 ? atomicAdd(&binCount[tile[j] * kNumCls + c], 1u) : 0xFFFFFFFFu;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+            if (pos[j] < cap)
+                binIdx[((size_t)tile[j] * kNumCls + c) * cap + pos[j]] = e;
+    }
+}
 
 /// Append one record to the view's region; on the tile path also classify it and bin it.
 /// "Regular" = every span of the triangle lies inside its own row of the buffer (0 <= row < h, 0 <= xl, xr <= w for all rows),
@@ -641,15 +672,43 @@ __device__ __forceinline__ void emit_tri(const EmitCtx& ec, const TriSetup& ts)
     else
         cls = kClsCta;
     const int txa = x0 / ec.tileW, txb = min((x1 - 1) / ec.tileW, ec.tilesX - 1);
-    const int tya = ts.y0 / kTileH, tyb = min((ts.y2 - 1) / kTileH, ec.tilesY - 1);
-    for (int ty = tya; ty <= tyb; ++ty)
-        for (int tx = txa; tx <= txb; ++tx)
+    const int tya = ts.y0 >> ec.tileHLog, tyb = min((ts.y2 - 1) >> ec.tileHLog, ec.tilesY - 1);
+    const int nx = txb - txa + 1, n = nx * (tyb - tya + 1);
+    const uint32_t entry = slot | (hint << 29);
+    constexpr int kBinAlone = 16;
+    if (n > kBinAlone && ec.defer)
+    {
+        const uint32_t q = atomicAdd(ec.deferCount, 1u);
+        if (q < (uint32_t)kDeferCap)
         {
-            const int tile = ty * ec.tilesX + tx;
-            const uint32_t pos = atomicAdd(&ec.binCount[tile * kNumCls + cls], 1u);
-            if (pos < ec.cap)
-                ec.binIdx[((size_t)tile * kNumCls + cls) * ec.cap + pos] = slot | (hint << 29);
+            BinRequest rq;
+            rq.view = ec.view; rq.txa = txa; rq.tya = tya; rq.nx = nx; rq.n = n; rq.cls = cls; rq.entry = entry; rq.pad = 0;
+            ec.defer[q] = rq;
+            return;
         }
+    }
+    // A triangle that covers many tiles (a ground plane over a 2048 x 2048 buffer: hundreds) is binned by all lanes that arrived here
+    // together.  Lanes of one warp may belong to different views, so the bins' addresses travel with the triangle.
+    const uint32_t active = __activemask();
+    uint32_t big = __ballot_sync(active, n > kBinAlone);
+    if (n <= kBinAlone)
+        bin_tiles(ec.binCount, ec.binIdx, ec.cap, ec.tilesX, txa, tya, nx, n, cls, entry, 0, 1);
+    if (!big)
+        return;
+    const int lane = threadIdx.x & 31;
+    const int rank = __popc(active & ((1u << lane) - 1u)), nActive = __popc(active);
+    const unsigned long long pc = (unsigned long long)ec.binCount, pi = (unsigned long long)ec.binIdx;
+    while (big)
+    {
+        const int src = __ffs(big) - 1;
+        big &= big - 1;
+        uint32_t* sCount = (uint32_t*)__shfl_sync(active, pc, src);
+        uint32_t* sIdx = (uint32_t*)__shfl_sync(active, pi, src);
+        const uint32_t sCap = __shfl_sync(active, ec.cap, src), sCls = __shfl_sync(active, cls, src), sEntry = __shfl_sync(active, entry, src);
+        const int sTilesX = __shfl_sync(active, ec.tilesX, src), sTxa = __shfl_sync(active, txa, src), sTya = __shfl_sync(active, tya, src);
+        const int sNx = __shfl_sync(active, nx, src), sN = __shfl_sync(active, n, src);
+        bin_tiles(sCount, sIdx, sCap, sTilesX, sTxa, sTya, sNx, sN, sCls, sEntry, rank, nActive);
+    }
 }
 
 /// ViewportTransform x3 + SignedArea + cull test (OB.cpp:629-634).  Returns true when the reference would call DrawTriangle2D.
@@ -849,10 +908,13 @@ __device__ __forceinline__ EmitCtx make_emit_ctx(const BufGeom& g, const TileGeo
     ec.tileW = tg.tileW;
     ec.tilesX = tg.tilesX;
     ec.tilesY = tg.tilesY;
+    ec.tileHLog = tg.tileHLog;
     ec.forceIrregular = rd.forceIrregular;
     ec.laneAreaMax = rd.laneAreaMax;
     ec.warpAreaMax = rd.warpAreaMax;
     ec.countOnly = rd.countOnly;
+    ec.defer = nullptr;
+    ec.deferCount = nullptr;
     return ec;
 }
 
@@ -860,16 +922,45 @@ __device__ __forceinline__ EmitCtx make_emit_ctx(const BufGeom& g, const TileGeo
 /// so that the slow path (<= 64 triangles of scratch in local memory) never stalls the set-up blocks.  DrawTriangle's else-branch, OB.cpp:640-679.
 __global__ void __launch_bounds__(128) k_clip_triangles(BufGeom g, TileGeom tg, const ViewConst* __restrict__ views, RasterDev rd)
 {
+    __shared__ BinRequest sDefer[4][kDeferCap];
+    __shared__ uint32_t sDeferCount[4];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const uint32_t n = min(*rd.clipCount, rd.clipCap);
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    if (lane == 0)
+        sDeferCount[wid] = 0;
+    __syncwarp();
+    // every warp takes 32 queue entries at a time, a triangle per lane; what the clipped pieces cover in many tiles is binned by the
+    // whole warp afterwards (one thread alone would pay an atomic's round trip per tile and piece: 0.6 ms for a 2048 x 2048 city view)
+    for (uint32_t base = (blockIdx.x * 4u + (uint32_t)wid) * 32u; base < n; base += gridDim.x * 128u)
     {
-        const float4* d = reinterpret_cast<const float4*>(rd.clipQueue + (size_t)i * kClipEntryFloats);
-        const float4 a = d[0], b = d[1], c = d[2], m = d[3];
-        const int v = (int)__float_as_uint(m.y);
-        const EmitCtx ec = make_emit_ctx(g, tg, rd, v);
-        const V4 c0 = {a.x, a.y, a.z, a.w}, c1 = {b.x, b.y, b.z, b.w}, c2 = {c.x, c.y, c.z, c.w};
-        if (clip_and_setup(g, views[v].cullMode, __float_as_uint(m.x), c0, c1, c2, ec))
-            atomicAdd(&rd.drawnSources[v], 1u);
+        const uint32_t i = base + (uint32_t)lane;
+        if (i < n)
+        {
+            const float4* d = reinterpret_cast<const float4*>(rd.clipQueue + (size_t)i * kClipEntryFloats);
+            const float4 a = d[0], b = d[1], c = d[2], m = d[3];
+            const int v = (int)__float_as_uint(m.y);
+            EmitCtx ec = make_emit_ctx(g, tg, rd, v);
+            if (ec.binIdx)
+            {
+                ec.defer = sDefer[wid];
+                ec.deferCount = &sDeferCount[wid];
+            }
+            const V4 c0 = {a.x, a.y, a.z, a.w}, c1 = {b.x, b.y, b.z, b.w}, c2 = {c.x, c.y, c.z, c.w};
+            if (clip_and_setup(g, views[v].cullMode, __float_as_uint(m.x), c0, c1, c2, ec))
+                atomicAdd(&rd.drawnSources[v], 1u);
+        }
+        __syncwarp();
+        const uint32_t nReq = min(sDeferCount[wid], (uint32_t)kDeferCap);
+        for (uint32_t r = 0; r < nReq; ++r)
+        {
+            const BinRequest rq = sDefer[wid][r];
+            const EmitCtx ec = make_emit_ctx(g, tg, rd, (int)rq.view);
+            bin_tiles(ec.binCount, ec.binIdx, ec.cap, ec.tilesX, rq.txa, rq.tya, rq.nx, rq.n, rq.cls, rq.entry, lane, 32);
+        }
+        __syncwarp();
+        if (lane == 0)
+            sDeferCount[wid] = 0;
+        __syncwarp();
     }
 }
 
@@ -1472,16 +1563,17 @@ __device__ __forceinline__ void tile_min(int* tile, int idx, int z)
 #endif
 __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufGeom g, TileGeom tg, int* __restrict__ depthAll, int2* __restrict__ mipAll, RasterDev rd)
 {
-    extern __shared__ int tile[]; // tileW x kTileH ints, later reused for the mip levels
+    extern __shared__ int tile[]; // tileW x tileH ints, later reused for the mip levels
     __shared__ uint32_t sNext[2];
     constexpr int kCtaStage = kTileThreads / 4; // CTA-class records staged per batch: one int4 per thread
     __shared__ int4 sCtaTri[kCtaStage][4];
 
     const int v = blockIdx.y;
     const int tIdx = blockIdx.x;
-    const int tx0 = (tIdx % tg.tilesX) * tg.tileW, ty0 = (tIdx / tg.tilesX) * kTileH;
+    const int tileH = tg.tileH;
+    const int tx0 = (tIdx % tg.tilesX) * tg.tileW, ty0 = (tIdx / tg.tilesX) * tileH;
     const int tw = tg.tileW, twLog = tg.tileWLog, tw4Log = twLog - 2;
-    const int rows = min(kTileH, g.h - ty0); // valid rows of this tile
+    const int rows = min(tileH, g.h - ty0); // valid rows of this tile
     const int tid = threadIdx.x, lane = tid & 31;
     int* depth = depthAll + (size_t)v * g.w * g.h;
     // second pass of the two-phase occluder drawing: composite on top of what the first pass left in HBM; tiles without new triangles
@@ -1507,7 +1599,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
                 {
                     const int lw = tw >> (lv + 1);
                     const int gy0 = ty0 >> (lv + 1), gx0 = tx0 >> (lv + 1);
-                    const int lrows = min(g.mh[lv] - gy0, kTileH >> (lv + 1));
+                    const int lrows = min(g.mh[lv] - gy0, tileH >> (lv + 1));
                     for (int i = tid; i < lw * lrows; i += kTileThreads)
                         mips[g.moff[lv] + (size_t)(gy0 + (i >> (twLog - lv - 1))) * g.mw[lv] + gx0 + (i & (lw - 1))] = c2;
                 }
@@ -1518,7 +1610,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
 
     // ---- initialise ----
     {
-        const int n4 = (tw * kTileH) >> 2;
+        const int n4 = (tw * tileH) >> 2;
         int4* t4 = reinterpret_cast<int4*>(tile);
         const int tw4 = tw >> 2;
         for (int i = tid; i < n4; i += kTileThreads)
@@ -1784,7 +1876,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
     }
     int2* prev = lv0;
     int prevW = tw >> 1, prevRows = (rows + 1) >> 1;
-    int2* next = lv0 + (tw >> 1) * (kTileH >> 1);
+    int2* next = lv0 + (tw >> 1) * (tileH >> 1);
     for (int lv = 1; lv < tg.fused; ++lv)
     {
         const int lw = tw >> (lv + 1);
@@ -1812,7 +1904,7 @@ __global__ void __launch_bounds__(kTileThreads, U3D_TILE_MINB) k_fill_tiles(BufG
         prev = next;
         prevW = lw;
         prevRows = lrows;
-        next = next + lw * (kTileH >> (lv + 1));
+        next = next + lw * (tileH >> (lv + 1));
     }
 }
 
@@ -1858,16 +1950,26 @@ __global__ void k_mip_level(BufGeom g, int lv, const int* __restrict__ depthAll,
 // ---------------------------------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------------------------------
-TileGeom make_tile_geom(const BufGeom& g)
+TileGeom make_tile_geom(const BufGeom& g, uint32_t maxViews, uint32_t targetTiles)
 {
     TileGeom t{};
     t.tileW = g.w < 256 ? g.w : 256;
     t.tilesX = g.w / t.tileW;
-    t.tilesY = (g.h + kTileH - 1) / kTileH;
+    // Tile height: kTileH rows, halved (down to 16: a row per warp for the CTA-class triangles) while a full batch would launch fewer tiles
+    // than `targetTiles` (three per SM, one wave of k_fill_tiles): a single 2048 x 2048 view gets 512 tiles of 256 x 32 instead of 256,
+    // which also splits the rows a city's horizon crowds with triangles over twice as many CTAs (C5: fill 1.01 -> 0.54 ms; 16 rows: 0.51,
+    // but twice the bin inserts in set-up).
+    t.tileH = kTileH;
+    while (t.tileH > 16 && (uint64_t)std::max<uint32_t>(maxViews, 1u) * t.tilesX * ((g.h + t.tileH - 1) / t.tileH) < targetTiles)
+        t.tileH >>= 1;
+    t.tileHLog = 0;
+    while ((1 << t.tileHLog) < t.tileH)
+        ++t.tileHLog;
+    t.tilesY = (g.h + t.tileH - 1) / t.tileH;
     t.numTiles = t.tilesX * t.tilesY;
     // levels that can be reduced inside one tile: both tile dimensions must cover whole texels of the level
     int f = 0;
-    while (f < g.nlev && (2 << f) <= t.tileW && (2 << f) <= kTileH)
+    while (f < g.nlev && (2 << f) <= t.tileW && (2 << f) <= t.tileH)
         ++f;
     // the in-place level-0 pass keeps its inputs in registers: needs tileW >= 4 for the int4 paths
     t.fused = t.tileW >= 4 ? f : 0;
@@ -1974,7 +2076,7 @@ void launch_fill_tiles(const BufGeom& g, const TileGeom& tg, int numViews, int* 
     if (!rd.secondPass)
         k_irregular_clear<<<dim3(4, numViews), 256, 0, s>>>(g, depth, rd.irrOfView);
     k_irregular_fill<<<148, 256, 0, s>>>(g, depth, rd.pool, rd.triBase, rd.irrList, rd.irrCap, rd.irrTotal);
-    k_fill_tiles<<<dim3(tg.numTiles, numViews), kTileThreads, (size_t)tg.tileW * kTileH * 4, s>>>(g, tg, depth, mips, rd);
+    k_fill_tiles<<<dim3(tg.numTiles, numViews), kTileThreads, (size_t)tg.tileW * tg.tileH * 4, s>>>(g, tg, depth, mips, rd);
 }
 
 void launch_hierarchy(const BufGeom& g, int numViews, const int* depth, int2* mips, int firstLevel, cudaStream_t s)

@@ -22,7 +22,7 @@ constexpr int kRankCap = 4096;               // occluder candidates per view in 
 constexpr uint32_t kFlagClipOverflow = 16u;  // more plane-crossing triangles than the clipper queue holds
 
 // tile path
-constexpr int kTileH = 64;          // tile = min(width, 256) x 64 pixels of int depth in shared memory (64 KiB for 256 wide)
+constexpr int kTileH = 64;          // tile = min(width, 256) x (at most) 64 pixels of int depth in shared memory (64 KiB for 256 wide)
 constexpr int kTileThreads = 512;
 constexpr uint32_t kClsLane = 0;      // bbox area <= 64: one lane rasterises it
 constexpr uint32_t kClsWarp = 1;      // bbox area <= 16384: one warp, laid out as rows x lanes-per-row
@@ -35,6 +35,7 @@ constexpr int kWarpGroup = 8;         // warp-class triangles handed to a warp a
 struct TileGeom
 {
     int tileW, tilesX, tilesY, numTiles;
+    int tileH, tileHLog; // rows per tile: kTileH, or 32 / 16 for batches of few views (make_tile_geom)
     int tileWLog; // tileW is a power of two (min(width, 256), widths are powers of two): index arithmetic by shifts
     int fused;   // hierarchy levels reduced inside the tile kernel
 };
@@ -116,7 +117,7 @@ void launch_setup(const BufGeom& g, const TileGeom& tg, const ViewConst* views, 
     const uint32_t* itemCount, const float* models, const MeshDev* meshes, const RasterDev& rd, cudaStream_t s);
 void launch_fill_global(const BufGeom& g, int numViews, int* depth, const TriSetup* pool, const uint64_t* triBase, const uint32_t* triCap,
     const uint32_t* triCount, int blocksPerView, cudaStream_t s);
-TileGeom make_tile_geom(const BufGeom& g);
+TileGeom make_tile_geom(const BufGeom& g, uint32_t maxViews, uint32_t targetTiles);
 cudaError_t init_tile_kernel();
 /// Two-phase occluder drawing.  An occluder whose box fails OcclusionBuffer::IsVisible against a buffer that holds only SOME of the
 /// occluders cannot change the final plane either (every pixel of its rect is already nearer than its nearest point), so a view first
