@@ -697,6 +697,13 @@ def main():
     # K steps shared by one thread per slot is one or two calls per thread at small K: the e2e leg runs at least 8 calls per slot (its own
     # step count is reported as e2e.steps) so that it measures the steady state of the call path, like `value` does for the kernels
     e2e_steps = max(args.steps, 8 * len(slots))
+    if world * len(slots) > (os.cpu_count() or 1):
+        # more calling threads on the box than host cores: wait on a blocking event instead of spinning (what an engine with that many
+        # worker threads would configure)
+        capi.debug_set_option("blocking_wait", 1)
+        e2e_wait = "blocking event (%d calling threads on %d host cores)" % (world * len(slots), os.cpu_count() or 1)
+    else:
+        e2e_wait = "cudaStreamSynchronize"
     e2e_run(2 * len(slots))
     if world > 1:
         dist.barrier()
@@ -785,7 +792,7 @@ def main():
                 # SURVEY 8d's definition: submitted triangles / time of the draw + hierarchy phases alone (rank 0's shard, phase timers)
                 "occluder_mtri_per_s_raster_phases": float(stats[:, 0].sum()) / max(1e-9, 1e-3 * raster_ms) / 1e6,
                 "per_view": {"submitted_tris": tri_per_view, "query_result": n_cand / args.views, "visible": vis_per_view, "octants": M},
-                "e2e": {"value": args.views * e2e_steps / e2e_s, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+                "e2e": {"value": args.views * e2e_steps / e2e_s, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_wait": e2e_wait},
                 "gpu_launches": launches,
                 "roofline": {"bound": "hbm", "kernel": "cull = k_dense_tree + k_dense_frustum + k_dense_occlusion_walk + k_dense_emit (phases tree, frustum, "
                                                        "occlusion, emit)",

@@ -215,6 +215,30 @@ def test_octree_queries(gpu_ctx, mode):
     ob.close()
 
 
+def test_cull_views_with_a_blocking_wait(gpu_ctx):
+    """`blocking_wait` (for callers with more threads than host cores) changes how the call waits, not what it returns."""
+    w = h = 128
+    sc = helpers.small_scene(n=6000, k=120, extent=100.0, seed=77)
+    tree, flat, gs = gpu_scene(gpu_ctx, sc)
+    mesh = capi.Mesh(gpu_ctx, sc.mesh_vtx, sc.mesh_stride, sc.mesh_idx)
+    occ = capi.Occluders(gpu_ctx, sc.occ_aabb, sc.occ_model, [mesh], cull_mode=sc.cull_mode)
+    views = scenes.agent_cameras(24, 100.0, w, h, seed=5)
+    batch = capi.Batch(gpu_ctx, gs, occ, w, h, len(views), sc.n)
+    packed = capi.pack_views(views)
+    ref = [np.array(a, copy=True) for a in batch.cull_views(packed, capi.STAGE_VISIBLE)]
+    capi.debug_set_option("blocking_wait", 1)
+    try:
+        for _ in range(3):
+            got = batch.cull_views(packed, capi.STAGE_VISIBLE)
+            for a, b in zip(ref, got):
+                assert np.array_equal(a, b)
+    finally:
+        capi.debug_set_option("blocking_wait", 0)
+    assert ref[0][:, 1].sum() > 0
+    for o in (batch, occ, mesh, gs, tree):
+        o.close()
+
+
 @pytest.mark.parametrize("w,h,nviews,stress", [(256, 160, 12, False), (256, 256, 8, True), (64, 64, 40, True), (1024, 576, 2, False)])
 def test_batched_views(gpu_ctx, w, h, nviews, stress):
     """The batched many-view entry point: depth plane, every mip level, tri counts, query result and visible set per view."""

@@ -26,6 +26,7 @@ static uint32_t g_denseQueueCap = 0, g_densePoolCap = 0;
 // (launch_items_near_far / launch_items_far_test), 0 = every selected occluder is set up and filled.  "two_phase_min" / "two_phase_shift":
 // the near set holds at least that many draw items, or 1 / 2^shift of the view's items.
 static int g_twoPhase = 1, g_twoPhaseMin = 32, g_twoPhaseShift = 4;
+static int g_blockingWait = 0; // u3d_batch_cull_views waits on a blocking event instead of spinning in cudaStreamSynchronize ("blocking_wait")
 static int g_tileTarget = 148 * 3; // tiles a full batch should launch at least (make_tile_geom halves the tile height below it); "tile_target"
 static int g_readDenseProf = 0; // "read_dense_prof": u3d_debug_read_cull_prof returns the dense path's timers
 constexpr int kDenseMinViews = 16;
@@ -448,6 +449,8 @@ struct u3d_batch
     PinnedBuf<uint32_t> hostCounts;
     cudaEvent_t viewsCopied{};        // the last host -> device copy out of hostViews (whatever stream it ran on)
     bool haveViewsEvent{};
+    cudaEvent_t done{};               // blocking wait of u3d_batch_cull_views (option "blocking_wait")
+    bool haveDoneEvent{};
     // u3d_batch_cull_views: flags | counts | packed offsets leave the device as ONE block, and the packed ids are copied in the same
     // breath up to the size the previous call needed (+ 1/8), so that the call has a single synchronisation in the steady state
     DevBuf<uint32_t> hdr;
@@ -475,6 +478,8 @@ struct u3d_batch
                 cudaEventDestroy(e);
         if (haveViewsEvent)
             cudaEventDestroy(viewsCopied);
+        if (haveDoneEvent)
+            cudaEventDestroy(done);
     }
 };
 
@@ -515,6 +520,11 @@ int u3d_debug_set_option(const char* name, int value)
     if (name && std::strcmp(name, "two_phase_min") == 0)
     {
         g_twoPhaseMin = value;
+        return U3D_OK;
+    }
+    if (name && std::strcmp(name, "blocking_wait") == 0)
+    {
+        g_blockingWait = value;
         return U3D_OK;
     }
     if (name && std::strcmp(name, "tile_target") == 0)
@@ -3223,7 +3233,20 @@ int u3d_batch_cull_views(u3d_batch* b, const u3d_view* views, uint32_t n, int st
     const uint64_t first = wantIds ? std::min<uint64_t>(std::min<uint64_t>(capacity, packedCap), b->idsGuess) : 0;
     if (first)
         CU_CHECK(cudaMemcpyAsync(ids, b->packed.p, first * 4, cudaMemcpyDeviceToHost, st));
-    CU_CHECK(cudaStreamSynchronize(st));
+    if (g_blockingWait)
+    {
+        // more calling threads than host cores (8 ranks x 12 slots on a 16-core box): a spinning wait takes the cores the other threads
+        // need to launch their batches; a blocking event gives them back
+        if (!b->haveDoneEvent)
+        {
+            CU_CHECK(cudaEventCreateWithFlags(&b->done, cudaEventBlockingSync | cudaEventDisableTiming));
+            b->haveDoneEvent = true;
+        }
+        CU_CHECK(cudaEventRecord(b->done, st));
+        CU_CHECK(cudaEventSynchronize(b->done));
+    }
+    else
+        CU_CHECK(cudaStreamSynchronize(st));
     rc = flags_to_error(b->hostHdr.p[0]);
     if (rc < 0)
         return rc;
