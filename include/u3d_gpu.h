@@ -92,7 +92,11 @@ typedef struct u3d_view
 
 U3D_API const char* u3d_last_error(void);
 U3D_API int u3d_abi_version(void);
-/* Test hook.  "force_irregular" = 1 routes every set-up triangle of the batched path through the general (global-memory) fill. */
+/* Test hook / tuning.  "force_irregular" = 1 routes every set-up triangle of the batched path through the general (global-memory) fill.
+   "blocking_wait" = 1 makes u3d_batch_cull_views wait on a blocking event instead of spinning in cudaStreamSynchronize: for hosts that run
+   more calling threads than cores (8 ranks x 12 batch slots on a 32-core box: 3.5 -> 5.1 M views/s end to end).  "tile_target" = tiles a
+   full batch should launch at least (default 3 per SM); buffers / batches created afterwards pick their tile height (64 / 32 / 16 rows)
+   from it.  The other names are A/B switches of the kernels (csrc/capi.cu), each documented where it is read. */
 U3D_API int u3d_debug_set_option(const char* name, int value);
 /* Diagnostic: after u3d_debug_set_option("cull_prof", 1), clock64 sums of the cull kernel's phases over all CTAs (8 slots). */
 U3D_API int u3d_debug_read_cull_prof(unsigned long long* out8);
