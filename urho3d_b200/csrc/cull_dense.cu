@@ -974,14 +974,14 @@ __device__ __forceinline__ uint2 ld_volatile_u2(const uint2* p)
 
 /// Warp-wide: lanes with `alive` record their octant's state and publish its children behind the queue's tail.
 __device__ __forceinline__ void tree_finalize(const SceneDev& sc, const DenseDev& dd, unsigned char* __restrict__ stateAll, uint32_t epochTag, bool alive,
-    int v, int o, bool inside)
+    int v, int o, bool inside, const int2* early = nullptr /* the octant's child range when the caller has loaded it already */)
 {
     const int lane = threadIdx.x & 31;
     int2 ch = make_int2(0, 0);
     if (alive)
     {
         dense_mark_alive(sc, dd, v, o, inside ? 2 : 1, stateAll);
-        ch = sc.octChild[o];
+        ch = early ? *early : sc.octChild[o];
     }
     int off = ch.y;
 #pragma unroll
@@ -1116,6 +1116,7 @@ __global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_tree(S
         int v = 0, o = 0, res = OUTSIDE;
         bool occluded = false;
         float4 mn = make_float4(0.f, 0.f, 0.f, 0.f), mx = mn;
+        int2 ch = make_int2(0, 0);
         if (ready)
         {
             v = (int)(e.x & 0xFFFFu);
@@ -1123,6 +1124,7 @@ __global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_tree(S
             const ViewConst& vc = views[v];
             mn = sc.octMin[o];
             mx = sc.octMax[o];
+            ch = sc.octChild[o]; // needed only if the octant survives, but asked for now: its round trip overlaps the tests
             if (e.y >> 31)
                 res = INSIDE; // FrustumOctreeQuery::TestOctant, OctreeQuery.cpp:98-104
             else
@@ -1151,7 +1153,7 @@ __global__ void __launch_bounds__(kDenseThreads, kDenseMinBlocks) k_dense_tree(S
                     res = OUTSIDE;
             }
         }
-        tree_finalize(sc, dd, stateAll, epochTag, ready && res != OUTSIDE && !undecided, v, o, res == INSIDE);
+        tree_finalize(sc, dd, stateAll, epochTag, ready && res != OUTSIDE && !undecided, v, o, res == INSIDE, &ch);
         finished += (uint32_t)__popc(__ballot_sync(0xffffffffu, ready && !undecided));
         if (buffered >= 32)
             drain();
