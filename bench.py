@@ -624,6 +624,7 @@ def main():
     fork(ev_start)
     for k in range(args.steps):
         launches += step_device(k)
+    t_enqueued = time.perf_counter()  # host time to enqueue the K steps: the step is launch-bound when this approaches the device time
     join()
     ev_end.record(tstream)
     torch.cuda.synchronize()
@@ -793,7 +794,7 @@ def main():
                 "occluder_mtri_per_s_raster_phases": float(stats[:, 0].sum()) / max(1e-9, 1e-3 * raster_ms) / 1e6,
                 "per_view": {"submitted_tris": tri_per_view, "query_result": n_cand / args.views, "visible": vis_per_view, "octants": M},
                 "e2e": {"value": args.views * e2e_steps / e2e_s, "unit": "views/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps, "host_wait": e2e_wait},
-                "gpu_launches": launches,
+                "gpu_launches": launches, "host_enqueue_ms_per_step": round((t_enqueued - t_begin) * 1e3 / args.steps, 4),
                 "roofline": {"bound": "hbm", "kernel": "cull = k_dense_tree + k_dense_frustum + k_dense_occlusion_walk + k_dense_emit (phases tree, frustum, "
                                                        "occlusion, emit)",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
