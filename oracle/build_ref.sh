@@ -27,6 +27,14 @@ awk '/^\/\/\/ %Frustum octree query for shadowcasters\./{on=1} /^void CheckVisib
 for c in "class ShadowCasterOctreeQuery" "class ZoneOccluderOctreeQuery" "class OccludedFrustumOctreeQuery"; do
   grep -q "$c" "$OUT/view_queries.inc" || { echo "could not extract '$c' from $VIEWCPP"; exit 1; }
 done
+# Two member functions of View that depend only on classes compiled here are also taken from the reference's own text and compiled as
+# members of a stand-in class (ref_harness.cpp: RefViewShim, `#define View RefViewShim` around the include): View::UpdateOccluders
+# (View.cpp:2171-2229; touches renderer_->GetOccluderSizeThreshold() and frame_) and View::IsShadowCasterVisible (View.cpp:2455-2489;
+# touches frame_).
+awk '/^void View::UpdateOccluders\(/{on=1} /^void View::DrawOccluders\(/{on=0} on' "$VIEWCPP" > "$OUT/view_update_occluders.inc"
+awk '/^bool View::IsShadowCasterVisible\(/{on=1} /^IntRect View::GetShadowMapViewport\(/{on=0} on' "$VIEWCPP" > "$OUT/view_shadow_caster_visible.inc"
+grep -q "Sort(occluders.Begin(), occluders.End(), CompareDrawables)" "$OUT/view_update_occluders.inc" || { echo "could not extract View::UpdateOccluders from $VIEWCPP"; exit 1; }
+grep -q "lightViewFrustum.IsInsideFast(lightViewBox)" "$OUT/view_shadow_caster_visible.inc" || { echo "could not extract View::IsShadowCasterVisible from $VIEWCPP"; exit 1; }
 FILES=""
 for d in Container Math Core IO Resource Scene; do FILES="$FILES $(ls $SRC/$d/*.cpp)"; done
 for f in OcclusionBuffer Octree OctreeQuery Camera Drawable GraphicsDefs; do FILES="$FILES $SRC/Graphics/$f.cpp"; done

@@ -9,6 +9,8 @@
 //   * the reference OcclusionBuffer (OcclusionBuffer.h:101-158),
 //   * the reference's OWN text of ShadowCasterOctreeQuery / ZoneOccluderOctreeQuery / OccludedFrustumOctreeQuery (file-local classes of
 //     View.cpp:58-157), extracted by the build recipe into a generated include and compiled here,
+//   * the reference's OWN text of View::UpdateOccluders (View.cpp:2171-2229) and View::IsShadowCasterVisible (View.cpp:2455-2489), extracted
+//     the same way and compiled as members of a stand-in class that holds the two View members they touch (renderer_, frame_),
 //   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
 //     View.cpp:897-920 does when worker threads exist.
 //
@@ -44,6 +46,34 @@ namespace Urho3D
 #include "view_queries.inc"
 }
 
+// The reference's own text of View::UpdateOccluders (View.cpp:2171-2229) and View::IsShadowCasterVisible (View.cpp:2455-2489), extracted the
+// same way and compiled as members of a stand-in for View that holds the two members they touch: renderer_ (asked for
+// GetOccluderSizeThreshold()) and frame_.  Everything else they use -- Drawable, Camera, BoundingBox, Frustum, Ray, Sort, CompareDrawables -- is
+// the reference's real code.
+namespace Urho3D
+{
+struct RefRendererShim
+{
+    float occluderSizeThreshold_{};
+    float GetOccluderSizeThreshold() const { return occluderSizeThreshold_; }
+};
+
+class RefViewShim
+{
+public:
+    void UpdateOccluders(PODVector<Drawable*>& occluders, Camera* camera);
+    bool IsShadowCasterVisible(Drawable* drawable, BoundingBox lightViewBox, Camera* shadowCamera, const Matrix3x4& lightView,
+        const Frustum& lightViewFrustum, const BoundingBox& lightViewFrustumBox);
+    RefRendererShim* renderer_{};
+    FrameInfo frame_{};
+};
+
+#define View RefViewShim
+#include "view_update_occluders.inc"
+#include "view_shadow_caster_visible.inc"
+#undef View
+}
+
 using namespace Urho3D;
 
 namespace
@@ -73,9 +103,11 @@ public:
     }
 
     void OnWorldBoundingBoxUpdate() override { worldBoundingBox_ = fixedWorldBox_; }
+    unsigned GetNumOccluderTriangles() override { return numOccluderTriangles_; }
 
     BoundingBox fixedWorldBox_;
     int id_{};
+    unsigned numOccluderTriangles_{};
 };
 
 struct Ref
@@ -715,6 +747,50 @@ int ref_select_occluders(void* h, int numOccluders, const float* occAabb6, const
     return n;
 }
 
+/// View::UpdateOccluders as the reference wrote it: the extracted text of View.cpp:2171-2229 (RefViewShim above) over real Drawables, one per
+/// table entry whose box passes the query frustum's IsInsideFast, with the harness's real Camera (ref_camera_set) as the cull camera.
+/// Drawable::UpdateBatches (Drawable.cpp:118-132) computes distance_ with Camera::GetDistance, CompareDrawables + Sort order the list.
+/// Pins ref_select_occluders (the restatement with injected camera quantities) to the reference's own lines.
+int ref_select_occluders_text(void* h, int numOccluders, const float* occAabb6, const unsigned* numTriangles, const float* drawDistance,
+    float occluderSizeThreshold, int* outIdx, float* outKeys, int cap)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    const Frustum& fr = r->QueryFrustum();
+    static unsigned frameNumber = 1000;
+    RefRendererShim renderer;
+    renderer.occluderSizeThreshold_ = occluderSizeThreshold;
+    RefViewShim view;
+    view.renderer_ = &renderer;
+    view.frame_.frameNumber_ = ++frameNumber;
+    view.frame_.timeStep_ = 0.0f;
+    view.frame_.viewSize_ = IntVector2(1024, 768);
+    view.frame_.camera_ = r->camera_;
+    std::vector<SharedPtr<Node> > nodes;
+    PODVector<Drawable*> occluders;
+    for (int i = 0; i < numOccluders; ++i)
+    {
+        const float* b = occAabb6 + 6 * (size_t)i;
+        BoundingBox box(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]));
+        if (fr.IsInsideFast(box) == OUTSIDE)
+            continue;
+        SharedPtr<Node> node(new Node(r->context_));
+        auto* d = node->CreateComponent<TestDrawable>();
+        d->Setup(box, DRAWABLE_GEOMETRY, DEFAULT_VIEWMASK, true, false, i);
+        d->numOccluderTriangles_ = numTriangles[i];
+        d->SetDrawDistance(drawDistance ? drawDistance[i] : 0.0f);
+        nodes.push_back(node);
+        occluders.Push(d);
+    }
+    view.UpdateOccluders(occluders, r->camera_);
+    int n = (int)occluders.Size();
+    for (int i = 0; i < n && i < cap; ++i)
+    {
+        outIdx[i] = static_cast<TestDrawable*>(occluders[i])->id_;
+        outKeys[i] = occluders[i]->GetSortValue();
+    }
+    return n;
+}
+
 /// View::DrawOccluders, threaded branch (View.cpp:2233-2234, 2258-2273), over an already sorted occluder list, then the query and the
 /// visibility predicate as ref_run_view.  outCounts4 = submitted triangles, query result size, visible, activeOccluders_.
 int ref_run_view_selected(void* h, int numSelected, const int* selected, const float* occModel12, const void* vtx, unsigned vtxSize, const void* idx,
@@ -813,8 +889,9 @@ int ref_shadow_split_setup(void* h, const float* mainCam12, const float* shadowC
     return lightViewFrustum.vertices_[0] == lightViewFrustum.vertices_[4] ? 1 : 0;
 }
 
-/// The per-drawable part of View::ProcessShadowCasters + View::IsShadowCasterVisible (View.cpp:2409-2489) restated on the reference's math types
-/// (BoundingBox::Transformed, Frustum::IsInsideFast, Ray, Vector3), over `numIn` drawable ids in order.  Per-drawable state the engine keeps on
+/// The per-drawable part of View::ProcessShadowCasters (View.cpp:2409-2452) restated on the reference's math types (BoundingBox::Transformed,
+/// Frustum::IsInsideFast), with View::IsShadowCasterVisible (View.cpp:2455-2489) called as the reference wrote it (extracted text, RefViewShim),
+/// over `numIn` drawable ids in order.  Per-drawable state the engine keeps on
 /// the Drawable is injected: shadow mask (View::GetShadowMask), shadow / draw distance, in-view flag (Drawable::IsInView(frame_)); distance_ is
 /// Camera::GetDistance of the cull camera (mainView12 / mainPos3 / mainOrtho, as ref_check_in_view).  Returns the shadow casters kept, in order.
 int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float* lightView12, const float* shadowPlanes24,
@@ -833,6 +910,17 @@ int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float
         lightViewFrustum.planes_[i].Define(Vector4(lightViewFrustumPlanes24[4 * i], lightViewFrustumPlanes24[4 * i + 1], lightViewFrustumPlanes24[4 * i + 2],
             lightViewFrustumPlanes24[4 * i + 3]));
     }
+    // what IsShadowCasterVisible asks its arguments and frame_ for: the shadow camera's projection type and far clip, the light-view frustum
+    // box's far side, and whether the drawable was marked in view this frame for the cull camera
+    static unsigned frameNumber = 5000;
+    SharedPtr<Node> shadowNode(new Node(r->context_));
+    Camera* shadowCamera = shadowNode->CreateComponent<Camera>();
+    shadowCamera->SetOrthographic(shadowOrtho != 0);
+    shadowCamera->SetFarClip(shadowFarClip);
+    BoundingBox lightViewFrustumBox(Vector3(0.0f, 0.0f, 0.0f), Vector3(0.0f, 0.0f, lightViewFrustumMaxZ));
+    RefViewShim view;
+    view.frame_.frameNumber_ = ++frameNumber;
+    view.frame_.camera_ = r->camera_;
     int n = 0;
     for (int k = 0; k < numIn; ++k)
     {
@@ -853,28 +941,10 @@ int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float
         if (maxShadowDistance > 0.0f && distance > maxShadowDistance)
             continue;
         BoundingBox lightViewBox = drawable->GetWorldBoundingBox().Transformed(lightView);
-        bool visible;
-        if (shadowOrtho)
-        {
-            lightViewBox.max_.z_ = Max(lightViewBox.max_.z_, lightViewFrustumMaxZ);
-            visible = lightViewFrustum.IsInsideFast(lightViewBox) != OUTSIDE;
-        }
-        else if (inView[id])
-            visible = true;
-        else
-        {
-            Vector3 center = lightViewBox.Center();
-            Ray extrusionRay(center, center);
-            float extrusionDistance = shadowFarClip;
-            float originalDistance = Clamp(center.Length(), M_EPSILON, extrusionDistance);
-            float sizeFactor = extrusionDistance / originalDistance;
-            Vector3 newCenter = extrusionDistance * extrusionRay.direction_;
-            Vector3 newHalfSize = lightViewBox.Size() * sizeFactor * 0.5f;
-            BoundingBox extrudedBox(newCenter - newHalfSize, newCenter + newHalfSize);
-            lightViewBox.Merge(extrudedBox);
-            visible = lightViewFrustum.IsInsideFast(lightViewBox) != OUTSIDE;
-        }
-        if (visible)
+        // View::IsShadowCasterVisible: the reference's own text (View.cpp:2455-2489, RefViewShim above)
+        if (inView[id])
+            drawable->MarkInView(view.frame_);
+        if (view.IsShadowCasterVisible(drawable, lightViewBox, shadowCamera, lightView, lightViewFrustum, lightViewFrustumBox))
             outIds[n++] = id;
     }
     return n;

@@ -68,6 +68,7 @@ class Ref:
         L.ref_move_drawables.argtypes = [C.c_void_p, C.c_int, _i, _f]
         L.ref_remove_drawable.argtypes = [C.c_void_p, C.c_int]
         L.ref_select_occluders.argtypes = [C.c_void_p, C.c_int, _f, _u32, _f, _f, _f, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, _i, _f, C.c_int]
+        L.ref_select_occluders_text.argtypes = [C.c_void_p, C.c_int, _f, _u32, _f, C.c_float, _i, _f, C.c_int]
         L.ref_run_view_selected.argtypes = [C.c_void_p, C.c_int, _i, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
                                             C.c_uint, C.c_uint, _i, C.c_int, _i]
         L.ref_query_zone_occluder.argtypes = [C.c_void_p, _u8, C.c_uint, _i, C.c_int]
@@ -249,6 +250,18 @@ class Ref:
         keys = np.zeros(max(k, 1), np.float32)
         n = self.lib.ref_select_occluders(self.h, k, _p(aabb, _f), _p(tris, _u32), _p(dd, _f), _p(v12, _f), _p(cp, _f), int(view.ortho),
                                           view.half_view_size, view.ortho_size, view.far, size_threshold, _p(out, _i), _p(keys, _f), out.shape[0])
+        return out[:n].copy(), keys[:n].copy()
+
+    def select_occluders_text(self, scene, size_threshold, draw_dist=None, num_triangles=None):
+        """View::UpdateOccluders compiled from the reference's own text (View.cpp:2171-2229) over real Drawables, with the camera last given to
+        camera_set() as the cull camera and the frustum last set as the occluder query.  Returns (occluder indices, sort values), sorted."""
+        k = scene.k
+        tris = np.full(k, scene.mesh_idx.shape[0] // 3, np.uint32) if num_triangles is None else np.ascontiguousarray(num_triangles, np.uint32)
+        dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, np.float32)
+        aabb = np.ascontiguousarray(scene.occ_aabb, np.float32)
+        out = np.zeros(max(k, 1), np.int32)
+        keys = np.zeros(max(k, 1), np.float32)
+        n = self.lib.ref_select_occluders_text(self.h, k, _p(aabb, _f), _p(tris, _u32), _p(dd, _f), size_threshold, _p(out, _i), _p(keys, _f), out.shape[0])
         return out[:n].copy(), keys[:n].copy()
 
     def run_view_selected(self, scene, selected, max_triangles, flags=0xFF, view_mask=0xFFFFFFFF):

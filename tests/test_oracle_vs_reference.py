@@ -253,8 +253,9 @@ def test_raycast_matches_reference():
 @pytest.mark.parametrize("ortho", [False, True])
 def test_occluder_selection_matches_reference(ortho):
     """View::UpdateOccluders (draw distance, size threshold, density key, Sort) and the triangle budget of DrawOccluders' threaded branch:
-    oracle list == the harness's restatement on the reference's math types and Sort, ties included (duplicated occluders), and the view drawn
-    from that list gives the same buffer, query result and visible set."""
+    oracle list == the harness's restatement on the reference's math types and Sort == View::UpdateOccluders compiled from the reference's own
+    text over real Drawables and the real Camera (ref_select_occluders_text), ties included (duplicated occluders), and the view drawn from
+    that list gives the same buffer, query result and visible set."""
     from urho3d_b200 import camera
     w, h = 128, 128
     sc = helpers.small_scene(n=3000, k=300, extent=90.0, seed=41)
@@ -272,11 +273,16 @@ def test_occluder_selection_matches_reference(ortho):
         if i % 6 == 0:  # camera inside an occluder's box
             b = sc.occ_aabb[rs.randint(sc.k)]
             pos = list((b[:3] + b[3:]) * 0.5)
-        v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(-30, 10), 45.0, 1.0, 0.1, rs.choice([150.0, 400.0]), ortho=ortho,
-                             ortho_size=rs.choice([20.0, 60.0]))
+        yaw, pitch, far, osize = rs.uniform(0, 360), rs.uniform(-30, 10), rs.choice([150.0, 400.0]), rs.choice([20.0, 60.0])
+        v = camera.make_view(pos, yaw, pitch, 45.0, 1.0, 0.1, far, ortho=ortho, ortho_size=osize)
         ref.set_view_raw(v)
+        ref.camera_set(pos, camera.quat_from_euler(pitch, yaw, 0.0), 45.0, 1.0, 0.1, far, ortho=ortho, ortho_size=osize)
         for thr, budget in ((0.025, 5000), (0.1, 30 * tri), (0.0, 7 * tri + 5), (0.025, 1 << 30)):
             ridx, rkeys = ref.select_occluders(sc, v, thr, draw_dist)
+            # the reference's own lines (View.cpp:2171-2229 compiled from its text, real Drawables / Camera) against the restatement ...
+            tidx, tkeys = ref.select_occluders_text(sc, thr, draw_dist)
+            assert np.array_equal(tidx, ridx) and np.array_equal(tkeys.view(np.uint32), rkeys.view(np.uint32)), (i, thr)
+            # ... and the oracle against both
             oidx, okeys, nsub = oraclebind.select_occluders(sc, v, thr, budget, draw_dist)
             assert np.array_equal(ridx, oidx) and np.array_equal(rkeys.view(np.uint32), okeys.view(np.uint32)), (i, thr)
             vis, counts = ref.run_view_selected(sc, ridx, budget)
