@@ -10,7 +10,8 @@
 //   * the reference's OWN text of ShadowCasterOctreeQuery / ZoneOccluderOctreeQuery / OccludedFrustumOctreeQuery (file-local classes of
 //     View.cpp:58-157), extracted by the build recipe into a generated include and compiled here,
 //   * the reference's OWN text of View::UpdateOccluders (View.cpp:2171-2229) and View::IsShadowCasterVisible (View.cpp:2455-2489), extracted
-//     the same way and compiled as members of a stand-in class that holds the two View members they touch (renderer_, frame_),
+//     the same way and compiled as members of a stand-in class that holds the two View members they touch (renderer_, frame_), and of the
+//     free function CheckVisibilityWork (View.cpp:160-227) with that stand-in as the View it works for,
 //   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
 //     View.cpp:897-920 does when worker threads exist.
 //
@@ -38,6 +39,9 @@
 #include <Urho3D/Math/Sphere.h>
 #include <Urho3D/Math/Ray.h>
 #include <Urho3D/Container/Sort.h>
+#include <Urho3D/Graphics/Light.h>
+#include <Urho3D/Graphics/Zone.h>
+#include <cstdlib>
 
 // The reference's own text of View.cpp:58-157 (ShadowCasterOctreeQuery, ZoneOccluderOctreeQuery, OccludedFrustumOctreeQuery), extracted at
 // build time by oracle/build_ref.sh into oracle/_ref/view_queries.inc: the classes are file-local in View.cpp, which cannot be compiled here.
@@ -58,19 +62,36 @@ struct RefRendererShim
     float GetOccluderSizeThreshold() const { return occluderSizeThreshold_; }
 };
 
+/// Data holder with the fields of View.h's PerThreadSceneResult that CheckVisibilityWork fills (View.h:97-109).
+struct PerThreadSceneResult
+{
+    PODVector<Drawable*> geometries_;
+    PODVector<Light*> lights_;
+    float minZ_;
+    float maxZ_;
+};
+
 class RefViewShim
 {
 public:
     void UpdateOccluders(PODVector<Drawable*>& occluders, Camera* camera);
     bool IsShadowCasterVisible(Drawable* drawable, BoundingBox lightViewBox, Camera* shadowCamera, const Matrix3x4& lightView,
         const Frustum& lightViewFrustum, const BoundingBox& lightViewFrustumBox);
+    /// Never reached: the harness runs CheckVisibilityWork with cameraZoneOverride_ set (zones are outside this path).
+    void FindZone(Drawable*) { abort(); }
     RefRendererShim* renderer_{};
     FrameInfo frame_{};
+    // what CheckVisibilityWork reads through its View pointer
+    OcclusionBuffer* occlusionBuffer_{};
+    Camera* cullCamera_{};
+    bool cameraZoneOverride_{};
+    Vector<PerThreadSceneResult> sceneResults_;
 };
 
 #define View RefViewShim
 #include "view_update_occluders.inc"
 #include "view_shadow_caster_visible.inc"
+#include "view_check_visibility_work.inc"
 #undef View
 }
 
@@ -577,6 +598,55 @@ int ref_check_in_view(void* h, int useBuffer, const float* view12, const float* 
             ++m;
         }
     }
+    if (minZ == M_INFINITY)
+        minZ = 0.0f;
+    minmax2[0] = minZ;
+    minmax2[1] = maxZ;
+    return m;
+}
+
+/// CheckVisibilityWork as the reference wrote it (the extracted text of View.cpp:160-227, one work item on thread 0) over the last ref_query()
+/// result, with the harness's real Camera (ref_camera_set) as the cull camera: Drawable::UpdateBatches computes distance_, MarkInView marks,
+/// the Z range accumulates in a PerThreadSceneResult initialised and merged as View::GetDrawables does (View.cpp:890-893, 926-951).
+/// Draw distances are set on the Drawables (by id).  Returns the drawables marked in view, in result order.  Pins ref_check_in_view.
+int ref_check_in_view_text(void* h, int useBuffer, const float* drawDistance /* by id */, int* outIdx, int cap, float* minmax2)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    static unsigned frameNumber = 9000;
+    RefViewShim view;
+    view.occlusionBuffer_ = useBuffer ? r->buffer_.Get() : nullptr;
+    view.cullCamera_ = r->camera_;
+    view.cameraZoneOverride_ = true;
+    view.frame_.frameNumber_ = ++frameNumber;
+    view.frame_.camera_ = r->camera_;
+    view.sceneResults_.Resize(1);
+    PerThreadSceneResult& result = view.sceneResults_[0];
+    result.geometries_.Clear();
+    result.lights_.Clear();
+    result.minZ_ = M_INFINITY;
+    result.maxZ_ = 0.0f;
+    for (unsigned i = 0; i < r->result_.Size(); ++i)
+    {
+        auto* d = static_cast<TestDrawable*>(r->result_[i]);
+        d->SetDrawDistance(drawDistance ? drawDistance[d->id_] : 0.0f);
+    }
+    if (r->result_.Size())
+    {
+        WorkItem item;
+        item.aux_ = &view;
+        item.start_ = &r->result_[0];
+        item.end_ = &r->result_[0] + r->result_.Size();
+        CheckVisibilityWork(&item, 0);
+    }
+    int m = 0;
+    for (unsigned i = 0; i < r->result_.Size(); ++i)
+        if (r->result_[i]->IsInView(view.frame_))
+        {
+            if (m < cap)
+                outIdx[m] = static_cast<TestDrawable*>(r->result_[i])->id_;
+            ++m;
+        }
+    float minZ = result.minZ_, maxZ = result.maxZ_;
     if (minZ == M_INFINITY)
         minZ = 0.0f;
     minmax2[0] = minZ;

@@ -41,6 +41,7 @@ void DebugRenderer::AddNode(Node*, float, bool) { U3D_STUB_DIE(); }
 bool DebugRenderer::IsInside(const BoundingBox&) const { U3D_STUB_DIE(); }
 void Geometry::GetRawData(const unsigned char*&, unsigned&, const unsigned char*&, unsigned&, const PODVector<VertexElement>*&) const { U3D_STUB_DIE(); }
 void Light::SetIntensitySortValue(const BoundingBox&) { U3D_STUB_DIE(); }
+Color Light::GetEffectiveColor() const { U3D_STUB_DIE(); } // CheckVisibilityWork's light branch: the harness has no Light drawables
 unsigned VertexBuffer::GetElementOffset(const PODVector<VertexElement>&, VertexElementType, VertexElementSemantic, unsigned char) { U3D_STUB_DIE(); }
 bool VertexBuffer::HasElement(const PODVector<VertexElement>&, VertexElementType, VertexElementSemantic, unsigned char) { U3D_STUB_DIE(); }
 }

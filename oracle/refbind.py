@@ -80,6 +80,7 @@ class Ref:
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
         L.ref_sort_by_key.argtypes = [C.c_int, _f, _i]
         L.ref_check_in_view.argtypes = [C.c_void_p, C.c_int, _f, _f, C.c_int, _f, _i, C.c_int, _f]
+        L.ref_check_in_view_text.argtypes = [C.c_void_p, C.c_int, _f, _i, C.c_int, _f]
         self.h = L.ref_create(int(worker_threads))
         self._keep = []
         self.n = 0
@@ -373,6 +374,15 @@ class Ref:
         cp = np.ascontiguousarray(cam_pos, dtype=np.float32)
         dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, dtype=np.float32)
         n = self.lib.ref_check_in_view(self.h, int(use_buffer), _p(v12, _f), _p(cp, _f), int(ortho), _p(dd, _f), _p(out, _i), out.shape[0], _p(mm, _f))
+        return out[:n].copy(), mm
+
+    def check_in_view_text(self, draw_dist=None, use_buffer=True):
+        """CheckVisibilityWork compiled from the reference's own text (View.cpp:160-227) over the last query() result, the camera last given
+        to camera_set() being the cull camera.  Returns (ids in view, (minZ, maxZ))."""
+        out = np.zeros(max(self.n, 1), np.int32)
+        mm = np.zeros(2, np.float32)
+        dd = None if draw_dist is None else np.ascontiguousarray(draw_dist, dtype=np.float32)
+        n = self.lib.ref_check_in_view_text(self.h, int(use_buffer), _p(dd, _f), _p(out, _i), out.shape[0], _p(mm, _f))
         return out[:n].copy(), mm
 
     def num_threads(self):

@@ -151,24 +151,34 @@ def test_reset_drops_queued_batches_and_the_triangle_count():
 
 @pytest.mark.parametrize("ortho", [False, True])
 def test_in_view_stage_matches_reference(ortho):
-    """Rest of CheckVisibilityWork (View.cpp:177-211): draw distance + view-space Z range, oracle vs the reference's own math types."""
+    """Rest of CheckVisibilityWork (View.cpp:177-211): draw distance + view-space Z range.  Oracle == the harness's restatement on the
+    reference's math types == CheckVisibilityWork compiled from the reference's own text (View.cpp:160-227) over real Drawables with the real
+    Camera as the cull camera (Drawable::UpdateBatches, MarkInView, PerThreadSceneResult merge)."""
     from urho3d_b200 import camera
     w, h = 128, 80
     sc = helpers.small_scene(n=4000, k=96, extent=80.0, seed=17)
     rs = np.random.RandomState(5)
     draw_dist = np.where(rs.uniform(size=sc.n) < 0.5, rs.uniform(5.0, 120.0, size=sc.n), 0.0).astype(np.float32)
-    sc.flags[::9] = 0x2  # lights: in view, but not part of the Z range
+    sc.flags[::9] = 0x4  # zones: in view, but not part of the Z range (the harness has no Light class behind a DRAWABLE_LIGHT flag)
     ref = helpers.make_ref(sc, w, h)
     tree, ob = helpers.make_oracle(sc, ref.flatten(), w, h)
     for i in range(8):
         pos = [rs.uniform(-60, 60), rs.uniform(1, 30) if ortho else 2.0, rs.uniform(-60, 60)]
-        v = camera.make_view(pos, rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), 45.0, w / h, 0.1, 300.0,
-                             ortho=ortho, ortho_size=rs.uniform(20, 100))
+        yaw, pitch, osize = rs.uniform(0, 360), rs.uniform(20, 70) if ortho else rs.uniform(-10, 10), rs.uniform(20, 100)
+        v = camera.make_view(pos, yaw, pitch, 45.0, w / h, 0.1, 300.0, ortho=ortho, ortho_size=osize)
         helpers.ref_draw_view(ref, sc, v)
         ob.draw_scene_view(sc, v)
         cand = tree.query(1, v.planes, ob, as_ids=False)
         assert np.array_equal(tree.order[cand], ref.query(1))
         want_ids, want_mm = ref.check_in_view(v.view, v.position, ortho, draw_dist)
+        # the reference's own lines, with the reference's Camera built from the same parameters
+        ref.camera_set(pos, camera.quat_from_euler(pitch, yaw, 0.0), 45.0, w / h, 0.1, 300.0, ortho=ortho, ortho_size=osize)
+        text_ids, text_mm = ref.check_in_view_text(draw_dist)
+        rview = ref.camera_get()[0]  # Camera::GetView(): the matrix the text version works with (urho3d_b200.camera's differs in the last bits)
+        rest_ids, rest_mm = ref.check_in_view(rview, pos, ortho, draw_dist)
+        assert np.array_equal(text_ids, rest_ids) and np.array_equal(text_mm.view(np.uint32), rest_mm.view(np.uint32)), (i, text_mm, rest_mm)
+        orc_pos, orc_mm = tree.check_in_view(ob, cand, rview, np.asarray(pos, np.float32), ortho, draw_dist)
+        assert np.array_equal(tree.order[orc_pos], text_ids) and np.array_equal(orc_mm.view(np.uint32), text_mm.view(np.uint32))
         got_pos, got_mm = tree.check_in_view(ob, cand, v.view, v.position, ortho, draw_dist)
         assert np.array_equal(tree.order[got_pos], want_ids)
         assert np.array_equal(got_mm, want_mm), (got_mm, want_mm)
