@@ -11,7 +11,8 @@
 //     View.cpp:58-157), extracted by the build recipe into a generated include and compiled here,
 //   * the reference's OWN text of View::UpdateOccluders (View.cpp:2171-2229) and View::IsShadowCasterVisible (View.cpp:2455-2489), extracted
 //     the same way and compiled as members of a stand-in class that holds the two View members they touch (renderer_, frame_), and of the
-//     free function CheckVisibilityWork (View.cpp:160-227) with that stand-in as the View it works for,
+//     free function CheckVisibilityWork (View.cpp:160-227) with that stand-in as the View it works for, and View::ProcessShadowCasters
+//     (View.cpp:2379-2453) with stand-ins for the Light and the LightQueryResult it reads,
 //   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
 //     View.cpp:897-920 does when worker threads exist.
 //
@@ -71,9 +72,38 @@ struct PerThreadSceneResult
     float maxZ_;
 };
 
+/// What View::ProcessShadowCasters asks a Light for (Light.h: GetLightMask is Drawable's, GetLightType, GetShadowFocus().focus_).
+struct RefFocusShim { bool focus_{}; };
+struct RefLightShim
+{
+    unsigned lightMask_{};
+    LightType lightType_{};
+    RefFocusShim shadowFocus_;
+    unsigned GetLightMask() const { return lightMask_; }
+    LightType GetLightType() const { return lightType_; }
+    const RefFocusShim& GetShadowFocus() const { return shadowFocus_; }
+};
+
+/// Data holder with the members of View.h's LightQueryResult that ProcessShadowCasters touches (View.h:55-77).
+struct RefLightQueryShim
+{
+    RefLightShim* light_{};
+    PODVector<Drawable*> shadowCasters_;
+    Camera* shadowCameras_[MAX_LIGHT_SPLITS];
+    unsigned shadowCasterEnd_[MAX_LIGHT_SPLITS];
+    BoundingBox shadowCasterBox_[MAX_LIGHT_SPLITS];
+    float shadowNearSplits_[MAX_LIGHT_SPLITS];
+    float shadowFarSplits_[MAX_LIGHT_SPLITS];
+};
+
 class RefViewShim
 {
 public:
+    void ProcessShadowCasters(RefLightQueryShim& query, const PODVector<Drawable*>& drawables, unsigned splitIndex);
+    /// View::GetShadowMask (View.h:297-300) without a zone: zones are outside this path, their mask is all ones.
+    unsigned GetShadowMask(Drawable* drawable) { return drawable->GetShadowMask(); }
+    float minZ_{};
+    float maxZ_{};
     void UpdateOccluders(PODVector<Drawable*>& occluders, Camera* camera);
     bool IsShadowCasterVisible(Drawable* drawable, BoundingBox lightViewBox, Camera* shadowCamera, const Matrix3x4& lightView,
         const Frustum& lightViewFrustum, const BoundingBox& lightViewFrustumBox);
@@ -92,6 +122,11 @@ public:
 #include "view_update_occluders.inc"
 #include "view_shadow_caster_visible.inc"
 #include "view_check_visibility_work.inc"
+#define Light RefLightShim
+#define LightQueryResult RefLightQueryShim
+#include "view_process_shadow_casters.inc"
+#undef LightQueryResult
+#undef Light
 #undef View
 }
 
@@ -1017,6 +1052,74 @@ int ref_process_shadow_casters(void* h, int numIn, const int* inIds, const float
         if (view.IsShadowCasterVisible(drawable, lightViewBox, shadowCamera, lightView, lightViewFrustum, lightViewFrustumBox))
             outIds[n++] = id;
     }
+    return n;
+}
+
+/// View::ProcessShadowCasters as the reference wrote it (the extracted text of View.cpp:2379-2453, which calls the extracted
+/// IsShadowCasterVisible) for one split: real cull and shadow Cameras built from the 12-float descriptions of ref_shadow_split_setup, the split
+/// frustum computed inside the text (minZ_ / maxZ_ = nearZ / farZ, the directional splits wide open, so both light kinds use [nearZ, farZ]), real
+/// Drawables carrying their shadow mask / shadow distance / draw distance; drawables flagged in view have had UpdateBatches + MarkInView for this
+/// frame, as CheckVisibilityWork leaves them.  Returns the shadow casters kept, in order.  Pins ref_shadow_split_setup + ref_process_shadow_casters.
+int ref_process_shadow_casters_text(void* h, int numIn, const int* inIds, const float* mainCam12, const float* shadowCam12, float nearZ, float farZ,
+    int lightType, unsigned lightMask, const unsigned* shadowMask, const float* shadowDistance, const float* drawDistanceArr,
+    const unsigned char* inView, int* outIds)
+{
+    auto* r = reinterpret_cast<Ref*>(h);
+    Context* c = r->context_;
+    auto make = [&](const float* p, SharedPtr<Node>& node) -> Camera* {
+        node = new Node(c);
+        node->SetTransform(Vector3(p), Quaternion(p[3], p[4], p[5], p[6]));
+        Camera* cam = node->CreateComponent<Camera>();
+        cam->SetOrthographic(p[10] != 0.0f);
+        cam->SetFov(p[7]);
+        cam->SetNearClip(p[8]);
+        cam->SetFarClip(p[9]);
+        if (p[10] != 0.0f)
+            cam->SetOrthoSize(p[11]);
+        cam->SetAspectRatio(1.0f);
+        return cam;
+    };
+    SharedPtr<Node> mainNode, shadowNode;
+    Camera* cullCamera = make(mainCam12, mainNode);
+    Camera* shadowCamera = make(shadowCam12, shadowNode);
+    static unsigned frameNumber = 20000;
+    RefViewShim view;
+    view.cullCamera_ = cullCamera;
+    view.minZ_ = nearZ;
+    view.maxZ_ = farZ;
+    view.frame_.frameNumber_ = ++frameNumber;
+    view.frame_.camera_ = cullCamera;
+    RefLightShim light;
+    light.lightMask_ = lightMask;
+    light.lightType_ = (LightType)lightType;
+    RefLightQueryShim query;
+    query.light_ = &light;
+    for (int i = 0; i < MAX_LIGHT_SPLITS; ++i)
+    {
+        query.shadowCameras_[i] = shadowCamera;
+        query.shadowNearSplits_[i] = 0.0f;
+        query.shadowFarSplits_[i] = M_INFINITY;
+        query.shadowCasterEnd_[i] = 0;
+    }
+    PODVector<Drawable*> drawables;
+    for (int k = 0; k < numIn; ++k)
+    {
+        const int id = inIds[k];
+        TestDrawable* d = r->drawables_[id];
+        d->SetShadowMask(shadowMask[id]);
+        d->SetShadowDistance(shadowDistance[id]);
+        d->SetDrawDistance(drawDistanceArr[id]);
+        if (inView[id])
+        {
+            d->UpdateBatches(view.frame_);
+            d->MarkInView(view.frame_);
+        }
+        drawables.Push(d);
+    }
+    view.ProcessShadowCasters(query, drawables, 0);
+    const int n = (int)query.shadowCasters_.Size();
+    for (int i = 0; i < n; ++i)
+        outIds[i] = static_cast<TestDrawable*>(query.shadowCasters_[i])->id_;
     return n;
 }
 

@@ -75,6 +75,7 @@ class Ref:
         L.ref_shadow_split_setup.argtypes = [C.c_void_p, _f, _f, C.c_float, C.c_float, _f, _f, _f, _f, _f]
         L.ref_process_shadow_casters.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, _f, C.c_float, C.c_float, C.c_int, C.c_int, C.c_uint, _u32, _f, _f, _u8,
                                                  _f, _f, C.c_int, _i]
+        L.ref_process_shadow_casters_text.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, C.c_float, C.c_float, C.c_int, C.c_uint, _u32, _f, _f, _u8, _i]
         L.ref_run_view_serial.argtypes = [C.c_void_p, C.c_int, _i, _f, _f, C.c_void_p, C.c_uint, C.c_void_p, C.c_uint, C.c_uint, C.c_int, C.c_uint,
                                           C.c_uint, C.c_uint, _i, C.c_int, _i]
         L.ref_raycast.argtypes = [C.c_void_p, _f, C.c_uint, C.c_uint, C.c_int, _i, _f, _f, C.c_int]
@@ -315,6 +316,22 @@ class Ref:
                                                 _p(split["lvf_planes"], _f), split["lvf_max_z"], split["shadow_far"], int(split["shadow_ortho"]),
                                                 light_type, light_mask, _p(sm, _u32), _p(sd, _f), _p(dd, _f), _p(iv, _u8), _p(mv, _f), _p(mp, _f),
                                                 int(main_ortho), _p(out, _i))
+        return out[:n].copy()
+
+    def process_shadow_casters_text(self, ids, main_cam, shadow_cam, near_z, far_z, light_type, light_mask, shadow_mask, shadow_distance,
+                                    draw_distance, in_view):
+        """View::ProcessShadowCasters compiled from the reference's own text (View.cpp:2379-2453 + IsShadowCasterVisible) for one split, with real
+        cull / shadow Cameras built from the 12-float descriptions of shadow_split_setup.  Returns the shadow casters in order."""
+        ids = np.ascontiguousarray(ids, np.int32)
+        out = np.zeros(max(len(ids), 1), np.int32)
+        m = np.ascontiguousarray(main_cam, np.float32)
+        sh = np.ascontiguousarray(shadow_cam, np.float32)
+        sm = np.ascontiguousarray(shadow_mask, np.uint32)
+        sd = np.ascontiguousarray(shadow_distance, np.float32)
+        dd = np.ascontiguousarray(draw_distance, np.float32)
+        iv = np.ascontiguousarray(in_view, np.uint8)
+        n = self.lib.ref_process_shadow_casters_text(self.h, len(ids), _p(ids, _i), _p(m, _f), _p(sh, _f), near_z, far_z, light_type, light_mask,
+                                                     _p(sm, _u32), _p(sd, _f), _p(dd, _f), _p(iv, _u8), _p(out, _i))
         return out[:n].copy()
 
     def run_view_serial(self, scene, sorted_occluders, max_triangles, flags=0xFF, view_mask=0xFFFFFFFF):

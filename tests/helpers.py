@@ -116,5 +116,6 @@ def shadow_scenarios(ref, extent, count, seed=5, shared_main=False):
         split = ref.shadow_split_setup(main_cam, shadow_cam, near_z, far_z)
         if split["degenerate"]:
             continue
-        out.append(dict(split=split, light_type=kind, main_view=mv.view.reshape(-1).copy(), main_pos=np.array(mpos, np.float32), view=mv))
+        out.append(dict(split=split, light_type=kind, main_view=mv.view.reshape(-1).copy(), main_pos=np.array(mpos, np.float32), view=mv,
+                        main_cam=main_cam, shadow_cam=shadow_cam, near_z=near_z, far_z=far_z))
     return out

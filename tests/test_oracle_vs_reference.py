@@ -332,8 +332,9 @@ def test_zone_occluder_query_matches_reference():
 
 
 def test_process_shadow_casters_matches_reference():
-    """View::ProcessShadowCasters' per-drawable filter + IsShadowCasterVisible (View.cpp:2409-2489): the oracle against the harness's restatement on
-    the reference's BoundingBox::Transformed / Frustum::IsInsideFast / Ray / Vector3 code, for directional (orthographic extrusion), spot and point
+    """View::ProcessShadowCasters' per-drawable filter + IsShadowCasterVisible (View.cpp:2379-2489): the oracle == the harness's loop on the
+    reference's BoundingBox::Transformed / Frustum::IsInsideFast code (with IsShadowCasterVisible compiled from the reference's text) == the
+    whole of View::ProcessShadowCasters compiled from the reference's text over real cameras and drawables, for directional (orthographic extrusion), spot and point
     (perspective extrusion, in-view shortcut, cube-face frustum test) splits, with shadow masks, shadow / draw distances and cast-shadow flags."""
     sc = helpers.small_scene(n=8000, k=8, extent=100.0, seed=71)
     rs = np.random.RandomState(9)
@@ -350,6 +351,10 @@ def test_process_shadow_casters_matches_reference():
         for light_mask in (0xFFFFFFFF, 0x1):
             want = ref.process_shadow_casters(ids_all, s["split"], s["light_type"], light_mask, shadow_mask, shadow_dist, draw_dist, in_view,
                                               s["main_view"], s["main_pos"])
+            # the reference's own lines for the whole function (split frustum included), real cameras and drawables
+            text = ref.process_shadow_casters_text(ids_all, s["main_cam"], s["shadow_cam"], s["near_z"], s["far_z"], s["light_type"], light_mask,
+                                                   shadow_mask, shadow_dist, draw_dist, in_view)
+            assert np.array_equal(text, want), (s["light_type"], light_mask, len(text), len(want))
             got = oraclebind.process_shadow_casters(ids_all, sc.aabb, sc.cast_shadows, s["split"], s["light_type"], light_mask, shadow_mask,
                                                     shadow_dist, draw_dist, in_view, s["main_view"], s["main_pos"])
             assert np.array_equal(want, got), (s["light_type"], light_mask)
