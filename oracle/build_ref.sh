@@ -30,11 +30,13 @@ done
 # Two member functions of View that depend only on classes compiled here are also taken from the reference's own text and compiled as
 # members of a stand-in class (ref_harness.cpp: RefViewShim, `#define View RefViewShim` around the include): View::UpdateOccluders
 # (View.cpp:2171-2229; touches renderer_->GetOccluderSizeThreshold() and frame_) and View::IsShadowCasterVisible (View.cpp:2455-2489;
-# touches frame_), View::ProcessShadowCasters (View.cpp:2379-2453; its Light and LightQueryResult are stand-ins with the members it reads), and
+# touches frame_), View::DrawOccluders (View.cpp:2231-2275; maxOccluderTriangles_, activeOccluders_), View::ProcessShadowCasters (View.cpp:2379-2453; its Light and LightQueryResult are stand-ins with the members it reads), and
 # the free function CheckVisibilityWork (View.cpp:160-227; reads occlusionBuffer_, cullCamera_, cameraZoneOverride_,
 # sceneResults_, frame_ and calls FindZone through its View pointer).
 awk '/^void View::UpdateOccluders\(/{on=1} /^void View::DrawOccluders\(/{on=0} on' "$VIEWCPP" > "$OUT/view_update_occluders.inc"
 awk '/^bool View::IsShadowCasterVisible\(/{on=1} /^IntRect View::GetShadowMapViewport\(/{on=0} on' "$VIEWCPP" > "$OUT/view_shadow_caster_visible.inc"
+awk '/^void View::DrawOccluders\(/{on=1} /^void View::ProcessLight\(/{on=0} on' "$VIEWCPP" > "$OUT/view_draw_occluders.inc"
+grep -q "bool success = occluder->DrawOcclusion(buffer)" "$OUT/view_draw_occluders.inc" || { echo "could not extract View::DrawOccluders from $VIEWCPP"; exit 1; }
 awk '/^void View::ProcessShadowCasters\(/{on=1} /^bool View::IsShadowCasterVisible\(/{on=0} on' "$VIEWCPP" > "$OUT/view_process_shadow_casters.inc"
 grep -q "query.shadowCasters_.Push(drawable)" "$OUT/view_process_shadow_casters.inc" || { echo "could not extract View::ProcessShadowCasters from $VIEWCPP"; exit 1; }
 awk '/^void CheckVisibilityWork\(/{on=1} /^void ProcessLightWork\(/{on=0} on' "$VIEWCPP" > "$OUT/view_check_visibility_work.inc"

@@ -11,7 +11,8 @@
 //     View.cpp:58-157), extracted by the build recipe into a generated include and compiled here,
 //   * the reference's OWN text of View::UpdateOccluders (View.cpp:2171-2229) and View::IsShadowCasterVisible (View.cpp:2455-2489), extracted
 //     the same way and compiled as members of a stand-in class that holds the two View members they touch (renderer_, frame_), and of the
-//     free function CheckVisibilityWork (View.cpp:160-227) with that stand-in as the View it works for, and View::ProcessShadowCasters
+//     free function CheckVisibilityWork (View.cpp:160-227) with that stand-in as the View it works for, View::DrawOccluders (View.cpp:2231-2275:
+//     budget, IsVisible gating, activeOccluders_) over Drawables whose DrawOcclusion submits the test mesh, and View::ProcessShadowCasters
 //     (View.cpp:2379-2453) with stand-ins for the Light and the LightQueryResult it reads,
 //   * the CheckVisibilityWork occlusion predicate (View.cpp:177), split over the WorkQueue the way
 //     View.cpp:897-920 does when worker threads exist.
@@ -105,6 +106,9 @@ public:
     float minZ_{};
     float maxZ_{};
     void UpdateOccluders(PODVector<Drawable*>& occluders, Camera* camera);
+    void DrawOccluders(OcclusionBuffer* buffer, const PODVector<Drawable*>& occluders);
+    int maxOccluderTriangles_{};
+    unsigned activeOccluders_{};
     bool IsShadowCasterVisible(Drawable* drawable, BoundingBox lightViewBox, Camera* shadowCamera, const Matrix3x4& lightView,
         const Frustum& lightViewFrustum, const BoundingBox& lightViewFrustumBox);
     /// Never reached: the harness runs CheckVisibilityWork with cameraZoneOverride_ set (zones are outside this path).
@@ -120,6 +124,7 @@ public:
 
 #define View RefViewShim
 #include "view_update_occluders.inc"
+#include "view_draw_occluders.inc"
 #include "view_shadow_caster_visible.inc"
 #include "view_check_visibility_work.inc"
 #define Light RefLightShim
@@ -161,9 +166,51 @@ public:
     void OnWorldBoundingBoxUpdate() override { worldBoundingBox_ = fixedWorldBox_; }
     unsigned GetNumOccluderTriangles() override { return numOccluderTriangles_; }
 
+    /// The calls StaticModel::DrawOcclusion makes per geometry (StaticModel.cpp:189-228): the material's cull mode, then the indexed triangles.
+    void SetOcclusionMesh(const Matrix3x4& model, const void* vtx, unsigned vtxSize, const void* idx, unsigned idxSize, unsigned idxCount, CullMode cull)
+    {
+        occModel_ = model; occVtx_ = vtx; occVtxSize_ = vtxSize; occIdx_ = idx; occIdxSize_ = idxSize; occIdxCount_ = idxCount; occCull_ = cull;
+    }
+    bool DrawOcclusion(OcclusionBuffer* buffer) override
+    {
+        buffer->SetCullMode(occCull_);
+        return buffer->AddTriangles(occModel_, occVtx_, occVtxSize_, occIdx_, occIdxSize_, 0, occIdxCount_);
+    }
+
     BoundingBox fixedWorldBox_;
     int id_{};
     unsigned numOccluderTriangles_{};
+    Matrix3x4 occModel_;
+    const void* occVtx_{};
+    const void* occIdx_{};
+    unsigned occVtxSize_{}, occIdxSize_{}, occIdxCount_{};
+    CullMode occCull_{CULL_CCW};
+};
+
+/// Occluder Drawables for View::DrawOccluders (the reference's text, RefViewShim): one per selected table entry, in order.
+struct OccluderSet
+{
+    std::vector<SharedPtr<Node> > nodes_;
+    PODVector<Drawable*> list_;
+    OccluderSet(Context* c, int numSelected, const int* selected, const float* occAabb6, const float* occModel12, const void* vtx, unsigned vtxSize,
+        const void* idx, unsigned idxSize, unsigned idxCount, int cullMode)
+    {
+        for (int i = 0; i < numSelected; ++i)
+        {
+            SharedPtr<Node> node(new Node(c));
+            auto* d = node->CreateComponent<TestDrawable>();
+            BoundingBox box;
+            if (occAabb6)
+            {
+                const float* b = occAabb6 + 6 * (size_t)selected[i];
+                box = BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]));
+            }
+            d->Setup(box, DRAWABLE_GEOMETRY, DEFAULT_VIEWMASK, true, false, selected[i]);
+            d->SetOcclusionMesh(Matrix3x4(occModel12 + 12 * (size_t)selected[i]), vtx, vtxSize, idx, idxSize, idxCount, (CullMode)cullMode);
+            nodes_.push_back(node);
+            list_.Push(d);
+        }
+    }
 };
 
 struct Ref
@@ -896,7 +943,7 @@ int ref_select_occluders_text(void* h, int numOccluders, const float* occAabb6, 
     return n;
 }
 
-/// View::DrawOccluders, threaded branch (View.cpp:2233-2234, 2258-2273), over an already sorted occluder list, then the query and the
+/// View::DrawOccluders (the reference's own text, View.cpp:2231-2275; threaded branch), over an already sorted occluder list, then the query and the
 /// visibility predicate as ref_run_view.  outCounts4 = submitted triangles, query result size, visible, activeOccluders_.
 int ref_run_view_selected(void* h, int numSelected, const int* selected, const float* occModel12, const void* vtx, unsigned vtxSize, const void* idx,
     unsigned idxSize, unsigned idxCount, int cullMode, unsigned maxTriangles, unsigned flags, unsigned viewMask, int* outVisible, int cap, int* outCounts4)
@@ -905,20 +952,25 @@ int ref_run_view_selected(void* h, int numSelected, const int* selected, const f
     OcclusionBuffer* ob = r->buffer_;
     if (!r->rawFrustum_)
         ob->SetView(r->camera_);
-    ob->SetMaxTriangles(maxTriangles);
-    ob->Clear();
-    unsigned submitted = 0, active = 0;
-    for (int i = 0; i < numSelected; ++i)
+    // View::DrawOccluders, the reference's own text, threaded branch.  IsThreaded() is "more than one work buffer" (OcclusionBuffer.h), which
+    // SetSize(.., threaded) only allocates when the WorkQueue has worker threads; a harness without workers gets the same layout by adding the
+    // second work buffer the way SetSize does (OB.cpp:83-92): the queued batches then run on the calling thread and MergeBuffers folds them.
+    const bool single = ob->buffers_.Size() == 1;
+    if (single)
     {
-        ++active;
-        ob->SetCullMode((CullMode)cullMode);
-        bool success = ob->AddTriangles(Matrix3x4(occModel12 + 12 * (size_t)selected[i]), vtx, vtxSize, idx, idxSize, 0, idxCount);
-        submitted += idxCount / 3;
-        if (!success)
-            break;
+        ob->buffers_.Resize(2);
+        OcclusionBufferData& extra = ob->buffers_[1];
+        extra.dataWithSafety_ = new int[ob->width_ * (ob->height_ + 2) + 2];
+        extra.data_ = extra.dataWithSafety_.Get() + ob->width_ + 1;
+        extra.used_ = false;
     }
-    ob->DrawTriangles();
-    ob->BuildDepthHierarchy();
+    OccluderSet occ(r->context_, numSelected, selected, nullptr, occModel12, vtx, vtxSize, idx, idxSize, idxCount, cullMode);
+    RefViewShim view;
+    view.maxOccluderTriangles_ = (int)maxTriangles;
+    view.DrawOccluders(ob, occ.list_);
+    if (single)
+        ob->buffers_.Resize(1);
+    const unsigned active = view.activeOccluders_, submitted = active * (idxCount / 3);
     const Frustum& fr = r->QueryFrustum();
     OccludedQuery q(r->result_, fr, ob, (unsigned char)flags, viewMask);
     r->octree_->GetDrawables(q);
@@ -1123,7 +1175,7 @@ int ref_process_shadow_casters_text(void* h, int numIn, const int* inIds, const 
     return n;
 }
 
-/// View::DrawOccluders, NON-threaded branch (View.cpp:2233-2256, 2272-2273) with the reference's own OcclusionBuffer (created non-threaded by
+/// View::DrawOccluders (the reference's own text, View.cpp:2231-2275; NON-threaded branch) with the reference's own OcclusionBuffer (created non-threaded by
 /// ref_ob_set_size(.., threaded = 0)) over an already sorted occluder list, then the query and the visibility predicate as ref_run_view.
 /// outCounts4 = numTriangles_, query result size, visible, activeOccluders_.
 int ref_run_view_serial(void* h, int numSelected, const int* selected, const float* occAabb6, const float* occModel12, const void* vtx, unsigned vtxSize,
@@ -1136,25 +1188,12 @@ int ref_run_view_serial(void* h, int numSelected, const int* selected, const flo
         return -1;
     if (!r->rawFrustum_)
         buffer->SetView(r->camera_);
-    buffer->SetMaxTriangles(maxTriangles);
-    buffer->Clear();
-    unsigned active = 0;
-    for (int i = 0; i < numSelected; ++i)
-    {
-        const float* b = occAabb6 + 6 * (size_t)selected[i];
-        if (i > 0)
-        {
-            if (!buffer->IsVisible(BoundingBox(Vector3(b[0], b[1], b[2]), Vector3(b[3], b[4], b[5]))))
-                continue;
-        }
-        ++active;
-        buffer->SetCullMode((CullMode)cullMode);
-        bool success = buffer->AddTriangles(Matrix3x4(occModel12 + 12 * (size_t)selected[i]), vtx, vtxSize, idx, idxSize, 0, idxCount);
-        buffer->DrawTriangles();
-        if (!success)
-            break;
-    }
-    buffer->BuildDepthHierarchy();
+    // View::DrawOccluders, the reference's own text (non-threaded branch: IsVisible-gated, one occluder at a time)
+    OccluderSet occ(r->context_, numSelected, selected, occAabb6, occModel12, vtx, vtxSize, idx, idxSize, idxCount, cullMode);
+    RefViewShim view;
+    view.maxOccluderTriangles_ = (int)maxTriangles;
+    view.DrawOccluders(buffer, occ.list_);
+    const unsigned active = view.activeOccluders_;
     const Frustum& fr = r->QueryFrustum();
     OccludedQuery q(r->result_, fr, buffer, (unsigned char)flags, viewMask);
     r->octree_->GetDrawables(q);
