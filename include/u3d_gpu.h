@@ -91,6 +91,8 @@ typedef struct u3d_view
 } u3d_view;
 
 U3D_API const char* u3d_last_error(void);
+/* Version of this header; u3d_abi_version() returns the library's.  2 = round 2: u3d_batch_set_scene added, U3D_NUM_PHASES 8 -> 10. */
+#define U3D_ABI_VERSION 2
 U3D_API int u3d_abi_version(void);
 /* Test hook / tuning.  "force_irregular" = 1 routes every set-up triangle of the batched path through the general (global-memory) fill.
    "blocking_wait" = 1 makes u3d_batch_cull_views wait on a blocking event instead of spinning in cudaStreamSynchronize: for hosts that run

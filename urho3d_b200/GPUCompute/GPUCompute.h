@@ -44,7 +44,12 @@ inline void Check(int rc, const char* what)
 class GpuContext
 {
 public:
-    explicit GpuContext(int device = 0) { Check(u3d_ctx_create(device, &ctx_), "u3d_ctx_create"); }
+    explicit GpuContext(int device = 0)
+    {
+        if (u3d_abi_version() != U3D_ABI_VERSION)
+            throw std::runtime_error("libu3dgpu.so was built from another version of u3d_gpu.h: rebuild it");
+        Check(u3d_ctx_create(device, &ctx_), "u3d_ctx_create");
+    }
     ~GpuContext() { u3d_ctx_destroy(ctx_); }
     GpuContext(const GpuContext&) = delete;
     GpuContext& operator=(const GpuContext&) = delete;

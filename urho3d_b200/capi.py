@@ -148,6 +148,9 @@ class U3DError(RuntimeError):
         self.code = code
 
 
+ABI_VERSION = 2  # include/u3d_gpu.h: U3D_ABI_VERSION
+
+
 def lib():
     """Load libu3dgpu.so.  Fails loudly when the CUDA extension has not been built: there is no other implementation."""
     global _lib
@@ -160,6 +163,9 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
+        if L.u3d_abi_version() != ABI_VERSION:
+            raise RuntimeError("libu3dgpu.so reports ABI version %d, this binding was written for %d: rebuild it (make -C urho3d_b200/csrc)"
+                               % (L.u3d_abi_version(), ABI_VERSION))
         _lib = L
     return _lib
 

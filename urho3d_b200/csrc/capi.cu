@@ -488,7 +488,7 @@ extern "C"
 {
 
 const char* u3d_last_error(void) { return g_err.c_str(); }
-int u3d_abi_version(void) { return 1; }
+int u3d_abi_version(void) { return U3D_ABI_VERSION; }
 
 int u3d_debug_set_option(const char* name, int value)
 {
